@@ -1,0 +1,307 @@
+#!/usr/bin/env python3
+"""Generate the golden vectors in this directory by running the UNMODIFIED reference.
+
+Run it only where the reference checkout is mounted (the build container):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py [/root/reference]
+
+The reference package is imported as-is from that path.  Two things it needs are not
+installed offline and are injected through ``sys.modules`` before the import:
+
+* ``gonzag.ncio`` (netCDF4 readers) -> an in-memory stand-in exposing `GetModel2DVar` and
+  `GetSatSSH`, so that `Model2SatTrack` (gonzag/mod2sat.py:20) runs without files;
+* ``shapely.geometry`` -> a planar strict-interior point-in-polygon stand-in (only the
+  heavy-duty quadrant branch, gonzag/bilin_mapping.py:415-426, reaches it).  That branch
+  is therefore "parity unpinned" (see oracle/gz_oracle.py header).
+
+Inputs are stored in the fixtures next to the outputs (fp32-born coordinates are stored
+as float32, which is lossless) so the fixtures do not depend on the generator staying
+bit-stable across machines.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from gonzag_b200 import synthetic as syn          # noqa: E402
+from oracle.gz_oracle import point_strictly_in_quad  # noqa: E402  (shapely stand-in only)
+
+
+# ----------------------------------------------------------------- reference loading
+def load_reference(ref_root):
+    shp = types.ModuleType("shapely")
+    geo = types.ModuleType("shapely.geometry")
+    pol = types.ModuleType("shapely.geometry.polygon")
+
+    class Point:
+        def __init__(self, a, b):
+            self.a, self.b = a, b
+
+    class Polygon:
+        def __init__(self, pts):
+            self.qa = tuple(p[0] for p in pts)
+            self.qb = tuple(p[1] for p in pts)
+
+        def contains(self, p):
+            return point_strictly_in_quad(p.a, p.b, self.qa, self.qb)
+
+    geo.Point = Point
+    pol.Polygon = Polygon
+    geo.polygon = pol
+    shp.geometry = geo
+    sys.modules["shapely"] = shp
+    sys.modules["shapely.geometry"] = geo
+    sys.modules["shapely.geometry.polygon"] = pol
+
+    sys.path.insert(0, ref_root)
+    import gonzag  # noqa
+    store = {"fields": {}, "sat": {}}
+    nc = types.ModuleType("gonzag.ncio")
+    nc.GetModel2DVar = lambda f, v, kt=0: store["fields"][f][kt].copy()   # a file read returns a fresh array
+    nc.GetSatSSH = lambda f, v, kt1=0, kt2=0, ikeep=[]: store["sat"][f]
+    sys.modules["gonzag.ncio"] = nc
+    gonzag.ncio = nc
+    return gonzag, store
+
+
+@contextlib.contextmanager
+def quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def run_model2sat(gz, store, lat, lon, mask, angle, kew, tmod, field, tsat, ysat, xsat, ssat, res):
+    store["fields"]["mod"] = field
+    store["sat"]["sat"] = ssat
+    MG = types.SimpleNamespace(shape=lat.shape, HResDeg=res, lat=lat, lon=lon, xangle=angle,
+                               EWPer=kew, time=tmod, file="mod", mask=mask)
+    ST = types.SimpleNamespace(size=len(tsat), lat=ysat, lon=xsat, time=tsat, file="sat",
+                               jt1=0, jt2=0, keepit=[])
+    with quiet():
+        R = gz.Model2SatTrack(MG, "ssh", ST, "ssh")
+    return R
+
+
+def pack_masked(prefix, arr, out):
+    out[prefix + "_data"] = np.ma.getdata(arr)
+    out[prefix + "_mask"] = np.ma.getmaskarray(arr)
+
+
+# ----------------------------------------------------------------- cases
+def sat_ssh(n, seed):
+    rng = np.random.default_rng(seed)
+    s = rng.normal(0.0, 0.3, n)
+    s[rng.uniform(size=n) < 0.03] = -9999.0
+    return s
+
+
+def case_global(gz, store):
+    """C1-shaped global periodic grid, -D angle, land mask, SARAL-like track (2 orbits)."""
+    lat, lon = syn.orca_like_grid(292, 362)
+    mask = syn.land_mask(lat, lon)
+    with quiet():
+        angle = gz.GridAngle(lat, lon)
+    res = float(gz.GridResolution(lon))
+    t, y, x = syn.orbit_track(12070, t0=1000.0, **syn.SARAL)
+    tmod = 7000.0 * np.arange(3)
+    f32 = syn.ssh_records(lat, lon, 3, dtype=np.float32)
+    f64 = f32.astype(np.float64) + lat[None] * 2.0 ** -20
+    ssat = sat_ssh(len(t), 11)
+    out = dict(lat=lat.astype(np.float32), lon=lon.astype(np.float32), mask=mask.astype(np.int8),
+               angle=angle, res=res, kew=2, tmod=tmod, f32=f32, tsat=t, ysat=y, xsat=x, ssat=ssat)
+    for tag, fld in (("f32", f32), ("f64", f64)):
+        R = run_model2sat(gz, store, lat, lon, mask, angle, 2, tmod, fld, t, y, x, ssat.copy(), res)
+        pack_masked("ssh_np_" + tag, R.ssh_mod_np, out)
+        pack_masked("ssh_bl_" + tag, R.ssh_mod, out)
+        out["imask_" + tag] = R.mask
+    pack_masked("ssh_sat", R.ssh_sat, out)
+    out["distance"] = R.distance
+    pack_masked("xnp", R.XNPtrack, out)
+    with quiet():
+        BT = gz.BilinTrack(y, x, lat, lon, src_grid_local_angle=angle, k_ew_per=2,
+                           rd_found_km=0.75 * res * 111.11, np_box_r=int(0.5 * 500. / (res * 111.11)))
+    out.update(NP=BT.NP, SM=BT.SM, WB=BT.WB)
+    # same track without -D and without periodicity knowledge
+    with quiet():
+        BT0 = gz.BilinTrack(y, x, lat, lon, k_ew_per=-1,
+                            rd_found_km=0.75 * res * 111.11, np_box_r=int(0.5 * 500. / (res * 111.11)))
+    out.update(NP_noper=BT0.NP, SM_noper=BT0.SM, WB_noper=BT0.WB)
+    return out
+
+
+def case_regional(gz, store):
+    """1/12-degree sheared regional box (r = 27), SARAL passes over it, bbox slightly larger
+    than the grid so some points are outside (-> not found)."""
+    lat, lon = syn.regional_grid(300, 360, lat0=-40.0, lon0=150.0, res_deg=1.0 / 12.0, shear=0.02)
+    mask = syn.land_mask(lat, lon, seed=5, level=0.9)
+    res = float(gz.GridResolution(lon))
+    t, y, x = syn.orbit_track(5 * 86400, t0=50.0, drop_land_seed=None,
+                              lat_bounds=(lat.min() - 0.4, lat.max() + 0.4),
+                              lon_bounds=(lon.min() - 0.4, lon.max() + 0.4), **syn.SARAL)
+    rd = 0.75 * res * 111.11
+    r = int(0.5 * 500. / (res * 111.11))
+    with quiet():
+        BT = gz.BilinTrack(y, x, lat, lon, k_ew_per=-1, rd_found_km=rd, np_box_r=r)
+    tmod = 2.6 * 86400.0 * np.arange(3)
+    f32 = syn.ssh_records(lat, lon, 3, dtype=np.float32)
+    ssat = sat_ssh(len(t), 12)
+    R = run_model2sat(gz, store, lat, lon, mask, np.zeros(lat.shape), -1, tmod, f32, t, y, x,
+                      ssat.copy(), res)
+    out = dict(lat=lat.astype(np.float32), lon=lon.astype(np.float32), mask=mask.astype(np.int8),
+               res=res, rd=rd, r=r, tmod=tmod, f32=f32, tsat=t, ysat=y, xsat=x, ssat=ssat,
+               NP=BT.NP, SM=BT.SM, WB=BT.WB, distance=R.distance, imask=R.mask)
+    pack_masked("ssh_np", R.ssh_mod_np, out)
+    pack_masked("ssh_bl", R.ssh_mod, out)
+    # shuffled targets: no continuity between consecutive points
+    perm = np.random.default_rng(4).permutation(len(y))[:400]
+    with quiet():
+        BTs = gz.BilinTrack(y[perm], x[perm], lat, lon, k_ew_per=-1, rd_found_km=rd, np_box_r=r)
+    out.update(perm=perm, NP_perm=BTs.NP, SM_perm=BTs.SM, WB_perm=BTs.WB)
+    return out
+
+
+def case_seam(gz, store):
+    """Tracks hugging the E-W seam and the grid edges of the C1-shaped global grid: long
+    chains where the box answer differs from the global answer."""
+    lat, lon = syn.orca_like_grid(292, 362)
+    res = float(gz.GridResolution(lon))
+    rd = 0.75 * res * 111.11
+    r = int(0.5 * 500. / (res * 111.11))
+    rng = np.random.default_rng(21)
+    n = 1500
+    s = np.linspace(0.0, 1.0, n)
+    # slow drift across the seam while moving north, then back south, then a polar leg
+    y = np.concatenate([-70.0 + 150.0 * s, 80.0 - 150.0 * s, 60.0 + 29.5 * s])
+    x = np.concatenate([357.0 + 5.0 * s, 2.5 - 5.5 * s, 200.0 + 170.0 * s])
+    y = y + rng.normal(0, 0.03, y.size)
+    x = np.mod(x + rng.normal(0, 0.03, x.size), 360.0)
+    with quiet():
+        angle = gz.GridAngle(lat, lon)
+        BT = gz.BilinTrack(y, x, lat, lon, src_grid_local_angle=angle, k_ew_per=2,
+                           rd_found_km=rd, np_box_r=r)
+        BTn = gz.BilinTrack(y, x, lat, lon, src_grid_local_angle=angle, k_ew_per=-1,
+                            rd_found_km=rd, np_box_r=r)
+    return dict(rd=rd, r=r, ysat=y, xsat=x, NP=BT.NP, SM=BT.SM, WB=BT.WB,
+                NP_noper=BTn.NP, SM_noper=BTn.SM, WB_noper=BTn.WB)
+
+
+def case_units(gz, store):
+    """Known-answer vectors for the scalar helpers."""
+    rng = np.random.default_rng(7)
+    out = {}
+    # Heading
+    n = 2000
+    a = np.stack([rng.uniform(-89, 89, n), rng.uniform(0, 360, n),
+                  rng.uniform(-89, 89, n), rng.uniform(0, 360, n)], 1)
+    a[:50, 2] = a[:50, 0] + rng.normal(0, 0.1, 50)       # nearby pairs
+    a[:50, 3] = np.mod(a[:50, 1] + rng.normal(0, 0.1, 50), 360.)
+    a[50:60, 3] = a[50:60, 1]                            # same meridian
+    a[60:70, 2] = a[60:70, 0]                            # same parallel
+    a[70, :] = [90.0, 10.0, 20.0, 30.0]                  # pole (epsilon clamp)
+    out["heading_in"] = a
+    out["heading_out"] = np.array([gz.Heading(*row) for row in a])
+    # degE_to_degWE
+    v = np.concatenate([rng.uniform(0, 360, 200), [0.0, 180.0, 360.0, 179.999, 180.001]])
+    out["pm180_in"] = v
+    out["pm180_out"] = np.array([gz.degE_to_degWE(float(q)) for q in v])
+    out["pm180_out_vec"] = gz.degE_to_degWE(v.copy())
+    # AlfaBeta on random quads
+    m = 3000
+    cy = rng.uniform(-80, 80, m)
+    cx = rng.uniform(0, 360, m)
+    vy = np.zeros((m, 5))
+    vx = np.zeros((m, 5))
+    h = rng.uniform(0.02, 1.0, m)
+    for k, (dy, dx) in enumerate([(-.5, -.5), (-.5, .5), (.5, .5), (.5, -.5)]):
+        vy[:, k + 1] = cy + h * (dy + rng.normal(0, 0.08, m))
+        vx[:, k + 1] = cx + h * (dx + rng.normal(0, 0.08, m))
+    vy[:, 0] = cy + h * rng.uniform(-.6, .6, m)
+    vx[:, 0] = cx + h * rng.uniform(-.6, .6, m)
+    vx[:300] = np.mod(vx[:300] - cx[:300, None], 360.)   # quads straddling Greenwich
+    vy[300:320, 1:] = vy[300:320, 1:2]                   # four equal latitudes
+    vx[320:330, 1:] = vx[320:330, 1:2]
+    vy[320:330, 1:] = vy[320:330, 1:2]                   # fully degenerate quad (det = 0)
+    ab = np.zeros((m, 2))
+    for q in range(m):
+        ab[q] = gz.AlfaBeta(vy[q].copy(), vx[q].copy())
+    out.update(ab_vy=vy, ab_vx=vx, ab_out=ab)
+    # Haversine
+    glat = rng.uniform(-80, 80, (20, 30))
+    glon = rng.uniform(0, 360, (20, 30))
+    out["hav_glat"], out["hav_glon"] = glat, glon
+    out["hav_pt"] = np.array([12.3, 321.0])
+    out["hav_out"] = gz.Haversine(np.float64(12.3), np.float64(321.0), glat, glon)
+    # NearestPoint quirks on a small regular grid
+    lon1 = np.arange(0.0, 72.0, 1.0)
+    lat1 = np.arange(-20.0, 21.0, 1.0)
+    X, Y = np.meshgrid(lon1, lat1)
+    out["np_Y"], out["np_X"] = Y, X
+    rd = 0.75 * 111.11
+    calls = []
+    res = []
+    for (yt, xt, jp, ip, rr) in [
+            (0.3, 30.4, 20, 30, 2), (0.3, 33.0, 20, 30, 2), (0.3, 30.4, 0, 30, 2),
+            (0.3, 30.4, 20, 0, 2), (0.3, 30.4, -1, -1, 2), (0.3, 30.4, None, None, 2),
+            (0.3, 30.4, 5, 5, 2), (21.0, 30.2, 38, 30, 2), (20.0 + 1.332 * 0.75, 30.0, 38, 30, 2),
+            (20.0 + 1.465 * 0.75, 30.0, 38, 30, 2), (20.0 + 1.2 * 0.75, 30.0, None, None, 2),
+            (-20.4, 0.2, 2, 2, 2), (0.5, 30.5, 20, 30, 2), (0.0, 30.5, 20, 30, 2),
+            (0.3, 71.4, 20, 69, 3), (0.3, 359.8, 20, 69, 3), (5.2, 10.7, 25, 12, 0)]:
+        with quiet():
+            got = gz.NearestPoint((yt, xt), Y, X, rd_found_km=rd, j_prv=jp, i_prv=ip, np_box_r=rr)
+        calls.append([yt, xt, -99 if jp is None else jp, -99 if ip is None else ip, rr])
+        res.append(got)
+    out["np_calls"] = np.array(calls)
+    out["np_out"] = np.array(res, dtype=np.int64)
+    out["np_rd"] = rd
+    # GridAngle on a small rotated grid
+    glat, glon = syn.orca_like_grid(60, 82, pole_shift_deg=25.0)
+    with quiet():
+        out["ga_out"] = gz.GridAngle(glat, glon)
+    out["ga_lat"], out["ga_lon"] = glat, glon
+    # Haversine_sclr / RadiusEarth
+    pr = np.stack([rng.uniform(-89, 89, 300), rng.uniform(0, 360, 300)], 1)
+    pr2 = pr + rng.normal(0, 0.1, pr.shape)
+    out["hs_in"] = np.concatenate([pr, pr2], 1)
+    out["hs_out"] = np.array([gz.Haversine_sclr(a0, a1, b0, b1) for a0, a1, b0, b1 in out["hs_in"]])
+    out["re_out"] = np.array([gz.RadiusEarth(a0) for a0 in pr[:, 0]])
+    # IDSourceMesh / WeightBL single calls incl. forced heavy-duty (angle > 45) and a target
+    # exactly due north of its nearest point (light test fails -> heavy-duty)
+    sm_calls, sm_out, wb_out = [], [], []
+    for (yt, xt, jP, iP, kew, ang) in [
+            (0.3, 30.4, 20, 30, -1, 0.0), (0.3, 30.4, 20, 30, -1, 60.0), (0.4, 30.0, 20, 30, -1, 0.0),
+            (-0.3, 29.6, 20, 30, -1, -50.0), (0.3, 29.6, 20, 30, 2, 0.0), (-0.2, 71.3, 20, 71, 2, 0.0),
+            (0.2, 0.3, 20, 0, 2, 0.0), (0.0, 30.4, 20, 30, -1, 0.0)]:
+        with quiet():
+            sm = gz.IDSourceMesh((yt, xt), Y, X, jP, iP, k_ew_per=kew, grid_s_angle=ang)
+            wb = gz.WeightBL((yt, xt), Y, X, sm)
+        sm_calls.append([yt, xt, jP, iP, kew, ang])
+        sm_out.append(sm)
+        wb_out.append(wb)
+    out["sm_calls"] = np.array(sm_calls)
+    out["sm_out"] = np.array(sm_out)
+    out["wb_out"] = np.array(wb_out)
+    return out
+
+
+def main():
+    ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+    gz, store = load_reference(ref_root)
+    for name, fn in (("units", case_units), ("global", case_global), ("regional", case_regional),
+                     ("seam", case_seam)):
+        data = fn(gz, store)
+        path = os.path.join(HERE, "golden_%s.npz" % name)
+        np.savez_compressed(path, **data)
+        print("%-9s -> %s  (%.2f MB)" % (name, os.path.basename(path), os.path.getsize(path) / 1e6))
+
+
+if __name__ == "__main__":
+    main()
