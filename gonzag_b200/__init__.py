@@ -1,0 +1,13 @@
+"""gonzag_b200: the gridded -> along-track mapping + interpolation path of brodeau/gonzag,
+rebuilt for NVIDIA B200 (sm_100a).  Same Python surface as `gonzag.bilin_mapping` and
+`gonzag.mod2sat`; the work is done by hand-written CUDA kernels behind a C ABI
+(include/gonzag_b200.h, gonzag_b200/libgonzag_b200.so).  No CPU fallback."""
+from .config import *                                   # noqa: F401,F403
+from ._lib import GonzagB200Error, device_count        # noqa: F401
+from .context import GridContext                        # noqa: F401
+from .bilin_mapping import BilinTrack                   # noqa: F401
+from .mod2sat import Model2SatTrack                     # noqa: F401
+from .utils import GridAngle, SearchBoxSize, degE_to_degWE   # noqa: F401
+
+__all__ = ["BilinTrack", "Model2SatTrack", "GridContext", "GridAngle", "SearchBoxSize",
+           "degE_to_degWE", "GonzagB200Error", "device_count"]

@@ -1,0 +1,199 @@
+// Shared declarations of libgonzag_b200: context layout, error plumbing and the device
+// math helpers that restate the reference's scalar formulas.  The whole library is compiled
+// with -fmad=false so that every a*b+c below rounds twice, like NumPy / CPython do.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gonzag_b200.h"
+
+#define GZB_PI 3.141592653589793      // == math.pi
+#define GZB_D2R (GZB_PI / 180.0)      // CPython's radians() multiplies by this constant
+#define GZB_MAXLEV 12
+#define GZB_TILE_J 4
+#define GZB_TILE_I 8
+
+// ------------------------------------------------------------------ bounding-sphere pyramid
+// Level 0 nodes are leaf tiles of GZB_TILE_J x GZB_TILE_I cells; a level-l node (l >= 1) covers
+// bj x bi nodes of level l-1.  Nodes of a level are stored "parent-blocked": the (up to) 32
+// children of a parent are contiguous (one warp loads them with one coalesced request), at
+// index parent_rowmajor_id*32 + slot.  The top level has <= 32 nodes and is stored row-major.
+struct GzbLevel {
+    double4* nodes;   // (cx, cy, cz, chord radius); radius < 0 marks an empty slot
+    int nJ, nI;       // logical node counts
+    int bj, bi;       // branching of THIS level's nodes over their children
+    int sJ, sI;       // cells covered by one node in j and i
+};
+
+struct GzbGrid {
+    int64_t Nj, Ni;
+    int kew;
+    const double* lat;
+    const double* lon;
+    const double* angle;    // may be null
+    const int8_t* mask;     // may be null
+    const double* cells;    // per leaf tile: x[32] y[32] z[32] (unit vectors), tile row-major
+    int nlev;
+    GzbLevel lev[GZB_MAXLEV];
+};
+
+struct GzbArena {
+    char* base = nullptr;
+    size_t cap = 0;
+    size_t off = 0;
+};
+
+struct gzb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    GzbGrid g;
+    double* d_lat = nullptr;
+    double* d_lon = nullptr;
+    double* d_angle = nullptr;
+    int8_t* d_mask = nullptr;
+    double* d_cells = nullptr;
+    double4* d_nodes[GZB_MAXLEV] = {};
+    GzbArena arena;
+    void* pinned = nullptr;          // small pinned scratch for status words
+    size_t pinned_cap = 0;
+    void* stage[2] = {nullptr, nullptr};   // pinned staging for pageable field slabs
+    size_t stage_cap = 0;
+    // corner-box bounding sphere cache (predecessor == (-1,-1)), keyed by np_box_r
+    int corner_r = -1;
+    double corner[4] = {0, 0, 0, -1};
+    gzb_stats stats;
+    char err[512];
+};
+
+// ------------------------------------------------------------------ host-side error plumbing
+void gzb_set_global_error(const char* msg);
+int gzb_fail(gzb_ctx* ctx, int code, const char* fmt, ...);
+
+#define GZB_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return gzb_fail((ctx), GZB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,         \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                \
+    } while (0)
+
+#define GZB_LAUNCH_CHECK(ctx)                                                            \
+    do {                                                                                 \
+        (ctx)->stats.kernel_launches++;                                                  \
+        cudaError_t e__ = cudaGetLastError();                                            \
+        if (e__ != cudaSuccess)                                                          \
+            return gzb_fail((ctx), GZB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",     \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                \
+    } while (0)
+
+int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes);            // grow (contents lost), reset offset
+void* gzb_arena_take(gzb_ctx* ctx, size_t bytes);             // 256-byte aligned slice or null
+int gzb_use_device(gzb_ctx* ctx);
+
+static inline size_t gzb_align(size_t n) { return (n + 255) & ~size_t(255); }
+
+// ------------------------------------------------------------------ device math helpers
+#ifdef __CUDACC__
+
+// Python's float `%` (and numpy.remainder): result takes the sign of the divisor.
+__device__ __forceinline__ double gzb_pymod(double a, double b) {
+    double m = fmod(a, b);
+    if (m != 0.0) {
+        if ((b < 0.0) != (m < 0.0)) m += b;
+    } else {
+        m = copysign(0.0, b);
+    }
+    return m;
+}
+
+// gonzag/utils.py:24-33 (degE_to_degWE)
+__device__ __forceinline__ double gzb_pm180(double x) {
+    return copysign(1.0, 180.0 - x) * fmin(x, fabs(x - 360.0));
+}
+
+// gonzag/bilin_mapping.py:16-47 (Heading): loxodromic bearing a->b, degrees in [0,360)
+__device__ __forceinline__ double gzb_heading_dev(double lata, double lona, double latb, double lonb) {
+    const double xa = lona * GZB_D2R;
+    const double xb = lonb * GZB_D2R;
+    double ra = fmax(fabs(tan(GZB_PI / 4.0 - (lata * GZB_D2R) / 2.0)), 1.0e-9);
+    double ya = -log(ra);
+    double rb = fmax(fabs(tan(GZB_PI / 4.0 - (latb * GZB_D2R) / 2.0)), 1.0e-9);
+    double yb = -log(rb);
+    double d = gzb_pymod(xb - xa, 2.0 * GZB_PI);
+    if (d >= GZB_PI) d = d - 2.0 * GZB_PI;
+    if (d <= -GZB_PI) d = d + 2.0 * GZB_PI;
+    double ang = atan2(d, yb - ya);
+    return gzb_pymod(ang * 180.0 / GZB_PI, 360.0);
+}
+
+// gonzag/utils.py:296-316 (Haversine), same operation order; cos_plat = cos(plat*to_rad)
+__device__ __forceinline__ double gzb_haversine_dev(double plat, double plon, double cos_plat,
+                                                    double glat, double glon) {
+    double a1 = sin(0.5 * ((glat - plat) * GZB_D2R));
+    double a2 = sin(0.5 * ((glon - plon) * GZB_D2R));
+    double a3 = cos(glat * GZB_D2R) * cos_plat;
+    return 2.0 * 6360.0 * asin(sqrt(a1 * a1 + a3 * a2 * a2));
+}
+
+// gonzag/bilin_mapping.py:50-141 (AlfaBeta).  y[0],x[0] = target, 1..4 = mesh corners.
+__device__ __forceinline__ void gzb_alfabeta_dev(const double* yin, const double* xin,
+                                                 double& alfa, double& beta) {
+    double y[5], x[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { y[k] = yin[k]; x[k] = xin[k]; }
+    const bool wrap = (fabs(x[1] - x[4]) >= 180.0) || (fabs(x[1] - x[2]) >= 180.0) ||
+                      (fabs(x[1] - x[3]) >= 180.0);
+    if (wrap) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) x[k] = gzb_pm180(x[k]);
+    }
+    double step = 1000.0, ex = 0.5, ey = 0.5, a = 0.0, b = 0.0;
+    int it = 0;
+    while ((step > 0.1) && (it < 100)) {
+        const double e12 = x[2] - x[1];
+        const double e41 = x[1] - x[4];
+        const double e23 = x[3] - x[2];
+        const double j00 = e12 + (e41 + e23) * b;
+        const double j01 = -e41 + (e41 + e23) * a;
+        const double j10 = y[2] - y[1] + (y[1] - y[4] + y[3] - y[2]) * b;
+        const double j11 = y[4] - y[1] + (y[1] - y[4] + y[3] - y[2]) * a;
+        const double det = j00 * j11 - j01 * j10;
+        if (det == 0.0) {
+            // the reference "gives up" with a no-op and spins to the iteration cap
+            it = 100;
+            break;
+        }
+        const double da = (ex * j11 - j01 * ey) / det;
+        const double db = (j00 * ey - ex * j10) / det;
+        step = sqrt(da * da + db * db);
+        a = a + da;
+        b = b + db;
+        const double ca = 1.0 - a;
+        const double cb = 1.0 - b;
+        ex = x[0] - (ca * cb * x[1] + a * cb * x[2] + a * b * x[3] + ca * b * x[4]);
+        ey = y[0] - (ca * cb * y[1] + a * cb * y[2] + a * b * y[3] + ca * b * y[4]);
+        it = it + 1;
+    }
+    if (it >= 100) { a = 0.5; b = 0.5; }
+    if (y[1] == y[2] && y[2] == y[3] && y[3] == y[4]) { a = 0.5; b = 0.5; }
+    alfa = a;
+    beta = b;
+}
+
+// warp-wide minimum of a non-negative double (or +inf): two REDUX on the hi/lo words
+__device__ __forceinline__ double gzb_warp_min_nonneg(double v) {
+    unsigned hi = (unsigned)__double2hiint(v);
+    unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    unsigned lo = (hi == mhi) ? (unsigned)__double2loint(v) : 0xffffffffu;
+    unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
+    return __hiloint2double((int)mhi, (int)mlo);
+}
+
+#endif  // __CUDACC__

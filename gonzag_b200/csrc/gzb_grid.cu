@@ -1,0 +1,554 @@
+// Context management, the bounding-sphere pyramid over the model grid, and K0 (grid angle).
+#include <stdarg.h>
+
+#include <new>
+
+#include "gzb_common.cuh"
+
+// ======================================================================== error plumbing
+static thread_local char g_global_err[512] = "";
+
+void gzb_set_global_error(const char* msg) {
+    strncpy(g_global_err, msg, sizeof(g_global_err) - 1);
+    g_global_err[sizeof(g_global_err) - 1] = 0;
+}
+
+int gzb_fail(gzb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        strncpy(ctx->err, buf, sizeof(ctx->err) - 1);
+        ctx->err[sizeof(ctx->err) - 1] = 0;
+    }
+    gzb_set_global_error(buf);
+    return code;
+}
+
+extern "C" const char* gzb_version(void) { return "gonzag_b200 0.1 (sm_100a)"; }
+extern "C" const char* gzb_last_global_error(void) { return g_global_err; }
+extern "C" const char* gzb_last_error(const gzb_ctx* ctx) { return ctx ? ctx->err : g_global_err; }
+
+extern "C" int gzb_device_count(int* n_out) {
+    if (!n_out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_device_count: null output");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *n_out = 0;
+        return gzb_fail(nullptr, GZB_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *n_out = n;
+    return GZB_OK;
+}
+
+int gzb_use_device(gzb_ctx* ctx) {
+    GZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return GZB_OK;
+}
+
+// ======================================================================== workspace arena
+int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes) {
+    ctx->arena.off = 0;
+    if (bytes <= ctx->arena.cap) return GZB_OK;
+    if (ctx->arena.base) {
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        GZB_CUDA(ctx, cudaFree(ctx->arena.base));
+        ctx->arena.base = nullptr;
+        ctx->arena.cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + (size_t(1) << 20);
+    cudaError_t e = cudaMalloc((void**)&ctx->arena.base, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gzb_fail(ctx, GZB_ERR_NOMEM, "workspace of %zu bytes: %s", want, cudaGetErrorString(e));
+    }
+    ctx->arena.cap = want;
+    return GZB_OK;
+}
+
+void* gzb_arena_take(gzb_ctx* ctx, size_t bytes) {
+    size_t n = gzb_align(bytes ? bytes : 1);
+    if (ctx->arena.off + n > ctx->arena.cap) return nullptr;
+    void* p = ctx->arena.base + ctx->arena.off;
+    ctx->arena.off += n;
+    return p;
+}
+
+// ======================================================================== pyramid build
+// One warp per leaf tile: unit vectors of its 32 cells + the tile's bounding sphere.
+__global__ void __launch_bounds__(256)
+k_build_leaves(GzbGrid g, double* __restrict__ cells, double4* __restrict__ nodes0, int top_is_leaf) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const GzbLevel L0 = g.lev[0];
+    const int64_t ntile = (int64_t)L0.nJ * L0.nI;
+    if (tile >= ntile) return;
+    const int tJ = (int)(tile / L0.nI), tI = (int)(tile % L0.nI);
+    const int64_t j = (int64_t)tJ * GZB_TILE_J + (lane >> 3);
+    const int64_t i = (int64_t)tI * GZB_TILE_I + (lane & 7);
+    const bool ok = (j < g.Nj) && (i < g.Ni);
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (ok) {
+        const double la = g.lat[j * g.Ni + i] * GZB_D2R;
+        const double lo = g.lon[j * g.Ni + i] * GZB_D2R;
+        const double cl = cos(la);
+        x = cl * cos(lo);
+        y = cl * sin(lo);
+        z = sin(la);
+    }
+    double* c = cells + tile * 96;
+    c[lane] = ok ? x : 1.0e3;
+    c[32 + lane] = ok ? y : 1.0e3;
+    c[64 + lane] = ok ? z : 1.0e3;
+    // centre = normalised mean of the valid cells
+    double sx = x, sy = y, sz = z;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    double nrm = sqrt(sx * sx + sy * sy + sz * sz);
+    if (!(nrm > 1.0e-6)) {   // degenerate mean: fall back to the first cell of the tile
+        sx = __shfl_sync(0xffffffffu, x, 0);
+        sy = __shfl_sync(0xffffffffu, y, 0);
+        sz = __shfl_sync(0xffffffffu, z, 0);
+        nrm = 1.0;
+    }
+    const double cx = sx / nrm, cy = sy / nrm, cz = sz / nrm;
+    double r = 0.0;
+    if (ok) {
+        const double dx = x - cx, dy = y - cy, dz = z - cz;
+        r = sqrt(dx * dx + dy * dy + dz * dz);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+    r = r * (1.0 + 1.0e-12) + 1.0e-15;
+    if (lane == 0) {
+        int64_t idx;
+        if (top_is_leaf) {
+            idx = tile;
+        } else {
+            const GzbLevel L1 = g.lev[1];
+            const int pJ = tJ / L1.bj, pI = tI / L1.bi;
+            idx = ((int64_t)pJ * L1.nI + pI) * 32 + (tJ % L1.bj) * L1.bi + (tI % L1.bi);
+        }
+        nodes0[idx] = make_double4(cx, cy, cz, r);
+    }
+}
+
+// One warp per node of level `l` (l >= 1): sphere around its (up to 32) children.
+__global__ void __launch_bounds__(256)
+k_build_level(GzbGrid g, int l, int is_top) {
+    const int lane = threadIdx.x & 31;
+    const int64_t node = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const GzbLevel L = g.lev[l];
+    const int64_t nn = (int64_t)L.nJ * L.nI;
+    if (node >= nn) return;
+    const int J = (int)(node / L.nI), I = (int)(node % L.nI);
+    const double4 ch = g.lev[l - 1].nodes[node * 32 + lane];
+    const bool ok = ch.w >= 0.0;
+    double sx = ok ? ch.x : 0.0, sy = ok ? ch.y : 0.0, sz = ok ? ch.z : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    double nrm = sqrt(sx * sx + sy * sy + sz * sz);
+    const unsigned okm = __ballot_sync(0xffffffffu, ok);
+    if (!(nrm > 1.0e-6)) {
+        const int f = __ffs(okm) - 1;
+        sx = __shfl_sync(0xffffffffu, ch.x, f);
+        sy = __shfl_sync(0xffffffffu, ch.y, f);
+        sz = __shfl_sync(0xffffffffu, ch.z, f);
+        nrm = 1.0;
+    }
+    const double cx = sx / nrm, cy = sy / nrm, cz = sz / nrm;
+    double r = 0.0;
+    if (ok) {
+        const double dx = ch.x - cx, dy = ch.y - cy, dz = ch.z - cz;
+        r = sqrt(dx * dx + dy * dy + dz * dz) + ch.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+    r = r * (1.0 + 1.0e-12) + 1.0e-15;
+    if (lane == 0) {
+        int64_t idx;
+        if (is_top) {
+            idx = node;
+        } else {
+            const GzbLevel P = g.lev[l + 1];
+            const int pJ = J / P.bj, pI = I / P.bi;
+            idx = ((int64_t)pJ * P.nI + pI) * 32 + (J % P.bj) * P.bi + (I % P.bi);
+        }
+        L.nodes[idx] = make_double4(cx, cy, cz, r);
+    }
+}
+
+__global__ void k_fill_empty(double4* p, int64_t n) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) p[k] = make_double4(0.0, 0.0, 0.0, -1.0);
+}
+
+static int build_pyramid(gzb_ctx* ctx) {
+    GzbGrid& g = ctx->g;
+    // level geometry
+    int l = 0;
+    g.lev[0].nJ = (int)((g.Nj + GZB_TILE_J - 1) / GZB_TILE_J);
+    g.lev[0].nI = (int)((g.Ni + GZB_TILE_I - 1) / GZB_TILE_I);
+    g.lev[0].bj = GZB_TILE_J;
+    g.lev[0].bi = GZB_TILE_I;
+    g.lev[0].sJ = GZB_TILE_J;
+    g.lev[0].sI = GZB_TILE_I;
+    while ((int64_t)g.lev[l].nJ * g.lev[l].nI > 32) {
+        if (l + 1 >= GZB_MAXLEV) return gzb_fail(ctx, GZB_ERR_ARG, "grid too large for %d pyramid levels", GZB_MAXLEV);
+        GzbLevel& P = g.lev[l + 1];
+        P.bj = ((l + 1) & 1) ? 8 : 4;
+        P.bi = ((l + 1) & 1) ? 4 : 8;
+        P.nJ = (g.lev[l].nJ + P.bj - 1) / P.bj;
+        P.nI = (g.lev[l].nI + P.bi - 1) / P.bi;
+        P.sJ = g.lev[l].sJ * P.bj;
+        P.sI = g.lev[l].sI * P.bi;
+        ++l;
+    }
+    g.nlev = l + 1;
+    ctx->stats.pyramid_levels = g.nlev;
+    // storage
+    const int64_t ntile = (int64_t)g.lev[0].nJ * g.lev[0].nI;
+    GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_cells, (size_t)ntile * 96 * sizeof(double)));
+    g.cells = ctx->d_cells;
+    for (int k = 0; k < g.nlev; ++k) {
+        int64_t n = (k == g.nlev - 1) ? 32 : (int64_t)g.lev[k + 1].nJ * g.lev[k + 1].nI * 32;
+        GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_nodes[k], (size_t)n * sizeof(double4)));
+        g.lev[k].nodes = ctx->d_nodes[k];
+        k_fill_empty<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_nodes[k], n);
+        GZB_LAUNCH_CHECK(ctx);
+    }
+    k_build_leaves<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cells, ctx->d_nodes[0],
+                                                                       g.nlev == 1 ? 1 : 0);
+    GZB_LAUNCH_CHECK(ctx);
+    for (int k = 1; k < g.nlev; ++k) {
+        const int64_t nn = (int64_t)g.lev[k].nJ * g.lev[k].nI;
+        k_build_level<<<(unsigned)((nn + 7) / 8), 256, 0, ctx->stream>>>(g, k, k == g.nlev - 1 ? 1 : 0);
+        GZB_LAUNCH_CHECK(ctx);
+    }
+    return GZB_OK;
+}
+
+// ======================================================================== create / destroy
+extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat, const double* lon,
+                          const double* angle_or_null, const int8_t* mask_or_null, int k_ew_per,
+                          gzb_ctx** ctx_out) {
+    if (!ctx_out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: null ctx_out");
+    *ctx_out = nullptr;
+    if (nj < 3 || ni < 3 || !lat || !lon)
+        return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: need lat/lon of shape (nj>=3, ni>=3)");
+    if (nj * ni > (int64_t)1 << 40) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: grid too large");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return gzb_fail(nullptr, GZB_ERR_CUDA,
+                        "gzb_create: no CUDA device (%s); this library has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev)
+        return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: device %d out of range (have %d)", device, ndev);
+    gzb_ctx* ctx = new (std::nothrow) gzb_ctx();
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_NOMEM, "gzb_create: host allocation failed");
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    memset(&ctx->g, 0, sizeof(ctx->g));
+    ctx->err[0] = 0;
+    ctx->device = device;
+    int rc = GZB_OK;
+    do {
+        if ((rc = gzb_use_device(ctx)) != GZB_OK) break;
+#define CK(call) if ((e = (call)) != cudaSuccess) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
+        CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        bool evfail = false;
+        for (int k = 0; k < 4; ++k)
+            if ((e = cudaEventCreateWithFlags(&ctx->ev[k], cudaEventDisableTiming)) != cudaSuccess) evfail = true;
+        if (evfail) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); break; }
+        const size_t n = (size_t)nj * (size_t)ni;
+        CK(cudaMalloc((void**)&ctx->d_lat, n * sizeof(double)));
+        CK(cudaMalloc((void**)&ctx->d_lon, n * sizeof(double)));
+        CK(cudaMemcpyAsync(ctx->d_lat, lat, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_lon, lon, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += 2 * n * sizeof(double);
+        if (angle_or_null) {
+            CK(cudaMalloc((void**)&ctx->d_angle, n * sizeof(double)));
+            CK(cudaMemcpyAsync(ctx->d_angle, angle_or_null, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->stats.h2d_bytes += n * sizeof(double);
+        }
+        if (mask_or_null) {
+            CK(cudaMalloc((void**)&ctx->d_mask, n));
+            CK(cudaMemcpyAsync(ctx->d_mask, mask_or_null, n, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->stats.h2d_bytes += n;
+        }
+        CK(cudaHostAlloc(&ctx->pinned, 4096, cudaHostAllocPortable));
+        ctx->pinned_cap = 4096;
+#undef CK
+        ctx->g.Nj = nj;
+        ctx->g.Ni = ni;
+        ctx->g.kew = k_ew_per;
+        ctx->g.lat = ctx->d_lat;
+        ctx->g.lon = ctx->d_lon;
+        ctx->g.angle = ctx->d_angle;
+        ctx->g.mask = ctx->d_mask;
+        if ((rc = build_pyramid(ctx)) != GZB_OK) break;
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "grid upload / pyramid build: %s", cudaGetErrorString(e)); break; }
+    } while (0);
+    if (rc != GZB_OK) {
+        char keep[512];
+        strncpy(keep, ctx->err, sizeof(keep));
+        gzb_destroy(ctx);
+        gzb_set_global_error(keep);
+        return rc;
+    }
+    *ctx_out = ctx;
+    return GZB_OK;
+}
+
+extern "C" int gzb_destroy(gzb_ctx* ctx) {
+    if (!ctx) return GZB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    cudaFree(ctx->d_lat);
+    cudaFree(ctx->d_lon);
+    cudaFree(ctx->d_angle);
+    cudaFree(ctx->d_mask);
+    cudaFree(ctx->d_cells);
+    for (int k = 0; k < GZB_MAXLEV; ++k) cudaFree(ctx->d_nodes[k]);
+    cudaFree(ctx->arena.base);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+    for (int k = 0; k < 4; ++k)
+        if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    cudaGetLastError();
+    delete ctx;
+    return GZB_OK;
+}
+
+extern "C" int gzb_set_stream(gzb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_set_stream: null ctx");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return GZB_OK;
+}
+
+extern "C" int gzb_sync(gzb_ctx* ctx) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_sync: null ctx");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GZB_OK;
+}
+
+extern "C" int gzb_get_stats(const gzb_ctx* ctx, gzb_stats* out) {
+    if (!ctx || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_get_stats: null argument");
+    *out = ctx->stats;
+    return GZB_OK;
+}
+
+extern "C" int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_set_ew_per: null ctx");
+    ctx->g.kew = k_ew_per;
+    return GZB_OK;
+}
+
+extern "C" int gzb_set_mask(gzb_ctx* ctx, const int8_t* mask, int where) {
+    if (!ctx || !mask) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_mask: null argument");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const size_t n = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni;
+    if (!ctx->d_mask) GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_mask, n));
+    GZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, mask, n,
+                                  where == GZB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    if (where == GZB_HOST) {
+        ctx->stats.h2d_bytes += n;
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->g.mask = ctx->d_mask;
+    return GZB_OK;
+}
+
+extern "C" int gzb_set_angle(gzb_ctx* ctx, const double* angle_or_null, int where) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_set_angle: null ctx");
+    if (!angle_or_null) {
+        ctx->g.angle = nullptr;
+        return GZB_OK;
+    }
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const size_t n = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni * sizeof(double);
+    if (!ctx->d_angle) GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_angle, n));
+    GZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_angle, angle_or_null, n,
+                                  where == GZB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    if (where == GZB_HOST) {
+        ctx->stats.h2d_bytes += n;
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->g.angle = ctx->d_angle;
+    return GZB_OK;
+}
+
+// ======================================================================== K0: grid angle
+// gonzag/utils.py:226-262.  One thread walks a column strip of GA_ROWS rows with a 3-row
+// sliding window, so each lat/lon value is loaded once per strip (plus a 2-row halo) and its
+// tan / cos / sin are evaluated once and reused as the j-1, j and j+1 operand.
+#define GA_ROWS 32
+
+struct GaRow {
+    double t, c, s, lm;   // tan(pi/4 - lat/2), cos(lon), sin(lon), lon % 360
+};
+
+__device__ __forceinline__ GaRow ga_load(const double* __restrict__ lat, const double* __restrict__ lon, int64_t k) {
+    GaRow r;
+    const double la = lat[k], lo = lon[k];
+    r.t = tan(GZB_PI / 4.0 - GZB_D2R * la / 2.0);
+    r.c = cos(GZB_D2R * lo);
+    r.s = sin(GZB_D2R * lo);
+    r.lm = gzb_pymod(lo, 360.0);
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
+k_grid_angle(int64_t Nj, int64_t Ni, const double* __restrict__ lat, const double* __restrict__ lon,
+             double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Ni) return;
+    const int64_t j0 = (int64_t)blockIdx.y * GA_ROWS;
+    int64_t ja = j0 < 1 ? 1 : j0;
+    int64_t jb = j0 + GA_ROWS;
+    if (jb > Nj - 1) jb = Nj - 1;
+    if (j0 == 0) out[i] = 0.0;
+    if (j0 + GA_ROWS >= Nj) out[(Nj - 1) * Ni + i] = 0.0;
+    if (ja >= jb) return;
+    GaRow dn = ga_load(lat, lon, (ja - 1) * Ni + i);
+    GaRow md = ga_load(lat, lon, ja * Ni + i);
+    for (int64_t j = ja; j < jb; ++j) {
+        const GaRow up = ga_load(lat, lon, (j + 1) * Ni + i);
+        double ang = 0.0;
+        if (!(fabs(up.lm - dn.lm) < 1.0e-8)) {
+            const double px = 0.0 - 2.0 * md.c * md.t;
+            const double py = 0.0 - 2.0 * md.s * md.t;
+            const double pn = px * px + py * py;
+            const double vx = 2.0 * (up.c * up.t - dn.c * dn.t);
+            const double vy = 2.0 * (up.s * up.t - dn.s * dn.t);
+            double nv = sqrt(pn * (vx * vx + vy * vy));
+            nv = fmax(nv, 1.0e-12);
+            const double sn = (px * vy - py * vx) / nv;
+            const double cs = (px * vx + py * vy) / nv;
+            ang = atan2(sn, cs) * 180.0 / GZB_PI;
+        }
+        out[j * Ni + i] = ang;
+        dn = md;
+        md = up;
+    }
+}
+
+extern "C" int gzb_grid_angle(gzb_ctx* ctx, double* angle_out_or_null, int where) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_grid_angle: null ctx");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const int64_t Nj = ctx->g.Nj, Ni = ctx->g.Ni;
+    const size_t bytes = (size_t)Nj * (size_t)Ni * sizeof(double);
+    if (!ctx->d_angle) GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_angle, bytes));
+    dim3 grid((unsigned)((Ni + 127) / 128), (unsigned)((Nj + GA_ROWS - 1) / GA_ROWS));
+    k_grid_angle<<<grid, 128, 0, ctx->stream>>>(Nj, Ni, ctx->d_lat, ctx->d_lon, ctx->d_angle);
+    GZB_LAUNCH_CHECK(ctx);
+    ctx->g.angle = ctx->d_angle;
+    if (angle_out_or_null) {
+        if (where == GZB_HOST) {
+            GZB_CUDA(ctx, cudaMemcpyAsync(angle_out_or_null, ctx->d_angle, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->stats.d2h_bytes += bytes;
+        } else {
+            GZB_CUDA(ctx, cudaMemcpyAsync(angle_out_or_null, ctx->d_angle, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    if (where == GZB_HOST) GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GZB_OK;
+}
+
+// ======================================================================== memory helpers
+extern "C" int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out) {
+    if (!ctx || !dptr_out) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_dev_alloc: null argument");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    *dptr_out = nullptr;
+    cudaError_t e = cudaMalloc(dptr_out, bytes ? (size_t)bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gzb_fail(ctx, GZB_ERR_NOMEM, "cudaMalloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return GZB_OK;
+}
+
+extern "C" int gzb_dev_free(gzb_ctx* ctx, void* dptr) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_dev_free: null ctx");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GZB_CUDA(ctx, cudaFree(dptr));
+    return GZB_OK;
+}
+
+extern "C" int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_h2d: null ctx");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GZB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += bytes;
+    return GZB_OK;
+}
+
+extern "C" int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_d2h: null ctx");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GZB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += bytes;
+    return GZB_OK;
+}
+
+extern "C" int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_memset: null ctx");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GZB_CUDA(ctx, cudaMemsetAsync(dst_dev, byte, (size_t)bytes, ctx->stream));
+    return GZB_OK;
+}
+
+extern "C" int gzb_host_alloc(uint64_t bytes, void** hptr_out) {
+    if (!hptr_out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_host_alloc: null output");
+    *hptr_out = nullptr;
+    cudaError_t e = cudaHostAlloc(hptr_out, bytes ? (size_t)bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gzb_fail(nullptr, GZB_ERR_NOMEM, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return GZB_OK;
+}
+
+extern "C" int gzb_host_free(void* hptr) {
+    if (!hptr) return GZB_OK;
+    cudaError_t e = cudaFreeHost(hptr);
+    if (e != cudaSuccess) return gzb_fail(nullptr, GZB_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(e));
+    return GZB_OK;
+}
+
+extern "C" int gzb_host_register(void* hptr, uint64_t bytes) {
+    cudaError_t e = cudaHostRegister(hptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gzb_fail(nullptr, GZB_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+    }
+    return GZB_OK;
+}
+
+extern "C" int gzb_host_unregister(void* hptr) {
+    cudaError_t e = cudaHostUnregister(hptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return gzb_fail(nullptr, GZB_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    }
+    return GZB_OK;
+}

@@ -1,0 +1,410 @@
+// K4: fused time-linear + space-bilinear gather (gonzag/mod2sat.py:74-139), plus the cheap
+// a14 outputs: cumulative along-track distance (gonzag/mod2sat.py:146-148) and the
+// nearest-point map XNPtrack (gonzag/mod2sat.py:177-184).
+#include "gzb_common.cuh"
+
+__device__ __forceinline__ long long pywrap_idx(long long k, long long n) {
+    k = k < 0 ? k + n : k;                      // Python negative indexing (SM == -1 reads the last cell)
+    return k < 0 ? 0 : (k >= n ? n - 1 : k);    // anything else out of range is clamped, never faults
+}
+
+// One thread per track point.  T is the dtype of the model field: the time interpolation
+// x1 + ((x2 - x1) / dt) * (t - t1) is carried out in T (NumPy keeps float32 arrays in float32
+// when combined with Python floats), the weighted sum in float64, left to right, no FMA.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
+         const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
+         const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
+         const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
+         int* __restrict__ err) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    if (init) {
+        out_np[t] = rmiss;
+        out_bl[t] = rmiss;
+    }
+    const double now = t_sat[t];
+    if (!(now >= tmod[0]) || !(now < tmod[nrec - 1])) {
+        atomicOr(err, 1);
+        return;
+    }
+    long long lo = 0, hi = nrec - 1;            // tmod[lo] <= now < tmod[hi]
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (tmod[mid] <= now) lo = mid; else hi = mid;
+    }
+    if (lo < k0 || lo + 1 >= k0 + nk) return;   // bracket not inside this slab
+    const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
+    const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
+    const longlong2 p1 = sm[0], p2 = sm[1], p3 = sm[2], p4 = sm[3];
+    const double2 wa = wb[0], wc = wb[1];
+    const long long c1 = pywrap_idx(p1.x, g.Nj) * g.Ni + pywrap_idx(p1.y, g.Ni);
+    const long long c2 = pywrap_idx(p2.x, g.Nj) * g.Ni + pywrap_idx(p2.y, g.Ni);
+    const long long c3 = pywrap_idx(p3.x, g.Nj) * g.Ni + pywrap_idx(p3.y, g.Ni);
+    const long long c4 = pywrap_idx(p4.x, g.Nj) * g.Ni + pywrap_idx(p4.y, g.Ni);
+    const int ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
+    if (ocean != 4) return;
+    const long long cells = g.Nj * g.Ni;
+    const T* __restrict__ X1 = slab + (lo - k0) * cells;
+    const T* __restrict__ X2 = X1 + cells;
+    const T dt = (T)(tmod[lo + 1] - tmod[lo]);
+    const T de = (T)(now - tmod[lo]);
+    const T a1 = X1[c1], b1 = X2[c1];
+    const T a2 = X1[c2], b2 = X2[c2];
+    const T a3 = X1[c3], b3 = X2[c3];
+    const T a4 = X1[c4], b4 = X2[c4];
+    const T v1 = a1 + ((b1 - a1) / dt) * de;
+    const T v2 = a2 + ((b2 - a2) / dt) * de;
+    const T v3 = a3 + ((b3 - a3) / dt) * de;
+    const T v4 = a4 + ((b4 - a4) / dt) * de;
+    out_np[t] = (double)v1;
+    const double sw = ((wa.x + wa.y) + wc.x) + wc.y;
+    if (!(fabs(sw - 1.0) > 0.001))
+        out_bl[t] = ((wa.x * (double)v1 + wa.y * (double)v2) + wc.x * (double)v3) + wc.y * (double)v4;
+}
+
+template <typename T>
+static int launch_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,
+                         int64_t nrec, const double* tmod, const void* slab, int64_t k0, int64_t nk,
+                         double rmiss, int init, double* np_out, double* bl_out, int* err) {
+    k_interp<T><<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab, k0, nk, rmiss, init, np_out, bl_out, err);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
+}
+
+static int interp_chunk(gzb_ctx* ctx, int dtype, int64_t nt, const double* t, const int64_t* sm, const double* wb,
+                        int64_t nrec, const double* tmod, const void* slab, int64_t k0, int64_t nk, double rmiss,
+                        int init, double* np_out, double* bl_out, int* err) {
+    if (dtype == GZB_F32)
+        return launch_interp<float>(ctx, nt, t, sm, wb, nrec, tmod, slab, k0, nk, rmiss, init, np_out, bl_out, err);
+    return launch_interp<double>(ctx, nt, t, sm, wb, nrec, tmod, slab, k0, nk, rmiss, init, np_out, bl_out, err);
+}
+
+extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,
+                          int64_t nrec, const double* tmod, const void* slab, int dtype, int64_t k0, int64_t nk,
+                          double rmissval, int init_outputs, double* np_out, double* bl_out, int where) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_interp: null ctx");
+    if (nt < 0 || nrec < 2 || nk < 0 || k0 < 0 || k0 + nk > nrec || !tmod || !slab || (nt > 0 && (!t || !sm || !wb || !np_out || !bl_out)))
+        return gzb_fail(ctx, GZB_ERR_ARG, "gzb_interp: bad arguments (nt=%lld nrec=%lld k0=%lld nk=%lld)",
+                        (long long)nt, (long long)nrec, (long long)k0, (long long)nk);
+    if (dtype != GZB_F32 && dtype != GZB_F64) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_interp: dtype must be GZB_F32 or GZB_F64");
+    if (!ctx->g.mask) return gzb_fail(ctx, GZB_ERR_STATE, "gzb_interp: the context has no land-sea mask (gzb_set_mask)");
+    if (nt == 0) return GZB_OK;
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const size_t elsz = dtype == GZB_F32 ? 4 : 8;
+    const size_t rec_bytes = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni * elsz;
+    const size_t n = (size_t)nt;
+
+    // where does the field slab live?  (independent of `where`)
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, slab);
+    if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
+    const bool slab_on_device = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) || nk == 0;
+    const bool slab_pinned = (at.type == cudaMemoryTypeHost);
+
+    // chunking of a host slab: consecutive chunks share one record
+    int64_t C = nk;
+    if (!slab_on_device) {
+        const size_t budget = (size_t)256 << 20;
+        C = (int64_t)(budget / rec_bytes);
+        if (C < 2) C = 2;
+        if (C > nk) C = nk;
+    }
+    size_t need = gzb_align(64) + gzb_align((size_t)nrec * 8);
+    if (where == GZB_HOST) need += gzb_align(n * 8) * 3 + gzb_align(n * 64) + gzb_align(n * 32);
+    if (!slab_on_device) need += 2 * gzb_align((size_t)C * rec_bytes);
+    if (gzb_arena_reserve(ctx, need) != GZB_OK) return GZB_ERR_NOMEM;
+    cudaStream_t s = ctx->stream;
+    int* d_err = (int*)gzb_arena_take(ctx, 64);
+    GZB_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, s));
+    const double* d_t = t;
+    const long long* d_sm = (const long long*)sm;
+    const double* d_wb = wb;
+    const double* d_tmod = tmod;
+    double* d_np = np_out;
+    double* d_bl = bl_out;
+    if (where == GZB_HOST) {
+        double* a = (double*)gzb_arena_take(ctx, n * 8);
+        long long* b = (long long*)gzb_arena_take(ctx, n * 64);
+        double* c = (double*)gzb_arena_take(ctx, n * 32);
+        double* tm = (double*)gzb_arena_take(ctx, (size_t)nrec * 8);
+        d_np = (double*)gzb_arena_take(ctx, n * 8);
+        d_bl = (double*)gzb_arena_take(ctx, n * 8);
+        GZB_CUDA(ctx, cudaMemcpyAsync(a, t, n * 8, cudaMemcpyHostToDevice, s));
+        GZB_CUDA(ctx, cudaMemcpyAsync(b, sm, n * 64, cudaMemcpyHostToDevice, s));
+        GZB_CUDA(ctx, cudaMemcpyAsync(c, wb, n * 32, cudaMemcpyHostToDevice, s));
+        GZB_CUDA(ctx, cudaMemcpyAsync(tm, tmod, (size_t)nrec * 8, cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += n * 104 + (size_t)nrec * 8;
+        if (!init_outputs) {
+            GZB_CUDA(ctx, cudaMemcpyAsync(d_np, np_out, n * 8, cudaMemcpyHostToDevice, s));
+            GZB_CUDA(ctx, cudaMemcpyAsync(d_bl, bl_out, n * 8, cudaMemcpyHostToDevice, s));
+            ctx->stats.h2d_bytes += n * 16;
+        }
+        d_t = a; d_sm = b; d_wb = c; d_tmod = tm;
+    }
+
+    int rc = GZB_OK;
+    if (slab_on_device) {
+        rc = interp_chunk(ctx, dtype, nt, d_t, (const int64_t*)d_sm, d_wb, nrec, d_tmod, slab, k0, nk, rmissval,
+                          init_outputs, d_np, d_bl, d_err);
+        if (rc != GZB_OK) return rc;
+    } else {
+        char* dbuf[2];
+        dbuf[0] = (char*)gzb_arena_take(ctx, (size_t)C * rec_bytes);
+        dbuf[1] = (char*)gzb_arena_take(ctx, (size_t)C * rec_bytes);
+        if (!dbuf[1]) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_interp: workspace too small");
+        if (!slab_pinned && ctx->stage_cap < (size_t)C * rec_bytes) {
+            for (int k = 0; k < 2; ++k) {
+                if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+                ctx->stage[k] = nullptr;
+                GZB_CUDA(ctx, cudaHostAlloc(&ctx->stage[k], (size_t)C * rec_bytes, cudaHostAllocPortable));
+            }
+            ctx->stage_cap = (size_t)C * rec_bytes;
+        }
+        // the copy stream must not run ahead of work already queued on the main stream
+        GZB_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+        GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[0], 0));
+        bool used[2] = {false, false};
+        int init = init_outputs;
+        int64_t a = k0;
+        int c = 0;
+        const int64_t kend = k0 + nk;
+        for (;;) {
+            const int64_t len = (kend - a < C) ? (kend - a) : C;
+            const int b = c & 1;
+            const char* src = (const char*)slab + (size_t)(a - k0) * rec_bytes;
+            const size_t bytes = (size_t)len * rec_bytes;
+            if (used[b]) GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[2 + b], 0));
+            if (slab_pinned) {
+                GZB_CUDA(ctx, cudaMemcpyAsync(dbuf[b], src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            } else {
+                if (used[b]) GZB_CUDA(ctx, cudaEventSynchronize(ctx->ev[b]));   // previous H2D out of stage[b] done
+                memcpy(ctx->stage[b], src, bytes);
+                GZB_CUDA(ctx, cudaMemcpyAsync(dbuf[b], ctx->stage[b], bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            }
+            ctx->stats.h2d_bytes += bytes;
+            GZB_CUDA(ctx, cudaEventRecord(ctx->ev[b], ctx->copy_stream));
+            GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev[b], 0));
+            rc = interp_chunk(ctx, dtype, nt, d_t, (const int64_t*)d_sm, d_wb, nrec, d_tmod, dbuf[b], a, len, rmissval,
+                              init, d_np, d_bl, d_err);
+            if (rc != GZB_OK) return rc;
+            GZB_CUDA(ctx, cudaEventRecord(ctx->ev[2 + b], s));
+            used[b] = true;
+            init = 0;
+            ++c;
+            if (a + len >= kend) break;
+            a += len - 1;
+        }
+    }
+    int* h_err = (int*)((char*)ctx->pinned + 64);
+    GZB_CUDA(ctx, cudaMemcpyAsync(h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+    if (where == GZB_HOST) {
+        GZB_CUDA(ctx, cudaMemcpyAsync(np_out, d_np, n * 8, cudaMemcpyDeviceToHost, s));
+        GZB_CUDA(ctx, cudaMemcpyAsync(bl_out, d_bl, n * 8, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += n * 16;
+    }
+    if (where == GZB_HOST || !slab_on_device) {
+        GZB_CUDA(ctx, cudaStreamSynchronize(s));
+        if (*h_err) {
+            *h_err = 0;
+            return gzb_fail(ctx, GZB_ERR_TIME, "gzb_interp: track time outside the model records [tmod[0], tmod[nrec-1])");
+        }
+    }
+    return GZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// along-track distance: per-step Haversine_sclr (gonzag/utils.py:267-293) then a prefix sum
+#define GZB_REQ2 40680631.59076899   /* 6378.137**2 */
+#define GZB_RPL2 40408295.989504     /* 6356.752**2 */
+
+__device__ __forceinline__ double radius_earth_dev(double lat) {
+    const double p = lat * GZB_D2R;
+    const double cp = cos(p), sp = sin(p);
+    const double c0 = GZB_REQ2 * cp, d0 = GZB_RPL2 * sp, e0 = 6378.137 * cp, f0 = 6356.752 * sp;
+    return sqrt((c0 * c0 + d0 * d0) / (e0 * e0 + f0 * f0));
+}
+
+__device__ __forceinline__ double haversine_sclr_dev(double lat1, double lon1, double lat2, double lon2) {
+    const double R = radius_earth_dev(0.5 * (lat1 + lat2));
+    const double dlat = (lat2 - lat1) * GZB_D2R;
+    const double dlon = (lon2 - lon1) * GZB_D2R;
+    const double p1 = lat1 * GZB_D2R, p2 = lat2 * GZB_D2R;
+    const double s1 = sin(dlat / 2.0), s2 = sin(dlon / 2.0);
+    const double a = s1 * s1 + cos(p1) * cos(p2) * (s2 * s2);
+    return R * (2.0 * asin(sqrt(a)));
+}
+
+// block-local inclusive scan of the step lengths; block totals go to `tot`
+__global__ void __launch_bounds__(1024)
+k_dist_blocks(const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+              double* __restrict__ out, double* __restrict__ tot) {
+    __shared__ double wsum[32];
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v = 0.0;
+    if (t < nt && t > 0) v = haversine_sclr_dev(yt[t], xt[t], yt[t - 1], xt[t - 1]);
+    double s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += u;
+    }
+    if (lane == 31) wsum[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double w = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    const double incl = s + (warp ? wsum[warp - 1] : 0.0);
+    if (t < nt) out[t] = incl;
+    if (threadIdx.x == 1023) tot[blockIdx.x] = incl;
+}
+
+__global__ void __launch_bounds__(1024)
+k_dist_totals(double* __restrict__ tot, const long long nblk) {
+    __shared__ double wsum[32];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long base = 0; base < nblk; base += 1024) {
+        const long long k = base + threadIdx.x;
+        const double v = k < nblk ? tot[k] : 0.0;
+        double s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        if (lane == 31) wsum[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            double w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const double excl = carry + (warp ? wsum[warp - 1] : 0.0) + s - v;
+        if (k < nblk) tot[k] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_dist_add(const long long nt, double* __restrict__ out, const double* __restrict__ tot) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nt && blockIdx.x > 0) out[t] += tot[blockIdx.x];
+}
+
+extern "C" int gzb_track_distance(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double* dist_out,
+                                  int where) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_track_distance: null ctx");
+    if (nt < 0 || (nt > 0 && (!yt || !xt || !dist_out))) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_track_distance: bad arguments");
+    if (nt == 0) return GZB_OK;
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const size_t n = (size_t)nt;
+    const long long nblk = (long long)((n + 1023) / 1024);
+    size_t need = gzb_align((size_t)nblk * 8);
+    if (where == GZB_HOST) need += 3 * gzb_align(n * 8);
+    if (gzb_arena_reserve(ctx, need) != GZB_OK) return GZB_ERR_NOMEM;
+    cudaStream_t s = ctx->stream;
+    double* tot = (double*)gzb_arena_take(ctx, (size_t)nblk * 8);
+    const double* dy = yt;
+    const double* dx = xt;
+    double* dout = dist_out;
+    if (where == GZB_HOST) {
+        double* a = (double*)gzb_arena_take(ctx, n * 8);
+        double* b = (double*)gzb_arena_take(ctx, n * 8);
+        dout = (double*)gzb_arena_take(ctx, n * 8);
+        GZB_CUDA(ctx, cudaMemcpyAsync(a, yt, n * 8, cudaMemcpyHostToDevice, s));
+        GZB_CUDA(ctx, cudaMemcpyAsync(b, xt, n * 8, cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += n * 16;
+        dy = a;
+        dx = b;
+    }
+    k_dist_blocks<<<(unsigned)nblk, 1024, 0, s>>>(nt, dy, dx, dout, tot);
+    GZB_LAUNCH_CHECK(ctx);
+    if (nblk > 1) {
+        k_dist_totals<<<1, 1024, 0, s>>>(tot, nblk);
+        GZB_LAUNCH_CHECK(ctx);
+        k_dist_add<<<(unsigned)nblk, 1024, 0, s>>>(nt, dout, tot);
+        GZB_LAUNCH_CHECK(ctx);
+    }
+    if (where == GZB_HOST) {
+        GZB_CUDA(ctx, cudaMemcpyAsync(dist_out, dout, n * 8, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += n * 8;
+        GZB_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return GZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// XNPtrack: last track index per cell (Python's last-writer-wins loop == max index)
+__global__ void k_xnp_scatter(const GzbGrid g, const long long nt, const long long* __restrict__ NP,
+                              long long* __restrict__ last) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const long long j = pywrap_idx(NP[2 * t], g.Nj), i = pywrap_idx(NP[2 * t + 1], g.Ni);
+    atomicMax(last + j * g.Ni + i, t);
+}
+
+__global__ void k_xnp_final(const GzbGrid g, const long long* __restrict__ last, const double rmiss,
+                            double* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.Nj * g.Ni) return;
+    const long long l = last[k];
+    double v = l >= 0 ? (double)l : rmiss;
+    if (g.mask[k] == 0) v = -100.0;
+    out[k] = v;
+}
+
+extern "C" int gzb_xnp_track(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval, double* xnp_out,
+                             int where) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_xnp_track: null ctx");
+    if (nt < 0 || !xnp_out || (nt > 0 && !np)) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_xnp_track: bad arguments");
+    if (!ctx->g.mask) return gzb_fail(ctx, GZB_ERR_STATE, "gzb_xnp_track: the context has no land-sea mask");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const size_t n = (size_t)nt, cells = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni;
+    size_t need = gzb_align(cells * 8);
+    if (where == GZB_HOST) need += gzb_align(n * 16 + 16) + gzb_align(cells * 8);
+    if (gzb_arena_reserve(ctx, need) != GZB_OK) return GZB_ERR_NOMEM;
+    cudaStream_t s = ctx->stream;
+    long long* last = (long long*)gzb_arena_take(ctx, cells * 8);
+    const long long* dnp = (const long long*)np;
+    double* dout = xnp_out;
+    if (where == GZB_HOST) {
+        long long* a = (long long*)gzb_arena_take(ctx, n * 16 + 16);
+        dout = (double*)gzb_arena_take(ctx, cells * 8);
+        if (nt > 0) GZB_CUDA(ctx, cudaMemcpyAsync(a, np, n * 16, cudaMemcpyHostToDevice, s));
+        ctx->stats.h2d_bytes += n * 16;
+        dnp = a;
+    }
+    GZB_CUDA(ctx, cudaMemsetAsync(last, 0xff, cells * 8, s));
+    if (nt > 0) {
+        k_xnp_scatter<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(ctx->g, nt, dnp, last);
+        GZB_LAUNCH_CHECK(ctx);
+    }
+    k_xnp_final<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(ctx->g, last, rmissval, dout);
+    GZB_LAUNCH_CHECK(ctx);
+    if (where == GZB_HOST) {
+        GZB_CUDA(ctx, cudaMemcpyAsync(xnp_out, dout, cells * 8, cudaMemcpyDeviceToHost, s));
+        ctx->stats.d2h_bytes += cells * 8;
+        GZB_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    return GZB_OK;
+}

@@ -1,0 +1,269 @@
+// K2 (source mesh) and K3 (bilinear weights): one thread per track point.
+//   K2 restates BilinTrack.srcm / IDSourceMesh / Iquadran / Iquadran2SrcMesh / surrounding_j_i
+//      (gonzag/bilin_mapping.py:595-608, 453-486, 329-449, 215-262, 194-212)
+//   K3 restates BilinTrack.wght / WeightBL / AlfaBeta (gonzag/bilin_mapping.py:610-617, 490-527, 50-141)
+#include "gzb_common.cuh"
+
+// gonzag/bilin_mapping.py:194-212; -1 flags a missing neighbour
+__device__ __forceinline__ void neighbours(const GzbGrid& g, long long jP, long long iP, long long& jm,
+                                           long long& jp, long long& im, long long& ip) {
+    jm = jP - 1;
+    jp = jP + 1;
+    im = iP - 1;
+    ip = iP + 1;
+    if (jp == g.Nj) jp = -1;
+    if (im == -1) {
+        if (g.kew >= 0) im = g.Ni - g.kew - 1;
+    }
+    if (ip == g.Ni) {
+        ip = -1;
+        if (g.kew >= 0) ip = g.kew;
+    }
+}
+
+// gonzag/bilin_mapping.py:241-260: the three other corners, counter-clockwise from P
+__device__ __forceinline__ void quad_corners(int iq, long long jP, long long iP, long long jm, long long jp,
+                                             long long im, long long ip, long long* cj, long long* ci) {
+    cj[0] = jP; ci[0] = iP;
+    if (iq == 1)      { cj[1] = jP; ci[1] = ip; cj[2] = jp; ci[2] = ip; cj[3] = jp; ci[3] = iP; }
+    else if (iq == 2) { cj[1] = jm; ci[1] = iP; cj[2] = jm; ci[2] = ip; cj[3] = jP; ci[3] = ip; }
+    else if (iq == 3) { cj[1] = jP; ci[1] = im; cj[2] = jm; ci[2] = im; cj[3] = jm; ci[3] = iP; }
+    else              { cj[1] = jp; ci[1] = iP; cj[2] = jp; ci[2] = im; cj[3] = jP; ci[3] = im; }
+}
+
+// planar strict point-in-quadrilateral (boundary = outside): the stand-in for shapely's
+// Polygon.contains at gonzag/bilin_mapping.py:421-423, identical to
+// oracle/gz_oracle.py:point_strictly_in_quad (products and one subtraction, no FMA).
+__device__ __forceinline__ bool strictly_in_quad(double py, double px, const double* qy, const double* qx) {
+    int wn = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double ay = qy[k], ax = qx[k];
+        const double by = qy[(k + 1) & 3], bx = qx[(k + 1) & 3];
+        const double side = (by - ay) * (px - ax) - (bx - ax) * (py - ay);
+        if (side == 0.0) {
+            if (fmin(ay, by) <= py && py <= fmax(ay, by) && fmin(ax, bx) <= px && px <= fmax(ax, bx)) return false;
+        }
+        if (ax <= px) {
+            if (bx > px && side > 0.0) ++wn;
+        } else {
+            if (bx <= px && side < 0.0) --wn;
+        }
+    }
+    return wn != 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+              const long long* __restrict__ NP, long long* __restrict__ SM) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const long long jP = NP[2 * t], iP = NP[2 * t + 1];
+    long long cj[4], ci[4];
+    longlong2* out = reinterpret_cast<longlong2*>(SM + 8 * t);
+    if (jP == -1 && iP == -1) {   // nearest point not found: the row stays zero
+        const longlong2 z = make_longlong2(0, 0);
+        out[0] = z; out[1] = z; out[2] = z; out[3] = z;
+        return;
+    }
+    int iq = -1;
+    bool usable = (jP >= 0 && jP < g.Nj && iP >= 0 && iP < g.Ni);
+    long long jm = 0, jp = 0, im = 0, ip = 0;
+    if (usable) {
+        neighbours(g, jP, iP, jm, jp, im, ip);
+        if (jm == -1 || jp == -1 || im == -1 || ip == -1) usable = false;
+        else if (im < 0 || jm < 0 || ip > g.Ni - 1) usable = false;
+    }
+    if (usable) {
+        const double yT = yt[t], xT = xt[t];
+        const double lat0 = g.lat[jP * g.Ni + iP], lonP = g.lon[jP * g.Ni + iP];
+        const double latN = g.lat[jp * g.Ni + iP], lonN = g.lon[jp * g.Ni + iP];
+        const double latE = g.lat[jP * g.Ni + ip], lonE = g.lon[jP * g.Ni + ip];
+        const double latS = g.lat[jm * g.Ni + iP], lonS = g.lon[jm * g.Ni + iP];
+        const double latW = g.lat[jP * g.Ni + im], lonW = g.lon[jP * g.Ni + im];
+        const double lon0 = gzb_pymod(lonP, 360.0);
+        const double zT = gzb_pymod(xT, 360.0);
+        const double ht = gzb_heading_dev(lat0, lon0, yT, zT);
+        double hN = gzb_heading_dev(lat0, lon0, latN, gzb_pymod(lonN, 360.0));
+        const double hE = gzb_heading_dev(lat0, lon0, latE, gzb_pymod(lonE, 360.0));
+        const double hS = gzb_heading_dev(lat0, lon0, latS, gzb_pymod(lonS, 360.0));
+        const double hW = gzb_heading_dev(lat0, lon0, latW, gzb_pymod(lonW, 360.0));
+        const double hz = gzb_pm180(ht);
+        if (hN > hE) hN = hN - 360.0;
+        if (hz > hN && hz <= hE) iq = 1;
+        if (ht > hE && ht <= hS) iq = 2;
+        if (ht > hS && ht <= hW) iq = 3;
+        if (ht > hW && hz <= hN) iq = 4;
+        const double ang = g.angle ? g.angle[jP * g.Ni + iP] : 0.0;
+        if (iq < 1 || fabs(ang) > 45.0) {
+            // heavy-duty: quads 4,3,2,1 in the raw (lat, lon) plane, first strict-interior hit
+            for (int cand = 4; cand >= 1; --cand) {
+                quad_corners(cand, jP, iP, jm, jp, im, ip, cj, ci);
+                double qy[4], qx[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    qy[k] = g.lat[cj[k] * g.Ni + ci[k]];
+                    qx[k] = g.lon[cj[k] * g.Ni + ci[k]];
+                }
+                if (strictly_in_quad(yT, xT, qy, qx)) {
+                    iq = cand;
+                    break;
+                }
+            }
+        }
+    }
+    if (iq >= 1) {
+        quad_corners(iq, jP, iP, jm, jp, im, ip, cj, ci);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cj[k] = -1; ci[k] = -1; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = make_longlong2(cj[k], ci[k]);
+}
+
+__device__ __forceinline__ long long pywrap(long long k, long long n) { return k < 0 ? k + n : k; }
+
+__global__ void __launch_bounds__(128)
+k_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+          const long long* __restrict__ SM, double* __restrict__ WB) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
+    double w1 = 1.0, w2 = 0.0, w3 = 0.0, w4 = 0.0;
+    const longlong2 p1 = sm[0];
+    if (p1.x >= 0) {
+        double vy[5], vx[5];
+        vy[0] = yt[t];
+        vx[0] = xt[t];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const longlong2 p = sm[k];
+            long long j = pywrap(p.x, g.Nj), i = pywrap(p.y, g.Ni);
+            j = j < 0 ? 0 : (j >= g.Nj ? g.Nj - 1 : j);
+            i = i < 0 ? 0 : (i >= g.Ni ? g.Ni - 1 : i);
+            vy[k + 1] = g.lat[j * g.Ni + i];
+            vx[k + 1] = g.lon[j * g.Ni + i];
+        }
+        double a, b;
+        gzb_alfabeta_dev(vy, vx, a, b);
+        w1 = (1.0 - a) * (1.0 - b);
+        w2 = a * (1.0 - b);
+        w3 = a * b;
+        w4 = (1.0 - a) * b;
+    }
+    double2* out = reinterpret_cast<double2*>(WB + 4 * t);
+    out[0] = make_double2(w1, w2);
+    out[1] = make_double2(w3, w4);
+}
+
+int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
+                        int64_t* sm_out) {
+    if (nt <= 0) return GZB_OK;
+    k_source_mesh<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
+                                                                        (long long*)sm_out);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
+}
+
+int gzb_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* sm,
+                    double* wb_out) {
+    if (nt <= 0) return GZB_OK;
+    k_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)sm, wb_out);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched scalar helpers (Heading, AlfaBeta, Haversine) for the free functions the reference
+// package re-exports (gonzag/__init__.py:13)
+__global__ void k_heading(long long n, const double* a, const double* b, const double* c, const double* d, double* o) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) o[k] = gzb_heading_dev(a[k], b[k], c[k], d[k]);
+}
+
+__global__ void k_alfabeta(long long n, const double* vy, const double* vx, double* ab) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        double a, b;
+        gzb_alfabeta_dev(vy + 5 * k, vx + 5 * k, a, b);
+        ab[2 * k] = a;
+        ab[2 * k + 1] = b;
+    }
+}
+
+__global__ void k_haversine(long long n, double plat, double plon, const double* la, const double* lo, double* o) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) o[k] = gzb_haversine_dev(plat, plon, cos(plat * GZB_D2R), la[k], lo[k]);
+}
+
+namespace {
+struct TmpDev {
+    void* p = nullptr;
+    ~TmpDev() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+static int helper_run(int device, size_t in_doubles, size_t out_doubles, const double* const* ins,
+                      const size_t* in_sizes, int nin, double* out, void (*launch)(double** din, double* dout)) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return gzb_fail(nullptr, GZB_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    TmpDev buf;
+    e = cudaMalloc(&buf.p, (in_doubles + out_doubles + 8) * sizeof(double));
+    if (e != cudaSuccess) return gzb_fail(nullptr, GZB_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    double* base = (double*)buf.p;
+    double* din[8];
+    size_t off = 0;
+    for (int k = 0; k < nin; ++k) {
+        din[k] = base + off;
+        e = cudaMemcpy(din[k], ins[k], in_sizes[k] * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return gzb_fail(nullptr, GZB_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
+        off += in_sizes[k];
+    }
+    double* dout = base + off;
+    launch(din, dout);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, out_doubles * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return gzb_fail(nullptr, GZB_ERR_CUDA, "helper kernel: %s", cudaGetErrorString(e));
+    return GZB_OK;
+}
+
+static thread_local long long h_n;
+static thread_local double h_plat, h_plon;
+
+extern "C" int gzb_heading(int device, int64_t n, const double* lata, const double* lona, const double* latb,
+                           const double* lonb, double* out) {
+    if (n <= 0) return GZB_OK;
+    if (!lata || !lona || !latb || !lonb || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_heading: null argument");
+    const double* ins[4] = {lata, lona, latb, lonb};
+    const size_t sz[4] = {(size_t)n, (size_t)n, (size_t)n, (size_t)n};
+    h_n = n;
+    return helper_run(device, 4 * (size_t)n, (size_t)n, ins, sz, 4, out, [](double** d, double* o) {
+        k_heading<<<(unsigned)((h_n + 255) / 256), 256>>>(h_n, d[0], d[1], d[2], d[3], o);
+    });
+}
+
+extern "C" int gzb_alfabeta(int device, int64_t n, const double* vy5, const double* vx5, double* ab_out) {
+    if (n <= 0) return GZB_OK;
+    if (!vy5 || !vx5 || !ab_out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_alfabeta: null argument");
+    const double* ins[2] = {vy5, vx5};
+    const size_t sz[2] = {5 * (size_t)n, 5 * (size_t)n};
+    h_n = n;
+    return helper_run(device, 10 * (size_t)n, 2 * (size_t)n, ins, sz, 2, ab_out, [](double** d, double* o) {
+        k_alfabeta<<<(unsigned)((h_n + 255) / 256), 256>>>(h_n, d[0], d[1], o);
+    });
+}
+
+extern "C" int gzb_haversine(int device, int64_t n, double plat, double plon, const double* xlat,
+                             const double* xlon, double* out) {
+    if (n <= 0) return GZB_OK;
+    if (!xlat || !xlon || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_haversine: null argument");
+    const double* ins[2] = {xlat, xlon};
+    const size_t sz[2] = {(size_t)n, (size_t)n};
+    h_n = n;
+    h_plat = plat;
+    h_plon = plon;
+    return helper_run(device, 2 * (size_t)n, (size_t)n, ins, sz, 2, out, [](double** d, double* o) {
+        k_haversine<<<(unsigned)((h_n + 255) / 256), 256>>>(h_n, h_plat, h_plon, d[0], d[1], o);
+    });
+}

@@ -1,0 +1,158 @@
+/*
+ * gonzag_b200 -- C ABI of the B200 (sm_100a) implementation of gonzag's
+ * gridded -> along-track mapping + interpolation path.
+ *
+ * The reference (brodeau/gonzag) is pure Python; the interface this library replaces is
+ * the Python surface of gonzag/bilin_mapping.py and gonzag/mod2sat.py.  Each entry point
+ * below names the reference lines it stands in for.  INTEGRATION.md shows the ctypes stub a
+ * gonzag maintainer would add to call them.
+ *
+ * Conventions
+ *   - every function returns an int status (GZB_OK == 0); nothing throws, nothing exits;
+ *     gzb_last_error() gives the message of the last failure on a context
+ *     (gzb_last_global_error() for failures before a context exists);
+ *   - arrays are C-contiguous; grids are row-major (Nj, Ni); indices are int64, weights and
+ *     coordinates float64, exactly the dtypes of the reference attributes
+ *     BilinTrack.NP (Nt,2), .SM (Nt,4,2), .WB (Nt,4)  (gonzag/bilin_mapping.py:547-549);
+ *   - `where` says where the array arguments of a call live: GZB_HOST (caller-owned host
+ *     buffers; the call copies in/out and is synchronous on return) or GZB_DEVICE (device
+ *     pointers on the context's GPU; the call only enqueues work on the context's stream);
+ *   - a context owns the device copy of one model grid and its search structure; it is not
+ *     thread-safe (one context per GPU / stream);
+ *   - there is no CPU fallback: without a CUDA device gzb_create() fails.
+ */
+#ifndef GONZAG_B200_H
+#define GONZAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gzb_ctx gzb_ctx;
+
+enum { GZB_OK = 0, GZB_ERR_CUDA = 1, GZB_ERR_ARG = 2, GZB_ERR_NOMEM = 3, GZB_ERR_STATE = 4,
+       GZB_ERR_TIME = 5 };
+enum { GZB_HOST = 0, GZB_DEVICE = 1 };
+enum { GZB_F32 = 0, GZB_F64 = 1 };
+
+/* counters filled by gzb_get_stats() */
+typedef struct gzb_stats {
+    uint64_t kernel_launches;   /* kernels launched by this context since creation          */
+    uint64_t h2d_bytes;         /* bytes copied host->device by this context                */
+    uint64_t d2h_bytes;         /* bytes copied device->host by this context                */
+    int64_t  last_breaks;       /* last gzb_nearest: points whose seeding had to be replayed */
+    int64_t  last_chain_steps;  /* last gzb_nearest: sequential replay steps, all chains     */
+    int32_t  pyramid_levels;    /* depth of the bounding-sphere pyramid over the grid       */
+    int32_t  reserved;
+} gzb_stats;
+
+const char* gzb_version(void);
+const char* gzb_last_global_error(void);
+int gzb_device_count(int* n_out);
+
+/* ---- context: one model grid resident on one GPU ---------------------------------------
+ * Replaces the grid arguments of BilinTrack(Yt,Xt,Ys,Xs,src_grid_local_angle,k_ew_per,...)
+ * (gonzag/bilin_mapping.py:533-545) and MG.lat/MG.lon/MG.xangle/MG.EWPer/MG.mask as read by
+ * Model2SatTrack (gonzag/mod2sat.py:33-50,124).  lat/lon: (nj,ni) float64 degrees, finite.
+ * angle: (nj,ni) float64 degrees or NULL (no -D).  mask: (nj,ni) int8 {0,1} or NULL.
+ * k_ew_per: -1 none, >=0 overlap of the East-West periodicity. */
+int gzb_create(int device, int64_t nj, int64_t ni, const double* lat, const double* lon,
+               const double* angle_or_null, const int8_t* mask_or_null, int k_ew_per,
+               gzb_ctx** ctx_out);
+int gzb_destroy(gzb_ctx* ctx);
+const char* gzb_last_error(const gzb_ctx* ctx);
+int gzb_set_stream(gzb_ctx* ctx, void* cuda_stream);      /* NULL -> context's own stream */
+int gzb_sync(gzb_ctx* ctx);
+int gzb_get_stats(const gzb_ctx* ctx, gzb_stats* out);
+int gzb_set_mask(gzb_ctx* ctx, const int8_t* mask, int where);
+int gzb_set_angle(gzb_ctx* ctx, const double* angle_or_null, int where);
+int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
+
+/* ---- K0: local grid rotation, the `-D` pre-pass --------------------------------------------
+ * Replaces GridAngle(xlat, xlon) (gonzag/utils.py:226-262).  Computes the (nj,ni) angle in
+ * degrees from the context's lat/lon, installs it as the context's angle and, when
+ * angle_out is not NULL, copies it there. */
+int gzb_grid_angle(gzb_ctx* ctx, double* angle_out_or_null, int where);
+
+/* ---- K1: nearest points along a track --------------------------------------------------
+ * Replaces BilinTrack.nrpt() + NearestPoint() + the edge exclusion
+ * (gonzag/bilin_mapping.py:566-593, 144-191).  yt/xt: (nt,) float64.  The previous-hit
+ * seeding of consecutive points is reproduced exactly; (seed_j, seed_i) is the pair handed
+ * to the first point (the reference uses (np_box_r, np_box_r)).
+ * np_out: (nt,2) int64, [j,i], (-1,-1) = not found. */
+int gzb_nearest(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
+                double rd_found_km, int np_box_r, int64_t seed_j, int64_t seed_i,
+                int64_t* np_out, int where);
+
+/* ---- K2: source mesh ---------------------------------------------------------------------
+ * Replaces BilinTrack.srcm() + IDSourceMesh() + Iquadran() + Iquadran2SrcMesh()
+ * (gonzag/bilin_mapping.py:595-608, 453-486, 329-449, 215-262), including the local-angle
+ * lookup, the heavy-duty polygon search and the East-West wrap.
+ * np: (nt,2) int64.  sm_out: (nt,4,2) int64; all -1 = quadrant not found; all 0 where the
+ * nearest point is (-1,-1). */
+int gzb_source_mesh(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
+                    const int64_t* np, int64_t* sm_out, int where);
+
+/* ---- K3: bilinear weights ------------------------------------------------------------------
+ * Replaces BilinTrack.wght() + WeightBL() + AlfaBeta()
+ * (gonzag/bilin_mapping.py:610-617, 490-527, 50-141).  wb_out: (nt,4) float64. */
+int gzb_weights(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
+                const int64_t* sm, double* wb_out, int where);
+
+/* K1+K2+K3 in one call (what BilinTrack.__init__ does, gonzag/bilin_mapping.py:554-564). */
+int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
+                double rd_found_km, int np_box_r, int64_t seed_j, int64_t seed_i,
+                int64_t* np_out, int64_t* sm_out, double* wb_out, int where);
+
+/* ---- K4: fused time-linear + space-bilinear gather -----------------------------------------
+ * Replaces the interpolation loop of Model2SatTrack (gonzag/mod2sat.py:74-139).
+ * t: (nt,) float64 track times; tmod: (nrec,) float64 model record times, increasing;
+ * slab: records [k0, k0+nk) of the model field, (nk,nj,ni) of `dtype` (GZB_F32 / GZB_F64);
+ * points whose bracketing records both lie in the slab are written, the others are left
+ * untouched, so a caller streams a long series by looping over slabs (never over points).
+ * init_outputs != 0 first fills np_out/bl_out with rmissval (do it on the first slab).
+ * Needs a mask in the context.  Points outside [tmod[0], tmod[nrec-1]) -> GZB_ERR_TIME. */
+int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,
+               int64_t nrec, const double* tmod, const void* slab, int dtype, int64_t k0,
+               int64_t nk, double rmissval, int init_outputs, double* np_out, double* bl_out,
+               int where);
+
+/* ---- a14: along-track distance and nearest-point map ---------------------------------------
+ * gzb_track_distance: cumulative distance (km) from the first point, Haversine_sclr with the
+ * latitude-dependent Earth radius (gonzag/mod2sat.py:146-148, gonzag/utils.py:267-293).
+ * gzb_xnp_track: (nj,ni) float64 map holding the last track index that hit each cell,
+ * -100 over land, rmissval elsewhere (gonzag/mod2sat.py:177-184).  Needs a mask. */
+int gzb_track_distance(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
+                       double* dist_out, int where);
+int gzb_xnp_track(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval,
+                  double* xnp_out, int where);
+
+/* ---- scalar helpers exported by the reference package, batched ------------------------------
+ * gzb_heading  : Heading(lata,lona,latb,lonb)      gonzag/bilin_mapping.py:16-47
+ * gzb_alfabeta : AlfaBeta(vy[5], vx[5]) -> (a,b)   gonzag/bilin_mapping.py:50-141
+ * gzb_haversine: Haversine(plat,plon,xlat,xlon)     gonzag/utils.py:296-316
+ * All arrays HOST, n independent problems per call; they run on `device`. */
+int gzb_heading(int device, int64_t n, const double* lata, const double* lona,
+                const double* latb, const double* lonb, double* out);
+int gzb_alfabeta(int device, int64_t n, const double* vy5, const double* vx5, double* ab_out);
+int gzb_haversine(int device, int64_t n, double plat, double plon, const double* xlat,
+                  const double* xlon, double* out);
+
+/* ---- memory helpers so that a host language without a CUDA binding can keep a pipeline on
+ * the device (used by the Python layer; not part of the reference's surface) ---------------- */
+int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out);
+int gzb_dev_free(gzb_ctx* ctx, void* dptr);
+int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);   /* async */
+int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);   /* async */
+int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes);            /* async */
+int gzb_host_alloc(uint64_t bytes, void** hptr_out);     /* pinned, portable, mapped */
+int gzb_host_free(void* hptr);
+int gzb_host_register(void* hptr, uint64_t bytes);
+int gzb_host_unregister(void* hptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GONZAG_B200_H */

@@ -1,0 +1,202 @@
+"""Parity of the CUDA path (through the C ABI / the drop-in Python API) against the golden
+vectors of the reference and against the CPU oracle.  Indices and masks must be identical;
+weights and interpolated values within 1e-6 relative (north_star), with a small absolute term
+because weights can be ~1e-8."""
+import types
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import gonzag_b200 as gzb
+from gonzag_b200 import synthetic as syn
+from oracle import gz_oracle as orc
+
+RTOL, ATOL = 1e-6, 1e-9
+
+
+def _grid(g):
+    return g["lat"].astype(np.float64), g["lon"].astype(np.float64)
+
+
+def _report_index_mismatch(name, got, want, extra=""):
+    bad = np.where((got != want).reshape(got.shape[0], -1).any(axis=1))[0]
+    assert bad.size == 0, "%s: %d rows differ, first at %s: got %s want %s %s" % (
+        name, bad.size, bad[:5], got[bad[:3]].tolist(), want[bad[:3]].tolist(), extra)
+
+
+def test_scalar_helpers(golden_units):
+    g = golden_units
+    from gonzag_b200 import _lib as L
+    a = g["heading_in"]
+    out = np.empty(len(a))
+    cols = [np.ascontiguousarray(a[:, k]) for k in range(4)]
+    L.check(L.lib().gzb_heading(0, len(a), *[L.ptr(c) for c in cols], L.ptr(out)))
+    d = np.abs(out - g["heading_out"])
+    d = np.minimum(d, 360.0 - d)
+    assert d.max() < 1e-9
+    vy, vx = np.ascontiguousarray(g["ab_vy"]), np.ascontiguousarray(g["ab_vx"])
+    ab = np.empty((len(vy), 2))
+    L.check(L.lib().gzb_alfabeta(0, len(vy), L.ptr(vy), L.ptr(vx), L.ptr(ab)))
+    np.testing.assert_allclose(ab, g["ab_out"], rtol=RTOL, atol=ATOL)
+    glat, glon = np.ascontiguousarray(g["hav_glat"]), np.ascontiguousarray(g["hav_glon"])
+    hv = np.empty(glat.shape)
+    L.check(L.lib().gzb_haversine(0, glat.size, float(g["hav_pt"][0]), float(g["hav_pt"][1]), L.ptr(glat),
+                                  L.ptr(glon), L.ptr(hv)))
+    np.testing.assert_allclose(hv, g["hav_out"], rtol=1e-13)
+
+
+def test_grid_angle(golden_units, golden_global):
+    g = golden_units
+    got = gzb.GridAngle(g["ga_lat"], g["ga_lon"])
+    np.testing.assert_allclose(got, g["ga_out"], rtol=0, atol=1e-9)
+    lat, lon = _grid(golden_global)
+    got = gzb.GridAngle(lat, lon)
+    np.testing.assert_allclose(got, golden_global["angle"], rtol=0, atol=1e-9)
+    assert (got[0] == 0).all() and (got[-1] == 0).all()
+
+
+def _check_bt(bt, g, suffix=""):
+    _report_index_mismatch("NP" + suffix, bt.NP, g["NP" + suffix])
+    _report_index_mismatch("SM" + suffix, bt.SM, g["SM" + suffix])
+    np.testing.assert_allclose(bt.WB, g["WB" + suffix], rtol=RTOL, atol=ATOL)
+    assert bt.NP.dtype == np.int64 and bt.SM.dtype == np.int64 and bt.WB.dtype == np.float64
+    assert bt.SM.shape == (bt.Nt, 4, 2) and bt.WB.shape == (bt.Nt, 4)
+
+
+def test_global_mapping(golden_global):
+    g = golden_global
+    lat, lon = _grid(g)
+    res = float(g["res"])
+    rd, r = 0.75 * res * 111.11, int(0.5 * 500. / (res * 111.11))
+    bt = gzb.BilinTrack(g["ysat"], g["xsat"], lat, lon, src_grid_local_angle=g["angle"], k_ew_per=2,
+                        rd_found_km=rd, np_box_r=r)
+    _check_bt(bt, g)
+    # the stage methods return fresh arrays equal to the attributes
+    np.testing.assert_array_equal(bt.nrpt(), bt.NP)
+    np.testing.assert_array_equal(bt.srcm(), bt.SM)
+    np.testing.assert_array_equal(bt.wght(), bt.WB)
+    st = bt.ctx.stats()
+    assert st["kernel_launches"] > 0 and st["last_breaks"] > 0
+    bt.close()
+    bt0 = gzb.BilinTrack(g["ysat"], g["xsat"], lat, lon, k_ew_per=-1, rd_found_km=rd, np_box_r=r)
+    _check_bt(bt0, g, "_noper")
+    bt0.close()
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_global_model2sat(golden_global, tag):
+    g = golden_global
+    lat, lon = _grid(g)
+    f32 = g["f32"]
+    fld = f32 if tag == "f32" else f32.astype(np.float64) + lat[None] * 2.0 ** -20
+    MG = types.SimpleNamespace(shape=lat.shape, HResDeg=float(g["res"]), lat=lat, lon=lon, xangle=g["angle"],
+                               EWPer=2, time=g["tmod"], file="mem", mask=g["mask"].astype(np.int64), field=fld)
+    ST = types.SimpleNamespace(size=len(g["tsat"]), lat=g["ysat"], lon=g["xsat"], time=g["tsat"], file="mem",
+                               jt1=0, jt2=0, keepit=[], ssh=g["ssat"])
+    R = gzb.Model2SatTrack(MG, "ssh", ST, "ssh")
+    _report_index_mismatch("NP", R.BT.NP, g["NP"])
+    _report_index_mismatch("SM", R.BT.SM, g["SM"])
+    np.testing.assert_array_equal(R.mask, g["imask_" + tag])
+    assert R.mask.dtype == np.int8
+    np.testing.assert_array_equal(np.ma.getmaskarray(R.ssh_mod), g["ssh_bl_%s_mask" % tag])
+    np.testing.assert_allclose(np.ma.getdata(R.ssh_mod), g["ssh_bl_%s_data" % tag], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.ma.getdata(R.ssh_mod_np), g["ssh_np_%s_data" % tag], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.ma.getdata(R.ssh_sat), g["ssh_sat_data"])
+    np.testing.assert_allclose(R.distance, g["distance"], rtol=1e-9)
+    np.testing.assert_array_equal(np.ma.getmaskarray(R.XNPtrack), g["xnp_mask"])
+    np.testing.assert_array_equal(np.ma.getdata(R.XNPtrack), g["xnp_data"])
+    # per-record provider (the reference's GetModel2DVar shape of access) gives the same answer
+    MG2 = types.SimpleNamespace(**{k: v for k, v in vars(MG).items() if k != "field"})
+    MG2.get_record = lambda k: fld[k].copy()
+    R2 = gzb.Model2SatTrack(MG2, "ssh", ST, "ssh", slab_bytes=2 * fld[0].nbytes)
+    np.testing.assert_array_equal(np.ma.getdata(R2.ssh_mod), np.ma.getdata(R.ssh_mod))
+    np.testing.assert_array_equal(np.ma.getdata(R2.ssh_mod_np), np.ma.getdata(R.ssh_mod_np))
+
+
+def test_regional(golden_regional):
+    g = golden_regional
+    lat, lon = _grid(g)
+    rd, r = float(g["rd"]), int(g["r"])
+    bt = gzb.BilinTrack(g["ysat"], g["xsat"], lat, lon, k_ew_per=-1, rd_found_km=rd, np_box_r=r)
+    _check_bt(bt, g)
+    ctx = bt.ctx
+    ctx.set_mask(g["mask"])
+    v_np, v_bl = ctx.interp(g["tsat"], bt.SM, bt.WB, g["tmod"], g["f32"])
+    np.testing.assert_allclose(v_bl, g["ssh_bl_data"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(v_np, g["ssh_np_data"], rtol=RTOL, atol=ATOL)
+    # two slabs sharing a record == one slab
+    o = ctx.interp(g["tsat"], bt.SM, bt.WB, g["tmod"], g["f32"][0:2], k0=0)
+    o = ctx.interp(g["tsat"], bt.SM, bt.WB, g["tmod"], g["f32"][1:3], k0=1, out=o)
+    np.testing.assert_array_equal(o[1], v_bl)
+    np.testing.assert_array_equal(o[0], v_np)
+    # shuffled targets: every point restarts the seeding
+    p = g["perm"]
+    NP, SM, WB = ctx.mapping(g["ysat"][p], g["xsat"][p], rd, r)
+    _report_index_mismatch("NP_perm", NP, g["NP_perm"])
+    _report_index_mismatch("SM_perm", SM, g["SM_perm"])
+    np.testing.assert_allclose(WB, g["WB_perm"], rtol=RTOL, atol=ATOL)
+    bt.close()
+
+
+def test_seam(golden_seam, golden_global):
+    g = golden_seam
+    lat, lon = _grid(golden_global)
+    rd, r = float(g["rd"]), int(g["r"])
+    for kew, suf in ((2, ""), (-1, "_noper")):
+        bt = gzb.BilinTrack(g["ysat"], g["xsat"], lat, lon, src_grid_local_angle=golden_global["angle"],
+                            k_ew_per=kew, rd_found_km=rd, np_box_r=r)
+        _check_bt(bt, g, suf)
+        assert bt.ctx.stats()["last_chain_steps"] > bt.ctx.stats()["last_breaks"]   # real multi-step replays
+        bt.close()
+
+
+def test_time_out_of_range(golden_regional):
+    g = golden_regional
+    lat, lon = _grid(g)
+    with gzb.GridContext(lat, lon, mask=g["mask"]) as ctx:
+        SM = np.zeros((4, 4, 2), dtype=np.int64)
+        WB = np.full((4, 4), 0.25)
+        with pytest.raises(gzb.GonzagB200Error):
+            ctx.interp(np.array([1e9, 2e9, 3e9, 4e9]), SM, WB, g["tmod"], g["f32"])
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2"])
+def test_config_vs_oracle(cfg):
+    """BASELINE configs 1 and 2 at full grid size, oracle on a contiguous prefix of the track
+    (the nearest-point chain) and on a random subset (mesh, weights, interpolation)."""
+    if cfg == "C1":
+        lat, lon = syn.orca_like_grid(292, 362)
+        kew = 2
+        t, y, x = syn.orbit_track(86400, t0=10.0, **syn.SARAL)
+        n_chain = 6000
+    else:
+        lat, lon = syn.regional_grid(800, 1000, lat0=-55.0, lon0=140.0, res_deg=1.0 / 12.0)
+        kew = -1
+        t, y, x = syn.orbit_track(3 * 86400, t0=10.0, drop_land_seed=None,
+                                  lat_bounds=(lat.min(), lat.max()), lon_bounds=(lon.min(), lon.max()), **syn.SARAL)
+        n_chain = 1500
+    res = syn.grid_resolution_deg(lon)
+    rd, r = syn.search_params(res)
+    mask = syn.land_mask(lat, lon)
+    with gzb.GridContext(lat, lon, mask=mask, k_ew_per=kew) as ctx:
+        ang = ctx.grid_angle()
+        NP, SM, WB = ctx.mapping(y, x, rd, r)
+        n = min(n_chain, len(y))
+        want = orc.nearest_chain(y[:n], x[:n], lat, lon, kew, rd, r)
+        _report_index_mismatch("NP", NP[:n], want)
+        idx = np.sort(np.random.default_rng(0).choice(len(y), size=min(3000, len(y)), replace=False))
+        sm = orc.source_meshes(y, x, lat, lon, NP, kew, angle=ang, idx=idx)
+        _report_index_mismatch("SM", SM[idx], sm)
+        wb = orc.weights(y, x, lat, lon, sm, idx=idx)
+        np.testing.assert_allclose(WB[idx], wb, rtol=RTOL, atol=ATOL)
+        nrec = 4
+        tmod = np.linspace(0.0, t[-1] + 100.0, nrec)
+        fld = syn.ssh_records(lat, lon, nrec)
+        v_np, v_bl = ctx.interp(t, SM, WB, tmod, fld)
+        o_np, o_bl = orc.interp_track(t[idx], tmod, lambda k: fld[k], mask, SM[idx], WB[idx])
+        np.testing.assert_allclose(v_bl[idx], o_bl, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(v_np[idx], o_np, rtol=RTOL, atol=ATOL)
+        d = ctx.track_distance(y[:5000], x[:5000])
+        np.testing.assert_allclose(d, orc.along_track_distance(y[:5000], x[:5000]), rtol=1e-9)
