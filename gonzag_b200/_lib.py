@@ -40,6 +40,7 @@ _SIGNATURES = {
     "gzb_destroy": (C.c_int, [_P]),
     "gzb_last_error": (C.c_char_p, [_P]),
     "gzb_set_stream": (C.c_int, [_P, _P]),
+    "gzb_use_own_stream": (C.c_int, [_P]),
     "gzb_sync": (C.c_int, [_P]),
     "gzb_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "gzb_set_mask": (C.c_int, [_P, _P, C.c_int]),

@@ -108,7 +108,11 @@ class GridContext:
         self.k_ew_per = int(k)
 
     def set_stream(self, cuda_stream_ptr):
+        """Run on a caller-provided cudaStream_t (0 / None = the legacy default stream)."""
         self._ck(L.lib().gzb_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr)) if cuda_stream_ptr else None))
+
+    def use_own_stream(self):
+        self._ck(L.lib().gzb_use_own_stream(self._h))
 
     def sync(self):
         self._ck(L.lib().gzb_sync(self._h))

@@ -340,7 +340,13 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
 
 extern "C" int gzb_set_stream(gzb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_set_stream: null ctx");
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return GZB_OK;
+}
+
+extern "C" int gzb_use_own_stream(gzb_ctx* ctx) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_use_own_stream: null ctx");
+    ctx->stream = ctx->own_stream;
     return GZB_OK;
 }
 

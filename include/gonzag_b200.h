@@ -63,7 +63,8 @@ int gzb_create(int device, int64_t nj, int64_t ni, const double* lat, const doub
                gzb_ctx** ctx_out);
 int gzb_destroy(gzb_ctx* ctx);
 const char* gzb_last_error(const gzb_ctx* ctx);
-int gzb_set_stream(gzb_ctx* ctx, void* cuda_stream);      /* NULL -> context's own stream */
+int gzb_set_stream(gzb_ctx* ctx, void* cuda_stream);      /* a cudaStream_t; NULL = the legacy default stream */
+int gzb_use_own_stream(gzb_ctx* ctx);                      /* back to the context's private stream (the default) */
 int gzb_sync(gzb_ctx* ctx);
 int gzb_get_stats(const gzb_ctx* ctx, gzb_stats* out);
 int gzb_set_mask(gzb_ctx* ctx, const int8_t* mask, int where);
