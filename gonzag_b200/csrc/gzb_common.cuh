@@ -22,8 +22,10 @@
 // bj x bi nodes of level l-1.  Nodes of a level are stored "parent-blocked": the (up to) 32
 // children of a parent are contiguous (one warp loads them with one coalesced request), at
 // index parent_rowmajor_id*32 + slot.  The top level has <= 32 nodes and is stored row-major.
+// The pyramid is fp32: it only PROPOSES candidate cells (with explicit error margins, see
+// gzb_nearest.cu); every candidate is then compared with the reference's fp64 haversine.
 struct GzbLevel {
-    double4* nodes;   // (cx, cy, cz, chord radius); radius < 0 marks an empty slot
+    float4* nodes;    // (cx, cy, cz, chord radius, rounded up); radius < 0 marks an empty slot
     int nJ, nI;       // logical node counts
     int bj, bi;       // branching of THIS level's nodes over their children
     int sJ, sI;       // cells covered by one node in j and i
@@ -36,7 +38,9 @@ struct GzbGrid {
     const double* lon;
     const double* angle;    // may be null
     const int8_t* mask;     // may be null
-    const double* cells;    // per leaf tile: x[32] y[32] z[32] (unit vectors), tile row-major
+    const float* cells;     // per leaf tile: x[32] y[32] z[32] (unit vectors), tile row-major
+    const float* cert;      // per leaf tile (same index as its node): chord distance from the tile
+                            // centre to the nearest cell outside the tile's 5x3-tile neighbourhood
     int nlev;
     GzbLevel lev[GZB_MAXLEV];
 };
@@ -58,8 +62,9 @@ struct gzb_ctx {
     double* d_lon = nullptr;
     double* d_angle = nullptr;
     int8_t* d_mask = nullptr;
-    double* d_cells = nullptr;
-    double4* d_nodes[GZB_MAXLEV] = {};
+    float* d_cells = nullptr;
+    float4* d_nodes[GZB_MAXLEV] = {};
+    float* d_cert = nullptr;
     GzbArena arena;
     void* pinned = nullptr;          // small pinned scratch for status words
     size_t pinned_cap = 0;
@@ -187,13 +192,17 @@ __device__ __forceinline__ void gzb_alfabeta_dev(const double* yin, const double
     beta = b;
 }
 
-// warp-wide minimum of a non-negative double (or +inf): two REDUX on the hi/lo words
-__device__ __forceinline__ double gzb_warp_min_nonneg(double v) {
-    unsigned hi = (unsigned)__double2hiint(v);
-    unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-    unsigned lo = (hi == mhi) ? (unsigned)__double2loint(v) : 0xffffffffu;
-    unsigned mlo = __reduce_min_sync(0xffffffffu, lo);
-    return __hiloint2double((int)mhi, (int)mlo);
+// warp-wide minimum of a non-negative float (or +inf): one REDUX on the bit pattern
+__device__ __forceinline__ float gzb_warp_min_nonneg(float v) {
+    return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+
+// index of leaf tile (tJ, tI) in the level-0 node array (and in GzbGrid::cert)
+__device__ __forceinline__ long long gzb_leaf_index(const GzbGrid& g, int tJ, int tI) {
+    if (g.nlev == 1) return (long long)tJ * g.lev[0].nI + tI;
+    const GzbLevel& P = g.lev[1];
+    const int pJ = tJ / P.bj, pI = tI / P.bi;
+    return ((long long)pJ * P.nI + pI) * 32 + (tJ - pJ * P.bj) * P.bi + (tI - pI * P.bi);
 }
 
 #endif  // __CUDACC__

@@ -77,9 +77,17 @@ void* gzb_arena_take(gzb_ctx* ctx, size_t bytes) {
 }
 
 // ======================================================================== pyramid build
+int gzb_build_cert(gzb_ctx* ctx);   // gzb_nearest.cu
+
+// fp32 storage of a sphere computed in fp64: the radius is rounded up and padded by 2.5e-7 so
+// that it still bounds the members after the centre itself was rounded to float
+__device__ __forceinline__ float4 pack_sphere(double cx, double cy, double cz, double r) {
+    return make_float4((float)cx, (float)cy, (float)cz, __double2float_ru(r + 2.5e-7));
+}
+
 // One warp per leaf tile: unit vectors of its 32 cells + the tile's bounding sphere.
 __global__ void __launch_bounds__(256)
-k_build_leaves(GzbGrid g, double* __restrict__ cells, double4* __restrict__ nodes0, int top_is_leaf) {
+k_build_leaves(GzbGrid g, float* __restrict__ cells, float4* __restrict__ nodes0) {
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const GzbLevel L0 = g.lev[0];
@@ -98,10 +106,10 @@ k_build_leaves(GzbGrid g, double* __restrict__ cells, double4* __restrict__ node
         y = cl * sin(lo);
         z = sin(la);
     }
-    double* c = cells + tile * 96;
-    c[lane] = ok ? x : 1.0e3;
-    c[32 + lane] = ok ? y : 1.0e3;
-    c[64 + lane] = ok ? z : 1.0e3;
+    float* c = cells + tile * 96;
+    c[lane] = ok ? (float)x : 1.0e3f;
+    c[32 + lane] = ok ? (float)y : 1.0e3f;
+    c[64 + lane] = ok ? (float)z : 1.0e3f;
     // centre = normalised mean of the valid cells
     double sx = x, sy = y, sz = z;
 #pragma unroll
@@ -126,17 +134,7 @@ k_build_leaves(GzbGrid g, double* __restrict__ cells, double4* __restrict__ node
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
     r = r * (1.0 + 1.0e-12) + 1.0e-15;
-    if (lane == 0) {
-        int64_t idx;
-        if (top_is_leaf) {
-            idx = tile;
-        } else {
-            const GzbLevel L1 = g.lev[1];
-            const int pJ = tJ / L1.bj, pI = tI / L1.bi;
-            idx = ((int64_t)pJ * L1.nI + pI) * 32 + (tJ % L1.bj) * L1.bi + (tI % L1.bi);
-        }
-        nodes0[idx] = make_double4(cx, cy, cz, r);
-    }
+    if (lane == 0) nodes0[gzb_leaf_index(g, tJ, tI)] = pack_sphere(cx, cy, cz, r);
 }
 
 // One warp per node of level `l` (l >= 1): sphere around its (up to 32) children.
@@ -148,9 +146,10 @@ k_build_level(GzbGrid g, int l, int is_top) {
     const int64_t nn = (int64_t)L.nJ * L.nI;
     if (node >= nn) return;
     const int J = (int)(node / L.nI), I = (int)(node % L.nI);
-    const double4 ch = g.lev[l - 1].nodes[node * 32 + lane];
-    const bool ok = ch.w >= 0.0;
-    double sx = ok ? ch.x : 0.0, sy = ok ? ch.y : 0.0, sz = ok ? ch.z : 0.0;
+    const float4 chf = g.lev[l - 1].nodes[node * 32 + lane];
+    const bool ok = chf.w >= 0.0f;
+    const double chx = chf.x, chy = chf.y, chz = chf.z, chw = chf.w;
+    double sx = ok ? chx : 0.0, sy = ok ? chy : 0.0, sz = ok ? chz : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sx += __shfl_xor_sync(0xffffffffu, sx, o);
@@ -161,16 +160,16 @@ k_build_level(GzbGrid g, int l, int is_top) {
     const unsigned okm = __ballot_sync(0xffffffffu, ok);
     if (!(nrm > 1.0e-6)) {
         const int f = __ffs(okm) - 1;
-        sx = __shfl_sync(0xffffffffu, ch.x, f);
-        sy = __shfl_sync(0xffffffffu, ch.y, f);
-        sz = __shfl_sync(0xffffffffu, ch.z, f);
+        sx = __shfl_sync(0xffffffffu, chx, f);
+        sy = __shfl_sync(0xffffffffu, chy, f);
+        sz = __shfl_sync(0xffffffffu, chz, f);
         nrm = 1.0;
     }
     const double cx = sx / nrm, cy = sy / nrm, cz = sz / nrm;
     double r = 0.0;
     if (ok) {
-        const double dx = ch.x - cx, dy = ch.y - cy, dz = ch.z - cz;
-        r = sqrt(dx * dx + dy * dy + dz * dz) + ch.w;
+        const double dx = chx - cx, dy = chy - cy, dz = chz - cz;
+        r = sqrt(dx * dx + dy * dy + dz * dz) + chw;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
@@ -184,13 +183,13 @@ k_build_level(GzbGrid g, int l, int is_top) {
             const int pJ = J / P.bj, pI = I / P.bi;
             idx = ((int64_t)pJ * P.nI + pI) * 32 + (J % P.bj) * P.bi + (I % P.bi);
         }
-        L.nodes[idx] = make_double4(cx, cy, cz, r);
+        L.nodes[idx] = pack_sphere(cx, cy, cz, r);
     }
 }
 
-__global__ void k_fill_empty(double4* p, int64_t n) {
+__global__ void k_fill_empty(float4* p, int64_t n) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) p[k] = make_double4(0.0, 0.0, 0.0, -1.0);
+    if (k < n) p[k] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
 }
 
 static int build_pyramid(gzb_ctx* ctx) {
@@ -218,24 +217,28 @@ static int build_pyramid(gzb_ctx* ctx) {
     ctx->stats.pyramid_levels = g.nlev;
     // storage
     const int64_t ntile = (int64_t)g.lev[0].nJ * g.lev[0].nI;
-    GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_cells, (size_t)ntile * 96 * sizeof(double)));
+    GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_cells, (size_t)ntile * 96 * sizeof(float)));
     g.cells = ctx->d_cells;
     for (int k = 0; k < g.nlev; ++k) {
         int64_t n = (k == g.nlev - 1) ? 32 : (int64_t)g.lev[k + 1].nJ * g.lev[k + 1].nI * 32;
-        GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_nodes[k], (size_t)n * sizeof(double4)));
+        GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_nodes[k], (size_t)n * sizeof(float4)));
         g.lev[k].nodes = ctx->d_nodes[k];
         k_fill_empty<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_nodes[k], n);
         GZB_LAUNCH_CHECK(ctx);
+        if (k == 0) {
+            GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_cert, (size_t)n * sizeof(float)));
+            GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_cert, 0, (size_t)n * sizeof(float), ctx->stream));
+            g.cert = ctx->d_cert;
+        }
     }
-    k_build_leaves<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cells, ctx->d_nodes[0],
-                                                                       g.nlev == 1 ? 1 : 0);
+    k_build_leaves<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cells, ctx->d_nodes[0]);
     GZB_LAUNCH_CHECK(ctx);
     for (int k = 1; k < g.nlev; ++k) {
         const int64_t nn = (int64_t)g.lev[k].nJ * g.lev[k].nI;
         k_build_level<<<(unsigned)((nn + 7) / 8), 256, 0, ctx->stream>>>(g, k, k == g.nlev - 1 ? 1 : 0);
         GZB_LAUNCH_CHECK(ctx);
     }
-    return GZB_OK;
+    return gzb_build_cert(ctx);
 }
 
 // ======================================================================== create / destroy
@@ -324,6 +327,7 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     cudaFree(ctx->d_angle);
     cudaFree(ctx->d_mask);
     cudaFree(ctx->d_cells);
+    cudaFree(ctx->d_cert);
     for (int k = 0; k < GZB_MAXLEV; ++k) cudaFree(ctx->d_nodes[k]);
     cudaFree(ctx->arena.base);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

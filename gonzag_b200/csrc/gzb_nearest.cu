@@ -3,74 +3,165 @@
 // (gonzag/bilin_mapping.py:144-191 NearestPoint, :566-593 BilinTrack.nrpt).
 //
 // Decomposition:
-//   K1b k_global   - exact global first-index haversine argmin G(t) for every point, one warp
-//                    per point: best-first descent of the bounding-sphere pyramid (coarse to
-//                    fine), 32 nodes / 32 cells per step, warp REDUX for the minima; only
-//                    cells whose chord^2 proxy ties the best one are evaluated with the
-//                    reference's own haversine formula in fp64.
-//   K1c k_flags    - speculative chain: R(t) = E(t) (edge-excluded, threshold-accepted G(t))
-//                    whenever G(t) lies inside the search box of E(t-1); the other points are
-//                    "breaks".
-//        k_walk    - one warp per break replays the reference's recurrence
-//                    R(t) = F_t(R(t-1)) with the true box-restricted search (K1a: the
-//                    (2r+1)^2 window, clamped not wrapped, accepted iff d < r0) until the
-//                    chain rejoins the speculative one; k_valid discards replays whose own
-//                    starting assumption was overwritten by an earlier replay.
+//   k_global   exact global first-index haversine argmin G(t) of every point.  A warp owns a
+//              chunk of consecutive track points and walks it in order:
+//                K1a  continuity-seeded local window: the 5x3 leaf tiles (20x24 cells) around
+//                     the previous point's tile; 32 cells per step, warp REDUX for the minimum;
+//                     a precomputed per-tile certificate (distance from the tile centre to the
+//                     nearest cell OUTSIDE the window) proves the local minimum is global;
+//                K1b  when the certificate fails (track jump, E-W seam, first point of a
+//                     chunk): coarse-to-fine best-first descent of the bounding-sphere pyramid
+//                     over the whole grid.
+//              Both work on fp32 unit vectors and only PROPOSE cells: every cell whose chord
+//              is within the fp32 error margin of the best one is then evaluated with the
+//              reference's own fp64 haversine formula (32 candidates at a time, one per lane)
+//              and the winner is the lexicographic minimum (distance, row-major index), i.e.
+//              numpy.argmin's first occurrence.
+//   k_flags    speculative chain: R(t) = E(t) (edge-excluded, threshold-accepted G(t)) whenever
+//              G(t) lies inside the search box of E(t-1); the other points are "breaks".
+//   k_walk     K1c: one warp per break replays the reference's recurrence R(t) = F_t(R(t-1))
+//              with the true box-restricted search (the (2r+1)^2 window, clamped not wrapped,
+//              accepted iff d < r0) until the chain rejoins the speculative one; k_valid
+//              discards replays whose own starting assumption was overwritten by an earlier one.
 #include "gzb_common.cuh"
 
 #define GZB_NOFLAT 0x7fffffffffffffffLL
+#define GZB_QCAP 64
 
-struct WarpScratch {
+// search modes
+#define M_GLOBAL 0   // whole grid
+#define M_BOX 1      // only cells inside the index box
+#define M_EXCL 2     // only cells outside the index box, proxies only (certificate build)
+
+struct WarpSm {
     int fJ[GZB_MAXLEV + 1];
     int fI[GZB_MAXLEV + 1];
     unsigned fmask[GZB_MAXLEV + 1];
     int pad;
-    long long cflat[32];
-    double cprox[32];
+    int qpt[GZB_QCAP];
+    float qP[GZB_QCAP];
+    long long qflat[GZB_QCAP];
+    unsigned long long bd[32];   // per owned point: bits of the best exact distance
+    long long bf[32];            // ... and the smallest flat index achieving it
+    float pb2[32];               // ... and the current candidate bound (chord^2)
+};
+
+struct Srch {          // warp-uniform state of the search for one point
+    float px, py, pz;  // target unit vector
+    float Pmin;        // smallest chord^2 seen (fp32 proxy)
+    float B, B2;       // candidate / pruning bound on the chord and its square
+    int bJ, bI;        // leaf tile holding the best proxy
+};
+
+struct Owner {         // the point a lane owns (exact evaluation needs its coordinates)
+    double plat, plon, cpl;
 };
 
 struct NearParams {
     double r0;         // rd_found_km
     double thr2;       // fl(1.2*fl(1.2*r0)): acceptance radius of the last useful global pass
-    double prox_r0;    // chord^2 bound that contains every cell with d < r0
+    float prox_r0;     // chord^2 bound that contains every cell with d < r0
     double chord_r0;   // chord length of r0 (with margin)
     int r;             // np_box_r
     long long seed_j, seed_i;
     const double* corner;   // bounding sphere (cx,cy,cz,rho) of the box of predecessor (-1,-1)
 };
 
-// ------------------------------------------------------------------------------------------
-// Warp-cooperative exact nearest-cell search over the whole grid or a clamped index box.
-// Returns the minimum reference distance and, among equal distances, the smallest row-major
-// flat index (numpy.argmin's first occurrence).  `bound0` is an upper bound on the chord^2 of
-// acceptable cells (+inf for the global search).
-template <bool BOXED>
-__device__ __forceinline__ void warp_search(const GzbGrid& g, WarpScratch& ws, const int lane,
-                                            const double plat, const double plon,
-                                            const long long j0, const long long j1,
-                                            const long long i0, const long long i1,
-                                            const double bound0, double& out_d, long long& out_flat) {
-    const double la = plat * GZB_D2R, lo = plon * GZB_D2R;
-    const double cpl = cos(la);
-    const double px = cpl * cos(lo), py = cpl * sin(lo), pz = sin(la);
-    double best = bound0;
-    double bnd = best * (1.0 + 1.0e-7) + 1.0e-24;
-    double my_d = INFINITY;
-    long long my_flat = GZB_NOFLAT;
-    int ncand = 0;
+// fp32 error budget (see DESIGN.md "K1 numerics"): a stored coordinate is within 6e-8 of the
+// fp64 one, so a computed chord D differs from the true chord c by at most 3e-7*D + 3e-7.
+// Every cell whose true chord is within 1e-9 relative of the best is kept as a candidate if the
+// bound is  B = Dmin*(1+2e-6) + 2e-6  (chord units; 2e-6 is 12.7 m on the ground).
+__device__ __forceinline__ void set_bound(Srch& s, float pm) {
+    s.Pmin = pm;
+    s.B = sqrtf(pm) * (1.0f + 2.0e-6f) + 2.0e-6f;
+    s.B2 = s.B * s.B;
+}
 
-    auto flush = [&]() {
-        if (lane < ncand && ws.cprox[lane] <= bnd) {
-            const long long f = ws.cflat[lane];
-            const double d = gzb_haversine_dev(plat, plon, cpl, g.lat[f], g.lon[f]);
-            if (d < my_d || (d == my_d && f < my_flat)) { my_d = d; my_flat = f; }
+__device__ __forceinline__ void srch_init(Srch& s, float px, float py, float pz) {
+    s.px = px; s.py = py; s.pz = pz;
+    s.Pmin = INFINITY; s.B = INFINITY; s.B2 = INFINITY;
+    s.bJ = -1; s.bI = -1;
+}
+
+// exact evaluation of the queued candidates, 32 at a time, and per-point lexicographic minimum
+__device__ __forceinline__ void flush_queue(const GzbGrid& g, WarpSm& w, const int lane, int& qn, const Owner& me) {
+    __syncwarp();
+    for (int base = 0; base < qn; base += 32) {
+        const int e = base + lane;
+        bool act = e < qn;
+        const int pt = act ? w.qpt[e] : 0;
+        const double plat = __shfl_sync(0xffffffffu, me.plat, pt);
+        const double plon = __shfl_sync(0xffffffffu, me.plon, pt);
+        const double cpl = __shfl_sync(0xffffffffu, me.cpl, pt);
+        act = act && (w.qP[e] <= w.pb2[pt]);
+        unsigned long long dbits = ~0ull, pre = 0ull;
+        long long flat = 0;
+        if (act) {
+            flat = w.qflat[e];
+            const double d = gzb_haversine_dev(plat, plon, cpl, g.lat[flat], g.lon[flat]);
+            if (d == d) dbits = (unsigned long long)__double_as_longlong(d); else act = false;
         }
-        ncand = 0;
+        if (act) pre = w.bd[pt];
         __syncwarp();
-    };
+        if (act) atomicMin(&w.bd[pt], dbits);
+        __syncwarp();
+        const bool holder = act && (w.bd[pt] == dbits);
+        if (holder && dbits < pre) w.bf[pt] = GZB_NOFLAT;
+        __syncwarp();
+        if (holder) atomicMin(&w.bf[pt], flat);
+        __syncwarp();
+    }
+    qn = 0;
+}
 
+// 32 cells of leaf tile (tJ, tI), one per lane
+template <int MODE>
+__device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
+                                          const int tJ, const int tI, const long long j0, const long long j1,
+                                          const long long i0, const long long i1, int& qn, const Owner& me) {
+    const float* __restrict__ cc = g.cells + ((long long)tJ * g.lev[0].nI + tI) * 96;
+    const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
+    const long long j = (long long)tJ * GZB_TILE_J + (lane >> 3);
+    const long long i = (long long)tI * GZB_TILE_I + (lane & 7);
+    bool ok = (j < g.Nj) && (i < g.Ni);
+    if (MODE != M_GLOBAL) {
+        const bool inside = (j >= j0) && (j < j1) && (i >= i0) && (i < i1);
+        ok = ok && (MODE == M_BOX ? inside : !inside);
+    }
+    const float dx = s.px - x, dy = s.py - y, dz = s.pz - z;
+    const float P = dx * dx + dy * dy + dz * dz;
+    const float pm = gzb_warp_min_nonneg(ok ? P : INFINITY);
+    if (pm < s.Pmin) {
+        set_bound(s, pm);
+        s.bJ = tJ;
+        s.bI = tI;
+        if (MODE != M_EXCL && lane == 0) w.pb2[pt] = s.B2;
+    }
+    if (MODE != M_EXCL) {
+        const bool cand = ok && (P <= s.B2);
+        const unsigned cm = __ballot_sync(0xffffffffu, cand);
+        const int nnew = __popc(cm);
+        if (nnew) {
+            if (qn + nnew > GZB_QCAP) flush_queue(g, w, lane, qn, me);
+            if (cand) {
+                const int pos = qn + __popc(cm & ((1u << lane) - 1u));
+                w.qpt[pos] = pt;
+                w.qP[pos] = P;
+                w.qflat[pos] = j * g.Ni + i;
+            }
+            qn += nnew;
+        }
+        __syncwarp();
+    }
+}
+
+// K1b: best-first descent of the pyramid, pruned by the running bound s.B
+template <int MODE>
+__device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
+                                               const long long j0, const long long j1, const long long i0,
+                                               const long long i1, int& qn, const Owner& me) {
     int depth = 0;
-    if (lane == 0) ws.fmask[0] = 0xffffffffu;
+    if (lane == 0) w.fmask[0] = 0xffffffffu;
     __syncwarp();
     while (depth >= 0) {
         const int cl = g.nlev - 1 - depth;   // level of this frame's children
@@ -83,107 +174,170 @@ __device__ __forceinline__ void warp_search(const GzbGrid& g, WarpScratch& ws, c
             cI = lane - cJ * L.nI;
         } else {
             const GzbLevel P = g.lev[cl + 1];
-            J = ws.fJ[depth];
-            I = ws.fI[depth];
+            J = w.fJ[depth];
+            I = w.fI[depth];
             base = ((long long)J * P.nI + I) * 32;
             const int a = lane / P.bi;
             cJ = J * P.bj + a;
             cI = I * P.bi + (lane - a * P.bi);
         }
-        const double4 nd = L.nodes[base + lane];
-        bool keep = ((ws.fmask[depth] >> lane) & 1u) && (nd.w >= 0.0);
-        if (BOXED && keep) {
+        const float4 nd = L.nodes[base + lane];
+        bool keep = ((w.fmask[depth] >> lane) & 1u) && (nd.w >= 0.0f);
+        if (MODE != M_GLOBAL && keep) {
             const long long a0 = (long long)cJ * L.sJ, b0 = (long long)cI * L.sI;
-            keep = (a0 < j1) && (a0 + L.sJ > j0) && (b0 < i1) && (b0 + L.sI > i0);
+            if (MODE == M_BOX) keep = (a0 < j1) && (a0 + L.sJ > j0) && (b0 < i1) && (b0 + L.sI > i0);
+            else keep = !((a0 >= j0) && (a0 + L.sJ <= j1) && (b0 >= i0) && (b0 + L.sI <= i1));
         }
-        double lb2 = 0.0;
-        if (keep) {
-            const double dx = px - nd.x, dy = py - nd.y, dz = pz - nd.z;
-            const double lb = sqrt(dx * dx + dy * dy + dz * dz) - nd.w;
-            lb2 = lb > 0.0 ? lb * lb : 0.0;
-            keep = lb2 <= bnd;
-        }
+        const float dx = s.px - nd.x, dy = s.py - nd.y, dz = s.pz - nd.z;
+        const float dn2 = dx * dx + dy * dy + dz * dz;
+        const float lim = nd.w + s.B;
+        keep = keep && (dn2 <= lim * lim);
         unsigned m = __ballot_sync(0xffffffffu, keep);
         if (m == 0u) {
             --depth;
             continue;
         }
-        const unsigned key = keep ? ((__float_as_uint((float)lb2) & 0xffffffe0u) | (unsigned)lane) : 0xffffffffu;
+        const unsigned key = keep ? ((__float_as_uint(dn2) & 0xffffffe0u) | (unsigned)lane) : 0xffffffffu;
         const int c = (int)(__reduce_min_sync(0xffffffffu, key) & 31u);
         m &= ~(1u << c);
         const int sJ = __shfl_sync(0xffffffffu, cJ, c);
         const int sI = __shfl_sync(0xffffffffu, cI, c);
         __syncwarp();
-        if (lane == 0) ws.fmask[depth] = m;
+        if (lane == 0) w.fmask[depth] = m;
         if (cl > 0) {
             ++depth;
             if (lane == 0) {
-                ws.fJ[depth] = sJ;
-                ws.fI[depth] = sI;
-                ws.fmask[depth] = 0xffffffffu;
+                w.fJ[depth] = sJ;
+                w.fI[depth] = sI;
+                w.fmask[depth] = 0xffffffffu;
             }
             __syncwarp();
         } else {
-            // leaf tile (sJ, sI): 32 cells, one per lane
-            const double* __restrict__ cc = g.cells + ((long long)sJ * L.nI + sI) * 96;
-            const double x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
-            const long long j = (long long)sJ * GZB_TILE_J + (lane >> 3);
-            const long long i = (long long)sI * GZB_TILE_I + (lane & 7);
-            bool ok = (j < g.Nj) && (i < g.Ni);
-            if (BOXED) ok = ok && (j >= j0) && (j < j1) && (i >= i0) && (i < i1);
-            const double dx = px - x, dy = py - y, dz = pz - z;
-            const double prox = dx * dx + dy * dy + dz * dz;
-            const double pm = gzb_warp_min_nonneg(ok ? prox : INFINITY);
-            if (pm < best) {
-                best = pm;
-                bnd = best * (1.0 + 1.0e-7) + 1.0e-24;
-            }
-            const bool cand = ok && (prox <= bnd);
-            const unsigned cm = __ballot_sync(0xffffffffu, cand);
-            const int nnew = __popc(cm);
-            if (nnew) {
-                if (ncand + nnew > 32) flush();
-                if (cand) {
-                    const int pos = ncand + __popc(cm & ((1u << lane) - 1u));
-                    ws.cflat[pos] = j * g.Ni + i;
-                    ws.cprox[pos] = prox;
-                }
-                ncand += nnew;
-            }
+            leaf_eval<MODE>(g, w, lane, s, pt, sJ, sI, j0, j1, i0, i1, qn, me);
             __syncwarp();
         }
     }
-    flush();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double d2 = __shfl_xor_sync(0xffffffffu, my_d, o);
-        const long long f2 = __shfl_xor_sync(0xffffffffu, my_flat, o);
-        if (d2 < my_d || (d2 == my_d && f2 < my_flat)) { my_d = d2; my_flat = f2; }
+}
+
+// K1a: the 5x3-tile window around tile (sJ, sI); returns true when the certificate proves that
+// no cell outside the window can tie or beat the best cell found inside it
+#define NBJ 2
+#define NBI 1
+__device__ __forceinline__ bool window_search(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
+                                              const int sJ, const int sI, int& qn, const Owner& me) {
+    const GzbLevel& L0 = g.lev[0];
+    const int nJ = sJ + lane / (2 * NBI + 1) - NBJ;
+    const int nI = sI + lane % (2 * NBI + 1) - NBI;
+    const bool nv = (lane < (2 * NBJ + 1) * (2 * NBI + 1)) && nJ >= 0 && nJ < L0.nJ && nI >= 0 && nI < L0.nI;
+    const long long nidx = nv ? gzb_leaf_index(g, nJ, nI) : 0;
+    const int centre = NBJ * (2 * NBI + 1) + NBI;
+    float4 nd = make_float4(0.f, 0.f, 0.f, -1.f);
+    float gc = 0.f;
+    if (nv) nd = L0.nodes[nidx];
+    if (lane == centre) gc = g.cert[nidx];
+    const float dx = s.px - nd.x, dy = s.py - nd.y, dz = s.pz - nd.z;
+    const float dn2 = dx * dx + dy * dy + dz * dz;
+    unsigned pending = __ballot_sync(0xffffffffu, nv && nd.w >= 0.0f);
+    for (;;) {
+        const float lim = nd.w + s.B;
+        const bool keep = ((pending >> lane) & 1u) && (dn2 <= lim * lim);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m == 0u) break;
+        const unsigned key = keep ? ((__float_as_uint(dn2) & 0xffffffe0u) | (unsigned)lane) : 0xffffffffu;
+        const int c = (int)(__reduce_min_sync(0xffffffffu, key) & 31u);
+        pending &= ~(1u << c);
+        leaf_eval<M_GLOBAL>(g, w, lane, s, pt, __shfl_sync(0xffffffffu, nJ, c), __shfl_sync(0xffffffffu, nI, c),
+                            0, 0, 0, 0, qn, me);
     }
-    out_d = my_d;
-    out_flat = my_flat;
+    const float a = sqrtf(__shfl_sync(0xffffffffu, dn2, centre));
+    const float gcert = __shfl_sync(0xffffffffu, gc, centre);
+    return (gcert - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (s.B + 1.0e-6f);
+}
+
+__device__ __forceinline__ void owner_point(const double lat, const double lon, Owner& me, float& px, float& py,
+                                            float& pz) {
+    const double la = lat * GZB_D2R, lo = lon * GZB_D2R;
+    me.plat = lat;
+    me.plon = lon;
+    me.cpl = cos(la);
+    px = (float)(me.cpl * cos(lo));
+    py = (float)(me.cpl * sin(lo));
+    pz = (float)sin(la);
 }
 
 // ------------------------------------------------------------------------------------------
-// K1b: global nearest point of every track point.
+// global nearest point of every track point; a warp owns K (<= 32) consecutive points
 __global__ void __launch_bounds__(256)
 k_global(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-         long long* __restrict__ G, double* __restrict__ dG) {
-    __shared__ WarpScratch ws[8];
+         long long* __restrict__ G, double* __restrict__ dG, const int K) {
+    __shared__ WarpSm ws[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (long long base = (long long)blockIdx.x * 32; base < nt; base += (long long)gridDim.x * 32) {
-        for (int q = warp; q < 32; q += 8) {
-            const long long t = base + q;
-            if (t >= nt) break;
-            double d;
-            long long f;
-            warp_search<false>(g, ws[warp], lane, yt[t], xt[t], 0, g.Nj, 0, g.Ni, INFINITY, d, f);
-            if (lane == 0) {
-                G[t] = f;
-                dG[t] = d;
-            }
+    WarpSm& w = ws[warp];
+    const long long nchunk = (nt + K - 1) / K;
+    for (long long ch = (long long)blockIdx.x * 8 + warp; ch < nchunk; ch += (long long)gridDim.x * 8) {
+        const long long t0 = ch * K;
+        const int n = (int)((nt - t0 < K) ? (nt - t0) : K);
+        Owner me;
+        float mpx = 0.f, mpy = 0.f, mpz = 0.f;
+        me.plat = me.plon = me.cpl = 0.0;
+        if (lane < n) owner_point(yt[t0 + lane], xt[t0 + lane], me, mpx, mpy, mpz);
+        w.bd[lane] = ~0ull;
+        w.bf[lane] = GZB_NOFLAT;
+        w.pb2[lane] = INFINITY;
+        __syncwarp();
+        int qn = 0;
+        int sJ = -1, sI = -1;
+        for (int q = 0; q < n; ++q) {
+            Srch s;
+            srch_init(s, __shfl_sync(0xffffffffu, mpx, q), __shfl_sync(0xffffffffu, mpy, q),
+                      __shfl_sync(0xffffffffu, mpz, q));
+            bool proven = false;
+            if (sJ >= 0) proven = window_search(g, w, lane, s, q, sJ, sI, qn, me);
+            if (!proven) pyramid_search<M_GLOBAL>(g, w, lane, s, q, 0, 0, 0, 0, qn, me);
+            sJ = s.bJ;
+            sI = s.bI;
         }
+        flush_queue(g, w, lane, qn, me);
+        if (lane < n) {
+            G[t0 + lane] = w.bf[lane];
+            dG[t0 + lane] = __longlong_as_double((long long)w.bd[lane]);
+        }
+        __syncwarp();
     }
+}
+
+// certificate of every leaf tile: chord from its centre to the nearest cell outside its window
+__global__ void __launch_bounds__(256)
+k_cert(const GzbGrid g, float* __restrict__ cert) {
+    __shared__ WarpSm ws[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GzbLevel L0 = g.lev[0];
+    const long long ntile = (long long)L0.nJ * L0.nI;
+    const long long tile = (long long)blockIdx.x * 8 + warp;
+    if (tile >= ntile) return;
+    const int tJ = (int)(tile / L0.nI), tI = (int)(tile - (long long)tJ * L0.nI);
+    const long long idx = gzb_leaf_index(g, tJ, tI);
+    const float4 nd = L0.nodes[idx];
+    Srch s;
+    srch_init(s, nd.x, nd.y, nd.z);
+    Owner me;
+    me.plat = me.plon = me.cpl = 0.0;
+    int qn = 0;
+    pyramid_search<M_EXCL>(g, ws[warp], lane, s, 0, (long long)(tJ - NBJ) * GZB_TILE_J,
+                           (long long)(tJ + NBJ + 1) * GZB_TILE_J, (long long)(tI - NBI) * GZB_TILE_I,
+                           (long long)(tI + NBI + 1) * GZB_TILE_I, qn, me);
+    if (lane == 0) {
+        float gval = INFINITY;
+        if (s.Pmin < INFINITY) gval = fmaxf((sqrtf(s.Pmin) - 5.0e-7f) * (1.0f - 1.0e-6f), 0.0f);
+        cert[idx] = gval;
+    }
+}
+
+int gzb_build_cert(gzb_ctx* ctx) {
+    const long long ntile = (long long)ctx->g.lev[0].nJ * ctx->g.lev[0].nI;
+    k_cert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(ctx->g, ctx->d_cert);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
 }
 
 // threshold acceptance of the global hit + the edge exclusion of BilinTrack.nrpt
@@ -276,13 +430,13 @@ k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, c
         if (lane == 31) wsum[warp] = s;
         __syncthreads();
         if (warp == 0) {
-            long long w = wsum[lane];
+            long long ww = wsum[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const long long u = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += u;
+                const long long u = __shfl_up_sync(0xffffffffu, ww, o);
+                if (lane >= o) ww += u;
             }
-            wsum[lane] = w;
+            wsum[lane] = ww;
         }
         __syncthreads();
         const long long pre = carry + (warp ? wsum[warp - 1] : 0) + s - v;
@@ -306,21 +460,21 @@ k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ o
     if (lane == 0) wcnt[warp] = __popc(m);
     __syncthreads();
     if (warp == 0) {
-        int w = wcnt[lane];
-        int s = w;
+        int ww = wcnt[lane];
+        int s = ww;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += u;
         }
-        wcnt[lane] = s - w;
+        wcnt[lane] = s - ww;
     }
     __syncthreads();
     if (b) breaks[offsets[blockIdx.x] + wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = t;
 }
 
-// one step of the reference recurrence: R(t) = F_t(pred)
-__device__ __forceinline__ void chain_step(const GzbGrid& g, WarpScratch& ws, const int lane, const NearParams& p,
+// one step of the reference recurrence: R(t) = F_t(pred).  All lanes hold the same point.
+__device__ __forceinline__ void chain_step(const GzbGrid& g, WarpSm& w, const int lane, const NearParams& p,
                                            const long long t, const long long pj, const long long pi,
                                            const double* __restrict__ yt, const double* __restrict__ xt,
                                            const long long ej, const long long ei, long long& rj, long long& ri) {
@@ -329,9 +483,24 @@ __device__ __forceinline__ void chain_step(const GzbGrid& g, WarpScratch& ws, co
     if (pj != 0 && pi != 0) {
         long long j0, j1, i0, i1;
         if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
-            double d;
-            long long f;
-            warp_search<true>(g, ws, lane, yt[t], xt[t], j0, j1, i0, i1, p.prox_r0, d, f);
+            Owner me;
+            float px, py, pz;
+            owner_point(yt[t], xt[t], me, px, py, pz);
+            Srch s;
+            srch_init(s, px, py, pz);
+            set_bound(s, p.prox_r0);
+            if (lane == 0) {
+                w.bd[0] = ~0ull;
+                w.bf[0] = GZB_NOFLAT;
+                w.pb2[0] = s.B2;
+            }
+            __syncwarp();
+            int qn = 0;
+            pyramid_search<M_BOX>(g, w, lane, s, 0, j0, j1, i0, i1, qn, me);
+            flush_queue(g, w, lane, qn, me);
+            const long long f = w.bf[0];
+            const double d = __longlong_as_double((long long)w.bd[0]);
+            __syncwarp();
             if (f != GZB_NOFLAT && d < p.r0) accept_edge(g, f, d, INFINITY, rj, ri);
         }
     }
@@ -346,7 +515,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
        const long long* __restrict__ breaks, const long long* __restrict__ nbrk_p,
        long long* __restrict__ stop, long long* __restrict__ first, const unsigned char* __restrict__ valid,
        long long* __restrict__ NP, unsigned long long* __restrict__ steps) {
-    __shared__ WarpScratch ws[8];
+    __shared__ WarpSm ws[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nb = *nbrk_p;
     const long long nwarps = (long long)gridDim.x * 8;
@@ -533,7 +702,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     p.thr2 = t2;
     const double half = r0 / (2.0 * 6360.0);
     const double sn = sin(half < 1.5 ? half : 1.5);
-    p.prox_r0 = 4.0 * sn * sn * (1.0 + 1.0e-6) + 1.0e-24;
+    p.prox_r0 = (float)(4.0 * sn * sn * (1.0 + 1.0e-5) + 1.0e-20);
     p.chord_r0 = 2.0 * sn * (1.0 + 1.0e-6) + 1.0e-12;
     p.r = np_box_r;
     p.seed_j = seed_j;
@@ -546,10 +715,13 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
 
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    long long gblocks = (long long)((n + 31) / 32);
-    const long long gmax = (long long)nsm * 8 * 4;
+    // chunk length: long enough to amortise the unseeded first point, short enough to fill the GPU
+    int K = 32;
+    while (K > 4 && (long long)((n + K - 1) / K) < (long long)nsm * 8 * 4) K >>= 1;
+    long long gblocks = (long long)(((n + K - 1) / K + 7) / 8);
+    const long long gmax = (long long)nsm * 16;
     if (gblocks > gmax) gblocks = gmax;
-    k_global<<<(unsigned)gblocks, 256, 0, s>>>(ctx->g, nt, yt, xt, G, dG);
+    k_global<<<(unsigned)gblocks, 256, 0, s>>>(ctx->g, nt, yt, xt, G, dG, K);
     GZB_LAUNCH_CHECK(ctx);
     k_flags<<<(unsigned)nblk, 1024, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, (long long*)np_out, brk, counts);
     GZB_LAUNCH_CHECK(ctx);
