@@ -1,0 +1,107 @@
+"""CPU-only tests: the C ABI library loads and exports what include/gonzag_b200.h declares,
+the host-side planning logic, and the failure mode without a GPU (no CPU fallback)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+from gonzag_b200 import _lib as L
+from gonzag_b200 import synthetic as syn
+from gonzag_b200.mod2sat import plan_slabs
+from gonzag_b200.multi import segment_bounds
+
+
+@pytest.fixture(scope="module")
+def built():
+    from gonzag_b200 import build
+    return build.build()
+
+
+def test_library_exports_header_symbols(built):
+    lib = ctypes.CDLL(built)
+    syms = ge.header_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert sorted(L.exported_symbols()) == syms        # the ctypes binding covers the whole header
+    assert b"sm_100a" in L.lib().gzb_version()
+
+
+def test_sass_is_sm100a(built):
+    out = os.popen("cuobjdump -lelf %s 2>/dev/null" % built).read()
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(built):
+    import gonzag_b200 as gzb
+    if gzb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    lat, lon = syn.regional_grid(8, 9)
+    with pytest.raises(gzb.GonzagB200Error) as e:
+        gzb.GridContext(lat, lon)
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(gzb.GonzagB200Error):
+        gzb.BilinTrack(np.zeros(3), np.zeros(3), lat, lon)
+
+
+def test_argument_validation(built):
+    import gonzag_b200 as gzb
+    lat, lon = syn.regional_grid(8, 9)
+    with pytest.raises(ValueError):
+        gzb.GridContext(lat, lon[:, :-1])
+    bad = lat.copy()
+    bad[2, 2] = np.nan
+    with pytest.raises(ValueError):
+        gzb.GridContext(bad, lon)
+    # C-level checks do not need a device
+    h = ctypes.c_void_p()
+    rc = L.lib().gzb_create(0, 2, 2, L.ptr(lat), L.ptr(lon), None, None, -1, ctypes.byref(h))
+    assert rc == L.GZB_ERR_ARG and h.value is None
+    assert L.lib().gzb_sync(None) == L.GZB_ERR_ARG
+    assert L.lib().gzb_destroy(None) == L.GZB_OK
+
+
+def test_plan_slabs():
+    tmod = 3600.0 * np.arange(10)
+    t = np.array([10.0, 20.0, 3599.0, 3600.0, 7300.0, 30000.0, 30001.0])
+    assert plan_slabs(t, tmod, 100) == [(0, 3), (8, 9)]
+    assert plan_slabs(t, tmod, 2) == [(0, 1), (1, 2), (2, 3), (8, 9)]
+    assert plan_slabs(t[:3], tmod, 3) == [(0, 1)]
+    assert plan_slabs(np.array([]), tmod, 3) == []
+    with pytest.raises(ValueError):
+        plan_slabs(np.array([-1.0]), tmod, 3)
+    with pytest.raises(ValueError):
+        plan_slabs(np.array([9 * 3600.0]), tmod, 3)      # the last record time is excluded
+    # every bracket [k, k+1] of every point lies inside one slab
+    rng = np.random.default_rng(0)
+    t = np.sort(rng.uniform(0, 9 * 3600.0 - 1, 500))
+    for cap in (2, 3, 5, 64):
+        slabs = plan_slabs(t, tmod, cap)
+        kt = np.searchsorted(tmod, t, side="right") - 1
+        for k in kt:
+            assert any(a <= k and k + 1 <= b for a, b in slabs)
+        assert all(b - a + 1 <= cap for a, b in slabs)
+
+
+def test_segment_bounds():
+    assert segment_bounds(10, 3) == [0, 4, 7, 10]
+    assert segment_bounds(2, 4) == [0, 1, 2, 2, 2]
+    b = segment_bounds(1000003, 8)
+    assert b[0] == 0 and b[-1] == 1000003 and max(np.diff(b)) - min(np.diff(b)) <= 1
+
+
+def test_synthetic_inputs_have_the_advertised_shape():
+    lat, lon = syn.orca_like_grid(146, 182)
+    assert lat.shape == (146, 182)
+    np.testing.assert_array_equal(lat[:, 0], lat[:, -2])      # exact E-W overlap copies
+    np.testing.assert_array_equal(lon[:, -1], lon[:, 1])
+    assert lon.min() >= 0.0 and lon.max() < 360.0
+    m = syn.land_mask(lat, lon)
+    assert m.dtype == np.int64 and m[0, 0] == 0 and 0.1 < 1.0 - m.mean() < 0.6
+    t, y, x = syn.orbit_track(20000, **syn.JASON)
+    assert np.all(np.diff(t) > 0) and np.abs(y).max() < 66.1 and len(t) < 20000   # land gaps
+    rd, r = syn.search_params(1.0 / 12.0)
+    assert r == 26 or r == 27
+    assert abs(rd - 0.75 * 111.11 / 12.0) < 1e-9

@@ -1,0 +1,96 @@
+"""World-size-2 test of the multi-GPU driver on CPU (gloo): segmentation, the halo / seed
+hand-off between segments and the final gather.  The compute engine is the CPU oracle plugged
+into the driver's engine interface -- test infrastructure only; the product engine is CUDA."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gonzag_b200 import synthetic as syn
+from gonzag_b200.multi import ShardedMapper, segment_bounds
+from oracle import gz_oracle as orc
+
+
+class OracleEngine:
+    """Same interface as gonzag_b200.multi.CudaEngine, backed by the oracle (tests only)."""
+
+    def __init__(self, lat, lon, kew):
+        self.lat, self.lon, self.kew = lat, lon, kew
+        self.torch = torch
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype)
+
+    def nearest(self, y, x, rd, r, seed, out):
+        res = orc.nearest_chain(y.numpy(), x.numpy(), self.lat, self.lon, self.kew, rd, r, seed=tuple(seed))
+        out.copy_(torch.from_numpy(res))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _case():
+    lat, lon = syn.orca_like_grid(146, 182)
+    res = syn.grid_resolution_deg(lon)
+    rd, r = syn.search_params(res)
+    rng = np.random.default_rng(21)
+    n = 240
+    s = np.linspace(0.0, 1.0, n)
+    # a seam-hugging leg: chain deviations are long, so a segment boundary falls inside one
+    y = -60.0 + 120.0 * s + rng.normal(0, 0.02, n)
+    x = np.mod(356.5 + 6.0 * s + rng.normal(0, 0.02, n), 360.0)
+    return lat, lon, rd, r, y, x
+
+
+def _worker(rank, world, port, cut, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lat, lon, rd, r, y, x = _case()
+        bounds = [0, cut, len(y)] if cut is not None else segment_bounds(len(y), world)
+        s0, s1 = bounds[rank], bounds[rank + 1]
+        halo = rank > 0
+        h0 = s0 - 1 if halo else s0
+        m = ShardedMapper(OracleEngine(lat, lon, 2), dist, torch)
+        NP = m.nearest_segment(torch.from_numpy(y[h0:s1].copy()), torch.from_numpy(x[h0:s1].copy()), halo, rd, r)
+        (full,) = m.gather([NP], bounds)
+        q.put((rank, full.numpy(), m.reseeds))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cut", [None, "inside_chain"])
+def test_two_ranks_match_single_chain(cut):
+    lat, lon, rd, r, y, x = _case()
+    want = orc.nearest_chain(y, x, lat, lon, 2, rd, r)
+    cut_at = None
+    if cut == "inside_chain":
+        # put the boundary where the sequential answer differs from the plain global answer
+        dev = np.where((want != np.array([orc.edge_exclusion(*orc.nearest_point((y[t], x[t]), lat, lon, rd), *lat.shape, 2)
+                                          for t in range(len(y))])).any(axis=1))[0]
+        assert dev.size > 3, "the test track must contain a chain deviation"
+        cut_at = int(dev[len(dev) // 2]) + 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(rk, 2, port, cut_at, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, full, reseeds in got:
+        np.testing.assert_array_equal(full, want)
+    if cut == "inside_chain":
+        assert max(rs for _, _, rs in got) >= 1      # the hand-off really had to re-seed rank 1
