@@ -422,6 +422,7 @@ def run_ours(args, w):
             torch.cuda.synchronize()
             dt_ = time.perf_counter() - t0
             stats = R.stats
+            timing = R.timing
             if it > 0:
                 e2e_s.append(dt_)
         t_e2e = float(np.mean(e2e_s))
@@ -432,7 +433,8 @@ def run_ours(args, w):
         e2e = {"value": nt_total / t_e2e, "unit": "points/s", "h2d_bytes_per_step": int(stats["h2d_bytes"]),
                "d2h_bytes_per_step": int(stats["d2h_bytes"]), "ms_per_step": t_e2e * 1e3,
                "api": "gonzag_b200.Model2SatTrack(MG, name, ST, name) with host NumPy inputs, model records in pinned host memory",
-               "gpu_launches_per_step": int(stats["kernel_launches"])}
+               "gpu_launches_per_step": int(stats["kernel_launches"]),
+               "breakdown_s": {k: round(v, 5) for k, v in timing.items()}}
         L.pinned_free(host_field)
 
     # ---- CPU baseline (oracle port), rank 0 at N=1 only
@@ -461,7 +463,8 @@ def run_ours(args, w):
                            "np_box_r": r, "rd_found_km": rd, "k_ew_per": 2,
                            "sharding": "contiguous time segments, grid replicated, 1 all-gather of (ssh_np, ssh_bl, NP)",
                            "l2": "flushed (256 MiB write) before every timed step and stage",
-                           "seed_reseeds": mapper.reseeds},
+                           "seed_reseeds": mapper.reseeds, "chain_breaks": int(ctx.stats()["last_breaks"]),
+                           "chain_replay_steps": int(ctx.stats()["last_chain_steps"])},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "kernels": kern,
                 "cpu_baseline": cpu, "e2e": e2e}
         print(json.dumps(line), flush=True)

@@ -42,8 +42,6 @@ class GridContext:
         Xs = L.as_f64(Xs)
         if Ys.ndim != 2 or Ys.shape != Xs.shape:
             raise ValueError("Ys and Xs must be 2-D arrays of the same shape")
-        if not (np.isfinite(Ys).all() and np.isfinite(Xs).all()):
-            raise ValueError("grid coordinates must be finite")
         self.Nj, self.Ni = Ys.shape
         self.device = int(device)
         self._h = None
@@ -83,7 +81,9 @@ class GridContext:
         m = np.asarray(np.ma.getdata(mask))
         if m.shape != (self.Nj, self.Ni):
             raise ValueError("mask has shape %s, grid is %s" % (m.shape, (self.Nj, self.Ni)))
-        return np.ascontiguousarray(np.clip(m, -128, 127).astype(np.int8))
+        if m.dtype in (np.int8, np.uint8, np.bool_):
+            return np.ascontiguousarray(m).view(np.int8)
+        return np.ascontiguousarray(m.astype(np.int8))     # a {0,1} land-sea mask (gonzag/ncio.py:164-191)
 
     def _ck(self, code):
         L.check(code, self._h)
@@ -106,6 +106,9 @@ class GridContext:
     def set_ew_per(self, k):
         self._ck(L.lib().gzb_set_ew_per(self._h, int(k)))
         self.k_ew_per = int(k)
+
+    def set_option(self, name, value):
+        self._ck(L.lib().gzb_set_option(self._h, name.encode(), int(value)))
 
     def set_stream(self, cuda_stream_ptr):
         """Run on a caller-provided cudaStream_t (0 / None = the legacy default stream)."""

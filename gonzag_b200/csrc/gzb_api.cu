@@ -89,11 +89,6 @@ int run_stages(gzb_ctx* ctx, int stages, int64_t nt, const double* yt, const dou
             ctx->stats.d2h_bytes += n * 32;
         }
         GZB_CUDA(ctx, cudaStreamSynchronize(s));
-        if (stages & ST_NP) {
-            const long long* w = (const long long*)ctx->pinned;
-            ctx->stats.last_breaks = w[0];
-            ctx->stats.last_chain_steps = w[1];
-        }
     }
     return GZB_OK;
 }

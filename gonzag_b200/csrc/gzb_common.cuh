@@ -27,7 +27,8 @@
 struct GzbLevel {
     float4* nodes;    // (cx, cy, cz, chord radius, rounded up); radius < 0 marks an empty slot
     int nJ, nI;       // logical node counts
-    int bj, bi;       // branching of THIS level's nodes over their children
+    int bj, bi;       // branching of THIS level's nodes over their children (powers of two)
+    int sbj, sbi;     // log2(bj), log2(bi)
     int sJ, sI;       // cells covered by one node in j and i
 };
 
@@ -70,6 +71,8 @@ struct gzb_ctx {
     size_t pinned_cap = 0;
     void* stage[2] = {nullptr, nullptr};   // pinned staging for pageable field slabs
     size_t stage_cap = 0;
+    int nearest_stats_pending = 0;
+    int zero_copy = 1;               // gather from pinned+mapped host slabs instead of copying them
     // corner-box bounding sphere cache (predecessor == (-1,-1)), keyed by np_box_r
     int corner_r = -1;
     double corner[4] = {0, 0, 0, -1};
@@ -201,8 +204,8 @@ __device__ __forceinline__ float gzb_warp_min_nonneg(float v) {
 __device__ __forceinline__ long long gzb_leaf_index(const GzbGrid& g, int tJ, int tI) {
     if (g.nlev == 1) return (long long)tJ * g.lev[0].nI + tI;
     const GzbLevel& P = g.lev[1];
-    const int pJ = tJ / P.bj, pI = tI / P.bi;
-    return ((long long)pJ * P.nI + pI) * 32 + (tJ - pJ * P.bj) * P.bi + (tI - pI * P.bi);
+    const int pJ = tJ >> P.sbj, pI = tI >> P.sbi;
+    return ((long long)pJ * P.nI + pI) * 32 + ((tJ - (pJ << P.sbj)) << P.sbi) + (tI - (pI << P.sbi));
 }
 
 #endif  // __CUDACC__

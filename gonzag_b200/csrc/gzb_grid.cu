@@ -87,7 +87,7 @@ __device__ __forceinline__ float4 pack_sphere(double cx, double cy, double cz, d
 
 // One warp per leaf tile: unit vectors of its 32 cells + the tile's bounding sphere.
 __global__ void __launch_bounds__(256)
-k_build_leaves(GzbGrid g, float* __restrict__ cells, float4* __restrict__ nodes0) {
+k_build_leaves(GzbGrid g, float* __restrict__ cells, float4* __restrict__ nodes0, int* __restrict__ bad) {
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const GzbLevel L0 = g.lev[0];
@@ -105,6 +105,7 @@ k_build_leaves(GzbGrid g, float* __restrict__ cells, float4* __restrict__ nodes0
         x = cl * cos(lo);
         y = cl * sin(lo);
         z = sin(la);
+        if (!(isfinite(la) && isfinite(lo))) atomicOr(bad, 1);
     }
     float* c = cells + tile * 96;
     c[lane] = ok ? (float)x : 1.0e3f;
@@ -202,11 +203,15 @@ static int build_pyramid(gzb_ctx* ctx) {
     g.lev[0].bi = GZB_TILE_I;
     g.lev[0].sJ = GZB_TILE_J;
     g.lev[0].sI = GZB_TILE_I;
+    g.lev[0].sbj = 2;
+    g.lev[0].sbi = 3;
     while ((int64_t)g.lev[l].nJ * g.lev[l].nI > 32) {
         if (l + 1 >= GZB_MAXLEV) return gzb_fail(ctx, GZB_ERR_ARG, "grid too large for %d pyramid levels", GZB_MAXLEV);
         GzbLevel& P = g.lev[l + 1];
         P.bj = ((l + 1) & 1) ? 8 : 4;
         P.bi = ((l + 1) & 1) ? 4 : 8;
+        P.sbj = ((l + 1) & 1) ? 3 : 2;
+        P.sbi = ((l + 1) & 1) ? 2 : 3;
         P.nJ = (g.lev[l].nJ + P.bj - 1) / P.bj;
         P.nI = (g.lev[l].nI + P.bi - 1) / P.bi;
         P.sJ = g.lev[l].sJ * P.bj;
@@ -231,8 +236,13 @@ static int build_pyramid(gzb_ctx* ctx) {
             g.cert = ctx->d_cert;
         }
     }
-    k_build_leaves<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cells, ctx->d_nodes[0]);
+    int* d_bad = (int*)ctx->d_cert;     // the certificate array is filled last; borrow its first word
+    k_build_leaves<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cells, ctx->d_nodes[0], d_bad);
     GZB_LAUNCH_CHECK(ctx);
+    GZB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 128, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(int*)((char*)ctx->pinned + 128)) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_create: grid coordinates must be finite");
+    GZB_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
     for (int k = 1; k < g.nlev; ++k) {
         const int64_t nn = (int64_t)g.lev[k].nJ * g.lev[k].nI;
         k_build_level<<<(unsigned)((nn + 7) / 8), 256, 0, ctx->stream>>>(g, k, k == g.nlev - 1 ? 1 : 0);
@@ -249,7 +259,7 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
     *ctx_out = nullptr;
     if (nj < 3 || ni < 3 || !lat || !lon)
         return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: need lat/lon of shape (nj>=3, ni>=3)");
-    if (nj * ni > (int64_t)1 << 40) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: grid too large");
+    if (nj * ni > ((int64_t)1 << 36) - 2 || nj > 0x3fffffff || ni > 0x3fffffff) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: grid too large");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -361,10 +371,25 @@ extern "C" int gzb_sync(gzb_ctx* ctx) {
     return GZB_OK;
 }
 
-extern "C" int gzb_get_stats(const gzb_ctx* ctx, gzb_stats* out) {
+extern "C" int gzb_get_stats(const gzb_ctx* ctx_c, gzb_stats* out) {
+    gzb_ctx* ctx = const_cast<gzb_ctx*>(ctx_c);
     if (!ctx || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_get_stats: null argument");
+    if (ctx->nearest_stats_pending) {      // the words were copied asynchronously by gzb_nearest
+        if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const long long* w = (const long long*)ctx->pinned;
+        ctx->stats.last_breaks = w[0];
+        ctx->stats.last_chain_steps = w[1];
+        ctx->nearest_stats_pending = 0;
+    }
     *out = ctx->stats;
     return GZB_OK;
+}
+
+extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: null argument");
+    if (!strcmp(name, "zero_copy")) { ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
+    return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: unknown option '%s'", name);
 }
 
 extern "C" int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per) {

@@ -100,9 +100,19 @@ extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64
     // where does the field slab live?  (independent of `where`)
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, slab);
-    if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; }
-    const bool slab_on_device = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) || nk == 0;
+    if (e != cudaSuccess) { cudaGetLastError(); at.type = cudaMemoryTypeUnregistered; at.devicePointer = nullptr; }
+    bool slab_on_device = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) || nk == 0;
     const bool slab_pinned = (at.type == cudaMemoryTypeHost);
+    // Sparse gather straight from pinned + mapped host memory: a track touches 8 values per point
+    // in records of Nj*Ni values, so when the sectors the kernel would read (<= 8 x 32 B per point)
+    // are a small fraction of the slab, reading them over PCIe beats copying the slab to HBM.
+    const void* slab_dev = slab;
+    if (!slab_on_device && slab_pinned && at.devicePointer && ctx->zero_copy &&
+        (ctx->zero_copy == 2 || (double)nt * 256.0 * 4.0 < (double)nk * (double)rec_bytes)) {
+        slab_dev = at.devicePointer;
+        slab_on_device = true;
+        ctx->stats.h2d_bytes += (uint64_t)nt * 8 * 32;     // upper bound of what crosses PCIe: 8 sectors per point
+    }
 
     // chunking of a host slab: consecutive chunks share one record
     int64_t C = nk;
@@ -147,7 +157,7 @@ extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64
 
     int rc = GZB_OK;
     if (slab_on_device) {
-        rc = interp_chunk(ctx, dtype, nt, d_t, (const int64_t*)d_sm, d_wb, nrec, d_tmod, slab, k0, nk, rmissval,
+        rc = interp_chunk(ctx, dtype, nt, d_t, (const int64_t*)d_sm, d_wb, nrec, d_tmod, slab_dev, k0, nk, rmissval,
                           init_outputs, d_np, d_bl, d_err);
         if (rc != GZB_OK) return rc;
     } else {
@@ -205,7 +215,7 @@ extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64
         GZB_CUDA(ctx, cudaMemcpyAsync(bl_out, d_bl, n * 8, cudaMemcpyDeviceToHost, s));
         ctx->stats.d2h_bytes += n * 16;
     }
-    if (where == GZB_HOST || !slab_on_device) {
+    if (where == GZB_HOST || !slab_on_device || slab_dev != slab) {
         GZB_CUDA(ctx, cudaStreamSynchronize(s));
         if (*h_err) {
             *h_err = 0;

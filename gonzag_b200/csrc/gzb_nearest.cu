@@ -123,10 +123,11 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
     const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
     const long long j = (long long)tJ * GZB_TILE_J + (lane >> 3);
     const long long i = (long long)tI * GZB_TILE_I + (lane & 7);
-    bool ok = (j < g.Nj) && (i < g.Ni);
+    // padded cells of edge tiles are stored at (1e3,1e3,1e3): chord^2 ~ 3e6, never a candidate
+    bool ok = true;
     if (MODE != M_GLOBAL) {
         const bool inside = (j >= j0) && (j < j1) && (i >= i0) && (i < i1);
-        ok = ok && (MODE == M_BOX ? inside : !inside);
+        ok = (j < g.Nj) && (i < g.Ni) && (MODE == M_BOX ? inside : !inside);
     }
     const float dx = s.px - x, dy = s.py - y, dz = s.pz - z;
     const float P = dx * dx + dy * dy + dz * dz;
@@ -177,9 +178,9 @@ __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, cons
             J = w.fJ[depth];
             I = w.fI[depth];
             base = ((long long)J * P.nI + I) * 32;
-            const int a = lane / P.bi;
-            cJ = J * P.bj + a;
-            cI = I * P.bi + (lane - a * P.bi);
+            const int a = lane >> P.sbi;
+            cJ = (J << P.sbj) + a;
+            cI = (I << P.sbi) + (lane - (a << P.sbi));
         }
         const float4 nd = L.nodes[base + lane];
         bool keep = ((w.fmask[depth] >> lane) & 1u) && (nd.w >= 0.0f);
@@ -223,8 +224,10 @@ __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, cons
 // no cell outside the window can tie or beat the best cell found inside it
 #define NBJ 2
 #define NBI 1
+template <int MODE>
 __device__ __forceinline__ bool window_search(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
-                                              const int sJ, const int sI, int& qn, const Owner& me) {
+                                              const int sJ, const int sI, const long long j0, const long long j1,
+                                              const long long i0, const long long i1, int& qn, const Owner& me) {
     const GzbLevel& L0 = g.lev[0];
     const int nJ = sJ + lane / (2 * NBI + 1) - NBJ;
     const int nI = sI + lane % (2 * NBI + 1) - NBI;
@@ -246,8 +249,8 @@ __device__ __forceinline__ bool window_search(const GzbGrid& g, WarpSm& w, const
         const unsigned key = keep ? ((__float_as_uint(dn2) & 0xffffffe0u) | (unsigned)lane) : 0xffffffffu;
         const int c = (int)(__reduce_min_sync(0xffffffffu, key) & 31u);
         pending &= ~(1u << c);
-        leaf_eval<M_GLOBAL>(g, w, lane, s, pt, __shfl_sync(0xffffffffu, nJ, c), __shfl_sync(0xffffffffu, nI, c),
-                            0, 0, 0, 0, qn, me);
+        leaf_eval<MODE>(g, w, lane, s, pt, __shfl_sync(0xffffffffu, nJ, c), __shfl_sync(0xffffffffu, nI, c),
+                        j0, j1, i0, i1, qn, me);
     }
     const float a = sqrtf(__shfl_sync(0xffffffffu, dn2, centre));
     const float gcert = __shfl_sync(0xffffffffu, gc, centre);
@@ -292,7 +295,7 @@ k_global(const GzbGrid g, const long long nt, const double* __restrict__ yt, con
             srch_init(s, __shfl_sync(0xffffffffu, mpx, q), __shfl_sync(0xffffffffu, mpy, q),
                       __shfl_sync(0xffffffffu, mpz, q));
             bool proven = false;
-            if (sJ >= 0) proven = window_search(g, w, lane, s, q, sJ, sI, qn, me);
+            if (sJ >= 0) proven = window_search<M_GLOBAL>(g, w, lane, s, q, sJ, sI, 0, 0, 0, 0, qn, me);
             if (!proven) pyramid_search<M_GLOBAL>(g, w, lane, s, q, 0, 0, 0, 0, qn, me);
             sJ = s.bJ;
             sI = s.bI;
@@ -496,7 +499,10 @@ __device__ __forceinline__ void chain_step(const GzbGrid& g, WarpSm& w, const in
             }
             __syncwarp();
             int qn = 0;
-            pyramid_search<M_BOX>(g, w, lane, s, 0, j0, j1, i0, i1, qn, me);
+            bool proven = false;
+            if (pj > 0 && pi > 0)      // continuity: the window around the predecessor's tile
+                proven = window_search<M_BOX>(g, w, lane, s, 0, (int)(pj >> 2), (int)(pi >> 3), j0, j1, i0, i1, qn, me);
+            if (!proven) pyramid_search<M_BOX>(g, w, lane, s, 0, j0, j1, i0, i1, qn, me);
             flush_queue(g, w, lane, qn, me);
             const long long f = w.bf[0];
             const double d = __longlong_as_double((long long)w.bd[0]);
@@ -507,14 +513,19 @@ __device__ __forceinline__ void chain_step(const GzbGrid& g, WarpSm& w, const in
 }
 
 // K1c, step 2/4: chain replay, one warp per break.  WRITE=false records where the replay
-// rejoins the speculative chain; WRITE=true (valid replays only) stores the results.
+// rejoins the speculative chain and logs every replayed value tagged with the replay's id
+// (one 64-bit word per point: id in the high 27 bits, flat index + 1 in the low 36); WRITE=true
+// (valid replays only) copies the logged values, 32 per step, and replays again only if another
+// (discarded) replay overwrote part of its log.
+#define WLOG_TAG(k) ((unsigned long long)(((k) + 1) & 0x7ffffffLL) << 36)
+
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
 k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
        const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
        const long long* __restrict__ breaks, const long long* __restrict__ nbrk_p,
        long long* __restrict__ stop, long long* __restrict__ first, const unsigned char* __restrict__ valid,
-       long long* __restrict__ NP, unsigned long long* __restrict__ steps) {
+       unsigned long long* __restrict__ wlog, long long* __restrict__ NP, unsigned long long* __restrict__ steps) {
     __shared__ WarpSm ws[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nb = *nbrk_p;
@@ -523,13 +534,33 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
         const long long b = breaks[k];
         if (WRITE) {
             if (!valid[k]) continue;
-            if (stop[k] == b) {
+            const long long e = stop[k];
+            if (e == b) {
                 if (lane == 0) {
                     NP[2 * b] = first[2 * k];
                     NP[2 * b + 1] = first[2 * k + 1];
                 }
                 continue;
             }
+            // copy from the log
+            bool clobbered = false;
+            for (long long t0 = b; t0 <= e; t0 += 32) {
+                const long long t = t0 + lane;
+                bool bad = false;
+                if (t <= e) {
+                    const unsigned long long v = wlog[t];
+                    if ((v >> 36) != (WLOG_TAG(k) >> 36)) {
+                        bad = true;
+                    } else {
+                        const long long f = (long long)(v & 0xfffffffffULL) - 1;
+                        const long long j = f < 0 ? -1 : f / g.Ni;
+                        NP[2 * t] = j;
+                        NP[2 * t + 1] = f < 0 ? -1 : f - j * g.Ni;
+                    }
+                }
+                if (__any_sync(0xffffffffu, bad)) clobbered = true;
+            }
+            if (!clobbered) continue;
         }
         long long pj, pi;
         if (b == 0) {
@@ -552,9 +583,12 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                 }
                 if (t >= stop[k]) break;
             } else {
-                if (t == b && lane == 0) {
-                    first[2 * k] = rj;
-                    first[2 * k + 1] = ri;
+                if (lane == 0) {
+                    wlog[t] = WLOG_TAG(k) | (unsigned long long)(rj < 0 ? 0 : rj * g.Ni + ri + 1);
+                    if (t == b) {
+                        first[2 * k] = rj;
+                        first[2 * k + 1] = ri;
+                    }
                 }
                 if ((rj == ej && ri == ei) || t + 1 >= nt) {
                     if (lane == 0) stop[k] = t;
@@ -670,6 +704,7 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
            + gzb_align(n * 8) * 2    // breaks, stop
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
+           + gzb_align(n * 8)        // replay log
            + gzb_align(64) * 2;      // scalars, corner
 }
 
@@ -689,6 +724,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     long long* stop = (long long*)gzb_arena_take(ctx, n * 8);
     long long* first = (long long*)gzb_arena_take(ctx, n * 16);
     unsigned char* valid = (unsigned char*)gzb_arena_take(ctx, n);
+    unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
     long long* scal = (long long*)gzb_arena_take(ctx, 64);
     double* corner = (double*)gzb_arena_take(ctx, 64);
     if (!corner) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
@@ -733,14 +769,15 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     const long long wmax = (long long)nsm * 8;
     if (wblocks > wmax) wblocks = wmax;
     k_walk<false><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
-                                                   valid, (long long*)np_out, (unsigned long long*)(scal + 1));
+                                                   valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));
     GZB_LAUNCH_CHECK(ctx);
     k_valid<<<1, 32, 0, s>>>(breaks, stop, scal, valid);
     GZB_LAUNCH_CHECK(ctx);
     k_walk<true><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
-                                                  valid, (long long*)np_out, (unsigned long long*)(scal + 1));
+                                                  valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));
     GZB_LAUNCH_CHECK(ctx);
     // stats: (breaks, chain steps) -> pinned words, read by gzb_get_stats after a sync
     GZB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, scal, 16, cudaMemcpyDeviceToHost, s));
+    ctx->nearest_stats_pending = 1;
     return GZB_OK;
 }

@@ -80,7 +80,9 @@ class Model2SatTrack:
         lib = L.lib()
 
         own_ctx = ctx is None
+        tim = {}
         t0 = time.time()
+        tc = time.perf_counter()
         if ctx is None:
             ang = MG.xangle if np.shape(getattr(MG, "xangle", ())) == (Nj, Ni) else None
             ctx = GridContext(MG.lat, MG.lon, angle=ang, mask=MG.mask, k_ew_per=MG.EWPer, device=device)
@@ -88,6 +90,8 @@ class Model2SatTrack:
             ctx.set_mask(MG.mask)
         h = ctx._h
         ck = ctx._ck
+        tim["context_s"] = time.perf_counter() - tc
+        tc = time.perf_counter()
 
         # ---- track to the device, once
         yt = L.as_f64(ST.lat)
@@ -107,6 +111,8 @@ class Model2SatTrack:
                            int(np_box_radius), int(np_box_radius), P(d_np), P(d_sm), P(d_wb), L.GZB_DEVICE))
         ctx.sync()
         time_bl_mapping = time.time() - t0
+        tim["mapping_s"] = time.perf_counter() - tc
+        tc = time.perf_counter()
 
         # ---- space-time interpolation: K4 over slabs of records                 (mod2sat.py:86-139)
         t0 = time.time()
@@ -148,6 +154,9 @@ class Model2SatTrack:
         if first and Nt > 0:   # no slab at all cannot happen (plan_slabs raises), kept for safety
             raise RuntimeError("no model record brackets the track")
 
+        ctx.sync()
+        tim["interp_s"] = time.perf_counter() - tc
+        tc = time.perf_counter()
         # ---- distance and nearest-point map                                      (mod2sat.py:146-148, 177-184)
         d_dist = ctx.dev_alloc(Nt * 8)
         ck(lib.gzb_track_distance(h, Nt, P(d_y), P(d_x), P(d_dist), L.GZB_DEVICE))
@@ -166,6 +175,8 @@ class Model2SatTrack:
                                   ctx.download(d_wb, (Nt, 4), np.float64))
         for b in (d_y, d_x, d_t, d_tm, d_np, d_sm, d_wb, d_vnp, d_vbl, d_dist):
             b.free()
+        tim["outputs_s"] = time.perf_counter() - tc
+        tc = time.perf_counter()
 
         # ---- satellite SSH and the output conventions (API packaging, host)      (mod2sat.py:151-168)
         ssh_attr = getattr(ST, "ssh", None)
@@ -185,7 +196,9 @@ class Model2SatTrack:
         self.ssh_sat = np.ma.masked_where(imask == 0, vssh_s)
         self.distance = vdistance
         if xnp is not None:
-            self.XNPtrack = np.ma.masked_where(xnp == config.rmissval, xnp)
+            self.XNPtrack = np.ma.MaskedArray(xnp, mask=(xnp == config.rmissval), copy=False)
+        tim["packaging_s"] = time.perf_counter() - tc
+        self.timing = tim
         self.time_bl_mapping = time_bl_mapping
         self.time_bl_interp = time_bl_interp
         self.stats = ctx.stats()

@@ -70,6 +70,10 @@ int gzb_get_stats(const gzb_ctx* ctx, gzb_stats* out);
 int gzb_set_mask(gzb_ctx* ctx, const int8_t* mask, int where);
 int gzb_set_angle(gzb_ctx* ctx, const double* angle_or_null, int where);
 int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
+/* options: "zero_copy": 1 (default) gzb_interp gathers straight from a pinned + mapped host slab
+ * over PCIe when the track is sparse w.r.t. the slab, instead of copying the slab to the GPU;
+ * 0 never; 2 whenever the slab is pinned + mapped. */
+int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value);
 
 /* ---- K0: local grid rotation, the `-D` pre-pass --------------------------------------------
  * Replaces GridAngle(xlat, xlon) (gonzag/utils.py:226-262).  Computes the (nj,ni) angle in
@@ -113,6 +117,9 @@ int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
  * slab: records [k0, k0+nk) of the model field, (nk,nj,ni) of `dtype` (GZB_F32 / GZB_F64);
  * points whose bracketing records both lie in the slab are written, the others are left
  * untouched, so a caller streams a long series by looping over slabs (never over points).
+ * `slab` may be a device pointer, a pinned host pointer or a pageable host pointer whatever
+ * `where` says (detected): device slabs are used in place, host slabs are gathered over PCIe
+ * (pinned + mapped, sparse track) or streamed through the GPU in 256 MiB chunks.
  * init_outputs != 0 first fills np_out/bl_out with rmissval (do it on the first slab).
  * Needs a mask in the context.  Points outside [tmod[0], tmod[nrec-1]) -> GZB_ERR_TIME. */
 int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,

@@ -140,6 +140,27 @@ def test_regional(golden_regional):
     bt.close()
 
 
+def test_pinned_slab_zero_copy(golden_regional):
+    """A pinned + mapped host slab is gathered over PCIe without a copy: same bits as streaming."""
+    from gonzag_b200 import _lib as L
+    g = golden_regional
+    lat, lon = _grid(g)
+    with gzb.GridContext(lat, lon, mask=g["mask"]) as ctx:
+        NP, SM, WB = ctx.mapping(g["ysat"], g["xsat"], float(g["rd"]), int(g["r"]))
+        ref = ctx.interp(g["tsat"], SM, WB, g["tmod"], g["f32"])
+        pin = L.pinned_empty(g["f32"].shape, np.float32)
+        pin[...] = g["f32"]
+        ctx.set_option("zero_copy", 2)
+        got = ctx.interp(g["tsat"], SM, WB, g["tmod"], pin)
+        ctx.set_option("zero_copy", 0)
+        got2 = ctx.interp(g["tsat"], SM, WB, g["tmod"], pin)
+        L.pinned_free(pin)
+    np.testing.assert_array_equal(got[0], ref[0])
+    np.testing.assert_array_equal(got[1], ref[1])
+    np.testing.assert_array_equal(got2[1], ref[1])
+    np.testing.assert_allclose(ref[1], g["ssh_bl_data"], rtol=RTOL, atol=ATOL)
+
+
 def test_seam(golden_seam, golden_global):
     g = golden_seam
     lat, lon = _grid(golden_global)
@@ -150,6 +171,14 @@ def test_seam(golden_seam, golden_global):
         _check_bt(bt, g, suf)
         assert bt.ctx.stats()["last_chain_steps"] > bt.ctx.stats()["last_breaks"]   # real multi-step replays
         bt.close()
+
+
+def test_non_finite_grid_is_rejected(golden_regional):
+    lat, lon = _grid(golden_regional)
+    bad = lat.copy()
+    bad[7, 11] = np.nan
+    with pytest.raises(gzb.GonzagB200Error):
+        gzb.GridContext(bad, lon)
 
 
 def test_time_out_of_range(golden_regional):
