@@ -54,6 +54,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL prints its version banner on stdout) must not pollute the one JSON line:
+    point fd 1 at stderr for the whole run and keep the real stdout for `emit`."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 # ----------------------------------------------------------------------------- inputs
 def make_grid(w):
     lat, lon = syn.orca_like_grid(w["nj"], w["ni"])
@@ -216,7 +238,7 @@ def run_reference(args, w):
                        "np_box_r": r, "rd_found_km": rd},
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -228,6 +250,7 @@ def run_ours(args, w):
     from gonzag_b200.multi import CudaEngine, ShardedMapper, segment_bounds
     import types
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("GZB_NCCL_DEBUG", "WARN")   # NCCL logs go to stdout: keep it to the JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -280,8 +303,8 @@ def run_ours(args, w):
     tmod_d = eng.tensor(tmod_all)
     SM = eng.empty((nt_local, 4, 2), torch.int64)
     WB = eng.empty((nt_local, 4), torch.float64)
-    v_np = eng.empty((nt_local,), torch.float64)
-    v_bl = eng.empty((nt_local,), torch.float64)
+    mapper.make_buffers(bounds)
+    v_np, v_bl = mapper.v_np, mapper.v_bl
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     log("[rank %d] setup %.1f s: grid %dx%d, %d track points (of %d), records %d..%d (%.2f GB), r=%d"
@@ -290,11 +313,19 @@ def run_ours(args, w):
 
     state = {}
 
-    def step():
-        NP = mapper.nearest_segment(y_h, x_h, has_halo, rd, r)
-        eng.mesh_weights(y_d, x_d, NP, SM, WB)
+    def rest_of_path():
+        eng.mesh_weights(y_d, x_d, mapper.NP, SM, WB)
         eng.interp(t_d, SM, WB, tmod_d, slab, k_lo, v_np, v_bl)
-        state["out"] = mapper.gather([v_np, v_bl, NP], bounds)
+
+    def step():
+        mapper.nearest_speculative(y_h, x_h, rd, r)
+        rest_of_path()
+        g = mapper.gather()
+        if not mapper.boundaries_ok(g):           # rare: a chain deviation straddles a segment boundary
+            if mapper.reseed(g, y_d, x_d, rd, r):
+                rest_of_path()
+            g = mapper.gather()
+        state["out"] = g
 
     def barrier():
         if world > 1:
@@ -304,6 +335,20 @@ def run_ours(args, w):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    verified = None
+    if args.verify:
+        # rank 0 maps + interpolates the WHOLE track alone and compares with the gathered shards
+        g_np, g_bl, g_NP = mapper.unpack(state["out"])
+        if rank == 0:
+            with gzb.GridContext(lat, lon, mask=mask, k_ew_per=2, device=local) as c2:
+                c2.grid_angle(out=False)
+                NPf, SMf, WBf = c2.mapping(yy, xx, rd, r)
+            ok_np = bool((torch.as_tensor(NPf, device=dev) == g_NP).all())
+            verified = {"NP_bit_exact": ok_np, "points": int(len(yy))}
+            log("[verify] sharded NP == single-GPU NP over %d points: %s" % (len(yy), ok_np))
+            if not ok_np:
+                raise SystemExit("sharded result differs from the single-GPU result")
+        barrier()
     launches0 = ctx.stats()["kernel_launches"]
     sampler = ClockSampler(local)
     if rank == 0:
@@ -463,11 +508,11 @@ def run_ours(args, w):
                            "np_box_r": r, "rd_found_km": rd, "k_ew_per": 2,
                            "sharding": "contiguous time segments, grid replicated, 1 all-gather of (ssh_np, ssh_bl, NP)",
                            "l2": "flushed (256 MiB write) before every timed step and stage",
-                           "seed_reseeds": mapper.reseeds, "chain_breaks": int(ctx.stats()["last_breaks"]),
+                           "seed_reseeds": mapper.reseeds, "verified": verified, "chain_breaks": int(ctx.stats()["last_breaks"]),
                            "chain_replay_steps": int(ctx.stats()["last_chain_steps"])},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "kernels": kern,
                 "cpu_baseline": cpu, "e2e": e2e}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -482,7 +527,9 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="check the sharded result against a single-GPU run")
     args = ap.parse_args()
+    claim_stdout()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)

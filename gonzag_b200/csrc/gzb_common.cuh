@@ -72,6 +72,8 @@ struct gzb_ctx {
     void* stage[2] = {nullptr, nullptr};   // pinned staging for pageable field slabs
     size_t stage_cap = 0;
     int nearest_stats_pending = 0;
+    int time_err_pending = 0;
+    int* d_flags = nullptr;          // persistent device status words (word 0: K4 time-range error)
     int zero_copy = 1;               // gather from pinned+mapped host slabs instead of copying them
     // corner-box bounding sphere cache (predecessor == (-1,-1)), keyed by np_box_r
     int corner_r = -1;

@@ -303,7 +303,10 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
             CK(cudaMemcpyAsync(ctx->d_mask, mask_or_null, n, cudaMemcpyHostToDevice, ctx->stream));
             ctx->stats.h2d_bytes += n;
         }
+        CK(cudaMalloc((void**)&ctx->d_flags, 256));
+        CK(cudaMemsetAsync(ctx->d_flags, 0, 256, ctx->stream));
         CK(cudaHostAlloc(&ctx->pinned, 4096, cudaHostAllocPortable));
+        memset(ctx->pinned, 0, 4096);
         ctx->pinned_cap = 4096;
 #undef CK
         ctx->g.Nj = nj;
@@ -338,6 +341,7 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     cudaFree(ctx->d_mask);
     cudaFree(ctx->d_cells);
     cudaFree(ctx->d_cert);
+    cudaFree(ctx->d_flags);
     for (int k = 0; k < GZB_MAXLEV; ++k) cudaFree(ctx->d_nodes[k]);
     cudaFree(ctx->arena.base);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -367,15 +371,29 @@ extern "C" int gzb_use_own_stream(gzb_ctx* ctx) {
 extern "C" int gzb_sync(gzb_ctx* ctx) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_sync: null ctx");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    if (ctx->time_err_pending) {
+        int* h_err = (int*)((char*)ctx->pinned + 64);
+        GZB_CUDA(ctx, cudaMemcpyAsync(h_err, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->time_err_pending) {
+        ctx->time_err_pending = 0;
+        int* h_err = (int*)((char*)ctx->pinned + 64);
+        if (*h_err) {
+            *h_err = 0;
+            GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, 4, ctx->stream));
+            return gzb_fail(ctx, GZB_ERR_TIME, "gzb_interp: track time outside the model records [tmod[0], tmod[nrec-1])");
+        }
+    }
     return GZB_OK;
 }
 
 extern "C" int gzb_get_stats(const gzb_ctx* ctx_c, gzb_stats* out) {
     gzb_ctx* ctx = const_cast<gzb_ctx*>(ctx_c);
     if (!ctx || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_get_stats: null argument");
-    if (ctx->nearest_stats_pending) {      // the words were copied asynchronously by gzb_nearest
+    if (ctx->nearest_stats_pending) {      // left in the persistent device flags by gzb_nearest
         if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+        GZB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->d_flags + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
         GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const long long* w = (const long long*)ctx->pinned;
         ctx->stats.last_breaks = w[0];

@@ -122,13 +122,12 @@ extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64
         if (C < 2) C = 2;
         if (C > nk) C = nk;
     }
-    size_t need = gzb_align(64) + gzb_align((size_t)nrec * 8);
+    size_t need = gzb_align((size_t)nrec * 8);
     if (where == GZB_HOST) need += gzb_align(n * 8) * 3 + gzb_align(n * 64) + gzb_align(n * 32);
     if (!slab_on_device) need += 2 * gzb_align((size_t)C * rec_bytes);
     if (gzb_arena_reserve(ctx, need) != GZB_OK) return GZB_ERR_NOMEM;
     cudaStream_t s = ctx->stream;
-    int* d_err = (int*)gzb_arena_take(ctx, 64);
-    GZB_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, s));
+    int* d_err = ctx->d_flags;      // persistent, zero unless a previous call flagged an error
     const double* d_t = t;
     const long long* d_sm = (const long long*)sm;
     const double* d_wb = wb;
@@ -209,16 +208,19 @@ extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64
         }
     }
     int* h_err = (int*)((char*)ctx->pinned + 64);
-    GZB_CUDA(ctx, cudaMemcpyAsync(h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+    const bool sync_now = (where == GZB_HOST || !slab_on_device || slab_dev != slab);
+    if (sync_now) GZB_CUDA(ctx, cudaMemcpyAsync(h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+    else ctx->time_err_pending = 1;          // checked by gzb_sync()
     if (where == GZB_HOST) {
         GZB_CUDA(ctx, cudaMemcpyAsync(np_out, d_np, n * 8, cudaMemcpyDeviceToHost, s));
         GZB_CUDA(ctx, cudaMemcpyAsync(bl_out, d_bl, n * 8, cudaMemcpyDeviceToHost, s));
         ctx->stats.d2h_bytes += n * 16;
     }
-    if (where == GZB_HOST || !slab_on_device || slab_dev != slab) {
+    if (sync_now) {
         GZB_CUDA(ctx, cudaStreamSynchronize(s));
         if (*h_err) {
             *h_err = 0;
+            GZB_CUDA(ctx, cudaMemsetAsync(d_err, 0, 4, s));
             return gzb_fail(ctx, GZB_ERR_TIME, "gzb_interp: track time outside the model records [tmod[0], tmod[nrec-1])");
         }
     }

@@ -608,7 +608,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
 // step on the common path where no replay reaches the next break.
 __global__ void __launch_bounds__(32)
 k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop,
-        const long long* __restrict__ nbrk_p, unsigned char* __restrict__ valid) {
+        const long long* __restrict__ nbrk_p, unsigned char* __restrict__ valid, long long* __restrict__ stats_out) {
     const int lane = threadIdx.x;
     const long long nb = *nbrk_p;
     long long cur_end = -1;
@@ -635,6 +635,10 @@ k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop
                 }
             }
         }
+    }
+    if (lane == 0) {      // (breaks, replay steps) of this call, for gzb_get_stats
+        stats_out[0] = nbrk_p[0];
+        stats_out[1] = nbrk_p[1];
     }
 }
 
@@ -726,8 +730,8 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     unsigned char* valid = (unsigned char*)gzb_arena_take(ctx, n);
     unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
     long long* scal = (long long*)gzb_arena_take(ctx, 64);
-    double* corner = (double*)gzb_arena_take(ctx, 64);
-    if (!corner) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
+    if (!scal) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
+    double* corner = (double*)(ctx->d_flags + 32);      // persistent: 4 doubles, keyed by np_box_r
     cudaStream_t s = ctx->stream;
 
     NearParams p;
@@ -746,8 +750,11 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     p.corner = corner;
 
     GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 64, s));
-    k_corner<<<1, 256, 0, s>>>(ctx->g, np_box_r, corner);
-    GZB_LAUNCH_CHECK(ctx);
+    if (ctx->corner_r != np_box_r) {
+        k_corner<<<1, 256, 0, s>>>(ctx->g, np_box_r, corner);
+        GZB_LAUNCH_CHECK(ctx);
+        ctx->corner_r = np_box_r;
+    }
 
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -771,13 +778,11 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     k_walk<false><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
                                                    valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));
     GZB_LAUNCH_CHECK(ctx);
-    k_valid<<<1, 32, 0, s>>>(breaks, stop, scal, valid);
+    k_valid<<<1, 32, 0, s>>>(breaks, stop, scal, valid, (long long*)(ctx->d_flags + 8));
     GZB_LAUNCH_CHECK(ctx);
     k_walk<true><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
                                                   valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));
     GZB_LAUNCH_CHECK(ctx);
-    // stats: (breaks, chain steps) -> pinned words, read by gzb_get_stats after a sync
-    GZB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, scal, 16, cudaMemcpyDeviceToHost, s));
-    ctx->nearest_stats_pending = 1;
+    ctx->nearest_stats_pending = 1;      // k_valid left (breaks, replay steps) in the persistent flags
     return GZB_OK;
 }

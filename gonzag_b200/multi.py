@@ -71,7 +71,11 @@ class CudaEngine:
 
 
 class ShardedMapper:
-    """Maps + interpolates one rank's segment and gathers the products of all ranks."""
+    """Maps one rank's segment and gathers the products of all ranks.
+
+    Product buffer of a rank (one allocation, so that ONE `all_gather_into_tensor` moves it):
+    int64 words ``[nmax*4]`` = ``ssh_np`` (f64, nmax) | ``ssh_bl`` (f64, nmax) | ``NP`` (i64, nmax*2);
+    the kernels write straight into views of it."""
 
     def __init__(self, engine, dist=None, torch_mod=None):
         self.e = engine
@@ -81,53 +85,89 @@ class ShardedMapper:
         self.world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
         self.reseeds = 0
 
-    # ---- K1 with the cross-segment seed hand-off -------------------------------------------
-    def nearest_segment(self, y_halo, x_halo, has_halo, rd, r):
-        """``y_halo/x_halo``: the rank's points, preceded by the previous rank's last point when
-        ``has_halo``.  Returns NP of the rank's own points, (n,2) int64."""
+    # ---- buffers -----------------------------------------------------------------------------
+    def make_buffers(self, bounds):
         tc = self.torch
-        n_all = y_halo.numel()
-        NPh = self.e.empty((n_all, 2), tc.int64)
-        # (0,0) is "no previous hit" in the reference (gonzag/bilin_mapping.py:157), so the halo
-        # point gets its plain global answer, i.e. the speculative value of the chain there
-        seed = (0, 0) if has_halo else (r, r)
-        self.e.nearest(y_halo, x_halo, rd, r, seed, NPh)
-        off = 1 if has_halo else 0
-        NP = NPh[off:]
-        if self.world == 1:
-            return NP
-        for _ in range(self.world):
-            mine = tc.stack([NPh[0] if has_halo else tc.full((2,), -7, dtype=tc.int64, device=NPh.device),
-                             NP[-1] if NP.shape[0] else tc.full((2,), -7, dtype=tc.int64, device=NPh.device)])
-            allb = [tc.empty_like(mine) for _ in range(self.world)]
-            self.dist.all_gather(allb, mine)
-            allb = [b.cpu() for b in allb]
-            wrong = []
-            for g in range(1, self.world):
-                prev_last = allb[g - 1][1]
-                if not bool((allb[g][0] == prev_last).all()):
-                    wrong.append(g)
-            if not wrong:
-                break
-            if self.rank in wrong:
-                prev_last = allb[self.rank - 1][1]
-                self.reseeds += 1
-                self.e.nearest(y_halo[off:], x_halo[off:], rd, r, (int(prev_last[0]), int(prev_last[1])), NP)
-                NPh[0] = prev_last.to(NPh.device)      # the halo now carries the true predecessor
-        return NP
+        self.bounds = list(bounds)
+        self.nmax = max(bounds[g + 1] - bounds[g] for g in range(self.world))
+        n = bounds[self.rank + 1] - bounds[self.rank]
+        self.n = n
+        self.halo = self.rank > 0
+        self.pack = self.e.empty((4 * self.nmax,), tc.int64)
+        self.pack.zero_()
+        self.v_np = self.pack[:self.nmax].view(tc.float64)[:n]
+        self.v_bl = self.pack[self.nmax:2 * self.nmax].view(tc.float64)[:n]
+        self.NP = self.pack[2 * self.nmax:].view(self.nmax, 2)[:n]
+        self.NPh = self.e.empty((n + 1, 2), tc.int64)          # halo row + own rows (scratch for K1)
+        self.gathered = self.e.empty((self.world, 4 * self.nmax), tc.int64) if self.world > 1 else None
+        self.flag = self.e.empty((1,), tc.int32)
+        return self
 
-    # ---- final gather ------------------------------------------------------------------------
-    def gather(self, tensors, bounds):
-        """All-gather per-segment tensors (first dim = segment length) into full-track tensors."""
+    # ---- K1 with the cross-segment seed hand-off -----------------------------------------------
+    def nearest_speculative(self, y_halo, x_halo, rd, r):
+        """K1 on [halo point +] own points.  (0,0) is "no previous hit" in the reference
+        (gonzag/bilin_mapping.py:157), so the halo point gets its plain global answer, i.e. the
+        speculative value of the chain there.  The result lands in ``self.NP``."""
+        if self.halo:
+            self.e.nearest(y_halo, x_halo, rd, r, (0, 0), self.NPh)
+            self.NP.copy_(self.NPh[1:])
+        else:
+            self.e.nearest(y_halo, x_halo, rd, r, (r, r), self.NP)
+
+    def gather(self):
+        """The one data-path collective: all-gather of the packed products."""
         if self.world == 1:
-            return list(tensors)
+            return self.pack.view(1, -1)
+        self.dist.all_gather_into_tensor(self.gathered.view(-1), self.pack)
+        return self.gathered
+
+    def boundaries_ok(self, gathered):
+        """Does every rank's halo assumption equal the true last point of the previous rank?
+        One tiny all-reduce + one host read per step."""
+        if self.world == 1:
+            return True
         tc = self.torch
-        nmax = max(bounds[g + 1] - bounds[g] for g in range(self.world))
-        out = []
-        for t in tensors:
-            pad = tc.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            pad[:t.shape[0]] = t
-            parts = [tc.empty_like(pad) for _ in range(self.world)]
-            self.dist.all_gather(parts, pad)
-            out.append(tc.cat([parts[g][:bounds[g + 1] - bounds[g]] for g in range(self.world)], dim=0))
-        return out
+        if self.halo:
+            g = self.rank - 1
+            last = self.bounds[g + 1] - self.bounds[g] - 1
+            prev_last = gathered[g, 2 * self.nmax:].view(self.nmax, 2)[last]
+            self.flag[0] = (prev_last != self.NPh[0]).any().to(tc.int32)
+        else:
+            self.flag.zero_()
+        self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
+        return int(self.flag.item()) == 0
+
+    def reseed(self, gathered, y_own, x_own, rd, r):
+        """Rare path: re-map the segments whose predecessor assumption was wrong, in rank order,
+        until every boundary agrees (at most world-1 rounds).  Returns True if THIS rank re-mapped
+        (its mesh / weights / interpolation must then be redone by the caller)."""
+        tc = self.torch
+        changed = False
+        for _ in range(self.world):
+            if self.halo:
+                g = self.rank - 1
+                last = self.bounds[g + 1] - self.bounds[g] - 1
+                prev_last = gathered[g, 2 * self.nmax:].view(self.nmax, 2)[last].clone()
+                if bool((prev_last != self.NPh[0]).any()):
+                    self.reseeds += 1
+                    changed = True
+                    pl = prev_last.cpu()
+                    self.e.nearest(y_own, x_own, rd, r, (int(pl[0]), int(pl[1])), self.NP)
+                    self.NPh[0] = prev_last
+            gathered = self.gather()
+            if self.boundaries_ok(gathered):
+                break
+        return changed
+
+    # ---- views of the gathered products -------------------------------------------------------
+    def unpack(self, gathered):
+        """Full-track (ssh_np, ssh_bl, NP) tensors in track order (concatenation of the shards)."""
+        tc = self.torch
+        parts_np, parts_bl, parts_NP = [], [], []
+        for g in range(self.world):
+            n = self.bounds[g + 1] - self.bounds[g]
+            row = gathered[g]
+            parts_np.append(row[:self.nmax].view(tc.float64)[:n])
+            parts_bl.append(row[self.nmax:2 * self.nmax].view(tc.float64)[:n])
+            parts_NP.append(row[2 * self.nmax:].view(self.nmax, 2)[:n])
+        return tc.cat(parts_np), tc.cat(parts_bl), tc.cat(parts_NP)

@@ -121,7 +121,8 @@ int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
  * `where` says (detected): device slabs are used in place, host slabs are gathered over PCIe
  * (pinned + mapped, sparse track) or streamed through the GPU in 256 MiB chunks.
  * init_outputs != 0 first fills np_out/bl_out with rmissval (do it on the first slab).
- * Needs a mask in the context.  Points outside [tmod[0], tmod[nrec-1]) -> GZB_ERR_TIME. */
+ * Needs a mask in the context.  Points outside [tmod[0], tmod[nrec-1]) -> GZB_ERR_TIME
+ * (returned by this call when it synchronises, otherwise by the next gzb_sync()). */
 int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,
                int64_t nrec, const double* tmod, const void* slab, int dtype, int64_t k0,
                int64_t nk, double rmissval, int init_outputs, double* np_out, double* bl_out,

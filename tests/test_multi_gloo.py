@@ -61,9 +61,19 @@ def _worker(rank, world, port, cut, q):
         s0, s1 = bounds[rank], bounds[rank + 1]
         halo = rank > 0
         h0 = s0 - 1 if halo else s0
-        m = ShardedMapper(OracleEngine(lat, lon, 2), dist, torch)
-        NP = m.nearest_segment(torch.from_numpy(y[h0:s1].copy()), torch.from_numpy(x[h0:s1].copy()), halo, rd, r)
-        (full,) = m.gather([NP], bounds)
+        m = ShardedMapper(OracleEngine(lat, lon, 2), dist, torch).make_buffers(bounds)
+        yh, xh = torch.from_numpy(y[h0:s1].copy()), torch.from_numpy(x[h0:s1].copy())
+        off = 1 if halo else 0
+        m.nearest_speculative(yh, xh, rd, r)
+        m.v_np.copy_(torch.arange(s0, s1, dtype=torch.float64))        # stand-ins for the K4 products
+        m.v_bl.copy_(-torch.arange(s0, s1, dtype=torch.float64))
+        g = m.gather()
+        if not m.boundaries_ok(g):
+            m.reseed(g, yh[off:], xh[off:], rd, r)
+            g = m.gather()
+        v_np, v_bl, full = m.unpack(g)
+        assert torch.equal(v_np, torch.arange(len(y), dtype=torch.float64))
+        assert torch.equal(v_bl, -torch.arange(len(y), dtype=torch.float64))
         q.put((rank, full.numpy(), m.reseeds))
     finally:
         dist.destroy_process_group()
