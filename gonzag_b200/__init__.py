@@ -5,9 +5,11 @@ rebuilt for NVIDIA B200 (sm_100a).  Same Python surface as `gonzag.bilin_mapping
 from .config import *                                   # noqa: F401,F403
 from ._lib import GonzagB200Error, device_count        # noqa: F401
 from .context import GridContext                        # noqa: F401
-from .bilin_mapping import BilinTrack                   # noqa: F401
+from .bilin_mapping import (BilinTrack, NearestPoint, Iquadran, IDSourceMesh, AlfaBeta, WeightBL,   # noqa: F401
+                            Heading, release_cached_context)
 from .mod2sat import Model2SatTrack                     # noqa: F401
 from .utils import GridAngle, SearchBoxSize, degE_to_degWE   # noqa: F401
 
-__all__ = ["BilinTrack", "Model2SatTrack", "GridContext", "GridAngle", "SearchBoxSize",
+__all__ = ["BilinTrack", "NearestPoint", "Iquadran", "IDSourceMesh", "AlfaBeta", "WeightBL", "Heading",
+           "Model2SatTrack", "GridContext", "GridAngle", "SearchBoxSize",
            "degE_to_degWE", "GonzagB200Error", "device_count"]

@@ -14,8 +14,139 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import _lib as L
 from . import config
 from .context import GridContext
+
+# ---------------------------------------------------------------------------------------------
+# The free functions the reference package re-exports (gonzag/__init__.py:13).  Each is a
+# single-point call into the same CUDA kernels (no Python restatement of the arithmetic); the
+# grid context of the last (Ys, Xs) pair is kept so that loops over points do not re-upload it.
+_CTX_CACHE = {"key": None, "ctx": None}
+
+
+def _grid_ctx(Ys, Xs, device=0):
+    key = (id(Ys), id(Xs), np.shape(Ys), getattr(Ys, "ctypes", None) and Ys.ctypes.data,
+           getattr(Xs, "ctypes", None) and Xs.ctypes.data, device)
+    if _CTX_CACHE["key"] != key:
+        if _CTX_CACHE["ctx"] is not None:
+            _CTX_CACHE["ctx"].close()
+        _CTX_CACHE["ctx"] = GridContext(Ys, Xs, device=device)
+        _CTX_CACHE["key"] = key
+    return _CTX_CACHE["ctx"]
+
+
+def release_cached_context():
+    if _CTX_CACHE["ctx"] is not None:
+        _CTX_CACHE["ctx"].close()
+    _CTX_CACHE["ctx"] = None
+    _CTX_CACHE["key"] = None
+
+
+def Heading(plata, plona, platb, plonb):
+    """True heading from point a to point b, degrees clockwise from north
+    (gonzag/bilin_mapping.py:16-47)."""
+    a = [np.array([float(v)]) for v in (plata, plona, platb, plonb)]
+    out = np.empty(1)
+    L.check(L.lib().gzb_heading(0, 1, *[L.ptr(v) for v in a], L.ptr(out)))
+    return float(out[0])
+
+
+def AlfaBeta(vy, vx):
+    """Local coordinates (alpha, beta) of point 0 in the quad 1-2-3-4 (gonzag/bilin_mapping.py:50-141)."""
+    y = np.ascontiguousarray(vy, dtype=np.float64).reshape(5)
+    x = np.ascontiguousarray(vx, dtype=np.float64).reshape(5)
+    ab = np.empty(2)
+    L.check(L.lib().gzb_alfabeta(0, 1, L.ptr(y), L.ptr(x), L.ptr(ab)))
+    return float(ab[0]), float(ab[1])
+
+
+def NearestPoint(pcoor_trg, Ys, Xs, rd_found_km=10., resolkm=[], j_prv=None, i_prv=None, np_box_r=10, max_itr=5):
+    """[j, i] of the nearest source point, [-1,-1] if none within the acceptance radius
+    (gonzag/bilin_mapping.py:144-191).  The unused ``resolkm`` branch and ``max_itr != 5`` are not
+    supported."""
+    if np.shape(resolkm) == np.shape(Ys):
+        raise NotImplementedError("resolkm (2-D adaptive radius) is not supported")
+    if max_itr != 5:
+        raise NotImplementedError("only max_itr=5 (the reference's only use) is supported")
+    (yT, xT) = pcoor_trg
+    ctx = _grid_ctx(Ys, Xs)
+    ctx.set_option("edge_exclusion", 0)
+    try:
+        seed = (0 if j_prv is None else int(j_prv), 0 if i_prv is None else int(i_prv))
+        NP = ctx.nearest(np.array([yT], dtype=np.float64), np.array([xT], dtype=np.float64),
+                         rd_found_km, np_box_r, seed=seed)
+    finally:
+        ctx.set_option("edge_exclusion", 1)
+    return [int(NP[0, 0]), int(NP[0, 1])]
+
+
+def _neighbours(jP, iP, Ny, Nx, k_ew_per):
+    # index bookkeeping of gonzag/bilin_mapping.py:194-212
+    jm, jp, im, ip = jP - 1, jP + 1, iP - 1, iP + 1
+    if jp == Ny:
+        jp = -1
+    if im == -1 and k_ew_per >= 0:
+        im = Nx - k_ew_per - 1
+    if ip == Nx:
+        ip = k_ew_per if k_ew_per >= 0 else -1
+    return jm, jp, im, ip
+
+
+def _mesh_one(pcoor_trg, Ys, Xs, jP, iP, k_ew_per, grid_s_angle, lforceHD):
+    (yT, xT) = pcoor_trg
+    ctx = _grid_ctx(Ys, Xs)
+    ctx.set_ew_per(k_ew_per)
+    ctx.set_option("force_heavy", 2 if lforceHD else (1 if abs(grid_s_angle) > 45. else 0))
+    try:
+        SM = ctx.source_mesh(np.array([yT], dtype=np.float64), np.array([xT], dtype=np.float64),
+                             np.array([[jP, iP]], dtype=np.int64))
+    finally:
+        ctx.set_option("force_heavy", 0)
+    return SM[0]
+
+
+def Iquadran(pcoor_trg, Ys, Xs, jP, iP, k_ew_per=1, grid_s_angle=0., lforceHD=False):
+    """Which of the 4 cells around the nearest point holds the target: 1..4, -1 if undecided, None
+    when a neighbour is missing (gonzag/bilin_mapping.py:329-449)."""
+    (Ny, Nx) = np.shape(Ys)
+    jm, jp, im, ip = _neighbours(int(jP), int(iP), Ny, Nx, k_ew_per)
+    if -1 in (jm, jp, im, ip) or im < 0 or jm < 0 or ip > Nx - 1:
+        return None
+    sm = _mesh_one(pcoor_trg, Ys, Xs, int(jP), int(iP), k_ew_per, grid_s_angle, lforceHD)
+    if sm[0, 0] < 0:
+        return -1
+    p2 = (int(sm[1, 0]), int(sm[1, 1]))
+    return {(int(jP), ip): 1, (jm, int(iP)): 2, (int(jP), im): 3, (jp, int(iP)): 4}[p2]
+
+
+def IDSourceMesh(pcoor_trg, Ys, Xs, jP, iP, iquadran=-1, k_ew_per=-1, grid_s_angle=0., lforceHD=False):
+    """(4,2) int64 source mesh [P1(nearest), P2, P3, P4], all -1 if not found
+    (gonzag/bilin_mapping.py:453-486)."""
+    (Ny, Nx) = np.shape(Ys)
+    jP, iP = int(jP), int(iP)
+    if iquadran > 0:
+        if iquadran not in (1, 2, 3, 4):
+            raise ValueError('[Iquadran2SrcMesh()] non-valid "iquadran" value')
+        jm, jp, im, ip = _neighbours(jP, iP, Ny, Nx, k_ew_per)
+        if -1 in (jm, jp, im, ip):
+            raise ValueError("the nearest point has no complete neighbourhood")
+        table = {1: [(jP, ip), (jp, ip), (jp, iP)], 2: [(jm, iP), (jm, ip), (jP, ip)],
+                 3: [(jP, im), (jm, im), (jm, iP)], 4: [(jp, iP), (jp, im), (jP, im)]}
+        return np.array([(jP, iP)] + table[iquadran], dtype=np.int64)
+    jm, jp, im, ip = _neighbours(jP, iP, Ny, Nx, k_ew_per)
+    if -1 in (jm, jp, im, ip) or im < 0 or jm < 0 or ip > Nx - 1:
+        return np.full((4, 2), -1, dtype=np.int64)
+    return _mesh_one(pcoor_trg, Ys, Xs, jP, iP, k_ew_per, grid_s_angle, lforceHD)
+
+
+def WeightBL(pcoor_trg, Ys, Xs, isrc_msh):
+    """The 4 bilinear weights of a target inside its source mesh (gonzag/bilin_mapping.py:490-527)."""
+    (yT, xT) = pcoor_trg
+    ctx = _grid_ctx(Ys, Xs)
+    sm = np.ascontiguousarray(isrc_msh, dtype=np.int64).reshape(1, 4, 2)
+    WB = ctx.weights(np.array([yT], dtype=np.float64), np.array([xT], dtype=np.float64), sm)
+    return WB[0]
 
 
 class BilinTrack:

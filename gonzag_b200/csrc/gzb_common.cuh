@@ -72,6 +72,8 @@ struct gzb_ctx {
     void* stage[2] = {nullptr, nullptr};   // pinned staging for pageable field slabs
     size_t stage_cap = 0;
     int nearest_stats_pending = 0;
+    int edge_exclusion = 1;          // 0: plain NearestPoint() semantics (no BilinTrack.nrpt edge rule)
+    int force_heavy = 0;             // 1: heavy-duty quadrant search even if the light test succeeds; 2: skip the light test
     int time_err_pending = 0;
     int* d_flags = nullptr;          // persistent device status words (word 0: K4 time-range error)
     int zero_copy = 1;               // gather from pinned+mapped host slabs instead of copying them

@@ -407,6 +407,8 @@ extern "C" int gzb_get_stats(const gzb_ctx* ctx_c, gzb_stats* out) {
 extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: null argument");
     if (!strcmp(name, "zero_copy")) { ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
+    if (!strcmp(name, "edge_exclusion")) { ctx->edge_exclusion = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "force_heavy")) { ctx->force_heavy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
     return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: unknown option '%s'", name);
 }
 

@@ -55,7 +55,7 @@ __device__ __forceinline__ bool strictly_in_quad(double py, double px, const dou
 
 __global__ void __launch_bounds__(128)
 k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-              const long long* __restrict__ NP, long long* __restrict__ SM) {
+              const long long* __restrict__ NP, long long* __restrict__ SM, const int force_heavy) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const long long jP = NP[2 * t], iP = NP[2 * t + 1];
@@ -90,12 +90,14 @@ k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt
         const double hW = gzb_heading_dev(lat0, lon0, latW, gzb_pymod(lonW, 360.0));
         const double hz = gzb_pm180(ht);
         if (hN > hE) hN = hN - 360.0;
-        if (hz > hN && hz <= hE) iq = 1;
-        if (ht > hE && ht <= hS) iq = 2;
-        if (ht > hS && ht <= hW) iq = 3;
-        if (ht > hW && hz <= hN) iq = 4;
+        if (force_heavy < 2) {
+            if (hz > hN && hz <= hE) iq = 1;
+            if (ht > hE && ht <= hS) iq = 2;
+            if (ht > hS && ht <= hW) iq = 3;
+            if (ht > hW && hz <= hN) iq = 4;
+        }
         const double ang = g.angle ? g.angle[jP * g.Ni + iP] : 0.0;
-        if (iq < 1 || fabs(ang) > 45.0) {
+        if (iq < 1 || fabs(ang) > 45.0 || force_heavy) {
             // heavy-duty: quads 4,3,2,1 in the raw (lat, lon) plane, first strict-interior hit
             for (int cand = 4; cand >= 1; --cand) {
                 quad_corners(cand, jP, iP, jm, jp, im, ip, cj, ci);
@@ -161,7 +163,7 @@ int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double
                         int64_t* sm_out) {
     if (nt <= 0) return GZB_OK;
     k_source_mesh<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
-                                                                        (long long*)sm_out);
+                                                                        (long long*)sm_out, ctx->force_heavy);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }

@@ -63,6 +63,7 @@ struct NearParams {
     float prox_r0;     // chord^2 bound that contains every cell with d < r0
     double chord_r0;   // chord length of r0 (with margin)
     int r;             // np_box_r
+    int edge;          // apply the edge exclusion of BilinTrack.nrpt
     long long seed_j, seed_i;
     const double* corner;   // bounding sphere (cx,cy,cz,rho) of the box of predecessor (-1,-1)
 };
@@ -346,7 +347,7 @@ int gzb_build_cert(gzb_ctx* ctx) {
 // threshold acceptance of the global hit + the edge exclusion of BilinTrack.nrpt
 // (gonzag/bilin_mapping.py:169-190 and :582-585; column 0 is always excluded)
 __device__ __forceinline__ void accept_edge(const GzbGrid& g, const long long flat, const double d,
-                                            const double thr, long long& j, long long& i) {
+                                            const double thr, long long& j, long long& i, const int edge = 1) {
     if (flat != GZB_NOFLAT && d < thr) {
         j = flat / g.Ni;
         i = flat - j * g.Ni;
@@ -354,8 +355,10 @@ __device__ __forceinline__ void accept_edge(const GzbGrid& g, const long long fl
         j = -1;
         i = -1;
     }
-    if (i == 0 || (i == g.Ni - 1 && g.kew == -1)) { j = -1; i = -1; }
-    if (j == 0 || j == g.Nj - 1) { j = -1; i = -1; }
+    if (edge) {
+        if (i == 0 || (i == g.Ni - 1 && g.kew == -1)) { j = -1; i = -1; }
+        if (j == 0 || j == g.Nj - 1) { j = -1; i = -1; }
+    }
 }
 
 __device__ __forceinline__ bool clamp_box(const GzbGrid& g, const long long pj, const long long pi, const int r,
@@ -376,7 +379,7 @@ k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* _
     int isb = 0;
     if (t < nt) {
         long long ej, ei;
-        accept_edge(g, G[t], dG[t], p.thr2, ej, ei);
+        accept_edge(g, G[t], dG[t], p.thr2, ej, ei, p.edge);
         NP[2 * t] = ej;
         NP[2 * t + 1] = ei;
         long long pj, pi;
@@ -384,7 +387,7 @@ k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* _
             pj = p.seed_j;
             pi = p.seed_i;
         } else {
-            accept_edge(g, G[t - 1], dG[t - 1], p.thr2, pj, pi);
+            accept_edge(g, G[t - 1], dG[t - 1], p.thr2, pj, pi, p.edge);
         }
         if (pj != 0 && pi != 0) {   // Python truthiness of (j_prv and i_prv)
             long long j0, j1, i0, i1;
@@ -507,7 +510,7 @@ __device__ __forceinline__ void chain_step(const GzbGrid& g, WarpSm& w, const in
             const long long f = w.bf[0];
             const double d = __longlong_as_double((long long)w.bd[0]);
             __syncwarp();
-            if (f != GZB_NOFLAT && d < p.r0) accept_edge(g, f, d, INFINITY, rj, ri);
+            if (f != GZB_NOFLAT && d < p.r0) accept_edge(g, f, d, INFINITY, rj, ri, p.edge);
         }
     }
 }
@@ -567,13 +570,13 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
             pj = p.seed_j;
             pi = p.seed_i;
         } else {
-            accept_edge(g, G[b - 1], dG[b - 1], p.thr2, pj, pi);
+            accept_edge(g, G[b - 1], dG[b - 1], p.thr2, pj, pi, p.edge);
         }
         long long t = b;
         unsigned long long n = 0;
         for (;;) {
             long long ej, ei, rj, ri;
-            accept_edge(g, G[t], dG[t], p.thr2, ej, ei);
+            accept_edge(g, G[t], dG[t], p.thr2, ej, ei, p.edge);
             chain_step(g, ws[warp], lane, p, t, pj, pi, yt, xt, ej, ei, rj, ri);
             ++n;
             if (WRITE) {
@@ -745,6 +748,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     p.prox_r0 = (float)(4.0 * sn * sn * (1.0 + 1.0e-5) + 1.0e-20);
     p.chord_r0 = 2.0 * sn * (1.0 + 1.0e-6) + 1.0e-12;
     p.r = np_box_r;
+    p.edge = ctx->edge_exclusion;
     p.seed_j = seed_j;
     p.seed_i = seed_i;
     p.corner = corner;

@@ -72,7 +72,11 @@ int gzb_set_angle(gzb_ctx* ctx, const double* angle_or_null, int where);
 int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
 /* options: "zero_copy": 1 (default) gzb_interp gathers straight from a pinned + mapped host slab
  * over PCIe when the track is sparse w.r.t. the slab, instead of copying the slab to the GPU;
- * 0 never; 2 whenever the slab is pinned + mapped. */
+ * 0 never; 2 whenever the slab is pinned + mapped.
+ * "edge_exclusion": 1 (default) gzb_nearest applies the first/last row/column rule of
+ * BilinTrack.nrpt (gonzag/bilin_mapping.py:582-585); 0 gives plain NearestPoint() results.
+ * "force_heavy": 0 (default); 1 = heavy-duty quadrant search as if |angle| > 45 everywhere;
+ * 2 = also skip the light test (Iquadran's lforceHD, gonzag/bilin_mapping.py:375). */
 int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value);
 
 /* ---- K0: local grid rotation, the `-D` pre-pass --------------------------------------------

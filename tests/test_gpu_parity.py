@@ -47,6 +47,34 @@ def test_scalar_helpers(golden_units):
     np.testing.assert_allclose(hv, g["hav_out"], rtol=1e-13)
 
 
+def test_free_functions(golden_units):
+    """The functions gonzag re-exports at package level (gonzag/__init__.py:13), single-point calls."""
+    g = golden_units
+    for row, want in zip(g["heading_in"][:40], g["heading_out"][:40]):
+        d = abs(gzb.Heading(*row) - want)
+        assert min(d, 360.0 - d) < 1e-9
+    for vy, vx, want in zip(g["ab_vy"][:40], g["ab_vx"][:40], g["ab_out"][:40]):
+        np.testing.assert_allclose(gzb.AlfaBeta(vy.copy(), vx.copy()), want, rtol=RTOL, atol=ATOL)
+    Y, X = np.ascontiguousarray(g["np_Y"]), np.ascontiguousarray(g["np_X"])
+    for call, want in zip(g["np_calls"], g["np_out"]):
+        yt, xt, jp, ip, rr = call
+        jp = None if jp == -99 else int(jp)
+        ip = None if ip == -99 else int(ip)
+        got = gzb.NearestPoint((yt, xt), Y, X, rd_found_km=float(g["np_rd"]), j_prv=jp, i_prv=ip, np_box_r=int(rr))
+        assert list(got) == list(want), (call, got, want)
+    for call, sm_want, wb_want in zip(g["sm_calls"], g["sm_out"], g["wb_out"]):
+        yt, xt, jP, iP, kew, ang = call
+        sm = gzb.IDSourceMesh((yt, xt), Y, X, int(jP), int(iP), k_ew_per=int(kew), grid_s_angle=ang)
+        np.testing.assert_array_equal(sm, sm_want)
+        np.testing.assert_allclose(gzb.WeightBL((yt, xt), Y, X, sm), wb_want, rtol=RTOL, atol=ATOL)
+        iq = gzb.Iquadran((yt, xt), Y, X, int(jP), int(iP), k_ew_per=int(kew), grid_s_angle=ang)
+        if sm_want[0, 0] >= 0:
+            np.testing.assert_array_equal(gzb.IDSourceMesh((yt, xt), Y, X, int(jP), int(iP), iquadran=iq, k_ew_per=int(kew)), sm_want)
+        else:
+            assert iq in (-1, None)
+    gzb.release_cached_context()
+
+
 def test_grid_angle(golden_units, golden_global):
     g = golden_units
     got = gzb.GridAngle(g["ga_lat"], g["ga_lon"])
