@@ -27,7 +27,10 @@ class GonzagB200Error(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("last_breaks", C.c_int64), ("last_chain_steps", C.c_int64),
-                ("pyramid_levels", C.c_int32), ("reserved", C.c_int32)]
+                ("pyramid_levels", C.c_int32), ("reserved", C.c_int32),
+                ("lut_bins", C.c_int64), ("last_unresolved", C.c_int64),
+                ("last_unres_noseed", C.c_int64), ("last_unres_noconv", C.c_int64),
+                ("last_unres_nocert", C.c_int64), ("last_max_chain", C.c_int64)]
 
 
 _P = C.c_void_p
@@ -51,6 +54,7 @@ _SIGNATURES = {
     "gzb_nearest": (C.c_int, [_P, _I64, _P, _P, C.c_double, C.c_int, _I64, _I64, _P, C.c_int]),
     "gzb_source_mesh": (C.c_int, [_P, _I64, _P, _P, _P, _P, C.c_int]),
     "gzb_weights": (C.c_int, [_P, _I64, _P, _P, _P, _P, C.c_int]),
+    "gzb_mesh_weights": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, C.c_int]),
     "gzb_mapping": (C.c_int, [_P, _I64, _P, _P, C.c_double, C.c_int, _I64, _I64, _P, _P, _P, C.c_int]),
     "gzb_interp": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int,
                              _P, _P, C.c_int]),

@@ -10,6 +10,9 @@ int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double
 int gzb_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* sm,
                     double* wb_out);
 
+int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
+                         int64_t* sm_out, double* wb_out);
+
 namespace {
 
 // which stages a call runs
@@ -68,11 +71,11 @@ int run_stages(gzb_ctx* ctx, int stages, int64_t nt, const double* yt, const dou
         if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp)) != GZB_OK) return rc;
         dnp_in = dnp;
     }
-    if (stages & ST_SM) {
+    if ((stages & ST_SM) && (stages & ST_WB)) {
+        if ((rc = gzb_mesh_weights_dev(ctx, nt, dy, dx, dnp_in, dsm, dwb)) != GZB_OK) return rc;
+    } else if (stages & ST_SM) {
         if ((rc = gzb_source_mesh_dev(ctx, nt, dy, dx, dnp_in, dsm)) != GZB_OK) return rc;
-        dsm_in = dsm;
-    }
-    if (stages & ST_WB) {
+    } else if (stages & ST_WB) {
         if ((rc = gzb_weights_dev(ctx, nt, dy, dx, dsm_in, dwb)) != GZB_OK) return rc;
     }
     if (where == GZB_HOST) {
@@ -111,6 +114,12 @@ extern "C" int gzb_weights(gzb_ctx* ctx, int64_t nt, const double* yt, const dou
                            double* wb_out, int where) {
     return run_stages(ctx, ST_WB, nt, yt, xt, 1.0, 0, 0, 0, nullptr, sm, nullptr, nullptr, wb_out, where,
                       "gzb_weights");
+}
+
+extern "C" int gzb_mesh_weights(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
+                                int64_t* sm_out, double* wb_out, int where) {
+    return run_stages(ctx, ST_SM | ST_WB, nt, yt, xt, 1.0, 0, 0, 0, np, nullptr, nullptr, sm_out, wb_out, where,
+                      "gzb_mesh_weights");
 }
 
 extern "C" int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double rd_found_km,

@@ -32,6 +32,17 @@ struct GzbLevel {
     int sJ, sI;       // cells covered by one node in j and i
 };
 
+// Lat-lon binned look-up table: bin -> flat index of some grid cell lying in (or next to) the
+// bin; it only SEEDS the per-thread hill climb of k_near_fast.  bins == nullptr: no table.
+struct GzbLut {
+    const unsigned* bins;   // 0xffffffff = no cell anywhere near this bin
+    int nlat, nlon;
+    int wrap;               // the table covers the whole circle of longitudes
+    double lat0, lon0;      // south-west corner (degrees); longitudes are taken modulo 360 from lon0
+    double inv_d;           // 1 / bin size (degrees)
+    double lon_span;        // covered longitude span (degrees), 360 when wrap
+};
+
 struct GzbGrid {
     int64_t Nj, Ni;
     int kew;
@@ -42,6 +53,9 @@ struct GzbGrid {
     const float* cells;     // per leaf tile: x[32] y[32] z[32] (unit vectors), tile row-major
     const float* cert;      // per leaf tile (same index as its node): chord distance from the tile
                             // centre to the nearest cell outside the tile's 5x3-tile neighbourhood
+    const float4* cellv;    // per cell, row-major: unit vector (x,y,z) + w = lower bound of the chord
+                            // from this cell to any cell outside its 5x5 index neighbourhood
+    GzbLut lut;
     int nlev;
     GzbLevel lev[GZB_MAXLEV];
 };
@@ -66,6 +80,9 @@ struct gzb_ctx {
     float* d_cells = nullptr;
     float4* d_nodes[GZB_MAXLEV] = {};
     float* d_cert = nullptr;
+    float4* d_cellv = nullptr;
+    unsigned* d_lut[2] = {nullptr, nullptr};
+    int nearest_path = 1;            // 1: per-thread hill climb seeded by the look-up table (+ warp fallback); 0: warp walk only
     GzbArena arena;
     void* pinned = nullptr;          // small pinned scratch for status words
     size_t pinned_cap = 0;
@@ -130,19 +147,24 @@ __device__ __forceinline__ double gzb_pm180(double x) {
     return copysign(1.0, 180.0 - x) * fmin(x, fabs(x - 360.0));
 }
 
-// gonzag/bilin_mapping.py:16-47 (Heading): loxodromic bearing a->b, degrees in [0,360)
-__device__ __forceinline__ double gzb_heading_dev(double lata, double lona, double latb, double lonb) {
-    const double xa = lona * GZB_D2R;
-    const double xb = lonb * GZB_D2R;
-    double ra = fmax(fabs(tan(GZB_PI / 4.0 - (lata * GZB_D2R) / 2.0)), 1.0e-9);
-    double ya = -log(ra);
-    double rb = fmax(fabs(tan(GZB_PI / 4.0 - (latb * GZB_D2R) / 2.0)), 1.0e-9);
-    double yb = -log(rb);
+// gonzag/bilin_mapping.py:16-47 (Heading): loxodromic bearing a->b, degrees in [0,360).
+// Split in two so that a caller taking several headings from one point evaluates that point's
+// Mercator ordinate once (same operations, same bits).
+__device__ __forceinline__ double gzb_merc_y(double lat) {      // :29-35
+    const double r = fmax(fabs(tan(GZB_PI / 4.0 - (lat * GZB_D2R) / 2.0)), 1.0e-9);
+    return -log(r);
+}
+
+__device__ __forceinline__ double gzb_heading_y(double ya, double xa, double yb, double xb) {   // xa, xb in radians
     double d = gzb_pymod(xb - xa, 2.0 * GZB_PI);
     if (d >= GZB_PI) d = d - 2.0 * GZB_PI;
     if (d <= -GZB_PI) d = d + 2.0 * GZB_PI;
-    double ang = atan2(d, yb - ya);
+    const double ang = atan2(d, yb - ya);
     return gzb_pymod(ang * 180.0 / GZB_PI, 360.0);
+}
+
+__device__ __forceinline__ double gzb_heading_dev(double lata, double lona, double latb, double lonb) {
+    return gzb_heading_y(gzb_merc_y(lata), lona * GZB_D2R, gzb_merc_y(latb), lonb * GZB_D2R);
 }
 
 // gonzag/utils.py:296-316 (Haversine), same operation order; cos_plat = cos(plat*to_rad)
@@ -202,6 +224,21 @@ __device__ __forceinline__ void gzb_alfabeta_dev(const double* yin, const double
 // warp-wide minimum of a non-negative float (or +inf): one REDUX on the bit pattern
 __device__ __forceinline__ float gzb_warp_min_nonneg(float v) {
     return __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(v)));
+}
+
+// bin of a (finite) position in the look-up table
+__device__ __forceinline__ long long gzb_lut_bin(const GzbLut& L, double lat, double lon) {
+    const double fj = floor((lat - L.lat0) * L.inv_d);
+    const int bj = fj < 0.0 ? 0 : (fj >= (double)L.nlat ? L.nlat - 1 : (int)fj);
+    const double x = gzb_pymod(lon - L.lon0, 360.0);
+    int bi;
+    if (!L.wrap && x > L.lon_span) {
+        bi = (x - L.lon_span > 0.5 * (360.0 - L.lon_span)) ? 0 : L.nlon - 1;   // outside: the nearer edge
+    } else {
+        const double fi = floor(x * L.inv_d);
+        bi = fi >= (double)L.nlon ? L.nlon - 1 : (int)fi;
+    }
+    return (long long)bj * L.nlon + bi;
 }
 
 // index of leaf tile (tJ, tI) in the level-0 node array (and in GzbGrid::cert)

@@ -87,7 +87,8 @@ __device__ __forceinline__ float4 pack_sphere(double cx, double cy, double cz, d
 
 // One warp per leaf tile: unit vectors of its 32 cells + the tile's bounding sphere.
 __global__ void __launch_bounds__(256)
-k_build_leaves(GzbGrid g, float* __restrict__ cells, float4* __restrict__ nodes0, int* __restrict__ bad) {
+k_build_leaves(GzbGrid g, float* __restrict__ cells, float4* __restrict__ nodes0, float4* __restrict__ cellv,
+               int* __restrict__ bad) {
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const GzbLevel L0 = g.lev[0];
@@ -111,6 +112,7 @@ k_build_leaves(GzbGrid g, float* __restrict__ cells, float4* __restrict__ nodes0
     c[lane] = ok ? (float)x : 1.0e3f;
     c[32 + lane] = ok ? (float)y : 1.0e3f;
     c[64 + lane] = ok ? (float)z : 1.0e3f;
+    if (ok && cellv) cellv[j * g.Ni + i] = make_float4((float)x, (float)y, (float)z, 0.0f);
     // centre = normalised mean of the valid cells
     double sx = x, sy = y, sz = z;
 #pragma unroll
@@ -193,6 +195,217 @@ __global__ void k_fill_empty(float4* p, int64_t n) {
     if (k < n) p[k] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
 }
 
+
+// ======================================================================== seed look-up table
+// order-preserving map double -> uint64 so that atomicMin/atomicMax work on coordinates
+__device__ __forceinline__ unsigned long long ord_enc(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+static double ord_dec(unsigned long long u) {
+    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+// extent of the grid: min/max of lat, of lon % 360 (frame A) and of (lon + 180) % 360 (frame B)
+// out[0..5] = ord_enc(min lat, max lat, min A, max A, min B, max B)
+__global__ void __launch_bounds__(256)
+k_extent(const int64_t n, const double* __restrict__ lat, const double* __restrict__ lon,
+         unsigned long long* __restrict__ out) {
+    __shared__ double sm[6][8];
+    double v[6] = {INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY};
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double la = lat[k], lo = lon[k];
+        if (!(isfinite(la) && isfinite(lo))) continue;
+        const double a = gzb_pymod(lo, 360.0), b = gzb_pymod(lo + 180.0, 360.0);
+        v[0] = fmin(v[0], la); v[1] = fmax(v[1], la);
+        v[2] = fmin(v[2], a);  v[3] = fmax(v[3], a);
+        v[4] = fmin(v[4], b);  v[5] = fmax(v[5], b);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, v[q], o);
+            v[q] = (q & 1) ? fmax(v[q], u) : fmin(v[q], u);
+        }
+        if (lane == 0) sm[q][warp] = v[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int q = threadIdx.x;
+        double r = sm[q][0];
+        for (int w = 1; w < 8; ++w) r = (q & 1) ? fmax(r, sm[q][w]) : fmin(r, sm[q][w]);
+        if (isfinite(r)) {
+            if (q & 1) atomicMax(out + q, ord_enc(r)); else atomicMin(out + q, ord_enc(r));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_lut_scatter(const GzbGrid g, const GzbLut L, unsigned* __restrict__ bins) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.Nj * g.Ni) return;
+    const double la = g.lat[k], lo = g.lon[k];
+    if (!(isfinite(la) && isfinite(lo))) return;
+    atomicMin(bins + gzb_lut_bin(L, la, lo), (unsigned)k);
+}
+
+// empty bins take the value of the first non-empty neighbour at distance `step` (8 directions)
+__global__ void __launch_bounds__(256)
+k_lut_fill(const GzbLut L, const unsigned* __restrict__ in, unsigned* __restrict__ out, const int step) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (int64_t)L.nlat * L.nlon) return;
+    unsigned v = in[k];
+    if (v == 0xffffffffu) {
+        const int bj = (int)(k / L.nlon), bi = (int)(k - (int64_t)bj * L.nlon);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int dj = (q < 3) ? -1 : (q < 5 ? 0 : 1);
+            const int di = (q == 0 || q == 3 || q == 5) ? -1 : ((q == 1 || q == 6) ? 0 : 1);
+            const int nj = bj + dj * step;
+            int ni = bi + di * step;
+            if (nj < 0 || nj >= L.nlat) continue;
+            if (L.wrap) {
+                ni %= L.nlon;
+                if (ni < 0) ni += L.nlon;
+            } else if (ni < 0 || ni >= L.nlon) {
+                continue;
+            }
+            const unsigned u = in[(int64_t)nj * L.nlon + ni];
+            if (u != 0xffffffffu) { v = u; break; }
+        }
+    }
+    out[k] = v;
+}
+
+// Per-cell certificate (GzbGrid::cellv[].w): a lower bound of the chord from cell c to every
+// cell OUTSIDE its 5x5 index neighbourhood.  One warp per leaf tile T, lane = cell of T:
+//   cells inside T's 5x3-tile window  -> evaluated one by one (tiles too far to matter skipped);
+//   cells outside that window         -> cert(T) - |c - centre(T)|   (triangle inequality).
+__global__ void __launch_bounds__(256)
+k_cellcert(const GzbGrid g, float4* __restrict__ cellv) {
+    const int lane = threadIdx.x & 31;
+    const GzbLevel L0 = g.lev[0];
+    const int64_t ntile = (int64_t)L0.nJ * L0.nI;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= ntile) return;
+    const int tJ = (int)(tile / L0.nI), tI = (int)(tile - (int64_t)tJ * L0.nI);
+    const float* __restrict__ cc = g.cells + tile * 96;
+    const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
+    const int64_t j = (int64_t)tJ * GZB_TILE_J + (lane >> 3);
+    const int64_t i = (int64_t)tI * GZB_TILE_I + (lane & 7);
+    const bool ok = (j < g.Nj) && (i < g.Ni);
+    const int64_t tidx = gzb_leaf_index(g, tJ, tI);
+    const float4 nd = L0.nodes[tidx];
+    float far;
+    {
+        const float dx = x - nd.x, dy = y - nd.y, dz = z - nd.z;
+        const float a = sqrtf(dx * dx + dy * dy + dz * dz);
+        far = g.cert[tidx] - (a * (1.0f + 2.0e-7f) + 5.0e-7f);
+    }
+    float m2 = INFINITY;     // smallest chord^2 to a window cell outside the 5x5 neighbourhood
+    // nearest tiles first, so that the far ones can be skipped
+    const int order_j[5] = {0, -1, 1, -2, 2};
+    const int order_i[3] = {0, -1, 1};
+    for (int a = 0; a < 5; ++a) {
+        for (int b = 0; b < 3; ++b) {
+            const int wJ = tJ + order_j[a], wI = tI + order_i[b];
+            if (wJ < 0 || wJ >= L0.nJ || wI < 0 || wI >= L0.nI) continue;
+            const float4 wn = L0.nodes[gzb_leaf_index(g, wJ, wI)];
+            if (wn.w < 0.0f) continue;
+            {
+                const float dx = x - wn.x, dy = y - wn.y, dz = z - wn.z;
+                const float dc = sqrtf(dx * dx + dy * dy + dz * dz) - wn.w;     // lower bound to any cell of W
+                const bool skip = !ok || (dc > 0.0f && dc * dc * (1.0f - 1.0e-6f) > m2);
+                if (__all_sync(0xffffffffu, skip)) continue;
+            }
+            const float* __restrict__ wc = g.cells + ((int64_t)wJ * L0.nI + wI) * 96;
+            const float qx = wc[lane], qy = wc[32 + lane], qz = wc[64 + lane];
+            const int64_t qj0 = (int64_t)wJ * GZB_TILE_J, qi0 = (int64_t)wI * GZB_TILE_I;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                const float ux = __shfl_sync(0xffffffffu, qx, k);
+                const float uy = __shfl_sync(0xffffffffu, qy, k);
+                const float uz = __shfl_sync(0xffffffffu, qz, k);
+                const int64_t qj = qj0 + (k >> 3), qi = qi0 + (k & 7);
+                const int64_t aj = qj - j, ai = qi - i;
+                const bool inside = (aj >= -2) && (aj <= 2) && (ai >= -2) && (ai <= 2);
+                const float dx = x - ux, dy = y - uy, dz = z - uz;
+                const float d2 = dx * dx + dy * dy + dz * dz;     // padded cells sit at 1e3: never the minimum
+                if (!inside) m2 = fminf(m2, d2);
+            }
+        }
+    }
+    if (ok) {
+        float v = fminf(far, sqrtf(m2) - 5.0e-7f) * (1.0f - 1.0e-6f);
+        if (!(v > 0.0f)) v = 0.0f;        // also catches NaN
+        cellv[j * g.Ni + i].w = v;
+    }
+}
+
+// host side: geometry of the table from the extent, allocation, scatter and hole filling
+static int build_lut(gzb_ctx* ctx, const unsigned long long* ext) {
+    GzbGrid& g = ctx->g;
+    g.lut.bins = nullptr;
+    const double n = (double)g.Nj * (double)g.Ni;
+    if (n >= 4294967295.0) return GZB_OK;                    // flat indices must fit 32 bits
+    const double lat_min = ord_dec(ext[0]), lat_max = ord_dec(ext[1]);
+    const double a_min = ord_dec(ext[2]), a_max = ord_dec(ext[3]);
+    const double b_min = ord_dec(ext[4]), b_max = ord_dec(ext[5]);
+    if (!(lat_max >= lat_min) || !(a_max >= a_min) || !(b_max >= b_min)) return GZB_OK;
+    GzbLut L;
+    const double span_a = a_max - a_min, span_b = b_max - b_min;
+    if (fmin(span_a, span_b) > 300.0) {
+        L.wrap = 1; L.lon0 = 0.0; L.lon_span = 360.0;
+    } else if (span_a <= span_b) {
+        L.wrap = 0; L.lon0 = a_min; L.lon_span = span_a;
+    } else {
+        L.wrap = 0; L.lon0 = b_min - 180.0; L.lon_span = span_b;
+    }
+    const double lat_span = lat_max - lat_min;
+    L.lat0 = lat_min;
+    double d = sqrt(fmax(lat_span, 1.0e-9) * fmax(L.lon_span, 1.0e-9) / n);     // ~ one cell per bin
+    if (!(d > 1.0e-7)) d = 1.0e-7;
+    for (;;) {
+        const double nb = ceil(fmax(lat_span / d, 1.0)) * ceil(fmax(L.lon_span / d, 1.0));
+        if (nb <= 134217728.0) break;
+        d *= 1.25;
+    }
+    L.nlat = (int)fmax(1.0, ceil(lat_span / d));
+    L.nlon = (int)fmax(1.0, ceil(L.lon_span / d));
+    L.inv_d = 1.0 / d;
+    const size_t nb = (size_t)L.nlat * (size_t)L.nlon;
+    for (int k = 0; k < 2; ++k) {
+        cudaError_t e = cudaMalloc((void**)&ctx->d_lut[k], nb * sizeof(unsigned));
+        if (e != cudaSuccess) {             // not fatal: the warp walk needs no table
+            cudaGetLastError();
+            for (int q = 0; q < 2; ++q) { cudaFree(ctx->d_lut[q]); ctx->d_lut[q] = nullptr; }
+            return GZB_OK;
+        }
+    }
+    cudaStream_t s = ctx->stream;
+    GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_lut[0], 0xff, nb * sizeof(unsigned), s));
+    L.bins = nullptr;
+    const int64_t cells = g.Nj * g.Ni;
+    k_lut_scatter<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(g, L, ctx->d_lut[0]);
+    GZB_LAUNCH_CHECK(ctx);
+    int cur = 0;
+    const int steps[6] = {1, 1, 2, 4, 8, 16};
+    for (int q = 0; q < 6; ++q) {
+        k_lut_fill<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(L, ctx->d_lut[cur], ctx->d_lut[cur ^ 1], steps[q]);
+        GZB_LAUNCH_CHECK(ctx);
+        cur ^= 1;
+    }
+    L.bins = ctx->d_lut[cur];
+    g.lut = L;
+    ctx->stats.lut_bins = (int64_t)nb;
+    return GZB_OK;
+}
+
 static int build_pyramid(gzb_ctx* ctx) {
     GzbGrid& g = ctx->g;
     // level geometry
@@ -236,8 +449,24 @@ static int build_pyramid(gzb_ctx* ctx) {
             g.cert = ctx->d_cert;
         }
     }
+    {   // per-cell vectors + certificates of the per-thread search (optional: skipped when out of memory)
+        cudaError_t e = cudaMalloc((void**)&ctx->d_cellv, (size_t)g.Nj * (size_t)g.Ni * sizeof(float4));
+        if (e != cudaSuccess) { cudaGetLastError(); ctx->d_cellv = nullptr; }
+        g.cellv = ctx->d_cellv;
+    }
+    unsigned long long* d_ext = (unsigned long long*)(ctx->d_flags + 48);     // 6 words at byte 192, 8-byte aligned
+    {
+        unsigned long long* h_ext = (unsigned long long*)((char*)ctx->pinned + 256);
+        for (int q = 0; q < 6; ++q) h_ext[q] = (q & 1) ? 0ull : ~0ull;
+        GZB_CUDA(ctx, cudaMemcpyAsync(d_ext, h_ext, 48, cudaMemcpyHostToDevice, ctx->stream));
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+        k_extent<<<nsm * 8, 256, 0, ctx->stream>>>(g.Nj * g.Ni, g.lat, g.lon, d_ext);
+        GZB_LAUNCH_CHECK(ctx);
+        GZB_CUDA(ctx, cudaMemcpyAsync(h_ext, d_ext, 48, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     int* d_bad = (int*)ctx->d_cert;     // the certificate array is filled last; borrow its first word
-    k_build_leaves<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cells, ctx->d_nodes[0], d_bad);
+    k_build_leaves<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cells, ctx->d_nodes[0], ctx->d_cellv, d_bad);
     GZB_LAUNCH_CHECK(ctx);
     GZB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 128, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -248,7 +477,14 @@ static int build_pyramid(gzb_ctx* ctx) {
         k_build_level<<<(unsigned)((nn + 7) / 8), 256, 0, ctx->stream>>>(g, k, k == g.nlev - 1 ? 1 : 0);
         GZB_LAUNCH_CHECK(ctx);
     }
-    return gzb_build_cert(ctx);
+    int rc = gzb_build_cert(ctx);
+    if (rc != GZB_OK) return rc;
+    if (ctx->d_cellv) {
+        if ((rc = build_lut(ctx, (const unsigned long long*)((char*)ctx->pinned + 256))) != GZB_OK) return rc;
+        k_cellcert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cellv);
+        GZB_LAUNCH_CHECK(ctx);
+    }
+    return GZB_OK;
 }
 
 // ======================================================================== create / destroy
@@ -341,6 +577,9 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     cudaFree(ctx->d_mask);
     cudaFree(ctx->d_cells);
     cudaFree(ctx->d_cert);
+    cudaFree(ctx->d_cellv);
+    cudaFree(ctx->d_lut[0]);
+    cudaFree(ctx->d_lut[1]);
     cudaFree(ctx->d_flags);
     for (int k = 0; k < GZB_MAXLEV; ++k) cudaFree(ctx->d_nodes[k]);
     cudaFree(ctx->arena.base);
@@ -393,11 +632,16 @@ extern "C" int gzb_get_stats(const gzb_ctx* ctx_c, gzb_stats* out) {
     if (!ctx || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_get_stats: null argument");
     if (ctx->nearest_stats_pending) {      // left in the persistent device flags by gzb_nearest
         if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
-        GZB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->d_flags + 8, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        GZB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->d_flags + 8, 56, cudaMemcpyDeviceToHost, ctx->stream));
         GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const long long* w = (const long long*)ctx->pinned;
         ctx->stats.last_breaks = w[0];
         ctx->stats.last_chain_steps = w[1];
+        ctx->stats.last_unresolved = w[2];
+        ctx->stats.last_unres_noseed = w[3];
+        ctx->stats.last_unres_noconv = w[4];
+        ctx->stats.last_unres_nocert = w[5];
+        ctx->stats.last_max_chain = w[6];
         ctx->nearest_stats_pending = 0;
     }
     *out = ctx->stats;
@@ -407,6 +651,7 @@ extern "C" int gzb_get_stats(const gzb_ctx* ctx_c, gzb_stats* out) {
 extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: null argument");
     if (!strcmp(name, "zero_copy")) { ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
+    if (!strcmp(name, "nearest_path")) { ctx->nearest_path = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "edge_exclusion")) { ctx->edge_exclusion = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "force_heavy")) { ctx->force_heavy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
     return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: unknown option '%s'", name);

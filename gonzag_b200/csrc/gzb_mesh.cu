@@ -53,17 +53,14 @@ __device__ __forceinline__ bool strictly_in_quad(double py, double px, const dou
     return wn != 0;
 }
 
-__global__ void __launch_bounds__(128)
-k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-              const long long* __restrict__ NP, long long* __restrict__ SM, const int force_heavy) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nt) return;
-    const long long jP = NP[2 * t], iP = NP[2 * t + 1];
-    long long cj[4], ci[4];
-    longlong2* out = reinterpret_cast<longlong2*>(SM + 8 * t);
+// source mesh of one point: corners P1(nearest)..P4 counter-clockwise, all -1 when no quadrant
+// is found, all 0 when the nearest point itself was not found
+__device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double yT, const double xT,
+                                                const long long jP, const long long iP, const int force_heavy,
+                                                long long* cj, long long* ci) {
     if (jP == -1 && iP == -1) {   // nearest point not found: the row stays zero
-        const longlong2 z = make_longlong2(0, 0);
-        out[0] = z; out[1] = z; out[2] = z; out[3] = z;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cj[k] = 0; ci[k] = 0; }
         return;
     }
     int iq = -1;
@@ -75,19 +72,19 @@ k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt
         else if (im < 0 || jm < 0 || ip > g.Ni - 1) usable = false;
     }
     if (usable) {
-        const double yT = yt[t], xT = xt[t];
         const double lat0 = g.lat[jP * g.Ni + iP], lonP = g.lon[jP * g.Ni + iP];
         const double latN = g.lat[jp * g.Ni + iP], lonN = g.lon[jp * g.Ni + iP];
         const double latE = g.lat[jP * g.Ni + ip], lonE = g.lon[jP * g.Ni + ip];
         const double latS = g.lat[jm * g.Ni + iP], lonS = g.lon[jm * g.Ni + iP];
         const double latW = g.lat[jP * g.Ni + im], lonW = g.lon[jP * g.Ni + im];
-        const double lon0 = gzb_pymod(lonP, 360.0);
-        const double zT = gzb_pymod(xT, 360.0);
-        const double ht = gzb_heading_dev(lat0, lon0, yT, zT);
-        double hN = gzb_heading_dev(lat0, lon0, latN, gzb_pymod(lonN, 360.0));
-        const double hE = gzb_heading_dev(lat0, lon0, latE, gzb_pymod(lonE, 360.0));
-        const double hS = gzb_heading_dev(lat0, lon0, latS, gzb_pymod(lonS, 360.0));
-        const double hW = gzb_heading_dev(lat0, lon0, latW, gzb_pymod(lonW, 360.0));
+        // five headings from P (to the target and to the N, E, S, W neighbours): the Mercator
+        // ordinate of P is common to all of them
+        const double y0 = gzb_merc_y(lat0), x0 = gzb_pymod(lonP, 360.0) * GZB_D2R;
+        const double ht = gzb_heading_y(y0, x0, gzb_merc_y(yT), gzb_pymod(xT, 360.0) * GZB_D2R);
+        double hN = gzb_heading_y(y0, x0, gzb_merc_y(latN), gzb_pymod(lonN, 360.0) * GZB_D2R);
+        const double hE = gzb_heading_y(y0, x0, gzb_merc_y(latE), gzb_pymod(lonE, 360.0) * GZB_D2R);
+        const double hS = gzb_heading_y(y0, x0, gzb_merc_y(latS), gzb_pymod(lonS, 360.0) * GZB_D2R);
+        const double hW = gzb_heading_y(y0, x0, gzb_merc_y(latW), gzb_pymod(lonW, 360.0) * GZB_D2R);
         const double hz = gzb_pm180(ht);
         if (hN > hE) hN = hN - 360.0;
         if (force_heavy < 2) {
@@ -120,28 +117,21 @@ k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cj[k] = -1; ci[k] = -1; }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) out[k] = make_longlong2(cj[k], ci[k]);
 }
 
 __device__ __forceinline__ long long pywrap(long long k, long long n) { return k < 0 ? k + n : k; }
 
-__global__ void __launch_bounds__(128)
-k_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-          const long long* __restrict__ SM, double* __restrict__ WB) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nt) return;
-    const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
-    double w1 = 1.0, w2 = 0.0, w3 = 0.0, w4 = 0.0;
-    const longlong2 p1 = sm[0];
-    if (p1.x >= 0) {
+// bilinear weights of one point inside its source mesh (gonzag/bilin_mapping.py:490-527)
+__device__ __forceinline__ void weights_one(const GzbGrid& g, const double yT, const double xT,
+                                            const long long* cj, const long long* ci, double* w) {
+    w[0] = 1.0; w[1] = 0.0; w[2] = 0.0; w[3] = 0.0;
+    if (cj[0] >= 0) {
         double vy[5], vx[5];
-        vy[0] = yt[t];
-        vx[0] = xt[t];
+        vy[0] = yT;
+        vx[0] = xT;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const longlong2 p = sm[k];
-            long long j = pywrap(p.x, g.Nj), i = pywrap(p.y, g.Ni);
+            long long j = pywrap(cj[k], g.Nj), i = pywrap(ci[k], g.Ni);
             j = j < 0 ? 0 : (j >= g.Nj ? g.Nj - 1 : j);
             i = i < 0 ? 0 : (i >= g.Ni ? g.Ni - 1 : i);
             vy[k + 1] = g.lat[j * g.Ni + i];
@@ -149,14 +139,72 @@ k_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, co
         }
         double a, b;
         gzb_alfabeta_dev(vy, vx, a, b);
-        w1 = (1.0 - a) * (1.0 - b);
-        w2 = a * (1.0 - b);
-        w3 = a * b;
-        w4 = (1.0 - a) * b;
+        w[0] = (1.0 - a) * (1.0 - b);
+        w[1] = a * (1.0 - b);
+        w[2] = a * b;
+        w[3] = (1.0 - a) * b;
     }
+}
+
+__global__ void __launch_bounds__(128)
+k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+              const long long* __restrict__ NP, long long* __restrict__ SM, const int force_heavy) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    long long cj[4], ci[4];
+    source_mesh_one(g, yt[t], xt[t], NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
+    longlong2* out = reinterpret_cast<longlong2*>(SM + 8 * t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = make_longlong2(cj[k], ci[k]);
+}
+
+__global__ void __launch_bounds__(128)
+k_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+          const long long* __restrict__ SM, double* __restrict__ WB) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
+    long long cj[4], ci[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const longlong2 p = sm[k];
+        cj[k] = p.x;
+        ci[k] = p.y;
+    }
+    double w[4];
+    weights_one(g, yt[t], xt[t], cj, ci, w);
     double2* out = reinterpret_cast<double2*>(WB + 4 * t);
-    out[0] = make_double2(w1, w2);
-    out[1] = make_double2(w3, w4);
+    out[0] = make_double2(w[0], w[1]);
+    out[1] = make_double2(w[2], w[3]);
+}
+
+// K2 + K3 in one pass (what gzb_mapping runs): the mesh never travels through HBM between them
+__global__ void __launch_bounds__(128)
+k_mesh_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+               const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
+               const int force_heavy) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const double yT = yt[t], xT = xt[t];
+    long long cj[4], ci[4];
+    source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
+    longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sm[k] = make_longlong2(cj[k], ci[k]);
+    double w[4];
+    weights_one(g, yT, xT, cj, ci, w);
+    double2* out = reinterpret_cast<double2*>(WB + 4 * t);
+    out[0] = make_double2(w[0], w[1]);
+    out[1] = make_double2(w[2], w[3]);
+}
+
+int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
+                         int64_t* sm_out, double* wb_out) {
+    if (nt <= 0) return GZB_OK;
+    k_mesh_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
+                                                                         (long long*)sm_out, wb_out, ctx->force_heavy);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
 }
 
 int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,

@@ -310,6 +310,294 @@ k_global(const GzbGrid g, const long long nt, const double* __restrict__ yt, con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K1, fast path: one THREAD per track point.
+//   seed   the lat-lon look-up table gives a cell lying in (or next to) the point's bin;
+//   climb  evaluate the 5x5 index neighbourhood of the current cell (fp32 chord^2 from the
+//          row-major float4 array), move to its best cell, until the centre itself is the best;
+//   prove  cellv[c].w bounds from below the chord from c to every cell outside its 5x5
+//          neighbourhood, so  w - |p - c| > B  proves that no outside cell can tie or beat the
+//          best inside one (B = the fp32 candidate bound, as in the warp search);
+//   exact  the winner (and any other cell within the fp32 margin) goes through the reference's
+//          fp64 haversine; first-index tie-break.
+// Points without a seed, not converged in FAST_MAXIT moves, or not proven (duplicated E-W columns,
+// strongly anisotropic cells, targets outside the grid) are appended to `ulist` with the last
+// cell as a hint for the warp-cooperative search (k_near_slow).
+#define FAST_MAXIT 32
+
+// chord^2 (fp32 proxy) from the target to cell (j+DJ, i+DI); c0 points at cell (j, i)
+template <bool CHECK, int DJ, int DI>
+__device__ __forceinline__ float fast_cell(const GzbGrid& g, const float4* __restrict__ c0, const int j, const int i,
+                                           const float px, const float py, const float pz) {
+    if (CHECK) {
+        if ((unsigned)(j + DJ) >= (unsigned)g.Nj || (unsigned)(i + DI) >= (unsigned)g.Ni) return INFINITY;
+    }
+    const float4 v = __ldg(c0 + ((long long)DJ * g.Ni + DI));
+    const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+}
+
+#define FAST_UPD(P, DJ, DI)                          \
+    {                                                \
+        const float P__ = (P);                       \
+        if (P__ < nb) { nb = P__; mj = (DJ); mi = (DI); } \
+    }
+
+// 3x3 step around (j, i): moves (j, i) to the best of the 8 neighbours when it is strictly
+// better than the centre (returns 1), else returns 0 with Pc = chord^2 of the centre, cw = its
+// certificate, nb8 = the smallest chord^2 among the 8 neighbours.
+template <bool CHECK>
+__device__ __forceinline__ int fast_step3(const GzbGrid& g, const float px, const float py, const float pz,
+                                          int& j, int& i, float& Pc, float& cw, float& nb8) {
+    const float4* __restrict__ c0 = g.cellv + ((long long)j * g.Ni + i);
+    const float4 vc = __ldg(c0);
+    {
+        const float dx = px - vc.x, dy = py - vc.y, dz = pz - vc.z;
+        Pc = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+        cw = vc.w;
+    }
+    float nb = INFINITY;
+    int mj = 0, mi = 0;
+    FAST_UPD((fast_cell<CHECK, -1, -1>(g, c0, j, i, px, py, pz)), -1, -1)
+    FAST_UPD((fast_cell<CHECK, -1, 0>(g, c0, j, i, px, py, pz)), -1, 0)
+    FAST_UPD((fast_cell<CHECK, -1, 1>(g, c0, j, i, px, py, pz)), -1, 1)
+    FAST_UPD((fast_cell<CHECK, 0, -1>(g, c0, j, i, px, py, pz)), 0, -1)
+    FAST_UPD((fast_cell<CHECK, 0, 1>(g, c0, j, i, px, py, pz)), 0, 1)
+    FAST_UPD((fast_cell<CHECK, 1, -1>(g, c0, j, i, px, py, pz)), 1, -1)
+    FAST_UPD((fast_cell<CHECK, 1, 0>(g, c0, j, i, px, py, pz)), 1, 0)
+    FAST_UPD((fast_cell<CHECK, 1, 1>(g, c0, j, i, px, py, pz)), 1, 1)
+    nb8 = nb;
+    if (nb < Pc) { j += mj; i += mi; return 1; }
+    return 0;
+}
+
+// the 16 cells of the outer ring of the 5x5 neighbourhood of (j, i): moves to the best of them
+// when it beats the centre (returns 1), else returns 0 with ring = their smallest chord^2
+template <bool CHECK>
+__device__ __forceinline__ int fast_ring(const GzbGrid& g, const float px, const float py, const float pz,
+                                         int& j, int& i, const float Pc, float& ring) {
+    const float4* __restrict__ c0 = g.cellv + ((long long)j * g.Ni + i);
+    float nb = INFINITY;
+    int mj = 0, mi = 0;
+    FAST_UPD((fast_cell<CHECK, -2, -2>(g, c0, j, i, px, py, pz)), -2, -2)
+    FAST_UPD((fast_cell<CHECK, -2, -1>(g, c0, j, i, px, py, pz)), -2, -1)
+    FAST_UPD((fast_cell<CHECK, -2, 0>(g, c0, j, i, px, py, pz)), -2, 0)
+    FAST_UPD((fast_cell<CHECK, -2, 1>(g, c0, j, i, px, py, pz)), -2, 1)
+    FAST_UPD((fast_cell<CHECK, -2, 2>(g, c0, j, i, px, py, pz)), -2, 2)
+    FAST_UPD((fast_cell<CHECK, -1, -2>(g, c0, j, i, px, py, pz)), -1, -2)
+    FAST_UPD((fast_cell<CHECK, -1, 2>(g, c0, j, i, px, py, pz)), -1, 2)
+    FAST_UPD((fast_cell<CHECK, 0, -2>(g, c0, j, i, px, py, pz)), 0, -2)
+    FAST_UPD((fast_cell<CHECK, 0, 2>(g, c0, j, i, px, py, pz)), 0, 2)
+    FAST_UPD((fast_cell<CHECK, 1, -2>(g, c0, j, i, px, py, pz)), 1, -2)
+    FAST_UPD((fast_cell<CHECK, 1, 2>(g, c0, j, i, px, py, pz)), 1, 2)
+    FAST_UPD((fast_cell<CHECK, 2, -2>(g, c0, j, i, px, py, pz)), 2, -2)
+    FAST_UPD((fast_cell<CHECK, 2, -1>(g, c0, j, i, px, py, pz)), 2, -1)
+    FAST_UPD((fast_cell<CHECK, 2, 0>(g, c0, j, i, px, py, pz)), 2, 0)
+    FAST_UPD((fast_cell<CHECK, 2, 1>(g, c0, j, i, px, py, pz)), 2, 1)
+    FAST_UPD((fast_cell<CHECK, 2, 2>(g, c0, j, i, px, py, pz)), 2, 2)
+    ring = nb;
+    if (nb < Pc) { j += mj; i += mi; return 1; }
+    return 0;
+}
+
+// what k_near_search leaves per point for k_exact_flags (one 64-bit word):
+//   CAND_UNRES        handed to the warp search, which writes G/dG itself
+//   CAND_NONE         non-finite target: no nearest point
+//   flat | CAND_MULTI several cells of the 5x5 neighbourhood of `flat` are within the fp32 margin
+//   flat              the one candidate
+#define CAND_UNRES 0x4000000000000000LL
+#define CAND_NONE 0x2000000000000000LL
+#define CAND_MULTI 0x1000000000000000LL
+#define CAND_FLAT(v) ((v) & 0xfffffffffLL)
+
+__global__ void __launch_bounds__(128, 8)
+k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+              long long* __restrict__ cand, long long* __restrict__ ulist, unsigned* __restrict__ hint,
+              unsigned long long* __restrict__ ucount) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool unresolved = false;
+    unsigned myhint = 0xffffffffu;
+    if (t < nt) {
+        const double lat = yt[t], lon = xt[t];
+        long long out = CAND_NONE;
+        if (isfinite(lat) && isfinite(lon)) {
+            float px, py, pz;
+            {
+                const double la = lat * GZB_D2R, lo = lon * GZB_D2R;
+                double sa, ca, so, co;
+                sincos(la, &sa, &ca);
+                sincos(lo, &so, &co);
+                px = (float)(ca * co);
+                py = (float)(ca * so);
+                pz = (float)sa;
+            }
+            const unsigned seed = __ldg(g.lut.bins + gzb_lut_bin(g.lut, lat, lon));
+            int reason = 1;      // 1 no seed, 2 not converged, 3 not proven
+            if (seed != 0xffffffffu) {
+                int j = (int)(seed / (unsigned)g.Ni);
+                int i = (int)(seed - (unsigned)j * (unsigned)g.Ni);
+                const unsigned nj4 = g.Nj > 4 ? (unsigned)(g.Nj - 4) : 0u, ni4 = g.Ni > 4 ? (unsigned)(g.Ni - 4) : 0u;
+                const unsigned nj2 = (unsigned)(g.Nj - 2), ni2 = (unsigned)(g.Ni - 2);     // Nj, Ni >= 3
+                float Pc = 0.0f, cw = 0.0f, nb8 = INFINITY, ring = INFINITY;
+                bool conv = false;
+                int moves = 0;
+                for (;;) {
+                    // climb on 3x3 neighbourhoods; the lanes of a warp leave this loop together, so
+                    // that the 16 ring loads below are issued once per warp
+                    bool inner = (unsigned)(j - 1) < nj2 && (unsigned)(i - 1) < ni2;
+                    while (moves < FAST_MAXIT &&
+                           (inner ? fast_step3<false>(g, px, py, pz, j, i, Pc, cw, nb8)
+                                  : fast_step3<true>(g, px, py, pz, j, i, Pc, cw, nb8))) {
+                        ++moves;
+                        inner = (unsigned)(j - 1) < nj2 && (unsigned)(i - 1) < ni2;
+                    }
+                    if (moves >= FAST_MAXIT) break;
+                    const bool interior = (unsigned)(j - 2) < nj4 && (unsigned)(i - 2) < ni4;
+                    const int moved = interior ? fast_ring<false>(g, px, py, pz, j, i, Pc, ring)
+                                               : fast_ring<true>(g, px, py, pz, j, i, Pc, ring);
+                    if (!moved) { conv = true; break; }
+                    ++moves;
+                }
+                const long long f = (long long)j * g.Ni + i;
+                myhint = (unsigned)f;
+                reason = 2;
+                if (conv) {
+                    reason = 3;
+                    const float a = sqrtf(Pc);
+                    const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
+                    if ((cw - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
+                        reason = 0;
+                        out = f | ((fminf(nb8, ring) <= B * B) ? CAND_MULTI : 0LL);
+                    }
+                }
+            }
+            if (reason) {
+                unresolved = true;
+                out = CAND_UNRES;
+                atomicAdd(ucount + reason, 1ull);
+            }
+        }
+        cand[t] = out;
+    }
+    // warp-aggregated append of the unresolved points
+    const unsigned um = __ballot_sync(0xffffffffu, unresolved);
+    if (um) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == (__ffs(um) - 1)) base = atomicAdd(ucount, (unsigned long long)__popc(um));
+        base = __shfl_sync(0xffffffffu, base, __ffs(um) - 1);
+        if (unresolved) {
+            ulist[base + __popc(um & ((1u << lane) - 1u))] = t;
+            hint[t] = myhint;
+        }
+    }
+}
+
+// exact (reference formula, fp64) evaluation of the candidate(s) k_near_search left for point t:
+// returns the first-index argmin and its distance bits
+__device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long long c, const double lat, const double lon,
+                                                long long& bf, unsigned long long& bd) {
+    bf = GZB_NOFLAT;
+    bd = ~0ull;
+    if (c & CAND_NONE) return;
+    const double cpl = cos(lat * GZB_D2R);
+    const long long f0 = CAND_FLAT(c);
+    if (!(c & CAND_MULTI)) {
+        const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f0], g.lon[f0]);
+        if (d == d) { bd = (unsigned long long)__double_as_longlong(d); bf = f0; }
+        return;
+    }
+    // several cells within the fp32 margin of the best one: same proxy, same bound as the search
+    const double la = lat * GZB_D2R, lo = lon * GZB_D2R;
+    double sa, ca, so, co;
+    sincos(la, &sa, &ca);
+    sincos(lo, &so, &co);
+    const float px = (float)(ca * co), py = (float)(ca * so), pz = (float)sa;
+    const long long j = f0 / g.Ni, i = f0 - j * g.Ni;
+    float B2;
+    {
+        const float4 v = __ldg(g.cellv + f0);
+        const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+        const float a = sqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)));
+        const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
+        B2 = B * B;
+    }
+    for (int dj = -2; dj <= 2; ++dj) {
+        const long long jj = j + dj;
+        if (jj < 0 || jj >= g.Nj) continue;
+        for (int di = -2; di <= 2; ++di) {
+            const long long ii = i + di;
+            if (ii < 0 || ii >= g.Ni) continue;
+            const long long f = jj * g.Ni + ii;
+            const float4 v = __ldg(g.cellv + f);
+            const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+            const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+            if (!(P <= B2)) continue;
+            const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f], g.lon[f]);
+            if (!(d == d)) continue;
+            const unsigned long long db = (unsigned long long)__double_as_longlong(d);
+            if (db < bd) { bd = db; bf = f; }     // row-major scan: the first index keeps a tie
+        }
+    }
+}
+
+// K1, slow path: the warp-cooperative search (seeded window, then pyramid) for the listed points.
+// A warp takes K list entries at a time (K chosen so that every warp of the grid has work).
+__global__ void __launch_bounds__(256)
+k_near_slow(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
+            long long* __restrict__ G, double* __restrict__ dG, const long long* __restrict__ ulist,
+            const unsigned* __restrict__ hint, const unsigned long long* __restrict__ ucount) {
+    __shared__ WarpSm ws[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSm& w = ws[warp];
+    const long long nu = (long long)*ucount;
+    if (nu <= 0) return;
+    const long long nwarps = (long long)gridDim.x * 8;
+    long long K = (nu + nwarps - 1) / nwarps;
+    K = K < 1 ? 1 : (K > 32 ? 32 : K);
+    const long long nchunk = (nu + K - 1) / K;
+    for (long long ch = (long long)blockIdx.x * 8 + warp; ch < nchunk; ch += nwarps) {
+        const long long u0 = ch * K;
+        const int n = (int)((nu - u0 < K) ? (nu - u0) : K);
+        Owner me;
+        float mpx = 0.f, mpy = 0.f, mpz = 0.f;
+        me.plat = me.plon = me.cpl = 0.0;
+        long long idx = 0;
+        int hJ = -1, hI = -1;
+        if (lane < n) {
+            idx = ulist[u0 + lane];
+            owner_point(yt[idx], xt[idx], me, mpx, mpy, mpz);
+            const unsigned h = hint[idx];
+            if (h != 0xffffffffu) {
+                const long long hj = (long long)(h / (unsigned long long)g.Ni);
+                hJ = (int)(hj >> 2);
+                hI = (int)(((long long)h - hj * g.Ni) >> 3);
+            }
+        }
+        w.bd[lane] = ~0ull;
+        w.bf[lane] = GZB_NOFLAT;
+        w.pb2[lane] = INFINITY;
+        __syncwarp();
+        int qn = 0;
+        for (int q = 0; q < n; ++q) {
+            Srch s;
+            srch_init(s, __shfl_sync(0xffffffffu, mpx, q), __shfl_sync(0xffffffffu, mpy, q),
+                      __shfl_sync(0xffffffffu, mpz, q));
+            const int sJ = __shfl_sync(0xffffffffu, hJ, q), sI = __shfl_sync(0xffffffffu, hI, q);
+            bool proven = false;
+            if (sJ >= 0) proven = window_search<M_GLOBAL>(g, w, lane, s, q, sJ, sI, 0, 0, 0, 0, qn, me);
+            if (!proven) pyramid_search<M_GLOBAL>(g, w, lane, s, q, 0, 0, 0, 0, qn, me);
+        }
+        flush_queue(g, w, lane, qn, me);
+        if (lane < n) {
+            G[idx] = w.bf[lane];
+            dG[idx] = __longlong_as_double((long long)w.bd[lane]);
+        }
+        __syncwarp();
+    }
+}
+
 // certificate of every leaf tile: chord from its centre to the nearest cell outside its window
 __global__ void __launch_bounds__(256)
 k_cert(const GzbGrid g, float* __restrict__ cert) {
@@ -370,16 +658,39 @@ __device__ __forceinline__ bool clamp_box(const GzbGrid& g, const long long pj, 
     return (j0 < j1) && (i0 < i1);
 }
 
-// K1c, step 1: speculative chain + break detection.  One thread per point.
-__global__ void __launch_bounds__(1024)
+// K1c, step 1: speculative chain + break detection.  One thread per point.  With `cand` (the
+// per-thread search ran) the thread first settles its own point: exact fp64 evaluation of the
+// candidate(s), G/dG written here; the predecessor's values come through shared memory.
+#define FLAGS_BLOCK 256
+__global__ void __launch_bounds__(FLAGS_BLOCK)
 k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
-        const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
+        const double* __restrict__ xt, const long long* __restrict__ cand, long long* G, double* dG,
         long long* __restrict__ NP, unsigned char* __restrict__ brk, int* __restrict__ counts) {
+    __shared__ long long sf[FLAGS_BLOCK];
+    __shared__ double sd[FLAGS_BLOCK];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int isb = 0;
+    long long f = GZB_NOFLAT;
+    double d = __longlong_as_double(-1LL);
+    if (t < nt) {
+        const long long c = cand ? cand[t] : CAND_UNRES;
+        if (c & CAND_UNRES) {
+            f = G[t];
+            d = dG[t];
+        } else {
+            unsigned long long bd;
+            exact_from_cand(g, c, yt[t], xt[t], f, bd);
+            d = __longlong_as_double((long long)bd);
+            G[t] = f;
+            dG[t] = d;
+        }
+    }
+    sf[threadIdx.x] = f;
+    sd[threadIdx.x] = d;
+    __syncthreads();
     if (t < nt) {
         long long ej, ei;
-        accept_edge(g, G[t], dG[t], p.thr2, ej, ei, p.edge);
+        accept_edge(g, f, d, p.thr2, ej, ei, p.edge);
         NP[2 * t] = ej;
         NP[2 * t + 1] = ei;
         long long pj, pi;
@@ -387,12 +698,29 @@ k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* _
             pj = p.seed_j;
             pi = p.seed_i;
         } else {
-            accept_edge(g, G[t - 1], dG[t - 1], p.thr2, pj, pi, p.edge);
+            long long pf;
+            double pd;
+            if (threadIdx.x > 0) {
+                pf = sf[threadIdx.x - 1];
+                pd = sd[threadIdx.x - 1];
+            } else {
+                // the predecessor belongs to the previous block, which may not have written G/dG yet:
+                // settle it again from its candidate word
+                const long long c = cand ? cand[t - 1] : CAND_UNRES;
+                if (c & CAND_UNRES) {
+                    pf = G[t - 1];
+                    pd = dG[t - 1];
+                } else {
+                    unsigned long long bd;
+                    exact_from_cand(g, c, yt[t - 1], xt[t - 1], pf, bd);
+                    pd = __longlong_as_double((long long)bd);
+                }
+            }
+            accept_edge(g, pf, pd, p.thr2, pj, pi, p.edge);
         }
         if (pj != 0 && pi != 0) {   // Python truthiness of (j_prv and i_prv)
             long long j0, j1, i0, i1;
             if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
-                const long long f = G[t];
                 const long long gj = f / g.Ni, gi = f - gj * g.Ni;
                 const bool inside = (f != GZB_NOFLAT) && gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
                 if (!inside) {
@@ -455,7 +783,7 @@ k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, c
 }
 
 // ordered compaction of the break indices
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(FLAGS_BLOCK)
 k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ offsets, const long long nt,
           long long* __restrict__ breaks) {
     __shared__ int wcnt[32];
@@ -466,7 +794,7 @@ k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ o
     if (lane == 0) wcnt[warp] = __popc(m);
     __syncthreads();
     if (warp == 0) {
-        int ww = wcnt[lane];
+        int ww = lane < (int)(blockDim.x >> 5) ? wcnt[lane] : 0;
         int s = ww;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -483,12 +811,19 @@ k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ o
 __device__ __forceinline__ void chain_step(const GzbGrid& g, WarpSm& w, const int lane, const NearParams& p,
                                            const long long t, const long long pj, const long long pi,
                                            const double* __restrict__ yt, const double* __restrict__ xt,
-                                           const long long ej, const long long ei, long long& rj, long long& ri) {
+                                           const long long gflat, const long long ej, const long long ei,
+                                           long long& rj, long long& ri) {
     rj = ej;
     ri = ei;
     if (pj != 0 && pi != 0) {
         long long j0, j1, i0, i1;
         if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
+            // the global nearest point lies inside the box: the box pass finds that very point, so
+            // R(t) = E(t) whatever its distance (DESIGN.md, K1 key fact) -- no search needed
+            if (gflat != GZB_NOFLAT) {
+                const long long gj = gflat / g.Ni, gi = gflat - gj * g.Ni;
+                if (gj >= j0 && gj < j1 && gi >= i0 && gi < i1) return;
+            }
             Owner me;
             float px, py, pz;
             owner_point(yt[t], xt[t], me, px, py, pz);
@@ -577,7 +912,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
         for (;;) {
             long long ej, ei, rj, ri;
             accept_edge(g, G[t], dG[t], p.thr2, ej, ei, p.edge);
-            chain_step(g, ws[warp], lane, p, t, pj, pi, yt, xt, ej, ei, rj, ri);
+            chain_step(g, ws[warp], lane, p, t, pj, pi, yt, xt, G[t], ej, ei, rj, ri);
             ++n;
             if (WRITE) {
                 if (lane == 0) {
@@ -602,7 +937,10 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
             pi = ri;
             ++t;
         }
-        if (!WRITE && lane == 0) atomicAdd(steps, n);
+        if (!WRITE && lane == 0) {
+            atomicAdd(steps, n);
+            atomicMax(steps + 5, n);      // longest replay
+        }
     }
 }
 
@@ -642,6 +980,7 @@ k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop
     if (lane == 0) {      // (breaks, replay steps) of this call, for gzb_get_stats
         stats_out[0] = nbrk_p[0];
         stats_out[1] = nbrk_p[1];
+        for (int q = 2; q < 7; ++q) stats_out[q] = nbrk_p[q];   // k_near_fast: unresolved (total, no seed, not converged, not proven); longest replay
     }
 }
 
@@ -704,7 +1043,7 @@ k_corner(const GzbGrid g, const int r, double* __restrict__ out) {
 // ------------------------------------------------------------------------------------------
 size_t gzb_nearest_ws_bytes(int64_t nt) {
     const size_t n = (size_t)(nt > 0 ? nt : 1);
-    const size_t nblk = (n + 1023) / 1024;
+    const size_t nblk = (n + FLAGS_BLOCK - 1) / FLAGS_BLOCK;
     return gzb_align(n * 8) * 2      // G, dG
            + gzb_align(n)            // brk
            + gzb_align(nblk * 4) + gzb_align(nblk * 8)   // counts, offsets
@@ -712,6 +1051,7 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
            + gzb_align(n * 8)        // replay log
+           + gzb_align(n * 8) * 2 + gzb_align(n * 4)   // candidate words, unresolved list, hints
            + gzb_align(64) * 2;      // scalars, corner
 }
 
@@ -721,7 +1061,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     if (nt <= 0) return GZB_OK;
     if (np_box_r < 0) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_nearest: np_box_r must be >= 0");
     const size_t n = (size_t)nt;
-    const long long nblk = (long long)((n + 1023) / 1024);
+    const long long nblk = (long long)((n + FLAGS_BLOCK - 1) / FLAGS_BLOCK);
     long long* G = (long long*)gzb_arena_take(ctx, n * 8);
     double* dG = (double*)gzb_arena_take(ctx, n * 8);
     unsigned char* brk = (unsigned char*)gzb_arena_take(ctx, n);
@@ -732,6 +1072,9 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     long long* first = (long long*)gzb_arena_take(ctx, n * 16);
     unsigned char* valid = (unsigned char*)gzb_arena_take(ctx, n);
     unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
+    long long* candbuf = (long long*)gzb_arena_take(ctx, n * 8);
+    long long* ulist = (long long*)gzb_arena_take(ctx, n * 8);
+    unsigned* hint = (unsigned*)gzb_arena_take(ctx, n * 4);
     long long* scal = (long long*)gzb_arena_take(ctx, 64);
     if (!scal) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
     double* corner = (double*)(ctx->d_flags + 32);      // persistent: 4 doubles, keyed by np_box_r
@@ -762,19 +1105,30 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
 
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long long* cand = nullptr;
     // chunk length: long enough to amortise the unseeded first point, short enough to fill the GPU
     int K = 32;
     while (K > 4 && (long long)((n + K - 1) / K) < (long long)nsm * 8 * 4) K >>= 1;
     long long gblocks = (long long)(((n + K - 1) / K + 7) / 8);
     const long long gmax = (long long)nsm * 16;
     if (gblocks > gmax) gblocks = gmax;
-    k_global<<<(unsigned)gblocks, 256, 0, s>>>(ctx->g, nt, yt, xt, G, dG, K);
-    GZB_LAUNCH_CHECK(ctx);
-    k_flags<<<(unsigned)nblk, 1024, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, (long long*)np_out, brk, counts);
+    if (ctx->nearest_path && ctx->g.cellv && ctx->g.lut.bins) {
+        cand = candbuf;
+        k_near_search<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ctx->g, nt, yt, xt, candbuf, ulist, hint,
+                                                                 (unsigned long long*)(scal + 2));
+        GZB_LAUNCH_CHECK(ctx);
+        k_near_slow<<<(unsigned)(nsm * 4), 256, 0, s>>>(ctx->g, yt, xt, G, dG, ulist, hint,
+                                                       (const unsigned long long*)(scal + 2));
+        GZB_LAUNCH_CHECK(ctx);
+    } else {
+        k_global<<<(unsigned)gblocks, 256, 0, s>>>(ctx->g, nt, yt, xt, G, dG, K);
+        GZB_LAUNCH_CHECK(ctx);
+    }
+    k_flags<<<(unsigned)nblk, FLAGS_BLOCK, 0, s>>>(ctx->g, p, nt, yt, xt, cand, G, dG, (long long*)np_out, brk, counts);
     GZB_LAUNCH_CHECK(ctx);
     k_scan_counts<<<1, 1024, 0, s>>>(counts, offsets, nblk, scal);
     GZB_LAUNCH_CHECK(ctx);
-    k_compact<<<(unsigned)nblk, 1024, 0, s>>>(brk, offsets, nt, breaks);
+    k_compact<<<(unsigned)nblk, FLAGS_BLOCK, 0, s>>>(brk, offsets, nt, breaks);
     GZB_LAUNCH_CHECK(ctx);
     long long wblocks = (long long)((n + 7) / 8);
     const long long wmax = (long long)nsm * 8;

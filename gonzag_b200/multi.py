@@ -60,8 +60,8 @@ class CudaEngine:
 
     def mesh_weights(self, y, x, NP, SM, WB):
         n = y.numel()
-        self.ctx._ck(L.lib().gzb_source_mesh(self.ctx._h, n, self._p(y), self._p(x), self._p(NP), self._p(SM), L.GZB_DEVICE))
-        self.ctx._ck(L.lib().gzb_weights(self.ctx._h, n, self._p(y), self._p(x), self._p(SM), self._p(WB), L.GZB_DEVICE))
+        self.ctx._ck(L.lib().gzb_mesh_weights(self.ctx._h, n, self._p(y), self._p(x), self._p(NP), self._p(SM),
+                                              self._p(WB), L.GZB_DEVICE))
 
     def interp(self, t, SM, WB, tmod, slab, k0, v_np, v_bl):
         dt = L.GZB_F32 if slab.dtype == self.torch.float32 else L.GZB_F64

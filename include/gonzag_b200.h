@@ -46,6 +46,12 @@ typedef struct gzb_stats {
     int64_t  last_chain_steps;  /* last gzb_nearest: sequential replay steps, all chains     */
     int32_t  pyramid_levels;    /* depth of the bounding-sphere pyramid over the grid       */
     int32_t  reserved;
+    int64_t  lut_bins;          /* bins of the lat-lon seed table (0 = table not built)          */
+    int64_t  last_unresolved;   /* last gzb_nearest: points the per-thread search handed to the warp search */
+    int64_t  last_unres_noseed; /*   ... of which: no seed in the table                       */
+    int64_t  last_unres_noconv; /*   ... hill climb not converged                             */
+    int64_t  last_unres_nocert; /*   ... per-cell certificate not sufficient                  */
+    int64_t  last_max_chain;    /* last gzb_nearest: longest sequential replay (steps)         */
 } gzb_stats;
 
 const char* gzb_version(void);
@@ -73,6 +79,8 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
 /* options: "zero_copy": 1 (default) gzb_interp gathers straight from a pinned + mapped host slab
  * over PCIe when the track is sparse w.r.t. the slab, instead of copying the slab to the GPU;
  * 0 never; 2 whenever the slab is pinned + mapped.
+ * "nearest_path": 1 (default) per-thread hill climb seeded by a lat-lon table, proven by per-cell
+ * certificates, warp-cooperative search for the rest; 0 warp-cooperative search only (same results).
  * "edge_exclusion": 1 (default) gzb_nearest applies the first/last row/column rule of
  * BilinTrack.nrpt (gonzag/bilin_mapping.py:582-585); 0 gives plain NearestPoint() results.
  * "force_heavy": 0 (default); 1 = heavy-duty quadrant search as if |angle| > 45 everywhere;
@@ -109,6 +117,12 @@ int gzb_source_mesh(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
  * (gonzag/bilin_mapping.py:610-617, 490-527, 50-141).  wb_out: (nt,4) float64. */
 int gzb_weights(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
                 const int64_t* sm, double* wb_out, int where);
+
+/* K2+K3 in one kernel (BilinTrack.srcm() followed by BilinTrack.wght(),
+ * gonzag/bilin_mapping.py:562-563): same results as the two calls above, the mesh is written
+ * once and never re-read. */
+int gzb_mesh_weights(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
+                     const int64_t* np, int64_t* sm_out, double* wb_out, int where);
 
 /* K1+K2+K3 in one call (what BilinTrack.__init__ does, gonzag/bilin_mapping.py:554-564). */
 int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
