@@ -277,6 +277,7 @@ def run_ours(args, w):
     tmod_all = rec_dt * np.arange(nrec_all)
 
     ctx = gzb.GridContext(lat, lon, mask=mask, k_ew_per=2, device=local)
+    ctx.set_option("heading_table", args.heading_table)
     eng = CudaEngine(ctx, torch)
     mapper = ShardedMapper(eng, dist if world > 1 else None, torch)
     torch.cuda.synchronize()
@@ -356,8 +357,9 @@ def run_ours(args, w):
     step_ms = []
     barrier()
     for _ in range(args.steps):
-        flush.zero_()                      # L2 flush between timed steps (not timed)
         barrier()
+        flush.zero_()                      # L2 flush between timed steps (not timed); the host enqueues
+        flush.zero_()                      # the step while it runs, so launch latency stays out of the events
         e0.record()
         step()
         e1.record()
@@ -375,10 +377,14 @@ def run_ours(args, w):
 
     # ---- per-stage timing (rank 0 workload, no collectives), L2 flushed before each launch
     def time_stage(fn, reps=5):
+        # the L2 flush (a 256 MiB write, ~80 us) runs on the same stream just before the stage: while
+        # it executes the host enqueues e0, the stage's launches and e1, so the events bracket the
+        # kernels and not the host's launch latency
         out = []
         for _ in range(reps):
-            flush.zero_()
             torch.cuda.synchronize()
+            flush.zero_()
+            flush.zero_()
             e0.record()
             fn()
             e1.record()
@@ -508,6 +514,8 @@ def run_ours(args, w):
                            "np_box_r": r, "rd_found_km": rd, "k_ew_per": 2,
                            "sharding": "contiguous time segments, grid replicated, 1 all-gather of (ssh_np, ssh_bl, NP)",
                            "l2": "flushed (256 MiB write) before every timed step and stage",
+                           "heading_table": ("K2 reads a per-cell table of the grid-only headings (48 B/cell), built once per grid "
+                                             "like the -D angle" if ctx.stats()["heading_table"] else "off"),
                            "seed_reseeds": mapper.reseeds, "verified": verified, "chain_breaks": int(ctx.stats()["last_breaks"]),
                            "chain_replay_steps": int(ctx.stats()["last_chain_steps"])},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "kernels": kern,
@@ -525,6 +533,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--heading-table", type=int, default=2, choices=[0, 1, 2],
+                    help="K2 per-cell heading table: 0 never, 1 auto (amortised), 2 built at grid set-up (default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check the sharded result against a single-GPU run")

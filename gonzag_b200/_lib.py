@@ -30,7 +30,8 @@ class Stats(C.Structure):
                 ("pyramid_levels", C.c_int32), ("reserved", C.c_int32),
                 ("lut_bins", C.c_int64), ("last_unresolved", C.c_int64),
                 ("last_unres_noseed", C.c_int64), ("last_unres_noconv", C.c_int64),
-                ("last_unres_nocert", C.c_int64), ("last_max_chain", C.c_int64)]
+                ("last_unres_nocert", C.c_int64), ("last_max_chain", C.c_int64),
+                ("heading_table", C.c_int64)]
 
 
 _P = C.c_void_p

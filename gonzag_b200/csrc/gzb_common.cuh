@@ -55,6 +55,8 @@ struct GzbGrid {
                             // centre to the nearest cell outside the tile's 5x3-tile neighbourhood
     const float4* cellv;    // per cell, row-major: unit vector (x,y,z) + w = lower bound of the chord
                             // from this cell to any cell outside its 5x5 index neighbourhood
+    const double* hdg;      // optional per-cell table of K2 (6 doubles per cell): Mercator ordinate and
+                            // longitude (radians, [0,2pi)) of the cell, headings to its N, E, S, W neighbours
     GzbLut lut;
     int nlev;
     GzbLevel lev[GZB_MAXLEV];
@@ -82,6 +84,12 @@ struct gzb_ctx {
     float* d_cert = nullptr;
     float4* d_cellv = nullptr;
     unsigned* d_lut[2] = {nullptr, nullptr};
+    unsigned* d_mbits = nullptr;     // land-sea mask as bits in 16x16-cell tiles (K4); d_flags[2] != 0: mask not {0,1}
+    int mask_bits_ok = 0;
+    double* d_hdg = nullptr;         // heading table of K2 (48 B per cell), built on demand
+    int hdg_mode = 1;                // 0 never, 1 when the points mapped on this grid outnumber its cells / 2, 2 at the next K2 call
+    int hdg_built = 0;
+    int64_t k2_points = 0;           // points that went through K2 on this context
     int nearest_path = 1;            // 1: per-thread hill climb seeded by the look-up table (+ warp fallback); 0: warp walk only
     GzbArena arena;
     void* pinned = nullptr;          // small pinned scratch for status words
@@ -125,6 +133,7 @@ int gzb_fail(gzb_ctx* ctx, int code, const char* fmt, ...);
 int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes);            // grow (contents lost), reset offset
 void* gzb_arena_take(gzb_ctx* ctx, size_t bytes);             // 256-byte aligned slice or null
 int gzb_use_device(gzb_ctx* ctx);
+int gzb_build_mask_bits(gzb_ctx* ctx);                        // gzb_interp.cu: after every change of the mask
 
 static inline size_t gzb_align(size_t n) { return (n + 255) & ~size_t(255); }
 
@@ -133,6 +142,9 @@ static inline size_t gzb_align(size_t n) { return (n + 255) & ~size_t(255); }
 
 // Python's float `%` (and numpy.remainder): result takes the sign of the divisor.
 __device__ __forceinline__ double gzb_pymod(double a, double b) {
+    // |a| < b, a != 0: fmod(a, b) == a exactly, so the general path below reduces to these two lines
+    if (a > 0.0 && a < b) return a;
+    if (a < 0.0 && -a < b) return a + b;
     double m = fmod(a, b);
     if (m != 0.0) {
         if ((b < 0.0) != (m < 0.0)) m += b;

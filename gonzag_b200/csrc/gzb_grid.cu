@@ -553,6 +553,7 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
         ctx->g.angle = ctx->d_angle;
         ctx->g.mask = ctx->d_mask;
         if ((rc = build_pyramid(ctx)) != GZB_OK) break;
+        if ((rc = gzb_build_mask_bits(ctx)) != GZB_OK) break;
         e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "grid upload / pyramid build: %s", cudaGetErrorString(e)); break; }
     } while (0);
@@ -580,6 +581,8 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     cudaFree(ctx->d_cellv);
     cudaFree(ctx->d_lut[0]);
     cudaFree(ctx->d_lut[1]);
+    cudaFree(ctx->d_hdg);
+    cudaFree(ctx->d_mbits);
     cudaFree(ctx->d_flags);
     for (int k = 0; k < GZB_MAXLEV; ++k) cudaFree(ctx->d_nodes[k]);
     cudaFree(ctx->arena.base);
@@ -653,12 +656,22 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "zero_copy")) { ctx->zero_copy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
     if (!strcmp(name, "nearest_path")) { ctx->nearest_path = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "edge_exclusion")) { ctx->edge_exclusion = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "heading_table")) {
+        ctx->hdg_mode = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
+        if (ctx->hdg_mode == 0) { ctx->g.hdg = nullptr; ctx->hdg_built = 0; ctx->stats.heading_table = 0; }
+        return GZB_OK;
+    }
     if (!strcmp(name, "force_heavy")) { ctx->force_heavy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
     return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: unknown option '%s'", name);
 }
 
 extern "C" int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_set_ew_per: null ctx");
+    if (ctx->g.kew != k_ew_per) {      // the neighbours of the edge columns change: drop the K2 table
+        ctx->g.hdg = nullptr;
+        ctx->hdg_built = 0;
+        ctx->stats.heading_table = 0;
+    }
     ctx->g.kew = k_ew_per;
     return GZB_OK;
 }
@@ -670,11 +683,13 @@ extern "C" int gzb_set_mask(gzb_ctx* ctx, const int8_t* mask, int where) {
     if (!ctx->d_mask) GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_mask, n));
     GZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, mask, n,
                                   where == GZB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->g.mask = ctx->d_mask;
+    const int rc = gzb_build_mask_bits(ctx);
+    if (rc != GZB_OK) return rc;
     if (where == GZB_HOST) {
         ctx->stats.h2d_bytes += n;
         GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    ctx->g.mask = ctx->d_mask;
     return GZB_OK;
 }
 

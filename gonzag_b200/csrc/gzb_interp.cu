@@ -8,23 +8,66 @@ __device__ __forceinline__ long long pywrap_idx(long long k, long long n) {
     return k < 0 ? 0 : (k >= n ? n - 1 : k);    // anything else out of range is clamped, never faults
 }
 
+// Land-sea mask as bits, tiled 16 x 16 cells (one 32-byte sector per tile): the four corners of a
+// source mesh almost always fall in one sector, and consecutive track points reuse it, where the
+// row-major byte mask costs two sectors per point.  flag[0] != 0: the mask holds values other
+// than {0,1}, the ocean test `sum == 4` must then read the bytes.
+__global__ void __launch_bounds__(256)
+k_mask_bits(const long long Nj, const long long Ni, const int8_t* __restrict__ mask, unsigned* __restrict__ bits,
+            int* __restrict__ flag) {
+    // one warp per tile row of 16 cells x 2 rows = one 32-bit word
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // word index
+    const long long ntI = (Ni + 15) >> 4, ntJ = (Nj + 15) >> 4;
+    if (w >= ntJ * ntI * 8) return;
+    const long long tile = w >> 3;
+    const int wr = (int)(w & 7);
+    const long long tj = tile / ntI, ti = tile - tj * ntI;
+    unsigned v = 0;
+    bool odd = false;
+#pragma unroll 4
+    for (int b = 0; b < 32; ++b) {
+        const long long j = tj * 16 + wr * 2 + (b >> 4), i = ti * 16 + (b & 15);
+        if (j < Nj && i < Ni) {
+            const int m = mask[j * Ni + i];
+            if (m == 1) v |= 1u << b;
+            else if (m != 0) odd = true;
+        }
+    }
+    bits[w] = v;
+    if (odd) atomicOr(flag, 1);
+}
+
+__device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const long long ntI, const long long j,
+                                        const long long i) {
+    const long long tile = (j >> 4) * ntI + (i >> 4);
+    const int b = (int)(((j & 15) << 4) | (i & 15));
+    return (int)((__ldg(bits + tile * 8 + (b >> 5)) >> (b & 31)) & 1u);
+}
+
 // One thread per track point.  T is the dtype of the model field: the time interpolation
 // x1 + ((x2 - x1) / dt) * (t - t1) is carried out in T (NumPy keeps float32 arrays in float32
 // when combined with Python floats), the weighted sum in float64, left to right, no FMA.
+// Loads are issued as early as their addresses are known (mesh and weights before the bracket
+// search, the eight field values together with the mask) so that a point costs two dependent
+// DRAM round trips, not four.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
          const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
          const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
          const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
-         int* __restrict__ err) {
+         int* __restrict__ err, const unsigned* __restrict__ mbits, const int* __restrict__ mflag) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
+    const double now = __ldg(t_sat + t);
+    const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
+    const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
+    const longlong2 p1 = sm[0], p2 = sm[1], p3 = sm[2], p4 = sm[3];
+    const double2 wa = wb[0], wc = wb[1];
     if (init) {
         out_np[t] = rmiss;
         out_bl[t] = rmiss;
     }
-    const double now = t_sat[t];
     if (!(now >= tmod[0]) || !(now < tmod[nrec - 1])) {
         atomicOr(err, 1);
         return;
@@ -35,25 +78,29 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
         if (tmod[mid] <= now) lo = mid; else hi = mid;
     }
     if (lo < k0 || lo + 1 >= k0 + nk) return;   // bracket not inside this slab
-    const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
-    const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
-    const longlong2 p1 = sm[0], p2 = sm[1], p3 = sm[2], p4 = sm[3];
-    const double2 wa = wb[0], wc = wb[1];
-    const long long c1 = pywrap_idx(p1.x, g.Nj) * g.Ni + pywrap_idx(p1.y, g.Ni);
-    const long long c2 = pywrap_idx(p2.x, g.Nj) * g.Ni + pywrap_idx(p2.y, g.Ni);
-    const long long c3 = pywrap_idx(p3.x, g.Nj) * g.Ni + pywrap_idx(p3.y, g.Ni);
-    const long long c4 = pywrap_idx(p4.x, g.Nj) * g.Ni + pywrap_idx(p4.y, g.Ni);
-    const int ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
-    if (ocean != 4) return;
+    const long long j1 = pywrap_idx(p1.x, g.Nj), i1 = pywrap_idx(p1.y, g.Ni);
+    const long long j2 = pywrap_idx(p2.x, g.Nj), i2 = pywrap_idx(p2.y, g.Ni);
+    const long long j3 = pywrap_idx(p3.x, g.Nj), i3 = pywrap_idx(p3.y, g.Ni);
+    const long long j4 = pywrap_idx(p4.x, g.Nj), i4 = pywrap_idx(p4.y, g.Ni);
+    const long long c1 = j1 * g.Ni + i1, c2 = j2 * g.Ni + i2, c3 = j3 * g.Ni + i3, c4 = j4 * g.Ni + i4;
     const long long cells = g.Nj * g.Ni;
     const T* __restrict__ X1 = slab + (lo - k0) * cells;
     const T* __restrict__ X2 = X1 + cells;
-    const T dt = (T)(tmod[lo + 1] - tmod[lo]);
-    const T de = (T)(now - tmod[lo]);
     const T a1 = X1[c1], b1 = X2[c1];
     const T a2 = X1[c2], b2 = X2[c2];
     const T a3 = X1[c3], b3 = X2[c3];
     const T a4 = X1[c4], b4 = X2[c4];
+    int ocean;
+    if (mbits && *mflag == 0) {
+        const long long ntI = (g.Ni + 15) >> 4;
+        ocean = mask_bit(mbits, ntI, j1, i1) + mask_bit(mbits, ntI, j2, i2) + mask_bit(mbits, ntI, j3, i3) +
+                mask_bit(mbits, ntI, j4, i4);
+    } else {
+        ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
+    }
+    if (ocean != 4) return;
+    const T dt = (T)(tmod[lo + 1] - tmod[lo]);
+    const T de = (T)(now - tmod[lo]);
     const T v1 = a1 + ((b1 - a1) / dt) * de;
     const T v2 = a2 + ((b2 - a2) / dt) * de;
     const T v3 = a3 + ((b3 - a3) / dt) * de;
@@ -64,12 +111,29 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
         out_bl[t] = ((wa.x * (double)v1 + wa.y * (double)v2) + wc.x * (double)v3) + wc.y * (double)v4;
 }
 
+int gzb_build_mask_bits(gzb_ctx* ctx) {
+    const long long Nj = ctx->g.Nj, Ni = ctx->g.Ni;
+    const long long nw = ((Nj + 15) >> 4) * ((Ni + 15) >> 4) * 8;
+    ctx->mask_bits_ok = 0;
+    if (!ctx->d_mask) return GZB_OK;
+    if (!ctx->d_mbits) {
+        cudaError_t e = cudaMalloc((void**)&ctx->d_mbits, (size_t)nw * sizeof(unsigned));
+        if (e != cudaSuccess) { cudaGetLastError(); ctx->d_mbits = nullptr; return GZB_OK; }   // K4 reads the bytes
+    }
+    GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 2, 0, 4, ctx->stream));
+    k_mask_bits<<<(unsigned)((nw + 255) / 256), 256, 0, ctx->stream>>>(Nj, Ni, ctx->d_mask, ctx->d_mbits, ctx->d_flags + 2);
+    GZB_LAUNCH_CHECK(ctx);
+    ctx->mask_bits_ok = 1;
+    return GZB_OK;
+}
+
 template <typename T>
 static int launch_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,
                          int64_t nrec, const double* tmod, const void* slab, int64_t k0, int64_t nk,
                          double rmiss, int init, double* np_out, double* bl_out, int* err) {
     k_interp<T><<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab, k0, nk, rmiss, init, np_out, bl_out, err);
+        ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab, k0, nk, rmiss, init, np_out, bl_out, err,
+        ctx->mask_bits_ok ? ctx->d_mbits : nullptr, ctx->d_flags + 2);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }

@@ -53,6 +53,36 @@ __device__ __forceinline__ bool strictly_in_quad(double py, double px, const dou
     return wn != 0;
 }
 
+// the grid-only part of Iquadran's light test (gonzag/bilin_mapping.py:377-397): Mercator ordinate
+// and longitude of P, loxodromic headings from P to its four neighbours, hN already brought below hE
+__device__ __forceinline__ void cell_frame(const GzbGrid& g, const long long jP, const long long iP,
+                                           const long long jm, const long long jp, const long long im,
+                                           const long long ip, double& y0, double& x0, double& hN, double& hE,
+                                           double& hS, double& hW) {
+    const double lat0 = g.lat[jP * g.Ni + iP], lonP = g.lon[jP * g.Ni + iP];
+    const double latN = g.lat[jp * g.Ni + iP], lonN = g.lon[jp * g.Ni + iP];
+    const double latE = g.lat[jP * g.Ni + ip], lonE = g.lon[jP * g.Ni + ip];
+    const double latS = g.lat[jm * g.Ni + iP], lonS = g.lon[jm * g.Ni + iP];
+    const double latW = g.lat[jP * g.Ni + im], lonW = g.lon[jP * g.Ni + im];
+    y0 = gzb_merc_y(lat0);
+    x0 = gzb_pymod(lonP, 360.0) * GZB_D2R;
+    hN = gzb_heading_y(y0, x0, gzb_merc_y(latN), gzb_pymod(lonN, 360.0) * GZB_D2R);
+    hE = gzb_heading_y(y0, x0, gzb_merc_y(latE), gzb_pymod(lonE, 360.0) * GZB_D2R);
+    hS = gzb_heading_y(y0, x0, gzb_merc_y(latS), gzb_pymod(lonS, 360.0) * GZB_D2R);
+    hW = gzb_heading_y(y0, x0, gzb_merc_y(latW), gzb_pymod(lonW, 360.0) * GZB_D2R);
+    if (hN > hE) hN = hN - 360.0;
+}
+
+// can a quadrant be looked for around (jP, iP)?  (all four neighbours exist)
+__device__ __forceinline__ bool mesh_usable(const GzbGrid& g, const long long jP, const long long iP, long long& jm,
+                                            long long& jp, long long& im, long long& ip) {
+    if (!(jP >= 0 && jP < g.Nj && iP >= 0 && iP < g.Ni)) return false;
+    neighbours(g, jP, iP, jm, jp, im, ip);
+    if (jm == -1 || jp == -1 || im == -1 || ip == -1) return false;
+    if (im < 0 || jm < 0 || ip > g.Ni - 1) return false;
+    return true;
+}
+
 // source mesh of one point: corners P1(nearest)..P4 counter-clockwise, all -1 when no quadrant
 // is found, all 0 when the nearest point itself was not found
 __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double yT, const double xT,
@@ -64,29 +94,22 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
         return;
     }
     int iq = -1;
-    bool usable = (jP >= 0 && jP < g.Nj && iP >= 0 && iP < g.Ni);
     long long jm = 0, jp = 0, im = 0, ip = 0;
+    const bool usable = mesh_usable(g, jP, iP, jm, jp, im, ip);
     if (usable) {
-        neighbours(g, jP, iP, jm, jp, im, ip);
-        if (jm == -1 || jp == -1 || im == -1 || ip == -1) usable = false;
-        else if (im < 0 || jm < 0 || ip > g.Ni - 1) usable = false;
-    }
-    if (usable) {
-        const double lat0 = g.lat[jP * g.Ni + iP], lonP = g.lon[jP * g.Ni + iP];
-        const double latN = g.lat[jp * g.Ni + iP], lonN = g.lon[jp * g.Ni + iP];
-        const double latE = g.lat[jP * g.Ni + ip], lonE = g.lon[jP * g.Ni + ip];
-        const double latS = g.lat[jm * g.Ni + iP], lonS = g.lon[jm * g.Ni + iP];
-        const double latW = g.lat[jP * g.Ni + im], lonW = g.lon[jP * g.Ni + im];
         // five headings from P (to the target and to the N, E, S, W neighbours): the Mercator
-        // ordinate of P is common to all of them
-        const double y0 = gzb_merc_y(lat0), x0 = gzb_pymod(lonP, 360.0) * GZB_D2R;
+        // ordinate of P is common to all of them; the four that depend on the grid only come from
+        // the per-cell table when it has been built (same code, same bits)
+        double y0, x0, hN, hE, hS, hW;
+        if (g.hdg) {
+            const double2* __restrict__ h = reinterpret_cast<const double2*>(g.hdg + 6 * (jP * g.Ni + iP));
+            const double2 a = h[0], b = h[1], c = h[2];
+            y0 = a.x; x0 = a.y; hN = b.x; hE = b.y; hS = c.x; hW = c.y;
+        } else {
+            cell_frame(g, jP, iP, jm, jp, im, ip, y0, x0, hN, hE, hS, hW);
+        }
         const double ht = gzb_heading_y(y0, x0, gzb_merc_y(yT), gzb_pymod(xT, 360.0) * GZB_D2R);
-        double hN = gzb_heading_y(y0, x0, gzb_merc_y(latN), gzb_pymod(lonN, 360.0) * GZB_D2R);
-        const double hE = gzb_heading_y(y0, x0, gzb_merc_y(latE), gzb_pymod(lonE, 360.0) * GZB_D2R);
-        const double hS = gzb_heading_y(y0, x0, gzb_merc_y(latS), gzb_pymod(lonS, 360.0) * GZB_D2R);
-        const double hW = gzb_heading_y(y0, x0, gzb_merc_y(latW), gzb_pymod(lonW, 360.0) * GZB_D2R);
         const double hz = gzb_pm180(ht);
-        if (hN > hE) hN = hN - 360.0;
         if (force_heavy < 2) {
             if (hz > hN && hz <= hE) iq = 1;
             if (ht > hE && ht <= hS) iq = 2;
@@ -198,9 +221,51 @@ k_mesh_weights(const GzbGrid g, const long long nt, const double* __restrict__ y
     out[1] = make_double2(w[2], w[3]);
 }
 
+// per-cell table of cell_frame(): thread per cell
+__global__ void __launch_bounds__(128)
+k_heading_table(const GzbGrid g, double* __restrict__ hdg) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.Nj * g.Ni) return;
+    const long long jP = k / g.Ni, iP = k - jP * g.Ni;
+    long long jm = 0, jp = 0, im = 0, ip = 0;
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (mesh_usable(g, jP, iP, jm, jp, im, ip)) cell_frame(g, jP, iP, jm, jp, im, ip, v[0], v[1], v[2], v[3], v[4], v[5]);
+    double2* out = reinterpret_cast<double2*>(hdg + 6 * k);
+    out[0] = make_double2(v[0], v[1]);
+    out[1] = make_double2(v[2], v[3]);
+    out[2] = make_double2(v[4], v[5]);
+}
+
+// The table costs one cell_frame() per grid cell; a K2 call costs one per track point.  Build it
+// once the points mapped on this grid outnumber half its cells (option "heading_table": 0 never,
+// 1 this rule, 2 at the next call).  Out of memory is not an error: K2 computes the frames itself.
+static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt) {
+    ctx->k2_points += nt;
+    if (ctx->hdg_built || ctx->hdg_mode == 0) return GZB_OK;
+    const int64_t cells = ctx->g.Nj * ctx->g.Ni;
+    if (ctx->hdg_mode == 1 && ctx->k2_points < cells / 2) return GZB_OK;
+    if (!ctx->d_hdg) {
+        cudaError_t e = cudaMalloc((void**)&ctx->d_hdg, (size_t)cells * 6 * sizeof(double));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->d_hdg = nullptr;
+            ctx->hdg_mode = 0;
+            return GZB_OK;
+        }
+    }
+    ctx->g.hdg = nullptr;
+    k_heading_table<<<(unsigned)((cells + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, ctx->d_hdg);
+    GZB_LAUNCH_CHECK(ctx);
+    ctx->g.hdg = ctx->d_hdg;
+    ctx->hdg_built = 1;
+    ctx->stats.heading_table = 1;
+    return GZB_OK;
+}
+
 int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
                          int64_t* sm_out, double* wb_out) {
     if (nt <= 0) return GZB_OK;
+    if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
     k_mesh_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
                                                                          (long long*)sm_out, wb_out, ctx->force_heavy);
     GZB_LAUNCH_CHECK(ctx);
@@ -210,6 +275,7 @@ int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const doubl
 int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
                         int64_t* sm_out) {
     if (nt <= 0) return GZB_OK;
+    if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
     k_source_mesh<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
                                                                         (long long*)sm_out, ctx->force_heavy);
     GZB_LAUNCH_CHECK(ctx);

@@ -27,6 +27,8 @@
 
 #define GZB_NOFLAT 0x7fffffffffffffffLL
 #define GZB_QCAP 64
+#define GZB_KCAP 64      // kept leaf tiles of one box scan
+#define GZB_BOX_MAXT 4096 // largest box (in leaf tiles) scanned flat; larger boxes descend the pyramid
 
 // search modes
 #define M_GLOBAL 0   // whole grid
@@ -44,6 +46,7 @@ struct WarpSm {
     unsigned long long bd[32];   // per owned point: bits of the best exact distance
     long long bf[32];            // ... and the smallest flat index achieving it
     float pb2[32];               // ... and the current candidate bound (chord^2)
+    int kt[GZB_KCAP];            // box scan: leaf tiles (row-major id) that can hold a cell within the bound
 };
 
 struct Srch {          // warp-uniform state of the search for one point
@@ -258,6 +261,123 @@ __device__ __forceinline__ bool window_search(const GzbGrid& g, WarpSm& w, const
     return (gcert - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (s.B + 1.0e-6f);
 }
 
+// K1c search: the cells of the index box [j0,j1) x [i0,i1) that can lie within the bound of `s`
+// (the caller set it to the r0 ball).  A chain replay is a sequence of DEPENDENT searches, so this
+// one is organised for latency, not throughput: the bounding spheres of all leaf tiles of the box
+// are tested in parallel (4 per lane and per round, loads issued back to back), the few tiles
+// that pass are evaluated with their loads batched four tiles at a time, and only then the
+// candidates go through the exact fp64 formula (flush_queue, by the caller).  Boxes of more than
+// GZB_BOX_MAXT tiles, or with more than GZB_KCAP tiles inside the bound, descend the pyramid.
+__device__ __forceinline__ void box_search(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
+                                           const long long j0, const long long j1, const long long i0,
+                                           const long long i1, int& qn, const Owner& me) {
+    const GzbLevel& L0 = g.lev[0];
+    const int tJ0 = (int)(j0 >> 2), tJ1 = (int)((j1 - 1) >> 2);
+    const int tI0 = (int)(i0 >> 3), tI1 = (int)((i1 - 1) >> 3);
+    const int nTI = tI1 - tI0 + 1;
+    const long long nTl = (long long)(tJ1 - tJ0 + 1) * nTI;
+    bool fallback = nTl > GZB_BOX_MAXT;
+    int nk = 0;
+    if (!fallback) {
+        const int nT = (int)nTl;
+        for (int base = 0; base < nT; base += 128) {
+            float4 nd[4];
+            int tl[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = base + u * 32 + lane;
+                tl[u] = -1;
+                nd[u] = make_float4(0.f, 0.f, 0.f, -1.f);
+                if (k < nT) {
+                    const int a = k / nTI;
+                    const int tj = tJ0 + a, ti = tI0 + (k - a * nTI);
+                    tl[u] = tj * L0.nI + ti;
+                    nd[u] = L0.nodes[gzb_leaf_index(g, tj, ti)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float dx = s.px - nd[u].x, dy = s.py - nd[u].y, dz = s.pz - nd[u].z;
+                const float dn2 = dx * dx + dy * dy + dz * dz;
+                const float lim = nd[u].w + s.B;
+                const bool keep = (nd[u].w >= 0.0f) && (dn2 <= lim * lim);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m) {
+                    const int cnt = __popc(m);
+                    if (nk + cnt > GZB_KCAP) fallback = true;
+                    else if (keep) w.kt[nk + __popc(m & ((1u << lane) - 1u))] = tl[u];
+                    nk += cnt;
+                }
+            }
+            if (fallback) break;
+        }
+        __syncwarp();
+    }
+    if (fallback) {
+        pyramid_search<M_BOX>(g, w, lane, s, pt, j0, j1, i0, i1, qn, me);
+        return;
+    }
+    if (nk == 0) return;
+    // smallest proxy over the kept tiles
+    const int lj = lane >> 3, li = lane & 7;
+    float pmin = INFINITY;
+    for (int b = 0; b < nk; b += 4) {
+        float x[4], y[4], z[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = false;
+            x[u] = y[u] = z[u] = 0.f;
+            if (b + u < nk) {
+                const int tile = w.kt[b + u];
+                const float* __restrict__ cc = g.cells + (long long)tile * 96;
+                x[u] = cc[lane]; y[u] = cc[32 + lane]; z[u] = cc[64 + lane];
+                const int tj = tile / L0.nI;
+                const long long j = (long long)tj * GZB_TILE_J + lj;
+                const long long i = (long long)(tile - tj * L0.nI) * GZB_TILE_I + li;
+                ok[u] = (j >= j0) && (j < j1) && (i >= i0) && (i < i1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float dx = s.px - x[u], dy = s.py - y[u], dz = s.pz - z[u];
+            const float P = dx * dx + dy * dy + dz * dz;
+            if (ok[u]) pmin = fminf(pmin, P);
+        }
+    }
+    const float pm = gzb_warp_min_nonneg(pmin);
+    if (pm < s.Pmin) {
+        set_bound(s, pm);
+        if (lane == 0) w.pb2[pt] = s.B2;
+    }
+    __syncwarp();
+    // candidates: every box cell of the kept tiles whose proxy is within the (final) bound
+    for (int b = 0; b < nk; ++b) {
+        const int tile = w.kt[b];
+        const float* __restrict__ cc = g.cells + (long long)tile * 96;
+        const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
+        const int tj = tile / L0.nI;
+        const long long j = (long long)tj * GZB_TILE_J + lj;
+        const long long i = (long long)(tile - tj * L0.nI) * GZB_TILE_I + li;
+        const float dx = s.px - x, dy = s.py - y, dz = s.pz - z;
+        const float P = dx * dx + dy * dy + dz * dz;
+        const bool cand = (j >= j0) && (j < j1) && (i >= i0) && (i < i1) && (P <= s.B2);
+        const unsigned cm = __ballot_sync(0xffffffffu, cand);
+        const int nnew = __popc(cm);
+        if (nnew) {
+            if (qn + nnew > GZB_QCAP) flush_queue(g, w, lane, qn, me);
+            if (cand) {
+                const int pos = qn + __popc(cm & ((1u << lane) - 1u));
+                w.qpt[pos] = pt;
+                w.qP[pos] = P;
+                w.qflat[pos] = j * g.Ni + i;
+            }
+            qn += nnew;
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ void owner_point(const double lat, const double lon, Owner& me, float& px, float& py,
                                             float& pz) {
     const double la = lat * GZB_D2R, lo = lon * GZB_D2R;
@@ -401,8 +521,8 @@ __device__ __forceinline__ int fast_ring(const GzbGrid& g, const float px, const
     return 0;
 }
 
-// what k_near_search leaves per point for k_exact_flags (one 64-bit word):
-//   CAND_UNRES        handed to the warp search, which writes G/dG itself
+// outcome of the per-thread search for one point (one 64-bit word):
+//   CAND_UNRES        handed to the warp search (k_near_slow), which writes G/dG itself
 //   CAND_NONE         non-finite target: no nearest point
 //   flat | CAND_MULTI several cells of the 5x5 neighbourhood of `flat` are within the fp32 margin
 //   flat              the one candidate
@@ -411,10 +531,54 @@ __device__ __forceinline__ int fast_ring(const GzbGrid& g, const float px, const
 #define CAND_MULTI 0x1000000000000000LL
 #define CAND_FLAT(v) ((v) & 0xfffffffffLL)
 
+// exact (reference formula, fp64) evaluation of the candidate(s) the per-thread search found for a point:
+// returns the first-index argmin and its distance bits
+__device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long long c, const double lat, const double lon,
+                                                const float px, const float py, const float pz, long long& bf,
+                                                unsigned long long& bd) {
+    bf = GZB_NOFLAT;
+    bd = ~0ull;
+    if (c & CAND_NONE) return;
+    const double cpl = cos(lat * GZB_D2R);
+    const long long f0 = CAND_FLAT(c);
+    if (!(c & CAND_MULTI)) {
+        const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f0], g.lon[f0]);
+        if (d == d) { bd = (unsigned long long)__double_as_longlong(d); bf = f0; }
+        return;
+    }
+    // several cells within the fp32 margin of the best one: same proxy, same bound as the search
+    const long long j = f0 / g.Ni, i = f0 - j * g.Ni;
+    float B2;
+    {
+        const float4 v = __ldg(g.cellv + f0);
+        const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+        const float a = sqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)));
+        const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
+        B2 = B * B;
+    }
+    for (int dj = -2; dj <= 2; ++dj) {
+        const long long jj = j + dj;
+        if (jj < 0 || jj >= g.Nj) continue;
+        for (int di = -2; di <= 2; ++di) {
+            const long long ii = i + di;
+            if (ii < 0 || ii >= g.Ni) continue;
+            const long long f = jj * g.Ni + ii;
+            const float4 v = __ldg(g.cellv + f);
+            const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+            const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+            if (!(P <= B2)) continue;
+            const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f], g.lon[f]);
+            if (!(d == d)) continue;
+            const unsigned long long db = (unsigned long long)__double_as_longlong(d);
+            if (db < bd) { bd = db; bf = f; }     // row-major scan: the first index keeps a tie
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128, 8)
 k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-              long long* __restrict__ cand, long long* __restrict__ ulist, unsigned* __restrict__ hint,
-              unsigned long long* __restrict__ ucount) {
+              long long* __restrict__ G, double* __restrict__ dG, long long* __restrict__ ulist,
+              unsigned* __restrict__ hint, unsigned long long* __restrict__ ucount) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool unresolved = false;
     unsigned myhint = 0xffffffffu;
@@ -477,8 +641,18 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
                 out = CAND_UNRES;
                 atomicAdd(ucount + reason, 1ull);
             }
+            if (!unresolved) {
+                // settle the point here: the reference's fp64 formula on the candidate(s)
+                long long bf;
+                unsigned long long bd;
+                exact_from_cand(g, out, lat, lon, px, py, pz, bf, bd);
+                G[t] = bf;
+                dG[t] = __longlong_as_double((long long)bd);
+            }
+        } else {
+            G[t] = GZB_NOFLAT;
+            dG[t] = __longlong_as_double(-1LL);
         }
-        cand[t] = out;
     }
     // warp-aggregated append of the unresolved points
     const unsigned um = __ballot_sync(0xffffffffu, unresolved);
@@ -490,54 +664,6 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
         if (unresolved) {
             ulist[base + __popc(um & ((1u << lane) - 1u))] = t;
             hint[t] = myhint;
-        }
-    }
-}
-
-// exact (reference formula, fp64) evaluation of the candidate(s) k_near_search left for point t:
-// returns the first-index argmin and its distance bits
-__device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long long c, const double lat, const double lon,
-                                                long long& bf, unsigned long long& bd) {
-    bf = GZB_NOFLAT;
-    bd = ~0ull;
-    if (c & CAND_NONE) return;
-    const double cpl = cos(lat * GZB_D2R);
-    const long long f0 = CAND_FLAT(c);
-    if (!(c & CAND_MULTI)) {
-        const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f0], g.lon[f0]);
-        if (d == d) { bd = (unsigned long long)__double_as_longlong(d); bf = f0; }
-        return;
-    }
-    // several cells within the fp32 margin of the best one: same proxy, same bound as the search
-    const double la = lat * GZB_D2R, lo = lon * GZB_D2R;
-    double sa, ca, so, co;
-    sincos(la, &sa, &ca);
-    sincos(lo, &so, &co);
-    const float px = (float)(ca * co), py = (float)(ca * so), pz = (float)sa;
-    const long long j = f0 / g.Ni, i = f0 - j * g.Ni;
-    float B2;
-    {
-        const float4 v = __ldg(g.cellv + f0);
-        const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
-        const float a = sqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)));
-        const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
-        B2 = B * B;
-    }
-    for (int dj = -2; dj <= 2; ++dj) {
-        const long long jj = j + dj;
-        if (jj < 0 || jj >= g.Nj) continue;
-        for (int di = -2; di <= 2; ++di) {
-            const long long ii = i + di;
-            if (ii < 0 || ii >= g.Ni) continue;
-            const long long f = jj * g.Ni + ii;
-            const float4 v = __ldg(g.cellv + f);
-            const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
-            const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-            if (!(P <= B2)) continue;
-            const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f], g.lon[f]);
-            if (!(d == d)) continue;
-            const unsigned long long db = (unsigned long long)__double_as_longlong(d);
-            if (db < bd) { bd = db; bf = f; }     // row-major scan: the first index keeps a tie
         }
     }
 }
@@ -658,65 +784,27 @@ __device__ __forceinline__ bool clamp_box(const GzbGrid& g, const long long pj, 
     return (j0 < j1) && (i0 < i1);
 }
 
-// K1c, step 1: speculative chain + break detection.  One thread per point.  With `cand` (the
-// per-thread search ran) the thread first settles its own point: exact fp64 evaluation of the
-// candidate(s), G/dG written here; the predecessor's values come through shared memory.
+// K1c, step 1: speculative chain + break detection.  One thread per point; G/dG are final
+// (k_near_search / k_near_slow or k_global wrote them).
 #define FLAGS_BLOCK 256
 __global__ void __launch_bounds__(FLAGS_BLOCK)
 k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
-        const double* __restrict__ xt, const long long* __restrict__ cand, long long* G, double* dG,
+        const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
         long long* __restrict__ NP, unsigned char* __restrict__ brk, int* __restrict__ counts) {
-    __shared__ long long sf[FLAGS_BLOCK];
-    __shared__ double sd[FLAGS_BLOCK];
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int isb = 0;
-    long long f = GZB_NOFLAT;
-    double d = __longlong_as_double(-1LL);
     if (t < nt) {
-        const long long c = cand ? cand[t] : CAND_UNRES;
-        if (c & CAND_UNRES) {
-            f = G[t];
-            d = dG[t];
-        } else {
-            unsigned long long bd;
-            exact_from_cand(g, c, yt[t], xt[t], f, bd);
-            d = __longlong_as_double((long long)bd);
-            G[t] = f;
-            dG[t] = d;
-        }
-    }
-    sf[threadIdx.x] = f;
-    sd[threadIdx.x] = d;
-    __syncthreads();
-    if (t < nt) {
+        const long long f = G[t];
+        const double d = dG[t];
         long long ej, ei;
         accept_edge(g, f, d, p.thr2, ej, ei, p.edge);
-        NP[2 * t] = ej;
-        NP[2 * t + 1] = ei;
+        reinterpret_cast<longlong2*>(NP)[t] = make_longlong2(ej, ei);
         long long pj, pi;
         if (t == 0) {
             pj = p.seed_j;
             pi = p.seed_i;
         } else {
-            long long pf;
-            double pd;
-            if (threadIdx.x > 0) {
-                pf = sf[threadIdx.x - 1];
-                pd = sd[threadIdx.x - 1];
-            } else {
-                // the predecessor belongs to the previous block, which may not have written G/dG yet:
-                // settle it again from its candidate word
-                const long long c = cand ? cand[t - 1] : CAND_UNRES;
-                if (c & CAND_UNRES) {
-                    pf = G[t - 1];
-                    pd = dG[t - 1];
-                } else {
-                    unsigned long long bd;
-                    exact_from_cand(g, c, yt[t - 1], xt[t - 1], pf, bd);
-                    pd = __longlong_as_double((long long)bd);
-                }
-            }
-            accept_edge(g, pf, pd, p.thr2, pj, pi, p.edge);
+            accept_edge(g, G[t - 1], dG[t - 1], p.thr2, pj, pi, p.edge);
         }
         if (pj != 0 && pi != 0) {   // Python truthiness of (j_prv and i_prv)
             long long j0, j1, i0, i1;
@@ -807,54 +895,14 @@ k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ o
     if (b) breaks[offsets[blockIdx.x] + wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = t;
 }
 
-// one step of the reference recurrence: R(t) = F_t(pred).  All lanes hold the same point.
-__device__ __forceinline__ void chain_step(const GzbGrid& g, WarpSm& w, const int lane, const NearParams& p,
-                                           const long long t, const long long pj, const long long pi,
-                                           const double* __restrict__ yt, const double* __restrict__ xt,
-                                           const long long gflat, const long long ej, const long long ei,
-                                           long long& rj, long long& ri) {
-    rj = ej;
-    ri = ei;
-    if (pj != 0 && pi != 0) {
-        long long j0, j1, i0, i1;
-        if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
-            // the global nearest point lies inside the box: the box pass finds that very point, so
-            // R(t) = E(t) whatever its distance (DESIGN.md, K1 key fact) -- no search needed
-            if (gflat != GZB_NOFLAT) {
-                const long long gj = gflat / g.Ni, gi = gflat - gj * g.Ni;
-                if (gj >= j0 && gj < j1 && gi >= i0 && gi < i1) return;
-            }
-            Owner me;
-            float px, py, pz;
-            owner_point(yt[t], xt[t], me, px, py, pz);
-            Srch s;
-            srch_init(s, px, py, pz);
-            set_bound(s, p.prox_r0);
-            if (lane == 0) {
-                w.bd[0] = ~0ull;
-                w.bf[0] = GZB_NOFLAT;
-                w.pb2[0] = s.B2;
-            }
-            __syncwarp();
-            int qn = 0;
-            bool proven = false;
-            if (pj > 0 && pi > 0)      // continuity: the window around the predecessor's tile
-                proven = window_search<M_BOX>(g, w, lane, s, 0, (int)(pj >> 2), (int)(pi >> 3), j0, j1, i0, i1, qn, me);
-            if (!proven) pyramid_search<M_BOX>(g, w, lane, s, 0, j0, j1, i0, i1, qn, me);
-            flush_queue(g, w, lane, qn, me);
-            const long long f = w.bf[0];
-            const double d = __longlong_as_double((long long)w.bd[0]);
-            __syncwarp();
-            if (f != GZB_NOFLAT && d < p.r0) accept_edge(g, f, d, INFINITY, rj, ri, p.edge);
-        }
-    }
-}
-
-// K1c, step 2/4: chain replay, one warp per break.  WRITE=false records where the replay
-// rejoins the speculative chain and logs every replayed value tagged with the replay's id
-// (one 64-bit word per point: id in the high 27 bits, flat index + 1 in the low 36); WRITE=true
-// (valid replays only) copies the logged values, 32 per step, and replays again only if another
-// (discarded) replay overwrote part of its log.
+// K1c, step 2/4: chain replay, one warp per break: the reference's recurrence R(t) = F_t(R(t-1))
+// from the break until the chain rejoins the speculative one.  The points are taken 32 at a
+// time: lane l prepares point t0+l (unit vector, cos(lat), G, E) in parallel, then the steps run
+// in order with those values shuffled in, so that a step costs one box_search and nothing else.
+// WRITE=false records where the replay rejoins the speculative chain and logs every replayed
+// value tagged with the replay's id (one 64-bit word per point: id in the high 27 bits, flat
+// index + 1 in the low 36); WRITE=true (valid replays only) copies the logged values, 32 per
+// step, and replays again only if another (discarded) replay overwrote part of its log.
 #define WLOG_TAG(k) ((unsigned long long)(((k) + 1) & 0x7ffffffLL) << 36)
 
 template <bool WRITE>
@@ -866,10 +914,12 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
        unsigned long long* __restrict__ wlog, long long* __restrict__ NP, unsigned long long* __restrict__ steps) {
     __shared__ WarpSm ws[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpSm& w = ws[warp];
     const long long nb = *nbrk_p;
     const long long nwarps = (long long)gridDim.x * 8;
     for (long long k = (long long)blockIdx.x * 8 + warp; k < nb; k += nwarps) {
         const long long b = breaks[k];
+        long long tend = nt - 1;          // last point this replay may touch
         if (WRITE) {
             if (!valid[k]) continue;
             const long long e = stop[k];
@@ -899,6 +949,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                 if (__any_sync(0xffffffffu, bad)) clobbered = true;
             }
             if (!clobbered) continue;
+            tend = e;
         }
         long long pj, pi;
         if (b == 0) {
@@ -907,35 +958,80 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
         } else {
             accept_edge(g, G[b - 1], dG[b - 1], p.thr2, pj, pi, p.edge);
         }
-        long long t = b;
         unsigned long long n = 0;
-        for (;;) {
-            long long ej, ei, rj, ri;
-            accept_edge(g, G[t], dG[t], p.thr2, ej, ei, p.edge);
-            chain_step(g, ws[warp], lane, p, t, pj, pi, yt, xt, G[t], ej, ei, rj, ri);
-            ++n;
-            if (WRITE) {
-                if (lane == 0) {
-                    NP[2 * t] = rj;
-                    NP[2 * t + 1] = ri;
-                }
-                if (t >= stop[k]) break;
-            } else {
-                if (lane == 0) {
-                    wlog[t] = WLOG_TAG(k) | (unsigned long long)(rj < 0 ? 0 : rj * g.Ni + ri + 1);
-                    if (t == b) {
-                        first[2 * k] = rj;
-                        first[2 * k + 1] = ri;
+        bool done = false;
+        for (long long t0 = b; !done; t0 += 32) {
+            const int nq = (int)((tend - t0 + 1 < 32) ? (tend - t0 + 1) : 32);
+            Owner me;
+            float mpx = 0.f, mpy = 0.f, mpz = 0.f;
+            me.plat = me.plon = me.cpl = 0.0;
+            long long gf = GZB_NOFLAT, ej = -1, ei = -1;
+            if (lane < nq) {
+                owner_point(yt[t0 + lane], xt[t0 + lane], me, mpx, mpy, mpz);
+                gf = G[t0 + lane];
+                accept_edge(g, gf, dG[t0 + lane], p.thr2, ej, ei, p.edge);
+            }
+            __syncwarp();
+            w.bd[lane] = ~0ull;
+            w.bf[lane] = GZB_NOFLAT;
+            w.pb2[lane] = INFINITY;
+            __syncwarp();
+            for (int q = 0; q < nq; ++q) {
+                const long long t = t0 + q;
+                const long long qej = __shfl_sync(0xffffffffu, ej, q), qei = __shfl_sync(0xffffffffu, ei, q);
+                const long long qgf = __shfl_sync(0xffffffffu, gf, q);
+                long long rj = qej, ri = qei;
+                if (pj != 0 && pi != 0) {     // Python truthiness of (j_prv and i_prv)
+                    long long j0, j1, i0, i1;
+                    if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
+                        // the global nearest point inside the box: the box pass finds that very point,
+                        // so R(t) = E(t) whatever its distance (DESIGN.md, K1 key fact) -- no search
+                        bool inside = false;
+                        if (qgf != GZB_NOFLAT) {
+                            const long long gj = qgf / g.Ni, gi = qgf - gj * g.Ni;
+                            inside = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
+                        }
+                        if (!inside) {
+                            Srch s;
+                            srch_init(s, __shfl_sync(0xffffffffu, mpx, q), __shfl_sync(0xffffffffu, mpy, q),
+                                      __shfl_sync(0xffffffffu, mpz, q));
+                            set_bound(s, p.prox_r0);
+                            if (lane == 0) w.pb2[q] = s.B2;
+                            __syncwarp();
+                            int qn = 0;
+                            box_search(g, w, lane, s, q, j0, j1, i0, i1, qn, me);
+                            flush_queue(g, w, lane, qn, me);
+                            const long long f = w.bf[q];
+                            const double d = __longlong_as_double((long long)w.bd[q]);
+                            if (f != GZB_NOFLAT && d < p.r0) accept_edge(g, f, d, INFINITY, rj, ri, p.edge);
+                        }
                     }
                 }
-                if ((rj == ej && ri == ei) || t + 1 >= nt) {
-                    if (lane == 0) stop[k] = t;
-                    break;
+                ++n;
+                if (WRITE) {
+                    if (lane == 0) {
+                        NP[2 * t] = rj;
+                        NP[2 * t + 1] = ri;
+                    }
+                    if (t >= tend) { done = true; break; }
+                } else {
+                    if (lane == 0) {
+                        wlog[t] = WLOG_TAG(k) | (unsigned long long)(rj < 0 ? 0 : rj * g.Ni + ri + 1);
+                        if (t == b) {
+                            first[2 * k] = rj;
+                            first[2 * k + 1] = ri;
+                        }
+                    }
+                    if ((rj == qej && ri == qei) || t + 1 >= nt) {
+                        if (lane == 0) stop[k] = t;
+                        done = true;
+                        break;
+                    }
                 }
+                pj = rj;
+                pi = ri;
             }
-            pj = rj;
-            pi = ri;
-            ++t;
+            __syncwarp();
         }
         if (!WRITE && lane == 0) {
             atomicAdd(steps, n);
@@ -945,42 +1041,57 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
 }
 
 // K1c, step 3: a replay is valid iff it does not start inside an earlier valid replay
-// (whose deviating values would have been its true predecessor).  Single warp, 32 breaks per
-// step on the common path where no replay reaches the next break.
-__global__ void __launch_bounds__(32)
+// (whose deviating values would have been its true predecessor).  The block stages the break
+// list in shared memory, 2048 entries at a time; warp 0 then runs the (inherently ordered)
+// scan, 32 breaks per step on the common path where no replay reaches the next break.
+#define VALID_CHUNK 2048
+__global__ void __launch_bounds__(1024)
 k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop,
         const long long* __restrict__ nbrk_p, unsigned char* __restrict__ valid, long long* __restrict__ stats_out) {
-    const int lane = threadIdx.x;
+    __shared__ long long sb[VALID_CHUNK + 1];
+    __shared__ long long ss[VALID_CHUNK];
+    const int lane = threadIdx.x & 31;
     const long long nb = *nbrk_p;
     long long cur_end = -1;
-    for (long long base = 0; base < nb; base += 32) {
-        const long long k = base + lane;
-        const long long b = k < nb ? breaks[k] : GZB_NOFLAT;
-        const long long s = k < nb ? stop[k] : GZB_NOFLAT;
-        long long nxt = __shfl_down_sync(0xffffffffu, b, 1);
-        if (lane == 31) nxt = (base + 32 < nb) ? breaks[base + 32] : GZB_NOFLAT;
-        const bool simple = (k >= nb) || (s < nxt);
-        const long long b0 = __shfl_sync(0xffffffffu, b, 0);
-        if (__all_sync(0xffffffffu, simple) && b0 > cur_end) {
-            if (k < nb) valid[k] = 1;
-            const int last = (int)((nb - base < 32 ? nb - base : 32) - 1);
-            cur_end = __shfl_sync(0xffffffffu, s, last);
-        } else {
-            for (int l = 0; l < 32; ++l) {
-                const long long kb = __shfl_sync(0xffffffffu, b, l);
-                const long long ks = __shfl_sync(0xffffffffu, s, l);
-                if (base + l < nb) {
-                    const bool v = kb > cur_end;
-                    if (v) cur_end = ks;
-                    if (lane == l) valid[k] = v ? 1 : 0;
+    for (long long c0 = 0; c0 < nb; c0 += VALID_CHUNK) {
+        const int cn = (int)((nb - c0 < VALID_CHUNK) ? (nb - c0) : VALID_CHUNK);
+        for (int e = threadIdx.x; e <= cn; e += blockDim.x) {
+            sb[e] = (c0 + e < nb) ? breaks[c0 + e] : GZB_NOFLAT;
+            if (e < cn) ss[e] = stop[c0 + e];
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            for (int base = 0; base < cn; base += 32) {
+                const int e = base + lane;
+                const bool in = e < cn;
+                const long long b = in ? sb[e] : GZB_NOFLAT;
+                const long long s = in ? ss[e] : GZB_NOFLAT;
+                const long long nxt = in ? sb[e + 1] : GZB_NOFLAT;
+                const bool simple = !in || (s < nxt);
+                const long long b0 = __shfl_sync(0xffffffffu, b, 0);
+                if (__all_sync(0xffffffffu, simple) && b0 > cur_end) {
+                    if (in) valid[c0 + e] = 1;
+                    const int last = ((cn - base < 32) ? (cn - base) : 32) - 1;
+                    cur_end = __shfl_sync(0xffffffffu, s, last);
+                } else {
+                    for (int l = 0; l < 32; ++l) {
+                        const long long kb = __shfl_sync(0xffffffffu, b, l);
+                        const long long ks = __shfl_sync(0xffffffffu, s, l);
+                        if (base + l < cn) {
+                            const bool v = kb > cur_end;
+                            if (v) cur_end = ks;
+                            if (lane == l) valid[c0 + e] = v ? 1 : 0;
+                        }
+                    }
                 }
             }
         }
+        __syncthreads();
     }
-    if (lane == 0) {      // (breaks, replay steps) of this call, for gzb_get_stats
+    if (threadIdx.x == 0) {      // (breaks, replay steps, ...) of this call, for gzb_get_stats
         stats_out[0] = nbrk_p[0];
         stats_out[1] = nbrk_p[1];
-        for (int q = 2; q < 7; ++q) stats_out[q] = nbrk_p[q];   // k_near_fast: unresolved (total, no seed, not converged, not proven); longest replay
+        for (int q = 2; q < 7; ++q) stats_out[q] = nbrk_p[q];   // k_near_search: unresolved (total, no seed, not converged, not proven); longest replay
     }
 }
 
@@ -1051,7 +1162,7 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
            + gzb_align(n * 8)        // replay log
-           + gzb_align(n * 8) * 2 + gzb_align(n * 4)   // candidate words, unresolved list, hints
+           + gzb_align(n * 8) + gzb_align(n * 4)   // unresolved list, hints
            + gzb_align(64) * 2;      // scalars, corner
 }
 
@@ -1072,7 +1183,6 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     long long* first = (long long*)gzb_arena_take(ctx, n * 16);
     unsigned char* valid = (unsigned char*)gzb_arena_take(ctx, n);
     unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
-    long long* candbuf = (long long*)gzb_arena_take(ctx, n * 8);
     long long* ulist = (long long*)gzb_arena_take(ctx, n * 8);
     unsigned* hint = (unsigned*)gzb_arena_take(ctx, n * 4);
     long long* scal = (long long*)gzb_arena_take(ctx, 64);
@@ -1105,7 +1215,6 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
 
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    const long long* cand = nullptr;
     // chunk length: long enough to amortise the unseeded first point, short enough to fill the GPU
     int K = 32;
     while (K > 4 && (long long)((n + K - 1) / K) < (long long)nsm * 8 * 4) K >>= 1;
@@ -1113,8 +1222,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     const long long gmax = (long long)nsm * 16;
     if (gblocks > gmax) gblocks = gmax;
     if (ctx->nearest_path && ctx->g.cellv && ctx->g.lut.bins) {
-        cand = candbuf;
-        k_near_search<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ctx->g, nt, yt, xt, candbuf, ulist, hint,
+        k_near_search<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ctx->g, nt, yt, xt, G, dG, ulist, hint,
                                                                  (unsigned long long*)(scal + 2));
         GZB_LAUNCH_CHECK(ctx);
         k_near_slow<<<(unsigned)(nsm * 4), 256, 0, s>>>(ctx->g, yt, xt, G, dG, ulist, hint,
@@ -1124,7 +1232,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
         k_global<<<(unsigned)gblocks, 256, 0, s>>>(ctx->g, nt, yt, xt, G, dG, K);
         GZB_LAUNCH_CHECK(ctx);
     }
-    k_flags<<<(unsigned)nblk, FLAGS_BLOCK, 0, s>>>(ctx->g, p, nt, yt, xt, cand, G, dG, (long long*)np_out, brk, counts);
+    k_flags<<<(unsigned)nblk, FLAGS_BLOCK, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, (long long*)np_out, brk, counts);
     GZB_LAUNCH_CHECK(ctx);
     k_scan_counts<<<1, 1024, 0, s>>>(counts, offsets, nblk, scal);
     GZB_LAUNCH_CHECK(ctx);
@@ -1136,7 +1244,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     k_walk<false><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
                                                    valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));
     GZB_LAUNCH_CHECK(ctx);
-    k_valid<<<1, 32, 0, s>>>(breaks, stop, scal, valid, (long long*)(ctx->d_flags + 8));
+    k_valid<<<1, 1024, 0, s>>>(breaks, stop, scal, valid, (long long*)(ctx->d_flags + 8));
     GZB_LAUNCH_CHECK(ctx);
     k_walk<true><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
                                                   valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));

@@ -52,6 +52,7 @@ typedef struct gzb_stats {
     int64_t  last_unres_noconv; /*   ... hill climb not converged                             */
     int64_t  last_unres_nocert; /*   ... per-cell certificate not sufficient                  */
     int64_t  last_max_chain;    /* last gzb_nearest: longest sequential replay (steps)         */
+    int64_t  heading_table;     /* 1 once the per-cell heading table of K2 has been built       */
 } gzb_stats;
 
 const char* gzb_version(void);
@@ -81,6 +82,10 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * 0 never; 2 whenever the slab is pinned + mapped.
  * "nearest_path": 1 (default) per-thread hill climb seeded by a lat-lon table, proven by per-cell
  * certificates, warp-cooperative search for the rest; 0 warp-cooperative search only (same results).
+ * "heading_table": K2 can read the grid-only part of the quadrant test (Mercator ordinate of a
+ * cell and the headings to its four neighbours, 48 B per cell) from a table instead of computing
+ * it per track point: 0 never, 1 (default) build it once the points mapped on this context
+ * outnumber half the grid cells, 2 build it at the next K2 call.  Same results either way.
  * "edge_exclusion": 1 (default) gzb_nearest applies the first/last row/column rule of
  * BilinTrack.nrpt (gonzag/bilin_mapping.py:582-585); 0 gives plain NearestPoint() results.
  * "force_heavy": 0 (default); 1 = heavy-duty quadrant search as if |angle| > 45 everywhere;
