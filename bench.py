@@ -300,7 +300,8 @@ def run_ours(args, w):
     x_h = eng.tensor(xx[h0:s1])
     off = 1 if has_halo else 0
     y_d, x_d = y_h[off:], x_h[off:]
-    t_d = eng.tensor(tt[s0:s1])
+    t_h = eng.tensor(tt[h0:s1])
+    t_d = t_h[off:]
     tmod_d = eng.tensor(tmod_all)
     SM = eng.empty((nt_local, 4, 2), torch.int64)
     WB = eng.empty((nt_local, 4), torch.float64)
@@ -314,17 +315,14 @@ def run_ours(args, w):
 
     state = {}
 
-    def rest_of_path():
-        eng.mesh_weights(y_d, x_d, mapper.NP, SM, WB)
-        eng.interp(t_d, SM, WB, tmod_d, slab, k_lo, v_np, v_bl)
-
     def step():
-        mapper.nearest_speculative(y_h, x_h, rd, r)
-        rest_of_path()
+        # K1 + K2 + K3 + K4 in one call (gzb_map_interp), on [halo point +] this rank's points
+        mapper.path_speculative(y_h, x_h, t_h, rd, r, tmod_d, slab, k_lo)
         g = mapper.gather()
         if not mapper.boundaries_ok(g):           # rare: a chain deviation straddles a segment boundary
             if mapper.reseed(g, y_d, x_d, rd, r):
-                rest_of_path()
+                eng.mesh_weights(y_d, x_d, mapper.NP, mapper.SM, mapper.WB)
+                eng.interp(t_d, mapper.SM, mapper.WB, tmod_d, slab, k_lo, v_np, v_bl)
             g = mapper.gather()
         state["out"] = g
 
@@ -398,6 +396,8 @@ def run_ours(args, w):
     n = y_d.numel()
     s_el = 4
     stages = {
+        "K1-K4_path": (lambda: eng.map_interp(y_d, x_d, t_d, rd, r, (r, r), tmod_d, slab, k_lo, NPs, SM, WB, v_np, v_bl), "path"),
+        "K1K2K3_mapping": (lambda: eng.mapping(y_d, x_d, rd, r, (r, r), NPs, SM, WB), "map"),
         "K1_nearest": (lambda: eng.nearest(y_d, x_d, rd, r, (r, r), NPs), None),
         "K2_source_mesh": (lambda: ctx._ck(lib.gzb_source_mesh(h, n, P(y_d), P(x_d), P(NPs), P(SM), L.GZB_DEVICE)), 184.0 * n),
         "K3_weights": (lambda: ctx._ck(lib.gzb_weights(h, n, P(y_d), P(x_d), P(SM), P(WB), L.GZB_DEVICE)), 176.0 * n),
@@ -424,7 +424,8 @@ def run_ours(args, w):
     kern = {}
     for name, (fn, nbytes) in stages.items():
         mean_ms, min_ms = time_stage(fn)
-        nb = k1_bytes if nbytes is None else nbytes
+        extra = {"map": 360.0 * n, "path": (360.0 + 124.0 + 8 * s_el) * n}
+        nb = k1_bytes if nbytes is None else (k1_bytes + extra[nbytes] if isinstance(nbytes, str) else nbytes)
         ach = nb / (mean_ms * 1e-3) / 1e9
         kern[name] = {"ms": mean_ms, "ms_min": min_ms, "algorithmic_bytes": nb, "achieved_gbs": ach,
                       "frac_of_hbm_peak": ach / peaks["hbm_gbs"]}
@@ -432,7 +433,10 @@ def run_ours(args, w):
                              "achieved_gbs": 24.0 * lat.size / (np.mean(k0_ms[1:]) * 1e-3) / 1e9,
                              "frac_of_hbm_peak": 24.0 * lat.size / (np.mean(k0_ms[1:]) * 1e-3) / 1e9 / peaks["hbm_gbs"],
                              "note": "grid set-up (-D), outside the step"}
-    dom = max(stages, key=lambda k: kern[k]["ms"])
+    kern["K1-K4_path"]["note"] = ("what the step runs (gzb_map_interp): K1's chain replays on a second stream beside "
+                                  "K2-K4 on the speculative chain, then K2-K4 again for the points the replays changed")
+    kern["K1K2K3_mapping"]["note"] = "gzb_mapping: the same overlap without K4; the rows below time the stages called one by one"
+    dom = max((k for k in stages if k not in ("K1K2K3_mapping", "K1-K4_path")), key=lambda k: kern[k]["ms"])
     roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": kern[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peaks["src"],
             "note": "algorithmic bytes / CUDA-event time of the stage, L2 flushed before each launch; "

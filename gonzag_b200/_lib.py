@@ -57,6 +57,8 @@ _SIGNATURES = {
     "gzb_weights": (C.c_int, [_P, _I64, _P, _P, _P, _P, C.c_int]),
     "gzb_mesh_weights": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, C.c_int]),
     "gzb_mapping": (C.c_int, [_P, _I64, _P, _P, C.c_double, C.c_int, _I64, _I64, _P, _P, _P, C.c_int]),
+    "gzb_map_interp": (C.c_int, [_P, _I64, _P, _P, _P, C.c_double, C.c_int, _I64, _I64, _I64, _P, _P, C.c_int, _I64, _I64,
+                                 C.c_double, _P, _P, _P, _P, _P]),
     "gzb_interp": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int,
                              _P, _P, C.c_int]),
     "gzb_track_distance": (C.c_int, [_P, _I64, _P, _P, _P, C.c_int]),

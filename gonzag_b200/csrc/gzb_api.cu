@@ -4,7 +4,10 @@
 
 size_t gzb_nearest_ws_bytes(int64_t nt);
 int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double rd_found_km,
-                    int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out);
+                    int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out, bool split = false,
+                    const long long** chg_out = nullptr, const unsigned long long** nchg_out = nullptr);
+int gzb_mesh_weights_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
+                             double* wb_out, const long long* list, const unsigned long long* count);
 int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
                         int64_t* sm_out);
 int gzb_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* sm,
@@ -12,6 +15,11 @@ int gzb_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
 
 int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
                          int64_t* sm_out, double* wb_out);
+
+int gzb_interp_dev(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb, int64_t nrec,
+                   const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss,
+                   double* np_out, double* bl_out, const long long* list, const unsigned long long* count);
+int gzb_slab_device_pointer(const void* slab, const void** dev_out, int* is_host);
 
 namespace {
 
@@ -67,6 +75,17 @@ int run_stages(gzb_ctx* ctx, int stages, int64_t nt, const double* yt, const dou
         }
     }
     int rc;
+    if (stages == (ST_NP | ST_SM | ST_WB) && ctx->overlap) {
+        // K1's chain replays are a handful of long dependent walks that leave the GPU almost idle:
+        // run them on the auxiliary stream while K2+K3 work on the speculative chain, then redo
+        // K2+K3 for the few points the replays changed
+        const long long* chg = nullptr;
+        const unsigned long long* nchg = nullptr;
+        if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp, true, &chg, &nchg)) != GZB_OK) return rc;
+        if ((rc = gzb_mesh_weights_dev(ctx, nt, dy, dx, dnp, dsm, dwb)) != GZB_OK) return rc;
+        GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[1], 0));
+        if ((rc = gzb_mesh_weights_fix_dev(ctx, dy, dx, dnp, dsm, dwb, chg, nchg)) != GZB_OK) return rc;
+    } else {
     if (stages & ST_NP) {
         if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp)) != GZB_OK) return rc;
         dnp_in = dnp;
@@ -77,6 +96,7 @@ int run_stages(gzb_ctx* ctx, int stages, int64_t nt, const double* yt, const dou
         if ((rc = gzb_source_mesh_dev(ctx, nt, dy, dx, dnp_in, dsm)) != GZB_OK) return rc;
     } else if (stages & ST_WB) {
         if ((rc = gzb_weights_dev(ctx, nt, dy, dx, dsm_in, dwb)) != GZB_OK) return rc;
+    }
     }
     if (where == GZB_HOST) {
         if (stages & ST_NP) {
@@ -127,4 +147,49 @@ extern "C" int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const dou
                            double* wb_out, int where) {
     return run_stages(ctx, ST_NP | ST_SM | ST_WB, nt, yt, xt, rd_found_km, np_box_r, seed_j, seed_i, nullptr,
                       nullptr, np_out, sm_out, wb_out, where, "gzb_mapping");
+}
+
+// K1 + K2 + K3 + K4 in one call, device-resident track.  The chain replays of K1 (a few long
+// dependent walks) run on the auxiliary stream while K2, K3 and K4 work on the speculative chain;
+// the points the replays changed (a few hundred on a 10-day track) then go through K2-K4 again.
+extern "C" int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const double* tt,
+                              double rd_found_km, int np_box_r, int64_t seed_j, int64_t seed_i, int64_t nrec,
+                              const double* tmod, const void* slab, int dtype, int64_t k0, int64_t nk,
+                              double rmissval, int64_t* np_out, int64_t* sm_out, double* wb_out, double* vnp_out,
+                              double* vbl_out) {
+    const char* who = "gzb_map_interp";
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "%s: null ctx", who);
+    if (nt < 0 || nrec < 2 || nk < 2 || k0 < 0 || k0 + nk > nrec || !tmod || !slab)
+        return gzb_fail(ctx, GZB_ERR_ARG, "%s: bad arguments (nt=%lld nrec=%lld k0=%lld nk=%lld)", who, (long long)nt,
+                        (long long)nrec, (long long)k0, (long long)nk);
+    if (nt == 0) return GZB_OK;
+    if (!yt || !xt || !tt || !np_out || !sm_out || !wb_out || !vnp_out || !vbl_out)
+        return gzb_fail(ctx, GZB_ERR_ARG, "%s: null track array", who);
+    if (dtype != GZB_F32 && dtype != GZB_F64) return gzb_fail(ctx, GZB_ERR_ARG, "%s: dtype must be GZB_F32 or GZB_F64", who);
+    if (!(rd_found_km > 0.0)) return gzb_fail(ctx, GZB_ERR_ARG, "%s: rd_found_km must be > 0", who);
+    if (!ctx->g.mask) return gzb_fail(ctx, GZB_ERR_STATE, "%s: the context has no land-sea mask (gzb_set_mask)", who);
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const void* slab_dev = nullptr;
+    int slab_is_host = 0;
+    if (!gzb_slab_device_pointer(slab, &slab_dev, &slab_is_host))
+        return gzb_fail(ctx, GZB_ERR_ARG, "%s: the record slab must be in device memory or in pinned + mapped host memory "
+                        "(gzb_host_alloc / gzb_host_register); use gzb_mapping + gzb_interp for pageable slabs", who);
+    if (slab_is_host) ctx->stats.h2d_bytes += (uint64_t)nt * 8 * 32;
+    if (gzb_arena_reserve(ctx, gzb_nearest_ws_bytes(nt)) != GZB_OK) return GZB_ERR_NOMEM;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    const long long* chg = nullptr;
+    const unsigned long long* nchg = nullptr;
+    const bool split = ctx->overlap != 0;
+    if ((rc = gzb_nearest_dev(ctx, nt, yt, xt, rd_found_km, np_box_r, seed_j, seed_i, np_out, split, &chg, &nchg)) != GZB_OK) return rc;
+    if ((rc = gzb_mesh_weights_dev(ctx, nt, yt, xt, np_out, sm_out, wb_out)) != GZB_OK) return rc;
+    if ((rc = gzb_interp_dev(ctx, nt, tt, sm_out, wb_out, nrec, tmod, slab_dev, dtype, k0, nk, rmissval, vnp_out, vbl_out,
+                             nullptr, nullptr)) != GZB_OK) return rc;
+    if (split) {
+        GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[1], 0));
+        if ((rc = gzb_mesh_weights_fix_dev(ctx, yt, xt, np_out, sm_out, wb_out, chg, nchg)) != GZB_OK) return rc;
+        if ((rc = gzb_interp_dev(ctx, nt, tt, sm_out, wb_out, nrec, tmod, slab_dev, dtype, k0, nk, rmissval, vnp_out,
+                                 vbl_out, chg, nchg)) != GZB_OK) return rc;
+    }
+    return GZB_OK;
 }

@@ -46,8 +46,9 @@ struct GzbLut {
 struct GzbGrid {
     int64_t Nj, Ni;
     int kew;
-    const double* lat;
+    const double* lat;      // row-major (Nj, Ni), as uploaded: the streaming kernels read these
     const double* lon;
+    const double2* ll;      // the same coordinates interleaved (lat, lon): one sector per cell for the gathers
     const double* angle;    // may be null
     const int8_t* mask;     // may be null
     const float* cells;     // per leaf tile: x[32] y[32] z[32] (unit vectors), tile row-major
@@ -73,10 +74,14 @@ struct gzb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;     // chain part of K1 while K2+K3 run on `stream` (gzb_mapping)
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr};
+    int overlap = 1;                 // gzb_mapping: 1 run the chain replays beside K2+K3, 0 strictly in sequence
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     GzbGrid g;
     double* d_lat = nullptr;
     double* d_lon = nullptr;
+    double2* d_ll = nullptr;
     double* d_angle = nullptr;
     int8_t* d_mask = nullptr;
     float* d_cells = nullptr;
@@ -86,6 +91,7 @@ struct gzb_ctx {
     unsigned* d_lut[2] = {nullptr, nullptr};
     unsigned* d_mbits = nullptr;     // land-sea mask as bits in 16x16-cell tiles (K4); d_flags[2] != 0: mask not {0,1}
     int mask_bits_ok = 0;
+    int k4_early = 0;                // K4 load order: 1 field loads issued before the ocean test, 0 after it (measured faster)
     double* d_hdg = nullptr;         // heading table of K2 (48 B per cell), built on demand
     int hdg_mode = 1;                // 0 never, 1 when the points mapped on this grid outnumber its cells / 2, 2 at the next K2 call
     int hdg_built = 0;

@@ -190,6 +190,12 @@ k_build_level(GzbGrid g, int l, int is_top) {
     }
 }
 
+__global__ void __launch_bounds__(256)
+k_interleave(const int64_t n, const double* __restrict__ lat, const double* __restrict__ lon, double2* __restrict__ ll) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) ll[k] = make_double2(lat[k], lon[k]);
+}
+
 __global__ void k_fill_empty(float4* p, int64_t n) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) p[k] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
@@ -518,6 +524,13 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
 #define CK(call) if ((e = (call)) != cudaSuccess) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
         CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        {   // the chain part of K1 is latency-bound and small: it must get SM slots ahead of the bulk kernels
+            int least = 0, greatest = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, greatest));
+        }
+        CK(cudaEventCreateWithFlags(&ctx->ev_k1[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_k1[1], cudaEventDisableTiming));
         ctx->stream = ctx->own_stream;
         bool evfail = false;
         for (int k = 0; k < 4; ++k)
@@ -528,6 +541,9 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
         CK(cudaMalloc((void**)&ctx->d_lon, n * sizeof(double)));
         CK(cudaMemcpyAsync(ctx->d_lat, lat, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_lon, lon, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMalloc((void**)&ctx->d_ll, n * sizeof(double2)));
+        k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, ctx->d_lat, ctx->d_lon, ctx->d_ll);
+        ctx->stats.kernel_launches++;
         ctx->stats.h2d_bytes += 2 * n * sizeof(double);
         if (angle_or_null) {
             CK(cudaMalloc((void**)&ctx->d_angle, n * sizeof(double)));
@@ -550,6 +566,7 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
         ctx->g.kew = k_ew_per;
         ctx->g.lat = ctx->d_lat;
         ctx->g.lon = ctx->d_lon;
+        ctx->g.ll = ctx->d_ll;
         ctx->g.angle = ctx->d_angle;
         ctx->g.mask = ctx->d_mask;
         if ((rc = build_pyramid(ctx)) != GZB_OK) break;
@@ -574,6 +591,7 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     cudaFree(ctx->d_lat);
     cudaFree(ctx->d_lon);
+    cudaFree(ctx->d_ll);
     cudaFree(ctx->d_angle);
     cudaFree(ctx->d_mask);
     cudaFree(ctx->d_cells);
@@ -593,6 +611,9 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->ev_k1[k]) cudaEventDestroy(ctx->ev_k1[k]);
     cudaGetLastError();
     delete ctx;
     return GZB_OK;
@@ -660,6 +681,12 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
         ctx->hdg_mode = value < 0 ? 0 : (value > 2 ? 2 : (int)value);
         if (ctx->hdg_mode == 0) { ctx->g.hdg = nullptr; ctx->hdg_built = 0; ctx->stats.heading_table = 0; }
         return GZB_OK;
+    }
+    if (!strcmp(name, "overlap")) { ctx->overlap = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "k4_early")) { ctx->k4_early = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "mask_bits")) {
+        if (!value) { ctx->mask_bits_ok = 0; return GZB_OK; }
+        return gzb_build_mask_bits(ctx);
     }
     if (!strcmp(name, "force_heavy")) { ctx->force_heavy = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
     return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_option: unknown option '%s'", name);

@@ -50,20 +50,21 @@ __device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const
 // Loads are issued as early as their addresses are known (mesh and weights before the bracket
 // search, the eight field values together with the mask) so that a point costs two dependent
 // DRAM round trips, not four.
-template <typename T>
-__global__ void __launch_bounds__(256, 4)
-k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
+template <typename T, bool EARLY>
+__device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t, const double* __restrict__ t_sat,
          const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
          const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
          const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
          int* __restrict__ err, const unsigned* __restrict__ mbits, const int* __restrict__ mflag) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nt) return;
     const double now = __ldg(t_sat + t);
     const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
     const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
-    const longlong2 p1 = sm[0], p2 = sm[1], p3 = sm[2], p4 = sm[3];
-    const double2 wa = wb[0], wc = wb[1];
+    longlong2 p1, p2, p3, p4;
+    double2 wa, wc;
+    if (EARLY) {
+        p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
+        wa = wb[0]; wc = wb[1];
+    }
     if (init) {
         out_np[t] = rmiss;
         out_bl[t] = rmiss;
@@ -78,6 +79,9 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
         if (tmod[mid] <= now) lo = mid; else hi = mid;
     }
     if (lo < k0 || lo + 1 >= k0 + nk) return;   // bracket not inside this slab
+    if (!EARLY) {
+        p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
+    }
     const long long j1 = pywrap_idx(p1.x, g.Nj), i1 = pywrap_idx(p1.y, g.Ni);
     const long long j2 = pywrap_idx(p2.x, g.Nj), i2 = pywrap_idx(p2.y, g.Ni);
     const long long j3 = pywrap_idx(p3.x, g.Nj), i3 = pywrap_idx(p3.y, g.Ni);
@@ -86,10 +90,11 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
     const long long cells = g.Nj * g.Ni;
     const T* __restrict__ X1 = slab + (lo - k0) * cells;
     const T* __restrict__ X2 = X1 + cells;
-    const T a1 = X1[c1], b1 = X2[c1];
-    const T a2 = X1[c2], b2 = X2[c2];
-    const T a3 = X1[c3], b3 = X2[c3];
-    const T a4 = X1[c4], b4 = X2[c4];
+    T a1, b1, a2, b2, a3, b3, a4, b4;
+    if (EARLY) {
+        a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
+        a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
+    }
     int ocean;
     if (mbits && *mflag == 0) {
         const long long ntI = (g.Ni + 15) >> 4;
@@ -99,6 +104,11 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
         ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
     }
     if (ocean != 4) return;
+    if (!EARLY) {
+        wa = wb[0]; wc = wb[1];
+        a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
+        a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
+    }
     const T dt = (T)(tmod[lo + 1] - tmod[lo]);
     const T de = (T)(now - tmod[lo]);
     const T v1 = a1 + ((b1 - a1) / dt) * de;
@@ -109,6 +119,28 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
     const double sw = ((wa.x + wa.y) + wc.x) + wc.y;
     if (!(fabs(sw - 1.0) > 0.001))
         out_bl[t] = ((wa.x * (double)v1 + wa.y * (double)v2) + wc.x * (double)v3) + wc.y * (double)v4;
+}
+
+// `list` == nullptr: thread per point t < nt.  Otherwise only the *count points listed (the ones
+// whose mesh changed after a speculative pass, gzb_map_interp), grid-stride.
+template <typename T, bool EARLY>
+__global__ void __launch_bounds__(256, EARLY ? 4 : 5)
+k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
+         const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
+         const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
+         const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
+         int* __restrict__ err, const unsigned* __restrict__ mbits, const int* __restrict__ mflag,
+         const long long* __restrict__ list, const unsigned long long* __restrict__ count) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) {
+        const long long n = (long long)*count;
+        for (long long e = gt; e < n; e += (long long)gridDim.x * blockDim.x)
+            interp_point<T, EARLY>(g, list[e], t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl, err,
+                                   mbits, mflag);
+    } else if (gt < nt) {
+        interp_point<T, EARLY>(g, gt, t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl, err, mbits,
+                               mflag);
+    }
 }
 
 int gzb_build_mask_bits(gzb_ctx* ctx) {
@@ -130,20 +162,47 @@ int gzb_build_mask_bits(gzb_ctx* ctx) {
 template <typename T>
 static int launch_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,
                          int64_t nrec, const double* tmod, const void* slab, int64_t k0, int64_t nk,
-                         double rmiss, int init, double* np_out, double* bl_out, int* err) {
-    k_interp<T><<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab, k0, nk, rmiss, init, np_out, bl_out, err,
-        ctx->mask_bits_ok ? ctx->d_mbits : nullptr, ctx->d_flags + 2);
+                         double rmiss, int init, double* np_out, double* bl_out, int* err,
+                         const long long* list = nullptr, const unsigned long long* count = nullptr) {
+    const unsigned nblk = list ? 32u : (unsigned)((nt + 255) / 256);
+    const unsigned* mb = ctx->mask_bits_ok ? ctx->d_mbits : nullptr;
+    if (ctx->k4_early)
+        k_interp<T, true><<<nblk, 256, 0, ctx->stream>>>(ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab,
+                                                         k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count);
+    else
+        k_interp<T, false><<<nblk, 256, 0, ctx->stream>>>(ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab,
+                                                          k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }
 
 static int interp_chunk(gzb_ctx* ctx, int dtype, int64_t nt, const double* t, const int64_t* sm, const double* wb,
                         int64_t nrec, const double* tmod, const void* slab, int64_t k0, int64_t nk, double rmiss,
-                        int init, double* np_out, double* bl_out, int* err) {
+                        int init, double* np_out, double* bl_out, int* err, const long long* list = nullptr,
+                        const unsigned long long* count = nullptr) {
     if (dtype == GZB_F32)
-        return launch_interp<float>(ctx, nt, t, sm, wb, nrec, tmod, slab, k0, nk, rmiss, init, np_out, bl_out, err);
-    return launch_interp<double>(ctx, nt, t, sm, wb, nrec, tmod, slab, k0, nk, rmiss, init, np_out, bl_out, err);
+        return launch_interp<float>(ctx, nt, t, sm, wb, nrec, tmod, slab, k0, nk, rmiss, init, np_out, bl_out, err, list, count);
+    return launch_interp<double>(ctx, nt, t, sm, wb, nrec, tmod, slab, k0, nk, rmiss, init, np_out, bl_out, err, list, count);
+}
+
+// device-level K4 on a slab the GPU can read (HBM, or pinned + mapped host memory through
+// `slab_dev`); all other pointers are device pointers.  Used by gzb_map_interp.
+int gzb_interp_dev(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb, int64_t nrec,
+                   const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss,
+                   double* np_out, double* bl_out, const long long* list, const unsigned long long* count) {
+    ctx->time_err_pending = 1;          // checked by gzb_sync()
+    return interp_chunk(ctx, dtype, nt, t, sm, wb, nrec, tmod, slab_dev, k0, nk, rmiss, 1, np_out, bl_out, ctx->d_flags,
+                        list, count);
+}
+
+// can the GPU read `slab` directly?  (device / managed memory, or pinned + mapped host memory)
+int gzb_slab_device_pointer(const void* slab, const void** dev_out, int* is_host) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, slab);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) { *dev_out = slab; *is_host = 0; return 1; }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) { *dev_out = at.devicePointer; *is_host = 1; return 1; }
+    return 0;
 }
 
 extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb,

@@ -59,11 +59,11 @@ __device__ __forceinline__ void cell_frame(const GzbGrid& g, const long long jP,
                                            const long long jm, const long long jp, const long long im,
                                            const long long ip, double& y0, double& x0, double& hN, double& hE,
                                            double& hS, double& hW) {
-    const double lat0 = g.lat[jP * g.Ni + iP], lonP = g.lon[jP * g.Ni + iP];
-    const double latN = g.lat[jp * g.Ni + iP], lonN = g.lon[jp * g.Ni + iP];
-    const double latE = g.lat[jP * g.Ni + ip], lonE = g.lon[jP * g.Ni + ip];
-    const double latS = g.lat[jm * g.Ni + iP], lonS = g.lon[jm * g.Ni + iP];
-    const double latW = g.lat[jP * g.Ni + im], lonW = g.lon[jP * g.Ni + im];
+    const double2 cP = __ldg(g.ll + (jP * g.Ni + iP)), cN = __ldg(g.ll + (jp * g.Ni + iP));
+    const double2 cE = __ldg(g.ll + (jP * g.Ni + ip)), cS = __ldg(g.ll + (jm * g.Ni + iP));
+    const double2 cW = __ldg(g.ll + (jP * g.Ni + im));
+    const double lat0 = cP.x, lonP = cP.y, latN = cN.x, lonN = cN.y, latE = cE.x, lonE = cE.y;
+    const double latS = cS.x, lonS = cS.y, latW = cW.x, lonW = cW.y;
     y0 = gzb_merc_y(lat0);
     x0 = gzb_pymod(lonP, 360.0) * GZB_D2R;
     hN = gzb_heading_y(y0, x0, gzb_merc_y(latN), gzb_pymod(lonN, 360.0) * GZB_D2R);
@@ -124,8 +124,9 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
                 double qy[4], qx[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    qy[k] = g.lat[cj[k] * g.Ni + ci[k]];
-                    qx[k] = g.lon[cj[k] * g.Ni + ci[k]];
+                    const double2 c = __ldg(g.ll + (cj[k] * g.Ni + ci[k]));
+                    qy[k] = c.x;
+                    qx[k] = c.y;
                 }
                 if (strictly_in_quad(yT, xT, qy, qx)) {
                     iq = cand;
@@ -157,8 +158,9 @@ __device__ __forceinline__ void weights_one(const GzbGrid& g, const double yT, c
             long long j = pywrap(cj[k], g.Nj), i = pywrap(ci[k], g.Ni);
             j = j < 0 ? 0 : (j >= g.Nj ? g.Nj - 1 : j);
             i = i < 0 ? 0 : (i >= g.Ni ? g.Ni - 1 : i);
-            vy[k + 1] = g.lat[j * g.Ni + i];
-            vx[k + 1] = g.lon[j * g.Ni + i];
+            const double2 c = __ldg(g.ll + (j * g.Ni + i));
+            vy[k + 1] = c.x;
+            vx[k + 1] = c.y;
         }
         double a, b;
         gzb_alfabeta_dev(vy, vx, a, b);
@@ -268,6 +270,38 @@ int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const doubl
     if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
     k_mesh_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
                                                                          (long long*)sm_out, wb_out, ctx->force_heavy);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
+}
+
+// K2 + K3 again for the listed points (the ones whose nearest point the chain replays changed
+// after k_mesh_weights had used the speculative value); the list length lives on the device
+__global__ void __launch_bounds__(128)
+k_mesh_weights_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
+                   const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
+                   const long long* __restrict__ list, const unsigned long long* __restrict__ count,
+                   const int force_heavy) {
+    const long long n = (long long)*count;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long t = list[e];
+        const double yT = yt[t], xT = xt[t];
+        long long cj[4], ci[4];
+        source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
+        longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sm[k] = make_longlong2(cj[k], ci[k]);
+        double w[4];
+        weights_one(g, yT, xT, cj, ci, w);
+        double2* out = reinterpret_cast<double2*>(WB + 4 * t);
+        out[0] = make_double2(w[0], w[1]);
+        out[1] = make_double2(w[2], w[3]);
+    }
+}
+
+int gzb_mesh_weights_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
+                             double* wb_out, const long long* list, const unsigned long long* count) {
+    k_mesh_weights_fix<<<64, 128, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out,
+                                                   list, count, ctx->force_heavy);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }

@@ -35,6 +35,19 @@
 #define M_BOX 1      // only cells inside the index box
 #define M_EXCL 2     // only cells outside the index box, proxies only (certificate build)
 
+// flat index -> (j, i); grids of fewer than 2^32 cells (all but the largest) take a 32-bit division
+__device__ __forceinline__ void gzb_split(const GzbGrid& g, const long long flat, long long& j, long long& i) {
+    if ((unsigned long long)flat <= 0xffffffffull) {
+        const unsigned f = (unsigned)flat, n = (unsigned)g.Ni;
+        const unsigned q = f / n;
+        j = (long long)q;
+        i = (long long)(f - q * n);
+    } else {
+        j = flat / g.Ni;
+        i = flat - j * g.Ni;
+    }
+}
+
 struct WarpSm {
     int fJ[GZB_MAXLEV + 1];
     int fI[GZB_MAXLEV + 1];
@@ -102,7 +115,8 @@ __device__ __forceinline__ void flush_queue(const GzbGrid& g, WarpSm& w, const i
         long long flat = 0;
         if (act) {
             flat = w.qflat[e];
-            const double d = gzb_haversine_dev(plat, plon, cpl, g.lat[flat], g.lon[flat]);
+            const double2 c = __ldg(g.ll + flat);
+            const double d = gzb_haversine_dev(plat, plon, cpl, c.x, c.y);
             if (d == d) dbits = (unsigned long long)__double_as_longlong(d); else act = false;
         }
         if (act) pre = w.bd[pt];
@@ -289,7 +303,7 @@ __device__ __forceinline__ void box_search(const GzbGrid& g, WarpSm& w, const in
                 tl[u] = -1;
                 nd[u] = make_float4(0.f, 0.f, 0.f, -1.f);
                 if (k < nT) {
-                    const int a = k / nTI;
+                    const int a = (int)((unsigned)k / (unsigned)nTI);
                     const int tj = tJ0 + a, ti = tI0 + (k - a * nTI);
                     tl[u] = tj * L0.nI + ti;
                     nd[u] = L0.nodes[gzb_leaf_index(g, tj, ti)];
@@ -332,7 +346,7 @@ __device__ __forceinline__ void box_search(const GzbGrid& g, WarpSm& w, const in
                 const int tile = w.kt[b + u];
                 const float* __restrict__ cc = g.cells + (long long)tile * 96;
                 x[u] = cc[lane]; y[u] = cc[32 + lane]; z[u] = cc[64 + lane];
-                const int tj = tile / L0.nI;
+                const int tj = (int)((unsigned)tile / (unsigned)L0.nI);
                 const long long j = (long long)tj * GZB_TILE_J + lj;
                 const long long i = (long long)(tile - tj * L0.nI) * GZB_TILE_I + li;
                 ok[u] = (j >= j0) && (j < j1) && (i >= i0) && (i < i1);
@@ -356,7 +370,7 @@ __device__ __forceinline__ void box_search(const GzbGrid& g, WarpSm& w, const in
         const int tile = w.kt[b];
         const float* __restrict__ cc = g.cells + (long long)tile * 96;
         const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
-        const int tj = tile / L0.nI;
+        const int tj = (int)((unsigned)tile / (unsigned)L0.nI);
         const long long j = (long long)tj * GZB_TILE_J + lj;
         const long long i = (long long)(tile - tj * L0.nI) * GZB_TILE_I + li;
         const float dx = s.px - x, dy = s.py - y, dz = s.pz - z;
@@ -542,7 +556,8 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
     const double cpl = cos(lat * GZB_D2R);
     const long long f0 = CAND_FLAT(c);
     if (!(c & CAND_MULTI)) {
-        const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f0], g.lon[f0]);
+        const double2 c0 = __ldg(g.ll + f0);
+        const double d = gzb_haversine_dev(lat, lon, cpl, c0.x, c0.y);
         if (d == d) { bd = (unsigned long long)__double_as_longlong(d); bf = f0; }
         return;
     }
@@ -567,7 +582,8 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
             const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
             const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
             if (!(P <= B2)) continue;
-            const double d = gzb_haversine_dev(lat, lon, cpl, g.lat[f], g.lon[f]);
+            const double2 cf = __ldg(g.ll + f);
+            const double d = gzb_haversine_dev(lat, lon, cpl, cf.x, cf.y);
             if (!(d == d)) continue;
             const unsigned long long db = (unsigned long long)__double_as_longlong(d);
             if (db < bd) { bd = db; bf = f; }     // row-major scan: the first index keeps a tie
@@ -763,8 +779,7 @@ int gzb_build_cert(gzb_ctx* ctx) {
 __device__ __forceinline__ void accept_edge(const GzbGrid& g, const long long flat, const double d,
                                             const double thr, long long& j, long long& i, const int edge = 1) {
     if (flat != GZB_NOFLAT && d < thr) {
-        j = flat / g.Ni;
-        i = flat - j * g.Ni;
+        gzb_split(g, flat, j, i);
     } else {
         j = -1;
         i = -1;
@@ -809,7 +824,8 @@ k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* _
         if (pj != 0 && pi != 0) {   // Python truthiness of (j_prv and i_prv)
             long long j0, j1, i0, i1;
             if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
-                const long long gj = f / g.Ni, gi = f - gj * g.Ni;
+                long long gj = 0, gi = 0;
+                if (f != GZB_NOFLAT) gzb_split(g, f, gj, gi);
                 const bool inside = (f != GZB_NOFLAT) && gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
                 if (!inside) {
                     isb = 1;
@@ -832,7 +848,8 @@ k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* _
 }
 
 // exclusive scan of the per-block break counts (single block)
-__global__ void __launch_bounds__(1024)
+#define SCAN_T 256
+__global__ void __launch_bounds__(SCAN_T)
 k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, const long long nblk,
               long long* __restrict__ total) {
     __shared__ long long wsum[32];
@@ -840,7 +857,7 @@ k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, c
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < nblk; base += 1024) {
+    for (long long base = 0; base < nblk; base += SCAN_T) {
         const long long k = base + threadIdx.x;
         long long v = k < nblk ? counts[k] : 0;
         long long s = v;
@@ -852,7 +869,7 @@ k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, c
         if (lane == 31) wsum[warp] = s;
         __syncthreads();
         if (warp == 0) {
-            long long ww = wsum[lane];
+            long long ww = lane < (SCAN_T >> 5) ? wsum[lane] : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const long long u = __shfl_up_sync(0xffffffffu, ww, o);
@@ -864,7 +881,7 @@ k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, c
         const long long pre = carry + (warp ? wsum[warp - 1] : 0) + s - v;
         if (k < nblk) offsets[k] = pre;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = pre + v;
+        if (threadIdx.x == SCAN_T - 1) carry = pre + v;
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = carry;
@@ -905,19 +922,22 @@ k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ o
 // step, and replays again only if another (discarded) replay overwrote part of its log.
 #define WLOG_TAG(k) ((unsigned long long)(((k) + 1) & 0x7ffffffLL) << 36)
 
+// warps (= replays) per block of k_walk; one-warp blocks were measured slower, alone and beside K2+K3
+#define WALK_WARPS 8
 template <bool WRITE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * WALK_WARPS)
 k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
        const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
        const long long* __restrict__ breaks, const long long* __restrict__ nbrk_p,
        long long* __restrict__ stop, long long* __restrict__ first, const unsigned char* __restrict__ valid,
-       unsigned long long* __restrict__ wlog, long long* __restrict__ NP, unsigned long long* __restrict__ steps) {
-    __shared__ WarpSm ws[8];
+       unsigned long long* __restrict__ wlog, long long* __restrict__ NP, unsigned long long* __restrict__ steps,
+       long long* __restrict__ chg, unsigned long long* __restrict__ nchg) {
+    __shared__ WarpSm ws[WALK_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSm& w = ws[warp];
     const long long nb = *nbrk_p;
-    const long long nwarps = (long long)gridDim.x * 8;
-    for (long long k = (long long)blockIdx.x * 8 + warp; k < nb; k += nwarps) {
+    const long long nwarps = (long long)gridDim.x * WALK_WARPS;
+    for (long long k = (long long)blockIdx.x * WALK_WARPS + warp; k < nb; k += nwarps) {
         const long long b = breaks[k];
         long long tend = nt - 1;          // last point this replay may touch
         if (WRITE) {
@@ -927,6 +947,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                 if (lane == 0) {
                     NP[2 * b] = first[2 * k];
                     NP[2 * b + 1] = first[2 * k + 1];
+                    if (chg) chg[atomicAdd(nchg, 1ull)] = b;
                 }
                 continue;
             }
@@ -944,6 +965,16 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                         const long long j = f < 0 ? -1 : f / g.Ni;
                         NP[2 * t] = j;
                         NP[2 * t + 1] = f < 0 ? -1 : f - j * g.Ni;
+                    }
+                }
+                if (chg) {      // points whose mesh / weights must be recomputed (gzb_mapping overlap)
+                    const bool wrote = (t <= e) && !bad;
+                    const unsigned wm = __ballot_sync(0xffffffffu, wrote);
+                    if (wm) {
+                        unsigned long long base = 0;
+                        if (lane == __ffs(wm) - 1) base = atomicAdd(nchg, (unsigned long long)__popc(wm));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(wm) - 1);
+                        if (wrote) chg[base + __popc(wm & ((1u << lane) - 1u))] = t;
                     }
                 }
                 if (__any_sync(0xffffffffu, bad)) clobbered = true;
@@ -988,7 +1019,8 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                         // so R(t) = E(t) whatever its distance (DESIGN.md, K1 key fact) -- no search
                         bool inside = false;
                         if (qgf != GZB_NOFLAT) {
-                            const long long gj = qgf / g.Ni, gi = qgf - gj * g.Ni;
+                            long long gj, gi;
+                            gzb_split(g, qgf, gj, gi);
                             inside = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
                         }
                         if (!inside) {
@@ -1012,6 +1044,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                     if (lane == 0) {
                         NP[2 * t] = rj;
                         NP[2 * t + 1] = ri;
+                        if (chg) chg[atomicAdd(nchg, 1ull)] = t;
                     }
                     if (t >= tend) { done = true; break; }
                 } else {
@@ -1045,7 +1078,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
 // list in shared memory, 2048 entries at a time; warp 0 then runs the (inherently ordered)
 // scan, 32 breaks per step on the common path where no replay reaches the next break.
 #define VALID_CHUNK 2048
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop,
         const long long* __restrict__ nbrk_p, unsigned char* __restrict__ valid, long long* __restrict__ stats_out) {
     __shared__ long long sb[VALID_CHUNK + 1];
@@ -1163,12 +1196,18 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
            + gzb_align(n)            // valid
            + gzb_align(n * 8)        // replay log
            + gzb_align(n * 8) + gzb_align(n * 4)   // unresolved list, hints
+           + gzb_align(n * 16)       // points changed by the replays (gzb_mapping overlap)
            + gzb_align(64) * 2;      // scalars, corner
 }
 
 // device-level driver: all pointers are device pointers, work is enqueued on ctx->stream
+// With `split`, the chain part (K1c: scan, compaction, replays) is enqueued on ctx->aux_stream
+// behind an event, so that the caller can run K2+K3 on the speculative chain meanwhile; the
+// points the replays changed are listed in *chg_out / *nchg_out (device pointers) and ctx->ev_k1[1]
+// marks the end of the chain part.
 int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double rd_found_km,
-                    int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out) {
+                    int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out, bool split,
+                    const long long** chg_out, const unsigned long long** nchg_out) {
     if (nt <= 0) return GZB_OK;
     if (np_box_r < 0) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_nearest: np_box_r must be >= 0");
     const size_t n = (size_t)nt;
@@ -1185,8 +1224,13 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
     long long* ulist = (long long*)gzb_arena_take(ctx, n * 8);
     unsigned* hint = (unsigned*)gzb_arena_take(ctx, n * 4);
+    long long* chg = (long long*)gzb_arena_take(ctx, n * 16);
     long long* scal = (long long*)gzb_arena_take(ctx, 64);
     if (!scal) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
+    unsigned long long* nchg = (unsigned long long*)(scal + 7);
+    if (!split) chg = nullptr;
+    if (chg_out) *chg_out = chg;
+    if (nchg_out) *nchg_out = nchg;
     double* corner = (double*)(ctx->d_flags + 32);      // persistent: 4 doubles, keyed by np_box_r
     cudaStream_t s = ctx->stream;
 
@@ -1234,21 +1278,30 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     }
     k_flags<<<(unsigned)nblk, FLAGS_BLOCK, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, (long long*)np_out, brk, counts);
     GZB_LAUNCH_CHECK(ctx);
-    k_scan_counts<<<1, 1024, 0, s>>>(counts, offsets, nblk, scal);
+    cudaStream_t sb = s;
+    if (split) {
+        sb = ctx->aux_stream;
+        GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[0], s));
+        GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
+    }
+    k_scan_counts<<<1, SCAN_T, 0, sb>>>(counts, offsets, nblk, scal);
     GZB_LAUNCH_CHECK(ctx);
-    k_compact<<<(unsigned)nblk, FLAGS_BLOCK, 0, s>>>(brk, offsets, nt, breaks);
+    k_compact<<<(unsigned)nblk, FLAGS_BLOCK, 0, sb>>>(brk, offsets, nt, breaks);
     GZB_LAUNCH_CHECK(ctx);
-    long long wblocks = (long long)((n + 7) / 8);
-    const long long wmax = (long long)nsm * 8;
+    long long wblocks = (long long)((n + WALK_WARPS - 1) / WALK_WARPS);
+    const long long wmax = (long long)nsm * 64 / WALK_WARPS;
     if (wblocks > wmax) wblocks = wmax;
-    k_walk<false><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
-                                                   valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));
+    k_walk<false><<<(unsigned)wblocks, 32 * WALK_WARPS, 0, sb>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
+                                                    valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1),
+                                                    nullptr, nullptr);
     GZB_LAUNCH_CHECK(ctx);
-    k_valid<<<1, 1024, 0, s>>>(breaks, stop, scal, valid, (long long*)(ctx->d_flags + 8));
+    k_valid<<<1, 256, 0, sb>>>(breaks, stop, scal, valid, (long long*)(ctx->d_flags + 8));
     GZB_LAUNCH_CHECK(ctx);
-    k_walk<true><<<(unsigned)wblocks, 256, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
-                                                  valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1));
+    k_walk<true><<<(unsigned)wblocks, 32 * WALK_WARPS, 0, sb>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
+                                                   valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1),
+                                                   chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
+    if (split) GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[1], sb));
     ctx->nearest_stats_pending = 1;      // k_valid left (breaks, replay steps) in the persistent flags
     return GZB_OK;
 }

@@ -58,6 +58,20 @@ class CudaEngine:
         self.ctx._ck(L.lib().gzb_nearest(self.ctx._h, y.numel(), self._p(y), self._p(x), float(rd), int(r),
                                          int(seed[0]), int(seed[1]), self._p(out), L.GZB_DEVICE))
 
+    def mapping(self, y, x, rd, r, seed, NP, SM, WB):
+        """K1 + K2 + K3 in one call: the chain replays of K1 run beside K2 + K3."""
+        self.ctx._ck(L.lib().gzb_mapping(self.ctx._h, y.numel(), self._p(y), self._p(x), float(rd), int(r),
+                                         int(seed[0]), int(seed[1]), self._p(NP), self._p(SM), self._p(WB),
+                                         L.GZB_DEVICE))
+
+    def map_interp(self, y, x, t, rd, r, seed, tmod, slab, k0, NP, SM, WB, v_np, v_bl):
+        """K1 + K2 + K3 + K4 in one call (the chain replays of K1 run beside K2-K4)."""
+        dt = L.GZB_F32 if slab.dtype == self.torch.float32 else L.GZB_F64
+        self.ctx._ck(L.lib().gzb_map_interp(self.ctx._h, y.numel(), self._p(y), self._p(x), self._p(t), float(rd), int(r),
+                                            int(seed[0]), int(seed[1]), tmod.numel(), self._p(tmod), self._p(slab), dt,
+                                            int(k0), int(slab.shape[0]), float(config.rmissval), self._p(NP),
+                                            self._p(SM), self._p(WB), self._p(v_np), self._p(v_bl)))
+
     def mesh_weights(self, y, x, NP, SM, WB):
         n = y.numel()
         self.ctx._ck(L.lib().gzb_mesh_weights(self.ctx._h, n, self._p(y), self._p(x), self._p(NP), self._p(SM),
@@ -74,8 +88,10 @@ class ShardedMapper:
     """Maps one rank's segment and gathers the products of all ranks.
 
     Product buffer of a rank (one allocation, so that ONE `all_gather_into_tensor` moves it):
-    int64 words ``[nmax*4]`` = ``ssh_np`` (f64, nmax) | ``ssh_bl`` (f64, nmax) | ``NP`` (i64, nmax*2);
-    the kernels write straight into views of it."""
+    int64 words ``[(nmax+1)*4]`` = ``ssh_np`` (f64, nmax+1) | ``ssh_bl`` (f64, nmax+1) | ``NP``
+    (i64, (nmax+1)*2).  Row 0 of every section is the slot of the halo point (the last point of the
+    previous segment, mapped again here only to seed the chain), rows 1..n are the rank's own
+    points: the kernels write straight into views of it, halo included, and nothing is copied."""
 
     def __init__(self, engine, dist=None, torch_mod=None):
         self.e = engine
@@ -93,26 +109,45 @@ class ShardedMapper:
         n = bounds[self.rank + 1] - bounds[self.rank]
         self.n = n
         self.halo = self.rank > 0
-        self.pack = self.e.empty((4 * self.nmax,), tc.int64)
+        m1 = self.nmax + 1
+        self.m1 = m1
+        self.pack = self.e.empty((4 * m1,), tc.int64)
         self.pack.zero_()
-        self.v_np = self.pack[:self.nmax].view(tc.float64)[:n]
-        self.v_bl = self.pack[self.nmax:2 * self.nmax].view(tc.float64)[:n]
-        self.NP = self.pack[2 * self.nmax:].view(self.nmax, 2)[:n]
-        self.NPh = self.e.empty((n + 1, 2), tc.int64)          # halo row + own rows (scratch for K1)
-        self.gathered = self.e.empty((self.world, 4 * self.nmax), tc.int64) if self.world > 1 else None
+        self.v_np_h = self.pack[:m1].view(tc.float64)[:n + 1]              # halo slot + own rows
+        self.v_bl_h = self.pack[m1:2 * m1].view(tc.float64)[:n + 1]
+        self.NPh = self.pack[2 * m1:].view(m1, 2)[:n + 1]
+        self.v_np, self.v_bl, self.NP = self.v_np_h[1:], self.v_bl_h[1:], self.NPh[1:]
+        self.SMh = self.e.empty((n + 1, 4, 2), tc.int64)
+        self.WBh = self.e.empty((n + 1, 4), tc.float64)
+        self.SM, self.WB = self.SMh[1:], self.WBh[1:]
+        self.gathered = self.e.empty((self.world, 4 * m1), tc.int64) if self.world > 1 else None
         self.flag = self.e.empty((1,), tc.int32)
         return self
 
+    def _rows(self, t):
+        """The rows an engine call on [halo +] own points writes: from the halo slot, or from row 1."""
+        return t if self.halo else t[1:]
+
     # ---- K1 with the cross-segment seed hand-off -----------------------------------------------
+    def _seed(self, r):
+        # (0,0) is "no previous hit" in the reference (gonzag/bilin_mapping.py:157), so the halo point
+        # gets its plain global answer, i.e. the speculative value of the chain there
+        return (0, 0) if self.halo else (r, r)
+
     def nearest_speculative(self, y_halo, x_halo, rd, r):
-        """K1 on [halo point +] own points.  (0,0) is "no previous hit" in the reference
-        (gonzag/bilin_mapping.py:157), so the halo point gets its plain global answer, i.e. the
-        speculative value of the chain there.  The result lands in ``self.NP``."""
-        if self.halo:
-            self.e.nearest(y_halo, x_halo, rd, r, (0, 0), self.NPh)
-            self.NP.copy_(self.NPh[1:])
-        else:
-            self.e.nearest(y_halo, x_halo, rd, r, (r, r), self.NP)
+        """K1 on [halo point +] own points.  The result lands in ``self.NP`` (halo in ``self.NPh[0]``)."""
+        self.e.nearest(y_halo, x_halo, rd, r, self._seed(r), self._rows(self.NPh))
+
+    def map_speculative(self, y_halo, x_halo, rd, r):
+        """K1 + K2 + K3 on [halo point +] own points in one engine call: ``self.NP/SM/WB``."""
+        self.e.mapping(y_halo, x_halo, rd, r, self._seed(r), self._rows(self.NPh), self._rows(self.SMh),
+                       self._rows(self.WBh))
+
+    def path_speculative(self, y_halo, x_halo, t_halo, rd, r, tmod, slab, k0):
+        """K1 + K2 + K3 + K4 on [halo point +] own points in one engine call: ``self.NP/SM/WB``
+        and the interpolated series ``self.v_np / self.v_bl``."""
+        self.e.map_interp(y_halo, x_halo, t_halo, rd, r, self._seed(r), tmod, slab, k0, self._rows(self.NPh),
+                          self._rows(self.SMh), self._rows(self.WBh), self._rows(self.v_np_h), self._rows(self.v_bl_h))
 
     def gather(self):
         """The one data-path collective: all-gather of the packed products."""
@@ -121,6 +156,10 @@ class ShardedMapper:
         self.dist.all_gather_into_tensor(self.gathered.view(-1), self.pack)
         return self.gathered
 
+    def _last_np_of(self, gathered, g):
+        last = self.bounds[g + 1] - self.bounds[g]          # own rows start at 1
+        return gathered[g, 2 * self.m1:].view(self.m1, 2)[last]
+
     def boundaries_ok(self, gathered):
         """Does every rank's halo assumption equal the true last point of the previous rank?
         One tiny all-reduce + one host read per step."""
@@ -128,10 +167,7 @@ class ShardedMapper:
             return True
         tc = self.torch
         if self.halo:
-            g = self.rank - 1
-            last = self.bounds[g + 1] - self.bounds[g] - 1
-            prev_last = gathered[g, 2 * self.nmax:].view(self.nmax, 2)[last]
-            self.flag[0] = (prev_last != self.NPh[0]).any().to(tc.int32)
+            self.flag[0] = (self._last_np_of(gathered, self.rank - 1) != self.NPh[0]).any().to(tc.int32)
         else:
             self.flag.zero_()
         self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
@@ -141,13 +177,10 @@ class ShardedMapper:
         """Rare path: re-map the segments whose predecessor assumption was wrong, in rank order,
         until every boundary agrees (at most world-1 rounds).  Returns True if THIS rank re-mapped
         (its mesh / weights / interpolation must then be redone by the caller)."""
-        tc = self.torch
         changed = False
         for _ in range(self.world):
             if self.halo:
-                g = self.rank - 1
-                last = self.bounds[g + 1] - self.bounds[g] - 1
-                prev_last = gathered[g, 2 * self.nmax:].view(self.nmax, 2)[last].clone()
+                prev_last = self._last_np_of(gathered, self.rank - 1).clone()
                 if bool((prev_last != self.NPh[0]).any()):
                     self.reseeds += 1
                     changed = True
@@ -163,11 +196,12 @@ class ShardedMapper:
     def unpack(self, gathered):
         """Full-track (ssh_np, ssh_bl, NP) tensors in track order (concatenation of the shards)."""
         tc = self.torch
+        m1 = self.m1
         parts_np, parts_bl, parts_NP = [], [], []
         for g in range(self.world):
             n = self.bounds[g + 1] - self.bounds[g]
             row = gathered[g]
-            parts_np.append(row[:self.nmax].view(tc.float64)[:n])
-            parts_bl.append(row[self.nmax:2 * self.nmax].view(tc.float64)[:n])
-            parts_NP.append(row[2 * self.nmax:].view(self.nmax, 2)[:n])
+            parts_np.append(row[:m1].view(tc.float64)[1:n + 1])
+            parts_bl.append(row[m1:2 * m1].view(tc.float64)[1:n + 1])
+            parts_NP.append(row[2 * m1:].view(m1, 2)[1:n + 1])
         return tc.cat(parts_np), tc.cat(parts_bl), tc.cat(parts_NP)

@@ -86,6 +86,8 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * cell and the headings to its four neighbours, 48 B per cell) from a table instead of computing
  * it per track point: 0 never, 1 (default) build it once the points mapped on this context
  * outnumber half the grid cells, 2 build it at the next K2 call.  Same results either way.
+ * "overlap": 1 (default) gzb_mapping / gzb_map_interp run the chain replays of K1 on a second
+ * stream beside K2+K3(+K4) and repair the points the replays changed; 0 strictly in sequence.
  * "edge_exclusion": 1 (default) gzb_nearest applies the first/last row/column rule of
  * BilinTrack.nrpt (gonzag/bilin_mapping.py:582-585); 0 gives plain NearestPoint() results.
  * "force_heavy": 0 (default); 1 = heavy-duty quadrant search as if |angle| > 45 everywhere;
@@ -133,6 +135,17 @@ int gzb_mesh_weights(gzb_ctx* ctx, int64_t nt, const double* yt, const double* x
 int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
                 double rd_found_km, int np_box_r, int64_t seed_j, int64_t seed_i,
                 int64_t* np_out, int64_t* sm_out, double* wb_out, int where);
+
+/* K1+K2+K3+K4 in one call on a device-resident track (what Model2SatTrack.__init__ does from
+ * BilinTrack(...) to the end of its interpolation loop, gonzag/mod2sat.py:49-139).  All track
+ * arrays are DEVICE pointers; `slab` holds records k0 .. k0+nk-1 and must be readable by the GPU
+ * (device memory, or pinned + mapped host memory) and bracket every track time.  Same results as
+ * gzb_mapping followed by gzb_interp; the chain replays of K1 run beside K2-K4. */
+int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const double* tt,
+                   double rd_found_km, int np_box_r, int64_t seed_j, int64_t seed_i,
+                   int64_t nrec, const double* tmod, const void* slab, int dtype, int64_t k0, int64_t nk,
+                   double rmissval, int64_t* np_out, int64_t* sm_out, double* wb_out,
+                   double* vnp_out, double* vbl_out);
 
 /* ---- K4: fused time-linear + space-bilinear gather -----------------------------------------
  * Replaces the interpolation loop of Model2SatTrack (gonzag/mod2sat.py:74-139).

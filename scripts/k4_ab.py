@@ -1,0 +1,48 @@
+"""GPU experiment: K4 variants (load order x mask representation) on the bench workload."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import gonzag_b200 as gzb
+from gonzag_b200 import synthetic as syn
+from gonzag_b200.multi import CudaEngine
+import bench
+
+w = bench.WORKLOADS["C3"]
+lat, lon, mask, res, rd, r = bench.make_grid(w)
+t, y, x = bench.make_track(w, 0, 1)
+torch.cuda.set_device(0)
+dev = torch.device("cuda", 0)
+ctx = gzb.GridContext(lat, lon, mask=mask, k_ew_per=2)
+ctx.grid_angle(out=False)
+eng = CudaEngine(ctx, torch)
+k_hi = int(t[-1] // 3600.0) + 1
+slab = bench.field_on_device(torch, dev, torch.as_tensor(lat, device=dev), torch.as_tensor(lon, device=dev), 0, k_hi)
+tmod = eng.tensor(3600.0 * np.arange(k_hi + 1))
+yd, xd, td = eng.tensor(y), eng.tensor(x), eng.tensor(t)
+n = len(y)
+NP = eng.empty((n, 2), torch.int64); SM = eng.empty((n, 4, 2), torch.int64); WB = eng.empty((n, 4), torch.float64)
+v_np = eng.empty((n,), torch.float64); v_bl = eng.empty((n,), torch.float64)
+eng.nearest(yd, xd, rd, r, (r, r), NP)
+eng.mesh_weights(yd, xd, NP, SM, WB)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ref = None
+for early in (0, 1):
+    for bits in (0, 1):
+        ctx.set_option("k4_early", early)
+        ctx.set_option("mask_bits", bits)
+        ms = []
+        for it in range(8):
+            torch.cuda.synchronize()
+            flush.zero_(); flush.zero_()
+            e0.record()
+            eng.interp(td, SM, WB, tmod, slab, 0, v_np, v_bl)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        out = (v_np.clone(), v_bl.clone())
+        if ref is None:
+            ref = out
+        same = bool((out[0] == ref[0]).all() and (out[1] == ref[1]).all())
+        print("early %d bits %d: %.2f us (min %.2f)  identical %s" % (early, bits, 1e3 * np.mean(ms[2:]), 1e3 * np.min(ms[2:]), same))

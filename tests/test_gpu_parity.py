@@ -297,3 +297,58 @@ def test_nearest_paths_agree(golden_global, golden_seam):
         xi = np.mod(rng.uniform(355.0, 365.0, 5000), 360.0)
         ctx.nearest(yi, xi, 0.75 * 0.05 * 111.11, 45)
         assert ctx.stats()["last_unresolved"] == 0
+
+
+def test_mapping_overlap_matches_staged(golden_global, golden_seam):
+    """gzb_mapping runs K1's chain replays beside K2+K3 and then repairs the points the replays
+    changed: the result must be the one of the three stages run in sequence."""
+    lat, lon = _grid(golden_global)
+    rd, r = float(golden_seam["rd"]), int(golden_seam["r"])
+    y, x = golden_seam["ysat"], golden_seam["xsat"]
+    with gzb.GridContext(lat, lon, k_ew_per=2) as ctx:
+        ctx.grid_angle(out=False)
+        for table in (0, 2):
+            ctx.set_option("heading_table", table)
+            ctx.set_option("overlap", 1)
+            a = ctx.mapping(y, x, rd, r)
+            assert ctx.stats()["last_chain_steps"] > ctx.stats()["last_breaks"] > 0    # the replays changed points
+            ctx.set_option("overlap", 0)
+            b = ctx.mapping(y, x, rd, r)
+            NP = ctx.nearest(y, x, rd, r)
+            SM = ctx.source_mesh(y, x, NP)
+            WB = ctx.weights(y, x, SM)
+            for u, v, w_ in zip(a, b, (NP, SM, WB)):
+                assert np.array_equal(u, v)
+                assert np.array_equal(u, w_)
+    np.testing.assert_array_equal(a[0], golden_seam["NP"])
+
+
+def test_map_interp_matches_staged(golden_global):
+    """gzb_map_interp (K1-K4 in one call, replays beside K2-K4, repaired points) against the
+    staged calls, device-resident, on the global -D case with its land mask."""
+    import ctypes as C
+    from gonzag_b200 import _lib as L
+    g = golden_global
+    lat, lon = _grid(g)
+    res = float(g["res"])
+    rd, r = 0.75 * res * 111.11, int(0.5 * 500. / (res * 111.11))
+    y, x, t, tm = g["ysat"], g["xsat"], g["tsat"], g["tmod"]
+    n = len(y)
+    for fld in (g["f32"], g["f32"].astype(np.float64)):
+        with gzb.GridContext(lat, lon, angle=g["angle"], mask=g["mask"], k_ew_per=int(g["kew"])) as ctx:
+            NP, SM, WB = ctx.mapping(y, x, rd, r)
+            v_np, v_bl = ctx.interp(t, SM, WB, tm, fld)
+            d = [ctx.upload(a) for a in (L.as_f64(y), L.as_f64(x), L.as_f64(t), L.as_f64(tm), np.ascontiguousarray(fld))]
+            o = [ctx.dev_alloc(n * k) for k in (16, 64, 32, 8, 8)]
+            P = lambda b: C.c_void_p(b.ptr)
+            for overlap in (1, 0):
+                ctx.set_option("overlap", overlap)
+                ctx._ck(L.lib().gzb_map_interp(ctx._h, n, P(d[0]), P(d[1]), P(d[2]), rd, r, r, r, len(tm), P(d[3]), P(d[4]),
+                                               ctx._field_dtype(fld), 0, fld.shape[0], -9999., P(o[0]), P(o[1]), P(o[2]),
+                                               P(o[3]), P(o[4])))
+                ctx.sync()
+                assert np.array_equal(ctx.download(o[0], (n, 2), np.int64), NP)
+                assert np.array_equal(ctx.download(o[1], (n, 4, 2), np.int64), SM)
+                assert np.array_equal(ctx.download(o[2], (n, 4), np.float64), WB)
+                assert np.array_equal(ctx.download(o[3], (n,), np.float64), v_np)
+                assert np.array_equal(ctx.download(o[4], (n,), np.float64), v_bl)
