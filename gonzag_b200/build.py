@@ -39,7 +39,7 @@ def _stale(target, deps):
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "gzb_common.cuh"),
+    headers = [os.path.join(CSRC, "gzb_common.cuh"), os.path.join(CSRC, "gzb_point.cuh"),
                os.path.join(os.path.dirname(HERE), "include", "gonzag_b200.h"), __file__]
     jobs = []
     for src in SOURCES:

@@ -6,8 +6,10 @@ size_t gzb_nearest_ws_bytes(int64_t nt);
 int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double rd_found_km,
                     int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out, bool split = false,
                     const long long** chg_out = nullptr, const unsigned long long** nchg_out = nullptr);
-int gzb_mesh_weights_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
-                             double* wb_out, const long long* list, const unsigned long long* count);
+int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
+                     double* wb_out, const long long* list, const unsigned long long* count, const double* tt,
+                     int64_t nrec, const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk,
+                     double rmiss, double* vnp_out, double* vbl_out);
 int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
                         int64_t* sm_out);
 int gzb_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* sm,
@@ -84,7 +86,8 @@ int run_stages(gzb_ctx* ctx, int stages, int64_t nt, const double* yt, const dou
         if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp, true, &chg, &nchg)) != GZB_OK) return rc;
         if ((rc = gzb_mesh_weights_dev(ctx, nt, dy, dx, dnp, dsm, dwb)) != GZB_OK) return rc;
         GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[1], 0));
-        if ((rc = gzb_mesh_weights_fix_dev(ctx, dy, dx, dnp, dsm, dwb, chg, nchg)) != GZB_OK) return rc;
+        if ((rc = gzb_path_fix_dev(ctx, dy, dx, dnp, dsm, dwb, chg, nchg, nullptr, 0, nullptr, nullptr, 0, 0, 0, 0.0,
+                                   nullptr, nullptr)) != GZB_OK) return rc;
     } else {
     if (stages & ST_NP) {
         if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp)) != GZB_OK) return rc;
@@ -187,9 +190,8 @@ extern "C" int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const 
                              nullptr, nullptr)) != GZB_OK) return rc;
     if (split) {
         GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[1], 0));
-        if ((rc = gzb_mesh_weights_fix_dev(ctx, yt, xt, np_out, sm_out, wb_out, chg, nchg)) != GZB_OK) return rc;
-        if ((rc = gzb_interp_dev(ctx, nt, tt, sm_out, wb_out, nrec, tmod, slab_dev, dtype, k0, nk, rmissval, vnp_out,
-                                 vbl_out, chg, nchg)) != GZB_OK) return rc;
+        if ((rc = gzb_path_fix_dev(ctx, yt, xt, np_out, sm_out, wb_out, chg, nchg, tt, nrec, tmod, slab_dev, dtype, k0, nk,
+                                   rmissval, vnp_out, vbl_out)) != GZB_OK) return rc;
     }
     return GZB_OK;
 }

@@ -2,11 +2,7 @@
 // a14 outputs: cumulative along-track distance (gonzag/mod2sat.py:146-148) and the
 // nearest-point map XNPtrack (gonzag/mod2sat.py:177-184).
 #include "gzb_common.cuh"
-
-__device__ __forceinline__ long long pywrap_idx(long long k, long long n) {
-    k = k < 0 ? k + n : k;                      // Python negative indexing (SM == -1 reads the last cell)
-    return k < 0 ? 0 : (k >= n ? n - 1 : k);    // anything else out of range is clamped, never faults
-}
+#include "gzb_point.cuh"
 
 // Land-sea mask as bits, tiled 16 x 16 cells (one 32-byte sector per tile): the four corners of a
 // source mesh almost always fall in one sector, and consecutive track points reuse it, where the
@@ -35,90 +31,6 @@ k_mask_bits(const long long Nj, const long long Ni, const int8_t* __restrict__ m
     }
     bits[w] = v;
     if (odd) atomicOr(flag, 1);
-}
-
-__device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const long long ntI, const long long j,
-                                        const long long i) {
-    const long long tile = (j >> 4) * ntI + (i >> 4);
-    const int b = (int)(((j & 15) << 4) | (i & 15));
-    return (int)((__ldg(bits + tile * 8 + (b >> 5)) >> (b & 31)) & 1u);
-}
-
-// One thread per track point.  T is the dtype of the model field: the time interpolation
-// x1 + ((x2 - x1) / dt) * (t - t1) is carried out in T (NumPy keeps float32 arrays in float32
-// when combined with Python floats), the weighted sum in float64, left to right, no FMA.
-// Loads are issued as early as their addresses are known (mesh and weights before the bracket
-// search, the eight field values together with the mask) so that a point costs two dependent
-// DRAM round trips, not four.
-template <typename T, bool EARLY>
-__device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t, const double* __restrict__ t_sat,
-         const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
-         const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
-         const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
-         int* __restrict__ err, const unsigned* __restrict__ mbits, const int* __restrict__ mflag) {
-    const double now = __ldg(t_sat + t);
-    const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
-    const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
-    longlong2 p1, p2, p3, p4;
-    double2 wa, wc;
-    if (EARLY) {
-        p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
-        wa = wb[0]; wc = wb[1];
-    }
-    if (init) {
-        out_np[t] = rmiss;
-        out_bl[t] = rmiss;
-    }
-    if (!(now >= tmod[0]) || !(now < tmod[nrec - 1])) {
-        atomicOr(err, 1);
-        return;
-    }
-    long long lo = 0, hi = nrec - 1;            // tmod[lo] <= now < tmod[hi]
-    while (hi - lo > 1) {
-        const long long mid = (lo + hi) >> 1;
-        if (tmod[mid] <= now) lo = mid; else hi = mid;
-    }
-    if (lo < k0 || lo + 1 >= k0 + nk) return;   // bracket not inside this slab
-    if (!EARLY) {
-        p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
-    }
-    const long long j1 = pywrap_idx(p1.x, g.Nj), i1 = pywrap_idx(p1.y, g.Ni);
-    const long long j2 = pywrap_idx(p2.x, g.Nj), i2 = pywrap_idx(p2.y, g.Ni);
-    const long long j3 = pywrap_idx(p3.x, g.Nj), i3 = pywrap_idx(p3.y, g.Ni);
-    const long long j4 = pywrap_idx(p4.x, g.Nj), i4 = pywrap_idx(p4.y, g.Ni);
-    const long long c1 = j1 * g.Ni + i1, c2 = j2 * g.Ni + i2, c3 = j3 * g.Ni + i3, c4 = j4 * g.Ni + i4;
-    const long long cells = g.Nj * g.Ni;
-    const T* __restrict__ X1 = slab + (lo - k0) * cells;
-    const T* __restrict__ X2 = X1 + cells;
-    T a1, b1, a2, b2, a3, b3, a4, b4;
-    if (EARLY) {
-        a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
-        a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
-    }
-    int ocean;
-    if (mbits && *mflag == 0) {
-        const long long ntI = (g.Ni + 15) >> 4;
-        ocean = mask_bit(mbits, ntI, j1, i1) + mask_bit(mbits, ntI, j2, i2) + mask_bit(mbits, ntI, j3, i3) +
-                mask_bit(mbits, ntI, j4, i4);
-    } else {
-        ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
-    }
-    if (ocean != 4) return;
-    if (!EARLY) {
-        wa = wb[0]; wc = wb[1];
-        a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
-        a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
-    }
-    const T dt = (T)(tmod[lo + 1] - tmod[lo]);
-    const T de = (T)(now - tmod[lo]);
-    const T v1 = a1 + ((b1 - a1) / dt) * de;
-    const T v2 = a2 + ((b2 - a2) / dt) * de;
-    const T v3 = a3 + ((b3 - a3) / dt) * de;
-    const T v4 = a4 + ((b4 - a4) / dt) * de;
-    out_np[t] = (double)v1;
-    const double sw = ((wa.x + wa.y) + wc.x) + wc.y;
-    if (!(fabs(sw - 1.0) > 0.001))
-        out_bl[t] = ((wa.x * (double)v1 + wa.y * (double)v2) + wc.x * (double)v3) + wc.y * (double)v4;
 }
 
 // `list` == nullptr: thread per point t < nt.  Otherwise only the *count points listed (the ones

@@ -3,6 +3,7 @@
 //      (gonzag/bilin_mapping.py:595-608, 453-486, 329-449, 215-262, 194-212)
 //   K3 restates BilinTrack.wght / WeightBL / AlfaBeta (gonzag/bilin_mapping.py:610-617, 490-527, 50-141)
 #include "gzb_common.cuh"
+#include "gzb_point.cuh"
 
 // gonzag/bilin_mapping.py:194-212; -1 flags a missing neighbour
 __device__ __forceinline__ void neighbours(const GzbGrid& g, long long jP, long long iP, long long& jm,
@@ -274,13 +275,29 @@ int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const doubl
     return GZB_OK;
 }
 
-// K2 + K3 again for the listed points (the ones whose nearest point the chain replays changed
-// after k_mesh_weights had used the speculative value); the list length lives on the device
-__global__ void __launch_bounds__(128)
-k_mesh_weights_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
-                   const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
-                   const long long* __restrict__ list, const unsigned long long* __restrict__ count,
-                   const int force_heavy) {
+// K2 + K3 (+ K4) again for the listed points: the ones whose nearest point the chain replays
+// changed after the bulk kernels had used the speculative value.  The list length lives on the
+// device.  One kernel for the whole repair: it sits on the critical path behind the replays.
+struct InterpArgs {            // K4 arguments of the fused path; slab == nullptr: mapping only
+    const double* t_sat;
+    long long nrec;
+    const double* tmod;
+    const void* slab;
+    int dtype;
+    long long k0, nk;
+    double rmiss;
+    double* out_np;
+    double* out_bl;
+    int* err;
+    const unsigned* mbits;
+    const int* mflag;
+};
+
+__global__ void __launch_bounds__(64)
+k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
+           const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
+           const long long* __restrict__ list, const unsigned long long* __restrict__ count,
+           const int force_heavy, const InterpArgs ia) {
     const long long n = (long long)*count;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const long long t = list[e];
@@ -288,21 +305,43 @@ k_mesh_weights_fix(const GzbGrid g, const double* __restrict__ yt, const double*
         long long cj[4], ci[4];
         source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
         longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
+        longlong2 rp[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sm[k] = make_longlong2(cj[k], ci[k]);
+        for (int k = 0; k < 4; ++k) {
+            rp[k] = make_longlong2(cj[k], ci[k]);
+            sm[k] = rp[k];
+        }
         double w[4];
         weights_one(g, yT, xT, cj, ci, w);
         double2* out = reinterpret_cast<double2*>(WB + 4 * t);
-        out[0] = make_double2(w[0], w[1]);
-        out[1] = make_double2(w[2], w[3]);
+        const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
+        out[0] = rw[0];
+        out[1] = rw[1];
+        if (ia.slab) {      // K4 straight from the registers: the arrays just written are not read back
+            if (ia.dtype == GZB_F32)
+                interp_point<float, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const float*)ia.slab, ia.k0,
+                                                 ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, rp, rw);
+            else
+                interp_point<double, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const double*)ia.slab, ia.k0,
+                                                  ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, rp, rw);
+        }
     }
 }
 
-int gzb_mesh_weights_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
-                             double* wb_out, const long long* list, const unsigned long long* count) {
-    k_mesh_weights_fix<<<64, 128, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out,
-                                                   list, count, ctx->force_heavy);
+// mapping only (gzb_mapping) when slab_dev == nullptr, mapping + interpolation (gzb_map_interp) otherwise
+int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
+                     double* wb_out, const long long* list, const unsigned long long* count, const double* tt,
+                     int64_t nrec, const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk,
+                     double rmiss, double* vnp_out, double* vbl_out) {
+    InterpArgs ia;
+    ia.t_sat = tt; ia.nrec = nrec; ia.tmod = tmod; ia.slab = slab_dev; ia.dtype = dtype; ia.k0 = k0; ia.nk = nk;
+    ia.rmiss = rmiss; ia.out_np = vnp_out; ia.out_bl = vbl_out; ia.err = ctx->d_flags;
+    ia.mbits = ctx->mask_bits_ok ? ctx->d_mbits : nullptr;
+    ia.mflag = ctx->d_flags + 2;
+    k_path_fix<<<128, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
+                                           ctx->force_heavy, ia);
     GZB_LAUNCH_CHECK(ctx);
+    if (slab_dev) ctx->time_err_pending = 1;
     return GZB_OK;
 }
 

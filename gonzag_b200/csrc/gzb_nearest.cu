@@ -847,44 +847,34 @@ k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* _
     if (threadIdx.x == 0) counts[blockIdx.x] = c;
 }
 
-// exclusive scan of the per-block break counts (single block)
+// exclusive scan of the per-block break counts (single block): every thread sums a contiguous
+// chunk, one block-wide scan of the chunk sums, then the chunk is written out
 #define SCAN_T 256
 __global__ void __launch_bounds__(SCAN_T)
 k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, const long long nblk,
               long long* __restrict__ total) {
-    __shared__ long long wsum[32];
-    __shared__ long long carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
+    __shared__ long long wsum[SCAN_T / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (long long base = 0; base < nblk; base += SCAN_T) {
-        const long long k = base + threadIdx.x;
-        long long v = k < nblk ? counts[k] : 0;
-        long long s = v;
+    const long long per = (nblk + SCAN_T - 1) / SCAN_T;
+    const long long a = (long long)threadIdx.x * per;
+    const long long b = a + per < nblk ? a + per : nblk;
+    long long v = 0;
+    for (long long k = a; k < b; ++k) v += counts[k];
+    long long s = v;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long u = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += u;
-        }
-        if (lane == 31) wsum[warp] = s;
-        __syncthreads();
-        if (warp == 0) {
-            long long ww = lane < (SCAN_T >> 5) ? wsum[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long u = __shfl_up_sync(0xffffffffu, ww, o);
-                if (lane >= o) ww += u;
-            }
-            wsum[lane] = ww;
-        }
-        __syncthreads();
-        const long long pre = carry + (warp ? wsum[warp - 1] : 0) + s - v;
-        if (k < nblk) offsets[k] = pre;
-        __syncthreads();
-        if (threadIdx.x == SCAN_T - 1) carry = pre + v;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_up_sync(0xffffffffu, s, o);
+        if (lane >= o) s += u;
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (lane == 31) wsum[warp] = s;
+    __syncthreads();
+    long long pre = s - v;
+    for (int q = 0; q < warp; ++q) pre += wsum[q];
+    for (long long k = a; k < b; ++k) {
+        offsets[k] = pre;
+        pre += counts[k];
+    }
+    if (threadIdx.x == SCAN_T - 1) *total = pre;
 }
 
 // ordered compaction of the break indices
