@@ -57,6 +57,9 @@ _SIGNATURES = {
     "gzb_weights": (C.c_int, [_P, _I64, _P, _P, _P, _P, C.c_int]),
     "gzb_mesh_weights": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, C.c_int]),
     "gzb_mapping": (C.c_int, [_P, _I64, _P, _P, C.c_double, C.c_int, _I64, _I64, _P, _P, _P, C.c_int]),
+    "gzb_lon_stats": (C.c_int, [_P, _P, _P]),
+    "gzb_lon_to_pm180": (C.c_int, [_P, _P]),
+    "gzb_lat_range": (C.c_int, [_P, _P, _P]),
     "gzb_map_interp": (C.c_int, [_P, _I64, _P, _P, _P, C.c_double, C.c_int, _I64, _I64, _I64, _P, _P, C.c_int, _I64, _I64,
                                  C.c_double, _P, _P, _P, _P, _P]),
     "gzb_interp": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int,
@@ -71,6 +74,7 @@ _SIGNATURES = {
     "gzb_h2d": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gzb_d2h": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gzb_memset": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
+    "gzb_pointer_kind": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "gzb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "gzb_host_free": (C.c_int, [_P]),
     "gzb_host_register": (C.c_int, [_P, C.c_uint64]),
@@ -125,6 +129,13 @@ def as_f64(a):
 
 def as_i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def pointer_kind(arr_or_ptr):
+    """0 pageable host, 1 pinned + mapped host, 2 device memory."""
+    k = C.c_int(0)
+    check(lib().gzb_pointer_kind(ptr(arr_or_ptr), C.byref(k)))
+    return k.value
 
 
 def device_count():

@@ -95,6 +95,7 @@ struct gzb_ctx {
     double* d_hdg = nullptr;         // heading table of K2 (48 B per cell), built on demand
     int hdg_mode = 1;                // 0 never, 1 when the points mapped on this grid outnumber its cells / 2, 2 at the next K2 call
     int hdg_built = 0;
+    double lat_min = 0.0, lat_max = 0.0;   // extent of the grid latitudes (gzb_lat_range)
     int64_t k2_points = 0;           // points that went through K2 on this context
     int nearest_path = 1;            // 1: per-thread hill climb seeded by the look-up table (+ warp fallback); 0: warp walk only
     GzbArena arena;

@@ -360,6 +360,8 @@ static int build_lut(gzb_ctx* ctx, const unsigned long long* ext) {
     const double n = (double)g.Nj * (double)g.Ni;
     if (n >= 4294967295.0) return GZB_OK;                    // flat indices must fit 32 bits
     const double lat_min = ord_dec(ext[0]), lat_max = ord_dec(ext[1]);
+    ctx->lat_min = lat_min;
+    ctx->lat_max = lat_max;
     const double a_min = ord_dec(ext[2]), a_max = ord_dec(ext[3]);
     const double b_min = ord_dec(ext[4]), b_max = ord_dec(ext[5]);
     if (!(lat_max >= lat_min) || !(a_max >= a_min) || !(b_max >= b_min)) return GZB_OK;
@@ -739,6 +741,108 @@ extern "C" int gzb_set_angle(gzb_ctx* ctx, const double* angle_or_null, int wher
     return GZB_OK;
 }
 
+
+// ======================================================================== longitude statistics
+// What IsGlobalLongitudeWise needs (gonzag/utils.py:149-182): with X = lon % 360 and
+// XB = degE_to_degWE(X): min/max of X, the columns of the FIRST occurrences of that min and max
+// (numpy argmin / argmax), min/max of XB.  Two passes: extrema, then the smallest flat index
+// attaining them.  w[0..3] = ord_enc(min X, max X, min XB, max XB); w[4], w[5] = flat indices.
+__global__ void __launch_bounds__(256)
+k_lon_minmax(const int64_t n, const double* __restrict__ lon, unsigned long long* __restrict__ w) {
+    double v[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+    bool nan = false;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double x = gzb_pymod(lon[k], 360.0), xb = gzb_pm180(x);
+        if (x != x) nan = true;
+        v[0] = fmin(v[0], x); v[1] = fmax(v[1], x);
+        v[2] = fmin(v[2], xb); v[3] = fmax(v[3], xb);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, v[q], o);
+            v[q] = (q & 1) ? fmax(v[q], u) : fmin(v[q], u);
+        }
+        if ((threadIdx.x & 31) == 0 && isfinite(v[q])) {
+            if (q & 1) atomicMax(w + q, ord_enc(v[q])); else atomicMin(w + q, ord_enc(v[q]));
+        }
+    }
+    if (nan) atomicOr((unsigned long long*)(w + 6), 1ull);
+}
+
+__global__ void __launch_bounds__(256)
+k_lon_argminmax(const int64_t n, const double* __restrict__ lon, unsigned long long* __restrict__ w) {
+    const unsigned long long emin = w[0], emax = w[1];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long e = ord_enc(gzb_pymod(lon[k], 360.0));
+        if (e == emin) atomicMin(w + 4, (unsigned long long)k);
+        if (e == emax) atomicMin(w + 5, (unsigned long long)k);
+    }
+}
+
+extern "C" int gzb_lon_stats(gzb_ctx* ctx, double* vals4, int64_t* cols2) {
+    if (!ctx || !vals4 || !cols2) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_lon_stats: null argument");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    if (gzb_arena_reserve(ctx, 64) != GZB_OK) return GZB_ERR_NOMEM;
+    unsigned long long* w = (unsigned long long*)gzb_arena_take(ctx, 64);
+    unsigned long long* h = (unsigned long long*)((char*)ctx->pinned + 512);
+    h[0] = ~0ull; h[1] = 0ull; h[2] = ~0ull; h[3] = 0ull; h[4] = ~0ull; h[5] = ~0ull; h[6] = 0ull; h[7] = 0ull;
+    cudaStream_t s = ctx->stream;
+    GZB_CUDA(ctx, cudaMemcpyAsync(w, h, 64, cudaMemcpyHostToDevice, s));
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int64_t n = ctx->g.Nj * ctx->g.Ni;
+    k_lon_minmax<<<nsm * 8, 256, 0, s>>>(n, ctx->d_lon, w);
+    GZB_LAUNCH_CHECK(ctx);
+    k_lon_argminmax<<<nsm * 8, 256, 0, s>>>(n, ctx->d_lon, w);
+    GZB_LAUNCH_CHECK(ctx);
+    GZB_CUDA(ctx, cudaMemcpyAsync(h, w, 64, cudaMemcpyDeviceToHost, s));
+    GZB_CUDA(ctx, cudaStreamSynchronize(s));
+    if (h[6]) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_lon_stats: NaN longitude");
+    for (int q = 0; q < 4; ++q) vals4[q] = ord_dec(h[q]);
+    cols2[0] = (int64_t)(h[4] % (unsigned long long)ctx->g.Ni);
+    cols2[1] = (int64_t)(h[5] % (unsigned long long)ctx->g.Ni);
+    return GZB_OK;
+}
+
+// lon -> degE_to_degWE(lon) in place (ModGrid does it when the domain is handled in the
+// [-180,180] frame, gonzag/utils.py:441).  The fp32 search structures describe the same points on
+// the sphere and stay; the K2 table, which stores longitudes, is dropped.
+__global__ void __launch_bounds__(256)
+k_lon_pm180(const int64_t n, double* __restrict__ lon, double2* __restrict__ ll) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double x = gzb_pm180(lon[k]);
+    lon[k] = x;
+    ll[k].y = x;
+}
+
+extern "C" int gzb_lon_to_pm180(gzb_ctx* ctx, double* lon_out_or_null) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_lon_to_pm180: null ctx");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const int64_t n = ctx->g.Nj * ctx->g.Ni;
+    k_lon_pm180<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_lon, ctx->d_ll);
+    GZB_LAUNCH_CHECK(ctx);
+    ctx->g.hdg = nullptr;
+    ctx->hdg_built = 0;
+    ctx->stats.heading_table = 0;
+    if (lon_out_or_null) {
+        GZB_CUDA(ctx, cudaMemcpyAsync(lon_out_or_null, ctx->d_lon, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (uint64_t)n * sizeof(double);
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GZB_OK;
+}
+
+// extent of the latitudes (ModGrid.domain_bounds): computed when the context was built
+extern "C" int gzb_lat_range(gzb_ctx* ctx, double* lat_min, double* lat_max) {
+    if (!ctx || !lat_min || !lat_max) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_lat_range: null argument");
+    *lat_min = ctx->lat_min;
+    *lat_max = ctx->lat_max;
+    return GZB_OK;
+}
+
 // ======================================================================== K0: grid angle
 // gonzag/utils.py:226-262.  One thread walks a column strip of GA_ROWS rows with a 3-row
 // sliding window, so each lat/lon value is loaded once per strip (plus a 2-row halo) and its
@@ -856,6 +960,19 @@ extern "C" int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes)
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_memset: null ctx");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
     GZB_CUDA(ctx, cudaMemsetAsync(dst_dev, byte, (size_t)bytes, ctx->stream));
+    return GZB_OK;
+}
+
+// 0: pageable host memory (or unknown), 1: pinned + mapped host memory, 2: device / managed memory
+extern "C" int gzb_pointer_kind(const void* p, int* kind_out) {
+    if (!kind_out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_pointer_kind: null output");
+    *kind_out = 0;
+    if (!p) return GZB_OK;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return GZB_OK; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) *kind_out = 2;
+    else if (at.type == cudaMemoryTypeHost && at.devicePointer) *kind_out = 1;
     return GZB_OK;
 }
 

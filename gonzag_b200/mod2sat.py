@@ -7,9 +7,22 @@ loops only over *slabs of model records*, never over track points.
 Where the model records and the satellite SSH come from, in order of preference:
   * ``MG.field``      (nrec, Nj, Ni) array in memory  /  ``MG.get_record(k)`` callable,
     ``ST.ssh``        (Nt,) array in memory;
+  * ``MG.source`` / ``ST.source``: the in-memory sources of `gonzag_b200.sources` (what
+    `gonzag_b200.ModGrid` / `SatTrack` were built from), whole array or one record at a time;
   * otherwise the reference's own readers ``GetModel2DVar`` / ``GetSatSSH`` from
     ``gonzag.ncio`` / ``gonzag.zarrio`` (gonzag/mod2sat.py:27-31) when that package is importable,
     which is the drop-in situation inside ``alongtrack_sat_vs_nemo.py``.
+
+Record index convention, kept from the reference: record ``k`` is the one whose time is
+``MG.time[k]`` *as the reader numbers it*, i.e. the reference asks its reader for ``kt = k`` with
+``k`` an index into the (possibly sliced) ``MG.time`` (gonzag/mod2sat.py:94-112).
+
+How the work is issued:
+  * a field held as ONE array that the GPU can read (pinned + mapped host memory: gathered in
+    place over PCIe; or small enough to be copied to HBM first) goes through `gzb_map_interp`:
+    K1-K4 in one call, the chain replays of K1 beside K2-K4;
+  * anything else (pageable big arrays, per-record providers) goes through `gzb_mapping` and then
+    `gzb_interp` slab by slab, records staged through pinned memory, copies overlapped with K4.
 """
 from __future__ import annotations
 
@@ -33,8 +46,8 @@ def _reference_readers():
             from gonzag.zarrio import GetModel2DVar, GetSatSSH
         return GetModel2DVar, GetSatSSH
     except Exception as exc:   # pragma: no cover - depends on the environment
-        raise RuntimeError("no in-memory field provider (MG.field / MG.get_record, ST.ssh) and the "
-                           "reference's I/O readers are not importable: %s" % exc)
+        raise RuntimeError("no in-memory field provider (MG.field / MG.get_record / MG.source, ST.ssh / ST.source) "
+                           "and the reference's I/O readers are not importable: %s" % exc)
 
 
 class MappingView:
@@ -69,20 +82,44 @@ def plan_slabs(t_sat, t_mod, max_records):
     return slabs
 
 
+def _providers(MG, name_ssh_mod):
+    """(whole field array or None, per-record callable or None) for the model variable."""
+    field = getattr(MG, "field", None)
+    get_record = getattr(MG, "get_record", None)
+    if field is None and get_record is None:
+        src = getattr(MG, "source", None)
+        if src is not None and hasattr(src, "field_array"):
+            field = src.field_array(name_ssh_mod)
+            if field is None:
+                get_record = lambda k: src.GetModel2DVar(name_ssh_mod, kt=k)
+        elif src is not None:
+            get_record = lambda k: src.GetModel2DVar(name_ssh_mod, kt=k)
+        else:
+            reader, _ = _reference_readers()
+            get_record = lambda k: reader(MG.file, name_ssh_mod, kt=k)
+    return field, get_record
+
+
 class Model2SatTrack:
 
     def __init__(self, MG, name_ssh_mod, ST, name_ssh_sat, device=0, ctx=None, keep_mapping=True,
-                 slab_bytes=256 << 20):
+                 slab_bytes=256 << 20, resident_bytes=2 << 30, mapping=None):
+        """Same four arguments as the reference.  Extras: ``ctx`` (a `GridContext` to reuse),
+        ``keep_mapping`` (copy NP / SM / WB back as ``self.BT``), ``mapping`` (an object with
+        ``NP, SM, WB`` of this very grid + track pair, e.g. ``previous.BT``: K1-K3 are skipped and
+        only the interpolation runs -- another model variable onto the same track)."""
         (Nj, Ni) = MG.shape
         d_found_km = config.rfactor * MG.HResDeg * config.deg2km                    # mod2sat.py:35
         np_box_radius = SearchBoxSize(MG.HResDeg * config.deg2km, config.search_box_w_km)  # :39
         Nt = ST.size
         lib = L.lib()
 
-        own_ctx = ctx is None
         tim = {}
         t0 = time.time()
         tc = time.perf_counter()
+        if ctx is None:
+            ctx = getattr(MG, "ctx", None)          # a gonzag_b200.ModGrid keeps its grid on the GPU
+        own_ctx = ctx is None
         if ctx is None:
             ang = MG.xangle if np.shape(getattr(MG, "xangle", ())) == (Nj, Ni) else None
             ctx = GridContext(MG.lat, MG.lon, angle=ang, mask=MG.mask, k_ew_per=MG.EWPer, device=device)
@@ -93,88 +130,133 @@ class Model2SatTrack:
         tim["context_s"] = time.perf_counter() - tc
         tc = time.perf_counter()
 
-        # ---- track to the device, once
+        # ---- one device allocation for the whole track, asynchronous uploads
         yt = L.as_f64(ST.lat)
         xt = L.as_f64(ST.lon)
         tt = L.as_f64(ST.time)
         tm = L.as_f64(MG.time)
-        d_y, d_x, d_t, d_tm = ctx.upload(yt), ctx.upload(xt), ctx.upload(tt), ctx.upload(tm)
-        d_np = ctx.dev_alloc(Nt * 16)
-        d_sm = ctx.dev_alloc(Nt * 64)
-        d_wb = ctx.dev_alloc(Nt * 32)
-        d_vnp = ctx.dev_alloc(Nt * 8)
-        d_vbl = ctx.dev_alloc(Nt * 8)
-        P = lambda b: C.c_void_p(b.ptr)
+        nrec = tm.shape[0]
+        al = lambda n: (int(n) + 255) & ~255
+        sizes = [("y", Nt * 8), ("x", Nt * 8), ("t", Nt * 8), ("tm", nrec * 8), ("np", Nt * 16), ("sm", Nt * 64),
+                 ("wb", Nt * 32), ("vnp", Nt * 8), ("vbl", Nt * 8), ("dist", Nt * 8)]
+        off, total = {}, 0
+        for k, n in sizes:
+            off[k] = total
+            total += al(max(n, 8))
+        d_all = ctx.dev_alloc(total)
+        P = lambda k: C.c_void_p(d_all.ptr + off[k])
+        for k, a in (("y", yt), ("x", xt), ("t", tt), ("tm", tm)):
+            if a.nbytes:
+                ck(lib.gzb_h2d(h, P(k), L.ptr(a), a.nbytes))
 
-        # ---- the mapping: K1 + K2 + K3                                          (mod2sat.py:49-50)
-        ck(lib.gzb_mapping(h, Nt, P(d_y), P(d_x), float(d_found_km), int(np_box_radius),
-                           int(np_box_radius), int(np_box_radius), P(d_np), P(d_sm), P(d_wb), L.GZB_DEVICE))
-        ctx.sync()
-        time_bl_mapping = time.time() - t0
-        tim["mapping_s"] = time.perf_counter() - tc
-        tc = time.perf_counter()
+        field, get_record = _providers(MG, name_ssh_mod)
+        rmiss = float(config.rmissval)
+        r = int(np_box_radius)
+        fused = False
+        d_field = None
+        if mapping is not None:
+            mNP, mSM, mWB = L.as_i64(mapping.NP), L.as_i64(mapping.SM), L.as_f64(mapping.WB)
+            if mNP.shape != (Nt, 2) or mSM.shape != (Nt, 4, 2) or mWB.shape != (Nt, 4):
+                raise ValueError("`mapping` does not belong to this track (Nt = %d)" % Nt)
+            for k, a in (("np", mNP), ("sm", mSM), ("wb", mWB)):
+                if a.nbytes:
+                    ck(lib.gzb_h2d(h, P(k), L.ptr(a), a.nbytes))
+        if field is not None and Nt > 0 and mapping is None:
+            field = np.ma.getdata(field)
+            if not field.flags["C_CONTIGUOUS"]:
+                field = np.ascontiguousarray(field)
+            dt = GridContext._field_dtype(field)
+            if field.shape[0] != nrec:
+                raise ValueError("MG.field holds %d records, MG.time %d" % (field.shape[0], nrec))
+            kind = L.pointer_kind(field)
+            sparse = Nt * 1024.0 < field.nbytes          # same rule as gzb_interp's zero-copy gather
+            if kind >= 1 and (kind == 2 or sparse):
+                slab_ptr = L.ptr(field)
+                fused = True
+            elif field.nbytes <= resident_bytes:
+                d_field = ctx.dev_alloc(field.nbytes)    # small field: copy it to HBM once
+                ck(lib.gzb_h2d(h, C.c_void_p(d_field.ptr), L.ptr(field), field.nbytes))
+                slab_ptr = C.c_void_p(d_field.ptr)
+                fused = True
 
-        # ---- space-time interpolation: K4 over slabs of records                 (mod2sat.py:86-139)
-        t0 = time.time()
-        field = getattr(MG, "field", None)
-        get_record = getattr(MG, "get_record", None)
-        if field is None and get_record is None:
-            reader, _ = _reference_readers()
-            get_record = lambda k: reader(MG.file, name_ssh_mod, kt=k)
-        first = True
-        if Nt > 0:
-            if field is not None:
-                field = np.ma.getdata(field)
-                if not field.flags["C_CONTIGUOUS"]:
-                    field = np.ascontiguousarray(field)
-                dt = GridContext._field_dtype(field)
-                rec_bytes = field[0].nbytes
-                for (ka, kb) in plan_slabs(tt, tm, max(2, int(1 << 40))):
-                    slab = field[ka:kb + 1]
-                    ck(lib.gzb_interp(h, Nt, P(d_t), P(d_sm), P(d_wb), tm.shape[0], P(d_tm), L.ptr(slab), dt,
-                                      ka, kb + 1 - ka, float(config.rmissval), 1 if first else 0,
-                                      P(d_vnp), P(d_vbl), L.GZB_DEVICE))
-                    first = False
-            else:
-                probe = np.ma.getdata(get_record(int(np.searchsorted(tm, tt[0], side="right") - 1)))
-                dt = GridContext._field_dtype(probe)
-                rec_bytes = probe.nbytes
-                per_slab = max(2, int(slab_bytes // rec_bytes))
-                stage = L.pinned_empty((per_slab,) + probe.shape, probe.dtype)
-                try:
-                    for (ka, kb) in plan_slabs(tt, tm, per_slab):
-                        for k in range(ka, kb + 1):
-                            stage[k - ka] = np.ma.getdata(get_record(k))
-                        ck(lib.gzb_interp(h, Nt, P(d_t), P(d_sm), P(d_wb), tm.shape[0], P(d_tm), L.ptr(stage), dt,
-                                          ka, kb + 1 - ka, float(config.rmissval), 1 if first else 0,
-                                          P(d_vnp), P(d_vbl), L.GZB_DEVICE))
+        if fused:
+            # ---- K1-K4 in one call                                              (mod2sat.py:49-139)
+            ck(lib.gzb_map_interp(h, Nt, P("y"), P("x"), P("t"), float(d_found_km), r, r, r, nrec, P("tm"), slab_ptr,
+                                  dt, 0, nrec, rmiss, P("np"), P("sm"), P("wb"), P("vnp"), P("vbl")))
+            ctx.sync()
+            tim["mapping_s"] = tim["interp_s"] = 0.5 * (time.perf_counter() - tc)
+            time_bl_mapping = time_bl_interp = time.time() - t0
+        else:
+            # ---- the mapping: K1 + K2 + K3                                      (mod2sat.py:49-50)
+            if Nt > 0 and mapping is None:
+                ck(lib.gzb_mapping(h, Nt, P("y"), P("x"), float(d_found_km), r, r, r, P("np"), P("sm"), P("wb"),
+                                   L.GZB_DEVICE))
+            ctx.sync()
+            time_bl_mapping = time.time() - t0
+            tim["mapping_s"] = time.perf_counter() - tc
+            tc = time.perf_counter()
+            # ---- space-time interpolation: K4 over slabs of records             (mod2sat.py:86-139)
+            t0 = time.time()
+            first = True
+            if Nt > 0:
+                if field is not None:
+                    field = np.ma.getdata(field)
+                    if not field.flags["C_CONTIGUOUS"]:
+                        field = np.ascontiguousarray(field)
+                    dt = GridContext._field_dtype(field)
+                    for (ka, kb) in plan_slabs(tt, tm, max(2, int(1 << 40))):
+                        slab = field[ka:kb + 1]
+                        ck(lib.gzb_interp(h, Nt, P("t"), P("sm"), P("wb"), nrec, P("tm"), L.ptr(slab), dt,
+                                          ka, kb + 1 - ka, rmiss, 1 if first else 0, P("vnp"), P("vbl"), L.GZB_DEVICE))
                         first = False
-                finally:
-                    L.pinned_free(stage)
-        if first and Nt > 0:   # no slab at all cannot happen (plan_slabs raises), kept for safety
-            raise RuntimeError("no model record brackets the track")
-
-        ctx.sync()
-        tim["interp_s"] = time.perf_counter() - tc
+                else:
+                    probe = np.ma.getdata(get_record(int(np.searchsorted(tm, tt[0], side="right") - 1)))
+                    dt = GridContext._field_dtype(probe)
+                    per_slab = max(2, int(slab_bytes // probe.nbytes))
+                    stage = L.pinned_empty((per_slab,) + probe.shape, probe.dtype)
+                    try:
+                        for (ka, kb) in plan_slabs(tt, tm, per_slab):
+                            for k in range(ka, kb + 1):
+                                stage[k - ka] = np.ma.getdata(get_record(k))
+                            ck(lib.gzb_interp(h, Nt, P("t"), P("sm"), P("wb"), nrec, P("tm"), L.ptr(stage), dt,
+                                              ka, kb + 1 - ka, rmiss, 1 if first else 0, P("vnp"), P("vbl"),
+                                              L.GZB_DEVICE))
+                            first = False
+                    finally:
+                        L.pinned_free(stage)
+            ctx.sync()
+            tim["interp_s"] = time.perf_counter() - tc
+            time_bl_interp = time.time() - t0
         tc = time.perf_counter()
+
         # ---- distance and nearest-point map                                      (mod2sat.py:146-148, 177-184)
-        d_dist = ctx.dev_alloc(Nt * 8)
-        ck(lib.gzb_track_distance(h, Nt, P(d_y), P(d_x), P(d_dist), L.GZB_DEVICE))
+        vssh_m_np = np.empty(Nt)
+        vssh_m_bl = np.empty(Nt)
+        vdistance = np.empty(Nt)
         xnp = None
+        if Nt > 0:
+            ck(lib.gzb_track_distance(h, Nt, P("y"), P("x"), P("dist"), L.GZB_DEVICE))
+            ck(lib.gzb_d2h(h, L.ptr(vssh_m_np), P("vnp"), Nt * 8))
+            ck(lib.gzb_d2h(h, L.ptr(vssh_m_bl), P("vbl"), Nt * 8))
+            ck(lib.gzb_d2h(h, L.ptr(vdistance), P("dist"), Nt * 8))
         if config.l_save_track_on_model_grid:
             d_xnp = ctx.dev_alloc(Nj * Ni * 8)
-            ck(lib.gzb_xnp_track(h, Nt, P(d_np), float(config.rmissval), P(d_xnp), L.GZB_DEVICE))
-            xnp = ctx.download(d_xnp, (Nj, Ni), np.float64)
-            d_xnp.free()
-        vssh_m_np = ctx.download(d_vnp, (Nt,), np.float64)
-        vssh_m_bl = ctx.download(d_vbl, (Nt,), np.float64)
-        vdistance = ctx.download(d_dist, (Nt,), np.float64)
-        time_bl_interp = time.time() - t0
+            ck(lib.gzb_xnp_track(h, Nt, P("np"), rmiss, C.c_void_p(d_xnp.ptr), L.GZB_DEVICE))
+            xnp = np.empty((Nj, Ni))
+            ck(lib.gzb_d2h(h, L.ptr(xnp), C.c_void_p(d_xnp.ptr), xnp.nbytes))
         if keep_mapping:
-            self.BT = MappingView(ctx.download(d_np, (Nt, 2), np.int64), ctx.download(d_sm, (Nt, 4, 2), np.int64),
-                                  ctx.download(d_wb, (Nt, 4), np.float64))
-        for b in (d_y, d_x, d_t, d_tm, d_np, d_sm, d_wb, d_vnp, d_vbl, d_dist):
-            b.free()
+            NP, SM, WB = np.empty((Nt, 2), np.int64), np.empty((Nt, 4, 2), np.int64), np.empty((Nt, 4))
+            if Nt > 0:
+                ck(lib.gzb_d2h(h, L.ptr(NP), P("np"), NP.nbytes))
+                ck(lib.gzb_d2h(h, L.ptr(SM), P("sm"), SM.nbytes))
+                ck(lib.gzb_d2h(h, L.ptr(WB), P("wb"), WB.nbytes))
+            self.BT = MappingView(NP, SM, WB)
+        ctx.sync()
+        d_all.free()
+        if d_field is not None:
+            d_field.free()
+        if config.l_save_track_on_model_grid:
+            d_xnp.free()
         tim["outputs_s"] = time.perf_counter() - tc
         tc = time.perf_counter()
 
@@ -182,6 +264,8 @@ class Model2SatTrack:
         ssh_attr = getattr(ST, "ssh", None)
         if ssh_attr is not None:
             vssh_s = np.array(ssh_attr, dtype=np.float64, copy=True)
+        elif getattr(ST, "source", None) is not None:
+            vssh_s = ST.source.GetSatSSH(name_ssh_sat, kt1=ST.jt1, kt2=ST.jt2, ikeep=ST.keepit)
         else:
             _, sat_reader = _reference_readers()
             vssh_s = sat_reader(ST.file, name_ssh_sat, kt1=ST.jt1, kt2=ST.jt2, ikeep=ST.keepit)
@@ -199,6 +283,7 @@ class Model2SatTrack:
             self.XNPtrack = np.ma.MaskedArray(xnp, mask=(xnp == config.rmissval), copy=False)
         tim["packaging_s"] = time.perf_counter() - tc
         self.timing = tim
+        self.fused_path = fused
         self.time_bl_mapping = time_bl_mapping
         self.time_bl_interp = time_bl_interp
         self.stats = ctx.stats()

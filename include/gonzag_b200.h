@@ -94,6 +94,19 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * 2 = also skip the light test (Iquadran's lforceHD, gonzag/bilin_mapping.py:375). */
 int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value);
 
+/* ---- grid heuristics of ModGrid -------------------------------------------
+ * gzb_lon_stats: the reductions IsGlobalLongitudeWise() needs (gonzag/utils.py:149-182), on the
+ * context's longitudes: vals4 = { min X, max X, min XB, max XB } with X = lon % 360 and
+ * XB = degE_to_degWE(X); cols2 = { argmin(X) % ni, argmax(X) % ni } (first occurrences, like
+ * numpy).  Host outputs; synchronous.
+ * gzb_lon_to_pm180: rewrites the context's longitudes as degE_to_degWE(lon) (what ModGrid does
+ * for a regional domain handled in the [-180,180] frame, gonzag/utils.py:441) and optionally
+ * copies them to the host array lon_out.
+ * gzb_lat_range: min / max of the context's latitudes (ModGrid.domain_bounds, :420-421). */
+int gzb_lon_stats(gzb_ctx* ctx, double* vals4, int64_t* cols2);
+int gzb_lon_to_pm180(gzb_ctx* ctx, double* lon_out_or_null);
+int gzb_lat_range(gzb_ctx* ctx, double* lat_min, double* lat_max);
+
 /* ---- K0: local grid rotation, the `-D` pre-pass --------------------------------------------
  * Replaces GridAngle(xlat, xlon) (gonzag/utils.py:226-262).  Computes the (nj,ni) angle in
  * degrees from the context's lat/lon, installs it as the context's angle and, when
@@ -192,6 +205,9 @@ int gzb_dev_free(gzb_ctx* ctx, void* dptr);
 int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);   /* async */
 int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);   /* async */
 int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes);            /* async */
+/* Where does `p` live?  kind_out: 0 pageable host memory (or unknown), 1 pinned + mapped host
+ * memory (the GPU can read it in place), 2 device / managed memory. */
+int gzb_pointer_kind(const void* p, int* kind_out);
 int gzb_host_alloc(uint64_t bytes, void** hptr_out);     /* pinned, portable, mapped */
 int gzb_host_free(void* hptr);
 int gzb_host_register(void* hptr, uint64_t bytes);

@@ -66,8 +66,30 @@ def load_reference(ref_root):
     import gonzag  # noqa
     store = {"fields": {}, "sat": {}}
     nc = types.ModuleType("gonzag.ncio")
-    nc.GetModel2DVar = lambda f, v, kt=0: store["fields"][f][kt].copy()   # a file read returns a fresh array
-    nc.GetSatSSH = lambda f, v, kt1=0, kt2=0, ikeep=[]: store["sat"][f]
+    def _rd(fn):
+        # files registered as in-memory sources (case_grid) answer through them; the two legacy
+        # stand-ins below serve the SimpleNamespace cases
+        def call(f, *a, **k):
+            return getattr(store["src"][f], fn)(*a, **k)
+        return call
+
+    def get2d(f, v, kt=0):
+        if f in store.get("src", {}):
+            return np.array(store["src"][f].GetModel2DVar(v, kt=kt), copy=True)
+        return store["fields"][f][kt].copy()   # a file read returns a fresh array
+
+    def getsat(f, v, kt1=0, kt2=0, ikeep=[]):
+        if f in store.get("src", {}):
+            return store["src"][f].GetSatSSH(v, kt1=kt1, kt2=kt2, ikeep=ikeep)
+        return store["sat"][f]
+
+    nc.GetModel2DVar = get2d
+    nc.GetSatSSH = getsat
+    for fn in ("GetTimeEpochVector", "GetTimeInfo", "GetModelCoor", "GetModelLSM", "GetSatCoor"):
+        setattr(nc, fn, _rd(fn))
+    nc.Save2Dfield = lambda *a, **k: None
+    nc.SaveTimeSeries = lambda *a, **k: 0
+    store["src"] = {}
     sys.modules["gonzag.ncio"] = nc
     gonzag.ncio = nc
     return gonzag, store
@@ -292,11 +314,128 @@ def case_units(gz, store):
     return out
 
 
+def case_grid(gz, store):
+    """f1 rows: the grid heuristics on the reference's own test arrays (tests/test_functions.py) and
+    the UNMODIFIED `ModGrid` -> `SatTrack` -> `Model2SatTrack` sequence of alongtrack_sat_vs_nemo.py
+    on three in-memory data sets (global periodic with -D; regional across Greenwich, 2-D coordinates;
+    regional with 1-D coordinates and a mask from _FillValue)."""
+    import tempfile
+    from gonzag_b200.sources import ModelArrays, TrackArrays
+    out = {}
+    # ---- known-answer arrays of the reference's tests/test_functions.py
+    kat = [np.array([[0., 60., 120., 180., 240., 300.]] * 3),
+           np.array([[0., 60., 120., 180., 240., 300., 360.]] * 3),
+           np.array([[0., 60., 120., 180., 240., 300., 360., 60.]] * 3),
+           np.array([[0.5, 180., 359.5], [0.5, 180., 359.5]]),
+           np.array([[340., 358., 5.], [341., 359., 6.]]),
+           np.array([[170., 178., 201.], [169., 181., 200.]]),
+           np.array([[299., 324., 350.], [300., 325., 352.]]),
+           np.array([[30., 40., 60.], [29., 39., 59.]])]
+    for k, x in enumerate(kat):
+        out["kat%d_lon" % k] = x
+        res = float(gz.GridResolution(x)) if k < 3 else 1.0
+        g = gz.IsGlobalLongitudeWise(x, resd=res)
+        ew = gz.IsEastWestPeriodic(x) if k < 3 else -99     # the reference indexes 5 columns: 3-column arrays raise
+        out["kat%d_out" % k] = np.array([res, float(g[0]), float(g[1]), g[2], g[3], ew])
+    # ---- scan_idx
+    rng = np.random.default_rng(31)
+    vt = np.cumsum(rng.uniform(0.5, 1.5, 4000)) + 1000.0
+    qs = np.array([[vt[0], vt[-1]], [vt[10] + 0.2, vt[3000] + 0.1], [vt[1], vt[2]], [0.0, vt[50]],
+                   [vt[100], 1e9], [vt[3999] - 0.01, vt[3999]], [vt[7], vt[7]], [-5.0, -1.0]])
+    out["scan_vt"] = vt
+    out["scan_q"] = qs
+    out["scan_out"] = np.array([gz.scan_idx(vt, a, b) for a, b in qs], dtype=np.int64)
+    # ---- the three end-to-end data sets
+    tmp = tempfile.mkdtemp(prefix="gzgold")
+
+    def touch(name):
+        path = os.path.join(tmp, name)
+        open(path, "w").close()
+        return path
+
+    def run(tag, model, track, varlsm, lsm_model, distorded, Np):
+        fm, fs = touch(tag + "_mod.nc"), touch(tag + "_sat.nc")
+        fl = fm if lsm_model is None else touch(tag + "_lsm.nc")
+        store["src"][fm] = model
+        store["src"][fs] = track
+        if lsm_model is not None:
+            store["src"][fl] = lsm_model
+        with quiet():
+            (it1, it2), (Nts, Ntm) = gz.GetEpochTimeOverlap(fs, fm)
+            MG = gz.ModGrid(fm, it1, it2, fl, varlsm, distorded_grid=distorded)
+            ST = gz.SatTrack(fs, it1, it2, Np=Np, domain_bounds=MG.domain_bounds, l_0_360=MG.l360)
+            R = gz.Model2SatTrack(MG, "ssh", ST, "ssh")
+        o = {"it": np.array([it1, it2]), "nts_ntm": np.array([Nts, Ntm]),
+             "mg_time": MG.time, "mg_size": MG.size, "mg_lat": MG.lat, "mg_lon": MG.lon, "mg_mask": MG.mask,
+             "mg_scal": np.array([MG.HResDeg, MG.HResKM, float(MG.IsLonGlobal), float(MG.l360), MG.EWPer]),
+             "mg_bounds": np.array(MG.domain_bounds), "mg_xangle": MG.xangle,
+             "st_time": ST.time, "st_lat": ST.lat, "st_lon": ST.lon, "st_j": np.array([ST.jt1, ST.jt2, ST.size]),
+             "st_keepit": ST.keepit[0], "r_mask": R.mask, "r_dist": R.distance}
+        for nm in ("ssh_mod_np", "ssh_mod", "ssh_sat", "XNPtrack"):
+            pack_masked("r_" + nm, getattr(R, nm), o)
+        for k, v in o.items():
+            out[tag + "_" + k] = v
+
+    # (a) global periodic, -D, mask in a separate "file"; long track file (two-pass time scan)
+    lat, lon = syn.orca_like_grid(146, 182, pole_lon_deg=0.0)      # cap bent along the first meridian: column 0 keeps lon 0
+    # overlap columns at the END (cols ni-2, ni-1 repeat cols 0, 1), the layout of the reference's own
+    # periodic test array: the longitude heuristics then say "global, 2 overlapping points"
+    lat = np.ascontiguousarray(np.concatenate([lat[:, 1:-1], lat[:, 1:3]], axis=1))
+    lon = np.ascontiguousarray(np.concatenate([lon[:, 1:-1], lon[:, 1:3]], axis=1))
+    mask = syn.land_mask(lat, lon)
+    tm = 1.0e9 + 7000.0 * np.arange(6)
+    f32 = syn.ssh_records(lat, lon, 6, dtype=np.float32)
+    # (the reference needs the track window strictly inside the model records: its bracket search
+    # runs off the end of MG.time otherwise, gonzag/mod2sat.py:95)
+    t, y, x = syn.orbit_track(30000, t0=1000.0, **syn.SARAL)
+    t = t + 1.0e9
+    ssat = sat_ssh(len(t), 13)
+    out.update(a_lat=lat.astype(np.float32), a_lon=lon.astype(np.float32), a_maskin=mask.astype(np.int8), a_tm=tm,
+               a_f32=f32, a_t=t, a_y=y, a_x=x, a_ssat=ssat)
+    run("a", ModelArrays(tm, lat.astype(np.float32).astype(np.float64), lon.astype(np.float32).astype(np.float64),
+                         fields={"ssh": f32}),
+        TrackArrays(t, y, x, {"ssh": ssat}), "tmask",
+        ModelArrays(tm, None, None, masks={"tmask": mask}), True, len(t))
+    # (b) regional across Greenwich (2-D coordinates in [-180,180] input frame), no -D
+    latb, lonb = syn.regional_grid(120, 160, lat0=30.0, lon0=352.0, res_deg=0.1, shear=0.05)
+    lonb_in = np.where(lonb > 180.0, lonb - 360.0, lonb)
+    maskb = syn.land_mask(latb, lonb, seed=6, level=0.95)
+    tmb = 2.0e9 + 3600.0 * np.arange(5)
+    fb = syn.ssh_records(latb, lonb, 5, dtype=np.float64)
+    tb, yb, xb = syn.orbit_track(43200, t0=0.0, drop_land_seed=None, **syn.SARAL)
+    tb = tb * (3.5 * 3600.0 / 43200.0) + 2.0e9 + 300.0     # squeeze a day of passes into the record span
+    xb_in = np.where(xb > 180.0, xb - 360.0, xb)
+    ssb = sat_ssh(len(tb), 14)
+    out.update(b_lat=latb, b_lon=lonb_in, b_maskin=maskb.astype(np.int8), b_tm=tmb, b_f64=fb, b_t=tb, b_y=yb,
+               b_x=xb_in, b_ssat=ssb)
+    run("b", ModelArrays(tmb, latb, lonb_in, fields={"ssh": fb}, masks={"tmask": maskb}),
+        TrackArrays(tb, yb, xb_in, {"ssh": ssb}), "tmask", None, False, 100)
+    # (c) regular regional grid given by 1-D coordinates, mask from _FillValue of the field
+    lat1 = np.linspace(-30.0, -10.0, 81)
+    lon1 = np.linspace(100.0, 130.0, 121)
+    lon2, lat2 = np.meshgrid(lon1, lat1)
+    maskc = syn.land_mask(lat2, lon2, seed=7, level=0.9)
+    tmc = 3.0e9 + 1800.0 * np.arange(7)
+    fc = syn.ssh_records(lat2, lon2, 7, dtype=np.float32)
+    fcm = np.ma.masked_array(fc, mask=np.broadcast_to(maskc == 0, fc.shape))
+    tc_, yc, xc = syn.orbit_track(43200, t0=0.0, drop_land_seed=None, **syn.JASON)
+    tc_ = tc_ * (2.8 * 3600.0 / 43200.0) + 3.0e9 + 30.0
+    ssc = sat_ssh(len(tc_), 15)
+    out.update(c_lat1=lat1, c_lon1=lon1, c_maskin=maskc.astype(np.int8), c_tm=tmc, c_f32=fc, c_t=tc_, c_y=yc, c_x=xc,
+               c_ssat=ssc)
+    run("c", ModelArrays(tmc, lat1, lon1, fields={"ssh": fcm}),
+        TrackArrays(tc_, yc, xc, {"ssh": ssc}), "_FillValue@ssh", None, False, len(tc_))
+    return out
+
+
 def main():
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     gz, store = load_reference(ref_root)
+    only = sys.argv[2:] if len(sys.argv) > 2 else None
     for name, fn in (("units", case_units), ("global", case_global), ("regional", case_regional),
-                     ("seam", case_seam)):
+                     ("seam", case_seam), ("grid", case_grid)):
+        if only and name not in only:
+            continue
         data = fn(gz, store)
         path = os.path.join(HERE, "golden_%s.npz" % name)
         np.savez_compressed(path, **data)
