@@ -247,7 +247,7 @@ def run_ours(args, w):
     import torch.distributed as dist
     import gonzag_b200 as gzb
     from gonzag_b200 import _lib as L
-    from gonzag_b200.multi import CudaEngine, ShardedMapper, segment_bounds
+    from gonzag_b200.multi import CudaEngine, ShardedMapper, P2PShardedMapper, segment_bounds
     import types
 
     os.environ["NCCL_DEBUG"] = os.environ.get("GZB_NCCL_DEBUG", "WARN")   # NCCL logs go to stdout: keep it to the JSON line
@@ -279,7 +279,8 @@ def run_ours(args, w):
     ctx = gzb.GridContext(lat, lon, mask=mask, k_ew_per=2, device=local)
     ctx.set_option("heading_table", args.heading_table)
     eng = CudaEngine(ctx, torch)
-    mapper = ShardedMapper(eng, dist if world > 1 else None, torch)
+    Mapper = P2PShardedMapper if (world > 1 and args.gather == "p2p") else ShardedMapper
+    mapper = Mapper(eng, dist if world > 1 else None, torch)
     torch.cuda.synchronize()
 
     # K0 (-D): part of the grid set-up (ModGrid in the reference), timed on its own
@@ -315,14 +316,16 @@ def run_ours(args, w):
 
     state = {}
 
-    def step():
+    def step(check_now=False):
         # K1 + K2 + K3 + K4 in one call (gzb_map_interp), on [halo point +] this rank's points
         mapper.path_speculative(y_h, x_h, t_h, rd, r, tmod_d, slab, k_lo)
         g = mapper.gather()
-        if not mapper.boundaries_ok(g):           # rare: a chain deviation straddles a segment boundary
+        # segment boundaries: compared on the device from the gathered buffer (every rank's halo
+        # assumption travels with its products); the host reads the verdict once per batch of steps
+        mapper.check_boundaries_async(g)
+        if check_now and not mapper.boundaries_verdict():      # rare: a chain deviation straddles a boundary
             if mapper.reseed(g, y_d, x_d, rd, r):
-                eng.mesh_weights(y_d, x_d, mapper.NP, mapper.SM, mapper.WB)
-                eng.interp(t_d, mapper.SM, mapper.WB, tmod_d, slab, k_lo, v_np, v_bl)
+                mapper.redo_own_points(y_d, x_d, t_d, tmod_d, slab, k_lo)
             g = mapper.gather()
         state["out"] = g
 
@@ -332,20 +335,41 @@ def run_ours(args, w):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        step(check_now=True)
     barrier()
     verified = None
     if args.verify:
-        # rank 0 maps + interpolates the WHOLE track alone and compares with the gathered shards
+        # rank 0 maps the WHOLE track alone and compares with the shards; the series every rank holds
+        # after the step are compared with a plain NCCL all-gather of the ranks' local series
         g_np, g_bl, g_NP = mapper.unpack(state["out"])
+
+        def nccl_gather(local, width):
+            if world == 1:
+                return local
+            pad = torch.zeros((mapper.nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
+            pad[:local.shape[0]] = local
+            lst = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(lst, pad)
+            return torch.cat([lst[g][:bounds[g + 1] - bounds[g]] for g in range(world)])
+
+        ref_np, ref_bl = nccl_gather(mapper.v_np, 1), nccl_gather(mapper.v_bl, 1)
+        if g_NP is None:
+            g_NP = nccl_gather(mapper.NP, 2)
+        ok_series = bool((ref_np.view(torch.int64) == g_np.view(torch.int64)).all()
+                         and (ref_bl.view(torch.int64) == g_bl.view(torch.int64)).all())
+        oks = torch.tensor([1 if ok_series else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+        ok_series = bool(oks.item())
         if rank == 0:
             with gzb.GridContext(lat, lon, mask=mask, k_ew_per=2, device=local) as c2:
                 c2.grid_angle(out=False)
                 NPf, SMf, WBf = c2.mapping(yy, xx, rd, r)
             ok_np = bool((torch.as_tensor(NPf, device=dev) == g_NP).all())
-            verified = {"NP_bit_exact": ok_np, "points": int(len(yy))}
-            log("[verify] sharded NP == single-GPU NP over %d points: %s" % (len(yy), ok_np))
-            if not ok_np:
+            verified = {"NP_bit_exact": ok_np, "series_on_every_rank_bit_exact": ok_series, "points": int(len(yy))}
+            log("[verify] sharded NP == single-GPU NP over %d points: %s; gathered series identical on every rank: %s"
+                % (len(yy), ok_np, ok_series))
+            if not (ok_np and ok_series):
                 raise SystemExit("sharded result differs from the single-GPU result")
         barrier()
     launches0 = ctx.stats()["kernel_launches"]
@@ -364,7 +388,11 @@ def run_ours(args, w):
         torch.cuda.synchronize()
         step_ms.append(e0.elapsed_time(e1))
     barrier()
+    if not mapper.boundaries_verdict():
+        raise SystemExit("a timed step needed a re-seed across a segment boundary: its result was not final")
     launches = ctx.stats()["kernel_launches"] - launches0
+    if hasattr(mapper, "detach"):
+        mapper.detach()                    # the per-stage timings below are local: no stores into the peers
     total_ms = float(np.sum(step_ms))
     if world > 1:
         tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -516,7 +544,11 @@ def run_ours(args, w):
                            "track_points_total": nt_total, "track_points_per_gpu": nt_local,
                            "records_per_gpu": int(k_hi - k_lo + 1), "field_dtype": "f32",
                            "np_box_r": r, "rd_found_km": rd, "k_ew_per": 2,
-                           "sharding": "contiguous time segments, grid replicated, 1 all-gather of (ssh_np, ssh_bl, NP)",
+                           "sharding": ("contiguous time segments, grid replicated; " + (
+                               "K4 stores the two series into every rank's buffer over NVLink (CUDA IPC peer memory), a one-word "
+                               "all-reduce orders the ranks" if isinstance(mapper, P2PShardedMapper) else
+                               "1 all-gather of (ssh_np, ssh_bl, NP)") + "; segment-boundary check on the device, verdict read "
+                               "once after the timed steps"),
                            "l2": "flushed (256 MiB write) before every timed step and stage",
                            "heading_table": ("K2 reads a per-cell table of the grid-only headings (48 B/cell), built once per grid "
                                              "like the -D angle" if ctx.stats()["heading_table"] else "off"),
@@ -525,6 +557,8 @@ def run_ours(args, w):
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "kernels": kern,
                 "cpu_baseline": cpu, "e2e": e2e}
         emit(line)
+    if hasattr(mapper, "close"):
+        mapper.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -539,6 +573,9 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--heading-table", type=int, default=2, choices=[0, 1, 2],
                     help="K2 per-cell heading table: 0 never, 1 auto (amortised), 2 built at grid set-up (default)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: p2p = K4 stores its results into every rank's buffer over NVLink (one-word all-reduce "
+                         "as the barrier); nccl = all-gather of the packed products after K4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check the sharded result against a single-GPU run")

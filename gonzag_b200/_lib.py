@@ -74,6 +74,11 @@ _SIGNATURES = {
     "gzb_h2d": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gzb_d2h": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gzb_memset": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
+    "gzb_ipc_export": (C.c_int, [_P, _P, _P]),
+    "gzb_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "gzb_ipc_close": (C.c_int, [_P, _P]),
+    "gzb_set_peer_outputs": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
+    "gzb_publish_edges": (C.c_int, [_P, _P, _I64, C.c_int, _P]),
     "gzb_pointer_kind": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "gzb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "gzb_host_free": (C.c_int, [_P]),

@@ -69,6 +69,14 @@ struct GzbArena {
     size_t off = 0;
 };
 
+// remote output copies of K4 (see gzb_point.cuh); declared here because the context stores one
+#define GZB_MAX_PEERS 15
+struct GzbPeerOut {
+    int n;
+    double* np[GZB_MAX_PEERS];
+    double* bl[GZB_MAX_PEERS];
+};
+
 struct gzb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -76,6 +84,9 @@ struct gzb_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;     // chain part of K1 while K2+K3 run on `stream` (gzb_mapping)
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};
+    GzbPeerOut peer_out = {0, {}, {}};   // gzb_set_peer_outputs: where K4 also writes its two series
+    double* peer_local_np = nullptr;     // ... when its local outputs are these buffers
+    double* peer_local_bl = nullptr;
     int overlap = 1;                 // gzb_mapping: 1 run the chain replays beside K2+K3, 0 strictly in sequence
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     GzbGrid g;

@@ -843,6 +843,78 @@ extern "C" int gzb_lat_range(gzb_ctx* ctx, double* lat_min, double* lat_max) {
     return GZB_OK;
 }
 
+// ======================================================================== peer (NVLink) outputs
+// One process per GPU: a rank exports its product buffer with CUDA IPC, the other ranks map it and
+// hand the mapped addresses to gzb_set_peer_outputs; K4 then stores its two series into every
+// peer's buffer as it computes them (gzb_point.cuh), which replaces the all-gather that would
+// otherwise follow it.
+extern "C" int gzb_ipc_export(gzb_ctx* ctx, void* dptr, unsigned char* handle64) {
+    if (!ctx || !dptr || !handle64) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_ipc_export: null argument");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GZB_CUDA(ctx, cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle64, &h, 64);
+    return GZB_OK;
+}
+
+extern "C" int gzb_ipc_open(gzb_ctx* ctx, const unsigned char* handle64, void** dptr_out) {
+    if (!ctx || !handle64 || !dptr_out) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_ipc_open: null argument");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    *dptr_out = nullptr;
+    GZB_CUDA(ctx, cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return GZB_OK;
+}
+
+extern "C" int gzb_ipc_close(gzb_ctx* ctx, void* dptr) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_ipc_close: null ctx");
+    if (!dptr) return GZB_OK;
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GZB_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
+    return GZB_OK;
+}
+
+extern "C" int gzb_set_peer_outputs(gzb_ctx* ctx, int n, void* const* vnp_peers, void* const* vbl_peers,
+                                    void* vnp_local, void* vbl_local) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_set_peer_outputs: null ctx");
+    if (n < 0 || n > GZB_MAX_PEERS) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_peer_outputs: 0 <= n <= %d", GZB_MAX_PEERS);
+    if (n > 0 && (!vnp_peers || !vbl_peers || !vnp_local || !vbl_local))
+        return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_peer_outputs: null pointer");
+    ctx->peer_out.n = n;
+    for (int k = 0; k < n; ++k) {
+        ctx->peer_out.np[k] = (double*)vnp_peers[k];
+        ctx->peer_out.bl[k] = (double*)vbl_peers[k];
+    }
+    ctx->peer_local_np = (double*)vnp_local;
+    ctx->peer_local_bl = (double*)vbl_local;
+    return GZB_OK;
+}
+
+// first and last row of an (nrows, 2) int64 array (the halo assumption and the last nearest point of
+// a segment) to n destinations of 4 int64 each: what the ranks compare at the segment boundaries
+struct GzbEdgeDst { long long* p[GZB_MAX_PEERS + 1]; };
+__global__ void k_publish_edges(const long long* __restrict__ rows, const long long nrows, const int n, const GzbEdgeDst d) {
+    const int k = threadIdx.x >> 2, w = threadIdx.x & 3;
+    if (k >= n) return;
+    const long long v = (w < 2) ? rows[w] : rows[2 * (nrows - 1) + (w - 2)];
+    d.p[k][w] = v;
+}
+
+extern "C" int gzb_publish_edges(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int n, void* const* dst) {
+    if (!ctx || !np_rows || nrows < 1 || n < 0 || n > GZB_MAX_PEERS + 1 || (n > 0 && !dst))
+        return gzb_fail(ctx, GZB_ERR_ARG, "gzb_publish_edges: bad arguments");
+    if (n == 0) return GZB_OK;
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GzbEdgeDst d;
+    for (int k = 0; k < n; ++k) d.p[k] = (long long*)dst[k];
+    k_publish_edges<<<1, 4 * (GZB_MAX_PEERS + 1), 0, ctx->stream>>>((const long long*)np_rows, nrows, n, d);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
+}
+
 // ======================================================================== K0: grid angle
 // gonzag/utils.py:226-262.  One thread walks a column strip of GA_ROWS rows with a 3-row
 // sliding window, so each lat/lon value is loaded once per strip (plus a 2-row halo) and its

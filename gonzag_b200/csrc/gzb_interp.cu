@@ -42,16 +42,16 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
          const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
          const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
          int* __restrict__ err, const unsigned* __restrict__ mbits, const int* __restrict__ mflag,
-         const long long* __restrict__ list, const unsigned long long* __restrict__ count) {
+         const long long* __restrict__ list, const unsigned long long* __restrict__ count, const GzbPeerOut peers) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (list) {
         const long long n = (long long)*count;
         for (long long e = gt; e < n; e += (long long)gridDim.x * blockDim.x)
             interp_point<T, EARLY>(g, list[e], t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl, err,
-                                   mbits, mflag);
+                                   mbits, mflag, peers);
     } else if (gt < nt) {
         interp_point<T, EARLY>(g, gt, t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl, err, mbits,
-                               mflag);
+                               mflag, peers);
     }
 }
 
@@ -78,12 +78,16 @@ static int launch_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_
                          const long long* list = nullptr, const unsigned long long* count = nullptr) {
     const unsigned nblk = list ? 32u : (unsigned)((nt + 255) / 256);
     const unsigned* mb = ctx->mask_bits_ok ? ctx->d_mbits : nullptr;
+    // remote copies only for the buffers they were registered for (gzb_set_peer_outputs)
+    GzbPeerOut po;
+    po.n = 0;
+    if (ctx->peer_out.n > 0 && np_out == ctx->peer_local_np && bl_out == ctx->peer_local_bl && init) po = ctx->peer_out;
     if (ctx->k4_early)
         k_interp<T, true><<<nblk, 256, 0, ctx->stream>>>(ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab,
-                                                         k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count);
+                                                         k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count, po);
     else
         k_interp<T, false><<<nblk, 256, 0, ctx->stream>>>(ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, (const T*)slab,
-                                                          k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count);
+                                                          k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count, po);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }

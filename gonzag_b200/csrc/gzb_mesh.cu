@@ -291,6 +291,7 @@ struct InterpArgs {            // K4 arguments of the fused path; slab == nullpt
     int* err;
     const unsigned* mbits;
     const int* mflag;
+    GzbPeerOut peers;
 };
 
 __global__ void __launch_bounds__(64)
@@ -320,10 +321,10 @@ k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restr
         if (ia.slab) {      // K4 straight from the registers: the arrays just written are not read back
             if (ia.dtype == GZB_F32)
                 interp_point<float, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const float*)ia.slab, ia.k0,
-                                                 ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, rp, rw);
+                                                 ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
             else
                 interp_point<double, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const double*)ia.slab, ia.k0,
-                                                  ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, rp, rw);
+                                                  ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
         }
     }
 }
@@ -338,6 +339,8 @@ int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int
     ia.rmiss = rmiss; ia.out_np = vnp_out; ia.out_bl = vbl_out; ia.err = ctx->d_flags;
     ia.mbits = ctx->mask_bits_ok ? ctx->d_mbits : nullptr;
     ia.mflag = ctx->d_flags + 2;
+    ia.peers.n = 0;
+    if (ctx->peer_out.n > 0 && vnp_out == ctx->peer_local_np && vbl_out == ctx->peer_local_bl) ia.peers = ctx->peer_out;
     k_path_fix<<<128, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
                                            ctx->force_heavy, ia);
     GZB_LAUNCH_CHECK(ctx);

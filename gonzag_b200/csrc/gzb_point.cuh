@@ -22,6 +22,11 @@ __device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const
 // Loads are issued as early as their addresses are known (mesh and weights before the bracket
 // search, the eight field values together with the mask) so that a point costs two dependent
 // DRAM round trips, not four.
+// Remote copies of the two output series: the other GPUs' product buffers, mapped through CUDA
+// IPC, receive the values straight from the kernel (stores over NVLink, one per point and peer)
+// instead of through a collective afterwards.  n == 0: local outputs only.
+// (struct GzbPeerOut: gzb_common.cuh)
+
 // REG: the mesh and weights come in registers (rp[4], rw[2]) instead of SM / WB.
 template <typename T, bool EARLY, bool REG = false>
 __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t, const double* __restrict__ t_sat,
@@ -29,7 +34,7 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
          const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
          const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
          int* __restrict__ err, const unsigned* __restrict__ mbits, const int* __restrict__ mflag,
-         const longlong2* rp = nullptr, const double2* rw = nullptr) {
+         const GzbPeerOut& peers, const longlong2* rp = nullptr, const double2* rw = nullptr) {
     const double now = __ldg(t_sat + t);
     const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
     const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
@@ -42,61 +47,72 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
         p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
         wa = wb[0]; wc = wb[1];
     }
-    if (init) {
-        out_np[t] = rmiss;
-        out_bl[t] = rmiss;
+    // the two results and whether this call produced them (init: they start as the missing value)
+    double r_np = rmiss, r_bl = rmiss;
+    bool w_np = init != 0, w_bl = init != 0;
+    do {
+        if (!(now >= tmod[0]) || !(now < tmod[nrec - 1])) {
+            atomicOr(err, 1);
+            break;
+        }
+        long long lo = 0, hi = nrec - 1;            // tmod[lo] <= now < tmod[hi]
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (tmod[mid] <= now) lo = mid; else hi = mid;
+        }
+        if (lo < k0 || lo + 1 >= k0 + nk) break;    // bracket not inside this slab
+        if (!EARLY && !REG) {
+            p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
+        }
+        const long long j1 = pywrap_idx(p1.x, g.Nj), i1 = pywrap_idx(p1.y, g.Ni);
+        const long long j2 = pywrap_idx(p2.x, g.Nj), i2 = pywrap_idx(p2.y, g.Ni);
+        const long long j3 = pywrap_idx(p3.x, g.Nj), i3 = pywrap_idx(p3.y, g.Ni);
+        const long long j4 = pywrap_idx(p4.x, g.Nj), i4 = pywrap_idx(p4.y, g.Ni);
+        const long long c1 = j1 * g.Ni + i1, c2 = j2 * g.Ni + i2, c3 = j3 * g.Ni + i3, c4 = j4 * g.Ni + i4;
+        const long long cells = g.Nj * g.Ni;
+        const T* __restrict__ X1 = slab + (lo - k0) * cells;
+        const T* __restrict__ X2 = X1 + cells;
+        T a1, b1, a2, b2, a3, b3, a4, b4;
+        if (EARLY) {
+            a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
+            a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
+        }
+        int ocean;
+        if (mbits && *mflag == 0) {
+            const long long ntI = (g.Ni + 15) >> 4;
+            ocean = mask_bit(mbits, ntI, j1, i1) + mask_bit(mbits, ntI, j2, i2) + mask_bit(mbits, ntI, j3, i3) +
+                    mask_bit(mbits, ntI, j4, i4);
+        } else {
+            ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
+        }
+        if (ocean != 4) break;
+        if (!EARLY && !REG) {
+            wa = wb[0]; wc = wb[1];
+        }
+        if (!EARLY) {
+            a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
+            a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
+        }
+        const T dt = (T)(tmod[lo + 1] - tmod[lo]);
+        const T de = (T)(now - tmod[lo]);
+        const T v1 = a1 + ((b1 - a1) / dt) * de;
+        const T v2 = a2 + ((b2 - a2) / dt) * de;
+        const T v3 = a3 + ((b3 - a3) / dt) * de;
+        const T v4 = a4 + ((b4 - a4) / dt) * de;
+        r_np = (double)v1;
+        w_np = true;
+        const double sw = ((wa.x + wa.y) + wc.x) + wc.y;
+        if (!(fabs(sw - 1.0) > 0.001)) {
+            r_bl = ((wa.x * (double)v1 + wa.y * (double)v2) + wc.x * (double)v3) + wc.y * (double)v4;
+            w_bl = true;
+        }
+    } while (0);
+    if (w_np) {
+        out_np[t] = r_np;
+        for (int k = 0; k < peers.n; ++k) peers.np[k][t] = r_np;
     }
-    if (!(now >= tmod[0]) || !(now < tmod[nrec - 1])) {
-        atomicOr(err, 1);
-        return;
+    if (w_bl) {
+        out_bl[t] = r_bl;
+        for (int k = 0; k < peers.n; ++k) peers.bl[k][t] = r_bl;
     }
-    long long lo = 0, hi = nrec - 1;            // tmod[lo] <= now < tmod[hi]
-    while (hi - lo > 1) {
-        const long long mid = (lo + hi) >> 1;
-        if (tmod[mid] <= now) lo = mid; else hi = mid;
-    }
-    if (lo < k0 || lo + 1 >= k0 + nk) return;   // bracket not inside this slab
-    if (!EARLY && !REG) {
-        p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
-    }
-    const long long j1 = pywrap_idx(p1.x, g.Nj), i1 = pywrap_idx(p1.y, g.Ni);
-    const long long j2 = pywrap_idx(p2.x, g.Nj), i2 = pywrap_idx(p2.y, g.Ni);
-    const long long j3 = pywrap_idx(p3.x, g.Nj), i3 = pywrap_idx(p3.y, g.Ni);
-    const long long j4 = pywrap_idx(p4.x, g.Nj), i4 = pywrap_idx(p4.y, g.Ni);
-    const long long c1 = j1 * g.Ni + i1, c2 = j2 * g.Ni + i2, c3 = j3 * g.Ni + i3, c4 = j4 * g.Ni + i4;
-    const long long cells = g.Nj * g.Ni;
-    const T* __restrict__ X1 = slab + (lo - k0) * cells;
-    const T* __restrict__ X2 = X1 + cells;
-    T a1, b1, a2, b2, a3, b3, a4, b4;
-    if (EARLY) {
-        a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
-        a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
-    }
-    int ocean;
-    if (mbits && *mflag == 0) {
-        const long long ntI = (g.Ni + 15) >> 4;
-        ocean = mask_bit(mbits, ntI, j1, i1) + mask_bit(mbits, ntI, j2, i2) + mask_bit(mbits, ntI, j3, i3) +
-                mask_bit(mbits, ntI, j4, i4);
-    } else {
-        ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
-    }
-    if (ocean != 4) return;
-    if (!EARLY && !REG) {
-        wa = wb[0]; wc = wb[1];
-    }
-    if (!EARLY) {
-        a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
-        a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
-    }
-    const T dt = (T)(tmod[lo + 1] - tmod[lo]);
-    const T de = (T)(now - tmod[lo]);
-    const T v1 = a1 + ((b1 - a1) / dt) * de;
-    const T v2 = a2 + ((b2 - a2) / dt) * de;
-    const T v3 = a3 + ((b3 - a3) / dt) * de;
-    const T v4 = a4 + ((b4 - a4) / dt) * de;
-    out_np[t] = (double)v1;
-    const double sw = ((wa.x + wa.y) + wc.x) + wc.y;
-    if (!(fabs(sw - 1.0) > 0.001))
-        out_bl[t] = ((wa.x * (double)v1 + wa.y * (double)v2) + wc.x * (double)v3) + wc.y * (double)v4;
 }
-

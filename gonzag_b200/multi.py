@@ -173,6 +173,38 @@ class ShardedMapper:
         self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
         return int(self.flag.item()) == 0
 
+    def redo_own_points(self, y_own, x_own, t_own, tmod, slab, k0):
+        """K2 + K3 + K4 on this rank's own points (after `reseed` changed their nearest points)."""
+        self.e.mesh_weights(y_own, x_own, self.NP, self.SM, self.WB)
+        self.e.interp(t_own, self.SM, self.WB, tmod, slab, k0, self.v_np, self.v_bl)
+
+    def check_boundaries_async(self, gathered):
+        """Device-side version of `boundaries_ok`, no collective and no host read: every rank's halo
+        assumption travels in row 0 of its NP section, so after the all-gather each rank can compare
+        all boundaries itself.  The verdict is OR-ed into ``self.flag_acc`` (a device int32) and read
+        later with `boundaries_verdict()` -- a pipeline checks once per batch of steps, like an
+        asynchronous error flag, and re-seeds (`reseed`) only if it is ever set."""
+        tc = self.torch
+        if getattr(self, "flag_acc", None) is None:
+            self.flag_acc = self.e.empty((1,), tc.int32)
+            self.flag_acc.zero_()
+            self._last_rows = tc.as_tensor([self.bounds[g + 1] - self.bounds[g] for g in range(self.world - 1)],
+                                           device=self.flag_acc.device) if self.world > 1 else None
+        if self.world == 1:
+            return
+        NPs = gathered[:, 2 * self.m1:].view(self.world, self.m1, 2)
+        prev_last = NPs[tc.arange(self.world - 1, device=NPs.device), self._last_rows]     # (world-1, 2)
+        halo = NPs[1:, 0]                                                                  # (world-1, 2)
+        self.flag_acc |= (prev_last != halo).any().to(tc.int32)
+
+    def boundaries_verdict(self):
+        """Host read of the accumulated flag (one synchronisation); True = every step was valid."""
+        if getattr(self, "flag_acc", None) is None:
+            return True
+        bad = int(self.flag_acc.item())
+        self.flag_acc.zero_()
+        return bad == 0
+
     def reseed(self, gathered, y_own, x_own, rd, r):
         """Rare path: re-map the segments whose predecessor assumption was wrong, in rank order,
         until every boundary agrees (at most world-1 rounds).  Returns True if THIS rank re-mapped
@@ -205,3 +237,201 @@ class ShardedMapper:
             parts_bl.append(row[m1:2 * m1].view(tc.float64)[1:n + 1])
             parts_NP.append(row[2 * m1:].view(m1, 2)[1:n + 1])
         return tc.cat(parts_np), tc.cat(parts_bl), tc.cat(parts_NP)
+
+
+class _DevView:
+    """`__cuda_array_interface__` wrapper so that torch can view raw device memory owned by a context."""
+
+    def __init__(self, ptr, nwords):
+        self.__cuda_array_interface__ = {"shape": (int(nwords),), "typestr": "<i8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class P2PShardedMapper(ShardedMapper):
+    """`ShardedMapper` whose gather is fused into K4: every rank maps the product buffers of the
+    other ranks (CUDA IPC) and K4 stores the two interpolated series into all of them, over NVLink,
+    as it computes them; the collective left is a one-word all-reduce that orders the ranks.
+
+    Buffer of a rank, two of them used alternately (a rank may start writing step k+1 into a peer
+    while that peer still reads step k): ``[world][2*(nmax+1) + 4]`` int64 words -- per source rank
+    ``ssh_np`` (f64, nmax+1, row 0 = halo slot) | ``ssh_bl`` | 4 edge words (halo NP assumption,
+    last NP of the segment).  NP, SM and WB stay on the rank that computed them."""
+
+    def make_buffers(self, bounds):
+        tc = self.torch
+        ctx = self.e.ctx
+        lib = L.lib()
+        self.bounds = list(bounds)
+        self.nmax = max(bounds[g + 1] - bounds[g] for g in range(self.world))
+        n = bounds[self.rank + 1] - bounds[self.rank]
+        self.n = n
+        self.halo = self.rank > 0
+        m1 = self.nmax + 1
+        self.m1 = m1
+        self.slot = 2 * m1 + 4
+        self.NPh = self.e.empty((n + 1, 2), tc.int64)
+        self.NPh.zero_()
+        self.NP = self.NPh[1:]
+        self.SMh = self.e.empty((n + 1, 4, 2), tc.int64)
+        self.WBh = self.e.empty((n + 1, 4), tc.float64)
+        self.SM, self.WB = self.SMh[1:], self.WBh[1:]
+        self.flag = self.e.empty((1,), tc.int32)
+        self.flag.zero_()
+        nbytes = self.world * self.slot * 8
+        self._bufs = [ctx.dev_alloc(nbytes) for _ in range(2)]
+        for b in self._bufs:
+            ctx._ck(lib.gzb_memset(ctx._h, C.c_void_p(b.ptr), 0, nbytes))
+        ctx.sync()
+        self.gath = [tc.as_tensor(_DevView(b.ptr, self.world * self.slot), device=self.e.dev).view(self.world, self.slot)
+                     for b in self._bufs]
+        # exchange the IPC handles and map the peers' buffers
+        mine = []
+        for b in self._bufs:
+            hbuf = (C.c_ubyte * 64)()
+            ctx._ck(lib.gzb_ipc_export(ctx._h, C.c_void_p(b.ptr), hbuf))
+            mine.append(bytes(hbuf))
+        allh = [None] * self.world
+        if self.world > 1:
+            self.dist.all_gather_object(allh, mine)
+        else:
+            allh[0] = mine
+        self._peer_base = []          # [buffer][peer index] -> mapped base address on this device
+        self._peers = [g for g in range(self.world) if g != self.rank]
+        for bi in range(2):
+            row = []
+            for g in self._peers:
+                p = C.c_void_p()
+                ctx._ck(lib.gzb_ipc_open(ctx._h, (C.c_ubyte * 64).from_buffer_copy(allh[g][bi]), C.byref(p)))
+                row.append(p.value)
+            self._peer_base.append(row)
+        self.step_no = 0
+        self._select(0)
+        if self.world > 1:
+            self.dist.barrier()
+        return self
+
+    def _select(self, bi, first_row=None):
+        """Point the kernels at buffer `bi`: local views, and the peers' slots for this rank starting
+        at `first_row` (0: the call also covers the halo point, 1: own points only)."""
+        tc = self.torch
+        ctx = self.e.ctx
+        m1, slot, r = self.m1, self.slot, self.rank
+        mine = self.gath[bi][r]
+        self.v_np_h = mine[:m1].view(tc.float64)[:self.n + 1]
+        self.v_bl_h = mine[m1:2 * m1].view(tc.float64)[:self.n + 1]
+        self.v_np, self.v_bl = self.v_np_h[1:], self.v_bl_h[1:]
+        self.cur = bi
+        off = (0 if self.halo else 1) if first_row is None else first_row
+        npk = len(self._peers)
+        arr_np = (C.c_void_p * max(npk, 1))()
+        arr_bl = (C.c_void_p * max(npk, 1))()
+        self._edge_dst = (C.c_void_p * (npk + 1))()
+        for k in range(npk):
+            base = self._peer_base[bi][k] + r * slot * 8
+            arr_np[k] = base + off * 8
+            arr_bl[k] = base + (m1 + off) * 8
+            self._edge_dst[k] = base + 2 * m1 * 8
+        self._edge_dst[npk] = self._bufs[bi].ptr + (r * slot + 2 * m1) * 8
+        loc_np = self.v_np_h[off:].data_ptr()
+        loc_bl = self.v_bl_h[off:].data_ptr()
+        ctx._ck(L.lib().gzb_set_peer_outputs(ctx._h, npk, arr_np, arr_bl, C.c_void_p(loc_np), C.c_void_p(loc_bl)))
+
+    def _publish(self):
+        ctx = self.e.ctx
+        ctx._ck(L.lib().gzb_publish_edges(ctx._h, C.c_void_p(self.NPh.data_ptr()), self.n + 1, len(self._peers) + 1,
+                                          self._edge_dst))
+
+    def path_speculative(self, y_halo, x_halo, t_halo, rd, r, tmod, slab, k0):
+        """K1-K4 on [halo +] own points; K4 writes the series here and into every peer."""
+        self._select(self.step_no & 1)
+        self.step_no += 1
+        super().path_speculative(y_halo, x_halo, t_halo, rd, r, tmod, slab, k0)
+        self._publish()
+
+    def gather(self):
+        """No data moves here: the one-word all-reduce orders the ranks, after it every rank's buffer
+        holds the series of all segments."""
+        if self.world > 1:
+            self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
+        return self.gath[self.cur]
+
+    def _edges(self, gathered):
+        return gathered[:, 2 * self.m1:2 * self.m1 + 4]          # (world, 4): halo j,i, last j,i
+
+    def check_boundaries_async(self, gathered):
+        tc = self.torch
+        if getattr(self, "flag_acc", None) is None:
+            self.flag_acc = self.e.empty((1,), tc.int32)
+            self.flag_acc.zero_()
+        if self.world == 1:
+            return
+        e = self._edges(gathered)
+        self.flag_acc |= (e[1:, 0:2] != e[:-1, 2:4]).any().to(tc.int32)
+
+    def boundaries_ok(self, gathered):
+        if self.world == 1:
+            return True
+        e = self._edges(gathered)
+        return not bool((e[1:, 0:2] != e[:-1, 2:4]).any().item())
+
+    def _last_np_of(self, gathered, g):
+        return self._edges(gathered)[g, 2:4]
+
+    def reseed(self, gathered, y_own, x_own, rd, r):
+        """Rare path, as in the base class; the edge words are published again after a re-map.  The
+        caller then redoes K2-K4 on its own points with `redo_own_points`."""
+        changed = False
+        for _ in range(self.world):
+            if self.halo:
+                prev_last = self._last_np_of(gathered, self.rank - 1).clone()
+                if bool((prev_last != self.NPh[0]).any()):
+                    self.reseeds += 1
+                    changed = True
+                    pl = prev_last.cpu()
+                    self.e.nearest(y_own, x_own, rd, r, (int(pl[0]), int(pl[1])), self.NP)
+                    self.NPh[0] = prev_last
+            self._publish()
+            gathered = self.gather()
+            if self.boundaries_ok(gathered):
+                break
+        return changed
+
+    def redo_own_points(self, y_own, x_own, t_own, tmod, slab, k0):
+        """K2 + K3 + K4 on this rank's own points (after `reseed` changed their nearest points); K4
+        writes into the peers again."""
+        self._select(self.cur, first_row=1)
+        self.e.mesh_weights(y_own, x_own, self.NP, self.SM, self.WB)
+        self.e.interp(t_own, self.SM, self.WB, tmod, slab, k0, self.v_np, self.v_bl)
+
+    def unpack(self, gathered):
+        """Full-track (ssh_np, ssh_bl) in track order; NP stays sharded (None)."""
+        tc = self.torch
+        m1 = self.m1
+        parts_np, parts_bl = [], []
+        for g in range(self.world):
+            n = self.bounds[g + 1] - self.bounds[g]
+            row = gathered[g]
+            parts_np.append(row[:m1].view(tc.float64)[1:n + 1])
+            parts_bl.append(row[m1:2 * m1].view(tc.float64)[1:n + 1])
+        return tc.cat(parts_np), tc.cat(parts_bl), None
+
+    def detach(self):
+        """Stop replicating K4's outputs into the peers (local work only from here on)."""
+        ctx = self.e.ctx
+        if ctx._h is not None:
+            ctx._ck(L.lib().gzb_set_peer_outputs(ctx._h, 0, None, None, None, None))
+
+    def close(self):
+        ctx = self.e.ctx
+        if ctx._h is None:
+            return
+        L.lib().gzb_set_peer_outputs(ctx._h, 0, None, None, None, None)
+        for row in getattr(self, "_peer_base", []):
+            for p in row:
+                L.lib().gzb_ipc_close(ctx._h, C.c_void_p(p))
+        self._peer_base = []
+        if self.world > 1:
+            self.dist.barrier()
+        for b in getattr(self, "_bufs", []):
+            b.free()
+        self._bufs = []

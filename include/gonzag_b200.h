@@ -198,6 +198,23 @@ int gzb_alfabeta(int device, int64_t n, const double* vy5, const double* vx5, do
 int gzb_haversine(int device, int64_t n, double plat, double plon, const double* xlat,
                   const double* xlon, double* out);
 
+/* ---- multi-GPU, one process per GPU: K4 fused with the gather of its results ----------------
+ * A rank exports its product buffer (gzb_dev_alloc memory) with gzb_ipc_export; the 64-byte handle
+ * travels to the other ranks by any means (torch.distributed here), which map it with gzb_ipc_open.
+ * gzb_set_peer_outputs registers, for the local output buffers (vnp_local, vbl_local), n remote
+ * copies: from then on gzb_interp / gzb_map_interp calls writing those local buffers with
+ * init_outputs = 1 also store every value into the n peer buffers (NVLink stores issued by the
+ * gather kernel itself).  n = 0 turns it off.  The caller orders the ranks afterwards (a barrier:
+ * peers may read their buffer once every rank's call has completed).
+ * gzb_publish_edges copies the first and the last row of an (nrows,2) int64 array (a segment's halo
+ * assumption and its last nearest point) into n destinations of 4 int64. */
+int gzb_ipc_export(gzb_ctx* ctx, void* dptr, unsigned char* handle64);
+int gzb_ipc_open(gzb_ctx* ctx, const unsigned char* handle64, void** dptr_out);
+int gzb_ipc_close(gzb_ctx* ctx, void* dptr);
+int gzb_set_peer_outputs(gzb_ctx* ctx, int n, void* const* vnp_peers, void* const* vbl_peers,
+                         void* vnp_local, void* vbl_local);
+int gzb_publish_edges(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int n, void* const* dst);
+
 /* ---- memory helpers so that a host language without a CUDA binding can keep a pipeline on
  * the device (used by the Python layer; not part of the reference's surface) ---------------- */
 int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out);

@@ -68,6 +68,8 @@ def _worker(rank, world, port, cut, q):
         m.v_np.copy_(torch.arange(s0, s1, dtype=torch.float64))        # stand-ins for the K4 products
         m.v_bl.copy_(-torch.arange(s0, s1, dtype=torch.float64))
         g = m.gather()
+        m.check_boundaries_async(g)                # device-side check, no collective ...
+        assert m.boundaries_verdict() == m.boundaries_ok(g)     # ... same verdict as the all-reduce version
         if not m.boundaries_ok(g):
             m.reseed(g, yh[off:], xh[off:], rd, r)
             g = m.gather()
