@@ -471,10 +471,15 @@ def run_ours(args, w):
                     "K1 is a pointer-chasing search bounded by issue slots / L1-L2 latency rather than HBM "
                     "(see DESIGN.md); the HBM-bound stage is K4 (see kernels)"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file):        # dram__bytes_read+write per launch from the committed ncu capture
         try:
             with open(traffic_file) as f:
-                roof["traffic"] = json.load(f).get(dom)
+                tr = json.load(f)
+            roof["traffic"] = tr.get(dom)
+            for k in kern:
+                if k in tr:
+                    kern[k]["traffic"] = tr[k]
+            kern["K2K3_mesh_weights_traffic"] = tr.get("K2K3_mesh_weights")
         except Exception:
             pass
     clocks = sampler.stop() if rank == 0 else None
