@@ -23,6 +23,11 @@ int gzb_interp_dev(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm,
                    double* np_out, double* bl_out, const long long* list, const unsigned long long* count);
 int gzb_slab_device_pointer(const void* slab, const void** dev_out, int* is_host);
 
+int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
+                                int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
+                                const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss, double* vnp_out,
+                                double* vbl_out);
+
 namespace {
 
 // which stages a call runs
@@ -185,9 +190,14 @@ extern "C" int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const 
     const unsigned long long* nchg = nullptr;
     const bool split = ctx->overlap != 0;
     if ((rc = gzb_nearest_dev(ctx, nt, yt, xt, rd_found_km, np_box_r, seed_j, seed_i, np_out, split, &chg, &nchg)) != GZB_OK) return rc;
-    if ((rc = gzb_mesh_weights_dev(ctx, nt, yt, xt, np_out, sm_out, wb_out)) != GZB_OK) return rc;
-    if ((rc = gzb_interp_dev(ctx, nt, tt, sm_out, wb_out, nrec, tmod, slab_dev, dtype, k0, nk, rmissval, vnp_out, vbl_out,
-                             nullptr, nullptr)) != GZB_OK) return rc;
+    if (ctx->fuse_k4) {
+        if ((rc = gzb_mesh_weights_interp_dev(ctx, nt, yt, xt, np_out, sm_out, wb_out, tt, nrec, tmod, slab_dev, dtype, k0,
+                                              nk, rmissval, vnp_out, vbl_out)) != GZB_OK) return rc;
+    } else {
+        if ((rc = gzb_mesh_weights_dev(ctx, nt, yt, xt, np_out, sm_out, wb_out)) != GZB_OK) return rc;
+        if ((rc = gzb_interp_dev(ctx, nt, tt, sm_out, wb_out, nrec, tmod, slab_dev, dtype, k0, nk, rmissval, vnp_out,
+                                 vbl_out, nullptr, nullptr)) != GZB_OK) return rc;
+    }
     if (split) {
         GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[1], 0));
         if ((rc = gzb_path_fix_dev(ctx, yt, xt, np_out, sm_out, wb_out, chg, nchg, tt, nrec, tmod, slab_dev, dtype, k0, nk,

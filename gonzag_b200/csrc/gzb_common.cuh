@@ -87,6 +87,7 @@ struct gzb_ctx {
     GzbPeerOut peer_out = {0, {}, {}};   // gzb_set_peer_outputs: where K4 also writes its two series
     double* peer_local_np = nullptr;     // ... when its local outputs are these buffers
     double* peer_local_bl = nullptr;
+    int fuse_k4 = 1;                 // gzb_map_interp: 1 K2+K3+K4 in one kernel (mesh and weights never re-read), 0 K2+K3 then K4
     int overlap = 1;                 // gzb_mapping: 1 run the chain replays beside K2+K3, 0 strictly in sequence
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     GzbGrid g;

@@ -684,6 +684,7 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
         if (ctx->hdg_mode == 0) { ctx->g.hdg = nullptr; ctx->hdg_built = 0; ctx->stats.heading_table = 0; }
         return GZB_OK;
     }
+    if (!strcmp(name, "fuse_k4")) { ctx->fuse_k4 = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "overlap")) { ctx->overlap = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "k4_early")) { ctx->k4_early = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "mask_bits")) {

@@ -329,18 +329,75 @@ k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restr
     }
 }
 
-// mapping only (gzb_mapping) when slab_dev == nullptr, mapping + interpolation (gzb_map_interp) otherwise
-int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
-                     double* wb_out, const long long* list, const unsigned long long* count, const double* tt,
-                     int64_t nrec, const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk,
-                     double rmiss, double* vnp_out, double* vbl_out) {
-    InterpArgs ia;
+static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt);
+
+// K2 + K3 + K4 for every point in one pass (gzb_map_interp): the mesh and the weights go from the
+// registers of K3 straight into the gather, SM / WB are written once and never read back
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
+                      const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
+                      const int force_heavy, const InterpArgs ia) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const double yT = yt[t], xT = xt[t];
+    long long cj[4], ci[4];
+    source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
+    longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
+    longlong2 rp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        rp[k] = make_longlong2(cj[k], ci[k]);
+        sm[k] = rp[k];
+    }
+    double w[4];
+    weights_one(g, yT, xT, cj, ci, w);
+    double2* out = reinterpret_cast<double2*>(WB + 4 * t);
+    const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
+    out[0] = rw[0];
+    out[1] = rw[1];
+    interp_point<T, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
+                                 ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
+}
+
+static void fill_interp_args(gzb_ctx* ctx, InterpArgs& ia, const double* tt, int64_t nrec, const double* tmod,
+                             const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss, double* vnp_out,
+                             double* vbl_out) {
     ia.t_sat = tt; ia.nrec = nrec; ia.tmod = tmod; ia.slab = slab_dev; ia.dtype = dtype; ia.k0 = k0; ia.nk = nk;
     ia.rmiss = rmiss; ia.out_np = vnp_out; ia.out_bl = vbl_out; ia.err = ctx->d_flags;
     ia.mbits = ctx->mask_bits_ok ? ctx->d_mbits : nullptr;
     ia.mflag = ctx->d_flags + 2;
     ia.peers.n = 0;
     if (ctx->peer_out.n > 0 && vnp_out == ctx->peer_local_np && vbl_out == ctx->peer_local_bl) ia.peers = ctx->peer_out;
+}
+
+int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
+                                int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
+                                const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss, double* vnp_out,
+                                double* vbl_out) {
+    if (nt <= 0) return GZB_OK;
+    if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
+    InterpArgs ia;
+    fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
+    const unsigned nblk = (unsigned)((nt + 127) / 128);
+    if (dtype == GZB_F32)
+        k_mesh_weights_interp<float><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
+                                                                    (long long*)sm_out, wb_out, ctx->force_heavy, ia);
+    else
+        k_mesh_weights_interp<double><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
+                                                                     (long long*)sm_out, wb_out, ctx->force_heavy, ia);
+    GZB_LAUNCH_CHECK(ctx);
+    ctx->time_err_pending = 1;
+    return GZB_OK;
+}
+
+// mapping only (gzb_mapping) when slab_dev == nullptr, mapping + interpolation (gzb_map_interp) otherwise
+int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
+                     double* wb_out, const long long* list, const unsigned long long* count, const double* tt,
+                     int64_t nrec, const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk,
+                     double rmiss, double* vnp_out, double* vbl_out) {
+    InterpArgs ia;
+    fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
     k_path_fix<<<128, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
                                            ctx->force_heavy, ia);
     GZB_LAUNCH_CHECK(ctx);

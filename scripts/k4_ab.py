@@ -15,6 +15,7 @@ torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 ctx = gzb.GridContext(lat, lon, mask=mask, k_ew_per=2)
 ctx.grid_angle(out=False)
+ctx.set_option("heading_table", 2)
 eng = CudaEngine(ctx, torch)
 k_hi = int(t[-1] // 3600.0) + 1
 slab = bench.field_on_device(torch, dev, torch.as_tensor(lat, device=dev), torch.as_tensor(lon, device=dev), 0, k_hi)
@@ -28,21 +29,24 @@ eng.mesh_weights(yd, xd, NP, SM, WB)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
-for early in (0, 1):
-    for bits in (0, 1):
+for fuse in (0, 1, 0, 1):
+  ctx.set_option("fuse_k4", fuse)
+  print("fuse_k4", fuse)
+  for early in (0,):
+    for bits in (1,):
         ctx.set_option("k4_early", early)
         ctx.set_option("mask_bits", bits)
-        ms = []
-        for it in range(8):
-            torch.cuda.synchronize()
-            flush.zero_(); flush.zero_()
-            e0.record()
-            eng.interp(td, SM, WB, tmod, slab, 0, v_np, v_bl)
-            e1.record()
-            torch.cuda.synchronize()
-            ms.append(e0.elapsed_time(e1))
-        out = (v_np.clone(), v_bl.clone())
-        if ref is None:
-            ref = out
-        same = bool((out[0] == ref[0]).all() and (out[1] == ref[1]).all())
-        print("early %d bits %d: %.2f us (min %.2f)  identical %s" % (early, bits, 1e3 * np.mean(ms[2:]), 1e3 * np.min(ms[2:]), same))
+        for name, fn in (("K4", lambda: eng.interp(td, SM, WB, tmod, slab, 0, v_np, v_bl)),
+                         ("K2K3", lambda: eng.mesh_weights(yd, xd, NP, SM, WB)),
+                         ("K1", lambda: eng.nearest(yd, xd, rd, r, (r, r), NP)),
+                         ("path", lambda: eng.map_interp(yd, xd, td, rd, r, (r, r), tmod, slab, 0, NP, SM, WB, v_np, v_bl))):
+            ms = []
+            for it in range(8):
+                torch.cuda.synchronize()
+                flush.zero_(); flush.zero_()
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            print("  %-5s %.2f us (min %.2f)" % (name, 1e3 * np.mean(ms[2:]), 1e3 * np.min(ms[2:])))
