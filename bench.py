@@ -502,7 +502,7 @@ def run_ours(args, w):
                                    jt1=0, jt2=0, keepit=[], ssh=ssat)
         e2e_s = []
         stats = None
-        n_e2e = max(2, min(args.steps, 3))
+        n_e2e = max(3, min(args.steps, 5))
         for it in range(1 + n_e2e):
             barrier()
             t0 = time.perf_counter()
@@ -513,6 +513,7 @@ def run_ours(args, w):
             timing = R.timing
             if it > 0:
                 e2e_s.append(dt_)
+        log("[rank %d] e2e calls: %s ms" % (rank, ", ".join("%.1f" % (1e3 * v) for v in e2e_s)))
         t_e2e = float(np.mean(e2e_s))
         if world > 1:
             tm = torch.tensor([t_e2e], dtype=torch.float64, device=dev)

@@ -66,6 +66,7 @@ _SIGNATURES = {
                              _P, _P, C.c_int]),
     "gzb_track_distance": (C.c_int, [_P, _I64, _P, _P, _P, C.c_int]),
     "gzb_xnp_track": (C.c_int, [_P, _I64, _P, C.c_double, _P, C.c_int]),
+    "gzb_xnp_track_masked": (C.c_int, [_P, _I64, _P, C.c_double, _P, _P, C.c_int]),
     "gzb_heading": (C.c_int, [C.c_int, _I64, _P, _P, _P, _P, _P]),
     "gzb_alfabeta": (C.c_int, [C.c_int, _I64, _P, _P, _P]),
     "gzb_haversine": (C.c_int, [C.c_int, _I64, C.c_double, C.c_double, _P, _P, _P]),
@@ -79,6 +80,9 @@ _SIGNATURES = {
     "gzb_ipc_close": (C.c_int, [_P, _P]),
     "gzb_set_peer_outputs": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "gzb_publish_edges": (C.c_int, [_P, _P, _I64, C.c_int, _P]),
+    "gzb_pool_config": (C.c_int, [C.c_int, C.c_uint64]),
+    "gzb_pool_trim": (C.c_int, []),
+    "gzb_pool_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gzb_pointer_kind": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "gzb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "gzb_host_free": (C.c_int, [_P]),

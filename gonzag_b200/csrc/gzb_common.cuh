@@ -149,6 +149,8 @@ int gzb_fail(gzb_ctx* ctx, int code, const char* fmt, ...);
                             cudaGetErrorString(e__), __FILE__, __LINE__);                \
     } while (0)
 
+cudaError_t gzb_pool_malloc(void** p, size_t bytes);          // device memory through the process-wide pool
+cudaError_t gzb_pool_free(void* p);
 int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes);            // grow (contents lost), reset offset
 void* gzb_arena_take(gzb_ctx* ctx, size_t bytes);             // 256-byte aligned slice or null
 int gzb_use_device(gzb_ctx* ctx);

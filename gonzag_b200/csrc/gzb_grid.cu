@@ -1,7 +1,10 @@
 // Context management, the bounding-sphere pyramid over the model grid, and K0 (grid angle).
 #include <stdarg.h>
 
+#include <mutex>
 #include <new>
+#include <unordered_map>
+#include <vector>
 
 #include "gzb_common.cuh"
 
@@ -48,18 +51,153 @@ int gzb_use_device(gzb_ctx* ctx) {
     return GZB_OK;
 }
 
+
+// ======================================================================== device memory pool
+// cudaMalloc / cudaFree were measured to stall for 0.1 - 0.7 s now and then on a box that also holds
+// a large pinned + mapped host slab (the zero-copy field records), which dwarfs a 0.1 s end-to-end
+// call.  Every device buffer of the library therefore comes from a small process-wide pool: a freed
+// block is kept (per device, exact size) and handed to the next request of that size -- a second
+// context on the same grid, or the next Model2SatTrack call, allocates nothing.  Bounded by
+// gzb_pool_config; gzb_pool_trim gives everything back to the driver.
+namespace {
+struct PoolBlock { int dev; size_t bytes; void* p; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool_free;
+std::unordered_map<void*, std::pair<int, size_t>> g_pool_live;
+size_t g_pool_cached = 0;
+size_t g_pool_cap = (size_t)16 << 30;
+int g_pool_on = 1;
+}  // namespace
+
+cudaError_t gzb_pool_malloc(void** p, size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        for (size_t k = 0; k < g_pool_free.size(); ++k) {
+            if (g_pool_free[k].dev == dev && g_pool_free[k].bytes == bytes) {
+                *p = g_pool_free[k].p;
+                g_pool_cached -= bytes;
+                g_pool_free[k] = g_pool_free.back();
+                g_pool_free.pop_back();
+                g_pool_live[*p] = {dev, bytes};
+                return cudaSuccess;
+            }
+        }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {          // out of memory: give the cached blocks back and try once more
+        cudaGetLastError();
+        gzb_pool_trim();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool_live[*p] = {dev, bytes};
+    }
+    return e;
+}
+
+cudaError_t gzb_pool_free(void* p) {
+    if (!p) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_pool_live.find(p);
+        if (it != g_pool_live.end()) {
+            const int dev = it->second.first;
+            const size_t bytes = it->second.second;
+            g_pool_live.erase(it);
+            if (g_pool_on && g_pool_cached + bytes <= g_pool_cap) {
+                g_pool_free.push_back({dev, bytes, p});
+                g_pool_cached += bytes;
+                return cudaSuccess;
+            }
+        }
+    }
+    return cudaFree(p);
+}
+
+// The 4 KiB pinned scratch of a context (status words): pinning / unpinning host memory was
+// measured to stall like cudaMalloc / cudaFree do, so the blocks are recycled and only released by
+// gzb_pool_trim.
+namespace {
+std::vector<void*> g_scratch_free;
+}
+cudaError_t gzb_scratch_alloc(void** p) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_scratch_free.empty()) {
+            *p = g_scratch_free.back();
+            g_scratch_free.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaHostAlloc(p, 4096, cudaHostAllocPortable);
+}
+void gzb_scratch_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool_on && g_scratch_free.size() < 64) g_scratch_free.push_back(p);
+    else cudaFreeHost(p);
+}
+
+extern "C" int gzb_pool_trim(void) {
+    {
+        std::vector<void*> sc;
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            sc.swap(g_scratch_free);
+        }
+        for (void* q : sc) cudaFreeHost(q);
+    }
+    std::vector<PoolBlock> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        blocks.swap(g_pool_free);
+        g_pool_cached = 0;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const PoolBlock& b : blocks) {
+        cudaSetDevice(b.dev);
+        cudaFree(b.p);
+    }
+    cudaSetDevice(cur);
+    cudaGetLastError();
+    return GZB_OK;
+}
+
+extern "C" int gzb_pool_config(int enabled, uint64_t max_cached_bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool_on = enabled ? 1 : 0;
+        g_pool_cap = (size_t)max_cached_bytes;
+    }
+    if (!enabled) gzb_pool_trim();
+    return GZB_OK;
+}
+
+extern "C" int gzb_pool_stats(uint64_t* cached_bytes, uint64_t* cached_blocks, uint64_t* live_blocks) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (cached_bytes) *cached_bytes = g_pool_cached;
+    if (cached_blocks) *cached_blocks = g_pool_free.size();
+    if (live_blocks) *live_blocks = g_pool_live.size();
+    return GZB_OK;
+}
+
 // ======================================================================== workspace arena
 int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes) {
     ctx->arena.off = 0;
     if (bytes <= ctx->arena.cap) return GZB_OK;
     if (ctx->arena.base) {
         GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        GZB_CUDA(ctx, cudaFree(ctx->arena.base));
+        GZB_CUDA(ctx, gzb_pool_free(ctx->arena.base));
         ctx->arena.base = nullptr;
         ctx->arena.cap = 0;
     }
     size_t want = bytes + bytes / 4 + (size_t(1) << 20);
-    cudaError_t e = cudaMalloc((void**)&ctx->arena.base, want);
+    cudaError_t e = gzb_pool_malloc((void**)&ctx->arena.base, want);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return gzb_fail(ctx, GZB_ERR_NOMEM, "workspace of %zu bytes: %s", want, cudaGetErrorString(e));
@@ -388,10 +526,10 @@ static int build_lut(gzb_ctx* ctx, const unsigned long long* ext) {
     L.inv_d = 1.0 / d;
     const size_t nb = (size_t)L.nlat * (size_t)L.nlon;
     for (int k = 0; k < 2; ++k) {
-        cudaError_t e = cudaMalloc((void**)&ctx->d_lut[k], nb * sizeof(unsigned));
+        cudaError_t e = gzb_pool_malloc((void**)&ctx->d_lut[k], nb * sizeof(unsigned));
         if (e != cudaSuccess) {             // not fatal: the warp walk needs no table
             cudaGetLastError();
-            for (int q = 0; q < 2; ++q) { cudaFree(ctx->d_lut[q]); ctx->d_lut[q] = nullptr; }
+            for (int q = 0; q < 2; ++q) { gzb_pool_free(ctx->d_lut[q]); ctx->d_lut[q] = nullptr; }
             return GZB_OK;
         }
     }
@@ -443,22 +581,22 @@ static int build_pyramid(gzb_ctx* ctx) {
     ctx->stats.pyramid_levels = g.nlev;
     // storage
     const int64_t ntile = (int64_t)g.lev[0].nJ * g.lev[0].nI;
-    GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_cells, (size_t)ntile * 96 * sizeof(float)));
+    GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_cells, (size_t)ntile * 96 * sizeof(float)));
     g.cells = ctx->d_cells;
     for (int k = 0; k < g.nlev; ++k) {
         int64_t n = (k == g.nlev - 1) ? 32 : (int64_t)g.lev[k + 1].nJ * g.lev[k + 1].nI * 32;
-        GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_nodes[k], (size_t)n * sizeof(float4)));
+        GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_nodes[k], (size_t)n * sizeof(float4)));
         g.lev[k].nodes = ctx->d_nodes[k];
         k_fill_empty<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_nodes[k], n);
         GZB_LAUNCH_CHECK(ctx);
         if (k == 0) {
-            GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_cert, (size_t)n * sizeof(float)));
+            GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_cert, (size_t)n * sizeof(float)));
             GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_cert, 0, (size_t)n * sizeof(float), ctx->stream));
             g.cert = ctx->d_cert;
         }
     }
     {   // per-cell vectors + certificates of the per-thread search (optional: skipped when out of memory)
-        cudaError_t e = cudaMalloc((void**)&ctx->d_cellv, (size_t)g.Nj * (size_t)g.Ni * sizeof(float4));
+        cudaError_t e = gzb_pool_malloc((void**)&ctx->d_cellv, (size_t)g.Nj * (size_t)g.Ni * sizeof(float4));
         if (e != cudaSuccess) { cudaGetLastError(); ctx->d_cellv = nullptr; }
         g.cellv = ctx->d_cellv;
     }
@@ -539,27 +677,27 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
             if ((e = cudaEventCreateWithFlags(&ctx->ev[k], cudaEventDisableTiming)) != cudaSuccess) evfail = true;
         if (evfail) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); break; }
         const size_t n = (size_t)nj * (size_t)ni;
-        CK(cudaMalloc((void**)&ctx->d_lat, n * sizeof(double)));
-        CK(cudaMalloc((void**)&ctx->d_lon, n * sizeof(double)));
+        CK(gzb_pool_malloc((void**)&ctx->d_lat, n * sizeof(double)));
+        CK(gzb_pool_malloc((void**)&ctx->d_lon, n * sizeof(double)));
         CK(cudaMemcpyAsync(ctx->d_lat, lat, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_lon, lon, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMalloc((void**)&ctx->d_ll, n * sizeof(double2)));
+        CK(gzb_pool_malloc((void**)&ctx->d_ll, n * sizeof(double2)));
         k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, ctx->d_lat, ctx->d_lon, ctx->d_ll);
         ctx->stats.kernel_launches++;
         ctx->stats.h2d_bytes += 2 * n * sizeof(double);
         if (angle_or_null) {
-            CK(cudaMalloc((void**)&ctx->d_angle, n * sizeof(double)));
+            CK(gzb_pool_malloc((void**)&ctx->d_angle, n * sizeof(double)));
             CK(cudaMemcpyAsync(ctx->d_angle, angle_or_null, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             ctx->stats.h2d_bytes += n * sizeof(double);
         }
         if (mask_or_null) {
-            CK(cudaMalloc((void**)&ctx->d_mask, n));
+            CK(gzb_pool_malloc((void**)&ctx->d_mask, n));
             CK(cudaMemcpyAsync(ctx->d_mask, mask_or_null, n, cudaMemcpyHostToDevice, ctx->stream));
             ctx->stats.h2d_bytes += n;
         }
-        CK(cudaMalloc((void**)&ctx->d_flags, 256));
+        CK(gzb_pool_malloc((void**)&ctx->d_flags, 256));
         CK(cudaMemsetAsync(ctx->d_flags, 0, 256, ctx->stream));
-        CK(cudaHostAlloc(&ctx->pinned, 4096, cudaHostAllocPortable));
+        CK(gzb_scratch_alloc(&ctx->pinned));
         memset(ctx->pinned, 0, 4096);
         ctx->pinned_cap = 4096;
 #undef CK
@@ -591,22 +729,25 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     if (!ctx) return GZB_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    cudaFree(ctx->d_lat);
-    cudaFree(ctx->d_lon);
-    cudaFree(ctx->d_ll);
-    cudaFree(ctx->d_angle);
-    cudaFree(ctx->d_mask);
-    cudaFree(ctx->d_cells);
-    cudaFree(ctx->d_cert);
-    cudaFree(ctx->d_cellv);
-    cudaFree(ctx->d_lut[0]);
-    cudaFree(ctx->d_lut[1]);
-    cudaFree(ctx->d_hdg);
-    cudaFree(ctx->d_mbits);
-    cudaFree(ctx->d_flags);
-    for (int k = 0; k < GZB_MAXLEV; ++k) cudaFree(ctx->d_nodes[k]);
-    cudaFree(ctx->arena.base);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stream && ctx->stream != ctx->own_stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    gzb_pool_free(ctx->d_lat);
+    gzb_pool_free(ctx->d_lon);
+    gzb_pool_free(ctx->d_ll);
+    gzb_pool_free(ctx->d_angle);
+    gzb_pool_free(ctx->d_mask);
+    gzb_pool_free(ctx->d_cells);
+    gzb_pool_free(ctx->d_cert);
+    gzb_pool_free(ctx->d_cellv);
+    gzb_pool_free(ctx->d_lut[0]);
+    gzb_pool_free(ctx->d_lut[1]);
+    gzb_pool_free(ctx->d_hdg);
+    gzb_pool_free(ctx->d_mbits);
+    gzb_pool_free(ctx->d_flags);
+    for (int k = 0; k < GZB_MAXLEV; ++k) gzb_pool_free(ctx->d_nodes[k]);
+    gzb_pool_free(ctx->arena.base);
+    gzb_scratch_free(ctx->pinned);
     for (int k = 0; k < 2; ++k)
         if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
     for (int k = 0; k < 4; ++k)
@@ -710,7 +851,7 @@ extern "C" int gzb_set_mask(gzb_ctx* ctx, const int8_t* mask, int where) {
     if (!ctx || !mask) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_set_mask: null argument");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
     const size_t n = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni;
-    if (!ctx->d_mask) GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_mask, n));
+    if (!ctx->d_mask) GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_mask, n));
     GZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_mask, mask, n,
                                   where == GZB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->g.mask = ctx->d_mask;
@@ -731,7 +872,7 @@ extern "C" int gzb_set_angle(gzb_ctx* ctx, const double* angle_or_null, int wher
     }
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
     const size_t n = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni * sizeof(double);
-    if (!ctx->d_angle) GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_angle, n));
+    if (!ctx->d_angle) GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_angle, n));
     GZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_angle, angle_or_null, n,
                                   where == GZB_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
     if (where == GZB_HOST) {
@@ -976,7 +1117,7 @@ extern "C" int gzb_grid_angle(gzb_ctx* ctx, double* angle_out_or_null, int where
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
     const int64_t Nj = ctx->g.Nj, Ni = ctx->g.Ni;
     const size_t bytes = (size_t)Nj * (size_t)Ni * sizeof(double);
-    if (!ctx->d_angle) GZB_CUDA(ctx, cudaMalloc((void**)&ctx->d_angle, bytes));
+    if (!ctx->d_angle) GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_angle, bytes));
     dim3 grid((unsigned)((Ni + 127) / 128), (unsigned)((Nj + GA_ROWS - 1) / GA_ROWS));
     k_grid_angle<<<grid, 128, 0, ctx->stream>>>(Nj, Ni, ctx->d_lat, ctx->d_lon, ctx->d_angle);
     GZB_LAUNCH_CHECK(ctx);
@@ -998,10 +1139,10 @@ extern "C" int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out) {
     if (!ctx || !dptr_out) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_dev_alloc: null argument");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
     *dptr_out = nullptr;
-    cudaError_t e = cudaMalloc(dptr_out, bytes ? (size_t)bytes : 1);
+    cudaError_t e = gzb_pool_malloc(dptr_out, bytes ? (size_t)bytes : 1);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return gzb_fail(ctx, GZB_ERR_NOMEM, "cudaMalloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+        return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_pool_malloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
     }
     return GZB_OK;
 }
@@ -1009,7 +1150,9 @@ extern "C" int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out) {
 extern "C" int gzb_dev_free(gzb_ctx* ctx, void* dptr) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_dev_free: null ctx");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
-    GZB_CUDA(ctx, cudaFree(dptr));
+    // the block may be handed out again at once: nothing queued on this context may still use it
+    GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    GZB_CUDA(ctx, gzb_pool_free(dptr));
     return GZB_OK;
 }
 

@@ -61,7 +61,7 @@ int gzb_build_mask_bits(gzb_ctx* ctx) {
     ctx->mask_bits_ok = 0;
     if (!ctx->d_mask) return GZB_OK;
     if (!ctx->d_mbits) {
-        cudaError_t e = cudaMalloc((void**)&ctx->d_mbits, (size_t)nw * sizeof(unsigned));
+        cudaError_t e = gzb_pool_malloc((void**)&ctx->d_mbits, (size_t)nw * sizeof(unsigned));
         if (e != cudaSuccess) { cudaGetLastError(); ctx->d_mbits = nullptr; return GZB_OK; }   // K4 reads the bytes
     }
     GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 2, 0, 4, ctx->stream));
@@ -415,32 +415,49 @@ __global__ void k_xnp_scatter(const GzbGrid g, const long long nt, const long lo
 }
 
 __global__ void k_xnp_final(const GzbGrid g, const long long* __restrict__ last, const double rmiss,
-                            double* __restrict__ out) {
+                            double* __restrict__ out, unsigned char* __restrict__ missing) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= g.Nj * g.Ni) return;
     const long long l = last[k];
     double v = l >= 0 ? (double)l : rmiss;
     if (g.mask[k] == 0) v = -100.0;
     out[k] = v;
+    if (missing) missing[k] = (v == rmiss) ? 1 : 0;      // the mask of masked_where(XNPtrack == rmissval), mod2sat.py:186
 }
+
+static int xnp_track_impl(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval, double* xnp_out,
+                          unsigned char* missing_out, int where);
 
 extern "C" int gzb_xnp_track(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval, double* xnp_out,
                              int where) {
+    return xnp_track_impl(ctx, nt, np, rmissval, xnp_out, nullptr, where);
+}
+
+extern "C" int gzb_xnp_track_masked(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval, double* xnp_out,
+                                    unsigned char* missing_out, int where) {
+    if (!missing_out) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_xnp_track_masked: null missing_out");
+    return xnp_track_impl(ctx, nt, np, rmissval, xnp_out, missing_out, where);
+}
+
+static int xnp_track_impl(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval, double* xnp_out,
+                          unsigned char* missing_out, int where) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_xnp_track: null ctx");
     if (nt < 0 || !xnp_out || (nt > 0 && !np)) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_xnp_track: bad arguments");
     if (!ctx->g.mask) return gzb_fail(ctx, GZB_ERR_STATE, "gzb_xnp_track: the context has no land-sea mask");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
     const size_t n = (size_t)nt, cells = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni;
     size_t need = gzb_align(cells * 8);
-    if (where == GZB_HOST) need += gzb_align(n * 16 + 16) + gzb_align(cells * 8);
+    if (where == GZB_HOST) need += gzb_align(n * 16 + 16) + gzb_align(cells * 8) + gzb_align(cells);
     if (gzb_arena_reserve(ctx, need) != GZB_OK) return GZB_ERR_NOMEM;
     cudaStream_t s = ctx->stream;
     long long* last = (long long*)gzb_arena_take(ctx, cells * 8);
     const long long* dnp = (const long long*)np;
     double* dout = xnp_out;
+    unsigned char* dmiss = missing_out;
     if (where == GZB_HOST) {
         long long* a = (long long*)gzb_arena_take(ctx, n * 16 + 16);
         dout = (double*)gzb_arena_take(ctx, cells * 8);
+        if (missing_out) dmiss = (unsigned char*)gzb_arena_take(ctx, cells);
         if (nt > 0) GZB_CUDA(ctx, cudaMemcpyAsync(a, np, n * 16, cudaMemcpyHostToDevice, s));
         ctx->stats.h2d_bytes += n * 16;
         dnp = a;
@@ -450,11 +467,15 @@ extern "C" int gzb_xnp_track(gzb_ctx* ctx, int64_t nt, const int64_t* np, double
         k_xnp_scatter<<<(unsigned)((nt + 255) / 256), 256, 0, s>>>(ctx->g, nt, dnp, last);
         GZB_LAUNCH_CHECK(ctx);
     }
-    k_xnp_final<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(ctx->g, last, rmissval, dout);
+    k_xnp_final<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(ctx->g, last, rmissval, dout, dmiss);
     GZB_LAUNCH_CHECK(ctx);
     if (where == GZB_HOST) {
         GZB_CUDA(ctx, cudaMemcpyAsync(xnp_out, dout, cells * 8, cudaMemcpyDeviceToHost, s));
         ctx->stats.d2h_bytes += cells * 8;
+        if (missing_out) {
+            GZB_CUDA(ctx, cudaMemcpyAsync(missing_out, dmiss, cells, cudaMemcpyDeviceToHost, s));
+            ctx->stats.d2h_bytes += cells;
+        }
         GZB_CUDA(ctx, cudaStreamSynchronize(s));
     }
     return GZB_OK;

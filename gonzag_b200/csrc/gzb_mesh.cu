@@ -248,7 +248,7 @@ static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt) {
     const int64_t cells = ctx->g.Nj * ctx->g.Ni;
     if (ctx->hdg_mode == 1 && ctx->k2_points < cells / 2) return GZB_OK;
     if (!ctx->d_hdg) {
-        cudaError_t e = cudaMalloc((void**)&ctx->d_hdg, (size_t)cells * 6 * sizeof(double));
+        cudaError_t e = gzb_pool_malloc((void**)&ctx->d_hdg, (size_t)cells * 6 * sizeof(double));
         if (e != cudaSuccess) {
             cudaGetLastError();
             ctx->d_hdg = nullptr;
@@ -449,7 +449,7 @@ __global__ void k_haversine(long long n, double plat, double plon, const double*
 namespace {
 struct TmpDev {
     void* p = nullptr;
-    ~TmpDev() { if (p) cudaFree(p); }
+    ~TmpDev() { if (p) gzb_pool_free(p); }
 };
 }  // namespace
 
@@ -458,7 +458,7 @@ static int helper_run(int device, size_t in_doubles, size_t out_doubles, const d
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return gzb_fail(nullptr, GZB_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     TmpDev buf;
-    e = cudaMalloc(&buf.p, (in_doubles + out_doubles + 8) * sizeof(double));
+    e = gzb_pool_malloc(&buf.p, (in_doubles + out_doubles + 8) * sizeof(double));
     if (e != cudaSuccess) return gzb_fail(nullptr, GZB_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
     double* base = (double*)buf.p;
     double* din[8];

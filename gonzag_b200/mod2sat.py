@@ -239,11 +239,18 @@ class Model2SatTrack:
             ck(lib.gzb_d2h(h, L.ptr(vssh_m_np), P("vnp"), Nt * 8))
             ck(lib.gzb_d2h(h, L.ptr(vssh_m_bl), P("vbl"), Nt * 8))
             ck(lib.gzb_d2h(h, L.ptr(vdistance), P("dist"), Nt * 8))
+        tim["out_series_s"] = time.perf_counter() - tc
         if config.l_save_track_on_model_grid:
-            d_xnp = ctx.dev_alloc(Nj * Ni * 8)
-            ck(lib.gzb_xnp_track(h, Nt, P("np"), rmiss, C.c_void_p(d_xnp.ptr), L.GZB_DEVICE))
+            d_xnp = ctx.dev_alloc(Nj * Ni * 9)          # the map (f64) followed by its missing-value mask (u8)
+            d_xmk = C.c_void_p(d_xnp.ptr + Nj * Ni * 8)
+            ck(lib.gzb_xnp_track_masked(h, Nt, P("np"), rmiss, C.c_void_p(d_xnp.ptr), d_xmk, L.GZB_DEVICE))
             xnp = np.empty((Nj, Ni))
+            xmk = np.empty((Nj, Ni), dtype=np.bool_)
+            tim["out_xnp_kernel_s"] = time.perf_counter() - tc
             ck(lib.gzb_d2h(h, L.ptr(xnp), C.c_void_p(d_xnp.ptr), xnp.nbytes))
+            tim["out_xnp_d2h0_s"] = time.perf_counter() - tc
+            ck(lib.gzb_d2h(h, L.ptr(xmk), d_xmk, xmk.nbytes))
+            tim["out_xnp_d2h_s"] = time.perf_counter() - tc
         if keep_mapping:
             NP, SM, WB = np.empty((Nt, 2), np.int64), np.empty((Nt, 4, 2), np.int64), np.empty((Nt, 4))
             if Nt > 0:
@@ -252,6 +259,7 @@ class Model2SatTrack:
                 ck(lib.gzb_d2h(h, L.ptr(WB), P("wb"), WB.nbytes))
             self.BT = MappingView(NP, SM, WB)
         ctx.sync()
+        tim["out_sync_s"] = time.perf_counter() - tc
         d_all.free()
         if d_field is not None:
             d_field.free()
@@ -272,15 +280,19 @@ class Model2SatTrack:
         self.time = ST.time
         self.lat = ST.lat
         self.lon = ST.lon
-        imask = np.zeros(Nt, dtype=np.int8)
-        imask[np.where((vssh_m_bl > -100.) & (vssh_m_bl < 100.) & (vssh_s > -100.) & (vssh_s < 100.))] = 1
-        self.mask = imask
-        self.ssh_mod_np = np.ma.masked_where(imask == 0, vssh_m_np)
-        self.ssh_mod = np.ma.masked_where(imask == 0, vssh_m_bl)
-        self.ssh_sat = np.ma.masked_where(imask == 0, vssh_s)
+        good = (vssh_m_bl > -100.) & (vssh_m_bl < 100.) & (vssh_s > -100.) & (vssh_s < 100.)     # mod2sat.py:157-159
+        self.mask = good.astype(np.int8)
+        bad = ~good
+        # masked_where(imask == 0, x) on arrays this constructor owns: no copy of the data, one mask each
+        self.ssh_mod_np = np.ma.MaskedArray(vssh_m_np, mask=bad.copy(), copy=False)
+        self.ssh_mod = np.ma.MaskedArray(vssh_m_bl, mask=bad.copy(), copy=False)
+        self.ssh_sat = np.ma.MaskedArray(vssh_s, mask=bad, copy=False)
         self.distance = vdistance
         if xnp is not None:
-            self.XNPtrack = np.ma.MaskedArray(xnp, mask=(xnp == config.rmissval), copy=False)
+            X = xnp.view(np.ma.MaskedArray)              # masked_where(XNPtrack == rmissval, XNPtrack), mod2sat.py:186,
+            X._mask = xmk                                # with the comparison done on the GPU
+            X._sharedmask = False
+            self.XNPtrack = X
         tim["packaging_s"] = time.perf_counter() - tc
         self.timing = tim
         self.fused_path = fused
@@ -293,4 +305,6 @@ class Model2SatTrack:
             print('     - Interpolation of model data on the ' + str(Nt) + ' satellite points took: '
                   + str(round(time_bl_interp, 3)) + ' s \n')
         if own_ctx:
+            tc = time.perf_counter()
             ctx.close()
+            tim["close_s"] = time.perf_counter() - tc

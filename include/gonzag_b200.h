@@ -186,6 +186,10 @@ int gzb_track_distance(gzb_ctx* ctx, int64_t nt, const double* yt, const double*
                        double* dist_out, int where);
 int gzb_xnp_track(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval,
                   double* xnp_out, int where);
+/* same, plus missing_out (nj,ni) uint8 = (xnp == rmissval): the mask of the reference's
+ * masked_where(XNPtrack == rmissval, XNPtrack) (gonzag/mod2sat.py:186) without a host pass */
+int gzb_xnp_track_masked(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval,
+                         double* xnp_out, unsigned char* missing_out, int where);
 
 /* ---- scalar helpers exported by the reference package, batched ------------------------------
  * gzb_heading  : Heading(lata,lona,latb,lonb)      gonzag/bilin_mapping.py:16-47
@@ -222,6 +226,13 @@ int gzb_dev_free(gzb_ctx* ctx, void* dptr);
 int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);   /* async */
 int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);   /* async */
 int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes);            /* async */
+/* Device buffers of the library come from a process-wide pool (freed blocks are kept, per device
+ * and exact size, for the next request of that size: repeated calls on the same grid allocate
+ * nothing).  gzb_pool_config(enabled, max bytes kept; default on, 16 GiB), gzb_pool_trim() returns
+ * the kept blocks to the driver, gzb_pool_stats reports them. */
+int gzb_pool_config(int enabled, uint64_t max_cached_bytes);
+int gzb_pool_trim(void);
+int gzb_pool_stats(uint64_t* cached_bytes, uint64_t* cached_blocks, uint64_t* live_blocks);
 /* Where does `p` live?  kind_out: 0 pageable host memory (or unknown), 1 pinned + mapped host
  * memory (the GPU can read it in place), 2 device / managed memory. */
 int gzb_pointer_kind(const void* p, int* kind_out);
