@@ -3,6 +3,7 @@
 
 #include <mutex>
 #include <new>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -51,6 +52,124 @@ int gzb_use_device(gzb_ctx* ctx) {
     return GZB_OK;
 }
 
+
+// ======================================================================== big pageable copies
+// cudaMemcpy from / to pageable memory is bound by ONE host thread moving the data through the
+// driver's staging buffer (measured here: 11 GB/s up, 5 GB/s down into freshly allocated pages).
+// Large transfers are therefore cut into GZB_BC_THREADS contiguous parts, each moved by its own
+// thread through two pinned 8 MiB slots on its own stream (host memcpy of one slot overlapping the
+// DMA of the other).  The slots are allocated once per process and kept (gzb_pool_trim frees them).
+#define GZB_BC_THREADS 12
+#define GZB_BC_SLOT ((size_t)4 << 20)
+#define GZB_BC_MIN ((size_t)24 << 20)
+namespace {
+struct BigCopy {
+    void* slot[GZB_BC_THREADS][2];
+    cudaStream_t stream[GZB_BC_THREADS];
+    cudaEvent_t ev[GZB_BC_THREADS][2];
+    int dev = -1;
+    bool ok = false;
+};
+BigCopy g_bc;
+std::mutex g_bc_mu;
+
+bool bigcopy_ready(int dev) {
+    if (g_bc.ok && g_bc.dev == dev) return true;
+    if (g_bc.ok) return false;               // slots belong to another device: fall back to plain copies
+    for (int t = 0; t < GZB_BC_THREADS; ++t) {
+        for (int k = 0; k < 2; ++k) {
+            if (cudaHostAlloc(&g_bc.slot[t][k], GZB_BC_SLOT, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (cudaEventCreateWithFlags(&g_bc.ev[t][k], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+        }
+        if (cudaStreamCreateWithFlags(&g_bc.stream[t], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+    }
+    g_bc.dev = dev;
+    g_bc.ok = true;
+    return true;
+}
+
+void bigcopy_part(int dev, int t, char* dst, const char* src, size_t bytes, bool h2d, cudaError_t* err) {
+    cudaSetDevice(dev);
+    cudaError_t e = cudaSuccess;
+    size_t off = 0;
+    int k = 0;
+    bool used[2] = {false, false};
+    size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+    while (off < bytes && e == cudaSuccess) {
+        const size_t len = bytes - off < GZB_BC_SLOT ? bytes - off : GZB_BC_SLOT;
+        if (used[k]) {                           // the slot's previous transfer must be over
+            e = cudaEventSynchronize(g_bc.ev[t][k]);
+            if (!h2d && e == cudaSuccess) memcpy(dst + pend_off[k], g_bc.slot[t][k], pend_len[k]);
+        }
+        if (e != cudaSuccess) break;
+        if (h2d) {
+            memcpy(g_bc.slot[t][k], src + off, len);
+            e = cudaMemcpyAsync(dst + off, g_bc.slot[t][k], len, cudaMemcpyHostToDevice, g_bc.stream[t]);
+        } else {
+            e = cudaMemcpyAsync(g_bc.slot[t][k], src + off, len, cudaMemcpyDeviceToHost, g_bc.stream[t]);
+            pend_off[k] = off;
+            pend_len[k] = len;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(g_bc.ev[t][k], g_bc.stream[t]);
+        used[k] = true;
+        off += len;
+        k ^= 1;
+    }
+    for (int q = 0; q < 2 && e == cudaSuccess; ++q) {
+        const int kk = k ^ q;                    // oldest first
+        if (!used[kk]) continue;
+        e = cudaEventSynchronize(g_bc.ev[t][kk]);
+        if (!h2d && e == cudaSuccess) memcpy(dst + pend_off[kk], g_bc.slot[t][kk], pend_len[kk]);
+    }
+    *err = e;
+}
+}  // namespace
+
+// Copies `bytes` between pageable host memory and the device and RETURNS WHEN DONE.  Falls back to
+// one cudaMemcpyAsync + stream synchronisation for small or already pinned buffers.
+int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true) {
+    if (bytes == 0) return GZB_OK;
+    const void* host = h2d ? src : dst;
+    bool plain = bytes < GZB_BC_MIN;
+    if (!plain) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) plain = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    std::unique_lock<std::mutex> lk(g_bc_mu, std::defer_lock);
+    if (!plain) {
+        lk.lock();
+        if (!bigcopy_ready(ctx->device)) { plain = true; lk.unlock(); }
+    }
+    if (plain) {
+        GZB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, h2d ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return GZB_OK;
+    }
+    // everything queued so far (producers of `src`, users of `dst`) -- unless the caller knows better
+    if (sync_before) GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::thread th[GZB_BC_THREADS];
+    cudaError_t errs[GZB_BC_THREADS];
+    int want = (int)std::thread::hardware_concurrency() - 1;
+    want = want < 2 ? 2 : (want > GZB_BC_THREADS ? GZB_BC_THREADS : want);
+    const size_t part = (((bytes + want - 1) / want) + 4095) & ~(size_t)4095;
+    int nth = 0;
+    for (int t = 0; t < want; ++t) {
+        const size_t a = (size_t)t * part;
+        if (a >= bytes) break;
+        const size_t len = bytes - a < part ? bytes - a : part;
+        errs[t] = cudaSuccess;
+        th[t] = std::thread(bigcopy_part, ctx->device, t, (char*)dst + a, (const char*)src + a, len, h2d, &errs[t]);
+        ++nth;
+    }
+    for (int t = 0; t < nth; ++t) th[t].join();
+    for (int t = 0; t < nth; ++t)
+        if (errs[t] != cudaSuccess) return gzb_fail(ctx, GZB_ERR_CUDA, "parallel copy failed: %s", cudaGetErrorString(errs[t]));
+    return GZB_OK;
+}
 
 // ======================================================================== device memory pool
 // cudaMalloc / cudaFree were measured to stall for 0.1 - 0.7 s now and then on a box that also holds
@@ -144,6 +263,17 @@ void gzb_scratch_free(void* p) {
 
 extern "C" int gzb_pool_trim(void) {
     {
+        std::lock_guard<std::mutex> lk(g_bc_mu);
+        if (g_bc.ok) {
+            for (int t = 0; t < GZB_BC_THREADS; ++t) {
+                for (int k = 0; k < 2; ++k) { cudaFreeHost(g_bc.slot[t][k]); cudaEventDestroy(g_bc.ev[t][k]); }
+                cudaStreamDestroy(g_bc.stream[t]);
+            }
+            g_bc.ok = false;
+            g_bc.dev = -1;
+        }
+    }
+    {
         std::vector<void*> sc;
         {
             std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -185,6 +315,7 @@ extern "C" int gzb_pool_stats(uint64_t* cached_bytes, uint64_t* cached_blocks, u
     if (live_blocks) *live_blocks = g_pool_live.size();
     return GZB_OK;
 }
+
 
 // ======================================================================== workspace arena
 int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes) {
@@ -679,22 +810,14 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
         const size_t n = (size_t)nj * (size_t)ni;
         CK(gzb_pool_malloc((void**)&ctx->d_lat, n * sizeof(double)));
         CK(gzb_pool_malloc((void**)&ctx->d_lon, n * sizeof(double)));
-        CK(cudaMemcpyAsync(ctx->d_lat, lat, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_lon, lon, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = gzb_bigcopy(ctx, ctx->d_lat, lat, n * sizeof(double), true)) != GZB_OK) break;
+        if ((rc = gzb_bigcopy(ctx, ctx->d_lon, lon, n * sizeof(double), true)) != GZB_OK) break;
         CK(gzb_pool_malloc((void**)&ctx->d_ll, n * sizeof(double2)));
         k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, ctx->d_lat, ctx->d_lon, ctx->d_ll);
         ctx->stats.kernel_launches++;
         ctx->stats.h2d_bytes += 2 * n * sizeof(double);
-        if (angle_or_null) {
-            CK(gzb_pool_malloc((void**)&ctx->d_angle, n * sizeof(double)));
-            CK(cudaMemcpyAsync(ctx->d_angle, angle_or_null, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-            ctx->stats.h2d_bytes += n * sizeof(double);
-        }
-        if (mask_or_null) {
-            CK(gzb_pool_malloc((void**)&ctx->d_mask, n));
-            CK(cudaMemcpyAsync(ctx->d_mask, mask_or_null, n, cudaMemcpyHostToDevice, ctx->stream));
-            ctx->stats.h2d_bytes += n;
-        }
+        if (angle_or_null) CK(gzb_pool_malloc((void**)&ctx->d_angle, n * sizeof(double)));
+        if (mask_or_null) CK(gzb_pool_malloc((void**)&ctx->d_mask, n));
         CK(gzb_pool_malloc((void**)&ctx->d_flags, 256));
         CK(cudaMemsetAsync(ctx->d_flags, 0, 256, ctx->stream));
         CK(gzb_scratch_alloc(&ctx->pinned));
@@ -710,6 +833,16 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
         ctx->g.angle = ctx->d_angle;
         ctx->g.mask = ctx->d_mask;
         if ((rc = build_pyramid(ctx)) != GZB_OK) break;
+        // the angle and the mask are not needed by the search structures: their upload runs on the host
+        // threads while the GPU finishes the certificates and the seed table
+        if (angle_or_null) {
+            if ((rc = gzb_bigcopy(ctx, ctx->d_angle, angle_or_null, n * sizeof(double), true, false)) != GZB_OK) break;
+            ctx->stats.h2d_bytes += n * sizeof(double);
+        }
+        if (mask_or_null) {
+            if ((rc = gzb_bigcopy(ctx, ctx->d_mask, mask_or_null, n, true, false)) != GZB_OK) break;
+            ctx->stats.h2d_bytes += n;
+        }
         if ((rc = gzb_build_mask_bits(ctx)) != GZB_OK) break;
         e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "grid upload / pyramid build: %s", cudaGetErrorString(e)); break; }
@@ -1124,7 +1257,8 @@ extern "C" int gzb_grid_angle(gzb_ctx* ctx, double* angle_out_or_null, int where
     ctx->g.angle = ctx->d_angle;
     if (angle_out_or_null) {
         if (where == GZB_HOST) {
-            GZB_CUDA(ctx, cudaMemcpyAsync(angle_out_or_null, ctx->d_angle, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            const int rc = gzb_bigcopy(ctx, angle_out_or_null, ctx->d_angle, bytes, false);
+            if (rc != GZB_OK) return rc;
             ctx->stats.d2h_bytes += bytes;
         } else {
             GZB_CUDA(ctx, cudaMemcpyAsync(angle_out_or_null, ctx->d_angle, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1159,7 +1293,12 @@ extern "C" int gzb_dev_free(gzb_ctx* ctx, void* dptr) {
 extern "C" int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_h2d: null ctx");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
-    GZB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes >= GZB_BC_MIN) {         // large: parallel staging when the host buffer is pageable (returns when done)
+        const int rc = gzb_bigcopy(ctx, dst_dev, src_host, (size_t)bytes, true);
+        if (rc != GZB_OK) return rc;
+    } else {
+        GZB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->stats.h2d_bytes += bytes;
     return GZB_OK;
 }
@@ -1167,7 +1306,12 @@ extern "C" int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64
 extern "C" int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_d2h: null ctx");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
-    GZB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bytes >= GZB_BC_MIN) {
+        const int rc = gzb_bigcopy(ctx, dst_host, src_dev, (size_t)bytes, false);
+        if (rc != GZB_OK) return rc;
+    } else {
+        GZB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     ctx->stats.d2h_bytes += bytes;
     return GZB_OK;
 }

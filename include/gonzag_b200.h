@@ -223,8 +223,8 @@ int gzb_publish_edges(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int n
  * the device (used by the Python layer; not part of the reference's surface) ---------------- */
 int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out);
 int gzb_dev_free(gzb_ctx* ctx, void* dptr);
-int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);   /* async */
-int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);   /* async */
+int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);   /* async; >= 24 MiB of pageable memory: parallel staging, returns when done */
+int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);   /* idem */
 int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes);            /* async */
 /* Device buffers of the library come from a process-wide pool (freed blocks are kept, per device
  * and exact size, for the next request of that size: repeated calls on the same grid allocate

@@ -168,3 +168,32 @@ def test_heavy_duty_quadrant_everywhere():
     yn = lat[jj, 40] + 0.3 * (lat[jj + 1, 40] - lat[jj, 40])
     xn = lon[jj, 40].copy()
     _against_oracle(lat, lon, yn, xn, 2, rd, r, what="due north (light test finds no quadrant)")
+
+
+def test_device_pool_and_parallel_copies():
+    """Device buffers are recycled through the process-wide pool; big pageable arrays travel
+    through the parallel staged copy: same bytes either way."""
+    import ctypes as C
+    from gonzag_b200 import _lib as L
+    lib = L.lib()
+    lat, lon = syn.orca_like_grid(700, 5000)          # 28 MB per array: above the parallel-copy threshold
+    with gzb.GridContext(lat, lon, k_ew_per=2) as ctx:
+        a1 = ctx.grid_angle()                          # big D2H
+    cb, nb, live = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    L.check(lib.gzb_pool_stats(C.byref(cb), C.byref(nb), C.byref(live)))
+    assert cb.value > 3 * lat.nbytes and nb.value >= 8
+    L.check(lib.gzb_pool_config(0, 0))                 # pool off: plain cudaMalloc / cudaFree
+    L.check(lib.gzb_pool_stats(C.byref(cb), C.byref(nb), C.byref(live)))
+    assert cb.value == 0 and nb.value == 0
+    with gzb.GridContext(lat, lon, k_ew_per=2) as ctx:
+        a2 = ctx.grid_angle()
+        buf = ctx.dev_alloc(lat.nbytes)
+        ctx._ck(lib.gzb_h2d(ctx._h, C.c_void_p(buf.ptr), L.ptr(lat), lat.nbytes))       # big H2D ...
+        back = np.empty_like(lat)
+        ctx._ck(lib.gzb_d2h(ctx._h, L.ptr(back), C.c_void_p(buf.ptr), lat.nbytes))      # ... and back
+        ctx.sync()
+        buf.free()
+    L.check(lib.gzb_pool_config(1, 16 << 30))
+    np.testing.assert_array_equal(a1, a2)
+    np.testing.assert_array_equal(back, lat)
+    np.testing.assert_allclose(a1[:, 100:103], orc.grid_angle(lat[:, 100:103], lon[:, 100:103]), rtol=0, atol=1e-9)
