@@ -281,6 +281,7 @@ def run_ours(args, w):
     eng = CudaEngine(ctx, torch)
     Mapper = P2PShardedMapper if (world > 1 and args.gather == "p2p") else ShardedMapper
     mapper = Mapper(eng, dist if world > 1 else None, torch)
+    mapper.barrier = args.barrier
     torch.cuda.synchronize()
 
     # K0 (-D): part of the grid set-up (ModGrid in the reference), timed on its own
@@ -551,8 +552,8 @@ def run_ours(args, w):
                            "records_per_gpu": int(k_hi - k_lo + 1), "field_dtype": "f32",
                            "np_box_r": r, "rd_found_km": rd, "k_ew_per": 2,
                            "sharding": ("contiguous time segments, grid replicated; " + (
-                               "K4 stores the two series into every rank's buffer over NVLink (CUDA IPC peer memory), a one-word "
-                               "all-reduce orders the ranks" if isinstance(mapper, P2PShardedMapper) else
+                               "K4 stores the two series into every rank's buffer over NVLink (CUDA IPC peer memory), a barrier ("
+                               + ("own kernel over peer memory" if args.barrier == "p2p" else "one-word NCCL all-reduce") + ") orders the ranks" if isinstance(mapper, P2PShardedMapper) else
                                "1 all-gather of (ssh_np, ssh_bl, NP)") + "; segment-boundary check on the device, verdict read "
                                "once after the timed steps"),
                            "l2": "flushed (256 MiB write) before every timed step and stage",
@@ -582,6 +583,8 @@ def main():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: p2p = K4 stores its results into every rank's buffer over NVLink (one-word all-reduce "
                          "as the barrier); nccl = all-gather of the packed products after K4")
+    ap.add_argument("--barrier", default="nccl", choices=["p2p", "nccl"],
+                    help="with --gather p2p: how the ranks are ordered after K4 (own kernel over peer memory, or NCCL all-reduce)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check the sharded result against a single-GPU run")

@@ -119,6 +119,7 @@ struct gzb_ctx {
     int edge_exclusion = 1;          // 0: plain NearestPoint() semantics (no BilinTrack.nrpt edge rule)
     int force_heavy = 0;             // 1: heavy-duty quadrant search even if the light test succeeds; 2: skip the light test
     int time_err_pending = 0;
+    int barrier_err_pending = 0;     // d_flags[3] != 0: a peer barrier timed out (checked by gzb_sync)
     int* d_flags = nullptr;          // persistent device status words (word 0: K4 time-range error)
     int zero_copy = 1;               // gather from pinned+mapped host slabs instead of copying them
     // corner-box bounding sphere cache (predecessor == (-1,-1)), keyed by np_box_r

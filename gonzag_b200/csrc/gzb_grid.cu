@@ -914,7 +914,18 @@ extern "C" int gzb_sync(gzb_ctx* ctx) {
         int* h_err = (int*)((char*)ctx->pinned + 64);
         GZB_CUDA(ctx, cudaMemcpyAsync(h_err, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (ctx->barrier_err_pending)
+        GZB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 72, ctx->d_flags + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
     GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->barrier_err_pending) {
+        ctx->barrier_err_pending = 0;
+        int* h_b = (int*)((char*)ctx->pinned + 72);
+        if (*h_b) {
+            *h_b = 0;
+            GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 3, 0, 4, ctx->stream));
+            return gzb_fail(ctx, GZB_ERR_STATE, "gzb_peer_barrier: a peer did not arrive within the time limit");
+        }
+    }
     if (ctx->time_err_pending) {
         ctx->time_err_pending = 0;
         int* h_err = (int*)((char*)ctx->pinned + 64);
@@ -1176,6 +1187,64 @@ __global__ void k_publish_edges(const long long* __restrict__ rows, const long l
     if (k >= n) return;
     const long long v = (w < 2) ? rows[w] : rows[2 * (nrows - 1) + (w - 2)];
     d.p[k][w] = v;
+}
+
+// Cross-GPU barrier over peer memory, stream-ordered: every rank owns bar[world] epoch counters;
+// rank r stores `epoch` into bar[r] of every peer (P2P store after a system-wide fence, so that its
+// earlier stores into the peers -- K4's results -- are visible first) and waits until its own
+// bar[g] has reached `epoch` for every g.  Bounded wait: ~4 s of SM clocks, then *err |= 2.
+struct GzbBarDst { long long* p[GZB_MAX_PEERS + 1]; };
+__global__ void k_peer_barrier(const GzbBarDst d, const int n, volatile long long* local_bar, const int world,
+                               const int my_rank, const long long epoch, int* __restrict__ err) {
+    const int t = threadIdx.x;
+    __threadfence_system();
+    if (t < n) *(volatile long long*)d.p[t] = epoch;
+    __threadfence_system();
+    if (t < world && t != my_rank) {
+        const long long start = clock64();
+        while (local_bar[t] < epoch) {
+            if (clock64() - start > 8000000000LL) { atomicOr(err, 2); break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+extern "C" int gzb_peer_barrier(gzb_ctx* ctx, int n, void* const* peer_slots, void* local_bar, int world, int my_rank,
+                                int64_t epoch) {
+    if (!ctx || n < 0 || n > GZB_MAX_PEERS || world < 1 || world > GZB_MAX_PEERS + 1 || !local_bar || (n > 0 && !peer_slots))
+        return gzb_fail(ctx, GZB_ERR_ARG, "gzb_peer_barrier: bad arguments");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GzbBarDst d;
+    for (int k = 0; k < n; ++k) d.p[k] = (long long*)peer_slots[k];
+    k_peer_barrier<<<1, 32, 0, ctx->stream>>>(d, n, (volatile long long*)local_bar, world, my_rank, (long long)epoch,
+                                             ctx->d_flags + 3);
+    GZB_LAUNCH_CHECK(ctx);
+    ctx->barrier_err_pending = 1;
+    return GZB_OK;
+}
+
+// boundary check of the gathered edge words: flag |= any(halo assumption of rank g != last nearest
+// point of rank g-1).  edges: (world, stride) int64 with the 4 edge words at `offset` of every row.
+__global__ void k_check_edges(const long long* __restrict__ edges, const long long stride, const long long offset,
+                              const int world, int* __restrict__ flag) {
+    const int g = threadIdx.x + 1;
+    if (g >= world) return;
+    const long long* cur = edges + (long long)g * stride + offset;
+    const long long* prv = edges + (long long)(g - 1) * stride + offset;
+    if (cur[0] != prv[2] || cur[1] != prv[3]) atomicOr(flag, 1);
+}
+
+extern "C" int gzb_check_edges(gzb_ctx* ctx, const int64_t* gathered, int64_t stride_words, int64_t offset_words,
+                               int world, int* flag_dev) {
+    if (!ctx || !gathered || !flag_dev || world < 1 || world > 1024)
+        return gzb_fail(ctx, GZB_ERR_ARG, "gzb_check_edges: bad arguments");
+    if (world == 1) return GZB_OK;
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    k_check_edges<<<1, ((world + 31) / 32) * 32, 0, ctx->stream>>>((const long long*)gathered, stride_words, offset_words, world,
+                                                                  flag_dev);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
 }
 
 extern "C" int gzb_publish_edges(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int n, void* const* dst) {

@@ -277,7 +277,7 @@ class P2PShardedMapper(ShardedMapper):
         self.SM, self.WB = self.SMh[1:], self.WBh[1:]
         self.flag = self.e.empty((1,), tc.int32)
         self.flag.zero_()
-        nbytes = self.world * self.slot * 8
+        nbytes = (self.world * self.slot + self.world) * 8        # + the epoch counters of the peer barrier
         self._bufs = [ctx.dev_alloc(nbytes) for _ in range(2)]
         for b in self._bufs:
             ctx._ck(lib.gzb_memset(ctx._h, C.c_void_p(b.ptr), 0, nbytes))
@@ -304,37 +304,52 @@ class P2PShardedMapper(ShardedMapper):
                 ctx._ck(lib.gzb_ipc_open(ctx._h, (C.c_ubyte * 64).from_buffer_copy(allh[g][bi]), C.byref(p)))
                 row.append(p.value)
             self._peer_base.append(row)
+        # barrier: this rank's entry in every peer's counters (kept in buffer 0), its own counters
+        self._bar_slots = (C.c_void_p * max(len(self._peers), 1))()
+        for k in range(len(self._peers)):
+            self._bar_slots[k] = self._peer_base[0][k] + (self.world * self.slot + self.rank) * 8
+        self._bar_local = C.c_void_p(self._bufs[0].ptr + self.world * self.slot * 8)
+        self._epoch = 0
         self.step_no = 0
         self._select(0)
         if self.world > 1:
             self.dist.barrier()
         return self
 
-    def _select(self, bi, first_row=None):
-        """Point the kernels at buffer `bi`: local views, and the peers' slots for this rank starting
-        at `first_row` (0: the call also covers the halo point, 1: own points only)."""
+    def _selection(self, bi, off):
+        """Views and pointer tables for buffer `bi`, kernels writing from row `off` of this rank's slot."""
         tc = self.torch
-        ctx = self.e.ctx
         m1, slot, r = self.m1, self.slot, self.rank
         mine = self.gath[bi][r]
-        self.v_np_h = mine[:m1].view(tc.float64)[:self.n + 1]
-        self.v_bl_h = mine[m1:2 * m1].view(tc.float64)[:self.n + 1]
-        self.v_np, self.v_bl = self.v_np_h[1:], self.v_bl_h[1:]
-        self.cur = bi
-        off = (0 if self.halo else 1) if first_row is None else first_row
+        v_np_h = mine[:m1].view(tc.float64)[:self.n + 1]
+        v_bl_h = mine[m1:2 * m1].view(tc.float64)[:self.n + 1]
         npk = len(self._peers)
         arr_np = (C.c_void_p * max(npk, 1))()
         arr_bl = (C.c_void_p * max(npk, 1))()
-        self._edge_dst = (C.c_void_p * (npk + 1))()
+        edge_dst = (C.c_void_p * (npk + 1))()
         for k in range(npk):
             base = self._peer_base[bi][k] + r * slot * 8
             arr_np[k] = base + off * 8
             arr_bl[k] = base + (m1 + off) * 8
-            self._edge_dst[k] = base + 2 * m1 * 8
-        self._edge_dst[npk] = self._bufs[bi].ptr + (r * slot + 2 * m1) * 8
-        loc_np = self.v_np_h[off:].data_ptr()
-        loc_bl = self.v_bl_h[off:].data_ptr()
-        ctx._ck(L.lib().gzb_set_peer_outputs(ctx._h, npk, arr_np, arr_bl, C.c_void_p(loc_np), C.c_void_p(loc_bl)))
+            edge_dst[k] = base + 2 * m1 * 8
+        edge_dst[npk] = self._bufs[bi].ptr + (r * slot + 2 * m1) * 8
+        return dict(v_np_h=v_np_h, v_bl_h=v_bl_h, arr_np=arr_np, arr_bl=arr_bl, edge_dst=edge_dst, npk=npk,
+                    loc_np=C.c_void_p(v_np_h[off:].data_ptr()), loc_bl=C.c_void_p(v_bl_h[off:].data_ptr()))
+
+    def _select(self, bi, first_row=None):
+        """Point the kernels at buffer `bi`: local views, and the peers' slots for this rank starting
+        at `first_row` (0: the call also covers the halo point, 1: own points only)."""
+        off = (0 if self.halo else 1) if first_row is None else first_row
+        cache = self.__dict__.setdefault("_sel_cache", {})
+        sel = cache.get((bi, off))
+        if sel is None:
+            sel = cache[(bi, off)] = self._selection(bi, off)
+        self.v_np_h, self.v_bl_h = sel["v_np_h"], sel["v_bl_h"]
+        self.v_np, self.v_bl = self.v_np_h[1:], self.v_bl_h[1:]
+        self.cur = bi
+        self._edge_dst = sel["edge_dst"]
+        ctx = self.e.ctx
+        ctx._ck(L.lib().gzb_set_peer_outputs(ctx._h, sel["npk"], sel["arr_np"], sel["arr_bl"], sel["loc_np"], sel["loc_bl"]))
 
     def _publish(self):
         ctx = self.e.ctx
@@ -349,10 +364,17 @@ class P2PShardedMapper(ShardedMapper):
         self._publish()
 
     def gather(self):
-        """No data moves here: the one-word all-reduce orders the ranks, after it every rank's buffer
-        holds the series of all segments."""
+        """No data moves here: a barrier orders the ranks (a stream-ordered kernel over peer memory,
+        or NCCL's one-word all-reduce with ``barrier="nccl"``), after it every rank's buffer holds the
+        series of all segments."""
         if self.world > 1:
-            self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
+            if getattr(self, "barrier", "nccl") == "nccl":
+                self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
+            else:
+                ctx = self.e.ctx
+                self._epoch += 1
+                ctx._ck(L.lib().gzb_peer_barrier(ctx._h, len(self._peers), self._bar_slots, self._bar_local, self.world,
+                                                 self.rank, self._epoch))
         return self.gath[self.cur]
 
     def _edges(self, gathered):
@@ -365,8 +387,9 @@ class P2PShardedMapper(ShardedMapper):
             self.flag_acc.zero_()
         if self.world == 1:
             return
-        e = self._edges(gathered)
-        self.flag_acc |= (e[1:, 0:2] != e[:-1, 2:4]).any().to(tc.int32)
+        ctx = self.e.ctx
+        ctx._ck(L.lib().gzb_check_edges(ctx._h, C.c_void_p(gathered.data_ptr()), self.slot, 2 * self.m1, self.world,
+                                        C.c_void_p(self.flag_acc.data_ptr())))
 
     def boundaries_ok(self, gathered):
         if self.world == 1:

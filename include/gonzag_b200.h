@@ -218,6 +218,16 @@ int gzb_ipc_close(gzb_ctx* ctx, void* dptr);
 int gzb_set_peer_outputs(gzb_ctx* ctx, int n, void* const* vnp_peers, void* const* vbl_peers,
                          void* vnp_local, void* vbl_local);
 int gzb_publish_edges(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int n, void* const* dst);
+/* Stream-ordered barrier between the ranks over peer memory (no NCCL call): every rank owns `world`
+ * int64 epoch counters (local_bar, zero-initialised, IPC-mapped by the peers); peer_slots[k] is the
+ * address, in peer k's counters, of this rank's entry.  Epochs must increase by one per barrier.  A
+ * peer that does not arrive within ~4 s is reported by the next gzb_sync (GZB_ERR_STATE). */
+int gzb_peer_barrier(gzb_ctx* ctx, int n, void* const* peer_slots, void* local_bar, int world, int my_rank,
+                     int64_t epoch);
+/* *flag_dev |= 1 if, for some rank g > 0, the halo words of row g differ from the last-point words of
+ * row g-1 (rows of stride_words int64, the 4 edge words at offset_words). */
+int gzb_check_edges(gzb_ctx* ctx, const int64_t* gathered, int64_t stride_words, int64_t offset_words,
+                    int world, int* flag_dev);
 
 /* ---- memory helpers so that a host language without a CUDA binding can keep a pipeline on
  * the device (used by the Python layer; not part of the reference's surface) ---------------- */
