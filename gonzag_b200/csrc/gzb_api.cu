@@ -5,9 +5,11 @@
 size_t gzb_nearest_ws_bytes(int64_t nt);
 int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double rd_found_km,
                     int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out, bool split = false,
-                    const long long** chg_out = nullptr, const unsigned long long** nchg_out = nullptr);
+                    const long long** chg_out = nullptr, const unsigned long long** nchg_out = nullptr,
+                    GzbGlobalNearest* gn_out = nullptr);
 int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
-                     double* wb_out, const long long* list, const unsigned long long* count, const double* tt,
+                     double* wb_out, const long long* list, const unsigned long long* count, const long long* list2,
+                     const unsigned long long* count2, const double* tt,
                      int64_t nrec, const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk,
                      double rmiss, double* vnp_out, double* vbl_out);
 int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
@@ -16,7 +18,7 @@ int gzb_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
                     double* wb_out);
 
 int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
-                         int64_t* sm_out, double* wb_out);
+                         int64_t* sm_out, double* wb_out, const GzbGlobalNearest* gn_or_null = nullptr);
 
 int gzb_interp_dev(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm, const double* wb, int64_t nrec,
                    const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss,
@@ -24,7 +26,7 @@ int gzb_interp_dev(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm,
 int gzb_slab_device_pointer(const void* slab, const void** dev_out, int* is_host);
 
 int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
-                                int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
+                                const GzbGlobalNearest* gn_or_null, int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
                                 const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss, double* vnp_out,
                                 double* vbl_out);
 
@@ -88,11 +90,12 @@ int run_stages(gzb_ctx* ctx, int stages, int64_t nt, const double* yt, const dou
         // K2+K3 for the few points the replays changed
         const long long* chg = nullptr;
         const unsigned long long* nchg = nullptr;
-        if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp, true, &chg, &nchg)) != GZB_OK) return rc;
-        if ((rc = gzb_mesh_weights_dev(ctx, nt, dy, dx, dnp, dsm, dwb)) != GZB_OK) return rc;
+        GzbGlobalNearest gn;
+        if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp, true, &chg, &nchg, &gn)) != GZB_OK) return rc;
+        if ((rc = gzb_mesh_weights_dev(ctx, nt, dy, dx, dnp, dsm, dwb, &gn)) != GZB_OK) return rc;
         GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[1], 0));
-        if ((rc = gzb_path_fix_dev(ctx, dy, dx, dnp, dsm, dwb, chg, nchg, nullptr, 0, nullptr, nullptr, 0, 0, 0, 0.0,
-                                   nullptr, nullptr)) != GZB_OK) return rc;
+        if ((rc = gzb_path_fix_dev(ctx, dy, dx, dnp, dsm, dwb, chg, nchg, gn.ulist, gn.ucount, nullptr, 0, nullptr, nullptr,
+                                   0, 0, 0, 0.0, nullptr, nullptr)) != GZB_OK) return rc;
     } else {
     if (stages & ST_NP) {
         if ((rc = gzb_nearest_dev(ctx, nt, dy, dx, rd, r, seed_j, seed_i, dnp)) != GZB_OK) return rc;
@@ -189,19 +192,24 @@ extern "C" int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const 
     const long long* chg = nullptr;
     const unsigned long long* nchg = nullptr;
     const bool split = ctx->overlap != 0;
-    if ((rc = gzb_nearest_dev(ctx, nt, yt, xt, rd_found_km, np_box_r, seed_j, seed_i, np_out, split, &chg, &nchg)) != GZB_OK) return rc;
+    GzbGlobalNearest gn;
+    if ((rc = gzb_nearest_dev(ctx, nt, yt, xt, rd_found_km, np_box_r, seed_j, seed_i, np_out, split, &chg, &nchg, &gn)) != GZB_OK) return rc;
+    const GzbGlobalNearest* gnp = split ? &gn : nullptr;      // overlap: K2-K4 start from E(t), the chain runs beside them
     if (ctx->fuse_k4) {
-        if ((rc = gzb_mesh_weights_interp_dev(ctx, nt, yt, xt, np_out, sm_out, wb_out, tt, nrec, tmod, slab_dev, dtype, k0,
+        if ((rc = gzb_mesh_weights_interp_dev(ctx, nt, yt, xt, np_out, gnp, sm_out, wb_out, tt, nrec, tmod, slab_dev, dtype, k0,
                                               nk, rmissval, vnp_out, vbl_out)) != GZB_OK) return rc;
     } else {
-        if ((rc = gzb_mesh_weights_dev(ctx, nt, yt, xt, np_out, sm_out, wb_out)) != GZB_OK) return rc;
+        if ((rc = gzb_mesh_weights_dev(ctx, nt, yt, xt, np_out, sm_out, wb_out, gnp)) != GZB_OK) return rc;
         if ((rc = gzb_interp_dev(ctx, nt, tt, sm_out, wb_out, nrec, tmod, slab_dev, dtype, k0, nk, rmissval, vnp_out,
                                  vbl_out, nullptr, nullptr)) != GZB_OK) return rc;
     }
+    gzb_trace(ctx, s, "bulk end (main)");
     if (split) {
         GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[1], 0));
-        if ((rc = gzb_path_fix_dev(ctx, yt, xt, np_out, sm_out, wb_out, chg, nchg, tt, nrec, tmod, slab_dev, dtype, k0, nk,
+        if ((rc = gzb_path_fix_dev(ctx, yt, xt, np_out, sm_out, wb_out, chg, nchg, gn.ulist, gn.ucount, tt, nrec, tmod, slab_dev,
+                                   dtype, k0, nk,
                                    rmissval, vnp_out, vbl_out)) != GZB_OK) return rc;
     }
+    gzb_trace(ctx, s, "path end (main)");
     return GZB_OK;
 }

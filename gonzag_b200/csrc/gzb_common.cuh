@@ -63,6 +63,17 @@ struct GzbGrid {
     GzbLevel lev[GZB_MAXLEV];
 };
 
+// the plain global answers of K1 (before the chain logic): flat index + distance of the nearest cell of
+// every point, and what turns them into E(t) (threshold of the last useful pass, edge exclusion)
+struct GzbGlobalNearest {
+    const long long* G;     // 0x7ffffffffffffffe = not settled yet (the bulk kernels skip the point)
+    const double* dG;
+    double thr2;
+    int edge;
+    const long long* ulist;               // the points that were unsettled when the bulk kernels ran ...
+    const unsigned long long* ucount;     // ... and how many (device): they go through the repair kernel
+};
+
 struct GzbArena {
     char* base = nullptr;
     size_t cap = 0;
@@ -88,6 +99,13 @@ struct gzb_ctx {
     double* peer_local_np = nullptr;     // ... when its local outputs are these buffers
     double* peer_local_bl = nullptr;
     int fuse_k4 = 1;                 // gzb_map_interp: 1 K2+K3+K4 in one kernel (mesh and weights never re-read), 0 K2+K3 then K4
+    unsigned char* d_rowsafe = nullptr;   // per row: East-West twin shortcut allowed (k_rowsafe), for k_ew_per = rowsafe_kew
+    int rowsafe_kew = -2;
+    int twin_chain = 1;              // 1: the speculative chain of K1 knows the East-West twins (two-state scan); 0: R = E(t) only
+    int trace = 0;                   // option "trace": record a timing event at every gzb_trace() mark, printed by gzb_sync
+    int ntrace = 0;
+    cudaEvent_t trace_ev[48] = {};
+    const char* trace_name[48] = {};
     int overlap = 1;                 // gzb_mapping: 1 run the chain replays beside K2+K3, 0 strictly in sequence
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     GzbGrid g;
@@ -155,6 +173,7 @@ cudaError_t gzb_pool_free(void* p);
 int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes);            // grow (contents lost), reset offset
 void* gzb_arena_take(gzb_ctx* ctx, size_t bytes);             // 256-byte aligned slice or null
 int gzb_use_device(gzb_ctx* ctx);
+void gzb_trace(gzb_ctx* ctx, cudaStream_t s, const char* what);   // option "trace": timestamped marks on any stream (debugging aid)
 int gzb_build_mask_bits(gzb_ctx* ctx);                        // gzb_interp.cu: after every change of the mask
 
 static inline size_t gzb_align(size_t n) { return (n + 255) & ~size_t(255); }

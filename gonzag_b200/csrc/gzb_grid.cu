@@ -47,6 +47,14 @@ extern "C" int gzb_device_count(int* n_out) {
     return GZB_OK;
 }
 
+void gzb_trace(gzb_ctx* ctx, cudaStream_t s, const char* what) {
+    if (!ctx->trace || ctx->ntrace >= 48) return;
+    const int k = ctx->ntrace++;
+    if (!ctx->trace_ev[k]) cudaEventCreate(&ctx->trace_ev[k]);
+    ctx->trace_name[k] = what;
+    cudaEventRecord(ctx->trace_ev[k], s);
+}
+
 int gzb_use_device(gzb_ctx* ctx) {
     GZB_CUDA(ctx, cudaSetDevice(ctx->device));
     return GZB_OK;
@@ -877,6 +885,7 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     gzb_pool_free(ctx->d_lut[1]);
     gzb_pool_free(ctx->d_hdg);
     gzb_pool_free(ctx->d_mbits);
+    gzb_pool_free(ctx->d_rowsafe);
     gzb_pool_free(ctx->d_flags);
     for (int k = 0; k < GZB_MAXLEV; ++k) gzb_pool_free(ctx->d_nodes[k]);
     gzb_pool_free(ctx->arena.base);
@@ -913,6 +922,15 @@ extern "C" int gzb_sync(gzb_ctx* ctx) {
     if (ctx->time_err_pending) {
         int* h_err = (int*)((char*)ctx->pinned + 64);
         GZB_CUDA(ctx, cudaMemcpyAsync(h_err, ctx->d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (ctx->trace && ctx->ntrace > 0) {
+        cudaDeviceSynchronize();
+        for (int k = 0; k < ctx->ntrace; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->trace_ev[0], ctx->trace_ev[k]);
+            fprintf(stderr, "[gzb trace] %8.1f us  %s\n", 1e3 * ms, ctx->trace_name[k]);
+        }
+        ctx->ntrace = 0;
     }
     if (ctx->barrier_err_pending)
         GZB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 72, ctx->d_flags + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -969,6 +987,8 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
         if (ctx->hdg_mode == 0) { ctx->g.hdg = nullptr; ctx->hdg_built = 0; ctx->stats.heading_table = 0; }
         return GZB_OK;
     }
+    if (!strcmp(name, "trace")) { ctx->trace = value ? 1 : 0; ctx->ntrace = 0; return GZB_OK; }
+    if (!strcmp(name, "twin_chain")) { ctx->twin_chain = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "fuse_k4")) { ctx->fuse_k4 = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "overlap")) { ctx->overlap = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "k4_early")) { ctx->k4_early = value ? 1 : 0; return GZB_OK; }

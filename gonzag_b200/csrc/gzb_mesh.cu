@@ -146,6 +146,33 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
 
 __device__ __forceinline__ long long pywrap(long long k, long long n) { return k < 0 ? k + n : k; }
 
+// nearest point of track point t for the bulk kernels: from the NP array, or (gzb_mapping overlap, while
+// the chain logic still runs) E(t) derived from the plain global answer -- gonzag/bilin_mapping.py:169-190
+// threshold acceptance + :582-585 edge exclusion, as accept_edge() of gzb_nearest.cu
+__device__ __forceinline__ bool nearest_of(const GzbGrid& g, const long long* __restrict__ NP, const GzbGlobalNearest& gn,
+                                           const long long t, long long& jP, long long& iP) {
+    if (NP) {
+        jP = NP[2 * t];
+        iP = NP[2 * t + 1];
+        return true;
+    }
+    const long long flat = gn.G[t];
+    if (flat == 0x7ffffffffffffffeLL) return false;      // not settled yet: left to the repair kernel
+    const double d = gn.dG[t];
+    if (flat != 0x7fffffffffffffffLL && d < gn.thr2) {
+        jP = flat / g.Ni;
+        iP = flat - jP * g.Ni;
+    } else {
+        jP = -1;
+        iP = -1;
+    }
+    if (gn.edge) {
+        if (iP == 0 || (iP == g.Ni - 1 && g.kew == -1)) { jP = -1; iP = -1; }
+        if (jP == 0 || jP == g.Nj - 1) { jP = -1; iP = -1; }
+    }
+    return true;
+}
+
 // bilinear weights of one point inside its source mesh (gonzag/bilin_mapping.py:490-527)
 __device__ __forceinline__ void weights_one(const GzbGrid& g, const double yT, const double xT,
                                             const long long* cj, const long long* ci, double* w) {
@@ -207,13 +234,14 @@ k_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, co
 // K2 + K3 in one pass (what gzb_mapping runs): the mesh never travels through HBM between them
 __global__ void __launch_bounds__(128)
 k_mesh_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-               const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
-               const int force_heavy) {
+               const long long* __restrict__ NP, const GzbGlobalNearest gn, long long* __restrict__ SM,
+               double* __restrict__ WB, const int force_heavy) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const double yT = yt[t], xT = xt[t];
-    long long cj[4], ci[4];
-    source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
+    long long cj[4], ci[4], jP, iP;
+    if (!nearest_of(g, NP, gn, t, jP, iP)) return;
+    source_mesh_one(g, yT, xT, jP, iP, force_heavy, cj, ci);
     longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
 #pragma unroll
     for (int k = 0; k < 4; ++k) sm[k] = make_longlong2(cj[k], ci[k]);
@@ -266,11 +294,14 @@ static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt) {
 }
 
 int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
-                         int64_t* sm_out, double* wb_out) {
+                         int64_t* sm_out, double* wb_out, const GzbGlobalNearest* gn_or_null) {
     if (nt <= 0) return GZB_OK;
     if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
-    k_mesh_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
-                                                                         (long long*)sm_out, wb_out, ctx->force_heavy);
+    GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0};
+    const long long* npp = (const long long*)np;
+    if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
+    k_mesh_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out,
+                                                                         wb_out, ctx->force_heavy);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }
@@ -298,10 +329,12 @@ __global__ void __launch_bounds__(64)
 k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
            const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
            const long long* __restrict__ list, const unsigned long long* __restrict__ count,
+           const long long* __restrict__ list2, const unsigned long long* __restrict__ count2,
            const int force_heavy, const InterpArgs ia) {
-    const long long n = (long long)*count;
+    const long long n1 = (long long)*count;
+    const long long n = n1 + (list2 ? (long long)*count2 : 0);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-        const long long t = list[e];
+        const long long t = e < n1 ? list[e] : list2[e - n1];
         const double yT = yt[t], xT = xt[t];
         long long cj[4], ci[4];
         source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
@@ -336,13 +369,14 @@ static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt);
 template <typename T>
 __global__ void __launch_bounds__(128)
 k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-                      const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
-                      const int force_heavy, const InterpArgs ia) {
+                      const long long* __restrict__ NP, const GzbGlobalNearest gn, long long* __restrict__ SM,
+                      double* __restrict__ WB, const int force_heavy, const InterpArgs ia) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const double yT = yt[t], xT = xt[t];
-    long long cj[4], ci[4];
-    source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
+    long long cj[4], ci[4], jP, iP;
+    if (!nearest_of(g, NP, gn, t, jP, iP)) return;
+    source_mesh_one(g, yT, xT, jP, iP, force_heavy, cj, ci);
     longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
     longlong2 rp[4];
 #pragma unroll
@@ -372,7 +406,7 @@ static void fill_interp_args(gzb_ctx* ctx, InterpArgs& ia, const double* tt, int
 }
 
 int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
-                                int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
+                                const GzbGlobalNearest* gn_or_null, int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
                                 const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss, double* vnp_out,
                                 double* vbl_out) {
     if (nt <= 0) return GZB_OK;
@@ -380,12 +414,15 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     InterpArgs ia;
     fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
     const unsigned nblk = (unsigned)((nt + 127) / 128);
+    GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0};
+    const long long* npp = (const long long*)np;
+    if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
     if (dtype == GZB_F32)
-        k_mesh_weights_interp<float><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
-                                                                    (long long*)sm_out, wb_out, ctx->force_heavy, ia);
+        k_mesh_weights_interp<float><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out, wb_out,
+                                                                    ctx->force_heavy, ia);
     else
-        k_mesh_weights_interp<double><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
-                                                                     (long long*)sm_out, wb_out, ctx->force_heavy, ia);
+        k_mesh_weights_interp<double><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out, wb_out,
+                                                                     ctx->force_heavy, ia);
     GZB_LAUNCH_CHECK(ctx);
     ctx->time_err_pending = 1;
     return GZB_OK;
@@ -393,13 +430,14 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
 
 // mapping only (gzb_mapping) when slab_dev == nullptr, mapping + interpolation (gzb_map_interp) otherwise
 int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int64_t* np, int64_t* sm_out,
-                     double* wb_out, const long long* list, const unsigned long long* count, const double* tt,
+                     double* wb_out, const long long* list, const unsigned long long* count, const long long* list2,
+                     const unsigned long long* count2, const double* tt,
                      int64_t nrec, const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk,
                      double rmiss, double* vnp_out, double* vbl_out) {
     InterpArgs ia;
     fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
-    k_path_fix<<<128, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
-                                           ctx->force_heavy, ia);
+    k_path_fix<<<192, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
+                                           list2, count2, ctx->force_heavy, ia);
     GZB_LAUNCH_CHECK(ctx);
     if (slab_dev) ctx->time_err_pending = 1;
     return GZB_OK;

@@ -17,7 +17,8 @@
 //              reference's own fp64 haversine formula (32 candidates at a time, one per lane)
 //              and the winner is the lexicographic minimum (distance, row-major index), i.e.
 //              numpy.argmin's first occurrence.
-//   k_flags    speculative chain: R(t) = E(t) (edge-excluded, threshold-accepted G(t)) whenever
+//   k_chain    (called "k_flags" in older notes)
+//              speculative chain: R(t) = E(t) (edge-excluded, threshold-accepted G(t)) whenever
 //              G(t) lies inside the search box of E(t-1); the other points are "breaks".
 //   k_walk     K1c: one warp per break replays the reference's recurrence R(t) = F_t(R(t-1))
 //              with the true box-restricted search (the (2r+1)^2 window, clamped not wrapped,
@@ -26,6 +27,7 @@
 #include "gzb_common.cuh"
 
 #define GZB_NOFLAT 0x7fffffffffffffffLL
+#define GZB_UNRESOLVED 0x7ffffffffffffffeLL   /* G[t] until k_near_slow settles the point (bulk kernels skip it) */
 #define GZB_QCAP 64
 #define GZB_KCAP 64      // kept leaf tiles of one box scan
 #define GZB_BOX_MAXT 4096 // largest box (in leaf tiles) scanned flat; larger boxes descend the pyramid
@@ -82,6 +84,8 @@ struct NearParams {
     int edge;          // apply the edge exclusion of BilinTrack.nrpt
     long long seed_j, seed_i;
     const double* corner;   // bounding sphere (cx,cy,cz,rho) of the box of predecessor (-1,-1)
+    const unsigned char* rowsafe;   // per grid row: 1 = the only exact copies of its first k_ew_per cells are
+                                    // their East-West twins (null: no twin shortcut)
 };
 
 // fp32 error budget (see DESIGN.md "K1 numerics"): a stored coordinate is within 6e-8 of the
@@ -680,26 +684,29 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
         if (unresolved) {
             ulist[base + __popc(um & ((1u << lane) - 1u))] = t;
             hint[t] = myhint;
+            G[t] = GZB_UNRESOLVED;
         }
     }
 }
 
 // K1, slow path: the warp-cooperative search (seeded window, then pyramid) for the listed points.
 // A warp takes K list entries at a time (K chosen so that every warp of the grid has work).
-__global__ void __launch_bounds__(256)
+// small blocks (SLOW_WARPS warps): they must find room on SMs that the bulk kernels of gzb_mapping fill
+#define SLOW_WARPS 2
+__global__ void __launch_bounds__(32 * SLOW_WARPS)
 k_near_slow(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
             long long* __restrict__ G, double* __restrict__ dG, const long long* __restrict__ ulist,
             const unsigned* __restrict__ hint, const unsigned long long* __restrict__ ucount) {
-    __shared__ WarpSm ws[8];
+    __shared__ WarpSm ws[SLOW_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSm& w = ws[warp];
     const long long nu = (long long)*ucount;
     if (nu <= 0) return;
-    const long long nwarps = (long long)gridDim.x * 8;
+    const long long nwarps = (long long)gridDim.x * SLOW_WARPS;
     long long K = (nu + nwarps - 1) / nwarps;
     K = K < 1 ? 1 : (K > 32 ? 32 : K);
     const long long nchunk = (nu + K - 1) / K;
-    for (long long ch = (long long)blockIdx.x * 8 + warp; ch < nchunk; ch += nwarps) {
+    for (long long ch = (long long)blockIdx.x * SLOW_WARPS + warp; ch < nchunk; ch += nwarps) {
         const long long u0 = ch * K;
         const int n = (int)((nu - u0 < K) ? (nu - u0) : K);
         Owner me;
@@ -799,52 +806,211 @@ __device__ __forceinline__ bool clamp_box(const GzbGrid& g, const long long pj, 
     return (j0 < j1) && (i0 < i1);
 }
 
-// K1c, step 1: speculative chain + break detection.  One thread per point; G/dG are final
-// (k_near_search / k_near_slow or k_global wrote them).
+// K1c, step 1: the speculative chain and its breaks.
+//
+// The reference's R(t) = F_t(R(t-1)) depends on the predecessor only through its search box.  Two
+// values of R(t) can be written down without any search:
+//   E(t)  the global answer (edge-excluded, threshold-accepted G(t)): it is R(t) whenever G(t) lies in
+//         the box of the predecessor (DESIGN.md, K1 key fact), or when there is no box at all;
+//   T(t)  the East-West twin of G(t), when G(t) sits in one of the first k_ew_per columns, its copy
+//         k_ew_per columns before the eastern edge has bit-identical coordinates (so the very same
+//         distance) and d < r0: it is R(t) whenever G(t) is NOT in the box but the twin is -- the box
+//         pass then finds the twin, at the global minimum distance, and accepts it.  (No third exact
+//         copy can precede the twin in the box: it would have to sit in the same row between the two,
+//         which `rowsafe` excludes.)
+// A track crossing the seam eastwards is a long run of T(t)'s, each one depending on its predecessor
+// being T(t-1): a two-state chain.  So every point gets a transition code -- what F_t gives from
+// predecessor E(t-1) and from predecessor T(t-1): 0 = E(t), 1 = T(t), 2 = "needs a search" -- and the
+// states are resolved for the whole track by a parallel scan of function compositions.  Points that
+// come out as 2 are the breaks (speculation goes on from E(t) there); the replays (k_walk) start from
+// the speculative predecessor and run until they meet the speculative chain again.
 #define FLAGS_BLOCK 256
-__global__ void __launch_bounds__(FLAGS_BLOCK)
-k_flags(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
-        const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
-        long long* __restrict__ NP, unsigned char* __restrict__ brk, int* __restrict__ counts) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int isb = 0;
-    if (t < nt) {
-        const long long f = G[t];
-        const double d = dG[t];
-        long long ej, ei;
-        accept_edge(g, f, d, p.thr2, ej, ei, p.edge);
-        reinterpret_cast<longlong2*>(NP)[t] = make_longlong2(ej, ei);
-        long long pj, pi;
-        if (t == 0) {
-            pj = p.seed_j;
-            pi = p.seed_i;
-        } else {
-            accept_edge(g, G[t - 1], dG[t - 1], p.thr2, pj, pi, p.edge);
+
+__device__ __forceinline__ bool twin_of(const GzbGrid& g, const NearParams& p, const long long flat, const double d,
+                                        long long& tw) {
+    if (g.kew <= 0 || !p.rowsafe || flat == GZB_NOFLAT || !(d < p.r0)) return false;
+    long long j, i;
+    gzb_split(g, flat, j, i);
+    if (i >= g.kew || !p.rowsafe[j]) return false;
+    tw = flat + (g.Ni - g.kew);
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(g.ll) + flat);
+    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(g.ll) + tw);
+    return a.x == b.x && a.y == b.y;
+}
+
+// what the reference's step gives for point t from predecessor (pj, pi), as far as it can be told
+// without a search: 0 = E(t), 1 = T(t), 2 = unknown
+__device__ __forceinline__ int step_code(const GzbGrid& g, const NearParams& p, const long long pj, const long long pi,
+                                         const long long gflat, const bool tvalid, const long long tw,
+                                         const double yT, const double xT) {
+    if (pj == 0 || pi == 0) return 0;           // Python truthiness of (j_prv and i_prv): no box
+    long long j0, j1, i0, i1;
+    if (!clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) return 0;
+    if (gflat != GZB_NOFLAT) {
+        long long gj, gi;
+        gzb_split(g, gflat, gj, gi);
+        if (gj >= j0 && gj < j1 && gi >= i0 && gi < i1) return 0;
+        if (tvalid) {
+            const long long tj = gj, ti = gi + (g.Ni - g.kew);
+            if (tj >= j0 && tj < j1 && ti >= i0 && ti < i1) return 1;
         }
-        if (pj != 0 && pi != 0) {   // Python truthiness of (j_prv and i_prv)
-            long long j0, j1, i0, i1;
-            if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
-                long long gj = 0, gi = 0;
-                if (f != GZB_NOFLAT) gzb_split(g, f, gj, gi);
-                const bool inside = (f != GZB_NOFLAT) && gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
-                if (!inside) {
-                    isb = 1;
-                    if (pj == -1 && pi == -1 && p.corner[3] >= 0.0) {
-                        // the box of a not-found predecessor is the grid corner [0,r)^2: if even
-                        // its bounding sphere is farther than r0 the box pass cannot accept
-                        const double la = yt[t] * GZB_D2R, lo = xt[t] * GZB_D2R;
-                        const double cl = cos(la);
-                        const double dx = cl * cos(lo) - p.corner[0], dy = cl * sin(lo) - p.corner[1],
-                                     dz = sin(la) - p.corner[2];
-                        if (sqrt(dx * dx + dy * dy + dz * dz) - p.corner[3] > p.chord_r0) isb = 0;
-                    }
-                }
+    }
+    if (pj == -1 && pi == -1 && p.corner[3] >= 0.0) {
+        // the box of a not-found predecessor is the grid corner [0,r)^2: if even its bounding sphere
+        // is farther than r0 the box pass cannot accept
+        const double la = yT * GZB_D2R, lo = xT * GZB_D2R;
+        const double cl = cos(la);
+        const double dx = cl * cos(lo) - p.corner[0], dy = cl * sin(lo) - p.corner[1], dz = sin(la) - p.corner[2];
+        if (sqrt(dx * dx + dy * dy + dz * dz) - p.corner[3] > p.chord_r0) return 0;
+    }
+    return 2;
+}
+
+// a map {0,1} -> {0,1} in two bits (bit s = image of s); composition "first f, then h"
+__device__ __forceinline__ unsigned fn_then(const unsigned f, const unsigned h) {
+    return ((h >> (f & 1u)) & 1u) | (((h >> ((f >> 1) & 1u)) & 1u) << 1);
+}
+#define FN_ID 2u
+
+// inclusive scan of compositions over the block; returns this thread's prefix (maps the state that
+// enters the block to the state that LEAVES this thread's point); total = the whole block's map
+__device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned* sh /* [FLAGS_BLOCK/32] */, unsigned& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned f = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, f, o);
+        if (lane >= o) f = fn_then(u, f);
+    }
+    if (lane == 31) sh[warp] = f;
+    __syncthreads();
+    unsigned pre = FN_ID;
+    for (int q = 0; q < warp; ++q) pre = fn_then(pre, sh[q]);
+    total = pre;
+    for (int q = warp; q < FLAGS_BLOCK / 32; ++q) total = fn_then(total, sh[q]);
+    __syncthreads();
+    return fn_then(pre, f);
+}
+
+// One pass: transition code of every point (what F_t gives from predecessor E(t-1) and from
+// predecessor T(t-1)), composed map of the block, state entering the block by a decoupled look-back
+// over the maps the earlier blocks published (a map that sends both states to the same one -- any
+// block away from the seam -- ends the look-back, so its depth is almost always one), then the
+// speculative chain, the break flags and the per-block break counts.  Blocks take their index from a
+// ticket, so a block only ever waits for blocks that already started.
+__global__ void __launch_bounds__(FLAGS_BLOCK)
+k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
+        const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
+        long long* __restrict__ NP, unsigned char* __restrict__ brk, int* __restrict__ counts,
+        volatile unsigned* agg, unsigned* __restrict__ ticket, long long* __restrict__ chg,
+        unsigned long long* __restrict__ nchg) {
+    __shared__ unsigned sh[FLAGS_BLOCK / 32];
+    __shared__ unsigned last[FLAGS_BLOCK / 32];
+    __shared__ unsigned s_bid, s_entry;
+    if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const long long t = (long long)bid * blockDim.x + threadIdx.x;
+    unsigned c = 0, mine = FN_ID;
+    long long f = GZB_NOFLAT;
+    double d = 0.0;
+    if (t < nt) {
+        f = G[t];
+        d = dG[t];
+        long long tw = 0;
+        const bool tvalid = twin_of(g, p, f, d, tw);
+        int o0, o1;
+        const double yT = yt[t], xT = xt[t];
+        if (t == 0) {
+            o0 = o1 = step_code(g, p, p.seed_j, p.seed_i, f, tvalid, tw, yT, xT);
+        } else {
+            const long long pf = G[t - 1];
+            const double pd = dG[t - 1];
+            long long ej, ei;
+            accept_edge(g, pf, pd, p.thr2, ej, ei, p.edge);
+            o0 = step_code(g, p, ej, ei, f, tvalid, tw, yT, xT);
+            long long ptw = 0;
+            if (twin_of(g, p, pf, pd, ptw)) {
+                long long tj, ti;
+                accept_edge(g, ptw, pd, INFINITY, tj, ti, p.edge);
+                o1 = step_code(g, p, tj, ti, f, tvalid, tw, yT, xT);
+            } else {
+                o1 = o0;                 // the predecessor cannot be in the twin state
             }
         }
+        c = (unsigned)(o0 | (o1 << 2));
+        mine = (unsigned)((o0 == 1) ? 1 : 0) | ((unsigned)((o1 == 1) ? 1 : 0) << 1);     // 2 propagates as 0
+    }
+    unsigned total;
+    const unsigned incl = block_scan_fn(mine, sh, total);
+    if ((threadIdx.x & 31) == 31) last[threadIdx.x >> 5] = incl;
+    if (threadIdx.x == 0) {
+        agg[bid] = 0x100u | total;               // publish this block's map
+        __threadfence();
+        unsigned fmap = FN_ID;                   // map from the state entering block k+1 to the state entering this block
+        long long k = (long long)bid - 1;
+        while (k >= 0) {
+            unsigned v;
+            while (((v = agg[k]) & 0x100u) == 0u) __nanosleep(40);
+            const unsigned fk = v & 3u;
+            fmap = fn_then(fk, fmap);
+            if (fk == 0u || fk == 3u) break;     // constant map: nothing before block k matters
+            --k;
+        }
+        s_entry = fmap & 1u;                     // the track starts in state 0
+    }
+    __syncthreads();
+    const unsigned prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    unsigned before;          // map from the block's entry state to the state entering this point
+    if (threadIdx.x == 0) before = FN_ID;
+    else if ((threadIdx.x & 31) == 0) before = last[(threadIdx.x >> 5) - 1];
+    else before = prev;
+    const unsigned sin = (before >> s_entry) & 1u;
+    int isb = 0;
+    if (t < nt) {
+        const unsigned out = (c >> (2 * sin)) & 3u;
+        long long rj, ri;
+        if (out == 1u) {
+            accept_edge(g, f + (g.Ni - g.kew), d, INFINITY, rj, ri, p.edge);
+            if (chg) chg[atomicAdd(nchg, 1ull)] = t;      // differs from E(t): K2-K4 of this point are redone (gzb_mapping overlap)
+        } else {
+            accept_edge(g, f, d, p.thr2, rj, ri, p.edge);
+        }
+        reinterpret_cast<longlong2*>(NP)[t] = make_longlong2(rj, ri);
+        isb = out == 2u ? 1 : 0;
         brk[t] = (unsigned char)isb;
     }
-    const int c = __syncthreads_count(isb);
-    if (threadIdx.x == 0) counts[blockIdx.x] = c;
+    const int n = __syncthreads_count(isb);
+    if (threadIdx.x == 0) counts[bid] = n;
+}
+
+// per row: 1 = no cell strictly between a leading overlap cell and its East-West twin has that cell's
+// coordinates, and the row is not a pole (where every cell is the same point)
+__global__ void __launch_bounds__(256)
+k_rowsafe(const GzbGrid g, unsigned char* __restrict__ rowsafe) {
+    const long long j = blockIdx.x;
+    const int kew = g.kew < 8 ? g.kew : 8;
+    __shared__ long long sy[8], sx[8];
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    const longlong2* row = reinterpret_cast<const longlong2*>(g.ll) + j * g.Ni;
+    if (threadIdx.x < kew) {
+        const longlong2 c = row[threadIdx.x];
+        sy[threadIdx.x] = c.x;
+        sx[threadIdx.x] = c.y;
+    }
+    __syncthreads();
+    const long long P = g.Ni - g.kew;
+    int mybad = 0;
+    for (long long i = threadIdx.x; i < g.Ni; i += blockDim.x) {
+        const longlong2 c = row[i];
+        if (fabs(__longlong_as_double(c.x)) >= 90.0) mybad = 1;
+        for (int q = 0; q < kew; ++q)
+            if (i > q && i < q + P && c.x == sy[q] && c.y == sx[q]) mybad = 1;
+    }
+    if (mybad) atomicOr(&bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) rowsafe[j] = (g.kew > 8 || bad) ? 0 : 1;
 }
 
 // exclusive scan of the per-block break counts (single block): every thread sums a contiguous
@@ -913,7 +1079,7 @@ k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ o
 #define WLOG_TAG(k) ((unsigned long long)(((k) + 1) & 0x7ffffffLL) << 36)
 
 // warps (= replays) per block of k_walk; one-warp blocks were measured slower, alone and beside K2+K3
-#define WALK_WARPS 8
+#define WALK_WARPS 2
 template <bool WRITE>
 __global__ void __launch_bounds__(32 * WALK_WARPS)
 k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
@@ -976,8 +1142,9 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
         if (b == 0) {
             pj = p.seed_j;
             pi = p.seed_i;
-        } else {
-            accept_edge(g, G[b - 1], dG[b - 1], p.thr2, pj, pi, p.edge);
+        } else {                 // the speculative chain at b-1 (k_chain; an earlier valid replay ending there rejoined it)
+            pj = NP[2 * (b - 1)];
+            pi = NP[2 * (b - 1) + 1];
         }
         unsigned long long n = 0;
         bool done = false;
@@ -986,11 +1153,22 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
             Owner me;
             float mpx = 0.f, mpy = 0.f, mpz = 0.f;
             me.plat = me.plon = me.cpl = 0.0;
-            long long gf = GZB_NOFLAT, ej = -1, ei = -1;
+            long long gf = GZB_NOFLAT, ej = -1, ei = -1, sj = -1, si = -1, tj = -1, ti = -1;
+            int tv = 0;
             if (lane < nq) {
                 owner_point(yt[t0 + lane], xt[t0 + lane], me, mpx, mpy, mpz);
                 gf = G[t0 + lane];
-                accept_edge(g, gf, dG[t0 + lane], p.thr2, ej, ei, p.edge);
+                const double gd = dG[t0 + lane];
+                accept_edge(g, gf, gd, p.thr2, ej, ei, p.edge);
+                long long tw = 0;
+                if (twin_of(g, p, gf, gd, tw)) {          // T(t): see k_chain
+                    tv = 1;
+                    accept_edge(g, tw, gd, INFINITY, tj, ti, p.edge);
+                }
+                if (!WRITE) {                             // the speculative chain, to detect where the replay rejoins it
+                    sj = NP[2 * (t0 + lane)];
+                    si = NP[2 * (t0 + lane) + 1];
+                }
             }
             __syncwarp();
             w.bd[lane] = ~0ull;
@@ -1013,7 +1191,17 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                             gzb_split(g, qgf, gj, gi);
                             inside = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
                         }
-                        if (!inside) {
+                        bool twin_in = false;
+                        if (!inside && __shfl_sync(0xffffffffu, tv, q)) {
+                            long long gj, gi;
+                            gzb_split(g, qgf, gj, gi);
+                            gi += g.Ni - g.kew;
+                            twin_in = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
+                        }
+                        if (twin_in) {       // the box pass finds the twin of G(t), at the global minimum distance (< r0)
+                            rj = __shfl_sync(0xffffffffu, tj, q);
+                            ri = __shfl_sync(0xffffffffu, ti, q);
+                        } else if (!inside) {
                             Srch s;
                             srch_init(s, __shfl_sync(0xffffffffu, mpx, q), __shfl_sync(0xffffffffu, mpy, q),
                                       __shfl_sync(0xffffffffu, mpz, q));
@@ -1045,7 +1233,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
                             first[2 * k + 1] = ri;
                         }
                     }
-                    if ((rj == qej && ri == qei) || t + 1 >= nt) {
+                    if ((rj == __shfl_sync(0xffffffffu, sj, q) && ri == __shfl_sync(0xffffffffu, si, q)) || t + 1 >= nt) {
                         if (lane == 0) stop[k] = t;
                         done = true;
                         break;
@@ -1180,13 +1368,14 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
     const size_t nblk = (n + FLAGS_BLOCK - 1) / FLAGS_BLOCK;
     return gzb_align(n * 8) * 2      // G, dG
            + gzb_align(n)            // brk
+           + gzb_align((nblk + 1) * 4)   // published block maps + ticket
            + gzb_align(nblk * 4) + gzb_align(nblk * 8)   // counts, offsets
            + gzb_align(n * 8) * 2    // breaks, stop
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
            + gzb_align(n * 8)        // replay log
            + gzb_align(n * 8) + gzb_align(n * 4)   // unresolved list, hints
-           + gzb_align(n * 16)       // points changed by the replays (gzb_mapping overlap)
+           + gzb_align(n * 24)       // points whose nearest point differs from E(t): twin states + replay writes
            + gzb_align(64) * 2;      // scalars, corner
 }
 
@@ -1197,7 +1386,7 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
 // marks the end of the chain part.
 int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double rd_found_km,
                     int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out, bool split,
-                    const long long** chg_out, const unsigned long long** nchg_out) {
+                    const long long** chg_out, const unsigned long long** nchg_out, GzbGlobalNearest* gn_out) {
     if (nt <= 0) return GZB_OK;
     if (np_box_r < 0) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_nearest: np_box_r must be >= 0");
     const size_t n = (size_t)nt;
@@ -1205,6 +1394,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     long long* G = (long long*)gzb_arena_take(ctx, n * 8);
     double* dG = (double*)gzb_arena_take(ctx, n * 8);
     unsigned char* brk = (unsigned char*)gzb_arena_take(ctx, n);
+    unsigned* agg = (unsigned*)gzb_arena_take(ctx, ((size_t)nblk + 1) * 4);      // published block maps + the ticket
     int* counts = (int*)gzb_arena_take(ctx, (size_t)nblk * 4);
     long long* offsets = (long long*)gzb_arena_take(ctx, (size_t)nblk * 8);
     long long* breaks = (long long*)gzb_arena_take(ctx, n * 8);
@@ -1214,13 +1404,17 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
     long long* ulist = (long long*)gzb_arena_take(ctx, n * 8);
     unsigned* hint = (unsigned*)gzb_arena_take(ctx, n * 4);
-    long long* chg = (long long*)gzb_arena_take(ctx, n * 16);
+    long long* chg = (long long*)gzb_arena_take(ctx, n * 24);
     long long* scal = (long long*)gzb_arena_take(ctx, 64);
     if (!scal) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
     unsigned long long* nchg = (unsigned long long*)(scal + 7);
     if (!split) chg = nullptr;
     if (chg_out) *chg_out = chg;
     if (nchg_out) *nchg_out = nchg;
+    if (gn_out) {
+        gn_out->G = G; gn_out->dG = dG; gn_out->thr2 = 0.0; gn_out->edge = ctx->edge_exclusion;
+        gn_out->ulist = ulist; gn_out->ucount = (const unsigned long long*)(scal + 2);
+    }
     double* corner = (double*)(ctx->d_flags + 32);      // persistent: 4 doubles, keyed by np_box_r
     cudaStream_t s = ctx->stream;
 
@@ -1230,6 +1424,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     volatile double t2 = 1.2 * t1;
     p.r0 = r0;
     p.thr2 = t2;
+    if (gn_out) gn_out->thr2 = t2;
     const double half = r0 / (2.0 * 6360.0);
     const double sn = sin(half < 1.5 ? half : 1.5);
     p.prox_r0 = (float)(4.0 * sn * sn * (1.0 + 1.0e-5) + 1.0e-20);
@@ -1239,6 +1434,16 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     p.seed_j = seed_j;
     p.seed_i = seed_i;
     p.corner = corner;
+    p.rowsafe = nullptr;
+    if (ctx->twin_chain && ctx->g.kew > 0 && ctx->g.kew < ctx->g.Ni / 2) {
+        if (!ctx->d_rowsafe) GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_rowsafe, (size_t)ctx->g.Nj));
+        if (ctx->rowsafe_kew != ctx->g.kew) {
+            k_rowsafe<<<(unsigned)ctx->g.Nj, 256, 0, ctx->stream>>>(ctx->g, ctx->d_rowsafe);
+            GZB_LAUNCH_CHECK(ctx);
+            ctx->rowsafe_kew = ctx->g.kew;
+        }
+        p.rowsafe = ctx->d_rowsafe;
+    }
 
     GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 64, s));
     if (ctx->corner_r != np_box_r) {
@@ -1255,25 +1460,39 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     long long gblocks = (long long)(((n + K - 1) / K + 7) / 8);
     const long long gmax = (long long)nsm * 16;
     if (gblocks > gmax) gblocks = gmax;
+    cudaStream_t sb = s;
+    gzb_trace(ctx, s, "K1 start");
     if (ctx->nearest_path && ctx->g.cellv && ctx->g.lut.bins) {
         k_near_search<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ctx->g, nt, yt, xt, G, dG, ulist, hint,
                                                                  (unsigned long long*)(scal + 2));
         GZB_LAUNCH_CHECK(ctx);
-        k_near_slow<<<(unsigned)(nsm * 4), 256, 0, s>>>(ctx->g, yt, xt, G, dG, ulist, hint,
-                                                       (const unsigned long long*)(scal + 2));
+        // from here on everything is latency-bound (the warp search of the few unresolved points, then
+        // the chain): with `split` it goes to the auxiliary stream and the caller runs K2-K4 meanwhile on
+        // E(t) = the plain global answers, which it derives from G / dG itself, skipping the unresolved points
+        if (split) {
+            sb = ctx->aux_stream;
+            GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[0], s));
+            GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
+        }
+        gzb_trace(ctx, s, "search end (main)");
+        k_near_slow<<<(unsigned)(nsm * 32 / SLOW_WARPS), 32 * SLOW_WARPS, 0, sb>>>(ctx->g, yt, xt, G, dG, ulist, hint,
+                                                        (const unsigned long long*)(scal + 2));
         GZB_LAUNCH_CHECK(ctx);
+        gzb_trace(ctx, sb, "slow end");
     } else {
         k_global<<<(unsigned)gblocks, 256, 0, s>>>(ctx->g, nt, yt, xt, G, dG, K);
         GZB_LAUNCH_CHECK(ctx);
+        if (split) {
+            sb = ctx->aux_stream;
+            GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[0], s));
+            GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
+        }
     }
-    k_flags<<<(unsigned)nblk, FLAGS_BLOCK, 0, s>>>(ctx->g, p, nt, yt, xt, G, dG, (long long*)np_out, brk, counts);
+    GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 1) * sizeof(unsigned), sb));
+    k_chain<<<(unsigned)nblk, FLAGS_BLOCK, 0, sb>>>(ctx->g, p, nt, yt, xt, G, dG, (long long*)np_out, brk, counts, agg,
+                                                   agg + nblk, chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
-    cudaStream_t sb = s;
-    if (split) {
-        sb = ctx->aux_stream;
-        GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[0], s));
-        GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
-    }
+    gzb_trace(ctx, sb, "chain kernel end");
     k_scan_counts<<<1, SCAN_T, 0, sb>>>(counts, offsets, nblk, scal);
     GZB_LAUNCH_CHECK(ctx);
     k_compact<<<(unsigned)nblk, FLAGS_BLOCK, 0, sb>>>(brk, offsets, nt, breaks);
@@ -1285,12 +1504,14 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
                                                     valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1),
                                                     nullptr, nullptr);
     GZB_LAUNCH_CHECK(ctx);
+    gzb_trace(ctx, sb, "walk0 end");
     k_valid<<<1, 256, 0, sb>>>(breaks, stop, scal, valid, (long long*)(ctx->d_flags + 8));
     GZB_LAUNCH_CHECK(ctx);
     k_walk<true><<<(unsigned)wblocks, 32 * WALK_WARPS, 0, sb>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
                                                    valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1),
                                                    chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
+    gzb_trace(ctx, sb, "walk1 end (chain done)");
     if (split) GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[1], sb));
     ctx->nearest_stats_pending = 1;      // k_valid left (breaks, replay steps) in the persistent flags
     return GZB_OK;

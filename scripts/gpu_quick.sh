@@ -8,5 +8,6 @@ python - <<PY
 import json
 d=json.load(open("$OUT/bench_$TAG.json"))
 print("value %.4g pts/s  ms/step %.4f  launches %d" % (d["value"], d["ms_per_step"], d["gpu_launches"]))
-for k,v in d["kernels"].items(): print("  %-18s %.4f ms (min %.4f)  %.0f GB/s  frac %.3f" % (k, v["ms"], v.get("ms_min",0), v["achieved_gbs"], v["frac_of_hbm_peak"]))
+for k,v in d["kernels"].items():
+    if isinstance(v, dict): print("  %-18s %.4f ms (min %.4f)  %.0f GB/s  frac %.3f" % (k, v["ms"], v.get("ms_min",0), v["achieved_gbs"], v["frac_of_hbm_peak"]))
 PY

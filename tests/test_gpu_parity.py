@@ -352,3 +352,41 @@ def test_map_interp_matches_staged(golden_global):
                 assert np.array_equal(ctx.download(o[2], (n, 4), np.float64), WB)
                 assert np.array_equal(ctx.download(o[3], (n,), np.float64), v_np)
                 assert np.array_equal(ctx.download(o[4], (n,), np.float64), v_bl)
+
+
+def test_twin_chain_matches_replays(golden_global, golden_seam):
+    """The two-state speculative chain (East-West twins resolved by a scan) must give the nearest
+    points of the plain speculation + replays, and of the reference, while replaying far fewer steps."""
+    lat, lon = _grid(golden_global)
+    rd, r = float(golden_seam["rd"]), int(golden_seam["r"])
+    cases = [("seam", golden_seam["ysat"], golden_seam["xsat"], golden_seam["NP"])]
+    t, y, x = syn.orbit_track(60000, t0=7.0, **syn.JASON)
+    cases.append(("jason", y, x, None))
+    s_ = np.linspace(0, 1, 4000)                       # slow eastward drifts across the seam, both hemispheres
+    cases.append(("drift", np.concatenate([-60 + 120 * s_, 70 - 140 * s_]),
+                  np.mod(np.concatenate([352 + 14 * s_, 350 + 16 * s_]), 360.0), None))
+    for kew in (2, -1):
+        with gzb.GridContext(lat, lon, k_ew_per=kew) as ctx:
+            for name, yy, xx, want in cases:
+                ctx.set_option("twin_chain", 1)
+                a = ctx.nearest(yy, xx, rd, r)
+                sa = ctx.stats()
+                ctx.set_option("twin_chain", 0)
+                b = ctx.nearest(yy, xx, rd, r)
+                sb = ctx.stats()
+                _report_index_mismatch("NP[%s,kew=%d]" % (name, kew), a, b)
+                if want is not None and kew == 2:
+                    _report_index_mismatch("NP[%s] vs reference" % name, a, want)
+                if kew == 2:
+                    assert sa["last_chain_steps"] < sb["last_chain_steps"], (name, sa["last_chain_steps"], sb["last_chain_steps"])
+                    assert sa["last_max_chain"] <= sb["last_max_chain"]
+    # a grid whose overlap columns are NOT exact copies: no twin shortcut, same answers
+    lon2 = lon.copy()
+    lon2[:, 0] = np.mod(lon2[:, 0] + 1e-9, 360.0)
+    with gzb.GridContext(lat, lon2, k_ew_per=2) as ctx:
+        a = ctx.nearest(cases[2][1], cases[2][2], rd, r)
+        ctx.set_option("twin_chain", 0)
+        b = ctx.nearest(cases[2][1], cases[2][2], rd, r)
+    _report_index_mismatch("NP[inexact overlap]", a, b)
+    want = orc.nearest_chain(cases[2][1][:1500], cases[2][2][:1500], lat, lon2, 2, rd, r)
+    _report_index_mismatch("NP[inexact overlap] vs oracle", a[:1500], want)
