@@ -9,9 +9,8 @@ profiles/<round>_launches_C3.csv (+ .txt, the per-kernel share of one step) and 
 import csv, json, os, sys, collections
 
 raw, launches, rnd = sys.argv[1], sys.argv[2], sys.argv[3]
+extra_raw = sys.argv[4:]          # more raw exports (stand-alone stage kernels)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rows = list(csv.reader(open(raw)))
-hdr, units = rows[0], rows[1]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -23,23 +22,28 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
-idx = [(k, hdr.index(k)) for k in KEYS if k in hdr]
-ki = hdr.index("Kernel Name")
 out = ["# ncu --set full --clock-control none --import-source on, one launch of every kernel of a bench step",
        "#   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu   (C3: global ORCA12 3059x4322, 633122 track points)",
        "# caches are flushed before every profiled launch and launches are serialised: compare SHARES with the live run", ""]
 traffic = {}
-for r in rows[2:]:
-    name = r[ki].split("(")[0].replace("void ", "")
-    out.append("== " + name)
-    for k, i in idx:
-        out.append("  %-82s %16s %s" % (k, r[i], units[i]))
-    out.append("")
-    f = lambda k: float(r[hdr.index(k)].replace(",", ""))
-    u = lambda k: units[hdr.index(k)]
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    b = f("dram__bytes_read.sum") * scale[u("dram__bytes_read.sum")] + f("dram__bytes_write.sum") * scale[u("dram__bytes_write.sum")]
-    traffic.setdefault(name, []).append(b)
+scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+for path in [raw] + extra_raw:
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    idx = [(k, hdr.index(k)) for k in KEYS if k in hdr]
+    ki = hdr.index("Kernel Name")
+    if path != raw:
+        out += ["# ---- stand-alone stage kernel (per-stage table of bench.py): " + os.path.basename(path), ""]
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].replace("void ", "")
+        out.append("== " + name)
+        for k, i in idx:
+            out.append("  %-82s %16s %s" % (k, r[i], units[i]))
+        out.append("")
+        f = lambda k: float(r[hdr.index(k)].replace(",", ""))
+        u = lambda k: units[hdr.index(k)]
+        b_ = f("dram__bytes_read.sum") * scale[u("dram__bytes_read.sum")] + f("dram__bytes_write.sum") * scale[u("dram__bytes_write.sum")]
+        traffic.setdefault(name, []).append(b_)
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 open(os.path.join(ROOT, "profiles", rnd + "_kernels_ncu.txt"), "w").write("\n".join(out))
 
@@ -56,7 +60,8 @@ for r in lr[i0 + 1:]:
 ids = list(rec)
 starts = [k for k in ids if rec[k]["name"] == "k_near_search"]
 steps = [[k for k in ids if a_ <= k < b_] for a_, b_ in zip(starts[:-1], starts[1:])]
-step = [st for st in steps if any(rec[k]["name"].startswith("k_interp") for k in st)][-1]     # a whole K1-K4 step
+step = [st for st in steps if any(rec[k]["name"].startswith("k_mesh_weights_interp") for k in st)][-1]     # a whole K1-K4 step
+step = step[:[rec[k]["name"] for k in step].index("k_path_fix") + 1]
 tot = sum(rec[k]["gpu__time_duration.sum"] for k in step)
 txt = ["# one step of bench.py (C3) under `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
        "--clock-control none`: serialised, cold caches", "# kernel, duration us, share of the step, dram read MB, dram write MB"]
@@ -72,14 +77,16 @@ with open(os.path.join(ROOT, "profiles", rnd + "_launches_C3.csv"), "w") as f:
     for r in lr[i0 + 1:]:
         if len(r) > d and r[d].isdigit() and int(r[d]) in step:
             w.writerow(r)
-K1 = ["k_near_search", "k_near_slow", "k_flags", "k_scan_counts", "k_compact", "k_walk<0>", "k_valid", "k_walk<1>"]
+K1 = ["k_near_search", "k_near_slow", "k_chain", "k_scan_counts", "k_compact", "k_walk<0>", "k_valid", "k_walk<1>"]
 per = {k: sum(v) / len(v) for k, v in traffic.items()}
 for k in step:      # kernels the full capture did not include: take the launch list's counters
     e = rec[k]
     per.setdefault(e["name"], e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0))
 stage = {"K1_nearest": sum(per.get(k, 0.0) for k in K1), "K2K3_mesh_weights": per.get("k_mesh_weights", 0.0),
          "K4_interp_gather": per.get("k_interp<float, 0>", per.get("k_interp<float, 1>", 0.0))}
-stage["K1-K4_path"] = stage["K1_nearest"] + stage["K2K3_mesh_weights"] + stage["K4_interp_gather"] + per.get("k_path_fix", 0.0)
+stage["K2K3K4_bulk"] = per.get("k_mesh_weights_interp<float>", 0.0)
+stage["K1-K4_path"] = stage["K1_nearest"] + stage["K2K3K4_bulk"] + per.get("k_path_fix", 0.0)
+stage["K1K2K3_mapping"] = stage["K1_nearest"] + stage["K2K3_mesh_weights"]
 json.dump({"source": os.path.basename(raw), "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
            "kernels": per, **stage}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print("\n".join(txt))
