@@ -1,5 +1,6 @@
 // Context management, the bounding-sphere pyramid over the model grid, and K0 (grid angle).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <new>
@@ -806,7 +807,8 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
         {   // the chain part of K1 is latency-bound and small: it must get SM slots ahead of the bulk kernels
             int least = 0, greatest = 0;
             CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-            CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, greatest));
+            const char* pr = getenv("GZB_AUX_PRIORITY");          // experiment knob: 0 = same priority as the bulk stream
+            CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, (pr && pr[0] == '0') ? least : greatest));
         }
         CK(cudaEventCreateWithFlags(&ctx->ev_k1[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_k1[1], cudaEventDisableTiming));

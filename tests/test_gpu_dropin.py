@@ -120,3 +120,36 @@ def test_frame_switch_on_device():
         np.testing.assert_array_equal(out, xb)
         NP = ctx.nearest(np.array([11.1]), np.array([-0.8]), 200.0, 2)      # the context now lives in that frame
         assert NP.tolist() == [[1, 1]] or NP.tolist() == [[-1, -1]]
+
+
+def test_multi_mission_on_one_resident_grid(golden_grid):
+    """BASELINE config 5 in small: several missions mapped onto ONE model grid kept on the GPU
+    (`ModGrid.ctx`): each mission gets exactly what a fresh grid context gives it."""
+    import types
+    from gonzag_b200 import synthetic as syn
+    g = golden_grid
+    model, track, lsm, varlsm, dist, Np = grid_case_sources(g, "a")
+    (it1, it2), _ = gz.GetEpochTimeOverlap(track, model)
+    MG = gz.ModGrid(model, it1, it2, lsm, varlsm, distorded_grid=dist)
+    try:
+        missions = []
+        for k, orb in enumerate((syn.SARAL, syn.JASON, syn.SARAL)):
+            t, y, x = syn.orbit_track(9000, t0=1500.0 + 700.0 * k, **orb)
+            t = t + float(model.time[0])
+            missions.append(types.SimpleNamespace(size=len(t), lat=y, lon=x, time=t, file="mem", jt1=0, jt2=0, keepit=[],
+                                                  ssh=np.zeros(len(t))))
+        n0 = MG.ctx.stats()["kernel_launches"]
+        shared = [gz.Model2SatTrack(MG, "ssh", ST, "ssh") for ST in missions]
+        assert MG.ctx.stats()["kernel_launches"] - n0 < 3 * 40       # the path only: no grid upload, no pyramid / certificate build
+        for ST, R in zip(missions, shared):
+            fresh = types.SimpleNamespace(shape=MG.shape, HResDeg=MG.HResDeg, lat=MG.lat, lon=MG.lon, xangle=MG.xangle,
+                                          EWPer=MG.EWPer, time=MG.time, file="mem", mask=MG.mask,
+                                          field=model.fields["ssh"])
+            R2 = gz.Model2SatTrack(fresh, "ssh", ST, "ssh")
+            np.testing.assert_array_equal(R.BT.NP, R2.BT.NP)
+            np.testing.assert_array_equal(R.BT.SM, R2.BT.SM)
+            np.testing.assert_array_equal(R.BT.WB, R2.BT.WB)
+            np.testing.assert_array_equal(np.ma.getdata(R.ssh_mod), np.ma.getdata(R2.ssh_mod))
+            np.testing.assert_array_equal(R.mask, R2.mask)
+    finally:
+        MG.close()
