@@ -566,8 +566,8 @@ k_lut_fill(const GzbLut L, const unsigned* __restrict__ in, unsigned* __restrict
     out[k] = v;
 }
 
-// Per-cell certificate (GzbGrid::cellv[].w): a lower bound of the chord from cell c to every
-// cell OUTSIDE its 5x5 index neighbourhood.  One warp per leaf tile T, lane = cell of T:
+// Per-cell certificates (GzbGrid::cellv[].w, two bfloat16): lower bounds of the chord from cell c to
+// every cell OUTSIDE its 5x5 index neighbourhood, and outside its 3x3 one.  One warp per leaf tile T, lane = cell of T:
 //   cells inside T's 5x3-tile window  -> evaluated one by one (tiles too far to matter skipped);
 //   cells outside that window         -> cert(T) - |c - centre(T)|   (triangle inequality).
 __global__ void __launch_bounds__(256)
@@ -592,6 +592,7 @@ k_cellcert(const GzbGrid g, float4* __restrict__ cellv) {
         far = g.cert[tidx] - (a * (1.0f + 2.0e-7f) + 5.0e-7f);
     }
     float m2 = INFINITY;     // smallest chord^2 to a window cell outside the 5x5 neighbourhood
+    float m3 = INFINITY;     // ... outside the 3x3 neighbourhood (m3 <= m2)
     // nearest tiles first, so that the far ones can be skipped
     const int order_j[5] = {0, -1, 1, -2, 2};
     const int order_i[3] = {0, -1, 1};
@@ -618,16 +619,22 @@ k_cellcert(const GzbGrid g, float4* __restrict__ cellv) {
                 const int64_t qj = qj0 + (k >> 3), qi = qi0 + (k & 7);
                 const int64_t aj = qj - j, ai = qi - i;
                 const bool inside = (aj >= -2) && (aj <= 2) && (ai >= -2) && (ai <= 2);
+                const bool inside3 = (aj >= -1) && (aj <= 1) && (ai >= -1) && (ai <= 1);
                 const float dx = x - ux, dy = y - uy, dz = z - uz;
                 const float d2 = dx * dx + dy * dy + dz * dz;     // padded cells sit at 1e3: never the minimum
                 if (!inside) m2 = fminf(m2, d2);
+                if (!inside3) m3 = fminf(m3, d2);
             }
         }
     }
     if (ok) {
         float v = fminf(far, sqrtf(m2) - 5.0e-7f) * (1.0f - 1.0e-6f);
         if (!(v > 0.0f)) v = 0.0f;        // also catches NaN
-        cellv[j * g.Ni + i].w = v;
+        float v3 = fminf(far, sqrtf(m3) - 5.0e-7f) * (1.0f - 1.0e-6f);
+        if (!(v3 > 0.0f)) v3 = 0.0f;
+        // both certificates in one word, each truncated (towards zero: still a lower bound) to bfloat16:
+        // high half = 3x3 certificate, low half = 5x5 certificate
+        cellv[j * g.Ni + i].w = __uint_as_float((__float_as_uint(v3) & 0xffff0000u) | (__float_as_uint(v) >> 16));
     }
 }
 

@@ -454,7 +454,8 @@ k_global(const GzbGrid g, const long long nt, const double* __restrict__ yt, con
 //   seed   the lat-lon look-up table gives a cell lying in (or next to) the point's bin;
 //   climb  evaluate the 5x5 index neighbourhood of the current cell (fp32 chord^2 from the
 //          row-major float4 array), move to its best cell, until the centre itself is the best;
-//   prove  cellv[c].w bounds from below the chord from c to every cell outside its 5x5
+//   prove  (3x3 certificate first: when it already holds, the ring is never loaded)
+//          cellv[c].w bounds from below the chord from c to every cell outside its 5x5
 //          neighbourhood, so  w - |p - c| > B  proves that no outside cell can tie or beat the
 //          best inside one (B = the fp32 candidate bound, as in the warp search);
 //   exact  the winner (and any other cell within the fp32 margin) goes through the reference's
@@ -624,7 +625,7 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
                 const unsigned nj4 = g.Nj > 4 ? (unsigned)(g.Nj - 4) : 0u, ni4 = g.Ni > 4 ? (unsigned)(g.Ni - 4) : 0u;
                 const unsigned nj2 = (unsigned)(g.Nj - 2), ni2 = (unsigned)(g.Ni - 2);     // Nj, Ni >= 3
                 float Pc = 0.0f, cw = 0.0f, nb8 = INFINITY, ring = INFINITY;
-                bool conv = false;
+                bool conv = false, proven3 = false;
                 int moves = 0;
                 for (;;) {
                     // climb on 3x3 neighbourhoods; the lanes of a warp leave this loop together, so
@@ -637,6 +638,17 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
                         inner = (unsigned)(j - 1) < nj2 && (unsigned)(i - 1) < ni2;
                     }
                     if (moves >= FAST_MAXIT) break;
+                    {   // the centre is the best cell of its 3x3 neighbourhood: its 3x3 certificate may already
+                        // prove that nothing farther away in index space can tie or beat it (no ring needed)
+                        const float a = sqrtf(Pc);
+                        const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
+                        const float w3 = __uint_as_float(__float_as_uint(cw) & 0xffff0000u);
+                        if ((w3 - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
+                            proven3 = true;
+                            conv = true;
+                            break;
+                        }
+                    }
                     const bool interior = (unsigned)(j - 2) < nj4 && (unsigned)(i - 2) < ni4;
                     const int moved = interior ? fast_ring<false>(g, px, py, pz, j, i, Pc, ring)
                                                : fast_ring<true>(g, px, py, pz, j, i, Pc, ring);
@@ -650,7 +662,8 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
                     reason = 3;
                     const float a = sqrtf(Pc);
                     const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
-                    if ((cw - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
+                    const float w5 = __uint_as_float(__float_as_uint(cw) << 16);
+                    if (proven3 || (w5 - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
                         reason = 0;
                         out = f | ((fminf(nb8, ring) <= B * B) ? CAND_MULTI : 0LL);
                     }
