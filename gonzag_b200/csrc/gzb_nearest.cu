@@ -851,27 +851,65 @@ __device__ __forceinline__ bool twin_of(const GzbGrid& g, const NearParams& p, c
     return a.x == b.x && a.y == b.y;
 }
 
+// what the chain logic needs to know about one point: G(t) split, E(t), T(t)
+struct PointSum {
+    int gj, gi;       // G(t), (-1,-1) if none
+    int ej, ei;       // E(t)
+    int tj, ti;       // T(t); tv == 0: no twin state
+    int tv;
+};
+
+__device__ __forceinline__ void point_sum(const GzbGrid& g, const NearParams& p, const long long flat, const double d,
+                                          PointSum& q) {
+    q.gj = q.gi = q.ej = q.ei = q.tj = q.ti = -1;
+    q.tv = 0;
+    if (flat == GZB_NOFLAT || flat == GZB_UNRESOLVED) return;
+    long long j, i;
+    gzb_split(g, flat, j, i);
+    q.gj = (int)j;
+    q.gi = (int)i;
+    if (d < p.thr2) { q.ej = q.gj; q.ei = q.gi; }
+    if (p.edge) {
+        if (q.ei == 0 || (q.ei == g.Ni - 1 && g.kew == -1)) { q.ej = -1; q.ei = -1; }
+        if (q.ej == 0 || q.ej == g.Nj - 1) { q.ej = -1; q.ei = -1; }
+    }
+    if (g.kew > 0 && p.rowsafe && i < g.kew && d < p.r0 && p.rowsafe[j]) {
+        const long long tw = flat + (g.Ni - g.kew);
+        const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(g.ll) + flat);
+        const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(g.ll) + tw);
+        if (a.x == b.x && a.y == b.y) {
+            q.tv = 1;
+            q.tj = q.gj;
+            q.ti = q.gi + (int)(g.Ni - g.kew);
+            if (p.edge) {        // the twin column is never column 0; the last column only counts without periodicity
+                if (q.tj == 0 || q.tj == g.Nj - 1) { q.tj = -1; q.ti = -1; }
+            }
+        }
+    }
+}
+
 // what the reference's step gives for point t from predecessor (pj, pi), as far as it can be told
 // without a search: 0 = E(t), 1 = T(t), 2 = unknown
-__device__ __forceinline__ int step_code(const GzbGrid& g, const NearParams& p, const long long pj, const long long pi,
-                                         const long long gflat, const bool tvalid, const long long tw,
-                                         const double yT, const double xT) {
+__device__ __forceinline__ int step_code(const GzbGrid& g, const NearParams& p, const int pj, const int pi,
+                                         const PointSum& q, const double* __restrict__ yt, const double* __restrict__ xt,
+                                         const long long t) {
     if (pj == 0 || pi == 0) return 0;           // Python truthiness of (j_prv and i_prv): no box
-    long long j0, j1, i0, i1;
-    if (!clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) return 0;
-    if (gflat != GZB_NOFLAT) {
-        long long gj, gi;
-        gzb_split(g, gflat, gj, gi);
-        if (gj >= j0 && gj < j1 && gi >= i0 && gi < i1) return 0;
-        if (tvalid) {
-            const long long tj = gj, ti = gi + (g.Ni - g.kew);
-            if (tj >= j0 && tj < j1 && ti >= i0 && ti < i1) return 1;
+    const int j0 = pj - p.r > 0 ? pj - p.r : 0;
+    const int j1 = (long long)pj + p.r + 1 < g.Nj ? pj + p.r + 1 : (int)g.Nj;
+    const int i0 = pi - p.r > 0 ? pi - p.r : 0;
+    const int i1 = (long long)pi + p.r + 1 < g.Ni ? pi + p.r + 1 : (int)g.Ni;
+    if (!(j0 < j1 && i0 < i1)) return 0;
+    if (q.gj >= 0) {
+        if (q.gj >= j0 && q.gj < j1 && q.gi >= i0 && q.gi < i1) return 0;
+        if (q.tv) {
+            const int ti = q.gi + (int)(g.Ni - g.kew);      // the twin cell itself (before the edge rule)
+            if (q.gj >= j0 && q.gj < j1 && ti >= i0 && ti < i1) return 1;
         }
     }
     if (pj == -1 && pi == -1 && p.corner[3] >= 0.0) {
         // the box of a not-found predecessor is the grid corner [0,r)^2: if even its bounding sphere
         // is farther than r0 the box pass cannot accept
-        const double la = yT * GZB_D2R, lo = xT * GZB_D2R;
+        const double la = yt[t] * GZB_D2R, lo = xt[t] * GZB_D2R;
         const double cl = cos(la);
         const double dx = cl * cos(lo) - p.corner[0], dy = cl * sin(lo) - p.corner[1], dz = sin(la) - p.corner[2];
         if (sqrt(dx * dx + dy * dy + dz * dz) - p.corner[3] > p.chord_r0) return 0;
@@ -925,31 +963,30 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     const unsigned bid = s_bid;
     const long long t = (long long)bid * blockDim.x + threadIdx.x;
     unsigned c = 0, mine = FN_ID;
-    long long f = GZB_NOFLAT;
-    double d = 0.0;
+    __shared__ int sE[FLAGS_BLOCK][2], sT[FLAGS_BLOCK][3];
+    PointSum q;
+    q.gj = q.gi = q.ej = q.ei = q.tj = q.ti = -1;
+    q.tv = 0;
+    if (t < nt) point_sum(g, p, G[t], dG[t], q);
+    sE[threadIdx.x][0] = q.ej; sE[threadIdx.x][1] = q.ei;
+    sT[threadIdx.x][0] = q.tj; sT[threadIdx.x][1] = q.ti; sT[threadIdx.x][2] = q.tv;
+    __syncthreads();
     if (t < nt) {
-        f = G[t];
-        d = dG[t];
-        long long tw = 0;
-        const bool tvalid = twin_of(g, p, f, d, tw);
         int o0, o1;
-        const double yT = yt[t], xT = xt[t];
         if (t == 0) {
-            o0 = o1 = step_code(g, p, p.seed_j, p.seed_i, f, tvalid, tw, yT, xT);
+            o0 = o1 = step_code(g, p, (int)p.seed_j, (int)p.seed_i, q, yt, xt, t);
         } else {
-            const long long pf = G[t - 1];
-            const double pd = dG[t - 1];
-            long long ej, ei;
-            accept_edge(g, pf, pd, p.thr2, ej, ei, p.edge);
-            o0 = step_code(g, p, ej, ei, f, tvalid, tw, yT, xT);
-            long long ptw = 0;
-            if (twin_of(g, p, pf, pd, ptw)) {
-                long long tj, ti;
-                accept_edge(g, ptw, pd, INFINITY, tj, ti, p.edge);
-                o1 = step_code(g, p, tj, ti, f, tvalid, tw, yT, xT);
-            } else {
-                o1 = o0;                 // the predecessor cannot be in the twin state
+            int pe0, pe1, pt0, pt1, ptv;
+            if (threadIdx.x > 0) {
+                pe0 = sE[threadIdx.x - 1][0]; pe1 = sE[threadIdx.x - 1][1];
+                pt0 = sT[threadIdx.x - 1][0]; pt1 = sT[threadIdx.x - 1][1]; ptv = sT[threadIdx.x - 1][2];
+            } else {                 // the predecessor belongs to the previous block
+                PointSum pq;
+                point_sum(g, p, G[t - 1], dG[t - 1], pq);
+                pe0 = pq.ej; pe1 = pq.ei; pt0 = pq.tj; pt1 = pq.ti; ptv = pq.tv;
             }
+            o0 = step_code(g, p, pe0, pe1, q, yt, xt, t);
+            o1 = ptv ? step_code(g, p, pt0, pt1, q, yt, xt, t) : o0;     // no twin state at t-1: bit unused
         }
         c = (unsigned)(o0 | (o1 << 2));
         mine = (unsigned)((o0 == 1) ? 1 : 0) | ((unsigned)((o1 == 1) ? 1 : 0) << 1);     // 2 propagates as 0
@@ -982,12 +1019,11 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     int isb = 0;
     if (t < nt) {
         const unsigned out = (c >> (2 * sin)) & 3u;
-        long long rj, ri;
+        long long rj = q.ej, ri = q.ei;
         if (out == 1u) {
-            accept_edge(g, f + (g.Ni - g.kew), d, INFINITY, rj, ri, p.edge);
+            rj = q.tj;
+            ri = q.ti;
             if (chg) chg[atomicAdd(nchg, 1ull)] = t;      // differs from E(t): K2-K4 of this point are redone (gzb_mapping overlap)
-        } else {
-            accept_edge(g, f, d, p.thr2, rj, ri, p.edge);
         }
         reinterpret_cast<longlong2*>(NP)[t] = make_longlong2(rj, ri);
         isb = out == 2u ? 1 : 0;
