@@ -529,13 +529,31 @@ k_extent(const int64_t n, const double* __restrict__ lat, const double* __restri
     }
 }
 
+// A bin keeps, among the cells that fall into it, the one NEAREST TO ITS CENTRE (a target in the bin
+// is then rarely more than one hill-climb move away from its answer).  Two passes: smallest distance
+// code per bin, then the smallest flat index attaining it.
+__device__ __forceinline__ unsigned lut_dist_code(const GzbLut& L, const long long bin, const double la, const double lo) {
+    const long long bj = bin / L.nlon, bi = bin - bj * L.nlon;
+    const double d = 1.0 / L.inv_d;
+    const double latc = L.lat0 + ((double)bj + 0.5) * d;
+    const double lonc = L.lon0 + ((double)bi + 0.5) * d;
+    double dx = gzb_pymod(lo - lonc + 180.0, 360.0) - 180.0;
+    dx *= cos(latc * GZB_D2R);
+    const double dy = la - latc;
+    return __float_as_uint((float)(dx * dx + dy * dy));      // non-negative float: the bit pattern is ordered
+}
+
+template <int PASS>
 __global__ void __launch_bounds__(256)
-k_lut_scatter(const GzbGrid g, const GzbLut L, unsigned* __restrict__ bins) {
+k_lut_scatter(const GzbGrid g, const GzbLut L, unsigned* __restrict__ best, unsigned* __restrict__ bins) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= g.Nj * g.Ni) return;
     const double la = g.lat[k], lo = g.lon[k];
     if (!(isfinite(la) && isfinite(lo))) return;
-    atomicMin(bins + gzb_lut_bin(L, la, lo), (unsigned)k);
+    const long long bin = gzb_lut_bin(L, la, lo);
+    const unsigned code = lut_dist_code(L, bin, la, lo);
+    if (PASS == 0) atomicMin(best + bin, code);
+    else if (best[bin] == code) atomicMin(bins + bin, (unsigned)k);
 }
 
 // empty bins take the value of the first non-empty neighbour at distance `step` (8 directions)
@@ -682,9 +700,12 @@ static int build_lut(gzb_ctx* ctx, const unsigned long long* ext) {
     }
     cudaStream_t s = ctx->stream;
     GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_lut[0], 0xff, nb * sizeof(unsigned), s));
+    GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_lut[1], 0xff, nb * sizeof(unsigned), s));
     L.bins = nullptr;
     const int64_t cells = g.Nj * g.Ni;
-    k_lut_scatter<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(g, L, ctx->d_lut[0]);
+    k_lut_scatter<0><<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(g, L, ctx->d_lut[1], ctx->d_lut[0]);
+    GZB_LAUNCH_CHECK(ctx);
+    k_lut_scatter<1><<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(g, L, ctx->d_lut[1], ctx->d_lut[0]);
     GZB_LAUNCH_CHECK(ctx);
     int cur = 0;
     const int steps[6] = {1, 1, 2, 4, 8, 16};

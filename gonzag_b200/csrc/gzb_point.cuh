@@ -55,10 +55,18 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
             atomicOr(err, 1);
             break;
         }
-        long long lo = 0, hi = nrec - 1;            // tmod[lo] <= now < tmod[hi]
-        while (hi - lo > 1) {
-            const long long mid = (lo + hi) >> 1;
-            if (tmod[mid] <= now) lo = mid; else hi = mid;
+        // bracket tmod[lo] <= now < tmod[lo+1] (gonzag/mod2sat.py:94-96).  Model records are almost always
+        // evenly spaced: guess the index from the mean spacing, verify it against the actual times, and
+        // only search (binary, eight dependent loads for 242 records) when the guess is off
+        long long lo = (long long)((now - tmod[0]) / (tmod[nrec - 1] - tmod[0]) * (double)(nrec - 1));
+        lo = lo < 0 ? 0 : (lo > nrec - 2 ? nrec - 2 : lo);
+        if (!(tmod[lo] <= now && now < tmod[lo + 1])) {
+            lo = 0;
+            long long hi = nrec - 1;                // tmod[lo] <= now < tmod[hi]
+            while (hi - lo > 1) {
+                const long long mid = (lo + hi) >> 1;
+                if (tmod[mid] <= now) lo = mid; else hi = mid;
+            }
         }
         if (lo < k0 || lo + 1 >= k0 + nk) break;    // bracket not inside this slab
         if (!EARLY && !REG) {
