@@ -247,7 +247,7 @@ def run_ours(args, w):
     import torch.distributed as dist
     import gonzag_b200 as gzb
     from gonzag_b200 import _lib as L
-    from gonzag_b200.multi import CudaEngine, ShardedMapper, P2PShardedMapper, segment_bounds
+    from gonzag_b200.multi import CudaEngine, ShardedMapper, P2PShardedMapper, P2PUnavailable, segment_bounds
     import types
 
     os.environ["NCCL_DEBUG"] = os.environ.get("GZB_NCCL_DEBUG", "WARN")   # NCCL logs go to stdout: keep it to the JSON line
@@ -307,7 +307,12 @@ def run_ours(args, w):
     tmod_d = eng.tensor(tmod_all)
     SM = eng.empty((nt_local, 4, 2), torch.int64)
     WB = eng.empty((nt_local, 4), torch.float64)
-    mapper.make_buffers(bounds)
+    try:
+        mapper.make_buffers(bounds)
+    except P2PUnavailable as exc:          # raised on every rank alike: gather with NCCL instead
+        log("[rank %d] %s -- falling back to the NCCL all-gather" % (rank, exc))
+        mapper = ShardedMapper(eng, dist if world > 1 else None, torch)
+        mapper.make_buffers(bounds)
     v_np, v_bl = mapper.v_np, mapper.v_bl
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()

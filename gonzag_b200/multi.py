@@ -239,6 +239,11 @@ class ShardedMapper:
         return tc.cat(parts_np), tc.cat(parts_bl), tc.cat(parts_NP)
 
 
+class P2PUnavailable(RuntimeError):
+    """Raised by `P2PShardedMapper.make_buffers` ON EVERY RANK when some rank cannot map a peer's buffer;
+    the caller falls back to `ShardedMapper` (NCCL all-gather)."""
+
+
 class _DevView:
     """`__cuda_array_interface__` wrapper so that torch can view raw device memory owned by a context."""
 
@@ -297,13 +302,25 @@ class P2PShardedMapper(ShardedMapper):
             allh[0] = mine
         self._peer_base = []          # [buffer][peer index] -> mapped base address on this device
         self._peers = [g for g in range(self.world) if g != self.rank]
-        for bi in range(2):
-            row = []
-            for g in self._peers:
-                p = C.c_void_p()
-                ctx._ck(lib.gzb_ipc_open(ctx._h, (C.c_ubyte * 64).from_buffer_copy(allh[g][bi]), C.byref(p)))
-                row.append(p.value)
-            self._peer_base.append(row)
+        ok = 1
+        try:
+            for bi in range(2):
+                row = []
+                self._peer_base.append(row)
+                for g in self._peers:
+                    p = C.c_void_p()
+                    ctx._ck(lib.gzb_ipc_open(ctx._h, (C.c_ubyte * 64).from_buffer_copy(allh[g][bi]), C.byref(p)))
+                    row.append(p.value)
+        except L.GonzagB200Error as exc:
+            ok = 0
+            why = str(exc)
+        if self.world > 1:        # every rank must take the same decision (this all-reduce is also the barrier)
+            okt = tc.tensor([ok], dtype=tc.int32, device=self.e.dev)
+            self.dist.all_reduce(okt, op=self.dist.ReduceOp.MIN)
+            if int(okt.item()) == 0:
+                self.close()
+                raise P2PUnavailable("peer memory (CUDA IPC) is not available between the GPUs of this job" +
+                                     (": " + why if not ok else ""))
         # barrier: this rank's entry in every peer's counters (kept in buffer 0), its own counters
         self._bar_slots = (C.c_void_p * max(len(self._peers), 1))()
         for k in range(len(self._peers)):
@@ -312,8 +329,6 @@ class P2PShardedMapper(ShardedMapper):
         self._epoch = 0
         self.step_no = 0
         self._select(0)
-        if self.world > 1:
-            self.dist.barrier()
         return self
 
     def _selection(self, bi, off):
