@@ -924,23 +924,31 @@ __device__ __forceinline__ unsigned fn_then(const unsigned f, const unsigned h) 
 #define FN_ID 2u
 
 // inclusive scan of compositions over the block; returns this thread's prefix (maps the state that
-// enters the block to the state that LEAVES this thread's point); total = the whole block's map
+// enters the block to the state that LEAVES this thread's point); total = the whole block's map.
+// Away from the seam every point's map is "both states -> E" (0): a warp of those needs no shuffles.
 __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned* sh /* [FLAGS_BLOCK/32] */, unsigned& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned f = mine;
+    if (!__all_sync(0xffffffffu, mine == 0u)) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_up_sync(0xffffffffu, f, o);
-        if (lane >= o) f = fn_then(u, f);
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, f, o);
+            if (lane >= o) f = fn_then(u, f);
+        }
     }
     if (lane == 31) sh[warp] = f;
     __syncthreads();
-    unsigned pre = FN_ID;
-    for (int q = 0; q < warp; ++q) pre = fn_then(pre, sh[q]);
-    total = pre;
-    for (int q = warp; q < FLAGS_BLOCK / 32; ++q) total = fn_then(total, sh[q]);
+    // the (up to 8) warp maps, scanned by the first lanes of every warp
+    unsigned w = lane < FLAGS_BLOCK / 32 ? sh[lane] : FN_ID;
+#pragma unroll
+    for (int o = 1; o < FLAGS_BLOCK / 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w = fn_then(u, w);
+    }
+    total = __shfl_sync(0xffffffffu, w, FLAGS_BLOCK / 32 - 1);
+    const unsigned before = __shfl_sync(0xffffffffu, w, warp > 0 ? warp - 1 : 0);
     __syncthreads();
-    return fn_then(pre, f);
+    return warp > 0 ? fn_then(before, f) : f;
 }
 
 // One pass: transition code of every point (what F_t gives from predecessor E(t-1) and from
