@@ -279,9 +279,10 @@ def run_ours(args, w):
     ctx = gzb.GridContext(lat, lon, mask=mask, k_ew_per=2, device=local)
     ctx.set_option("heading_table", args.heading_table)
     eng = CudaEngine(ctx, torch)
-    Mapper = P2PShardedMapper if (world > 1 and args.gather == "p2p") else ShardedMapper
+    Mapper = P2PShardedMapper if (world > 1 and args.gather in ("p2p", "p2p-root")) else ShardedMapper
     mapper = Mapper(eng, dist if world > 1 else None, torch)
     mapper.barrier = args.barrier
+    mapper.root_only = args.gather == "p2p-root"
     torch.cuda.synchronize()
 
     # K0 (-D): part of the grid set-up (ModGrid in the reference), timed on its own
@@ -361,8 +362,9 @@ def run_ours(args, w):
         ref_np, ref_bl = nccl_gather(mapper.v_np, 1), nccl_gather(mapper.v_bl, 1)
         if g_NP is None:
             g_NP = nccl_gather(mapper.NP, 2)
-        ok_series = bool((ref_np.view(torch.int64) == g_np.view(torch.int64)).all()
-                         and (ref_bl.view(torch.int64) == g_bl.view(torch.int64)).all())
+        complete_here = rank == 0 or args.gather != "p2p-root"       # gather to root: only rank 0 holds the whole track
+        ok_series = (not complete_here) or bool((ref_np.view(torch.int64) == g_np.view(torch.int64)).all()
+                                                  and (ref_bl.view(torch.int64) == g_bl.view(torch.int64)).all())
         oks = torch.tensor([1 if ok_series else 0], dtype=torch.int32, device=dev)
         if world > 1:
             dist.all_reduce(oks, op=dist.ReduceOp.MIN)
@@ -557,7 +559,8 @@ def run_ours(args, w):
                            "records_per_gpu": int(k_hi - k_lo + 1), "field_dtype": "f32",
                            "np_box_r": r, "rd_found_km": rd, "k_ew_per": 2,
                            "sharding": ("contiguous time segments, grid replicated; " + (
-                               "K4 stores the two series into every rank's buffer over NVLink (CUDA IPC peer memory), a barrier ("
+                               "K4 stores the two series into " + ("rank 0's buffer" if args.gather == "p2p-root" else "every rank's buffer") +
+                               " over NVLink (CUDA IPC peer memory), a barrier ("
                                + ("own kernel over peer memory" if args.barrier == "p2p" else "one-word NCCL all-reduce") + ") orders the ranks" if isinstance(mapper, P2PShardedMapper) else
                                "1 all-gather of (ssh_np, ssh_bl, NP)") + "; segment-boundary check on the device, verdict read "
                                "once after the timed steps"),
@@ -585,9 +588,10 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--heading-table", type=int, default=2, choices=[0, 1, 2],
                     help="K2 per-cell heading table: 0 never, 1 auto (amortised), 2 built at grid set-up (default)")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: p2p = K4 stores its results into every rank's buffer over NVLink (one-word all-reduce "
-                         "as the barrier); nccl = all-gather of the packed products after K4")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-root", "nccl"],
+                    help="N > 1: p2p = K4 stores its results into EVERY rank's buffer over NVLink (all-gather; one-word "
+                         "all-reduce as the barrier); p2p-root = into rank 0's buffer only (gather); nccl = all-gather of the "
+                         "packed products after K4")
     ap.add_argument("--barrier", default="nccl", choices=["p2p", "nccl"],
                     help="with --gather p2p: how the ranks are ordered after K4 (own kernel over peer memory, or NCCL all-reduce)")
     ap.add_argument("--no-e2e", action="store_true")

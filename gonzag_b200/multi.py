@@ -201,6 +201,8 @@ class ShardedMapper:
         """Host read of the accumulated flag (one synchronisation); True = every step was valid."""
         if getattr(self, "flag_acc", None) is None:
             return True
+        if getattr(self, "root_only", False) and self.world > 1:      # only rank 0 saw every edge: share its verdict
+            self.dist.all_reduce(self.flag_acc, op=self.dist.ReduceOp.MAX)
         bad = int(self.flag_acc.item())
         self.flag_acc.zero_()
         return bad == 0
@@ -301,7 +303,12 @@ class P2PShardedMapper(ShardedMapper):
         else:
             allh[0] = mine
         self._peer_base = []          # [buffer][peer index] -> mapped base address on this device
-        self._peers = [g for g in range(self.world) if g != self.rank]
+        # where this rank's series go besides its own buffer: every other rank (all-gather: everybody ends up
+        # with the whole track), or rank 0 only (gather: ``root_only``, what writing one result file needs)
+        if getattr(self, "root_only", False):
+            self._peers = [0] if self.rank != 0 else []
+        else:
+            self._peers = [g for g in range(self.world) if g != self.rank]
         ok = 1
         try:
             for bi in range(2):
@@ -400,8 +407,8 @@ class P2PShardedMapper(ShardedMapper):
         if getattr(self, "flag_acc", None) is None:
             self.flag_acc = self.e.empty((1,), tc.int32)
             self.flag_acc.zero_()
-        if self.world == 1:
-            return
+        if self.world == 1 or (getattr(self, "root_only", False) and self.rank != 0):
+            return                          # gather to root: only rank 0 holds every segment's edge words
         ctx = self.e.ctx
         ctx._ck(L.lib().gzb_check_edges(ctx._h, C.c_void_p(gathered.data_ptr()), self.slot, 2 * self.m1, self.world,
                                         C.c_void_p(self.flag_acc.data_ptr())))
@@ -409,6 +416,9 @@ class P2PShardedMapper(ShardedMapper):
     def boundaries_ok(self, gathered):
         if self.world == 1:
             return True
+        if getattr(self, "root_only", False):
+            self.check_boundaries_async(gathered)
+            return self.boundaries_verdict()
         e = self._edges(gathered)
         return not bool((e[1:, 0:2] != e[:-1, 2:4]).any().item())
 
@@ -418,6 +428,9 @@ class P2PShardedMapper(ShardedMapper):
     def reseed(self, gathered, y_own, x_own, rd, r):
         """Rare path, as in the base class; the edge words are published again after a re-map.  The
         caller then redoes K2-K4 on its own points with `redo_own_points`."""
+        if getattr(self, "root_only", False):
+            raise RuntimeError("a chain deviation straddles a segment boundary: re-seeding needs every rank to see its "
+                               "predecessor's last point, i.e. the all-gather mode (root_only = False)")
         changed = False
         for _ in range(self.world):
             if self.halo:
