@@ -344,6 +344,14 @@ def run_ours(args, w):
     for _ in range(max(args.warmup, 3)):
         step(check_now=True)
     barrier()
+    if os.environ.get("GZB_TRACE_STEP") and rank == 0:      # debugging aid: stream timeline of one step on stderr
+        ctx.set_option("trace", 1)
+        step()
+        ctx.sync()
+        ctx.set_option("trace", 0)
+    elif os.environ.get("GZB_TRACE_STEP"):
+        step()
+    barrier()
     verified = None
     if args.verify:
         # rank 0 maps the WHOLE track alone and compares with the shards; the series every rank holds
@@ -385,11 +393,14 @@ def run_ours(args, w):
     if rank == 0:
         sampler.start()
     step_ms = []
+    sync_word = torch.zeros(1, dtype=torch.int32, device=dev)
     barrier()
     for _ in range(args.steps):
         barrier()
         flush.zero_()                      # L2 flush between timed steps (not timed); the host enqueues
         flush.zero_()                      # the step while it runs, so launch latency stays out of the events
+        if world > 1:                      # stream-ordered barrier: every GPU starts its step at the same moment,
+            dist.all_reduce(sync_word)     # otherwise the ranks' start skew is billed to the step's own barrier
         e0.record()
         step()
         e1.record()
@@ -402,8 +413,12 @@ def run_ours(args, w):
     if hasattr(mapper, "detach"):
         mapper.detach()                    # the per-stage timings below are local: no stores into the peers
     total_ms = float(np.sum(step_ms))
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
         tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        allms = [torch.zeros_like(tm) for _ in range(world)]
+        dist.all_gather(allms, tm)
+        per_rank_ms = [float(v.item()) / args.steps for v in allms]
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         total_ms = float(tm.item())
     ms_per_step = total_ms / args.steps
@@ -567,7 +582,7 @@ def run_ours(args, w):
                            "l2": "flushed (256 MiB write) before every timed step and stage",
                            "heading_table": ("K2 reads a per-cell table of the grid-only headings (48 B/cell), built once per grid "
                                              "like the -D angle" if ctx.stats()["heading_table"] else "off"),
-                           "seed_reseeds": mapper.reseeds, "verified": verified, "chain_breaks": int(ctx.stats()["last_breaks"]),
+                           "ms_per_step_by_rank": [round(v, 4) for v in per_rank_ms], "seed_reseeds": mapper.reseeds, "verified": verified, "chain_breaks": int(ctx.stats()["last_breaks"]),
                            "chain_replay_steps": int(ctx.stats()["last_chain_steps"])},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "kernels": kern,
                 "cpu_baseline": cpu, "e2e": e2e}

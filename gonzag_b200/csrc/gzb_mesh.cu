@@ -297,7 +297,7 @@ int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const doubl
                          int64_t* sm_out, double* wb_out, const GzbGlobalNearest* gn_or_null) {
     if (nt <= 0) return GZB_OK;
     if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
-    GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0};
+    GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0, nullptr, nullptr};
     const long long* npp = (const long long*)np;
     if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
     k_mesh_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out,
@@ -414,7 +414,7 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     InterpArgs ia;
     fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
     const unsigned nblk = (unsigned)((nt + 127) / 128);
-    GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0};
+    GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0, nullptr, nullptr};
     const long long* npp = (const long long*)np;
     if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
     if (dtype == GZB_F32)
