@@ -86,8 +86,15 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * cell and the headings to its four neighbours, 48 B per cell) from a table instead of computing
  * it per track point: 0 never, 1 (default) build it once the points mapped on this context
  * outnumber half the grid cells, 2 build it at the next K2 call.  Same results either way.
- * "overlap": 1 (default) gzb_mapping / gzb_map_interp run the chain replays of K1 on a second
- * stream beside K2+K3(+K4) and repair the points the replays changed; 0 strictly in sequence.
+ * "overlap": 1 (default) gzb_mapping / gzb_map_interp run everything of K1 that follows the
+ * per-thread search (warp search of the unsettled points, chain logic, replays) on a second stream
+ * beside K2+K3(+K4), which start from the plain global answers, and repair the points whose
+ * nearest point turned out different; 0 strictly in sequence.  Same results.
+ * "twin_chain": 1 (default) the speculative chain of K1 knows the East-West twins of the overlap
+ * columns (two-state scan, far fewer replays); 0 plain speculation + replays.  Same results.
+ * "fuse_k4": 1 (default) gzb_map_interp runs K2+K3+K4 as one kernel; 0 K2+K3 then K4.
+ * "k4_early", "mask_bits": K4 variants (load order; tiled bit mask on/off).  Same results.
+ * "trace": 1 records a timing event at internal marks on both streams; gzb_sync prints them.
  * "edge_exclusion": 1 (default) gzb_nearest applies the first/last row/column rule of
  * BilinTrack.nrpt (gonzag/bilin_mapping.py:582-585); 0 gives plain NearestPoint() results.
  * "force_heavy": 0 (default); 1 = heavy-duty quadrant search as if |angle| > 45 everywhere;
