@@ -20,12 +20,19 @@ where it is mounted) on seeded synthetic inputs and commits the outputs as
 bit-for-bit, and ``tests/test_oracle_vs_reference.py`` re-runs the comparison live
 whenever the reference checkout is present.
 
-PARITY UNPINNED for one branch: the "heavy-duty" quadrant search
-(gonzag/bilin_mapping.py:407-426) calls ``shapely`` (GEOS ``Polygon.contains``),
-an un-vendored dependency (pinned ``shapely=1.7.1`` in util/conda/environment-zarr.yml:17)
-that is absent offline.  `point_strictly_in_quad` restates the published semantics
-(planar, interior only, boundary = outside); the golden vectors for that branch were
-produced with the same stand-in injected into the reference.
+PARITY UNPINNED (by the reference's own vectors) for one branch: the "heavy-duty"
+quadrant search (gonzag/bilin_mapping.py:407-426) calls ``shapely`` (GEOS
+``Polygon.contains``), an un-vendored dependency (pinned ``shapely=1.7.1`` in
+util/conda/environment-zarr.yml:17) that is absent offline, and the reference holds no
+test of it.  `point_strictly_in_quad` is the stand-in (planar, interior only, boundary
+= outside); the golden vectors for that branch were produced with the same stand-in
+injected into the reference.  It is pinned instead to GEOS's published algorithm:
+``oracle/geos_contains.py`` restates the call chain behind ``contains`` (envelope test,
+rectangle shortcut, RayCrossingCounter with an exact orientation predicate) in exact
+arithmetic, and ``tests/test_oracle_geos.py`` holds the stand-in to it on random,
+grid-cell-like, degenerate and adversarial inputs.  Two documented differences remain:
+targets within fp64 rounding (~1e-16 relative) of a mesh edge, and zero-area rings with
+a repeated vertex that GEOS's ``isRectangle`` mistakes for rectangles.
 """
 from __future__ import annotations
 
