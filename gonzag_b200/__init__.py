@@ -11,10 +11,11 @@ from .mod2sat import Model2SatTrack                     # noqa: F401
 from .utils import (GridAngle, SearchBoxSize, degE_to_degWE, GridResolution, IsEastWestPeriodic,       # noqa: F401
                     IsGlobalLongitudeWise, scan_idx, GetEpochTimeOverlap, EpochT2Str, ModGrid, SatTrack, MsgExit)
 from .sources import ModelArrays, TrackArrays           # noqa: F401
+from .nc3io import NetCDF3Source                        # noqa: F401
 from .ncout import SaveTimeSeries, Save2Dfield          # noqa: F401
 
 __all__ = ["BilinTrack", "NearestPoint", "Iquadran", "IDSourceMesh", "AlfaBeta", "WeightBL", "Heading",
            "Model2SatTrack", "GridContext", "GridAngle", "SearchBoxSize",
            "degE_to_degWE", "GonzagB200Error", "device_count", "GridResolution", "IsEastWestPeriodic",
            "IsGlobalLongitudeWise", "scan_idx", "GetEpochTimeOverlap", "EpochT2Str", "ModGrid", "SatTrack",
-           "ModelArrays", "TrackArrays", "SaveTimeSeries", "Save2Dfield"]
+           "ModelArrays", "TrackArrays", "NetCDF3Source", "SaveTimeSeries", "Save2Dfield"]

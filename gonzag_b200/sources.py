@@ -8,8 +8,9 @@ the objects below: same functions, same argument meaning, same slicing quirks (`
 ignored unless BOTH are > 0, gonzag/ncio.py:119-125), backed by arrays or by a per-record callable
 (a streaming provider: one 2-D record at a time, as a file reader would deliver them).
 
-A real file name still works when the reference package is importable: the functions are then
-taken from ``gonzag.ncio`` / ``gonzag.zarrio``.
+A real file name works too: NetCDF-3 files (classic / 64-bit offset) are read by the built-in
+`gonzag_b200.nc3io.NetCDF3Source` (scipy, no external library); anything else (NetCDF-4, zarr) goes
+to ``gonzag.ncio`` / ``gonzag.zarrio`` when the reference package is importable.
 """
 from __future__ import annotations
 
@@ -155,7 +156,11 @@ class _FileSource:
 
 
 def as_source(obj):
-    """ModelArrays / TrackArrays pass through; anything else is taken as a file name."""
-    if isinstance(obj, (ModelArrays, TrackArrays)):
+    """ModelArrays / TrackArrays (or any object with the reader functions) pass through; a file name
+    goes to the built-in NetCDF-3 reader when the file is of that kind, else to the reference's I/O."""
+    if isinstance(obj, (ModelArrays, TrackArrays)) or hasattr(obj, "GetTimeEpochVector"):
         return obj
+    from .nc3io import NetCDF3Source, is_netcdf3
+    if is_netcdf3(str(obj)):
+        return NetCDF3Source(str(obj))
     return _FileSource(str(obj))

@@ -73,3 +73,78 @@ def ulp_diff(a, b):
     if a.size == 0:
         return 0
     return int(np.max(np.abs(ia - ib)))
+
+
+def write_grid_case_files(g, tag, directory):
+    """The data sets of `grid_case_sources` written as NetCDF-3 files (scipy), laid out like the files
+    the reference's examples read: NEMO-style model file (+ separate mesh-mask file for case a),
+    along-track satellite file.  Returns (model_path, track_path, lsm_path, varlsm, distorded, Np)."""
+    import os
+    from scipy.io import netcdf_file
+    units = "seconds since 1970-01-01 00:00:00"
+    d = str(directory)
+    fm, ft, fl = (os.path.join(d, "%s_%s.nc" % (tag, n)) for n in ("model", "track", "mesh_mask"))
+
+    def time_var(f, name, values, dim):
+        f.createDimension(dim, None)
+        v = f.createVariable(name, "f8", (dim,))
+        v.units = units
+        v.calendar = "gregorian"
+        v[:] = values
+        return v
+
+    with netcdf_file(ft, "w", version=2) as f:
+        time_var(f, "time", g[tag + "_t"], "time")
+        for name, key in (("latitude", "_y"), ("longitude", "_x")):
+            v = f.createVariable(name, "f8", ("time",))
+            v[:] = g[tag + key]
+        v = f.createVariable("ssh", "f8", ("time",))
+        v._FillValue = np.float64(1.e20)
+        v[:] = g[tag + "_ssat"]
+    if tag == "a":
+        with netcdf_file(fm, "w", version=2) as f:
+            nj, ni = g["a_lat"].shape
+            time_var(f, "time_counter", g["a_tm"], "time_counter")      # the record dimension comes first
+            f.createDimension("y", nj)
+            f.createDimension("x", ni)
+            for name, key in (("nav_lat", "a_lat"), ("nav_lon", "a_lon")):
+                v = f.createVariable(name, "f8", ("y", "x"))        # float32 values held as float64, as the
+                v[:] = g[key].astype(np.float64)                     # golden generator handed them to the reference
+            v = f.createVariable("ssh", "f4", ("time_counter", "y", "x"))
+            v[:] = g["a_f32"]
+        with netcdf_file(fl, "w", version=1) as f:
+            f.createDimension("t", 1)
+            f.createDimension("z", 2)
+            f.createDimension("y", nj)
+            f.createDimension("x", ni)
+            v = f.createVariable("tmask", "i1", ("t", "z", "y", "x"))
+            v[0, 0] = g["a_maskin"]
+            v[0, 1] = 0
+        return fm, ft, fl, "tmask", True, len(g["a_t"])
+    if tag == "b":
+        with netcdf_file(fm, "w", version=2) as f:
+            nj, ni = g["b_lat"].shape
+            time_var(f, "time", g["b_tm"], "time")
+            f.createDimension("y", nj)
+            f.createDimension("x", ni)
+            for name, key in (("gphit", "b_lat"), ("glamt", "b_lon")):
+                v = f.createVariable(name, "f8", ("y", "x"))
+                v[:] = g[key]
+            v = f.createVariable("ssh", "f8", ("time", "y", "x"))
+            v[:] = g["b_f64"]
+            v = f.createVariable("tmask", "i2", ("y", "x"))
+            v[:] = g["b_maskin"]
+        return fm, ft, fm, "tmask", False, 100
+    with netcdf_file(fm, "w", version=1) as f:
+        nj, ni = len(g["c_lat1"]), len(g["c_lon1"])
+        time_var(f, "time", g["c_tm"], "time")
+        f.createDimension("lat", nj)
+        f.createDimension("lon", ni)
+        v = f.createVariable("lat", "f8", ("lat",))
+        v[:] = g["c_lat1"]
+        v = f.createVariable("lon", "f8", ("lon",))
+        v[:] = g["c_lon1"]
+        v = f.createVariable("ssh", "f4", ("time", "lat", "lon"))
+        v._FillValue = np.float32(1.e20)
+        v[:] = np.where(g["c_maskin"][None] == 0, np.float32(1.e20), g["c_f32"])
+    return fm, ft, fm, "_FillValue@ssh", False, len(g["c_t"])

@@ -66,6 +66,41 @@ def test_cli_sequence_matches_reference(golden_grid, tag):
         MG.close()
 
 
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_cli_sequence_from_netcdf3_files(golden_grid, tmp_path, tag):
+    """The same sequence given FILE NAMES, as alongtrack_sat_vs_nemo.py:58-74 does: NetCDF-3 files read by
+    the built-in readers (gonzag_b200/nc3io.py), model records streamed one at a time through pinned
+    memory into K4.  Times pass through num2date's microsecond rounding (gonzag/ncio.py:40-46), hence
+    the 1.5e-6 s tolerance on them; indices and masks stay bit-exact."""
+    from tests.conftest import write_grid_case_files
+    g = golden_grid
+    fm, ft, fl, varlsm, dist, Np = write_grid_case_files(g, tag, tmp_path)
+    (it1, it2), (nts, ntm) = gz.GetEpochTimeOverlap(ft, fm)
+    MG = gz.ModGrid(fm, it1, it2, fl, varlsm, distorded_grid=dist)
+    try:
+        ST = gz.SatTrack(ft, it1, it2, Np=Np, domain_bounds=MG.domain_bounds, l_0_360=MG.l360)
+        assert MG.file == fm and ST.file == ft
+        assert MG.size == int(g[tag + "_mg_size"])
+        np.testing.assert_allclose(MG.time, g[tag + "_mg_time"], rtol=0, atol=1.5e-6)
+        np.testing.assert_array_equal(MG.lat, g[tag + "_mg_lat"])
+        np.testing.assert_array_equal(MG.lon, g[tag + "_mg_lon"])
+        np.testing.assert_array_equal(MG.mask, g[tag + "_mg_mask"])
+        assert MG.domain_bounds == g[tag + "_mg_bounds"].tolist()
+        assert [ST.jt1, ST.jt2, ST.size] == g[tag + "_st_j"].tolist()
+        R = gz.Model2SatTrack(MG, "ssh", ST, "ssh")
+        assert not R.fused_path                       # per-record provider: gzb_mapping + slabs of gzb_interp
+        _check_results(R, g, tag)
+        path = str(tmp_path / "result.nc")            # and out again through the writers, read back by the reader
+        gz.SaveTimeSeries(R.time, np.ma.array([R.lat, R.lon, R.ssh_mod, R.ssh_sat]), ["latitude", "longitude", "ssh_mod", "ssh_sat"],
+                          path, time_units="seconds since 1970-01-01 00:00:00", missing_val=gz.rmissval)
+        back = gz.NetCDF3Source(path)
+        np.testing.assert_allclose(back.GetTimeEpochVector(), R.time, rtol=0, atol=1.5e-6)
+        np.testing.assert_array_equal(back.GetSatSSH("ssh_mod"), np.ma.filled(R.ssh_mod, gz.rmissval).astype(np.float32))
+        back.close()
+    finally:
+        MG.close()
+
+
 def test_streaming_provider_and_staged_paths(golden_grid):
     """Records delivered one at a time (a file-like provider) and a whole pageable array too big
     to stay resident go through gzb_mapping + gzb_interp slab by slab: same products."""
