@@ -101,6 +101,34 @@ def test_cli_sequence_from_netcdf3_files(golden_grid, tmp_path, tag):
         MG.close()
 
 
+@pytest.mark.parametrize("tag", ["a", "c"])
+def test_cli_main_from_files(golden_grid, tmp_path, tag):
+    """`python -m gonzag_b200.cli` (flags and steps of alongtrack_sat_vs_nemo.py) from NetCDF-3 files to
+    result.nc / xnp_msk.nc: -D with a mesh-mask file (a), `-l 0` = mask from _FillValue (c)."""
+    from scipy.io import netcdf_file
+    from gonzag_b200 import cli
+    from tests.conftest import write_grid_case_files
+    g = golden_grid
+    fm, ft, fl, varlsm, dist, Np = write_grid_case_files(g, tag, tmp_path)
+    out = tmp_path / "out"
+    argv = ["-s", ft, "-n", "ssh", "-m", fm, "-v", "ssh", "-o", str(out)]
+    if tag == "a":
+        argv += ["-l", fl, "-k", "tmask", "-D"]
+    R = cli.main(argv)
+    _check_results(R, g, tag)
+    back = gz.NetCDF3Source(str(out / "result.nc"))
+    assert back.GetTimeInfo()[0] == len(R.time)
+    np.testing.assert_array_equal(back.GetSatSSH("ssh_bl"), np.ma.getdata(R.ssh_mod).astype(np.float32))
+    np.testing.assert_array_equal(back.GetSatSSH("ssh_np"), np.ma.getdata(R.ssh_mod_np).astype(np.float32))
+    np.testing.assert_array_equal(back.GetSatSSH("distance"), R.distance.astype(np.float32))
+    np.testing.assert_array_equal(np.ma.getdata(back.GetSatCoor("latitude")), R.lat.astype(np.float32))
+    back.close()
+    with netcdf_file(str(out / "xnp_msk.nc"), "r", mmap=False) as f:
+        trk = f.variables["track"][:]
+        assert trk.shape == R.XNPtrack.shape and f.variables["nav_lon"].shape == trk.shape
+        np.testing.assert_array_equal(np.isnan(trk), np.ma.getmaskarray(R.XNPtrack))
+
+
 def test_streaming_provider_and_staged_paths(golden_grid):
     """Records delivered one at a time (a file-like provider) and a whole pageable array too big
     to stay resident go through gzb_mapping + gzb_interp slab by slab: same products."""
