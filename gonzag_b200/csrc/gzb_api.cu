@@ -160,6 +160,33 @@ extern "C" int gzb_mapping(gzb_ctx* ctx, int64_t nt, const double* yt, const dou
                       nullptr, np_out, sm_out, wb_out, where, "gzb_mapping");
 }
 
+// K2 + K3 + K4 in ONE kernel from known nearest points, device-resident track: the bulk kernel of
+// gzb_map_interp on its own (mesh and weights of a point stay in registers between the stages).
+extern "C" int gzb_mesh_weights_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const double* tt,
+                                       const int64_t* np, int64_t nrec, const double* tmod, const void* slab, int dtype,
+                                       int64_t k0, int64_t nk, double rmissval, int64_t* sm_out, double* wb_out,
+                                       double* vnp_out, double* vbl_out) {
+    const char* who = "gzb_mesh_weights_interp";
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "%s: null ctx", who);
+    if (nt < 0 || nrec < 2 || nk < 2 || k0 < 0 || k0 + nk > nrec || !tmod || !slab)
+        return gzb_fail(ctx, GZB_ERR_ARG, "%s: bad arguments (nt=%lld nrec=%lld k0=%lld nk=%lld)", who, (long long)nt,
+                        (long long)nrec, (long long)k0, (long long)nk);
+    if (nt == 0) return GZB_OK;
+    if (!yt || !xt || !tt || !np || !sm_out || !wb_out || !vnp_out || !vbl_out)
+        return gzb_fail(ctx, GZB_ERR_ARG, "%s: null track array", who);
+    if (dtype != GZB_F32 && dtype != GZB_F64) return gzb_fail(ctx, GZB_ERR_ARG, "%s: dtype must be GZB_F32 or GZB_F64", who);
+    if (!ctx->g.mask) return gzb_fail(ctx, GZB_ERR_STATE, "%s: the context has no land-sea mask (gzb_set_mask)", who);
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    const void* slab_dev = nullptr;
+    int slab_is_host = 0;
+    if (!gzb_slab_device_pointer(slab, &slab_dev, &slab_is_host))
+        return gzb_fail(ctx, GZB_ERR_ARG, "%s: the record slab must be in device memory or in pinned + mapped host memory "
+                        "(gzb_host_alloc / gzb_host_register)", who);
+    if (slab_is_host) ctx->stats.h2d_bytes += (uint64_t)nt * 8 * 32;
+    return gzb_mesh_weights_interp_dev(ctx, nt, yt, xt, np, nullptr, sm_out, wb_out, tt, nrec, tmod, slab_dev, dtype, k0, nk,
+                                       rmissval, vnp_out, vbl_out);
+}
+
 // K1 + K2 + K3 + K4 in one call, device-resident track.  The chain replays of K1 (a few long
 // dependent walks) run on the auxiliary stream while K2, K3 and K4 work on the speculative chain;
 // the points the replays changed (a few hundred on a 10-day track) then go through K2-K4 again.

@@ -72,6 +72,14 @@ class CudaEngine:
                                             int(k0), int(slab.shape[0]), float(config.rmissval), self._p(NP),
                                             self._p(SM), self._p(WB), self._p(v_np), self._p(v_bl)))
 
+    def mesh_weights_interp(self, y, x, t, NP, tmod, slab, k0, SM, WB, v_np, v_bl):
+        """K2 + K3 + K4 as one kernel from known nearest points (the bulk kernel of `map_interp`)."""
+        dt = L.GZB_F32 if slab.dtype == self.torch.float32 else L.GZB_F64
+        self.ctx._ck(L.lib().gzb_mesh_weights_interp(self.ctx._h, y.numel(), self._p(y), self._p(x), self._p(t), self._p(NP),
+                                                     tmod.numel(), self._p(tmod), self._p(slab), dt, int(k0),
+                                                     int(slab.shape[0]), float(config.rmissval), self._p(SM), self._p(WB),
+                                                     self._p(v_np), self._p(v_bl)))
+
     def mesh_weights(self, y, x, NP, SM, WB):
         n = y.numel()
         self.ctx._ck(L.lib().gzb_mesh_weights(self.ctx._h, n, self._p(y), self._p(x), self._p(NP), self._p(SM),

@@ -167,6 +167,15 @@ int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
                    double rmissval, int64_t* np_out, int64_t* sm_out, double* wb_out,
                    double* vnp_out, double* vbl_out);
 
+/* K2+K3+K4 in ONE kernel from known nearest points (BilinTrack.srcm() + wght(),
+ * gonzag/bilin_mapping.py:595-617, then the interpolation loop, gonzag/mod2sat.py:74-139): the bulk
+ * kernel of gzb_map_interp on its own.  Device-resident track, slab as for gzb_map_interp.  Same
+ * results as gzb_mesh_weights followed by gzb_interp. */
+int gzb_mesh_weights_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const double* tt,
+                            const int64_t* np, int64_t nrec, const double* tmod, const void* slab, int dtype,
+                            int64_t k0, int64_t nk, double rmissval, int64_t* sm_out, double* wb_out,
+                            double* vnp_out, double* vbl_out);
+
 /* ---- K4: fused time-linear + space-bilinear gather -----------------------------------------
  * Replaces the interpolation loop of Model2SatTrack (gonzag/mod2sat.py:74-139).
  * t: (nt,) float64 track times; tmod: (nrec,) float64 model record times, increasing;

@@ -352,6 +352,16 @@ def test_map_interp_matches_staged(golden_global):
                 assert np.array_equal(ctx.download(o[2], (n, 4), np.float64), WB)
                 assert np.array_equal(ctx.download(o[3], (n,), np.float64), v_np)
                 assert np.array_equal(ctx.download(o[4], (n,), np.float64), v_bl)
+            # the bulk kernel on its own (K2+K3+K4 from the nearest points just computed)
+            o2 = [ctx.dev_alloc(n * k) for k in (64, 32, 8, 8)]
+            ctx._ck(L.lib().gzb_mesh_weights_interp(ctx._h, n, P(d[0]), P(d[1]), P(d[2]), P(o[0]), len(tm), P(d[3]), P(d[4]),
+                                                    ctx._field_dtype(fld), 0, fld.shape[0], -9999., P(o2[0]), P(o2[1]),
+                                                    P(o2[2]), P(o2[3])))
+            ctx.sync()
+            assert np.array_equal(ctx.download(o2[0], (n, 4, 2), np.int64), SM)
+            assert np.array_equal(ctx.download(o2[1], (n, 4), np.float64), WB)
+            assert np.array_equal(ctx.download(o2[2], (n,), np.float64), v_np)
+            assert np.array_equal(ctx.download(o2[3], (n,), np.float64), v_bl)
 
 
 def test_twin_chain_matches_replays(golden_global, golden_seam):
