@@ -27,7 +27,7 @@ class GonzagB200Error(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("last_breaks", C.c_int64), ("last_chain_steps", C.c_int64),
-                ("pyramid_levels", C.c_int32), ("reserved", C.c_int32),
+                ("pyramid_levels", C.c_int32), ("l2_fetch_bytes", C.c_int32),
                 ("lut_bins", C.c_int64), ("last_unresolved", C.c_int64),
                 ("last_unres_noseed", C.c_int64), ("last_unres_noconv", C.c_int64),
                 ("last_unres_nocert", C.c_int64), ("last_max_chain", C.c_int64),

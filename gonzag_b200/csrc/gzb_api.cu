@@ -183,6 +183,7 @@ extern "C" int gzb_mesh_weights_interp(gzb_ctx* ctx, int64_t nt, const double* y
         return gzb_fail(ctx, GZB_ERR_ARG, "%s: the record slab must be in device memory or in pinned + mapped host memory "
                         "(gzb_host_alloc / gzb_host_register)", who);
     if (slab_is_host) ctx->stats.h2d_bytes += (uint64_t)nt * 8 * 32;
+    ctx->pf_now = ctx->prefetch && !slab_is_host;
     return gzb_mesh_weights_interp_dev(ctx, nt, yt, xt, np, nullptr, sm_out, wb_out, tt, nrec, tmod, slab_dev, dtype, k0, nk,
                                        rmissval, vnp_out, vbl_out);
 }
@@ -213,6 +214,7 @@ extern "C" int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const 
         return gzb_fail(ctx, GZB_ERR_ARG, "%s: the record slab must be in device memory or in pinned + mapped host memory "
                         "(gzb_host_alloc / gzb_host_register); use gzb_mapping + gzb_interp for pageable slabs", who);
     if (slab_is_host) ctx->stats.h2d_bytes += (uint64_t)nt * 8 * 32;
+    ctx->pf_now = ctx->prefetch && !slab_is_host;
     if (gzb_arena_reserve(ctx, gzb_nearest_ws_bytes(nt)) != GZB_OK) return GZB_ERR_NOMEM;
     cudaStream_t s = ctx->stream;
     int rc;

@@ -106,6 +106,7 @@ struct gzb_ctx {
     int ntrace = 0;
     cudaEvent_t trace_ev[48] = {};
     const char* trace_name[48] = {};
+    int pdl = 0;                     // K1 chain kernels launched with programmatic dependent launch (griddepcontrol): the next kernel's launch overlaps the tail of the previous one
     int overlap = 1;                 // gzb_mapping: 1 run the chain replays beside K2+K3, 0 strictly in sequence
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     GzbGrid g;
@@ -121,6 +122,8 @@ struct gzb_ctx {
     unsigned* d_lut[2] = {nullptr, nullptr};
     unsigned* d_mbits = nullptr;     // land-sea mask as bits in 16x16-cell tiles (K4); d_flags[2] != 0: mask not {0,1}
     int mask_bits_ok = 0;
+    int prefetch = 0;                // bulk kernel: 1 = L2 prefetch of a point's eight field values + mask word as soon as its mesh is known (before the Newton solve)
+    int pf_now = 0;                  // ... resolved per call (off for host-resident slabs)
     int k4_early = 0;                // K4 load order: 1 field loads issued before the ocean test, 0 after it (measured faster)
     double* d_hdg = nullptr;         // heading table of K2 (48 B per cell), built on demand
     int hdg_mode = 1;                // 0 never, 1 when the points mapped on this grid outnumber its cells / 2, 2 at the next K2 call
@@ -158,6 +161,15 @@ int gzb_fail(gzb_ctx* ctx, int code, const char* fmt, ...);
             return gzb_fail((ctx), GZB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,         \
                             cudaGetErrorString(e__), __FILE__, __LINE__);                \
     } while (0)
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the ProgrammaticStreamSerialization attribute may
+// start while its predecessor in the stream is still finishing; gzb_pdl_wait() at its top blocks until the
+// predecessor has completed and its writes are visible (a no-op for a plain launch).  gzb_pdl_trigger() lets the
+// dependent launch before the calling grid ends (only used by one-block kernels: a resident dependent holds SM slots).
+#ifdef __CUDACC__
+__device__ __forceinline__ void gzb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gzb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 #define GZB_LAUNCH_CHECK(ctx)                                                            \
     do {                                                                                 \

@@ -1022,6 +1022,17 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "fuse_k4")) { ctx->fuse_k4 = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "overlap")) { ctx->overlap = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "k4_early")) { ctx->k4_early = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "pdl")) { ctx->pdl = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "prefetch")) { ctx->prefetch = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return GZB_OK; }
+    if (!strcmp(name, "l2_fetch")) {      // device-wide hint (cudaLimitMaxL2FetchGranularity): 32, 64 or 128 bytes
+        if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+        size_t got = 0;
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value);
+        if (e != cudaSuccess) { cudaGetLastError(); return gzb_fail(ctx, GZB_ERR_CUDA, "cudaDeviceSetLimit(L2 fetch granularity, %lld): %s", (long long)value, cudaGetErrorString(e)); }
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        ctx->stats.l2_fetch_bytes = (int32_t)got;
+        return GZB_OK;
+    }
     if (!strcmp(name, "mask_bits")) {
         if (!value) { ctx->mask_bits_ok = 0; return GZB_OK; }
         return gzb_build_mask_bits(ctx);

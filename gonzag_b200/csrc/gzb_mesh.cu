@@ -366,7 +366,33 @@ static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt);
 
 // K2 + K3 + K4 for every point in one pass (gzb_map_interp): the mesh and the weights go from the
 // registers of K3 straight into the gather, SM / WB are written once and never read back
+// Prefetch (option "prefetch"): the gather of a point is the last of four dependent DRAM round trips
+// (table -> mesh corners -> [Newton solve] -> mask word -> field values).  Its addresses are known as soon as
+// the mesh is: ask L2 for the sectors right then, so that they travel while the Newton iteration runs.
+// The time bracket is only guessed (mean record spacing); a wrong guess fetches a neighbouring record.
 template <typename T>
+__device__ __forceinline__ void prefetch_point(const GzbGrid& g, const long long t, const InterpArgs& ia,
+                                               const long long* cj, const long long* ci) {
+    const double now = __ldg(ia.t_sat + t);
+    const double ta = __ldg(ia.tmod), tb = __ldg(ia.tmod + ia.nrec - 1);
+    if (!(now >= ta) || !(now < tb)) return;
+    long long lo = (long long)((now - ta) / (tb - ta) * (double)(ia.nrec - 1));
+    lo = lo < 0 ? 0 : (lo > ia.nrec - 2 ? ia.nrec - 2 : lo);
+    if (lo < ia.k0 || lo + 1 >= ia.k0 + ia.nk) return;
+    const long long cells = g.Nj * g.Ni;
+    const T* X1 = (const T*)ia.slab + (lo - ia.k0) * cells;
+    const long long ntI = (g.Ni + 15) >> 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long j = pywrap_idx(cj[k], g.Nj), i = pywrap_idx(ci[k], g.Ni);
+        const long long c = j * g.Ni + i;
+        gzb_l2_prefetch(X1 + c);
+        gzb_l2_prefetch(X1 + cells + c);
+        if (ia.mbits && (k == 0 || k == 2)) gzb_l2_prefetch(ia.mbits + ((j >> 4) * ntI + (i >> 4)) * 8);
+    }
+}
+
+template <typename T, bool PF>
 __global__ void __launch_bounds__(128)      // 86 registers; capping it at 64 (more warps, some spills) measured 3 % slower
 k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
                       const long long* __restrict__ NP, const GzbGlobalNearest gn, long long* __restrict__ SM,
@@ -377,6 +403,7 @@ k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restr
     long long cj[4], ci[4], jP, iP;
     if (!nearest_of(g, NP, gn, t, jP, iP)) return;
     source_mesh_one(g, yT, xT, jP, iP, force_heavy, cj, ci);
+    if (PF) prefetch_point<T>(g, t, ia, cj, ci);
     longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
     longlong2 rp[4];
 #pragma unroll
@@ -417,12 +444,11 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0, nullptr, nullptr};
     const long long* npp = (const long long*)np;
     if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
-    if (dtype == GZB_F32)
-        k_mesh_weights_interp<float><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out, wb_out,
-                                                                    ctx->force_heavy, ia);
-    else
-        k_mesh_weights_interp<double><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out, wb_out,
-                                                                     ctx->force_heavy, ia);
+#define GZB_BULK(T, PF) k_mesh_weights_interp<T, PF><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out, \
+                                                                                   wb_out, ctx->force_heavy, ia)
+    if (dtype == GZB_F32) { if (ctx->pf_now) GZB_BULK(float, true); else GZB_BULK(float, false); }
+    else                  { if (ctx->pf_now) GZB_BULK(double, true); else GZB_BULK(double, false); }
+#undef GZB_BULK
     GZB_LAUNCH_CHECK(ctx);
     ctx->time_err_pending = 1;
     return GZB_OK;

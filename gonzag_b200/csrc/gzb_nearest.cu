@@ -966,6 +966,7 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     __shared__ unsigned sh[FLAGS_BLOCK / 32];
     __shared__ unsigned last[FLAGS_BLOCK / 32];
     __shared__ unsigned s_bid, s_entry;
+    gzb_pdl_wait();
     if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned bid = s_bid;
@@ -1077,6 +1078,8 @@ __global__ void __launch_bounds__(SCAN_T)
 k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, const long long nblk,
               long long* __restrict__ total) {
     __shared__ long long wsum[SCAN_T / 32];
+    gzb_pdl_wait();
+    gzb_pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long per = (nblk + SCAN_T - 1) / SCAN_T;
     const long long a = (long long)threadIdx.x * per;
@@ -1105,6 +1108,7 @@ __global__ void __launch_bounds__(FLAGS_BLOCK)
 k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ offsets, const long long nt,
           long long* __restrict__ breaks) {
     __shared__ int wcnt[32];
+    gzb_pdl_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = (t < nt) ? brk[t] : 0;
@@ -1148,6 +1152,7 @@ k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __
     __shared__ WarpSm ws[WALK_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSm& w = ws[warp];
+    gzb_pdl_wait();
     const long long nb = *nbrk_p;
     const long long nwarps = (long long)gridDim.x * WALK_WARPS;
     for (long long k = (long long)blockIdx.x * WALK_WARPS + warp; k < nb; k += nwarps) {
@@ -1318,6 +1323,8 @@ k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop
         const long long* __restrict__ nbrk_p, unsigned char* __restrict__ valid, long long* __restrict__ stats_out) {
     __shared__ long long sb[VALID_CHUNK + 1];
     __shared__ long long ss[VALID_CHUNK];
+    gzb_pdl_wait();
+    gzb_pdl_trigger();
     const int lane = threadIdx.x & 31;
     const long long nb = *nbrk_p;
     long long cur_end = -1;
@@ -1441,6 +1448,23 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
 // behind an event, so that the caller can run K2+K3 on the speculative chain meanwhile; the
 // points the replays changed are listed in *chg_out / *nchg_out (device pointers) and ctx->ev_k1[1]
 // marks the end of the chain part.
+// launch on `s`, optionally as a programmatic dependent of the previous kernel in that stream (option "pdl")
+template <typename... P, typename... A>
+static void launch_dep(bool pdl, void (*kern)(P...), unsigned grid, unsigned block, cudaStream_t s, A&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = s;
+    cudaLaunchAttribute at;
+    memset(&at, 0, sizeof(at));
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);     // errors surface in GZB_LAUNCH_CHECK
+}
+
 int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, double rd_found_km,
                     int np_box_r, int64_t seed_j, int64_t seed_i, int64_t* np_out, bool split,
                     const long long** chg_out, const unsigned long long** nchg_out, GzbGlobalNearest* gn_out) {
@@ -1503,6 +1527,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     }
 
     GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 64, s));
+    GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 1) * sizeof(unsigned), s));     // k_chain's ticket and block maps
     if (ctx->corner_r != np_box_r) {
         k_corner<<<1, 256, 0, s>>>(ctx->g, np_box_r, corner);
         GZB_LAUNCH_CHECK(ctx);
@@ -1518,6 +1543,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     const long long gmax = (long long)nsm * 16;
     if (gblocks > gmax) gblocks = gmax;
     cudaStream_t sb = s;
+    bool sb_has_kernel = false;      // is the operation right before k_chain on its stream a kernel?  (a dependent launch needs one)
     gzb_trace(ctx, s, "K1 start");
     if (ctx->nearest_path && ctx->g.cellv && ctx->g.lut.bins) {
         k_near_search<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ctx->g, nt, yt, xt, G, dG, ulist, hint,
@@ -1535,38 +1561,43 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
         k_near_slow<<<(unsigned)(nsm * 32 / SLOW_WARPS), 32 * SLOW_WARPS, 0, sb>>>(ctx->g, yt, xt, G, dG, ulist, hint,
                                                         (const unsigned long long*)(scal + 2));
         GZB_LAUNCH_CHECK(ctx);
+        sb_has_kernel = true;
         gzb_trace(ctx, sb, "slow end");
     } else {
         k_global<<<(unsigned)gblocks, 256, 0, s>>>(ctx->g, nt, yt, xt, G, dG, K);
         GZB_LAUNCH_CHECK(ctx);
+        sb_has_kernel = !split;
         if (split) {
             sb = ctx->aux_stream;
             GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[0], s));
             GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
         }
     }
-    GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 1) * sizeof(unsigned), sb));
-    k_chain<<<(unsigned)nblk, FLAGS_BLOCK, 0, sb>>>(ctx->g, p, nt, yt, xt, G, dG, (long long*)np_out, brk, counts, agg,
-                                                   agg + nblk, chg, nchg);
+    // the chain kernels follow each other on one stream: with "pdl" each is a programmatic dependent of the one
+    // before it (gzb_pdl_wait() at its top), so its launch overlaps the tail of its predecessor
+    const bool pdl = ctx->pdl != 0 && !ctx->trace;
+    launch_dep(pdl && sb_has_kernel, k_chain, (unsigned)nblk, FLAGS_BLOCK, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
+               (const double*)dG, (long long*)np_out, brk, counts, (volatile unsigned*)agg, agg + nblk, chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
     gzb_trace(ctx, sb, "chain kernel end");
-    k_scan_counts<<<1, SCAN_T, 0, sb>>>(counts, offsets, nblk, scal);
+    launch_dep(pdl, k_scan_counts, 1u, SCAN_T, sb, (const int*)counts, offsets, (long long)nblk, scal);
     GZB_LAUNCH_CHECK(ctx);
-    k_compact<<<(unsigned)nblk, FLAGS_BLOCK, 0, sb>>>(brk, offsets, nt, breaks);
+    launch_dep(pdl, k_compact, (unsigned)nblk, FLAGS_BLOCK, sb, (const unsigned char*)brk, (const long long*)offsets, (long long)nt, breaks);
     GZB_LAUNCH_CHECK(ctx);
     long long wblocks = (long long)((n + WALK_WARPS - 1) / WALK_WARPS);
     const long long wmax = (long long)nsm * 64 / WALK_WARPS;
     if (wblocks > wmax) wblocks = wmax;
-    k_walk<false><<<(unsigned)wblocks, 32 * WALK_WARPS, 0, sb>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
-                                                    valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1),
-                                                    nullptr, nullptr);
+    launch_dep(pdl, k_walk<false>, (unsigned)wblocks, 32 * WALK_WARPS, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
+               (const double*)dG, (const long long*)breaks, (const long long*)scal, stop, first, (const unsigned char*)valid, wlog,
+               (long long*)np_out, (unsigned long long*)(scal + 1), (long long*)nullptr, (unsigned long long*)nullptr);
     GZB_LAUNCH_CHECK(ctx);
     gzb_trace(ctx, sb, "walk0 end");
-    k_valid<<<1, 256, 0, sb>>>(breaks, stop, scal, valid, (long long*)(ctx->d_flags + 8));
+    launch_dep(pdl, k_valid, 1u, 256u, sb, (const long long*)breaks, (const long long*)stop, (const long long*)scal, valid,
+               (long long*)(ctx->d_flags + 8));
     GZB_LAUNCH_CHECK(ctx);
-    k_walk<true><<<(unsigned)wblocks, 32 * WALK_WARPS, 0, sb>>>(ctx->g, p, nt, yt, xt, G, dG, breaks, scal, stop, first,
-                                                   valid, wlog, (long long*)np_out, (unsigned long long*)(scal + 1),
-                                                   chg, nchg);
+    launch_dep(pdl, k_walk<true>, (unsigned)wblocks, 32 * WALK_WARPS, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
+               (const double*)dG, (const long long*)breaks, (const long long*)scal, stop, first, (const unsigned char*)valid, wlog,
+               (long long*)np_out, (unsigned long long*)(scal + 1), chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
     gzb_trace(ctx, sb, "walk1 end (chain done)");
     if (split) GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[1], sb));

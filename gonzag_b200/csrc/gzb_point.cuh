@@ -4,6 +4,8 @@
 #pragma once
 #include "gzb_common.cuh"
 
+__device__ __forceinline__ void gzb_l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ long long pywrap_idx(long long k, long long n) {
     k = k < 0 ? k + n : k;                      // Python negative indexing (SM == -1 reads the last cell)
     return k < 0 ? 0 : (k >= n ? n - 1 : k);    // anything else out of range is clamped, never faults
@@ -28,7 +30,7 @@ __device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const
 // (struct GzbPeerOut: gzb_common.cuh)
 
 // REG: the mesh and weights come in registers (rp[4], rw[2]) instead of SM / WB.
-template <typename T, bool EARLY, bool REG = false>
+template <typename T, bool EARLY, bool REG = false, int PF = 0>
 __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t, const double* __restrict__ t_sat,
          const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
          const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
@@ -38,6 +40,7 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
     const double now = __ldg(t_sat + t);
     const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
     const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
+    if (PF && !REG && !EARLY) gzb_l2_prefetch(wb);      // option "prefetch": the weights travel with the mesh
     longlong2 p1, p2, p3, p4;
     double2 wa, wc;
     if (REG) {
@@ -84,6 +87,10 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
         if (EARLY) {
             a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
             a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
+        }
+        if (PF) {      // option "prefetch": the eight field values travel while the mask word is fetched and tested
+            gzb_l2_prefetch(X1 + c1); gzb_l2_prefetch(X2 + c1); gzb_l2_prefetch(X1 + c2); gzb_l2_prefetch(X2 + c2);
+            gzb_l2_prefetch(X1 + c3); gzb_l2_prefetch(X2 + c3); gzb_l2_prefetch(X1 + c4); gzb_l2_prefetch(X2 + c4);
         }
         int ocean;
         if (mbits && *mflag == 0) {

@@ -45,7 +45,7 @@ typedef struct gzb_stats {
     int64_t  last_breaks;       /* last gzb_nearest: points whose seeding had to be replayed */
     int64_t  last_chain_steps;  /* last gzb_nearest: sequential replay steps, all chains     */
     int32_t  pyramid_levels;    /* depth of the bounding-sphere pyramid over the grid       */
-    int32_t  reserved;
+    int32_t  l2_fetch_bytes;    /* what the device reports after option "l2_fetch" (0: option never used)  */
     int64_t  lut_bins;          /* bins of the lat-lon seed table (0 = table not built)          */
     int64_t  last_unresolved;   /* last gzb_nearest: points the per-thread search handed to the warp search */
     int64_t  last_unres_noseed; /*   ... of which: no seed in the table                       */
@@ -94,6 +94,11 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * columns (two-state scan, far fewer replays); 0 plain speculation + replays.  Same results.
  * "fuse_k4": 1 (default) gzb_map_interp runs K2+K3+K4 as one kernel; 0 K2+K3 then K4.
  * "k4_early", "mask_bits": K4 variants (load order; tiled bit mask on/off).  Same results.
+ * "prefetch": 1 = the fused K2+K3+K4 kernel asks L2 for a point's eight field values and mask word as
+ * soon as its mesh is known, so they travel during the Newton solve (device-resident slabs only);
+ * 0 (default) off.  Same results.
+ * "l2_fetch": 32 / 64 / 128 = cudaLimitMaxL2FetchGranularity, a DEVICE-WIDE hint for the sparse
+ * gathers (not a per-context setting); gzb_stats.l2_fetch_bytes reports what the device answered.
  * "trace": 1 records a timing event at internal marks on both streams; gzb_sync prints them.
  * "edge_exclusion": 1 (default) gzb_nearest applies the first/last row/column rule of
  * BilinTrack.nrpt (gonzag/bilin_mapping.py:582-585); 0 gives plain NearestPoint() results.
