@@ -106,7 +106,7 @@ struct gzb_ctx {
     int ntrace = 0;
     cudaEvent_t trace_ev[48] = {};
     const char* trace_name[48] = {};
-    int pdl = 0;                     // K1 chain kernels launched with programmatic dependent launch (griddepcontrol): the next kernel's launch overlaps the tail of the previous one
+    int pdl = 1;                     // K1 chain kernels launched with programmatic dependent launch (griddepcontrol): the next kernel's launch overlaps the tail of the previous one
     int overlap = 1;                 // gzb_mapping: 1 run the chain replays beside K2+K3, 0 strictly in sequence
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     GzbGrid g;

@@ -1071,46 +1071,23 @@ k_rowsafe(const GzbGrid g, unsigned char* __restrict__ rowsafe) {
     if (threadIdx.x == 0) rowsafe[j] = (g.kew > 8 || bad) ? 0 : 1;
 }
 
-// exclusive scan of the per-block break counts (single block): every thread sums a contiguous
-// chunk, one block-wide scan of the chunk sums, then the chunk is written out
-#define SCAN_T 256
-__global__ void __launch_bounds__(SCAN_T)
-k_scan_counts(const int* __restrict__ counts, long long* __restrict__ offsets, const long long nblk,
-              long long* __restrict__ total) {
-    __shared__ long long wsum[SCAN_T / 32];
-    gzb_pdl_wait();
-    gzb_pdl_trigger();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long per = (nblk + SCAN_T - 1) / SCAN_T;
-    const long long a = (long long)threadIdx.x * per;
-    const long long b = a + per < nblk ? a + per : nblk;
-    long long v = 0;
-    for (long long k = a; k < b; ++k) v += counts[k];
-    long long s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long u = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += u;
-    }
-    if (lane == 31) wsum[warp] = s;
-    __syncthreads();
-    long long pre = s - v;
-    for (int q = 0; q < warp; ++q) pre += wsum[q];
-    for (long long k = a; k < b; ++k) {
-        offsets[k] = pre;
-        pre += counts[k];
-    }
-    if (threadIdx.x == SCAN_T - 1) *total = pre;
-}
-
-// ordered compaction of the break indices
+// ordered compaction of the break indices.  A block finds its own offset by adding up the break counts
+// of the blocks before it (a few thousand ints, L2-resident): no separate scan kernel on the critical path.
+// The last block leaves the number of breaks in *total.
 __global__ void __launch_bounds__(FLAGS_BLOCK)
-k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ offsets, const long long nt,
-          long long* __restrict__ breaks) {
+k_compact(const unsigned char* __restrict__ brk, const int* __restrict__ counts, const long long nt,
+          long long* __restrict__ breaks, long long* __restrict__ total) {
     __shared__ int wcnt[32];
+    __shared__ long long wsum[FLAGS_BLOCK / 32];
+    __shared__ long long s_off;
     gzb_pdl_wait();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long v = 0;
+    for (long long k = threadIdx.x; k < (long long)blockIdx.x; k += blockDim.x) v += counts[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) wsum[warp] = v;
     const int b = (t < nt) ? brk[t] : 0;
     const unsigned m = __ballot_sync(0xffffffffu, b);
     if (lane == 0) wcnt[warp] = __popc(m);
@@ -1124,9 +1101,15 @@ k_compact(const unsigned char* __restrict__ brk, const long long* __restrict__ o
             if (lane >= o) s += u;
         }
         wcnt[lane] = s - ww;
+        if (lane == 0) {
+            long long off = 0;
+            for (int q = 0; q < (int)(blockDim.x >> 5); ++q) off += wsum[q];
+            s_off = off;
+            if (blockIdx.x == gridDim.x - 1) *total = off + counts[blockIdx.x];
+        }
     }
     __syncthreads();
-    if (b) breaks[offsets[blockIdx.x] + wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = t;
+    if (b) breaks[s_off + wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = t;
 }
 
 // K1c, step 2/4: chain replay, one warp per break: the reference's recurrence R(t) = F_t(R(t-1))
@@ -1477,7 +1460,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     unsigned char* brk = (unsigned char*)gzb_arena_take(ctx, n);
     unsigned* agg = (unsigned*)gzb_arena_take(ctx, ((size_t)nblk + 1) * 4);      // published block maps + the ticket
     int* counts = (int*)gzb_arena_take(ctx, (size_t)nblk * 4);
-    long long* offsets = (long long*)gzb_arena_take(ctx, (size_t)nblk * 8);
+    (void)gzb_arena_take(ctx, (size_t)nblk * 8);      // (formerly the scanned offsets: kept so that the workspace layout matches gzb_nearest_ws_bytes)
     long long* breaks = (long long*)gzb_arena_take(ctx, n * 8);
     long long* stop = (long long*)gzb_arena_take(ctx, n * 8);
     long long* first = (long long*)gzb_arena_take(ctx, n * 16);
@@ -1580,9 +1563,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
                (const double*)dG, (long long*)np_out, brk, counts, (volatile unsigned*)agg, agg + nblk, chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
     gzb_trace(ctx, sb, "chain kernel end");
-    launch_dep(pdl, k_scan_counts, 1u, SCAN_T, sb, (const int*)counts, offsets, (long long)nblk, scal);
-    GZB_LAUNCH_CHECK(ctx);
-    launch_dep(pdl, k_compact, (unsigned)nblk, FLAGS_BLOCK, sb, (const unsigned char*)brk, (const long long*)offsets, (long long)nt, breaks);
+    launch_dep(pdl, k_compact, (unsigned)nblk, FLAGS_BLOCK, sb, (const unsigned char*)brk, (const int*)counts, (long long)nt, breaks, scal);
     GZB_LAUNCH_CHECK(ctx);
     long long wblocks = (long long)((n + WALK_WARPS - 1) / WALK_WARPS);
     const long long wmax = (long long)nsm * 64 / WALK_WARPS;

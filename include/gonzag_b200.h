@@ -97,6 +97,10 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * "prefetch": 1 = the fused K2+K3+K4 kernel asks L2 for a point's eight field values and mask word as
  * soon as its mesh is known, so they travel during the Newton solve (device-resident slabs only);
  * 0 (default) off.  Same results.
+ * "pdl": 1 (default) the kernels of K1's chain part (k_chain, k_compact, k_walk, k_valid), which follow each
+ * other on one stream, are launched as programmatic dependents (griddepcontrol.wait at their top): the
+ * launch of each overlaps the tail of the one before it (gzb_nearest 158 -> 143 us on ORCA12); 0 plain
+ * launches.  Same results.
  * "l2_fetch": 32 / 64 / 128 = cudaLimitMaxL2FetchGranularity, a DEVICE-WIDE hint for the sparse
  * gathers (not a per-context setting); gzb_stats.l2_fetch_bytes reports what the device answered.
  * "trace": 1 records a timing event at internal marks on both streams; gzb_sync prints them.

@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu list rc=$?"
 if [ -n "$FULL" ]; then
 # (a) the ten kernels of one gzb_map_interp step (the 4th one: after three warm-up steps)
-ncu --set full --clock-control none --import-source on -k 'regex:k_near_search|k_near_slow|k_chain|k_walk|k_valid|k_mesh_weights_interp|k_scan_counts|k_compact|k_path_fix' \
+ncu --set full --clock-control none --import-source on -k 'regex:k_near_search|k_near_slow|k_chain|k_walk|k_valid|k_mesh_weights_interp|k_compact|k_path_fix' \
     --launch-skip 30 --launch-count 10 -o $OUT/prof_$TAG -f \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full (step) rc=$?"
 # (b) the stand-alone stage kernels of the per-stage table: K2+K3 fused, K2, K3, K4

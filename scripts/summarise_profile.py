@@ -77,7 +77,7 @@ with open(os.path.join(ROOT, "profiles", rnd + "_launches_C3.csv"), "w") as f:
     for r in lr[i0 + 1:]:
         if len(r) > d and r[d].isdigit() and int(r[d]) in step:
             w.writerow(r)
-K1 = ["k_near_search", "k_near_slow", "k_chain", "k_scan_counts", "k_compact", "k_walk<0>", "k_valid", "k_walk<1>"]
+K1 = ["k_near_search", "k_near_slow", "k_chain", "k_compact", "k_walk<0>", "k_valid", "k_walk<1>"]
 per = {k: sum(v) / len(v) for k, v in traffic.items()}
 for k in step:      # kernels the full capture did not include: take the launch list's counters
     e = rec[k]
