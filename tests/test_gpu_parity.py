@@ -364,6 +364,50 @@ def test_map_interp_matches_staged(golden_global):
             assert np.array_equal(ctx.download(o2[3], (n,), np.float64), v_bl)
 
 
+def test_launch_and_memory_options_do_not_change_results(golden_global):
+    """Options that only change HOW the kernels are launched or fed -- "pdl" (programmatic dependent
+    launches of K1's chain kernels), "prefetch" (L2 prefetch of the gather, in the fused kernel and in
+    K4), "l2_fetch" (device-wide fetch-granularity hint) -- must leave every output bit-identical."""
+    import ctypes as C
+    from gonzag_b200 import _lib as L
+    g = golden_global
+    lat, lon = _grid(g)
+    res = float(g["res"])
+    rd, r = 0.75 * res * 111.11, int(0.5 * 500. / (res * 111.11))
+    y, x, t, tm, fld = g["ysat"], g["xsat"], g["tsat"], g["tmod"], g["f32"]
+    n = len(y)
+    with gzb.GridContext(lat, lon, angle=g["angle"], mask=g["mask"], k_ew_per=int(g["kew"])) as ctx:
+        d = [ctx.upload(a) for a in (L.as_f64(y), L.as_f64(x), L.as_f64(t), L.as_f64(tm), np.ascontiguousarray(fld))]
+        o = [ctx.dev_alloc(n * k) for k in (16, 64, 32, 8, 8)]
+        P = lambda b: C.c_void_p(b.ptr)
+        ref = None
+        for opts in ({"pdl": 1, "prefetch": 0}, {"pdl": 0}, {"pdl": 1, "prefetch": 1}, {"prefetch": 2},
+                     {"prefetch": 0, "l2_fetch": 32}, {"l2_fetch": 128}, {"l2_fetch": 64}):
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            # fused path on a device-resident slab (k_mesh_weights_interp: the prefetch variant applies)
+            ctx._ck(L.lib().gzb_map_interp(ctx._h, n, P(d[0]), P(d[1]), P(d[2]), rd, r, r, r, len(tm), P(d[3]), P(d[4]),
+                                           ctx._field_dtype(fld), 0, fld.shape[0], -9999., P(o[0]), P(o[1]), P(o[2]),
+                                           P(o[3]), P(o[4])))
+            ctx.sync()
+            got = [ctx.download(o[0], (n, 2), np.int64), ctx.download(o[1], (n, 4, 2), np.int64),
+                   ctx.download(o[2], (n, 4), np.float64), ctx.download(o[3], (n,), np.float64),
+                   ctx.download(o[4], (n,), np.float64)]
+            # K1 alone (the whole chain on one stream: where the dependent launches matter) and K4 alone
+            got.append(ctx.nearest(y, x, rd, r))
+            got += list(ctx.interp(t, got[1], got[2], tm, fld))
+            if ref is None:
+                ref = got
+                _report_index_mismatch("NP", got[0], g["NP"])
+                _report_index_mismatch("SM", got[1], g["SM"])
+                assert np.array_equal(got[5], got[0]) and np.array_equal(got[6], got[3]) and np.array_equal(got[7], got[4])
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b), opts
+        assert ctx.stats()["l2_fetch_bytes"] in (0, 32, 64, 128)
+        with pytest.raises(gzb.GonzagB200Error):
+            ctx.set_option("no_such_option", 1)
+
+
 def test_twin_chain_matches_replays(golden_global, golden_seam):
     """The two-state speculative chain (East-West twins resolved by a scan) must give the nearest
     points of the plain speculation + replays, and of the reference, while replaying far fewer steps."""
