@@ -392,7 +392,7 @@ __device__ __forceinline__ void prefetch_point(const GzbGrid& g, const long long
     }
 }
 
-template <typename T, bool PF>
+template <typename T, int PF>      // PF: 0 plain, 1 L2 prefetch of the gather, 3 gather with 64-byte L2 fetches
 __global__ void __launch_bounds__(128)      // 86 registers; capping it at 64 (more warps, some spills) measured 3 % slower
 k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
                       const long long* __restrict__ NP, const GzbGlobalNearest gn, long long* __restrict__ SM,
@@ -403,7 +403,7 @@ k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restr
     long long cj[4], ci[4], jP, iP;
     if (!nearest_of(g, NP, gn, t, jP, iP)) return;
     source_mesh_one(g, yT, xT, jP, iP, force_heavy, cj, ci);
-    if (PF) prefetch_point<T>(g, t, ia, cj, ci);
+    if (PF == 1) prefetch_point<T>(g, t, ia, cj, ci);
     longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
     longlong2 rp[4];
 #pragma unroll
@@ -417,7 +417,7 @@ k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restr
     const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
     out[0] = rw[0];
     out[1] = rw[1];
-    interp_point<T, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
+    interp_point<T, false, true, (PF == 3 ? 3 : 0)>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
                                  ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
 }
 
@@ -446,8 +446,9 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
 #define GZB_BULK(T, PF) k_mesh_weights_interp<T, PF><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out, \
                                                                                    wb_out, ctx->force_heavy, ia)
-    if (dtype == GZB_F32) { if (ctx->pf_now) GZB_BULK(float, true); else GZB_BULK(float, false); }
-    else                  { if (ctx->pf_now) GZB_BULK(double, true); else GZB_BULK(double, false); }
+    const int pfm = !ctx->pf_now ? 0 : (ctx->prefetch == 3 ? 3 : 1);
+    if (dtype == GZB_F32) { if (pfm == 3) GZB_BULK(float, 3); else if (pfm) GZB_BULK(float, 1); else GZB_BULK(float, 0); }
+    else                  { if (pfm == 3) GZB_BULK(double, 3); else if (pfm) GZB_BULK(double, 1); else GZB_BULK(double, 0); }
 #undef GZB_BULK
     GZB_LAUNCH_CHECK(ctx);
     ctx->time_err_pending = 1;

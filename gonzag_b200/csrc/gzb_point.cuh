@@ -6,6 +6,22 @@
 
 __device__ __forceinline__ void gzb_l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// Sparse loads with a 64-byte L2 fetch: a plain ld.global miss fills a whole 128-byte line from DRAM on B200
+// (measured, scripts/fetch_gran.cu: 125.6 B of DRAM traffic per isolated 4-byte load; 62.8 B with .L2::64B;
+// cudaLimitMaxL2FetchGranularity changes nothing).
+template <bool L64> __device__ __forceinline__ float gzb_ldg(const float* p) {
+    if (!L64) return *p;
+    float v;
+    asm volatile("ld.global.nc.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+template <bool L64> __device__ __forceinline__ double gzb_ldg(const double* p) {
+    if (!L64) return *p;
+    double v;
+    asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ long long pywrap_idx(long long k, long long n) {
     k = k < 0 ? k + n : k;                      // Python negative indexing (SM == -1 reads the last cell)
     return k < 0 ? 0 : (k >= n ? n - 1 : k);    // anything else out of range is clamped, never faults
@@ -40,7 +56,7 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
     const double now = __ldg(t_sat + t);
     const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
     const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
-    if (PF && !REG && !EARLY) gzb_l2_prefetch(wb);      // option "prefetch": the weights travel with the mesh
+    if ((PF == 1 || PF == 2) && !REG && !EARLY) gzb_l2_prefetch(wb);      // option "prefetch": the weights travel with the mesh
     longlong2 p1, p2, p3, p4;
     double2 wa, wc;
     if (REG) {
@@ -88,7 +104,7 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
             a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
             a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
         }
-        if (PF) {      // option "prefetch": the eight field values travel while the mask word is fetched and tested
+        if (PF == 1 || PF == 2) {      // option "prefetch": the eight field values travel while the mask word is fetched and tested
             gzb_l2_prefetch(X1 + c1); gzb_l2_prefetch(X2 + c1); gzb_l2_prefetch(X1 + c2); gzb_l2_prefetch(X2 + c2);
             gzb_l2_prefetch(X1 + c3); gzb_l2_prefetch(X2 + c3); gzb_l2_prefetch(X1 + c4); gzb_l2_prefetch(X2 + c4);
         }
@@ -104,9 +120,9 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
         if (!EARLY && !REG) {
             wa = wb[0]; wc = wb[1];
         }
-        if (!EARLY) {
-            a1 = X1[c1]; b1 = X2[c1]; a2 = X1[c2]; b2 = X2[c2];
-            a3 = X1[c3]; b3 = X2[c3]; a4 = X1[c4]; b4 = X2[c4];
+        if (!EARLY) {      // PF == 3: 64-byte L2 fetches for the gather (option "prefetch" = 3)
+            a1 = gzb_ldg<PF == 3>(X1 + c1); b1 = gzb_ldg<PF == 3>(X2 + c1); a2 = gzb_ldg<PF == 3>(X1 + c2); b2 = gzb_ldg<PF == 3>(X2 + c2);
+            a3 = gzb_ldg<PF == 3>(X1 + c3); b3 = gzb_ldg<PF == 3>(X2 + c3); a4 = gzb_ldg<PF == 3>(X1 + c4); b4 = gzb_ldg<PF == 3>(X2 + c4);
         }
         const T dt = (T)(tmod[lo + 1] - tmod[lo]);
         const T de = (T)(now - tmod[lo]);

@@ -34,6 +34,8 @@ stages = (("K4", lambda: eng.interp(td, SM, WB, tmod, slab, 0, v_np, v_bl)),
           ("K2K3", lambda: eng.mesh_weights(yd, xd, NP, SM, WB)),
           ("K1", lambda: eng.nearest(yd, xd, rd, r, (r, r), NP)),
           ("path", lambda: eng.map_interp(yd, xd, td, rd, r, (r, r), tmod, slab, 0, NP, SM, WB, v_np, v_bl)))
+if os.environ.get("AB_STAGES"):
+    stages = tuple(st for st in stages if st[0] in os.environ["AB_STAGES"].split(","))
 ref = {}
 flush2 = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
 sink = torch.zeros(1, dtype=torch.int64, device=dev)
