@@ -366,8 +366,8 @@ def test_map_interp_matches_staged(golden_global):
 
 def test_launch_and_memory_options_do_not_change_results(golden_global):
     """Options that only change HOW the kernels are launched or fed -- "pdl" (programmatic dependent
-    launches of K1's chain kernels), "prefetch" (L2 prefetch of the gather, in the fused kernel and in
-    K4), "l2_fetch" (device-wide fetch-granularity hint) -- must leave every output bit-identical."""
+    launches of K1's chain kernels), "prefetch" (L2 prefetch of the gather in the fused kernel and in
+    K4; 3 = 64-byte L2 fetches instead), "l2_fetch" (device-wide fetch-granularity hint) -- must leave every output bit-identical."""
     import ctypes as C
     from gonzag_b200 import _lib as L
     g = golden_global
@@ -381,7 +381,7 @@ def test_launch_and_memory_options_do_not_change_results(golden_global):
         o = [ctx.dev_alloc(n * k) for k in (16, 64, 32, 8, 8)]
         P = lambda b: C.c_void_p(b.ptr)
         ref = None
-        for opts in ({"pdl": 1, "prefetch": 0}, {"pdl": 0}, {"pdl": 1, "prefetch": 1}, {"prefetch": 2},
+        for opts in ({"pdl": 1, "prefetch": 0}, {"pdl": 0}, {"pdl": 1, "prefetch": 1}, {"prefetch": 2}, {"prefetch": 3},
                      {"prefetch": 0, "l2_fetch": 32}, {"l2_fetch": 128}, {"l2_fetch": 64}):
             for k, v in opts.items():
                 ctx.set_option(k, v)
