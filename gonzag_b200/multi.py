@@ -249,6 +249,49 @@ class ShardedMapper:
         return tc.cat(parts_np), tc.cat(parts_bl), tc.cat(parts_NP)
 
 
+def map_mission_batch(engine, dist, missions, rd, r, tmod=None, slab=None, k0=0, torch_mod=None):
+    """BASELINE config 5 (several altimeter missions onto one model grid, strong scaling): every mission
+    is cut into `world` contiguous time segments and rank g maps segment g of EVERY mission, one sharded
+    step per mission -- so each GPU gets 1/world of each mission and the grid context,
+    the model records and the kernels' workspace stay resident across missions.  A mission is a separate
+    chain: its first point is seeded with (r, r) exactly as a `BilinTrack` of its own would be
+    (gonzag/bilin_mapping.py:570); within a mission the segments hand their seed over as in
+    `ShardedMapper`.
+
+    missions: list of ``(t, y, x)`` host arrays (``t`` may be None for mapping only);
+    tmod / slab / k0: model record times (tensor), records ``k0 ..`` (tensor) -- None: K1 only.
+    Returns one ``(ssh_np, ssh_bl, NP)`` per mission, full track order, on every rank (tensors; the
+    two series are None without records)."""
+    tc = torch_mod if torch_mod is not None else engine.torch
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    results = []
+    for (t, y, x) in missions:
+        n = len(y)
+        if n < 2 * world:
+            raise ValueError("a mission of %d points cannot be cut into %d segments" % (n, world))
+        bounds = segment_bounds(n, world)
+        s0, s1 = bounds[rank], bounds[rank + 1]
+        h0 = s0 - 1 if rank > 0 else s0
+        off = s0 - h0
+        m = ShardedMapper(engine, dist if world > 1 else None, tc).make_buffers(bounds)
+        yh, xh = engine.tensor(y[h0:s1]), engine.tensor(x[h0:s1])
+        with_k4 = slab is not None and t is not None
+        if with_k4:
+            th = engine.tensor(t[h0:s1])
+            m.path_speculative(yh, xh, th, rd, r, tmod, slab, k0)
+        else:
+            m.nearest_speculative(yh, xh, rd, r)
+        g = m.gather()
+        if not m.boundaries_ok(g):                      # a chain deviation straddles a segment boundary
+            if m.reseed(g, yh[off:], xh[off:], rd, r) and with_k4:
+                m.redo_own_points(yh[off:], xh[off:], th[off:], tmod, slab, k0)
+            g = m.gather()
+        v_np, v_bl, NP = m.unpack(g)
+        results.append((v_np.clone() if with_k4 else None, v_bl.clone() if with_k4 else None, NP.clone()))
+    return results
+
+
 class P2PUnavailable(RuntimeError):
     """Raised by `P2PShardedMapper.make_buffers` ON EVERY RANK when some rank cannot map a peer's buffer;
     the caller falls back to `ShardedMapper` (NCCL all-gather)."""
