@@ -147,3 +147,46 @@ def test_overlap_and_sattrack_from_file_names(golden_grid, tmp_path, tag):
     ssh = ST.source.GetSatSSH("ssh", kt1=ST.jt1, kt2=ST.jt2, ikeep=ST.keepit)
     np.testing.assert_array_equal(ssh, g[tag + "_ssat"][ST.jt1:ST.jt2 + 1][ST.keepit] if ST.jt1 > 0 and ST.jt2 > 0
                                   else g[tag + "_ssat"][ST.keepit])
+
+
+def test_dimension_variants(tmp_path):
+    """The shapes gonzag/ncio.py accepts: 3-D coordinates (first record taken, :156), 4-D fields (surface level,
+    :204), 3-D masks (:187), mask from a 4-D field's fill value (:182), `TIME` as the record name (:77)."""
+    from scipy.io import netcdf_file
+    p = str(tmp_path / "nemo_like.nc")
+    lat2 = np.arange(6.0).reshape(2, 3)
+    fld = np.arange(2 * 2 * 2 * 3, dtype=np.float32).reshape(2, 2, 2, 3)
+    fld[:, :, 1, 2] = 1.e20
+    with netcdf_file(p, "w") as f:
+        f.createDimension("TIME", None)
+        f.createDimension("deptht", 2)
+        f.createDimension("y", 2)
+        f.createDimension("x", 3)
+        t = f.createVariable("TIME", "f8", ("TIME",))
+        t.units = "hours since 2000-01-01 00:00:00"
+        t.calendar = "gregorian"
+        t[:] = [0.0, 6.0]
+        v = f.createVariable("nav_lat", "f4", ("TIME", "y", "x"))
+        v[0] = lat2
+        v[1] = lat2 + 100.0
+        v = f.createVariable("nav_lon", "f4", ("TIME", "y", "x"))
+        v[0] = lat2 * 2
+        v[1] = 0.0
+        v = f.createVariable("thetao", "f4", ("TIME", "deptht", "y", "x"))
+        v._FillValue = np.float32(1.e20)
+        v[:] = fld
+        v = f.createVariable("tmask3", "i1", ("TIME", "y", "x"))
+        v[0] = [[1, 1, 0], [1, 0, 1]]
+        v[1] = 0
+    S = nc3io.NetCDF3Source(p)
+    assert S.GetTimeInfo() == (2, (_epoch(2000, 1, 1), _epoch(2000, 1, 1, 6)))
+    np.testing.assert_array_equal(np.ma.getdata(S.GetModelCoor("latitude")), lat2.astype(np.float32))
+    np.testing.assert_array_equal(np.ma.getdata(S.GetModelCoor("longitude")), (lat2 * 2).astype(np.float32))
+    x = S.GetModel2DVar("thetao", kt=1)
+    assert x.shape == (2, 3) and np.ma.getmaskarray(x).tolist() == [[False, False, False], [False, False, True]]
+    np.testing.assert_array_equal(np.ma.getdata(x)[0], fld[1, 0, 0])
+    assert S.GetModelLSM("_FillValue@thetao").tolist() == [[1, 1, 1], [1, 1, 0]]
+    assert S.GetModelLSM("tmask3").tolist() == [[1, 1, 0], [1, 0, 1]]
+    with pytest.raises(ValueError):
+        S.GetModelLSM("_FillValue@TIME")                    # a 1-D variable cannot give a mask
+    S.close()
