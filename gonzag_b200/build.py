@@ -20,6 +20,9 @@ LIB = os.path.join(HERE, "libgonzag_b200.so")
 SOURCES = ["gzb_grid.cu", "gzb_nearest.cu", "gzb_mesh.cu", "gzb_interp.cu", "gzb_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# experiment builds: GZB_NVCC_EXTRA="-DGZB_EXP_L64=1 -DGZB_EXP_HDG_STRIDE=8" python -m gonzag_b200.build --force
+# (compile-time variants listed in csrc/gzb_common.cuh; without the variable the build is the product)
+NVCC_FLAGS += os.environ.get("GZB_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

@@ -171,6 +171,42 @@ __device__ __forceinline__ void gzb_pdl_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void gzb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
 
+// ---- compile-time experiments (GZB_NVCC_EXTRA of gonzag_b200/build.py); all OFF in the product build ----------
+// GZB_EXP_L64=1          every sparse per-cell gather of K2 / K3 / K4 (coordinates, angle, heading table, mask words)
+//                        asks L2 for 64 bytes instead of a 128-byte line (ld.global.nc.L2::64B)
+// GZB_EXP_HDG_STRIDE=8   heading table rows of 8 doubles (64 B, one fetch) instead of 6 (48 B)
+// GZB_EXP_BULK_BLOCKS=n  __launch_bounds__(128, n) on the fused K2+K3+K4 kernel (register cap 65536 / (128 n))
+#ifndef GZB_EXP_L64
+#define GZB_EXP_L64 0
+#endif
+#ifndef GZB_EXP_HDG_STRIDE
+#define GZB_EXP_HDG_STRIDE 6
+#endif
+#ifdef __CUDACC__
+#if GZB_EXP_L64
+__device__ __forceinline__ double gzb_lds(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 gzb_lds(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L2::64B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned gzb_lds(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+#define GZB_LDS_LDG(p) gzb_lds(p)      /* replaces __ldg(p) */
+#define GZB_LDS_REF(p) gzb_lds(p)      /* replaces *(p)     */
+#else
+#define GZB_LDS_LDG(p) __ldg(p)
+#define GZB_LDS_REF(p) (*(p))
+#endif
+#endif
+
 #define GZB_LAUNCH_CHECK(ctx)                                                            \
     do {                                                                                 \
         (ctx)->stats.kernel_launches++;                                                  \

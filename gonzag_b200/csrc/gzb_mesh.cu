@@ -60,9 +60,9 @@ __device__ __forceinline__ void cell_frame(const GzbGrid& g, const long long jP,
                                            const long long jm, const long long jp, const long long im,
                                            const long long ip, double& y0, double& x0, double& hN, double& hE,
                                            double& hS, double& hW) {
-    const double2 cP = __ldg(g.ll + (jP * g.Ni + iP)), cN = __ldg(g.ll + (jp * g.Ni + iP));
-    const double2 cE = __ldg(g.ll + (jP * g.Ni + ip)), cS = __ldg(g.ll + (jm * g.Ni + iP));
-    const double2 cW = __ldg(g.ll + (jP * g.Ni + im));
+    const double2 cP = GZB_LDS_LDG(g.ll + (jP * g.Ni + iP)), cN = GZB_LDS_LDG(g.ll + (jp * g.Ni + iP));
+    const double2 cE = GZB_LDS_LDG(g.ll + (jP * g.Ni + ip)), cS = GZB_LDS_LDG(g.ll + (jm * g.Ni + iP));
+    const double2 cW = GZB_LDS_LDG(g.ll + (jP * g.Ni + im));
     const double lat0 = cP.x, lonP = cP.y, latN = cN.x, lonN = cN.y, latE = cE.x, lonE = cE.y;
     const double latS = cS.x, lonS = cS.y, latW = cW.x, lonW = cW.y;
     y0 = gzb_merc_y(lat0);
@@ -103,8 +103,8 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
         // the per-cell table when it has been built (same code, same bits)
         double y0, x0, hN, hE, hS, hW;
         if (g.hdg) {
-            const double2* __restrict__ h = reinterpret_cast<const double2*>(g.hdg + 6 * (jP * g.Ni + iP));
-            const double2 a = h[0], b = h[1], c = h[2];
+            const double2* __restrict__ h = reinterpret_cast<const double2*>(g.hdg + GZB_EXP_HDG_STRIDE * (jP * g.Ni + iP));
+            const double2 a = GZB_LDS_REF(h), b = GZB_LDS_REF(h + 1), c = GZB_LDS_REF(h + 2);
             y0 = a.x; x0 = a.y; hN = b.x; hE = b.y; hS = c.x; hW = c.y;
         } else {
             cell_frame(g, jP, iP, jm, jp, im, ip, y0, x0, hN, hE, hS, hW);
@@ -117,7 +117,7 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
             if (ht > hS && ht <= hW) iq = 3;
             if (ht > hW && hz <= hN) iq = 4;
         }
-        const double ang = g.angle ? g.angle[jP * g.Ni + iP] : 0.0;
+        const double ang = g.angle ? GZB_LDS_REF(g.angle + (jP * g.Ni + iP)) : 0.0;
         if (iq < 1 || fabs(ang) > 45.0 || force_heavy) {
             // heavy-duty: quads 4,3,2,1 in the raw (lat, lon) plane, first strict-interior hit
             for (int cand = 4; cand >= 1; --cand) {
@@ -125,7 +125,7 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
                 double qy[4], qx[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const double2 c = __ldg(g.ll + (cj[k] * g.Ni + ci[k]));
+                    const double2 c = GZB_LDS_LDG(g.ll + (cj[k] * g.Ni + ci[k]));
                     qy[k] = c.x;
                     qx[k] = c.y;
                 }
@@ -186,7 +186,7 @@ __device__ __forceinline__ void weights_one(const GzbGrid& g, const double yT, c
             long long j = pywrap(cj[k], g.Nj), i = pywrap(ci[k], g.Ni);
             j = j < 0 ? 0 : (j >= g.Nj ? g.Nj - 1 : j);
             i = i < 0 ? 0 : (i >= g.Ni ? g.Ni - 1 : i);
-            const double2 c = __ldg(g.ll + (j * g.Ni + i));
+            const double2 c = GZB_LDS_LDG(g.ll + (j * g.Ni + i));
             vy[k + 1] = c.x;
             vx[k + 1] = c.y;
         }
@@ -261,7 +261,7 @@ k_heading_table(const GzbGrid g, double* __restrict__ hdg) {
     long long jm = 0, jp = 0, im = 0, ip = 0;
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (mesh_usable(g, jP, iP, jm, jp, im, ip)) cell_frame(g, jP, iP, jm, jp, im, ip, v[0], v[1], v[2], v[3], v[4], v[5]);
-    double2* out = reinterpret_cast<double2*>(hdg + 6 * k);
+    double2* out = reinterpret_cast<double2*>(hdg + GZB_EXP_HDG_STRIDE * k);
     out[0] = make_double2(v[0], v[1]);
     out[1] = make_double2(v[2], v[3]);
     out[2] = make_double2(v[4], v[5]);
@@ -276,7 +276,7 @@ static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt) {
     const int64_t cells = ctx->g.Nj * ctx->g.Ni;
     if (ctx->hdg_mode == 1 && ctx->k2_points < cells / 2) return GZB_OK;
     if (!ctx->d_hdg) {
-        cudaError_t e = gzb_pool_malloc((void**)&ctx->d_hdg, (size_t)cells * 6 * sizeof(double));
+        cudaError_t e = gzb_pool_malloc((void**)&ctx->d_hdg, (size_t)cells * GZB_EXP_HDG_STRIDE * sizeof(double));
         if (e != cudaSuccess) {
             cudaGetLastError();
             ctx->d_hdg = nullptr;
@@ -392,8 +392,13 @@ __device__ __forceinline__ void prefetch_point(const GzbGrid& g, const long long
     }
 }
 
+#ifdef GZB_EXP_BULK_BLOCKS
+#define GZB_BULK_BOUNDS __launch_bounds__(128, GZB_EXP_BULK_BLOCKS)
+#else
+#define GZB_BULK_BOUNDS __launch_bounds__(128)
+#endif
 template <typename T, int PF>      // PF: 0 plain, 1 L2 prefetch of the gather, 3 gather with 64-byte L2 fetches
-__global__ void __launch_bounds__(128)      // 86 registers; capping it at 64 (more warps, some spills) measured 3 % slower
+__global__ void GZB_BULK_BOUNDS             // 86 registers; capping it at 64 (more warps, some spills) measured 3 % slower
 k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
                       const long long* __restrict__ NP, const GzbGlobalNearest gn, long long* __restrict__ SM,
                       double* __restrict__ WB, const int force_heavy, const InterpArgs ia) {

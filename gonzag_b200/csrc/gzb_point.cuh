@@ -31,7 +31,7 @@ __device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const
                                         const long long i) {
     const long long tile = (j >> 4) * ntI + (i >> 4);
     const int b = (int)(((j & 15) << 4) | (i & 15));
-    return (int)((__ldg(bits + tile * 8 + (b >> 5)) >> (b & 31)) & 1u);
+    return (int)((GZB_LDS_LDG(bits + tile * 8 + (b >> 5)) >> (b & 31)) & 1u);
 }
 
 // One thread per track point.  T is the dtype of the model field: the time interpolation
