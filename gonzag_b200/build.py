@@ -42,6 +42,12 @@ def _stale(target, deps):
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
+    stamp = os.path.join(OBJ, "flags.txt")          # objects compiled with other flags (an experiment build) are stale
+    flags_now = " ".join(NVCC_FLAGS)
+    if not os.path.exists(stamp) or open(stamp).read() != flags_now:
+        force = True
+    with open(stamp, "w") as f:
+        f.write(flags_now)
     headers = [os.path.join(CSRC, "gzb_common.cuh"), os.path.join(CSRC, "gzb_point.cuh"),
                os.path.join(os.path.dirname(HERE), "include", "gonzag_b200.h"), __file__]
     jobs = []
