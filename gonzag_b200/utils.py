@@ -69,17 +69,25 @@ def GridResolution(X):
     return np.mean(vx[np.where(vx < 120.)])
 
 
-def IsEastWestPeriodic(X):
+def IsEastWestPeriodic(X, tol=0.):
     """Number of overlapping columns of an East-West periodic grid, -1 if not periodic: the
     longitude one step past the last column of the middle row is looked for among the first five
-    columns (gonzag/utils.py:80-94; exact float equality, like the reference)."""
+    columns (gonzag/utils.py:80-94).  ``tol = 0`` (default) is the reference's test, exact float
+    equality -- which misses grids whose longitudes went through float32 or whose spacing is not a
+    binary fraction (a synthetic 4322-column ORCA12 gives -1).  ``tol > 0`` accepts a
+    match within ``tol`` grid steps, distances taken on the circle (0.01 is plenty)."""
     X = np.asarray(X)
     jj = X.shape[0] // 2
     iper = -1
     dx = X[jj, 1] - X[jj, 0]
     lon_last_p1 = (X[jj, -1] + dx) % 360.
     for it in range(min(5, X.shape[1])):
-        if lon_last_p1 == X[jj, it] % 360.:
+        if tol > 0.:
+            d = abs(lon_last_p1 - X[jj, it] % 360.)
+            hit = min(d, 360. - d) <= tol * abs(dx)
+        else:
+            hit = lon_last_p1 == X[jj, it] % 360.
+        if hit:
             iper = it
             break
     return iper
@@ -141,9 +149,10 @@ def GetEpochTimeOverlap(ncfile_sat, ncfile_mod):
 class ModGrid:
     """Model (source) grid: ``size, shape, time, lat, lon, mask, HResDeg, HResKM, IsLonGlobal,
     l360, EWPer, IsDistorded, xangle, domain_bounds, file`` as the reference's `ModGrid`
-    (gonzag/utils.py:369-466), plus ``ctx``: the grid resident on GPU ``device``."""
+    (gonzag/utils.py:369-466), plus ``ctx``: the grid resident on GPU ``device``.  ``ew_tolerance``: see
+    `IsEastWestPeriodic` (0 = the reference's exact-equality periodicity test)."""
 
-    def __init__(self, ncfile, rtu1, rtu2, nclsm, varlsm, distorded_grid=False, device=0):
+    def __init__(self, ncfile, rtu1, rtu2, nclsm, varlsm, distorded_grid=False, device=0, ew_tolerance=0.):
         src = as_source(ncfile)
         self.file = src if not hasattr(src, "path") else src.path
         self.source = src
@@ -189,7 +198,7 @@ class ModGrid:
         self.ctx._ck(L.lib().gzb_lon_stats(self.ctx._h, L.ptr(vals), L.ptr(cols)))
         self.IsLonGlobal, self.l360, lon_min, lon_max = _global_lonwise(
             self.shape[1], vals[0], vals[1], int(cols[0]), int(cols[1]), vals[2], vals[3], self.HResDeg)
-        self.EWPer = IsEastWestPeriodic(self.lon) if self.IsLonGlobal else -1
+        self.EWPer = IsEastWestPeriodic(self.lon, tol=ew_tolerance) if self.IsLonGlobal else -1    # tol 0 = the reference's exact test
         self.ctx.set_ew_per(self.EWPer)
         la0, la1 = C.c_double(), C.c_double()
         self.ctx._ck(L.lib().gzb_lat_range(self.ctx._h, C.byref(la0), C.byref(la1)))

@@ -107,3 +107,22 @@ def test_netcdf_writers(tmp_path):
         assert f.variables["nav_lon"].shape == (3, 4)
     with pytest.raises(ValueError):
         gz.SaveTimeSeries(t[:3], xd, ["a", "b", "c"], path)
+
+
+def test_periodicity_test_hardening():
+    """`IsEastWestPeriodic(X, tol)`: tol = 0 is the reference's exact equality (kept as the default, pinned by the
+    known answers above); a tolerance recovers the overlap of grids the exact test misses."""
+    from gonzag_b200 import synthetic as syn
+    for kew in (0, 1, 2):
+        nx = 90 + kew
+        lon = np.tile((4.0 * np.arange(nx)) % 360.0, (5, 1))              # exact in binary: both tests agree
+        assert gz.IsEastWestPeriodic(lon) == kew and gz.IsEastWestPeriodic(lon, tol=0.01) == kew
+    step = 360.0 / 4320.0                                                  # 1/12 degree: not a binary fraction
+    lon = np.tile(step * np.arange(4322), (3, 1))
+    lon32 = lon.astype(np.float32).astype(np.float64)                      # "file-like": through float32
+    assert gz.IsEastWestPeriodic(lon32) == -1                              # the reference's answer (SURVEY 7-10)
+    assert gz.IsEastWestPeriodic(lon32, tol=0.01) == 2
+    assert gz.IsEastWestPeriodic(lon, tol=0.01) == 2
+    assert gz.IsEastWestPeriodic(np.tile(np.linspace(100.0, 140.0, 81), (3, 1)), tol=0.01) == -1      # regional: still none
+    lat, glon = syn.orca_like_grid(60, 122)
+    assert gz.IsEastWestPeriodic(glon, tol=0.01) in (-1, 0, 1, 2)
