@@ -33,6 +33,8 @@ def parse(argv=None):
     p.add_argument("-D", "--distgrid", action="store_true", help="account for strong local distortion of the model grid")
     p.add_argument("-o", "--outdir", default=".", help="where result.nc and xnp_msk.nc go (default: current directory)")
     p.add_argument("--device", type=int, default=0, help="CUDA device")
+    p.add_argument("--ew-tolerance", type=float, default=0., help="tolerance (in grid steps) of the East-West periodicity "
+                   "test; 0 = the reference's exact float equality")
     return p.parse_args(argv)
 
 
@@ -45,7 +47,7 @@ def main(argv=None):
     print(' *** Time overlap between model and satellite in UNIX epoch time: it1, it2', it1, '--', it2)
     print('   => UTC: "' + EpochT2Str(it1) + '" to "' + EpochT2Str(it2) + '"\n')
     clsm = vlsm + "@" + a.vmod if vlsm == "_FillValue" else vlsm
-    MG = ModGrid(a.fmod, it1, it2, flsm, clsm, distorded_grid=a.distgrid, device=a.device)
+    MG = ModGrid(a.fmod, it1, it2, flsm, clsm, distorded_grid=a.distgrid, device=a.device, ew_tolerance=a.ew_tolerance)
     try:
         ST = SatTrack(a.fsat, it1, it2, Np=Nts, domain_bounds=MG.domain_bounds, l_0_360=MG.l360)
         RES = Model2SatTrack(MG, a.vmod, ST, a.vsat, device=a.device)
