@@ -8,19 +8,24 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over the
 of the workload:  K1 nearest points + K2 source mesh + K3 weights + K4 time/space gather.
 
   value     device-resident throughput: grid context, track, model records already in HBM;
-            timed with CUDA events on the launching stream, L2 flushed between steps.
+            timed with CUDA events on the launching stream, L2 flushed between steps (a write
+            pass, then a read pass of a second scratch buffer so that L2 starts clean).
   e2e       the same metric through the public drop-in API `Model2SatTrack(MG, .., ST, ..)` with
             HOST buffers (pinned model records): grid + track + record H2D, kernels, result D2H
             are all inside the timed region.
-  roofline  for the kernel that dominates the step (and, under "kernels", for each stage).
+  roofline  for the ONE kernel that dominates the step, k_mesh_weights_interp (K2+K3+K4 of a point in
+            registers), launched alone through gzb_mesh_weights_interp: fused algorithmic bytes
+            (260 + 8 s B/point) / CUDA-event time; `gather_kernel` = the same for K4 alone; under
+            "kernels", every stage.
   cpu_baseline  the CPU oracle (NumPy port of the reference) on a bounded prefix of the same
             workload, 1 core.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port: the reference is pure
 Python and is not present on the GPU box) on all host cores, bounded sample per step.
 Multi-GPU: launched by torchrun, one rank per GPU; the track is time-sharded (weak scaling:
-each rank maps its own 10-day segment of one long track), grid replicated, one NCCL all-gather
-of the products at the end of the step.
+each rank maps its own 10-day segment of one long track), grid replicated; the gather of the
+products is fused into K4 (stores into every rank's buffer over NVLink, --gather p2p, default)
+or done by one NCCL all-gather at the end of the step (--gather nccl).
 """
 from __future__ import annotations
 
