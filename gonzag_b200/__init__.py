@@ -6,15 +6,18 @@ from .config import *                                   # noqa: F401,F403
 from ._lib import GonzagB200Error, device_count        # noqa: F401
 from .context import GridContext                        # noqa: F401
 from .bilin_mapping import (BilinTrack, NearestPoint, Iquadran, IDSourceMesh, AlfaBeta, WeightBL,   # noqa: F401
-                            Heading, release_cached_context)
+                            Heading, IQH, surrounding_j_i, Iquadran2SrcMesh, release_cached_context)
 from .mod2sat import Model2SatTrack                     # noqa: F401
 from .utils import (GridAngle, SearchBoxSize, degE_to_degWE, GridResolution, IsEastWestPeriodic,       # noqa: F401
-                    IsGlobalLongitudeWise, scan_idx, GetEpochTimeOverlap, EpochT2Str, ModGrid, SatTrack, MsgExit)
+                    IsGlobalLongitudeWise, scan_idx, GetEpochTimeOverlap, EpochT2Str, ModGrid, SatTrack, MsgExit,
+                    Haversine, Haversine_sclr, RadiusEarth, find_j_i_min, find_j_i_max, chck4f)
 from .sources import ModelArrays, TrackArrays           # noqa: F401
 from .nc3io import NetCDF3Source                        # noqa: F401
 from .ncout import SaveTimeSeries, Save2Dfield          # noqa: F401
 
-__all__ = ["BilinTrack", "NearestPoint", "Iquadran", "IDSourceMesh", "AlfaBeta", "WeightBL", "Heading",
+__all__ = ["BilinTrack", "NearestPoint", "Iquadran", "IDSourceMesh", "AlfaBeta", "WeightBL", "Heading", "IQH",
+           "surrounding_j_i", "Iquadran2SrcMesh", "Haversine", "Haversine_sclr", "RadiusEarth", "find_j_i_min",
+           "find_j_i_max", "chck4f", "MsgExit",
            "Model2SatTrack", "GridContext", "GridAngle", "SearchBoxSize",
            "degE_to_degWE", "GonzagB200Error", "device_count", "GridResolution", "IsEastWestPeriodic",
            "IsGlobalLongitudeWise", "scan_idx", "GetEpochTimeOverlap", "EpochT2Str", "ModGrid", "SatTrack",

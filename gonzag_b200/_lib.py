@@ -72,6 +72,8 @@ _SIGNATURES = {
     "gzb_heading": (C.c_int, [C.c_int, _I64, _P, _P, _P, _P, _P]),
     "gzb_alfabeta": (C.c_int, [C.c_int, _I64, _P, _P, _P]),
     "gzb_haversine": (C.c_int, [C.c_int, _I64, C.c_double, C.c_double, _P, _P, _P]),
+    "gzb_haversine_sclr": (C.c_int, [C.c_int, _I64, _P, _P, _P, _P, _P]),
+    "gzb_radius_earth": (C.c_int, [C.c_int, _I64, _P, _P]),
     "gzb_dev_alloc": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),
     "gzb_dev_free": (C.c_int, [_P, _P]),
     "gzb_h2d": (C.c_int, [_P, _P, _P, C.c_uint64]),

@@ -81,8 +81,10 @@ def NearestPoint(pcoor_trg, Ys, Xs, rd_found_km=10., resolkm=[], j_prv=None, i_p
     return [int(NP[0, 0]), int(NP[0, 1])]
 
 
-def _neighbours(jP, iP, Ny, Nx, k_ew_per):
-    # index bookkeeping of gonzag/bilin_mapping.py:194-212
+def surrounding_j_i(jP, iP, Ny, Nx, k_ew_per=-1):
+    """(jP-1, jP+1, iP-1, iP+1) with the East-West wrap, -1 where the index does not exist
+    (gonzag/bilin_mapping.py:194-212).  Integer bookkeeping, done on the host like in the reference; the
+    kernels carry their own copy (gzb_mesh.cu)."""
     jm, jp, im, ip = jP - 1, jP + 1, iP - 1, iP + 1
     if jp == Ny:
         jp = -1
@@ -91,6 +93,63 @@ def _neighbours(jP, iP, Ny, Nx, k_ew_per):
     if ip == Nx:
         ip = k_ew_per if k_ew_per >= 0 else -1
     return jm, jp, im, ip
+
+
+def _neighbours(jP, iP, Ny, Nx, k_ew_per):
+    return surrounding_j_i(jP, iP, Ny, Nx, k_ew_per=k_ew_per)
+
+
+_QUADRANT_CORNERS = {   # iquadran -> (P2, P3, P4) as offsets picked from (jm, jp, im, ip); gonzag/bilin_mapping.py:240-262
+    1: (("j", "ip"), ("jp", "ip"), ("jp", "i")),
+    2: (("jm", "i"), ("jm", "ip"), ("j", "ip")),
+    3: (("j", "im"), ("jm", "im"), ("jm", "i")),
+    4: (("jp", "i"), ("jp", "im"), ("j", "im")),
+}
+
+
+def Iquadran2SrcMesh(jP, iP, Ny, Nx, iqd, k_ew_per=1):
+    """The (j,i) pairs of the 3 points that close the source mesh around the nearest point for quadrant `iqd`
+    (gonzag/bilin_mapping.py:215-262).  Exits the reference's way on a bad `iqd` or an incomplete
+    neighbourhood."""
+    from .utils import MsgExit
+    if iqd not in (1, 2, 3, 4):
+        MsgExit('[Iquadran2SrcMesh()] non-valid "iquadran" value')
+    jm, jp, im, ip = surrounding_j_i(jP, iP, Ny, Nx, k_ew_per=k_ew_per)
+    if -1 in (jm, jp, im, ip):
+        MsgExit('you should not see this! [ Iquadran2SrcMesh() ]')
+    v = {"j": jP, "i": iP, "jm": jm, "jp": jp, "im": im, "ip": ip}
+    return tuple((v[a], v[b]) for a, b in _QUADRANT_CORNERS[iqd])
+
+
+def IQH(yA, xA, yB, xB, vY, vX):
+    """Through which side of the quadrangle (vY, vX: bottom-left, bottom-right, upper-right, upper-left) the
+    segment from A (inside) to B (outside) leaves: (1,'down'), (2,'right'), (3,'up'), (4,'left')
+    (gonzag/bilin_mapping.py:267-312).  The five headings are one batched `gzb_heading` call; like the
+    reference, four independent tests on un-wrapped headings with the last true one winning, and an exit when
+    none is (as written there only 'up' can hold for a quad whose corners lie in their usual directions: the
+    other three tests would need a heading interval across 0/360; kept as is, the golden vectors show it)."""
+    lonA = float(xA) % 360.
+    la = np.full(5, float(yA))
+    lo = np.full(5, lonA)
+    lb = np.array([float(yB)] + [float(vY[k]) for k in range(4)])
+    ob = np.array([float(xB) % 360.] + [float(vX[k]) % 360. for k in range(4)])
+    h = np.empty(5)
+    L.check(L.lib().gzb_heading(0, 5, L.ptr(la), L.ptr(lo), L.ptr(lb), L.ptr(ob), L.ptr(h)))
+    ht, hBL, hBR, hUR, hUL = (float(v) for v in h)
+    idir, cdir = -1, 'nowhere'
+    if ht > hBL and ht < hBR:
+        idir, cdir = 1, 'down'
+    if ht > hBR and ht < hUR:
+        idir, cdir = 2, 'right'
+    if ht > hUR and ht < hUL:
+        idir, cdir = 3, 'up'
+    if ht > hUL and ht < hBL:
+        idir, cdir = 4, 'left'
+    if idir not in (1, 2, 3, 4):
+        from .utils import GonzagExit
+        print('ERROR [IQH]: no side of the quadrangle found!')
+        raise GonzagExit(0)
+    return idir, cdir
 
 
 def _mesh_one(pcoor_trg, Ys, Xs, jP, iP, k_ew_per, grid_s_angle, lforceHD):

@@ -275,28 +275,8 @@ extern "C" int gzb_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64
 }
 
 // ------------------------------------------------------------------------------------------
-// along-track distance: per-step Haversine_sclr (gonzag/utils.py:267-293) then a prefix sum
-#define GZB_REQ2 40680631.59076899   /* 6378.137**2 */
-#define GZB_RPL2 40408295.989504     /* 6356.752**2 */
-
-__device__ __forceinline__ double radius_earth_dev(double lat) {
-    const double p = lat * GZB_D2R;
-    const double cp = cos(p), sp = sin(p);
-    const double c0 = GZB_REQ2 * cp, d0 = GZB_RPL2 * sp, e0 = 6378.137 * cp, f0 = 6356.752 * sp;
-    return sqrt((c0 * c0 + d0 * d0) / (e0 * e0 + f0 * f0));
-}
-
-__device__ __forceinline__ double haversine_sclr_dev(double lat1, double lon1, double lat2, double lon2) {
-    const double R = radius_earth_dev(0.5 * (lat1 + lat2));
-    const double dlat = (lat2 - lat1) * GZB_D2R;
-    const double dlon = (lon2 - lon1) * GZB_D2R;
-    const double p1 = lat1 * GZB_D2R, p2 = lat2 * GZB_D2R;
-    const double s1 = sin(dlat / 2.0), s2 = sin(dlon / 2.0);
-    const double a = s1 * s1 + cos(p1) * cos(p2) * (s2 * s2);
-    return R * (2.0 * asin(sqrt(a)));
-}
-
-// block-local inclusive scan of the step lengths; block totals go to `tot`
+// along-track distance: per-step Haversine_sclr (gonzag/utils.py:267-293, device code in gzb_point.cuh) then a
+// prefix sum.  block-local inclusive scan of the step lengths; block totals go to `tot`
 __global__ void __launch_bounds__(1024)
 k_dist_blocks(const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
               double* __restrict__ out, double* __restrict__ tot) {

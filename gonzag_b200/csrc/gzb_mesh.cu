@@ -516,6 +516,18 @@ __global__ void k_haversine(long long n, double plat, double plon, const double*
     if (k < n) o[k] = gzb_haversine_dev(plat, plon, cos(plat * GZB_D2R), la[k], lo[k]);
 }
 
+// Haversine_sclr(lat1,lon1,lat2,lon2) and RadiusEarth(lat) (gonzag/utils.py:267-293): the device functions of the
+// along-track distance kernels, one problem per thread
+__global__ void k_haversine_sclr(long long n, const double* a, const double* b, const double* c, const double* d, double* o) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) o[k] = haversine_sclr_dev(a[k], b[k], c[k], d[k]);
+}
+
+__global__ void k_radius_earth(long long n, const double* lat, double* o) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) o[k] = radius_earth_dev(lat[k]);
+}
+
 namespace {
 struct TmpDev {
     void* p = nullptr;
@@ -584,5 +596,28 @@ extern "C" int gzb_haversine(int device, int64_t n, double plat, double plon, co
     h_plon = plon;
     return helper_run(device, 2 * (size_t)n, (size_t)n, ins, sz, 2, out, [](double** d, double* o) {
         k_haversine<<<(unsigned)((h_n + 255) / 256), 256>>>(h_n, h_plat, h_plon, d[0], d[1], o);
+    });
+}
+
+extern "C" int gzb_haversine_sclr(int device, int64_t n, const double* lat1, const double* lon1, const double* lat2,
+                                  const double* lon2, double* out) {
+    if (n <= 0) return GZB_OK;
+    if (!lat1 || !lon1 || !lat2 || !lon2 || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_haversine_sclr: null argument");
+    const double* ins[4] = {lat1, lon1, lat2, lon2};
+    const size_t sz[4] = {(size_t)n, (size_t)n, (size_t)n, (size_t)n};
+    h_n = n;
+    return helper_run(device, 4 * (size_t)n, (size_t)n, ins, sz, 4, out, [](double** d, double* o) {
+        k_haversine_sclr<<<(unsigned)((h_n + 255) / 256), 256>>>(h_n, d[0], d[1], d[2], d[3], o);
+    });
+}
+
+extern "C" int gzb_radius_earth(int device, int64_t n, const double* lat, double* out) {
+    if (n <= 0) return GZB_OK;
+    if (!lat || !out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_radius_earth: null argument");
+    const double* ins[1] = {lat};
+    const size_t sz[1] = {(size_t)n};
+    h_n = n;
+    return helper_run(device, (size_t)n, (size_t)n, ins, sz, 1, out, [](double** d, double* o) {
+        k_radius_earth<<<(unsigned)((h_n + 255) / 256), 256>>>(h_n, d[0], o);
     });
 }

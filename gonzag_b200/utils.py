@@ -36,6 +36,61 @@ def MsgExit(cmsg):
     raise GonzagExit(0)
 
 
+def chck4f(ncfile):
+    """Exit the reference's way when a file is missing (gonzag/utils.py:19-22)."""
+    from os.path import exists
+    if not exists(ncfile):
+        MsgExit('File ' + ncfile + ' does not exist')
+
+
+def find_j_i_min(x):
+    """(j, i) of the first minimum of a 2-D array in row-major order (gonzag/utils.py:48-55).  Index
+    bookkeeping on a caller's array: host NumPy, like the reference (on the mapping path the argmin is
+    part of kernel K1 and never comes through here)."""
+    k = x.argmin()
+    nx = x.shape[1]
+    return k // nx, k % nx
+
+
+def find_j_i_max(x):
+    """(j, i) of the first maximum of a 2-D array (gonzag/utils.py:57-64)."""
+    k = x.argmax()
+    nx = x.shape[1]
+    return k // nx, k % nx
+
+
+def Haversine(plat, plon, xlat, xlon, device=0):
+    """Distance in km (R = 6360 km) from the point (plat, plon) to every point of the arrays `xlat`, `xlon`
+    (gonzag/utils.py:296-316): the formula K1 evaluates, batched on the GPU (`gzb_haversine`).  Returns
+    float64 with the shape of `xlat`."""
+    la, lo = L.as_f64(xlat), L.as_f64(xlon)
+    if la.shape != lo.shape:
+        raise ValueError("xlat and xlon must have the same shape")
+    out = np.empty(la.shape, dtype=np.float64)
+    L.check(L.lib().gzb_haversine(int(device), la.size, float(plat), float(plon), L.ptr(la), L.ptr(lo), L.ptr(out)))
+    return out
+
+
+def Haversine_sclr(lat1, lon1, lat2, lon2, device=0):
+    """Distance in km between two points with the latitude-dependent Earth radius (gonzag/utils.py:281-293),
+    the per-step length of the along-track distance (`gzb_haversine_sclr`).  Scalars in, float out; arrays of
+    equal shape are accepted too (one distance per element)."""
+    a = [L.as_f64(np.atleast_1d(v)) for v in (lat1, lon1, lat2, lon2)]
+    if any(v.shape != a[0].shape for v in a):
+        raise ValueError("the four arguments must have the same shape")
+    out = np.empty(a[0].shape, dtype=np.float64)
+    L.check(L.lib().gzb_haversine_sclr(int(device), a[0].size, *[L.ptr(v) for v in a], L.ptr(out)))
+    return float(out[0]) if np.shape(lat1) == () else out
+
+
+def RadiusEarth(lat, device=0):
+    """Radius of the Earth in km at latitude `lat` (degrees North), gonzag/utils.py:267-278 (`gzb_radius_earth`)."""
+    a = L.as_f64(np.atleast_1d(lat))
+    out = np.empty(a.shape, dtype=np.float64)
+    L.check(L.lib().gzb_radius_earth(int(device), a.size, L.ptr(a), L.ptr(out)))
+    return float(out[0]) if np.shape(lat) == () else out
+
+
 def SearchBoxSize(res_mod, width_box):
     """Half-width, in grid points, of the first-attempt search box (gonzag/utils.py:97-110)."""
     return int(0.5 * width_box / res_mod)

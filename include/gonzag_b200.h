@@ -222,12 +222,17 @@ int gzb_xnp_track_masked(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmi
  * gzb_heading  : Heading(lata,lona,latb,lonb)      gonzag/bilin_mapping.py:16-47
  * gzb_alfabeta : AlfaBeta(vy[5], vx[5]) -> (a,b)   gonzag/bilin_mapping.py:50-141
  * gzb_haversine: Haversine(plat,plon,xlat,xlon)     gonzag/utils.py:296-316
+ * gzb_haversine_sclr: Haversine_sclr(lat1,lon1,lat2,lon2) gonzag/utils.py:281-293 (latitude-dependent radius)
+ * gzb_radius_earth  : RadiusEarth(lat)                     gonzag/utils.py:267-278
  * All arrays HOST, n independent problems per call; they run on `device`. */
 int gzb_heading(int device, int64_t n, const double* lata, const double* lona,
                 const double* latb, const double* lonb, double* out);
 int gzb_alfabeta(int device, int64_t n, const double* vy5, const double* vx5, double* ab_out);
 int gzb_haversine(int device, int64_t n, double plat, double plon, const double* xlat,
                   const double* xlon, double* out);
+int gzb_haversine_sclr(int device, int64_t n, const double* lat1, const double* lon1,
+                       const double* lat2, const double* lon2, double* out);
+int gzb_radius_earth(int device, int64_t n, const double* lat, double* out);
 
 /* ---- multi-GPU, one process per GPU: K4 fused with the gather of its results ----------------
  * A rank exports its product buffer (gzb_dev_alloc memory) with gzb_ipc_export; the 64-byte handle

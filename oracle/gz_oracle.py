@@ -239,6 +239,30 @@ def mesh_from_quadrant(jP, iP, Ny, Nx, iq, k_ew_per=1):
     return p2, p3, p4
 
 
+def side_of_exit(yA, xA, yB, xB, vY, vX):
+    """gonzag/bilin_mapping.py:267-312 (`IQH`, exported but not called on the path): the side of the quad
+    (corners bottom-left, bottom-right, upper-right, upper-left) the segment A -> B leaves through, 1..4
+    = down, right, up, left; -1 where the reference prints an error and exits.  Four independent tests on
+    un-wrapped headings, last true wins -- as written there, only 'up' can ever be true for a quad whose
+    corners sit in their usual directions."""
+    lonA = xA % 360.0
+    ht = heading(yA, lonA, yB, xB % 360.0)
+    hBL = heading(yA, lonA, vY[0], vX[0] % 360.0)
+    hBR = heading(yA, lonA, vY[1], vX[1] % 360.0)
+    hUR = heading(yA, lonA, vY[2], vX[2] % 360.0)
+    hUL = heading(yA, lonA, vY[3], vX[3] % 360.0)
+    idir = -1
+    if ht > hBL and ht < hBR:
+        idir = 1
+    if ht > hBR and ht < hUR:
+        idir = 2
+    if ht > hUR and ht < hUL:
+        idir = 3
+    if ht > hUL and ht < hBL:
+        idir = 4
+    return idir
+
+
 def point_strictly_in_quad(py, px, qy, qx):
     """Planar point-in-quadrilateral, interior only (a point on an edge or vertex is
     outside).  Stand-in for ``shapely`` ``Polygon.contains(Point)`` at

@@ -45,6 +45,11 @@ def golden_grid():
     return load_golden("grid")
 
 
+@pytest.fixture(scope="session")
+def golden_surface():
+    return load_golden("surface")          # tests/golden/make_golden_surface.py
+
+
 def grid_case_sources(g, tag):
     """The in-memory data sets of tests/golden/make_golden.py:case_grid, rebuilt from the fixture."""
     from gonzag_b200.sources import ModelArrays, TrackArrays
