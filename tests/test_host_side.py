@@ -101,3 +101,45 @@ def test_synthetic_inputs_have_the_advertised_shape():
     rd, r = syn.search_params(1.0 / 12.0)
     assert r == 26 or r == 27
     assert abs(rd - 0.75 * 111.11 / 12.0) < 1e-9
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/gonzag_b200.h is the boundary a non-Python host binds: it must compile as C99 with warnings as
+    errors, and a C program must link against the library and get the argument checks the ABI promises (no
+    device needed for those)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gonzag_b200.h"
+int main(void) {
+    gzb_ctx* h = NULL;
+    gzb_stats st;
+    double lat[4] = {0, 0, 1, 1}, lon[4] = {0, 1, 0, 1};
+    memset(&st, 0, sizeof st);
+    if (!strstr(gzb_version(), "sm_100a")) return 1;
+    if (gzb_create(0, 2, 2, lat, lon, NULL, NULL, -1, &h) != GZB_ERR_ARG || h != NULL) return 2;   /* grid too small */
+    if (gzb_create(0, 3, 3, NULL, lon, NULL, NULL, -1, &h) != GZB_ERR_ARG) return 3;
+    if (!gzb_last_global_error() || !gzb_last_global_error()[0]) return 4;
+    if (gzb_sync(NULL) != GZB_ERR_ARG || gzb_destroy(NULL) != GZB_OK) return 5;
+    if (gzb_heading(0, 0, NULL, NULL, NULL, NULL, NULL) != GZB_OK) return 6;               /* n = 0: nothing to do */
+    if (gzb_radius_earth(0, 3, NULL, NULL) != GZB_ERR_ARG) return 7;
+    if (gzb_haversine_sclr(0, 3, lat, lon, lat, NULL, lat) != GZB_ERR_ARG) return 8;
+    printf("sizeof(gzb_stats)=%u\n", (unsigned)sizeof(gzb_stats));
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(built)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-lgonzag_b200", "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "sizeof(gzb_stats)=%d" % ctypes.sizeof(L.Stats) in r.stdout          # the ctypes mirror has the same layout
