@@ -83,7 +83,12 @@ class GridContext:
             raise ValueError("mask has shape %s, grid is %s" % (m.shape, (self.Nj, self.Ni)))
         if m.dtype in (np.int8, np.uint8, np.bool_):
             return np.ascontiguousarray(m).view(np.int8)
-        return np.ascontiguousarray(m.astype(np.int8))     # a {0,1} land-sea mask (gonzag/ncio.py:164-191)
+        if m.dtype.kind in "iu" and m.dtype.isnative and m.flags["C_CONTIGUOUS"]:
+            # the reference's int64 {0,1} mask (gonzag/ncio.py:164-191): astype(int8) on the library's host threads
+            m8 = np.empty(m.shape, dtype=np.int8)
+            L.check(L.lib().gzb_pack_mask(L.ptr(m), m.dtype.itemsize, m.size, L.ptr(m8)))
+            return m8
+        return np.ascontiguousarray(m.astype(np.int8))
 
     def _ck(self, code):
         L.check(code, self._h)

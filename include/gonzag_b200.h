@@ -275,6 +275,11 @@ int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes);          
 int gzb_pool_config(int enabled, uint64_t max_cached_bytes);
 int gzb_pool_trim(void);
 int gzb_pool_stats(uint64_t* cached_bytes, uint64_t* cached_blocks, uint64_t* live_blocks);
+/* Host-only helper (no device, no context): dst[k] = (int8_t)src[k] for an integer land-sea mask of
+ * `itemsize` 1, 2, 4 or 8 bytes -- the reference's MG.mask is int64 {0,1} (gonzag/ncio.py:164-191), the
+ * context takes int8 -- cut over the host threads (NumPy's single-threaded astype costs a third of an
+ * end-to-end call on ORCA12). */
+int gzb_pack_mask(const void* src, int itemsize, int64_t n, int8_t* dst);
 /* Where does `p` live?  kind_out: 0 pageable host memory (or unknown), 1 pinned + mapped host
  * memory (the GPU can read it in place), 2 device / managed memory. */
 int gzb_pointer_kind(const void* p, int* kind_out);

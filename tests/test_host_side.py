@@ -1,6 +1,7 @@
 """CPU-only tests: the C ABI library loads and exports what include/gonzag_b200.h declares,
 the host-side planning logic, and the failure mode without a GPU (no CPU fallback)."""
 import ctypes
+import types
 import os
 
 import numpy as np
@@ -143,3 +144,34 @@ int main(void) {
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "sizeof(gzb_stats)=%d" % ctypes.sizeof(L.Stats) in r.stdout          # the ctypes mirror has the same layout
+
+
+def test_pack_mask_equals_astype(built):
+    """gzb_pack_mask (host-only, threaded): the int64 {0,1} mask of the reference -> int8, for every integer width,
+    lengths around the thread / alignment boundaries, and values whose low byte matters."""
+    rng = np.random.default_rng(0)
+    for dt in (np.int64, np.int32, np.int16, np.uint16, np.uint32, np.uint64, np.int8):
+        info = np.iinfo(dt)
+        for n in (0, 1, 5, 63, 64, 65, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 2500001):
+            m = rng.integers(max(info.min, -70000), min(info.max, 70000), n).astype(dt)
+            o = np.full(n + 1, 77, np.int8)
+            L.check(L.lib().gzb_pack_mask(L.ptr(m), m.dtype.itemsize, n, L.ptr(o)))
+            assert np.array_equal(o[:n], m.astype(np.int8)) and o[n] == 77, (dt, n)
+    assert L.lib().gzb_pack_mask(None, 8, 4, None) == L.GZB_ERR_ARG
+    assert L.lib().gzb_pack_mask(L.ptr(np.zeros(4)), 3, 4, L.ptr(np.zeros(4, np.int8))) == L.GZB_ERR_ARG
+
+
+def test_mask8_paths():
+    """GridContext._mask8 without a device: int64 (the reference's dtype) through gzb_pack_mask, int8 / bool viewed,
+    anything else through NumPy; masked arrays contribute their data."""
+    from gonzag_b200.context import GridContext
+    fake = types.SimpleNamespace(Nj=7, Ni=9)
+    rng = np.random.default_rng(1)
+    m = (rng.uniform(size=(7, 9)) < 0.6).astype(np.int64)
+    for arr in (m, m.astype(np.int32), m.astype(np.int8), m.astype(bool), m.astype(np.float64), m[:, ::-1],
+                np.ma.masked_array(m, mask=(m == 0)), np.asfortranarray(m)):
+        got = GridContext._mask8(fake, arr)
+        assert got.dtype == np.int8 and got.flags["C_CONTIGUOUS"]
+        np.testing.assert_array_equal(got, np.ma.getdata(arr).astype(np.int8))
+    with pytest.raises(ValueError):
+        GridContext._mask8(fake, m[:, :-1])
