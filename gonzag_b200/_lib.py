@@ -90,6 +90,7 @@ _SIGNATURES = {
     "gzb_peer_barrier": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _I64]),
     "gzb_check_edges": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P]),
     "gzb_pack_mask": (C.c_int, [_P, C.c_int, _I64, _P]),
+    "gzb_copy_swap": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int]),
     "gzb_pointer_kind": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "gzb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "gzb_host_free": (C.c_int, [_P]),

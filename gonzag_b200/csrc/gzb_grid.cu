@@ -1545,3 +1545,61 @@ extern "C" int gzb_pack_mask(const void* src, int itemsize, int64_t n, int8_t* d
     for (auto& t : th) t.join();
     return GZB_OK;
 }
+
+// ======================================================================== host-side record staging
+// Model records read from a NetCDF-3 file are big-endian views of the memory map; NumPy's byte-swapping
+// copy into the pinned staging slab is one thread (~25 ms per ORCA12 record, against a gather kernel that
+// needs 40 us for 10 days of track).  dst[k] = src[k] with the bytes of every item reversed when `swap`
+// is non-zero (plain copy otherwise), cut over the host threads.  itemsize 1, 2, 4 or 8; src and dst must
+// not overlap.  Pure host code: no device, no context.
+namespace {
+template <typename T> inline T bswap_item(T v);
+template <> inline uint16_t bswap_item(uint16_t v) { return __builtin_bswap16(v); }
+template <> inline uint32_t bswap_item(uint32_t v) { return __builtin_bswap32(v); }
+template <> inline uint64_t bswap_item(uint64_t v) { return __builtin_bswap64(v); }
+template <typename T> void swap_part(const char* src, char* dst, size_t a, size_t b) {
+    // memcpy in and out: the mapped file data need not be aligned to the item size
+    for (size_t k = a; k < b; ++k) {
+        T v;
+        memcpy(&v, src + k * sizeof(T), sizeof(T));
+        v = bswap_item<T>(v);
+        memcpy(dst + k * sizeof(T), &v, sizeof(T));
+    }
+}
+}  // namespace
+
+extern "C" int gzb_copy_swap(void* dst, const void* src, int itemsize, int64_t n, int swap) {
+    if (n < 0 || (n > 0 && (!src || !dst))) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_copy_swap: bad arguments");
+    if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)
+        return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_copy_swap: itemsize must be 1, 2, 4 or 8 (got %d)", itemsize);
+    if (n == 0) return GZB_OK;
+    const size_t N = (size_t)n;
+    const bool do_swap = swap != 0 && itemsize > 1;
+    int want = (int)std::thread::hardware_concurrency();
+    want = want < 1 ? 1 : (want > 16 ? 16 : want);
+    const size_t per_min = ((size_t)2 << 20) / (size_t)itemsize;       // 2 MiB per thread at least
+    int nth = (int)((N + per_min - 1) / per_min);
+    nth = nth > want ? want : nth;
+    const size_t part = (((N + nth - 1) / nth) + 63) & ~(size_t)63;
+    auto run = [&](size_t a, size_t b) {
+        const char* s = (const char*)src;
+        char* d = (char*)dst;
+        if (!do_swap) { memcpy(d + a * (size_t)itemsize, s + a * (size_t)itemsize, (b - a) * (size_t)itemsize); return; }
+        switch (itemsize) {
+            case 2: swap_part<uint16_t>(s, d, a, b); break;
+            case 4: swap_part<uint32_t>(s, d, a, b); break;
+            default: swap_part<uint64_t>(s, d, a, b); break;
+        }
+    };
+    if (nth <= 1) { run(0, N); return GZB_OK; }
+    std::vector<std::thread> th;
+    th.reserve(nth);
+    for (int t = 0; t < nth; ++t) {
+        const size_t a = (size_t)t * part;
+        if (a >= N) break;
+        const size_t b = a + part < N ? a + part : N;
+        th.emplace_back(run, a, b);
+    }
+    for (auto& t : th) t.join();
+    return GZB_OK;
+}

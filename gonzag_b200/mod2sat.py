@@ -100,6 +100,14 @@ def _providers(MG, name_ssh_mod):
     return field, get_record
 
 
+def _record_writer(MG):
+    """`into(name, k, out) -> bool` of the model source when it can write a record straight into a staging slot
+    (`NetCDF3Source.record_into`), else None."""
+    if getattr(MG, "field", None) is not None or getattr(MG, "get_record", None) is not None:
+        return None
+    return getattr(getattr(MG, "source", None), "record_into", None)
+
+
 class Model2SatTrack:
 
     def __init__(self, MG, name_ssh_mod, ST, name_ssh_sat, device=0, ctx=None, keep_mapping=True,
@@ -214,10 +222,12 @@ class Model2SatTrack:
                     dt = GridContext._field_dtype(probe)
                     per_slab = max(2, int(slab_bytes // probe.nbytes))
                     stage = L.pinned_empty((per_slab,) + probe.shape, probe.dtype)
+                    into = _record_writer(MG)
                     try:
                         for (ka, kb) in plan_slabs(tt, tm, per_slab):
                             for k in range(ka, kb + 1):
-                                stage[k - ka] = np.ma.getdata(get_record(k))
+                                if into is None or not into(name_ssh_mod, k, stage[k - ka]):
+                                    stage[k - ka] = np.ma.getdata(get_record(k))
                             ck(lib.gzb_interp(h, Nt, P("t"), P("sm"), P("wb"), nrec, P("tm"), L.ptr(stage), dt,
                                               ka, kb + 1 - ka, rmiss, 1 if first else 0, P("vnp"), P("vbl"),
                                               L.GZB_DEVICE))

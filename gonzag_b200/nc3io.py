@@ -174,6 +174,13 @@ def to_epoch_time(X, units, calendar):
 
 
 # ------------------------------------------------------------------------------- the source
+def C_void(a):
+    """Address of an array that may be read-only (a view of the memory map): `ndarray.ctypes.data` without the
+    writeable check of `ctypes.data_as`."""
+    import ctypes
+    return ctypes.c_void_p(a.__array_interface__['data'][0])
+
+
 class NetCDF3Source:
     """One NetCDF-3 file bound to the reader functions of the reference (`ncfile` argument
     dropped).  The file stays memory-mapped while the object lives; everything returned is a copy."""
@@ -302,6 +309,28 @@ class NetCDF3Source:
         """No whole-array view: NetCDF-3 data are big-endian and may carry fill values, so the
         records go through `GetModel2DVar` one at a time (streaming provider)."""
         return None
+
+    def record_into(self, ncvar, kt, out):
+        """The data of ``GetModel2DVar(ncvar, kt)`` (fill values included, as `numpy.ma.getdata` of it gives them)
+        written straight into `out` -- a C-contiguous native-endian array, typically a slot of the pinned staging
+        slab -- in one threaded byte-swapping pass over the memory map (`gzb_copy_swap`) instead of NumPy's three
+        single-threaded ones (swap, fill-value mask, copy).  Returns False, leaving `out` untouched, when the fast
+        path does not apply (scaled / offset variable, other dtype or shape): the caller then reads the record the
+        ordinary way."""
+        from . import _lib as L
+        v = self._f.variables[ncvar]
+        nd = len(v.dimensions)
+        if nd not in (3, 4):
+            raise ValueError('Model "' + ncvar + '" has a weird number of dimensions: ' + str(nd))
+        if getattr(v, 'scale_factor', None) is not None or getattr(v, 'add_offset', None) is not None:
+            return False
+        raw = v[int(kt)] if nd == 3 else v[int(kt), 0]
+        if (not isinstance(out, np.ndarray) or not out.flags['C_CONTIGUOUS'] or not out.flags['WRITEABLE']
+                or not raw.flags['C_CONTIGUOUS'] or out.shape != raw.shape or not out.dtype.isnative
+                or out.dtype != raw.dtype.newbyteorder('=') or raw.dtype.itemsize not in (1, 2, 4, 8)):
+            return False
+        L.check(L.lib().gzb_copy_swap(L.ptr(out), C_void(raw), raw.dtype.itemsize, raw.size, 0 if raw.dtype.isnative else 1))
+        return True
 
     # ---- gonzag/ncio.py:213-245
     def GetSatCoor(self, what, kt1=0, kt2=0):

@@ -280,6 +280,10 @@ int gzb_pool_stats(uint64_t* cached_bytes, uint64_t* cached_blocks, uint64_t* li
  * context takes int8 -- cut over the host threads (NumPy's single-threaded astype costs a third of an
  * end-to-end call on ORCA12). */
 int gzb_pack_mask(const void* src, int itemsize, int64_t n, int8_t* dst);
+/* Host-only helper: dst[k] = src[k] for n items of `itemsize` 1, 2, 4 or 8 bytes, bytes of every item reversed
+ * when `swap` != 0, cut over the host threads; src and dst must not overlap.  Stages the big-endian records
+ * of a NetCDF-3 file (what GetModel2DVar reads, gonzag/ncio.py:194-210) into the pinned slab K4 gathers from. */
+int gzb_copy_swap(void* dst, const void* src, int itemsize, int64_t n, int swap);
 /* Where does `p` live?  kind_out: 0 pageable host memory (or unknown), 1 pinned + mapped host
  * memory (the GPU can read it in place), 2 device / managed memory. */
 int gzb_pointer_kind(const void* p, int* kind_out);

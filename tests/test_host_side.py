@@ -175,3 +175,22 @@ def test_mask8_paths():
         np.testing.assert_array_equal(got, np.ma.getdata(arr).astype(np.int8))
     with pytest.raises(ValueError):
         GridContext._mask8(fake, m[:, :-1])
+
+
+def test_copy_swap(built):
+    """gzb_copy_swap (host-only, threaded): byte-reversing copy for every item size, lengths around the thread
+    boundaries, an unaligned source (a NetCDF-3 variable starts anywhere in the file)."""
+    rng = np.random.default_rng(2)
+    for dt in ("u1", "u2", "u4", "u8", "f4", "f8"):
+        size = np.dtype(dt).itemsize
+        for n in (0, 1, 7, 64, 65, (1 << 19) + 3, 3 * (1 << 20) + 1):
+            raw = rng.integers(0, 256, n * size + 3, dtype=np.uint8)
+            be = raw[3:].view(">" + dt)                       # unaligned, big-endian
+            out = np.zeros(n + 1, dtype="<" + dt)
+            L.check(L.lib().gzb_copy_swap(L.ptr(out), ctypes.c_void_p(be.__array_interface__["data"][0]), size, n, 1))
+            assert np.array_equal(out[:n].view("u" + str(size)), be.astype("<" + dt).view("u" + str(size))), (dt, n)
+            assert out[n] == 0
+            L.check(L.lib().gzb_copy_swap(L.ptr(out), ctypes.c_void_p(be.__array_interface__["data"][0]), size, n, 0))
+            assert out[:n].tobytes() == be.tobytes()
+    assert L.lib().gzb_copy_swap(None, None, 4, 3, 1) == L.GZB_ERR_ARG
+    assert L.lib().gzb_copy_swap(L.ptr(np.zeros(4)), L.ptr(np.zeros(4)), 3, 4, 1) == L.GZB_ERR_ARG

@@ -190,3 +190,64 @@ def test_dimension_variants(tmp_path):
     with pytest.raises(ValueError):
         S.GetModelLSM("_FillValue@TIME")                    # a 1-D variable cannot give a mask
     S.close()
+
+
+def test_record_into_equals_the_reader(tmp_path):
+    """`NetCDF3Source.record_into` (one threaded byte-swapping pass into a staging slot) against the data of
+    `GetModel2DVar` -- fill values included --, for 3-D and 4-D variables of several types; variables that need
+    scaling, and slots of another dtype / shape / layout, are declined."""
+    from scipy.io import netcdf_file
+    from gonzag_b200.nc3io import NetCDF3Source
+    from gonzag_b200.mod2sat import _record_writer
+    import types
+    rng = np.random.default_rng(3)
+    fn = str(tmp_path / "rec.nc")
+    nj, ni, nt = 37, 53, 4
+    with netcdf_file(fn, "w", version=2) as f:
+        f.createDimension("time_counter", None)
+        f.createDimension("deptht", 2)
+        f.createDimension("y", nj)
+        f.createDimension("x", ni)
+        v = f.createVariable("time_counter", "f8", ("time_counter",))
+        v.units = "seconds since 1970-01-01 00:00:00"
+        v[:] = 3600. * np.arange(nt)
+        a = f.createVariable("ssh", "f4", ("time_counter", "y", "x"))
+        a._FillValue = np.float32(1.e20)
+        b = f.createVariable("ssh8", "f8", ("time_counter", "y", "x"))
+        c = f.createVariable("temp", "f4", ("time_counter", "deptht", "y", "x"))
+        d = f.createVariable("packed", "i2", ("time_counter", "y", "x"))
+        d.scale_factor = 0.001
+        e = f.createVariable("counts", "i2", ("time_counter", "y", "x"))
+        for k in range(nt):
+            x = rng.standard_normal((nj, ni)).astype(np.float32)
+            x[::5, ::3] = 1.e20
+            a[k] = x
+            b[k] = rng.standard_normal((nj, ni))
+            c[k] = rng.standard_normal((2, nj, ni)).astype(np.float32)
+            d[k] = rng.integers(-3000, 3000, (nj, ni)).astype(np.int16)
+            e[k] = rng.integers(-3000, 3000, (nj, ni)).astype(np.int16)
+    src = NetCDF3Source(fn)
+    try:
+        for name, dt in (("ssh", np.float32), ("ssh8", np.float64), ("temp", np.float32), ("counts", np.int16)):
+            stage = np.full((3, nj, ni), 7, dtype=dt)
+            for k in (0, 2, 3):
+                want = np.ma.getdata(src.GetModel2DVar(name, kt=k))
+                assert want.dtype == dt
+                assert src.record_into(name, k, stage[1]) is True
+                assert stage[1].tobytes() == want.tobytes(), (name, k)
+                assert (stage[0] == 7).all() and (stage[2] == 7).all()
+        slot = np.zeros((nj, ni), np.float64)
+        assert src.record_into("packed", 1, slot) is False and not slot.any()           # needs scaling: ordinary reader
+        assert src.record_into("ssh", 1, slot) is False                                    # other dtype
+        assert src.record_into("ssh", 1, np.zeros((nj, ni + 1), np.float32)) is False      # other shape
+        assert src.record_into("ssh", 1, np.zeros((ni, nj), np.float32).T) is False        # not C-contiguous
+        assert src.record_into("ssh", 1, np.zeros((nj, ni), ">f4")) is False               # not native
+        with pytest.raises(ValueError):
+            src.record_into("time_counter", 0, slot)
+        # who gets the fast path: a model grid bound to a NetCDF-3 file, not one carrying arrays / callables
+        assert _record_writer(types.SimpleNamespace(source=src)) is not None
+        assert _record_writer(types.SimpleNamespace(source=src, field=np.zeros((2, 3, 3)))) is None
+        assert _record_writer(types.SimpleNamespace(source=object())) is None
+        assert _record_writer(types.SimpleNamespace()) is None
+    finally:
+        src.close()
