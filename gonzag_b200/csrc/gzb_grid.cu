@@ -1534,14 +1534,21 @@ extern "C" int gzb_pack_mask(const void* src, int itemsize, int64_t n, int8_t* d
         }
     };
     if (nth <= 1) { run(0, N); return GZB_OK; }
+    // a thread that cannot be started (resource limits) leaves its part, and the rest, to the caller's thread
     std::vector<std::thread> th;
-    th.reserve(nth);
-    for (int t = 0; t < nth; ++t) {
-        const size_t a = (size_t)t * part;
-        if (a >= N) break;
-        const size_t b = a + part < N ? a + part : N;
-        th.emplace_back(run, a, b);
+    size_t done_to = 0;
+    try {
+        th.reserve(nth);
+        for (int t = 0; t < nth; ++t) {
+            const size_t a = (size_t)t * part;
+            if (a >= N) break;
+            const size_t b = a + part < N ? a + part : N;
+            th.emplace_back(run, a, b);
+            done_to = b;
+        }
+    } catch (...) {
     }
+    if (done_to < N) run(done_to, N);
     for (auto& t : th) t.join();
     return GZB_OK;
 }
@@ -1592,14 +1599,21 @@ extern "C" int gzb_copy_swap(void* dst, const void* src, int itemsize, int64_t n
         }
     };
     if (nth <= 1) { run(0, N); return GZB_OK; }
+    // a thread that cannot be started (resource limits) leaves its part, and the rest, to the caller's thread
     std::vector<std::thread> th;
-    th.reserve(nth);
-    for (int t = 0; t < nth; ++t) {
-        const size_t a = (size_t)t * part;
-        if (a >= N) break;
-        const size_t b = a + part < N ? a + part : N;
-        th.emplace_back(run, a, b);
+    size_t done_to = 0;
+    try {
+        th.reserve(nth);
+        for (int t = 0; t < nth; ++t) {
+            const size_t a = (size_t)t * part;
+            if (a >= N) break;
+            const size_t b = a + part < N ? a + part : N;
+            th.emplace_back(run, a, b);
+            done_to = b;
+        }
+    } catch (...) {
     }
+    if (done_to < N) run(done_to, N);
     for (auto& t : th) t.join();
     return GZB_OK;
 }
