@@ -11,6 +11,7 @@ restore() { unset GZB_NVCC_EXTRA; python -m gonzag_b200.build --force > $OUT/bui
 trap restore EXIT
 timeout 260 python -m pytest tests -m gpu -q --durations=8 --deselect tests/test_gpu_fullsize.py > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$? ($((SECONDS-t0)) s)"; tail -3 $OUT/pytest_$TAG.log
 timeout 170 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$? ($((SECONDS-t0)) s)"; tail -2 $OUT/bench_$TAG.err
+timeout 120 python scripts/gpu_fuzz.py 5000 600 > $OUT/fuzz_$TAG.log 2>&1; echo "fuzz rc=$? ($((SECONDS-t0)) s)"; tail -5 $OUT/fuzz_$TAG.log
 AB_STAGES=K4,bulk,K2K3,path timeout 60 python scripts/ab_opt.py pdl=1 > $OUT/ab_base_$TAG.log 2>&1; echo "== product build"; cat $OUT/ab_base_$TAG.log
 k=0
 for EXP in "-DGZB_EXP_L64=1" "-DGZB_EXP_HDG_STRIDE=8" "-DGZB_EXP_L64=1 -DGZB_EXP_HDG_STRIDE=8" "-DGZB_EXP_BULK_BLOCKS=6" "-DGZB_EXP_BULK_BLOCKS=7" \
