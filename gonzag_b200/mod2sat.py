@@ -254,19 +254,22 @@ class Model2SatTrack:
             d_xnp = ctx.dev_alloc(Nj * Ni * 9)          # the map (f64) followed by its missing-value mask (u8)
             d_xmk = C.c_void_p(d_xnp.ptr + Nj * Ni * 8)
             ck(lib.gzb_xnp_track_masked(h, Nt, P("np"), rmiss, C.c_void_p(d_xnp.ptr), d_xmk, L.GZB_DEVICE))
-            xnp = np.empty((Nj, Ni))
-            xmk = np.empty((Nj, Ni), dtype=np.bool_)
+            # ONE transfer for the map and its mask (they sit back to back on the device): the mask alone (Nj*Ni bytes)
+            # is below the size from which a pageable transfer is cut over the copy threads, and crawled at 4 GB/s
+            xbuf = np.empty(Nj * Ni * 9, dtype=np.uint8)
+            xnp = xbuf[:Nj * Ni * 8].view(np.float64).reshape(Nj, Ni)
+            xmk = xbuf[Nj * Ni * 8:].view(np.bool_).reshape(Nj, Ni)
             tim["out_xnp_kernel_s"] = time.perf_counter() - tc
-            ck(lib.gzb_d2h(h, L.ptr(xnp), C.c_void_p(d_xnp.ptr), xnp.nbytes))
-            tim["out_xnp_d2h0_s"] = time.perf_counter() - tc
-            ck(lib.gzb_d2h(h, L.ptr(xmk), d_xmk, xmk.nbytes))
+            ck(lib.gzb_d2h(h, L.ptr(xbuf), C.c_void_p(d_xnp.ptr), xbuf.nbytes))
             tim["out_xnp_d2h_s"] = time.perf_counter() - tc
         if keep_mapping:
-            NP, SM, WB = np.empty((Nt, 2), np.int64), np.empty((Nt, 4, 2), np.int64), np.empty((Nt, 4))
+            # NP, SM, WB sit one after the other on the device: one transfer (big enough for the copy threads)
+            mbuf = np.empty(off["wb"] + Nt * 32 - off["np"], dtype=np.uint8)
+            part = lambda k, nbytes, dt, shape: mbuf[off[k] - off["np"]:off[k] - off["np"] + nbytes].view(dt).reshape(shape)
+            NP, SM, WB = (part("np", Nt * 16, np.int64, (Nt, 2)), part("sm", Nt * 64, np.int64, (Nt, 4, 2)),
+                          part("wb", Nt * 32, np.float64, (Nt, 4)))
             if Nt > 0:
-                ck(lib.gzb_d2h(h, L.ptr(NP), P("np"), NP.nbytes))
-                ck(lib.gzb_d2h(h, L.ptr(SM), P("sm"), SM.nbytes))
-                ck(lib.gzb_d2h(h, L.ptr(WB), P("wb"), WB.nbytes))
+                ck(lib.gzb_d2h(h, L.ptr(mbuf), P("np"), mbuf.nbytes))
             self.BT = MappingView(NP, SM, WB)
         ctx.sync()
         tim["out_sync_s"] = time.perf_counter() - tc
