@@ -293,7 +293,9 @@ class Model2SatTrack:
         self.time = ST.time
         self.lat = ST.lat
         self.lon = ST.lon
-        good = (vssh_m_bl > -100.) & (vssh_m_bl < 100.) & (vssh_s > -100.) & (vssh_s < 100.)     # mod2sat.py:157-159
+        # -100 < x < 100 for both series (mod2sat.py:157-159) written as |x| < 100: same truth table (NaN and inf fail
+        # either way), five passes over the track instead of seven
+        good = (np.abs(vssh_m_bl) < 100.) & (np.abs(vssh_s) < 100.)
         self.mask = good.astype(np.int8)
         bad = ~good
         # masked_where(imask == 0, x) on arrays this constructor owns: no copy of the data, one mask each
