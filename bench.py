@@ -12,7 +12,8 @@ of the workload:  K1 nearest points + K2 source mesh + K3 weights + K4 time/spac
             pass, then a read pass of a second scratch buffer so that L2 starts clean).
   e2e       the same metric through the public drop-in API `Model2SatTrack(MG, .., ST, ..)` with
             HOST buffers (pinned model records): grid + track + record H2D, kernels, result D2H
-            are all inside the timed region.
+            are all inside the timed region.  `e2e.resident_grid` (N=1, informational): the same call on a grid
+            context kept on the GPU between calls, as `ModGrid.ctx` gives it to the drop-in classes.
   roofline  for the ONE kernel that dominates the step, k_mesh_weights_interp (K2+K3+K4 of a point in
             registers), launched alone through gzb_mesh_weights_interp: fused algorithmic bytes
             (260 + 8 s B/point) / CUDA-event time; `gather_kernel` = the same for K4 alone; under
