@@ -176,6 +176,15 @@ __device__ __forceinline__ void gzb_pdl_trigger() { asm volatile("griddepcontrol
 //                        asks L2 for 64 bytes instead of a 128-byte line (ld.global.nc.L2::64B)
 // GZB_EXP_HDG_STRIDE=8   heading table rows of 8 doubles (64 B, one fetch) instead of 6 (48 B)
 // GZB_EXP_BULK_BLOCKS=n  __launch_bounds__(128, n) on the fused K2+K3+K4 kernel (register cap 65536 / (128 n))
+// GZB_EXP_SKIP_DG=1      k_near_search does not evaluate the fp64 haversine of a point's nearest cell when that cell is
+//                        alone within the fp32 budget AND its fp32 chord is farther than twice that budget from the
+//                        chords of both acceptance thresholds (r0, 1.2^2 r0): dG then holds 12720 asin(chord / 2),
+//                        which is on the same side of every threshold as the exact value -- the only thing dG is
+//                        used for (accept_edge, twin_of, point_sum).  Written after the round's last GPU visit:
+//                        never run; scripts/gpu_round2_first.sh measures it and runs the parity tests on it.
+#ifndef GZB_EXP_SKIP_DG
+#define GZB_EXP_SKIP_DG 0
+#endif
 #ifndef GZB_EXP_L64
 #define GZB_EXP_L64 0
 #endif

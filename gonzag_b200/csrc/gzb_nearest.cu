@@ -599,10 +599,17 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
 __global__ void __launch_bounds__(128, 8)
 k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
               long long* __restrict__ G, double* __restrict__ dG, long long* __restrict__ ulist,
-              unsigned* __restrict__ hint, unsigned long long* __restrict__ ucount) {
+              unsigned* __restrict__ hint, unsigned long long* __restrict__ ucount
+#if GZB_EXP_SKIP_DG
+              , const float cthr0, const float cthr1      // chords (unit sphere) of r0 and of 1.2^2 r0; NaN = no shortcut
+#endif
+              ) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool unresolved = false;
     unsigned myhint = 0xffffffffu;
+#if GZB_EXP_SKIP_DG
+    float a_win = -1.0f;                                  // fp32 chord of a proven, single winner
+#endif
     if (t < nt) {
         const double lat = yt[t], lon = xt[t];
         long long out = CAND_NONE;
@@ -666,6 +673,9 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
                     if (proven3 || (w5 - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
                         reason = 0;
                         out = f | ((fminf(nb8, ring) <= B * B) ? CAND_MULTI : 0LL);
+#if GZB_EXP_SKIP_DG
+                        if (!(out & CAND_MULTI)) a_win = a;
+#endif
                     }
                 }
             }
@@ -676,11 +686,20 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
             }
             if (!unresolved) {
                 // settle the point here: the reference's fp64 formula on the candidate(s)
+#if GZB_EXP_SKIP_DG
+                const float m2 = a_win * 4.0e-6f + 4.0e-6f;           // twice the proven fp32 error of the chord
+                if (a_win >= 0.0f && fabsf(a_win - cthr0) > m2 && fabsf(a_win - cthr1) > m2) {
+                    G[t] = CAND_FLAT(out);
+                    dG[t] = 12720.0 * asin(0.5 * (double)a_win);      // same side of r0 and 1.2^2 r0 as the exact distance
+                } else
+#endif
+                {
                 long long bf;
                 unsigned long long bd;
                 exact_from_cand(g, out, lat, lon, px, py, pz, bf, bd);
                 G[t] = bf;
                 dG[t] = __longlong_as_double((long long)bd);
+                }
             }
         } else {
             G[t] = GZB_NOFLAT;
@@ -1529,8 +1548,15 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     bool sb_has_kernel = false;      // is the operation right before k_chain on its stream a kernel?  (a dependent launch needs one)
     gzb_trace(ctx, s, "K1 start");
     if (ctx->nearest_path && ctx->g.cellv && ctx->g.lut.bins) {
+#if GZB_EXP_SKIP_DG
+        const float cthr0 = half < 1.5 ? (float)(2.0 * sn) : NAN;
+        const float cthr1 = (t2 / (2.0 * 6360.0)) < 1.5 ? (float)(2.0 * sin(t2 / (2.0 * 6360.0))) : NAN;
+        k_near_search<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ctx->g, nt, yt, xt, G, dG, ulist, hint,
+                                                                 (unsigned long long*)(scal + 2), cthr0, cthr1);
+#else
         k_near_search<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ctx->g, nt, yt, xt, G, dG, ulist, hint,
                                                                  (unsigned long long*)(scal + 2));
+#endif
         GZB_LAUNCH_CHECK(ctx);
         // from here on everything is latency-bound (the warp search of the few unresolved points, then
         // the chain): with `split` it goes to the auxiliary stream and the caller runs K2-K4 meanwhile on
