@@ -43,6 +43,10 @@ def test_frame_switch(emu):
     T.test_frame_switch_on_device()
 
 
+def test_multi_mission_on_one_resident_grid(emu, golden_grid):
+    T.test_multi_mission_on_one_resident_grid(golden_grid)
+
+
 def test_netcdf3_records_take_the_fast_path(emu, golden_grid, tmp_path, monkeypatch):
     """From file names the model records reach the staging slab through `NetCDF3Source.record_into` (one byte-swapping
     pass), not through the reader's masked arrays -- except the one probe read that tells the dtype."""
