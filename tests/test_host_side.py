@@ -194,3 +194,15 @@ def test_copy_swap(built):
             assert out[:n].tobytes() == be.tobytes()
     assert L.lib().gzb_copy_swap(None, None, 4, 3, 1) == L.GZB_ERR_ARG
     assert L.lib().gzb_copy_swap(L.ptr(np.zeros(4)), L.ptr(np.zeros(4)), 3, 4, 1) == L.GZB_ERR_ARG
+
+
+def test_integration_doc_matches_the_binding():
+    """The ctypes stub shown in INTEGRATION.md declares the same argument lists as the packaged binding."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    env = {"C": ctypes, "_P": ctypes.c_void_p, "_I64": ctypes.c_int64}
+    found = re.findall(r"_L\.(gzb_\w+)\.argtypes\s*=\s*(\[[^\]]*\])", text)
+    assert len(found) >= 3
+    for name, lst in found:
+        assert [a for a in eval(lst, env)] == list(L._SIGNATURES[name][1]), name
