@@ -18,6 +18,18 @@ from gonzag_b200 import _lib as L
 from oracle import gz_oracle as orc
 
 _REAL_LIB = L.lib            # captured before any test replaces it
+_MEMO = {}                   # the test bodies map the same few tracks again and again: oracle results by input digest
+
+
+def _memo(tag, fn, *arrays_and_scalars):
+    import hashlib
+    h = hashlib.blake2b(tag.encode(), digest_size=16)
+    for a in arrays_and_scalars:
+        h.update(np.ascontiguousarray(a).tobytes() if isinstance(a, np.ndarray) else repr(a).encode())
+    key = h.digest()
+    if key not in _MEMO:
+        _MEMO[key] = fn()
+    return _MEMO[key].copy()
 
 
 def _addr(p):
@@ -252,7 +264,8 @@ class EmuLib:
         Y, X = _view(yt, (nt,), np.float64), _view(xt, (nt,), np.float64)
         ctx.launches += 8
         if ctx.opt["edge_exclusion"]:
-            return orc.nearest_chain(Y, X, ctx.lat, ctx.lon, ctx.kew, rd, int(r), seed=(int(sj), int(si)))
+            return _memo("np", lambda: orc.nearest_chain(Y, X, ctx.lat, ctx.lon, ctx.kew, rd, int(r), seed=(int(sj), int(si))),
+                         Y, X, ctx.lat, ctx.lon, ctx.kew, float(rd), int(r), int(sj), int(si))
         out = np.zeros((nt, 2), np.int64)
         jj, ji = int(sj), int(si)
         for t in range(nt):
@@ -265,12 +278,13 @@ class EmuLib:
             raise NotImplementedError("tests/emulib.py: option force_heavy")
         Y, X = _view(yt, (nt,), np.float64), _view(xt, (nt,), np.float64)
         ctx.launches += 1
-        return orc.source_meshes(Y, X, ctx.lat, ctx.lon, NP, ctx.kew, angle=ctx.angle)
+        return _memo("sm", lambda: orc.source_meshes(Y, X, ctx.lat, ctx.lon, NP, ctx.kew, angle=ctx.angle),
+                     Y, X, ctx.lat, ctx.lon, NP, ctx.kew, ctx.angle if ctx.angle is not None else "no angle")
 
     def _wght(self, ctx, nt, yt, xt, SM):
         Y, X = _view(yt, (nt,), np.float64), _view(xt, (nt,), np.float64)
         ctx.launches += 1
-        return orc.weights(Y, X, ctx.lat, ctx.lon, SM)
+        return _memo("wb", lambda: orc.weights(Y, X, ctx.lat, ctx.lon, SM), Y, X, ctx.lat, ctx.lon, SM)
 
     def gzb_nearest(self, h, nt, yt, xt, rd, r, sj, si, np_out, where):
         ctx = self._c(h)
