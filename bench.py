@@ -166,25 +166,65 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline
-def _oracle_sample(lat, lon, mask, angle_band, kew, rd, r, t, y, x, tmod, rec0, rec1, n_map, n_interp):
-    """Times the oracle on a prefix: mapping on n_map points, interpolation (whole-grid time
-    interpolation per point, exactly the reference's cost profile) on n_interp points."""
+def _reference_pkg():
+    """The UNMODIFIED reference package when it can be imported here (checkout, or its verbatim copy oracle/_ref that
+    `make -C oracle` produced and the snapshot carried to this box), else None: the oracle port is timed instead."""
+    from oracle import ref_loader
+    root = ref_loader.find_reference()
+    if root is None:
+        return None, None, None
+    gz, store = ref_loader.load_reference(root)
+    return gz, store, ref_loader.reference_kind(root)
+
+
+def _cpu_sample(use_ref, lat, lon, mask, angle, kew, res, rd, r, t, y, x, tmod, rec0, rec1, n_map, n_int):
+    """One bounded sample of the reference algorithm on ONE core: the mapping (BilinTrack: nearest points, source meshes
+    with the -D angle, weights) on a contiguous n_map-point track segment, and the space-time interpolation on its first
+    n_int points (the reference interpolates the WHOLE grid in time for every point, gonzag/mod2sat.py:119).
+    use_ref: time the unmodified reference (gonzag.BilinTrack, then gonzag.Model2SatTrack on the short segment, whose own
+    mapping share is subtracted); else the oracle port.  Returns (s_map, s_interp)."""
+    import contextlib
+    import io
+    import types
+    if use_ref:
+        gz, store, _ = _reference_pkg()
+        with contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            gz.BilinTrack(y[:n_map], x[:n_map], lat, lon, src_grid_local_angle=angle, k_ew_per=kew, rd_found_km=rd,
+                          np_box_r=r, freq_talk=0)
+            t_map = time.perf_counter() - t0
+            store["fields"]["mod"] = [rec0, rec1]
+            store["sat"]["sat"] = np.zeros(n_int)
+            MG = types.SimpleNamespace(shape=lat.shape, HResDeg=res, lat=lat, lon=lon, xangle=angle, EWPer=kew,
+                                       time=tmod[:2], file="mod", mask=mask)
+            ST = types.SimpleNamespace(size=n_int, lat=y[:n_int], lon=x[:n_int], time=t[:n_int], file="sat", jt1=0, jt2=0,
+                                       keepit=[])
+            t0 = time.perf_counter()
+            gz.Model2SatTrack(MG, "ssh", ST, "ssh")
+            t_all = time.perf_counter() - t0
+        return t_map, max(t_all - n_int * t_map / n_map, 1e-9)
     from oracle import gz_oracle as orc
     t0 = time.perf_counter()
     NP = orc.nearest_chain(y[:n_map], x[:n_map], lat, lon, kew, rd, r)
-    SM = orc.source_meshes(y[:n_map], x[:n_map], lat, lon, NP, kew, angle=angle_band)
+    SM = orc.source_meshes(y[:n_map], x[:n_map], lat, lon, NP, kew, angle=angle)
     WB = orc.weights(y[:n_map], x[:n_map], lat, lon, SM)
     t_map = time.perf_counter() - t0
     recs = {0: rec0, 1: rec1}
     t0 = time.perf_counter()
-    orc.interp_track(t[:n_interp], tmod[:2], lambda k: recs[k], mask, SM[:n_interp], WB[:n_interp],
-                     faithful_cost=True)
-    t_int = time.perf_counter() - t0
-    return t_map, t_int
+    orc.interp_track(t[:n_int], tmod[:2], lambda k: recs[k], mask, SM[:n_int], WB[:n_int], faithful_cost=True)
+    return t_map, time.perf_counter() - t0
 
 
-def _oracle_worker(args):
-    return _oracle_sample(*args)
+_WORKER = {}
+
+
+def _cpu_worker(job):
+    """(segment start, n_map, n_int) -> (s_map, s_interp); the big arrays are inherited from the parent (fork)."""
+    a, n_map, n_int = job
+    W = _WORKER
+    t, y, x = W["t"], W["y"], W["x"]
+    return _cpu_sample(W["use_ref"], W["lat"], W["lon"], W["mask"], W["angle"], 2, W["res"], W["rd"], W["r"],
+                       t[a:a + n_map] - t[a] + 1.0, y[a:a + n_map], x[a:a + n_map], W["tmod"], W["rec0"], W["rec1"], n_map, n_int)
 
 
 def cpu_rate(t_map, n_map, t_int, n_interp):
@@ -192,57 +232,82 @@ def cpu_rate(t_map, n_map, t_int, n_interp):
     return 1.0 / per_pt
 
 
-def host_inputs_for_cpu(w, lat, lon, t, y, x, rec_dt):
-    """First two records (NumPy) + the prefix of the track that falls in the first bracket."""
+def host_inputs_for_cpu(w, lat, lon):
+    """First two records (NumPy, fp32 like the GPU arm's) and one wide bracket: the sample only needs records 0 and 1."""
     rec0 = syn.ssh_record(lat, lon, 0)
     rec1 = syn.ssh_record(lat, lon, 1)
-    tmod = np.array([0.0, 1.0e7])      # one wide bracket: the sample only needs records 0 and 1
+    tmod = np.array([0.0, 1.0e7])
     return rec0, rec1, tmod
+
+
+def bench_config(args, w, r, rd, **more):
+    """The `config` keys both arms emit (the driver compares them)."""
+    cfg = {"workload": args.workload + ": " + w["desc"], "grid": [w["nj"], w["ni"]], "field_dtype": "f32",
+           "np_box_r": r, "rd_found_km": rd, "k_ew_per": 2, "with_angle": True}
+    cfg.update(more)
+    return cfg
 
 
 # ----------------------------------------------------------------------------- reference arm
 def run_reference(args, w):
+    """The reference's own CPU implementation of the path on this box's host cores: the UNMODIFIED reference when it is
+    importable (oracle/_ref), else the oracle port.  One step = every worker maps the NEXT contiguous segment of the
+    workload's track (with the -D angle: heavy-duty quadrants included) and interpolates its first points; the per-step
+    sample is sized so that warmup + steps end within a few minutes and, added up over the steps, covers at least
+    BASELINE.md section 3's 20 000 mapping / 500 interpolation points per worker."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import gz_oracle as orc
+    t_set = time.perf_counter()
     lat, lon, mask, res, rd, r = make_grid(w)
     t, y, x = make_track(w, 0, 1)
-    rec0, rec1, tmod = host_inputs_for_cpu(w, lat, lon, t, y, x, w["rec_dt"])
+    rec0, rec1, tmod = host_inputs_for_cpu(w, lat, lon)
+    angle = orc.grid_angle(lat, lon)              # -D: GridAngle (set-up, like ModGrid; not part of the metric)
+    gz, _, kind = _reference_pkg()
+    use_ref = gz is not None
     big = lat.size > 2_000_000
-    n_map = 1500 if big else 4000
-    n_int = 24 if big else 4000
+    iters = max(1, args.warmup + args.steps)
+    if big:       # ~0.55 ms/pt mapping + ~25-50 ms/pt interpolation on ORCA12: ~10-25 s of CPU per worker and step
+        n_map = int(np.clip(200000 // iters, 4000, 20000))
+        n_int = int(np.clip(5000 // iters, 100, 500))
+    else:
+        n_map, n_int = 20000, 20000
+    n_map = min(n_map, len(y) // 2)
+    n_int = min(n_int, n_map)
     cores = max(1, min(os.cpu_count() or 1, 32))
-    if big:
-        cores = max(1, min(cores, 16))      # each worker holds whole-grid temporaries
-    # worker p takes its own contiguous prefix-sized segment of the track
-    segs = []
-    for p in range(cores):
-        a = (p * n_map) % max(1, len(y) - n_map)
-        segs.append((lat, lon, mask, None, 2, rd, r, t[a:a + n_map] - t[a] + 1.0, y[a:a + n_map], x[a:a + n_map],
-                     tmod, rec0, rec1, n_map, n_int))
+    _WORKER.update(lat=lat, lon=lon, mask=mask, angle=angle, res=res, rd=rd, r=r, t=t, y=y, x=x, tmod=tmod, rec0=rec0,
+                   rec1=rec1, use_ref=use_ref)
+    log("[reference arm] set-up %.1f s; %s; %d workers; per step and worker: %d mapping / %d interpolation points"
+        % (time.perf_counter() - t_set, "unmodified reference (%s)" % kind if use_ref else "oracle port", cores, n_map, n_int))
     ctx = mp.get_context("fork")
     times = []
+    span = max(1, len(y) - n_map)
     with ctx.Pool(cores) as pool:
-        for it in range(args.warmup + args.steps):
+        for it in range(iters):
+            jobs = [(((it * cores + p) * n_map) % span, n_map, n_int) for p in range(cores)]
             t0 = time.perf_counter()
-            res_ = pool.map(_oracle_worker, segs)
+            res_ = pool.map(_cpu_worker, jobs)
             wall = time.perf_counter() - t0
             if it >= args.warmup:
                 rates = [cpu_rate(tm, n_map, ti, n_int) for tm, ti in res_]
                 times.append((wall, float(np.sum(rates))))
     value = float(np.mean([v for _, v in times]))
     ms = float(np.mean([wl for wl, _ in times])) * 1e3
-    sample = ("per worker: mapping on a %d-point contiguous track segment, interpolation (whole-grid time "
-              "interpolation per point, as the reference does) on its first %d points; rate = 1/(s_map/pt + s_interp/pt), "
-              "summed over %d workers" % (n_map, n_int, cores))
+    sample = ("%s, -D angle on; per step each of %d workers (1 core each) maps the next contiguous %d-point segment of the "
+              "track and interpolates its first %d points (whole-grid time interpolation per point, as the reference does); "
+              "rate = sum over workers of 1/(s_map/pt + s_interp/pt), i.e. EXTRAPOLATED from the sample to the whole track; "
+              "over the %d timed steps: %d mapping / %d interpolation points per worker"
+              % ("unmodified reference (gonzag.BilinTrack + gonzag.Model2SatTrack from %s)" % kind if use_ref else
+                 "oracle port of the reference", cores, n_map, n_int, args.steps, n_map * args.steps, n_int * args.steps))
     line = {"impl": "reference", "metric": "track points/sec (mapping+interp)", "value": value,
             "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + w["desc"], "grid": [w["nj"], w["ni"]],
-                       "np_box_r": r, "rd_found_km": rd},
-            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": bench_config(args, w, r, rd),
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "reference" if use_ref else "port",
+                             "sample": sample},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "gzb_set_ew_per": (C.c_int, [_P, C.c_int]),
     "gzb_set_option": (C.c_int, [_P, C.c_char_p, _I64]),
     "gzb_grid_angle": (C.c_int, [_P, _P, C.c_int]),
+    "gzb_get_angle": (C.c_int, [_P, _P, C.c_int]),
     "gzb_nearest": (C.c_int, [_P, _I64, _P, _P, C.c_double, C.c_int, _I64, _I64, _P, C.c_int]),
     "gzb_source_mesh": (C.c_int, [_P, _I64, _P, _P, _P, _P, C.c_int]),
     "gzb_weights": (C.c_int, [_P, _I64, _P, _P, _P, _P, C.c_int]),

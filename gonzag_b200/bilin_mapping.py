@@ -25,9 +25,23 @@ from .context import GridContext
 _CTX_CACHE = {"key": None, "ctx": None}
 
 
+def _fingerprint(A):
+    """Cheap content fingerprint of a grid array: its corners plus a strided sample of ~4096 values.  The key of the
+    context cache must change when a caller edits Ys / Xs in place, or when a freed array's id and address are reused by
+    another grid of the same shape (the reference recomputes from the arrays on every call)."""
+    a = np.asarray(A)
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 4096)
+    sample = np.ascontiguousarray(flat[::step])
+    edge = np.ascontiguousarray(np.concatenate([a[0, ::max(1, a.shape[1] // 64)], a[-1, ::max(1, a.shape[1] // 64)],
+                                                a[::max(1, a.shape[0] // 64), 0], a[::max(1, a.shape[0] // 64), -1]])) \
+        if a.ndim == 2 and a.size else sample
+    return hash((sample.tobytes(), edge.tobytes()))
+
+
 def _grid_ctx(Ys, Xs, device=0):
     key = (id(Ys), id(Xs), np.shape(Ys), getattr(Ys, "ctypes", None) and Ys.ctypes.data,
-           getattr(Xs, "ctypes", None) and Xs.ctypes.data, device)
+           getattr(Xs, "ctypes", None) and Xs.ctypes.data, device, _fingerprint(Ys), _fingerprint(Xs))
     if _CTX_CACHE["key"] != key:
         if _CTX_CACHE["ctx"] is not None:
             _CTX_CACHE["ctx"].close()

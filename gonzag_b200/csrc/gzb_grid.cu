@@ -1398,6 +1398,24 @@ extern "C" int gzb_grid_angle(gzb_ctx* ctx, double* angle_out_or_null, int where
     return GZB_OK;
 }
 
+// Copy of the angle installed in the context (by gzb_create, gzb_set_angle or gzb_grid_angle): no kernel runs, so a
+// host that reads `ModGrid.xangle` lazily sees exactly what K2 uses (gonzag/utils.py:431 computes it once).
+extern "C" int gzb_get_angle(gzb_ctx* ctx, double* angle_out, int where) {
+    if (!ctx || !angle_out) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_get_angle: null argument");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    if (!ctx->g.angle) return gzb_fail(ctx, GZB_ERR_STATE, "gzb_get_angle: the context holds no angle (no -D)");
+    const size_t bytes = (size_t)ctx->g.Nj * (size_t)ctx->g.Ni * sizeof(double);
+    if (where == GZB_HOST) {
+        const int rc = gzb_bigcopy(ctx, angle_out, ctx->g.angle, bytes, false);
+        if (rc != GZB_OK) return rc;
+        ctx->stats.d2h_bytes += bytes;
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        GZB_CUDA(ctx, cudaMemcpyAsync(angle_out, ctx->g.angle, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return GZB_OK;
+}
+
 // ======================================================================== memory helpers
 extern "C" int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out) {
     if (!ctx || !dptr_out) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_dev_alloc: null argument");

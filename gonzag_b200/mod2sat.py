@@ -174,8 +174,11 @@ class Model2SatTrack:
             if not field.flags["C_CONTIGUOUS"]:
                 field = np.ascontiguousarray(field)
             dt = GridContext._field_dtype(field)
-            if field.shape[0] != nrec:
+            # the reference asks its reader for record k = index into the (possibly sliced) MG.time
+            # (gonzag/mod2sat.py:94-112): a window starting after record 0 still reads records 0 .. nrec-1
+            if field.shape[0] < nrec:
                 raise ValueError("MG.field holds %d records, MG.time %d" % (field.shape[0], nrec))
+            field = field[:nrec]
             kind = L.pointer_kind(field)
             sparse = Nt * 1024.0 < field.nbytes          # same rule as gzb_interp's zero-copy gather
             if kind >= 1 and (kind == 2 or sparse):
@@ -290,6 +293,11 @@ class Model2SatTrack:
         else:
             _, sat_reader = _reference_readers()
             vssh_s = sat_reader(ST.file, name_ssh_sat, kt1=ST.jt1, kt2=ST.jt2, ikeep=ST.keepit)
+        # netCDF4 hands back a MaskedArray under auto-masking; the reference's nmp.where drops the masked entries
+        # (gonzag/mod2sat.py:157-158), i.e. they end up with imask = 0 in a PLAIN int8 array: fill them with the
+        # missing value first so that `good` below is a plain ndarray too
+        if isinstance(vssh_s, np.ma.MaskedArray):
+            vssh_s = np.ma.filled(np.ma.asarray(vssh_s, dtype=np.float64), rmiss)
         self.time = ST.time
         self.lat = ST.lat
         self.lon = ST.lon

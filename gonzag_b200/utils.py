@@ -293,7 +293,7 @@ class ModGrid:
         if self._xangle is None:
             if self.IsDistorded:
                 self._xangle = np.empty(self.shape)
-                self.ctx._ck(L.lib().gzb_grid_angle(self.ctx._h, L.ptr(self._xangle), L.GZB_HOST))
+                self.ctx._ck(L.lib().gzb_get_angle(self.ctx._h, L.ptr(self._xangle), L.GZB_HOST))   # a copy: K0 ran once, before the frame switch
             else:
                 self._xangle = np.zeros(self.shape)
         return self._xangle

@@ -130,6 +130,10 @@ int gzb_lat_range(gzb_ctx* ctx, double* lat_min, double* lat_max);
  * degrees from the context's lat/lon, installs it as the context's angle and, when
  * angle_out is not NULL, copies it there. */
 int gzb_grid_angle(gzb_ctx* ctx, double* angle_out_or_null, int where);
+/* Copy of the angle the context holds (installed by gzb_create / gzb_set_angle / gzb_grid_angle); no kernel
+ * runs.  What reading `ModGrid.xangle` does (the reference computes the attribute once, gonzag/utils.py:431,
+ * on the 0..360 longitudes, before the regional frame switch of :441).  GZB_ERR_STATE without an angle. */
+int gzb_get_angle(gzb_ctx* ctx, double* angle_out, int where);
 
 /* ---- K1: nearest points along a track --------------------------------------------------
  * Replaces BilinTrack.nrpt() + NearestPoint() + the edge exclusion

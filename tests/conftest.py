@@ -46,6 +46,11 @@ def golden_grid():
 
 
 @pytest.fixture(scope="session")
+def golden_window():
+    return load_golden("window")           # case_window of make_golden.py: model window starting at record 2
+
+
+@pytest.fixture(scope="session")
 def golden_surface():
     return load_golden("surface")          # tests/golden/make_golden_surface.py
 
@@ -58,10 +63,10 @@ def grid_case_sources(g, tag):
         model = ModelArrays(g["a_tm"], lat, lon, fields={"ssh": g["a_f32"]})
         lsm = ModelArrays(g["a_tm"], None, None, masks={"tmask": g["a_maskin"].astype(np.int64)})
         return model, TrackArrays(g["a_t"], g["a_y"], g["a_x"], {"ssh": g["a_ssat"]}), lsm, "tmask", True, len(g["a_t"])
-    if tag == "b":
-        model = ModelArrays(g["b_tm"], g["b_lat"], g["b_lon"], fields={"ssh": g["b_f64"]},
-                            masks={"tmask": g["b_maskin"].astype(np.int64)})
-        return model, TrackArrays(g["b_t"], g["b_y"], g["b_x"], {"ssh": g["b_ssat"]}), model, "tmask", False, 100
+    if tag in ("b", "w"):
+        model = ModelArrays(g[tag + "_tm"], g[tag + "_lat"], g[tag + "_lon"], fields={"ssh": g[tag + "_f64"]},
+                            masks={"tmask": g[tag + "_maskin"].astype(np.int64)})
+        return model, TrackArrays(g[tag + "_t"], g[tag + "_y"], g[tag + "_x"], {"ssh": g[tag + "_ssat"]}), model, "tmask", False, 100
     fcm = np.ma.masked_array(g["c_f32"], mask=np.broadcast_to(g["c_maskin"] == 0, g["c_f32"].shape))
     model = ModelArrays(g["c_tm"], g["c_lat1"], g["c_lon1"], fields={"ssh": fcm})
     return model, TrackArrays(g["c_t"], g["c_y"], g["c_x"], {"ssh": g["c_ssat"]}), model, "_FillValue@ssh", False, len(g["c_t"])
@@ -126,19 +131,19 @@ def write_grid_case_files(g, tag, directory):
             v[0, 0] = g["a_maskin"]
             v[0, 1] = 0
         return fm, ft, fl, "tmask", True, len(g["a_t"])
-    if tag == "b":
+    if tag in ("b", "w"):
         with netcdf_file(fm, "w", version=2) as f:
-            nj, ni = g["b_lat"].shape
-            time_var(f, "time", g["b_tm"], "time")
+            nj, ni = g[tag + "_lat"].shape
+            time_var(f, "time", g[tag + "_tm"], "time")
             f.createDimension("y", nj)
             f.createDimension("x", ni)
-            for name, key in (("gphit", "b_lat"), ("glamt", "b_lon")):
+            for name, key in (("gphit", tag + "_lat"), ("glamt", tag + "_lon")):
                 v = f.createVariable(name, "f8", ("y", "x"))
                 v[:] = g[key]
             v = f.createVariable("ssh", "f8", ("time", "y", "x"))
-            v[:] = g["b_f64"]
+            v[:] = g[tag + "_f64"]
             v = f.createVariable("tmask", "i2", ("y", "x"))
-            v[:] = g["b_maskin"]
+            v[:] = g[tag + "_maskin"]
         return fm, ft, fm, "tmask", False, 100
     with netcdf_file(fm, "w", version=1) as f:
         nj, ni = len(g["c_lat1"]), len(g["c_lon1"])

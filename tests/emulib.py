@@ -259,6 +259,13 @@ class EmuLib:
         ctx.launches += 1
         return L.GZB_OK
 
+    def gzb_get_angle(self, h, out, where):
+        ctx = self._c(h)
+        if ctx.angle is None:
+            return self._fail(ctx, L.GZB_ERR_STATE, "gzb_get_angle: the context holds no angle (no -D)")
+        _view(out, (ctx.nj, ctx.ni), np.float64)[:] = ctx.angle
+        return L.GZB_OK
+
     # ------------------------------------------------------------------ K1 - K3
     def _nearest(self, ctx, nt, yt, xt, rd, r, sj, si):
         Y, X = _view(yt, (nt,), np.float64), _view(xt, (nt,), np.float64)

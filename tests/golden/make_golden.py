@@ -33,66 +33,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from gonzag_b200 import synthetic as syn          # noqa: E402
-from oracle.gz_oracle import point_strictly_in_quad  # noqa: E402  (shapely stand-in only)
 
 
 # ----------------------------------------------------------------- reference loading
-def load_reference(ref_root):
-    shp = types.ModuleType("shapely")
-    geo = types.ModuleType("shapely.geometry")
-    pol = types.ModuleType("shapely.geometry.polygon")
-
-    class Point:
-        def __init__(self, a, b):
-            self.a, self.b = a, b
-
-    class Polygon:
-        def __init__(self, pts):
-            self.qa = tuple(p[0] for p in pts)
-            self.qb = tuple(p[1] for p in pts)
-
-        def contains(self, p):
-            return point_strictly_in_quad(p.a, p.b, self.qa, self.qb)
-
-    geo.Point = Point
-    pol.Polygon = Polygon
-    geo.polygon = pol
-    shp.geometry = geo
-    sys.modules["shapely"] = shp
-    sys.modules["shapely.geometry"] = geo
-    sys.modules["shapely.geometry.polygon"] = pol
-
-    sys.path.insert(0, ref_root)
-    import gonzag  # noqa
-    store = {"fields": {}, "sat": {}}
-    nc = types.ModuleType("gonzag.ncio")
-    def _rd(fn):
-        # files registered as in-memory sources (case_grid) answer through them; the two legacy
-        # stand-ins below serve the SimpleNamespace cases
-        def call(f, *a, **k):
-            return getattr(store["src"][f], fn)(*a, **k)
-        return call
-
-    def get2d(f, v, kt=0):
-        if f in store.get("src", {}):
-            return np.array(store["src"][f].GetModel2DVar(v, kt=kt), copy=True)
-        return store["fields"][f][kt].copy()   # a file read returns a fresh array
-
-    def getsat(f, v, kt1=0, kt2=0, ikeep=[]):
-        if f in store.get("src", {}):
-            return store["src"][f].GetSatSSH(v, kt1=kt1, kt2=kt2, ikeep=ikeep)
-        return store["sat"][f]
-
-    nc.GetModel2DVar = get2d
-    nc.GetSatSSH = getsat
-    for fn in ("GetTimeEpochVector", "GetTimeInfo", "GetModelCoor", "GetModelLSM", "GetSatCoor"):
-        setattr(nc, fn, _rd(fn))
-    nc.Save2Dfield = lambda *a, **k: None
-    nc.SaveTimeSeries = lambda *a, **k: 0
-    store["src"] = {}
-    sys.modules["gonzag.ncio"] = nc
-    gonzag.ncio = nc
-    return gonzag, store
+from oracle.ref_loader import load_reference      # noqa: E402  (shapely + ncio stand-ins, then `import gonzag`)
 
 
 @contextlib.contextmanager
@@ -428,12 +372,52 @@ def case_grid(gz, store):
     return out
 
 
+def case_window(gz, store):
+    """A model time window that does NOT start at record 0: the track begins more than two model
+    records into the model file, so ModGrid keeps MG.time = time[jt1:jt2+1] with jt1 >= 2 while Model2SatTrack goes on
+    asking its reader for record k = index into that sliced vector (gonzag/mod2sat.py:94-112) -- i.e. records
+    0 .. nrec-1 of the file.  Unmodified GetEpochTimeOverlap -> ModGrid -> SatTrack -> Model2SatTrack."""
+    import tempfile
+    from gonzag_b200.sources import ModelArrays, TrackArrays
+    tmp = tempfile.mkdtemp(prefix="gzgoldw")
+    lat, lon = syn.regional_grid(90, 110, lat0=-42.0, lon0=12.0, res_deg=0.125, shear=0.03)
+    mask = syn.land_mask(lat, lon, seed=9, level=0.9)
+    tm = 4.0e9 + 1800.0 * np.arange(9)
+    f64 = syn.ssh_records(lat, lon, 9, dtype=np.float64)
+    t, y, x = syn.orbit_track(43200, t0=0.0, drop_land_seed=None, **syn.SARAL)
+    t = t * (2.6 * 1800.0 / 43200.0) + 4.0e9 + 2.0 * 1800.0 + 600.0      # inside records 2 .. 5
+    ssat = sat_ssh(len(t), 16)
+    out = dict(w_lat=lat, w_lon=lon, w_maskin=mask.astype(np.int8), w_tm=tm, w_f64=f64, w_t=t, w_y=y, w_x=x, w_ssat=ssat)
+    fm, fs = os.path.join(tmp, "w_mod.nc"), os.path.join(tmp, "w_sat.nc")
+    for f in (fm, fs):
+        open(f, "w").close()
+    store["src"][fm] = ModelArrays(tm, lat, lon, fields={"ssh": f64}, masks={"tmask": mask})
+    store["src"][fs] = TrackArrays(t, y, x, {"ssh": ssat})
+    with quiet():
+        (it1, it2), (Nts, Ntm) = gz.GetEpochTimeOverlap(fs, fm)
+        MG = gz.ModGrid(fm, it1, it2, fm, "tmask", distorded_grid=False)
+        ST = gz.SatTrack(fs, it1, it2, Np=100, domain_bounds=MG.domain_bounds, l_0_360=MG.l360)
+        R = gz.Model2SatTrack(MG, "ssh", ST, "ssh")
+    assert MG.time[0] == tm[2], "the window must start two records in"
+    o = {"it": np.array([it1, it2]), "nts_ntm": np.array([Nts, Ntm]),
+         "mg_time": MG.time, "mg_size": MG.size, "mg_lat": MG.lat, "mg_lon": MG.lon, "mg_mask": MG.mask,
+         "mg_scal": np.array([MG.HResDeg, MG.HResKM, float(MG.IsLonGlobal), float(MG.l360), MG.EWPer]),
+         "mg_bounds": np.array(MG.domain_bounds), "mg_xangle": MG.xangle,
+         "st_time": ST.time, "st_lat": ST.lat, "st_lon": ST.lon, "st_j": np.array([ST.jt1, ST.jt2, ST.size]),
+         "st_keepit": ST.keepit[0], "r_mask": R.mask, "r_dist": R.distance}
+    for nm in ("ssh_mod_np", "ssh_mod", "ssh_sat", "XNPtrack"):
+        pack_masked("r_" + nm, getattr(R, nm), o)
+    for k, v in o.items():
+        out["w_" + k] = v
+    return out
+
+
 def main():
     ref_root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
     gz, store = load_reference(ref_root)
     only = sys.argv[2:] if len(sys.argv) > 2 else None
     for name, fn in (("units", case_units), ("global", case_global), ("regional", case_regional),
-                     ("seam", case_seam), ("grid", case_grid)):
+                     ("seam", case_seam), ("grid", case_grid), ("window", case_window)):
         if only and name not in only:
             continue
         data = fn(gz, store)

@@ -35,6 +35,11 @@ def test_cli_main_from_files(emu, golden_grid, tmp_path, tag):
     T.test_cli_main_from_files(golden_grid, tmp_path, tag)
 
 
+@pytest.mark.parametrize("provider", ["array", "callable", "netcdf3"])
+def test_model_window_not_starting_at_record_0(emu, golden_window, tmp_path, provider):
+    T.test_model_window_not_starting_at_record_0(golden_window, tmp_path, provider)
+
+
 def test_streaming_provider_and_staged_paths(emu, golden_grid):
     T.test_streaming_provider_and_staged_paths(golden_grid)
 

@@ -129,6 +129,36 @@ def test_cli_main_from_files(golden_grid, tmp_path, tag):
         np.testing.assert_array_equal(np.isnan(trk), np.ma.getmaskarray(R.XNPtrack))
 
 
+@pytest.mark.parametrize("provider", ["array", "callable", "netcdf3"])
+def test_model_window_not_starting_at_record_0(golden_window, tmp_path, provider):
+    """The track starts two model records into the model file (jt1 = 2).  The reference keeps MG.time = time[2:6] and
+    asks its reader for record k = index into THAT vector (gonzag/mod2sat.py:94-112): every provider has to follow the
+    same rule -- a whole in-memory array (more records than MG.time), a per-record callable, a NetCDF-3 file."""
+    from tests.conftest import write_grid_case_files
+    g = golden_window
+    if provider == "netcdf3":
+        fm, ft, fl, varlsm, dist, Np = write_grid_case_files(g, "w", tmp_path)
+        model, track, lsm = fm, ft, fl
+    else:
+        model, track, lsm, varlsm, dist, Np = grid_case_sources(g, "w")
+        if provider == "callable":
+            arr = model.fields["ssh"]
+            model.fields["ssh"] = lambda k: arr[k]
+    (it1, it2), _ = gz.GetEpochTimeOverlap(track, model)
+    MG = gz.ModGrid(model, it1, it2, lsm, varlsm, distorded_grid=dist)
+    try:
+        assert MG.jt1 == 2 and MG.size == int(g["w_mg_size"])
+        np.testing.assert_allclose(MG.time, g["w_mg_time"], rtol=0, atol=1.5e-6)
+        ST = gz.SatTrack(track, it1, it2, Np=Np, domain_bounds=MG.domain_bounds, l_0_360=MG.l360)
+        assert [ST.jt1, ST.jt2, ST.size] == g["w_st_j"].tolist()
+        R = gz.Model2SatTrack(MG, "ssh", ST, "ssh")
+        assert R.fused_path == (provider == "array")
+        assert type(R.mask) is np.ndarray and R.mask.dtype == np.int8
+        _check_results(R, g, "w")
+    finally:
+        MG.close()
+
+
 def test_streaming_provider_and_staged_paths(golden_grid):
     """Records delivered one at a time (a file-like provider) and a whole pageable array too big
     to stay resident go through gzb_mapping + gzb_interp slab by slab: same products."""

@@ -1,6 +1,6 @@
-"""Live differential test of the oracle against the unmodified reference, run only where the
-reference checkout is mounted (the build container).  Complements the committed golden vectors
-with fresh random cases."""
+"""Live differential test of the oracle against the unmodified reference: run wherever the reference can be
+imported -- from the checkout (build container) or from its verbatim copy oracle/_ref (made by `make -C oracle`,
+travels to the GPU box).  Complements the committed golden vectors with fresh random cases."""
 import contextlib
 import io
 import os
@@ -9,21 +9,21 @@ import sys
 import numpy as np
 import pytest
 
-REF = os.environ.get("GONZAG_REFERENCE", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "gonzag")),
-                                reason="reference checkout not present")
+from oracle import ref_loader
+
+REF = ref_loader.find_reference()          # the checkout (build container) or its verbatim copy oracle/_ref (GPU box)
+pytestmark = pytest.mark.skipif(REF is None, reason="reference neither mounted nor copied (make -C oracle)")
 
 from gonzag_b200 import synthetic as syn
 from oracle import gz_oracle as orc
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))      # make_golden's helpers
 
 
 @pytest.fixture(scope="module")
 def ref():
     """(the imported reference package, the store behind its in-memory `ncio` stand-in)"""
-    sys.dont_write_bytecode = True
-    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
-    import make_golden
-    return make_golden.load_reference(REF)
+    return ref_loader.load_reference(REF)
 
 
 @pytest.fixture(scope="module")
