@@ -79,6 +79,7 @@ _SIGNATURES = {
     "gzb_dev_free": (C.c_int, [_P, _P]),
     "gzb_h2d": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gzb_d2h": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "gzb_d2d": (C.c_int, [_P, _P, _P, C.c_uint64]),
     "gzb_memset": (C.c_int, [_P, _P, C.c_int, C.c_uint64]),
     "gzb_ipc_export": (C.c_int, [_P, _P, _P]),
     "gzb_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
@@ -91,6 +92,9 @@ _SIGNATURES = {
     "gzb_peer_barrier": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _I64]),
     "gzb_check_edges": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P]),
     "gzb_pack_mask": (C.c_int, [_P, C.c_int, _I64, _P]),
+    "gzb_track_mask": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
+    "gzb_set_host_threads": (C.c_int, [C.c_int]),
+    "gzb_grid_arrays": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "gzb_copy_swap": (C.c_int, [_P, _P, C.c_int, _I64, C.c_int]),
     "gzb_pointer_kind": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "gzb_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),

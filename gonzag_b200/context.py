@@ -59,6 +59,31 @@ class GridContext:
         self.has_mask = msk is not None
         self.has_angle = ang is not None
 
+    @classmethod
+    def from_device(cls, Nj, Ni, lat_ptr, lon_ptr, angle_ptr=None, mask_ptr=None, k_ew_per=-1, device=0):
+        """A context built from arrays that already sit in DEVICE memory of GPU ``device`` (raw addresses: lat, lon
+        float64 (Nj, Ni); angle float64 or None; mask int8 or None) -- how the ranks of a sharded job get their copy of
+        a grid that one rank uploaded and the others received over NVLink (`gonzag_b200.sharded.replicate_grid`)."""
+        self = cls.__new__(cls)
+        self.Nj, self.Ni = int(Nj), int(Ni)
+        self.device = int(device)
+        self._h = None
+        h = C.c_void_p()
+        vp = lambda p: C.c_void_p(int(p)) if p else None
+        L.check(L.lib().gzb_create(self.device, self.Nj, self.Ni, vp(lat_ptr), vp(lon_ptr), vp(angle_ptr), vp(mask_ptr),
+                                   int(k_ew_per), C.byref(h)))
+        self._h = h
+        self.k_ew_per = int(k_ew_per)
+        self.has_mask = bool(mask_ptr)
+        self.has_angle = bool(angle_ptr)
+        return self
+
+    def grid_arrays(self):
+        """Device addresses (lat, lon, angle or None, int8 mask or None) of the arrays this context holds as uploaded."""
+        p = [C.c_void_p() for _ in range(4)]
+        self._ck(L.lib().gzb_grid_arrays(self._h, *[C.byref(q) for q in p]))
+        return tuple(q.value for q in p)
+
     # ------------------------------------------------------------------ life cycle
     def close(self):
         if self._h is not None:

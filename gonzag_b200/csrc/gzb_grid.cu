@@ -69,6 +69,27 @@ int gzb_use_device(gzb_ctx* ctx) {
 // thread through two pinned 8 MiB slots on its own stream (host memcpy of one slot overlapping the
 // DMA of the other).  The slots are allocated once per process and kept (gzb_pool_trim frees them).
 #define GZB_BC_THREADS 12
+// how many host threads the library's host-side helpers (parallel copies, mask packing, record staging) may start:
+// 0 = automatic (the machine's hardware threads), else the cap set by gzb_set_host_threads() or GZB_HOST_THREADS --
+// with one process per GPU every rank gets its share of the cores instead of all of them (8 x 12 threads on 32 cores)
+static int g_host_threads = -1;
+int gzb_host_threads(int fallback_cap) {
+    if (g_host_threads < 0) {
+        const char* e = getenv("GZB_HOST_THREADS");
+        g_host_threads = e ? atoi(e) : 0;
+        if (g_host_threads < 0) g_host_threads = 0;
+    }
+    int hw = (int)std::thread::hardware_concurrency();
+    if (hw < 1) hw = 1;
+    int want = g_host_threads > 0 ? g_host_threads : hw;
+    if (want > hw) want = hw;
+    if (want > fallback_cap) want = fallback_cap;
+    return want < 1 ? 1 : want;
+}
+extern "C" int gzb_set_host_threads(int n) {
+    g_host_threads = n < 0 ? 0 : n;
+    return GZB_OK;
+}
 #define GZB_BC_SLOT ((size_t)4 << 20)
 #define GZB_BC_MIN ((size_t)24 << 20)
 namespace {
@@ -154,7 +175,8 @@ int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d
         if (!bigcopy_ready(ctx->device)) { plain = true; lk.unlock(); }
     }
     if (plain) {
-        GZB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, h2d ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        // cudaMemcpyDefault: `src` of an upload may itself be device memory (a grid replicated from another GPU)
+        GZB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
         GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return GZB_OK;
     }
@@ -162,8 +184,9 @@ int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d
     if (sync_before) GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::thread th[GZB_BC_THREADS];
     cudaError_t errs[GZB_BC_THREADS];
-    int want = (int)std::thread::hardware_concurrency() - 1;
-    want = want < 2 ? 2 : (want > GZB_BC_THREADS ? GZB_BC_THREADS : want);
+    int want = gzb_host_threads(GZB_BC_THREADS);
+    if (want > 2 && want == (int)std::thread::hardware_concurrency()) --want;      // leave one core to the caller
+    want = want < 2 ? 2 : want;
     const size_t part = (((bytes + want - 1) / want) + 4095) & ~(size_t)4095;
     int nth = 0;
     for (int t = 0; t < want; ++t) {
@@ -1416,6 +1439,18 @@ extern "C" int gzb_get_angle(gzb_ctx* ctx, double* angle_out, int where) {
     return GZB_OK;
 }
 
+// Device pointers of the arrays a context was created from (as uploaded: lat, lon row-major float64; the angle
+// and the int8 mask when installed, else NULL).  A multi-GPU host replicates a grid with them: one rank uploads,
+// the others receive the arrays over NVLink (any collective) and call gzb_create with DEVICE pointers.
+extern "C" int gzb_grid_arrays(gzb_ctx* ctx, void** lat, void** lon, void** angle, void** mask) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_grid_arrays: null ctx");
+    if (lat) *lat = ctx->d_lat;
+    if (lon) *lon = ctx->d_lon;
+    if (angle) *angle = (void*)ctx->g.angle;
+    if (mask) *mask = (void*)ctx->g.mask;
+    return GZB_OK;
+}
+
 // ======================================================================== memory helpers
 extern "C" int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out) {
     if (!ctx || !dptr_out) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_dev_alloc: null argument");
@@ -1461,6 +1496,14 @@ extern "C" int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64
         GZB_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->stats.d2h_bytes += bytes;
+    return GZB_OK;
+}
+
+extern "C" int gzb_d2d(gzb_ctx* ctx, void* dst_dev, const void* src_dev, uint64_t bytes) {
+    if (!ctx || (bytes && (!dst_dev || !src_dev))) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_d2d: null argument");
+    if (!bytes) return GZB_OK;
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GZB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return GZB_OK;
 }
 
@@ -1536,8 +1579,7 @@ extern "C" int gzb_pack_mask(const void* src, int itemsize, int64_t n, int8_t* d
     if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)
         return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_pack_mask: itemsize must be 1, 2, 4 or 8 (got %d)", itemsize);
     if (n == 0) return GZB_OK;
-    int want = (int)std::thread::hardware_concurrency();
-    want = want < 1 ? 1 : (want > 16 ? 16 : want);
+    const int want = gzb_host_threads(16);
     const size_t per_min = (size_t)1 << 20;                        // below ~1 M elements a thread is not worth its start
     const size_t N = (size_t)n;
     int nth = (int)((N + per_min - 1) / per_min);
@@ -1600,8 +1642,7 @@ extern "C" int gzb_copy_swap(void* dst, const void* src, int itemsize, int64_t n
     if (n == 0) return GZB_OK;
     const size_t N = (size_t)n;
     const bool do_swap = swap != 0 && itemsize > 1;
-    int want = (int)std::thread::hardware_concurrency();
-    want = want < 1 ? 1 : (want > 16 ? 16 : want);
+    const int want = gzb_host_threads(16);
     const size_t per_min = ((size_t)2 << 20) / (size_t)itemsize;       // 2 MiB per thread at least
     int nth = (int)((N + per_min - 1) / per_min);
     nth = nth > want ? want : nth;

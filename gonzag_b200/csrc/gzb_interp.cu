@@ -393,6 +393,31 @@ extern "C" int gzb_track_distance(gzb_ctx* ctx, int64_t nt, const double* yt, co
 }
 
 // ------------------------------------------------------------------------------------------
+// imask of Model2SatTrack (gonzag/mod2sat.py:157-158): 1 where the interpolated model value and the satellite value
+// both lie in (-100, 100) -- NaN and inf fail, as in the reference's chained comparisons -- plus its complement, the
+// mask of the three masked_where(imask == 0, .) products (:160-162)
+__global__ void k_track_mask(const long long nt, const double* __restrict__ bl, const double* __restrict__ sat,
+                             signed char* __restrict__ imask, unsigned char* __restrict__ bad) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const double a = bl[t], b = sat[t];
+    const bool good = (a > -100.0) && (a < 100.0) && (b > -100.0) && (b < 100.0);
+    imask[t] = good ? 1 : 0;
+    if (bad) bad[t] = good ? 0 : 1;
+}
+
+extern "C" int gzb_track_mask(gzb_ctx* ctx, int64_t nt, const double* bl, const double* sat, int8_t* imask_out,
+                              unsigned char* bad_out_or_null) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_track_mask: null ctx");
+    if (nt < 0 || (nt > 0 && (!bl || !sat || !imask_out))) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_track_mask: bad arguments");
+    if (nt == 0) return GZB_OK;
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    k_track_mask<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(nt, bl, sat, (signed char*)imask_out, bad_out_or_null);
+    GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // XNPtrack: last track index per cell (Python's last-writer-wins loop == max index)
 __global__ void k_xnp_scatter(const GzbGrid g, const long long nt, const long long* __restrict__ NP,
                               long long* __restrict__ last) {

@@ -64,6 +64,7 @@ int gzb_device_count(int* n_out);
  * (gonzag/bilin_mapping.py:533-545) and MG.lat/MG.lon/MG.xangle/MG.EWPer/MG.mask as read by
  * Model2SatTrack (gonzag/mod2sat.py:33-50,124).  lat/lon: (nj,ni) float64 degrees, finite.
  * angle: (nj,ni) float64 degrees or NULL (no -D).  mask: (nj,ni) int8 {0,1} or NULL.
+ * The four arrays may live in host memory (pageable or pinned) or in device memory (detected).
  * k_ew_per: -1 none, >=0 overlap of the East-West periodicity. */
 int gzb_create(int device, int64_t nj, int64_t ni, const double* lat, const double* lon,
                const double* angle_or_null, const int8_t* mask_or_null, int k_ew_per,
@@ -222,6 +223,12 @@ int gzb_xnp_track(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval,
 int gzb_xnp_track_masked(gzb_ctx* ctx, int64_t nt, const int64_t* np, double rmissval,
                          double* xnp_out, unsigned char* missing_out, int where);
 
+/* imask of Model2SatTrack (gonzag/mod2sat.py:157-158) on DEVICE arrays: imask_out[t] = 1 iff -100 < bl[t] < 100 and
+ * -100 < sat[t] < 100 (int8, the dtype of the reference's attribute `mask`); bad_out (optional, uint8) = its
+ * complement, the mask of the reference's three masked_where(imask == 0, .) products (:160-162). */
+int gzb_track_mask(gzb_ctx* ctx, int64_t nt, const double* bl, const double* sat, int8_t* imask_out,
+                   unsigned char* bad_out_or_null);
+
 /* ---- scalar helpers exported by the reference package, batched ------------------------------
  * gzb_heading  : Heading(lata,lona,latb,lonb)      gonzag/bilin_mapping.py:16-47
  * gzb_alfabeta : AlfaBeta(vy[5], vx[5]) -> (a,b)   gonzag/bilin_mapping.py:50-141
@@ -271,6 +278,7 @@ int gzb_dev_alloc(gzb_ctx* ctx, uint64_t bytes, void** dptr_out);
 int gzb_dev_free(gzb_ctx* ctx, void* dptr);
 int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);   /* async; >= 24 MiB of pageable memory: parallel staging, returns when done */
 int gzb_d2h(gzb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);   /* idem */
+int gzb_d2d(gzb_ctx* ctx, void* dst_dev, const void* src_dev, uint64_t bytes);          /* async, on the context's stream */
 int gzb_memset(gzb_ctx* ctx, void* dst_dev, int byte, uint64_t bytes);            /* async */
 /* Device buffers of the library come from a process-wide pool (freed blocks are kept, per device
  * and exact size, for the next request of that size: repeated calls on the same grid allocate
@@ -291,6 +299,14 @@ int gzb_copy_swap(void* dst, const void* src, int itemsize, int64_t n, int swap)
 /* Where does `p` live?  kind_out: 0 pageable host memory (or unknown), 1 pinned + mapped host
  * memory (the GPU can read it in place), 2 device / managed memory. */
 int gzb_pointer_kind(const void* p, int* kind_out);
+/* Cap on the host threads the library starts for parallel copies, mask packing and record staging (0 = automatic:
+ * all hardware threads; also settable with the environment variable GZB_HOST_THREADS).  One process per GPU: give
+ * every rank cores / local world size. */
+int gzb_set_host_threads(int n);
+/* Device pointers of the arrays a context holds as uploaded (lat, lon float64 row-major; angle float64 and mask int8
+ * when installed, else NULL): what a multi-GPU host broadcasts so that the other ranks can call gzb_create with
+ * DEVICE pointers (gzb_create accepts host or device memory for its four arrays). */
+int gzb_grid_arrays(gzb_ctx* ctx, void** lat, void** lon, void** angle, void** mask);
 int gzb_host_alloc(uint64_t bytes, void** hptr_out);     /* pinned, portable, mapped */
 int gzb_host_free(void* hptr);
 int gzb_host_register(void* hptr, uint64_t bytes);

@@ -166,6 +166,18 @@ class EmuLib:
             return self._fail(ctx, L.GZB_ERR_TIME, "gzb_interp: track time outside the model records [tmod[0], tmod[nrec-1])")
         return L.GZB_OK
 
+    def gzb_set_host_threads(self, n):
+        return L.GZB_OK
+
+    def gzb_grid_arrays(self, h, lat, lon, angle, mask):
+        ctx = self._c(h)
+        if ctx.mask is not None and getattr(ctx, "mask8", None) is None:
+            ctx.mask8 = np.ascontiguousarray(ctx.mask.astype(np.int8))
+        for p, a in ((lat, ctx.lat), (lon, ctx.lon), (angle, ctx.angle), (mask, getattr(ctx, "mask8", None))):
+            if p is not None:
+                _target(p).value = None if a is None else a.ctypes.data
+        return L.GZB_OK
+
     def gzb_set_stream(self, h, s):
         return L.GZB_OK
 
@@ -181,6 +193,7 @@ class EmuLib:
     def gzb_set_mask(self, h, mask, where):
         ctx = self._c(h)
         ctx.mask = _view(mask, (ctx.nj, ctx.ni), np.int8).astype(np.int64)
+        ctx.mask8 = None
         ctx.h2d += ctx.nj * ctx.ni
         return L.GZB_OK
 
@@ -220,6 +233,10 @@ class EmuLib:
     def gzb_d2h(self, h, dst, src, nbytes):
         C.memmove(_addr(dst), _addr(src), int(nbytes))
         self._c(h).d2h += int(nbytes)
+        return L.GZB_OK
+
+    def gzb_d2d(self, h, dst, src, nbytes):
+        C.memmove(_addr(dst), _addr(src), int(nbytes))
         return L.GZB_OK
 
     def gzb_memset(self, h, dst, byte, nbytes):
@@ -359,6 +376,17 @@ class EmuLib:
         if nt:
             _view(out, (nt,), np.float64)[:] = orc.along_track_distance(_view(yt, (nt,), np.float64), _view(xt, (nt,), np.float64))
         ctx.launches += 3
+        return L.GZB_OK
+
+    def gzb_track_mask(self, h, nt, bl, sat, imask_out, bad_out):
+        if nt:
+            a, b = _view(bl, (nt,), np.float64), _view(sat, (nt,), np.float64)
+            with np.errstate(invalid="ignore"):
+                good = (a > -100.) & (a < 100.) & (b > -100.) & (b < 100.)      # gonzag/mod2sat.py:157-158
+            _view(imask_out, (nt,), np.int8)[:] = good
+            if _addr(bad_out):
+                _view(bad_out, (nt,), np.uint8)[:] = ~good
+        self._c(h).launches += 1
         return L.GZB_OK
 
     def gzb_xnp_track_masked(self, h, nt, np_in, rmiss, xnp_out, missing_out, where):
