@@ -180,7 +180,7 @@ def ssh_records(lat, lon, nrec: int, dtype=np.float32, seed: int = 2):
 def orbit_track(n_seconds: int, t0: float = 0.0, incl_deg: float = 98.55,
                 period_s: float = 6035.0, phase: float = 0.37, lon0_deg: float = 11.3,
                 dt: float = 1.0, drop_land_seed: int | None = 1,
-                lat_bounds=None, lon_bounds=None, lon_frame_360: bool = True):
+                lat_bounds=None, lon_bounds=None, lon_frame_360: bool = True, start_s: float = 0.0):
     """Ground track of a circular orbit: returns ``time, lat, lon`` (fp64).
 
     ``drop_land_seed`` removes points over the pseudo-continents of
@@ -189,7 +189,7 @@ def orbit_track(n_seconds: int, t0: float = 0.0, incl_deg: float = 98.55,
     reference's `SatTrack` (gonzag/utils.py:531-539).
     """
     n = int(round(n_seconds / dt))
-    tt = dt * np.arange(n, dtype=np.float64)
+    tt = start_s + dt * np.arange(n, dtype=np.float64)      # start_s: a later window of the same orbit
     u = 2.0 * np.pi * tt / period_s + phase
     inc = np.radians(incl_deg)
     lat = np.degrees(np.arcsin(np.sin(inc) * np.sin(u)))

@@ -189,15 +189,38 @@ def test_c3_chain_links_and_oracle_prefix(c3):
 
 
 def test_c4_shape_chain_links():
-    """ORCA36-class grid (BASELINE config 4 shape), one day of track: every chain link verified."""
+    """ORCA36-class grid (BASELINE config 4 shape), half a day of track: K0-K4 against the oracle on a subset, every chain
+    link of K1 verified by brute force."""
     lat, lon = syn.orca_like_grid(9000, 13000)
     res = syn.grid_resolution_deg(lon)
     rd, r = syn.search_params(res)
     assert r >= 80
     t, y, x = syn.orbit_track(43200, t0=100.0, **syn.JASON)
-    with gzb.GridContext(lat, lon, k_ew_per=2) as ctx:
+    mask = syn.land_mask(lat, lon)
+    with gzb.GridContext(lat, lon, mask=mask, k_ew_per=2) as ctx:
         NP = ctx.nearest(y, x, rd, r)
         assert ctx.stats()["pyramid_levels"] >= 5
+        # K0 + K2 + K3 + K4 at this size: the fused mapping call equals the staged nearest points, then the per-point
+        # stages against the oracle on a random subset plus the points whose cell is rotated by more than 45 degrees
+        ang = ctx.grid_angle()
+        NP2, SM, WB = ctx.mapping(y, x, rd, r)
+        np.testing.assert_array_equal(NP2, NP)
+        rng = np.random.default_rng(4)
+        idx = np.sort(rng.choice(len(y), 2000, replace=False))
+        hot = np.where((NP[:, 0] >= 0) & (np.abs(ang[NP[:, 0], NP[:, 1]]) > 45.0))[0]
+        if hot.size:
+            idx = np.unique(np.concatenate([idx, hot[:1000]]))
+        sm = orc.source_meshes(y, x, lat, lon, NP, 2, angle=ang, idx=idx)
+        bad = np.where((SM[idx] != sm).reshape(len(idx), -1).any(1))[0]
+        assert bad.size == 0, (idx[bad][:5], SM[idx][bad][:2], sm[bad][:2])
+        np.testing.assert_allclose(WB[idx], orc.weights(y, x, lat, lon, sm, idx=idx), rtol=1e-6, atol=1e-9)
+        tmod = np.array([0.0, t[-1] + 10.0])
+        fld = syn.ssh_records(lat, lon, 2)
+        v_np, v_bl = ctx.interp(t, SM, WB, tmod, fld)
+        o_np, o_bl = orc.interp_track(t[idx], tmod, lambda k: fld[k], mask, SM[idx], WB[idx])
+        np.testing.assert_allclose(v_bl[idx], o_bl, rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(v_np[idx], o_np, rtol=1e-6, atol=1e-9)
+        assert (v_bl != -9999.0).mean() > 0.5
     assert (NP[:, 0] >= 0).mean() > 0.9
     verify_chain_links(lat, lon, y, x, NP, 2, rd, r, batch=128)
 
