@@ -762,7 +762,10 @@ def run_ours(args, w):
                             "ms_per_step_by_rank": [round(v, 4) for v in per_rank_ms],
                             "ms_each_timed_step_rank0": [round(v, 4) for v in step_ms], "seed_reseeds": mapper.reseeds,
                             "chain_breaks": int(ctx.stats()["last_breaks"]),
-                            "chain_replay_steps": int(ctx.stats()["last_chain_steps"])},
+                            "chain_replay_steps": int(ctx.stats()["last_chain_steps"]),
+                            "k1_points_left_to_the_warp_search": {k: int(ctx.stats()[k]) for k in
+                                                                  ("last_unresolved", "last_unres_noseed", "last_unres_noconv",
+                                                                   "last_unres_nocert")}},
                 "verified": verified,
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roof, "kernels": kern,
                 "cpu_baseline": cpu, "e2e": e2e}
@@ -875,11 +878,11 @@ class RecordGenerator:
 def run_windowed(args, w):
     """C4 / C5: strong scaling.  Every mission is a chain of its own (first point seeded (r, r), gonzag/bilin_mapping.py:570),
     cut into `world` contiguous time segments; rank g maps segment g of every mission.  A rank walks its time slice window by
-    window: the records of a window are generated on the device (untimed: the stand-in for the reader), then every mission's
-    points of that window go through ONE gzb_map_interp call, seeded with the mission's previous nearest point (the first
-    window of a later rank: the unseeded nearest point of its predecessor's last point, checked against the truth after the
-    gather).  Timed: every gzb_map_interp call (CUDA events on the launching stream, L2 flushed before each) + the final
-    all-gather of (ssh_np, ssh_bl, NP) of every mission over NVLink; max over ranks."""
+    window: the records of a window are generated on the device (untimed: the stand-in for the reader), then the points of
+    ALL missions in that window go through ONE gzb_map_interp_multi call, one chain per mission, each seeded with the
+    mission's previous nearest point (the first window of a later rank: the unseeded nearest point of the mission's previous
+    point, checked against the truth after the gather).  Timed: every such call (CUDA events on the launching stream, L2
+    flushed before each) + the final all-gather of (ssh_np, ssh_bl, NP) over NVLink; max over ranks."""
     import types
     import torch
     import torch.distributed as dist
@@ -934,35 +937,48 @@ def run_windowed(args, w):
     hours = int(round(w["days"] * 24))
     nrec_all = hours + 2
     tmod_d = eng.tensor(rec_dt * np.arange(nrec_all))
-    # ---- missions (whole period, every rank: verification needs them), this rank's time slice
+    # ---- missions (whole period on every rank: verification needs them), laid out WINDOW-MAJOR: the points of all
+    # missions that fall into one record window are contiguous (mission after mission), windows in time order -- what a
+    # window's ONE gzb_map_interp_multi call takes, and a rank's windows are one contiguous range of every array
     nm = w["missions"]
     tracks = [orbit_track_device(torch, dev, hours * 3600, *MISSIONS[m]) for m in range(nm)]
     hb = [int(round(g * hours / world)) for g in range(world + 1)]          # slice boundaries in hours
-    t_lo, t_hi = hb[rank] * 3600.0, hb[rank + 1] * 3600.0
-    seg = []
-    for (t, y, x) in tracks:
-        cut = torch.searchsorted(t, torch.tensor([t_lo, t_hi, *[hb[g] * 3600.0 for g in range(world + 1)]], dtype=torch.float64,
-                                                 device=dev)).cpu().numpy()
-        seg.append((int(cut[0]), int(cut[1]), [int(v) for v in cut[2:]]))
-    nt_total = int(sum(len(t) for (t, _, _) in tracks))
-    nt_local = int(sum(b - a for (a, b, _) in seg))
     wh = int(w["window_h"])
-    windows = [(k, min(k + wh, hb[rank + 1])) for k in range(hb[rank], hb[rank + 1], wh)]
+    wins = [(g, k, min(k + wh, hb[g + 1])) for g in range(world) for k in range(hb[g], hb[g + 1], wh)]      # (rank, first hour, end hour)
+    edges_s = torch.tensor([3600.0 * k for (_, k, _) in wins] + [3600.0 * hours], dtype=torch.float64, device=dev)
+    cut = [torch.searchsorted(t, edges_s).cpu().numpy() for (t, _, _) in tracks]       # mission index of every window boundary
+    blocks, pieces, off = [], ([], [], []), 0
+    for wi in range(len(wins)):
+        row = []
+        for m in range(nm):
+            i0, i1 = int(cut[m][wi]), int(cut[m][wi + 1])
+            if i1 > i0:
+                row.append((m, off, i1 - i0, i0))               # mission, window-major offset, count, mission index
+                for q in range(3):
+                    pieces[q].append(tracks[m][q][i0:i1])
+                off += i1 - i0
+        blocks.append(row)
+    nt_total = off
+    T, Y, X = (torch.cat(pc) for pc in pieces)
+    del pieces
+    my_w = [wi for wi, (g, _, _) in enumerate(wins) if g == rank]
+    rng_of = []                                                   # window-major range of every rank
+    for g in range(world):
+        ws_ = [wi for wi, (gg, _, _) in enumerate(wins) if gg == g]
+        lo_ = min([blk[1] for wi in ws_ for blk in blocks[wi]], default=0)
+        hi_ = max([blk[1] + blk[2] for wi in ws_ for blk in blocks[wi]], default=lo_)
+        rng_of.append((lo_, hi_))
+    p0, p1 = rng_of[rank]
+    nt_local = p1 - p0
+    nloc_max = max(hi_ - lo_ for (lo_, hi_) in rng_of)
+    nwmax = max([sum(blk[2] for blk in blocks[wi]) for wi in my_w] + [1])
     slab = torch.empty((wh + 1, nj, ni), dtype=torch.float32, device=dev)
-    # ---- outputs: per mission, this rank's segment (+ SM / WB of the segment when verifying; else one reused window buffer)
-    verify = world > 1 and not args.no_verify
-    nwmax = 1
-    for (t, _, _), (a, b, _) in zip(tracks, seg):
-        for (ka, kb) in windows:
-            c = torch.searchsorted(t[a:b], torch.tensor([ka * 3600.0, kb * 3600.0], dtype=torch.float64, device=dev)).cpu().numpy()
-            nwmax = max(nwmax, int(c[1] - c[0]))
-    out = []
-    for (a, b, _) in seg:
-        n = b - a
-        out.append(dict(NP=eng.empty((max(n, 1), 2), torch.int64), vnp=eng.empty((max(n, 1),), torch.float64),
-                        vbl=eng.empty((max(n, 1),), torch.float64)))
+    NPa = eng.empty((max(nt_total, 1), 2), torch.int64)
+    vnp = eng.empty((max(nt_total, 1),), torch.float64)
+    vbl = eng.empty((max(nt_total, 1),), torch.float64)
     SMw = eng.empty((nwmax, 4, 2), torch.int64)
     WBw = eng.empty((nwmax, 4), torch.float64)
+    verify = world > 1 and not args.no_verify
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
     flush_sink = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -976,91 +992,90 @@ def run_windowed(args, w):
     torch.cuda.synchronize()
     log("[rank %d] setup %.1f s: grid %dx%d, %d missions, %d of %d track points, hours %d..%d in %d windows of <= %d h (%.1f GB of "
         "records each), r=%d" % (rank, time.perf_counter() - t_setup, nj, ni, nm, nt_local, nt_total, hb[rank], hb[rank + 1],
-                                 len(windows), wh, slab.numel() * 4 / 1e9, r))
+                                 len(my_w), wh, slab.numel() * 4 / 1e9, r))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # gather buffers: per mission [world, nseg_max] for ssh_np, ssh_bl, NP
-    nseg_max = [max(s[2][g + 1] - s[2][g] for g in range(world)) for s in seg]
-    gat = [dict(vnp=eng.empty((world, max(nmx, 1)), torch.float64), vbl=eng.empty((world, max(nmx, 1)), torch.float64),
-                NP=eng.empty((world, max(nmx, 1), 2), torch.int64)) if world > 1 else None for nmx in nseg_max]
-    pad = [dict(vnp=eng.empty((max(nmx, 1),), torch.float64), vbl=eng.empty((max(nmx, 1),), torch.float64),
-                NP=eng.empty((max(nmx, 1), 2), torch.int64)) if world > 1 else None for nmx in nseg_max]
+    gat = {k: eng.empty((world, max(nloc_max, 1)) + sh, ty) for k, sh, ty in
+           (("vnp", (), torch.float64), ("vbl", (), torch.float64), ("NP", (2,), torch.int64))} if world > 1 else None
+    pad = {k: eng.empty((max(nloc_max, 1),) + sh, ty) for k, sh, ty in
+           (("vnp", (), torch.float64), ("vbl", (), torch.float64), ("NP", (2,), torch.int64))} if world > 1 else None
+    # for every mission: where its last point before my slice sits (window-major position), if any
+    pred_pos = {}
+    if my_w:
+        for m in range(nm):
+            for wi in range(my_w[0] - 1, -1, -1):
+                hit = [blk for blk in blocks[wi] if blk[0] == m]
+                if hit:
+                    pred_pos[m] = hit[0][1] + hit[0][2] - 1
+                    break
 
-    def one_pass(keep_sm_wb=None, seeds0=None):
-        """One pass over this rank's slice.  Returns (timed ms, kernel launches, per-mission halo seed used, events)."""
-        seeds, halos = [], []
-        for m, ((t, y, x), (a, b, _)) in enumerate(zip(tracks, seg)):
-            if seeds0 is not None:
-                sd = seeds0[m]
-            elif a > 0 and b > a:      # a later segment: the unseeded nearest point of the predecessor's last point
+    def one_pass(keep=None, seeds0=None):
+        """One pass over this rank's windows.  Returns (timed ms, kernel launches, the seed each mission started from)."""
+        seeds = {}
+        for m in range(nm):
+            if seeds0 is not None and m in seeds0:
+                seeds[m] = seeds0[m]
+            elif m in pred_pos:           # a later slice: the unseeded nearest point of the mission's previous point
+                q = pred_pos[m]
                 NPh = eng.empty((1, 2), torch.int64)
-                eng.nearest(y[a - 1:a].contiguous(), x[a - 1:a].contiguous(), rd, r, (0, 0), NPh)
+                eng.nearest(Y[q:q + 1], X[q:q + 1], rd, r, (0, 0), NPh)
                 v = NPh.cpu().numpy()[0]
-                sd = (int(v[0]), int(v[1]))
+                seeds[m] = (int(v[0]), int(v[1]))
             else:
-                sd = (r, r)
-            seeds.append(sd)
-            halos.append(sd)
+                seeds[m] = (r, r)                               # gonzag/bilin_mapping.py:570
+        start_seeds = dict(seeds)
         pairs = []
         n0 = ctx.stats()["kernel_launches"]
-        for (ka, kb) in windows:
-            gen.fill(slab[:kb - ka + 1], ka)                      # records ka .. kb (untimed)
-            for m, ((t, y, x), (a, b, _)) in enumerate(zip(tracks, seg)):
-                if b <= a:
-                    continue
-                c = torch.searchsorted(t[a:b], torch.tensor([ka * 3600.0, kb * 3600.0], dtype=torch.float64, device=dev)).cpu().numpy()
-                i0, i1 = a + int(c[0]), a + int(c[1])
-                if i1 <= i0:
-                    continue
-                o = out[m]
-                lo_, hi_ = i0 - a, i1 - a
-                SMv = keep_sm_wb[m][0][lo_:hi_] if keep_sm_wb is not None else SMw[:hi_ - lo_]
-                WBv = keep_sm_wb[m][1][lo_:hi_] if keep_sm_wb is not None else WBw[:hi_ - lo_]
-                flush_l2()
-                e0, e1 = ev(), ev()
-                e0.record()
-                eng.map_interp(y[i0:i1], x[i0:i1], t[i0:i1], rd, r, seeds[m], tmod_d, slab[:kb - ka + 1], ka, o["NP"][lo_:hi_],
-                               SMv, WBv, o["vnp"][lo_:hi_], o["vbl"][lo_:hi_])
-                e1.record()
-                pairs.append((e0, e1))
-                v = o["NP"][hi_ - 1].cpu().numpy()               # the next window of this mission starts from here (sync; untimed)
-                seeds[m] = (int(v[0]), int(v[1]))
+        for wi in my_w:
+            _, ka, kb = wins[wi]
+            gen.fill(slab[:kb - ka + 1], ka)                      # records ka .. kb (untimed: the stand-in for the reader)
+            row = blocks[wi]
+            if not row:
+                continue
+            a_ = row[0][1]
+            n = sum(blk[2] for blk in row)
+            st = [blk[1] - a_ for blk in row]
+            sd = [seeds[blk[0]] for blk in row]
+            SMv = keep[0][a_ - p0:a_ - p0 + n] if keep is not None else SMw[:n]
+            WBv = keep[1][a_ - p0:a_ - p0 + n] if keep is not None else WBw[:n]
+            flush_l2()
+            e0, e1 = ev(), ev()
+            e0.record()
+            eng.map_interp_multi(st, sd, Y[a_:a_ + n], X[a_:a_ + n], T[a_:a_ + n], rd, r, tmod_d, slab[:kb - ka + 1], ka,
+                                 NPa[a_:a_ + n], SMv, WBv, vnp[a_:a_ + n], vbl[a_:a_ + n])
+            e1.record()
+            pairs.append((e0, e1))
+            tails = NPa[[blk[1] + blk[2] - 1 for blk in row]].cpu().numpy()      # every mission goes on from here (one sync; untimed)
+            for blk, v in zip(row, tails):
+                seeds[blk[0]] = (int(v[0]), int(v[1]))
         launches = ctx.stats()["kernel_launches"] - n0
-        # ---- the one data-path collective: all-gather of every mission's segment products
+        # ---- the one data-path collective: all-gather of the ranks' (contiguous) product ranges
         if world > 1:
             barrier()
             e0, e1 = ev(), ev()
             e0.record()
-            for m, (a, b, _) in enumerate(seg):
-                n = b - a
-                for key in ("vnp", "vbl", "NP"):
-                    pad[m][key][:n] = out[m][key][:n]
-                    dist.all_gather_into_tensor(gat[m][key].view(-1), pad[m][key].view(-1))
+            for key, src in (("vnp", vnp), ("vbl", vbl), ("NP", NPa)):
+                pad[key][:nt_local] = src[p0:p1]
+                dist.all_gather_into_tensor(gat[key].view(-1), pad[key].view(-1))
             e1.record()
             pairs.append((e0, e1))
         torch.cuda.synchronize()
-        ms = float(sum(a_.elapsed_time(b_) for a_, b_ in pairs))
-        return ms, launches, halos
+        ms = float(sum(a.elapsed_time(b) for a, b in pairs))
+        return ms, launches, start_seeds
 
-    def boundaries_ok(halos):
-        """every later segment's seed assumption == the true last nearest point of the segment before it (from the gather)"""
+    def boundaries(start_seeds):
+        """every later slice's seed assumption == the true nearest point of the mission's previous point (from the gather)"""
         if world == 1:
             return True, None
         fix = {}
-        for m, (a, b, cuts) in enumerate(seg):
-            if not (a > 0 and b > a):
-                continue
-            g = rank - 1
-            while g >= 0 and cuts[g + 1] - cuts[g] == 0:
-                g -= 1
-            if g < 0:
-                continue
-            true_last = gat[m]["NP"][g, cuts[g + 1] - cuts[g] - 1].cpu().numpy()
-            if (int(true_last[0]), int(true_last[1])) != tuple(halos[m]):
+        for m, q in pred_pos.items():
+            g = max(gg for gg in range(world) if rng_of[gg][0] <= q < rng_of[gg][1])
+            true_last = gat["NP"][g, q - rng_of[g][0]].cpu().numpy()
+            if (int(true_last[0]), int(true_last[1])) != tuple(start_seeds[m]):
                 fix[m] = (int(true_last[0]), int(true_last[1]))
         bad = torch.tensor([len(fix)], dtype=torch.int32, device=dev)
         dist.all_reduce(bad, op=dist.ReduceOp.SUM)
@@ -1068,17 +1083,18 @@ def run_windowed(args, w):
 
     reseeds = 0
 
-    def settled_pass(keep_sm_wb=None):
+    def settled_pass(keep=None):
         """a pass, repeated from the true seeds while some boundary disagrees (rare: a chain deviation across a boundary)"""
         nonlocal reseeds
-        ms, launches, halos = one_pass(keep_sm_wb)
+        ms, launches, start_seeds = one_pass(keep)
         for _ in range(world):
-            ok, fix = boundaries_ok(halos)
+            ok, fix = boundaries(start_seeds)
             if ok:
                 break
             reseeds += 1
-            seeds0 = [fix.get(m, halos[m]) for m in range(nm)]
-            ms, launches, halos = one_pass(keep_sm_wb, seeds0=seeds0)
+            seeds0 = dict(start_seeds)
+            seeds0.update(fix)
+            ms, launches, start_seeds = one_pass(keep, seeds0=seeds0)
         return ms, launches
 
     for _ in range(max(1, min(args.warmup, 2))):       # a pass is hundreds of launches: one or two warm-up passes are enough
@@ -1086,26 +1102,30 @@ def run_windowed(args, w):
     barrier()
     verified = None
     if verify:
-        # OUTSIDE the timed region: every rank maps every WHOLE mission alone (K1-K3, a second context is not needed: same
-        # grid) and compares (a) the all-gathered NP of all segments, (b) its own segment's SM / WB, bit for bit; the series
-        # every rank holds are compared with its own segment's (transport check).
-        keep = [(eng.empty((max(b - a, 1), 4, 2), torch.int64), eng.empty((max(b - a, 1), 4), torch.float64)) for (a, b, _) in seg]
+        # OUTSIDE the timed region: every rank maps every WHOLE mission alone (K1-K3, one chain from (r, r)) and compares
+        # (a) the all-gathered NP of all slices, (b) its own slice's SM / WB, bit for bit; the gathered series of its own
+        # range are compared with the local ones (transport).
+        keep = (eng.empty((max(nt_local, 1), 4, 2), torch.int64), eng.empty((max(nt_local, 1), 4), torch.float64))
         settled_pass(keep)
-        ok = True
-        for m, ((t, y, x), (a, b, cuts)) in enumerate(zip(tracks, seg)):
+        full_NP = torch.cat([gat["NP"][g, :rng_of[g][1] - rng_of[g][0]] for g in range(world)])
+        ok = bool((gat["vnp"][rank, :nt_local].view(torch.int64) == vnp[p0:p1].view(torch.int64)).all())
+        for m, (t, y, x) in enumerate(tracks):
             n_all = len(t)
             NPf, SMf, WBf = eng.empty((n_all, 2), torch.int64), eng.empty((n_all, 4, 2), torch.int64), eng.empty((n_all, 4), torch.float64)
             eng.mapping(y, x, rd, r, (r, r), NPf, SMf, WBf)
-            NPg = torch.cat([gat[m]["NP"][g, :cuts[g + 1] - cuts[g]] for g in range(world)])
-            ok = ok and bool((NPg == NPf).all()) and bool((keep[m][0][:b - a] == SMf[a:b]).all())
-            ok = ok and bool((keep[m][1][:b - a].view(torch.int64) == WBf[a:b].view(torch.int64)).all())
-            mine_np = gat[m]["vnp"][rank, :b - a].view(torch.int64)
-            ok = ok and bool((mine_np == out[m]["vnp"][:b - a].view(torch.int64)).all())
+            for wi, row in enumerate(blocks):
+                for (mm, o_, cnt, i0) in row:
+                    if mm != m:
+                        continue
+                    ok = ok and bool((full_NP[o_:o_ + cnt] == NPf[i0:i0 + cnt]).all())
+                    if wi in my_w:
+                        ok = ok and bool((keep[0][o_ - p0:o_ - p0 + cnt] == SMf[i0:i0 + cnt]).all())
+                        ok = ok and bool((keep[1][o_ - p0:o_ - p0 + cnt].view(torch.int64) == WBf[i0:i0 + cnt].view(torch.int64)).all())
             del NPf, SMf, WBf
         okt = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         ok = bool(okt.item())
-        del keep
+        del keep, full_NP
         verified = {"NP_SM_WB_bit_exact_on_every_rank": ok, "points": nt_total, "missions": nm,
                     "against": "every rank mapping every whole mission alone (K1-K3)"}
         log("[verify] %d points, %d missions over %d GPUs vs one GPU: %s" % (nt_total, nm, world, ok))
@@ -1146,13 +1166,13 @@ def run_windowed(args, w):
                 "config": bench_config(args, w, r, rd, l2="flushed before every timed call (2 x 256 MiB write + 256 MiB read); every call "
                                        "gathers from a freshly generated record window (%.1f GB)" % (slab.numel() * 4 / 1e9)),
                 "details": {"track_points_total": nt_total, "track_points_this_gpu": nt_local, "missions": nm,
-                            "hours_total": hours, "window_hours": wh, "windows_per_gpu": len(windows),
+                            "hours_total": hours, "window_hours": wh, "windows_per_gpu": len(my_w),
                             "sharding": "every mission cut into N contiguous time segments, rank g maps segment g of every mission from "
                                         "the records of its own time slice (generated on the device per window, untimed); grid uploaded "
                                         "by rank 0 and replicated over NVLink; ONE collective per pass: all-gather of (ssh_np, ssh_bl, "
                                         "NP) of every mission, inside the timed region",
-                            "timed": "sum over the pass of every gzb_map_interp call (K1-K4 of one mission's points in one record "
-                                     "window; CUDA events on the launching stream) + the final all-gather; max over ranks",
+                            "timed": "sum over the pass of every gzb_map_interp_multi call (K1-K4 of ALL missions' points in one record "
+                                     "window, one chain per mission; CUDA events on the launching stream) + the final all-gather; max over ranks",
                             "ms_per_step_by_rank": [round(v, 3) for v in per_rank], "seed_reseeds": reseeds,
                             "whole_path_algorithmic_gbs_per_gpu": ach, "frac_of_hbm_peak": ach / peak},
                 "verified": verified, "clocks": clocks, "gpu_launches": int(launches),

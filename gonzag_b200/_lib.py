@@ -63,6 +63,8 @@ _SIGNATURES = {
     "gzb_lat_range": (C.c_int, [_P, _P, _P]),
     "gzb_map_interp": (C.c_int, [_P, _I64, _P, _P, _P, C.c_double, C.c_int, _I64, _I64, _I64, _P, _P, C.c_int, _I64, _I64,
                                  C.c_double, _P, _P, _P, _P, _P]),
+    "gzb_map_interp_multi": (C.c_int, [_P, C.c_int, _P, _P, _I64, _P, _P, _P, C.c_double, C.c_int, _I64, _P, _P, C.c_int, _I64,
+                                       _I64, C.c_double, _P, _P, _P, _P, _P]),
     "gzb_mesh_weights_interp": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I64, _P, _P, C.c_int, _I64, _I64, C.c_double,
                                           _P, _P, _P, _P]),
     "gzb_interp": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _P, _P, C.c_int, _I64, _I64, C.c_double, C.c_int,

@@ -242,3 +242,33 @@ extern "C" int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const 
     gzb_trace(ctx, s, "path end (main)");
     return GZB_OK;
 }
+
+// Several independent chains in one K1-K4 call (BASELINE config 5: the points of several altimeter missions falling into
+// one window of model records).  The track arrays are the concatenation of nseg sub-tracks; sub-track s starts at point
+// seg_start[s] (seg_start[0] == 0, strictly increasing) and its first point is seeded with seg_seed[2s], seg_seed[2s+1]
+// -- what BilinTrack.nrpt would do for each mission on its own (gonzag/bilin_mapping.py:570, 579-580).  Same results
+// as one gzb_map_interp per sub-track; the latency-bound chain part of K1 is paid once.
+extern "C" int gzb_map_interp_multi(gzb_ctx* ctx, int nseg, const int64_t* seg_start, const int64_t* seg_seed, int64_t nt,
+                                    const double* yt, const double* xt, const double* tt, double rd_found_km, int np_box_r,
+                                    int64_t nrec, const double* tmod, const void* slab, int dtype, int64_t k0, int64_t nk,
+                                    double rmissval, int64_t* np_out, int64_t* sm_out, double* wb_out, double* vnp_out,
+                                    double* vbl_out) {
+    if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_map_interp_multi: null ctx");
+    if (nseg < 1 || nseg > GZB_MAX_SEGS || !seg_start || !seg_seed)
+        return gzb_fail(ctx, GZB_ERR_ARG, "gzb_map_interp_multi: 1 <= nseg <= %d sub-tracks", GZB_MAX_SEGS);
+    if (seg_start[0] != 0) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_map_interp_multi: seg_start[0] must be 0");
+    for (int q = 1; q < nseg; ++q)
+        if (seg_start[q] <= seg_start[q - 1] || seg_start[q] >= nt)
+            return gzb_fail(ctx, GZB_ERR_ARG, "gzb_map_interp_multi: seg_start must increase strictly inside [0, nt)");
+    GzbSegs& S = ctx->segs_next;
+    S.n = nseg;
+    for (int q = 0; q < nseg; ++q) {
+        S.start[q] = seg_start[q];
+        S.sj[q] = seg_seed[2 * q];
+        S.si[q] = seg_seed[2 * q + 1];
+    }
+    const int rc = gzb_map_interp(ctx, nt, yt, xt, tt, rd_found_km, np_box_r, seg_seed[0], seg_seed[1], nrec, tmod, slab, dtype,
+                                  k0, nk, rmissval, np_out, sm_out, wb_out, vnp_out, vbl_out);
+    S.n = 0;          // whatever happened: the next call is an ordinary one
+    return rc;
+}

@@ -74,6 +74,17 @@ struct GzbGlobalNearest {
     const unsigned long long* ucount;     // ... and how many (device): they go through the repair kernel
 };
 
+// Several independent chains in one call (BASELINE config 5: the points of several missions that fall into one window of
+// model records): the track arrays are the concatenation of `n` sub-tracks, sub-track s starts at point start[s]
+// (start[0] == 0, increasing) and its first nearest-point search is seeded with (sj[s], si[s]) -- no point of one
+// sub-track ever seeds a point of another.  n == 1 is the ordinary call.
+#define GZB_MAX_SEGS 16
+struct GzbSegs {
+    int n;
+    long long start[GZB_MAX_SEGS];
+    long long sj[GZB_MAX_SEGS], si[GZB_MAX_SEGS];
+};
+
 struct GzbArena {
     char* base = nullptr;
     size_t cap = 0;
@@ -106,6 +117,7 @@ struct gzb_ctx {
     int ntrace = 0;
     cudaEvent_t trace_ev[48] = {};
     const char* trace_name[48] = {};
+    GzbSegs segs_next = {0, {}, {}, {}};   // gzb_map_interp_multi: the sub-tracks of the NEXT K1 call (n == 0: one chain, seeded by the call's arguments)
     int pdl = 1;                     // K1 chain kernels launched with programmatic dependent launch (griddepcontrol): the next kernel's launch overlaps the tail of the previous one
     int overlap = 1;                 // gzb_mapping: 1 run the chain replays beside K2+K3, 0 strictly in sequence
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -176,14 +188,14 @@ __device__ __forceinline__ void gzb_pdl_trigger() { asm volatile("griddepcontrol
 //                        asks L2 for 64 bytes instead of a 128-byte line (ld.global.nc.L2::64B)
 // GZB_EXP_HDG_STRIDE=8   heading table rows of 8 doubles (64 B, one fetch) instead of 6 (48 B)
 // GZB_EXP_BULK_BLOCKS=n  __launch_bounds__(128, n) on the fused K2+K3+K4 kernel (register cap 65536 / (128 n))
-// GZB_EXP_SKIP_DG=1      k_near_search does not evaluate the fp64 haversine of a point's nearest cell when that cell is
+// GZB_EXP_SKIP_DG=0      (ON in the product since round 2: K1 141 -> 133 us, step 227 -> 217 us on C3, parity tests green)
+//                        k_near_search does not evaluate the fp64 haversine of a point's nearest cell when that cell is
 //                        alone within the fp32 budget AND its fp32 chord is farther than twice that budget from the
 //                        chords of both acceptance thresholds (r0, 1.2^2 r0): dG then holds 12720 asin(chord / 2),
 //                        which is on the same side of every threshold as the exact value -- the only thing dG is
-//                        used for (accept_edge, twin_of, point_sum).  Written after the round's last GPU visit:
-//                        never run; scripts/gpu_round2_first.sh measures it and runs the parity tests on it.
+//                        used for (accept_edge, twin_of, point_sum).  0 = always the exact value.
 #ifndef GZB_EXP_SKIP_DG
-#define GZB_EXP_SKIP_DG 0
+#define GZB_EXP_SKIP_DG 1
 #endif
 #ifndef GZB_EXP_L64
 #define GZB_EXP_L64 0

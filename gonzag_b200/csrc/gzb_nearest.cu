@@ -82,11 +82,20 @@ struct NearParams {
     double chord_r0;   // chord length of r0 (with margin)
     int r;             // np_box_r
     int edge;          // apply the edge exclusion of BilinTrack.nrpt
-    long long seed_j, seed_i;
+    GzbSegs segs;      // sub-tracks of this call and their seeds (n >= 1, start[0] == 0)
     const double* corner;   // bounding sphere (cx,cy,cz,rho) of the box of predecessor (-1,-1)
     const unsigned char* rowsafe;   // per grid row: 1 = the only exact copies of its first k_ew_per cells are
                                     // their East-West twins (null: no twin shortcut)
 };
+
+// sub-track of point t: index of the last start <= t; `end` = last point of that sub-track
+__device__ __forceinline__ int seg_of(const GzbSegs& S, const long long t, const long long nt, long long& end) {
+    int s = 0;
+    for (int q = 1; q < S.n; ++q)
+        if (S.start[q] <= t) s = q;
+    end = (s + 1 < S.n ? S.start[s + 1] : nt) - 1;
+    return s;
+}
 
 // fp32 error budget (see DESIGN.md "K1 numerics"): a stored coordinate is within 6e-8 of the
 // fp64 one, so a computed chord D differs from the true chord c by at most 3e-7*D + 3e-7.
@@ -974,50 +983,88 @@ __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned*
 // predecessor T(t-1)), composed map of the block, state entering the block by a decoupled look-back
 // over the maps the earlier blocks published (a map that sends both states to the same one -- any
 // block away from the seam -- ends the look-back, so its depth is almost always one), then the
-// speculative chain, the break flags and the per-block break counts.  Blocks take their index from a
-// ticket, so a block only ever waits for blocks that already started.
+// speculative chain and the ORDERED list of breaks: the block's offset in that list comes from a second
+// decoupled look-back, over the break counts (status word per block: aggregate, then inclusive prefix).
+// A thread owns CH_PPT consecutive points (one composed map per thread goes through the block scan; a
+// 10-day track is ~600 blocks: one wave).  Blocks take their index from a ticket, so a block only ever
+// waits for blocks that already started.
+#define CH_PPT 4
+#define CH_PTS (FLAGS_BLOCK * CH_PPT)
+#define CST_AGG 0x4000000000000000ull
+#define CST_INC 0x8000000000000000ull
 __global__ void __launch_bounds__(FLAGS_BLOCK)
 k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
         const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
-        long long* __restrict__ NP, unsigned char* __restrict__ brk, int* __restrict__ counts,
-        volatile unsigned* agg, unsigned* __restrict__ ticket, long long* __restrict__ chg,
-        unsigned long long* __restrict__ nchg) {
+        long long* __restrict__ NP, long long* __restrict__ breaks, volatile unsigned long long* cstat,
+        volatile unsigned* agg, unsigned* __restrict__ ticket, long long* __restrict__ nbrk_out,
+        long long* __restrict__ chg, unsigned long long* __restrict__ nchg) {
     __shared__ unsigned sh[FLAGS_BLOCK / 32];
     __shared__ unsigned last[FLAGS_BLOCK / 32];
+    __shared__ int wcnt[FLAGS_BLOCK / 32];
     __shared__ unsigned s_bid, s_entry;
+    __shared__ long long s_base;
+    __shared__ int sE[FLAGS_BLOCK][2], sT[FLAGS_BLOCK][3];      // E / T of the LAST point of every thread
     gzb_pdl_wait();
     if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned bid = s_bid;
-    const long long t = (long long)bid * blockDim.x + threadIdx.x;
-    unsigned c = 0, mine = FN_ID;
-    __shared__ int sE[FLAGS_BLOCK][2], sT[FLAGS_BLOCK][3];
-    PointSum q;
-    q.gj = q.gi = q.ej = q.ei = q.tj = q.ti = -1;
-    q.tv = 0;
-    if (t < nt) point_sum(g, p, G[t], dG[t], q);
-    sE[threadIdx.x][0] = q.ej; sE[threadIdx.x][1] = q.ei;
-    sT[threadIdx.x][0] = q.tj; sT[threadIdx.x][1] = q.ti; sT[threadIdx.x][2] = q.tv;
+    const long long t0 = (long long)bid * CH_PTS + (long long)threadIdx.x * CH_PPT;
+    PointSum q[CH_PPT];
+#pragma unroll
+    for (int k = 0; k < CH_PPT; ++k) {
+        q[k].gj = q[k].gi = q[k].ej = q[k].ei = q[k].tj = q[k].ti = -1;
+        q[k].tv = 0;
+        if (t0 + k < nt) point_sum(g, p, G[t0 + k], dG[t0 + k], q[k]);
+    }
+    sE[threadIdx.x][0] = q[CH_PPT - 1].ej; sE[threadIdx.x][1] = q[CH_PPT - 1].ei;
+    sT[threadIdx.x][0] = q[CH_PPT - 1].tj; sT[threadIdx.x][1] = q[CH_PPT - 1].ti; sT[threadIdx.x][2] = q[CH_PPT - 1].tv;
     __syncthreads();
-    if (t < nt) {
-        int o0, o1;
-        if (t == 0) {
-            o0 = o1 = step_code(g, p, (int)p.seed_j, (int)p.seed_i, q, yt, xt, t);
-        } else {
-            int pe0, pe1, pt0, pt1, ptv;
-            if (threadIdx.x > 0) {
+    unsigned c[CH_PPT];
+    unsigned mine = FN_ID;
+    {
+        int pe0 = 0, pe1 = 0, pt0 = 0, pt1 = 0, ptv = 0;
+        // which of my points start a sub-track (point 0 of the call always does)
+        unsigned smask = 0;
+        int sseg[CH_PPT];
+#pragma unroll
+        for (int k = 0; k < CH_PPT; ++k) sseg[k] = 0;
+        for (int q = 0; q < p.segs.n; ++q) {
+            const long long d = p.segs.start[q] - t0;
+            if (d >= 0 && d < CH_PPT) {
+                smask |= 1u << (int)d;
+#pragma unroll
+                for (int k = 0; k < CH_PPT; ++k)
+                    if (k == (int)d) sseg[k] = q;
+            }
+        }
+        if (t0 < nt) {
+            if (smask & 1u) {
+            } else if (threadIdx.x > 0) {
                 pe0 = sE[threadIdx.x - 1][0]; pe1 = sE[threadIdx.x - 1][1];
                 pt0 = sT[threadIdx.x - 1][0]; pt1 = sT[threadIdx.x - 1][1]; ptv = sT[threadIdx.x - 1][2];
             } else {                 // the predecessor belongs to the previous block
                 PointSum pq;
-                point_sum(g, p, G[t - 1], dG[t - 1], pq);
+                point_sum(g, p, G[t0 - 1], dG[t0 - 1], pq);
                 pe0 = pq.ej; pe1 = pq.ei; pt0 = pq.tj; pt1 = pq.ti; ptv = pq.tv;
             }
-            o0 = step_code(g, p, pe0, pe1, q, yt, xt, t);
-            o1 = ptv ? step_code(g, p, pt0, pt1, q, yt, xt, t) : o0;     // no twin state at t-1: bit unused
         }
-        c = (unsigned)(o0 | (o1 << 2));
-        mine = (unsigned)((o0 == 1) ? 1 : 0) | ((unsigned)((o1 == 1) ? 1 : 0) << 1);     // 2 propagates as 0
+#pragma unroll
+        for (int k = 0; k < CH_PPT; ++k) {
+            c[k] = 0;
+            if (t0 + k < nt) {
+                int o0, o1;
+                if (smask & (1u << k)) {       // first point of a sub-track: the predecessor is its seed
+                    o0 = o1 = step_code(g, p, (int)p.segs.sj[sseg[k]], (int)p.segs.si[sseg[k]], q[k], yt, xt, t0 + k);
+                } else {
+                    o0 = step_code(g, p, pe0, pe1, q[k], yt, xt, t0 + k);
+                    o1 = ptv ? step_code(g, p, pt0, pt1, q[k], yt, xt, t0 + k) : o0;     // no twin state at t-1: bit unused
+                }
+                c[k] = (unsigned)(o0 | (o1 << 2));
+                const unsigned mk = (unsigned)((o0 == 1) ? 1 : 0) | ((unsigned)((o1 == 1) ? 1 : 0) << 1);     // 2 propagates as 0
+                mine = (k == 0) ? mk : fn_then(mine, mk);
+            }
+            pe0 = q[k].ej; pe1 = q[k].ei; pt0 = q[k].tj; pt1 = q[k].ti; ptv = q[k].tv;
+        }
     }
     unsigned total;
     const unsigned incl = block_scan_fn(mine, sh, total);
@@ -1039,26 +1086,70 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     }
     __syncthreads();
     const unsigned prev = __shfl_up_sync(0xffffffffu, incl, 1);
-    unsigned before;          // map from the block's entry state to the state entering this point
+    unsigned before;          // map from the block's entry state to the state entering this thread's first point
     if (threadIdx.x == 0) before = FN_ID;
     else if ((threadIdx.x & 31) == 0) before = last[(threadIdx.x >> 5) - 1];
     else before = prev;
-    const unsigned sin = (before >> s_entry) & 1u;
-    int isb = 0;
-    if (t < nt) {
-        const unsigned out = (c >> (2 * sin)) & 3u;
-        long long rj = q.ej, ri = q.ei;
-        if (out == 1u) {
-            rj = q.tj;
-            ri = q.ti;
-            if (chg) chg[atomicAdd(nchg, 1ull)] = t;      // differs from E(t): K2-K4 of this point are redone (gzb_mapping overlap)
+    unsigned st = (before >> s_entry) & 1u;
+    unsigned bmask = 0;
+#pragma unroll
+    for (int k = 0; k < CH_PPT; ++k) {
+        if (t0 + k < nt) {
+            const unsigned out = (c[k] >> (2 * st)) & 3u;
+            long long rj = q[k].ej, ri = q[k].ei;
+            if (out == 1u) {
+                rj = q[k].tj;
+                ri = q[k].ti;
+                if (chg) chg[atomicAdd(nchg, 1ull)] = t0 + k;      // differs from E(t): K2-K4 of this point are redone (gzb_mapping overlap)
+            }
+            reinterpret_cast<longlong2*>(NP)[t0 + k] = make_longlong2(rj, ri);
+            if (out == 2u) bmask |= 1u << k;
+            st = out == 1u ? 1u : 0u;
         }
-        reinterpret_cast<longlong2*>(NP)[t] = make_longlong2(rj, ri);
-        isb = out == 2u ? 1 : 0;
-        brk[t] = (unsigned char)isb;
     }
-    const int n = __syncthreads_count(isb);
-    if (threadIdx.x == 0) counts[bid] = n;
+    // ---- ordered break list: exclusive offsets inside the block, block offset by look-back over the counts
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mycnt = __popc(bmask);
+    int wincl = mycnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += u;
+    }
+    if (lane == 31) wcnt[warp] = wincl;
+    __syncthreads();
+    int wbase = 0, btotal = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < FLAGS_BLOCK / 32; ++w2) {
+        if (w2 < warp) wbase += wcnt[w2];
+        btotal += wcnt[w2];
+    }
+    if (threadIdx.x == 0) {
+        long long excl = 0;
+        if (bid > 0) {
+            cstat[bid] = CST_AGG | (unsigned long long)btotal;
+            __threadfence();
+            long long k = (long long)bid - 1;
+            for (;;) {
+                unsigned long long v;
+                while (((v = cstat[k]) & (CST_AGG | CST_INC)) == 0ull) __nanosleep(40);
+                excl += (long long)(v & 0x3fffffffffffffffull);
+                if (v & CST_INC) break;
+                --k;      // block 0 always publishes an inclusive prefix: k never goes below 0
+            }
+        }
+        cstat[bid] = CST_INC | (unsigned long long)(excl + btotal);
+        __threadfence();
+        s_base = excl;
+        if ((long long)(bid + 1) * CH_PTS >= nt) nbrk_out[0] = excl + btotal;      // the block that holds the last point
+    }
+    __syncthreads();
+    if (bmask) {
+        long long pos = s_base + wbase + (wincl - mycnt);
+#pragma unroll
+        for (int k = 0; k < CH_PPT; ++k)
+            if (bmask & (1u << k)) breaks[pos++] = t0 + k;
+    }
 }
 
 // per row: 1 = no cell strictly between a leading overlap cell and its East-West twin has that cell's
@@ -1090,251 +1181,191 @@ k_rowsafe(const GzbGrid g, unsigned char* __restrict__ rowsafe) {
     if (threadIdx.x == 0) rowsafe[j] = (g.kew > 8 || bad) ? 0 : 1;
 }
 
-// ordered compaction of the break indices.  A block finds its own offset by adding up the break counts
-// of the blocks before it (a few thousand ints, L2-resident): no separate scan kernel on the critical path.
-// The last block leaves the number of breaks in *total.
-__global__ void __launch_bounds__(FLAGS_BLOCK)
-k_compact(const unsigned char* __restrict__ brk, const int* __restrict__ counts, const long long nt,
-          long long* __restrict__ breaks, long long* __restrict__ total) {
-    __shared__ int wcnt[32];
-    __shared__ long long wsum[FLAGS_BLOCK / 32];
-    __shared__ long long s_off;
-    gzb_pdl_wait();
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    long long v = 0;
-    for (long long k = threadIdx.x; k < (long long)blockIdx.x; k += blockDim.x) v += counts[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) wsum[warp] = v;
-    const int b = (t < nt) ? brk[t] : 0;
-    const unsigned m = __ballot_sync(0xffffffffu, b);
-    if (lane == 0) wcnt[warp] = __popc(m);
-    __syncthreads();
-    if (warp == 0) {
-        int ww = lane < (int)(blockDim.x >> 5) ? wcnt[lane] : 0;
-        int s = ww;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += u;
-        }
-        wcnt[lane] = s - ww;
-        if (lane == 0) {
-            long long off = 0;
-            for (int q = 0; q < (int)(blockDim.x >> 5); ++q) off += wsum[q];
-            s_off = off;
-            if (blockIdx.x == gridDim.x - 1) *total = off + counts[blockIdx.x];
-        }
-    }
-    __syncthreads();
-    if (b) breaks[s_off + wcnt[warp] + __popc(m & ((1u << lane) - 1u))] = t;
-}
-
-// K1c, step 2/4: chain replay, one warp per break: the reference's recurrence R(t) = F_t(R(t-1))
-// from the break until the chain rejoins the speculative one.  The points are taken 32 at a
-// time: lane l prepares point t0+l (unit vector, cos(lat), G, E) in parallel, then the steps run
-// in order with those values shuffled in, so that a step costs one box_search and nothing else.
-// WRITE=false records where the replay rejoins the speculative chain and logs every replayed
-// value tagged with the replay's id (one 64-bit word per point: id in the high 27 bits, flat
-// index + 1 in the low 36); WRITE=true (valid replays only) copies the logged values, 32 per
-// step, and replays again only if another (discarded) replay overwrote part of its log.
+// K1c, step 2: chain replays, validation and write-back in ONE kernel (k_tail).
+//
+// replay<WRITE>: one warp replays the reference's recurrence R(t) = F_t(R(t-1)) from break k until the
+// chain rejoins the speculative one.  The points are taken 32 at a time: lane l prepares point t0+l (unit
+// vector, cos(lat), G, E) in parallel, then the steps run in order with those values shuffled in, so that a
+// step costs one box_search and nothing else.  WRITE=false records where the replay rejoins the speculative
+// chain and logs every replayed value tagged with the replay's id (one 64-bit word per point: id in the high
+// 27 bits, flat index + 1 in the low 36); WRITE=true replays again up to the recorded stop and writes NP
+// (only needed when another, discarded, replay overwrote part of this one's log).
 #define WLOG_TAG(k) ((unsigned long long)(((k) + 1) & 0x7ffffffLL) << 36)
 
-// warps (= replays) per block of k_walk; one-warp blocks were measured slower, alone and beside K2+K3
-#define WALK_WARPS 2
 template <bool WRITE>
-__global__ void __launch_bounds__(32 * WALK_WARPS)
-k_walk(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
-       const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
-       const long long* __restrict__ breaks, const long long* __restrict__ nbrk_p,
-       long long* __restrict__ stop, long long* __restrict__ first, const unsigned char* __restrict__ valid,
-       unsigned long long* __restrict__ wlog, long long* __restrict__ NP, unsigned long long* __restrict__ steps,
-       long long* __restrict__ chg, unsigned long long* __restrict__ nchg) {
-    __shared__ WarpSm ws[WALK_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSm& w = ws[warp];
-    gzb_pdl_wait();
-    const long long nb = *nbrk_p;
-    const long long nwarps = (long long)gridDim.x * WALK_WARPS;
-    for (long long k = (long long)blockIdx.x * WALK_WARPS + warp; k < nb; k += nwarps) {
-        const long long b = breaks[k];
-        long long tend = nt - 1;          // last point this replay may touch
-        if (WRITE) {
-            if (!valid[k]) continue;
-            const long long e = stop[k];
-            if (e == b) {
+__device__ __forceinline__ void replay(const GzbGrid& g, const NearParams& p, WarpSm& w, const int lane, const long long nt,
+                                       const double* __restrict__ yt, const double* __restrict__ xt,
+                                       const long long* __restrict__ G, const double* __restrict__ dG, const long long k,
+                                       const long long b, long long tend, long long* __restrict__ stop,
+                                       long long* __restrict__ first, unsigned long long* __restrict__ wlog,
+                                       long long* __restrict__ NP, unsigned long long* __restrict__ steps,
+                                       long long* __restrict__ chg, unsigned long long* __restrict__ nchg) {
+    long long pj, pi;
+    long long seg_end;
+    const int sg = seg_of(p.segs, b, nt, seg_end);
+    if (!WRITE) tend = seg_end;          // a replay never runs into the next sub-track
+    if (b == p.segs.start[sg]) {
+        pj = p.segs.sj[sg];
+        pi = p.segs.si[sg];
+    } else {                 // the speculative chain at b-1 (k_chain; an earlier valid replay ending there rejoined it)
+        pj = __ldcg(NP + 2 * (b - 1));
+        pi = __ldcg(NP + 2 * (b - 1) + 1);
+    }
+    unsigned long long n = 0;
+    bool done = false;
+    // the first round prepares 4 points only: most replays rejoin the speculative chain after one or two steps
+    int width = 4;
+    for (long long t0 = b; !done; t0 += width, width = 32) {
+        const int nq = (int)((tend - t0 + 1 < width) ? (tend - t0 + 1) : width);
+        Owner me;
+        float mpx = 0.f, mpy = 0.f, mpz = 0.f;
+        me.plat = me.plon = me.cpl = 0.0;
+        long long gf = GZB_NOFLAT, ej = -1, ei = -1, sj = -1, si = -1, tj = -1, ti = -1;
+        int tv = 0;
+        if (lane < nq) {
+            owner_point(yt[t0 + lane], xt[t0 + lane], me, mpx, mpy, mpz);
+            gf = G[t0 + lane];
+            const double gd = dG[t0 + lane];
+            accept_edge(g, gf, gd, p.thr2, ej, ei, p.edge);
+            long long tw = 0;
+            if (twin_of(g, p, gf, gd, tw)) {          // T(t): see k_chain
+                tv = 1;
+                accept_edge(g, tw, gd, INFINITY, tj, ti, p.edge);
+            }
+            if (!WRITE) {                             // the speculative chain, to detect where the replay rejoins it
+                sj = __ldcg(NP + 2 * (t0 + lane));
+                si = __ldcg(NP + 2 * (t0 + lane) + 1);
+            }
+        }
+        __syncwarp();
+        w.bd[lane] = ~0ull;
+        w.bf[lane] = GZB_NOFLAT;
+        w.pb2[lane] = INFINITY;
+        __syncwarp();
+        for (int q = 0; q < nq; ++q) {
+            const long long t = t0 + q;
+            const long long qej = __shfl_sync(0xffffffffu, ej, q), qei = __shfl_sync(0xffffffffu, ei, q);
+            const long long qgf = __shfl_sync(0xffffffffu, gf, q);
+            long long rj = qej, ri = qei;
+            if (pj != 0 && pi != 0) {     // Python truthiness of (j_prv and i_prv)
+                long long j0, j1, i0, i1;
+                if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
+                    // the global nearest point inside the box: the box pass finds that very point,
+                    // so R(t) = E(t) whatever its distance (DESIGN.md, K1 key fact) -- no search
+                    bool inside = false;
+                    if (qgf != GZB_NOFLAT) {
+                        long long gj, gi;
+                        gzb_split(g, qgf, gj, gi);
+                        inside = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
+                    }
+                    bool twin_in = false;
+                    if (!inside && __shfl_sync(0xffffffffu, tv, q)) {
+                        long long gj, gi;
+                        gzb_split(g, qgf, gj, gi);
+                        gi += g.Ni - g.kew;
+                        twin_in = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
+                    }
+                    if (twin_in) {       // the box pass finds the twin of G(t), at the global minimum distance (< r0)
+                        rj = __shfl_sync(0xffffffffu, tj, q);
+                        ri = __shfl_sync(0xffffffffu, ti, q);
+                    } else if (!inside) {
+                        Srch s;
+                        srch_init(s, __shfl_sync(0xffffffffu, mpx, q), __shfl_sync(0xffffffffu, mpy, q),
+                                  __shfl_sync(0xffffffffu, mpz, q));
+                        set_bound(s, p.prox_r0);
+                        if (lane == 0) w.pb2[q] = s.B2;
+                        __syncwarp();
+                        int qn = 0;
+                        box_search(g, w, lane, s, q, j0, j1, i0, i1, qn, me);
+                        flush_queue(g, w, lane, qn, me);
+                        const long long f = w.bf[q];
+                        const double d = __longlong_as_double((long long)w.bd[q]);
+                        if (f != GZB_NOFLAT && d < p.r0) accept_edge(g, f, d, INFINITY, rj, ri, p.edge);
+                    }
+                }
+            }
+            ++n;
+            if (WRITE) {
                 if (lane == 0) {
-                    NP[2 * b] = first[2 * k];
-                    NP[2 * b + 1] = first[2 * k + 1];
-                    if (chg) chg[atomicAdd(nchg, 1ull)] = b;
+                    NP[2 * t] = rj;
+                    NP[2 * t + 1] = ri;
+                    if (chg) chg[atomicAdd(nchg, 1ull)] = t;
                 }
-                continue;
-            }
-            // copy from the log
-            bool clobbered = false;
-            for (long long t0 = b; t0 <= e; t0 += 32) {
-                const long long t = t0 + lane;
-                bool bad = false;
-                if (t <= e) {
-                    const unsigned long long v = wlog[t];
-                    if ((v >> 36) != (WLOG_TAG(k) >> 36)) {
-                        bad = true;
-                    } else {
-                        const long long f = (long long)(v & 0xfffffffffULL) - 1;
-                        const long long j = f < 0 ? -1 : f / g.Ni;
-                        NP[2 * t] = j;
-                        NP[2 * t + 1] = f < 0 ? -1 : f - j * g.Ni;
+                if (t >= tend) { done = true; break; }
+            } else {
+                if (lane == 0) {
+                    wlog[t] = WLOG_TAG(k) | (unsigned long long)(rj < 0 ? 0 : rj * g.Ni + ri + 1);
+                    if (t == b) {
+                        first[2 * k] = rj;
+                        first[2 * k + 1] = ri;
                     }
                 }
-                if (chg) {      // points whose mesh / weights must be recomputed (gzb_mapping overlap)
-                    const bool wrote = (t <= e) && !bad;
-                    const unsigned wm = __ballot_sync(0xffffffffu, wrote);
-                    if (wm) {
-                        unsigned long long base = 0;
-                        if (lane == __ffs(wm) - 1) base = atomicAdd(nchg, (unsigned long long)__popc(wm));
-                        base = __shfl_sync(0xffffffffu, base, __ffs(wm) - 1);
-                        if (wrote) chg[base + __popc(wm & ((1u << lane) - 1u))] = t;
-                    }
-                }
-                if (__any_sync(0xffffffffu, bad)) clobbered = true;
-            }
-            if (!clobbered) continue;
-            tend = e;
-        }
-        long long pj, pi;
-        if (b == 0) {
-            pj = p.seed_j;
-            pi = p.seed_i;
-        } else {                 // the speculative chain at b-1 (k_chain; an earlier valid replay ending there rejoined it)
-            pj = NP[2 * (b - 1)];
-            pi = NP[2 * (b - 1) + 1];
-        }
-        unsigned long long n = 0;
-        bool done = false;
-        for (long long t0 = b; !done; t0 += 32) {
-            const int nq = (int)((tend - t0 + 1 < 32) ? (tend - t0 + 1) : 32);
-            Owner me;
-            float mpx = 0.f, mpy = 0.f, mpz = 0.f;
-            me.plat = me.plon = me.cpl = 0.0;
-            long long gf = GZB_NOFLAT, ej = -1, ei = -1, sj = -1, si = -1, tj = -1, ti = -1;
-            int tv = 0;
-            if (lane < nq) {
-                owner_point(yt[t0 + lane], xt[t0 + lane], me, mpx, mpy, mpz);
-                gf = G[t0 + lane];
-                const double gd = dG[t0 + lane];
-                accept_edge(g, gf, gd, p.thr2, ej, ei, p.edge);
-                long long tw = 0;
-                if (twin_of(g, p, gf, gd, tw)) {          // T(t): see k_chain
-                    tv = 1;
-                    accept_edge(g, tw, gd, INFINITY, tj, ti, p.edge);
-                }
-                if (!WRITE) {                             // the speculative chain, to detect where the replay rejoins it
-                    sj = NP[2 * (t0 + lane)];
-                    si = NP[2 * (t0 + lane) + 1];
+                if ((rj == __shfl_sync(0xffffffffu, sj, q) && ri == __shfl_sync(0xffffffffu, si, q)) || t >= tend) {
+                    if (lane == 0) stop[k] = t;
+                    done = true;
+                    break;
                 }
             }
-            __syncwarp();
-            w.bd[lane] = ~0ull;
-            w.bf[lane] = GZB_NOFLAT;
-            w.pb2[lane] = INFINITY;
-            __syncwarp();
-            for (int q = 0; q < nq; ++q) {
-                const long long t = t0 + q;
-                const long long qej = __shfl_sync(0xffffffffu, ej, q), qei = __shfl_sync(0xffffffffu, ei, q);
-                const long long qgf = __shfl_sync(0xffffffffu, gf, q);
-                long long rj = qej, ri = qei;
-                if (pj != 0 && pi != 0) {     // Python truthiness of (j_prv and i_prv)
-                    long long j0, j1, i0, i1;
-                    if (clamp_box(g, pj, pi, p.r, j0, j1, i0, i1)) {
-                        // the global nearest point inside the box: the box pass finds that very point,
-                        // so R(t) = E(t) whatever its distance (DESIGN.md, K1 key fact) -- no search
-                        bool inside = false;
-                        if (qgf != GZB_NOFLAT) {
-                            long long gj, gi;
-                            gzb_split(g, qgf, gj, gi);
-                            inside = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
-                        }
-                        bool twin_in = false;
-                        if (!inside && __shfl_sync(0xffffffffu, tv, q)) {
-                            long long gj, gi;
-                            gzb_split(g, qgf, gj, gi);
-                            gi += g.Ni - g.kew;
-                            twin_in = gj >= j0 && gj < j1 && gi >= i0 && gi < i1;
-                        }
-                        if (twin_in) {       // the box pass finds the twin of G(t), at the global minimum distance (< r0)
-                            rj = __shfl_sync(0xffffffffu, tj, q);
-                            ri = __shfl_sync(0xffffffffu, ti, q);
-                        } else if (!inside) {
-                            Srch s;
-                            srch_init(s, __shfl_sync(0xffffffffu, mpx, q), __shfl_sync(0xffffffffu, mpy, q),
-                                      __shfl_sync(0xffffffffu, mpz, q));
-                            set_bound(s, p.prox_r0);
-                            if (lane == 0) w.pb2[q] = s.B2;
-                            __syncwarp();
-                            int qn = 0;
-                            box_search(g, w, lane, s, q, j0, j1, i0, i1, qn, me);
-                            flush_queue(g, w, lane, qn, me);
-                            const long long f = w.bf[q];
-                            const double d = __longlong_as_double((long long)w.bd[q]);
-                            if (f != GZB_NOFLAT && d < p.r0) accept_edge(g, f, d, INFINITY, rj, ri, p.edge);
-                        }
-                    }
-                }
-                ++n;
-                if (WRITE) {
-                    if (lane == 0) {
-                        NP[2 * t] = rj;
-                        NP[2 * t + 1] = ri;
-                        if (chg) chg[atomicAdd(nchg, 1ull)] = t;
-                    }
-                    if (t >= tend) { done = true; break; }
-                } else {
-                    if (lane == 0) {
-                        wlog[t] = WLOG_TAG(k) | (unsigned long long)(rj < 0 ? 0 : rj * g.Ni + ri + 1);
-                        if (t == b) {
-                            first[2 * k] = rj;
-                            first[2 * k + 1] = ri;
-                        }
-                    }
-                    if ((rj == __shfl_sync(0xffffffffu, sj, q) && ri == __shfl_sync(0xffffffffu, si, q)) || t + 1 >= nt) {
-                        if (lane == 0) stop[k] = t;
-                        done = true;
-                        break;
-                    }
-                }
-                pj = rj;
-                pi = ri;
-            }
-            __syncwarp();
+            pj = rj;
+            pi = ri;
         }
-        if (!WRITE && lane == 0) {
-            atomicAdd(steps, n);
-            atomicMax(steps + 5, n);      // longest replay
-        }
+        __syncwarp();
+    }
+    if (!WRITE && lane == 0) {
+        atomicAdd(steps, n);
+        atomicMax(steps + 5, n);      // longest replay
     }
 }
 
-// K1c, step 3: a replay is valid iff it does not start inside an earlier valid replay
-// (whose deviating values would have been its true predecessor).  The block stages the break
-// list in shared memory, 2048 entries at a time; warp 0 then runs the (inherently ordered)
-// scan, 32 breaks per step on the common path where no replay reaches the next break.
-#define VALID_CHUNK 2048
-__global__ void __launch_bounds__(256)
-k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop,
-        const long long* __restrict__ nbrk_p, unsigned char* __restrict__ valid, long long* __restrict__ stats_out) {
+// k_tail: (1) every warp of the grid replays its breaks (WRITE=false); (2) the block that finishes LAST (a counter
+// behind a __threadfence) decides which replays are valid -- a replay is valid iff it does not start inside an earlier
+// valid replay, whose deviating values would have been its true predecessor: an inherently ordered scan over the break
+// list, 32 breaks per step on the common path where no replay reaches the next break -- and (3) writes the valid
+// replays back: a THREAD per break copies its (short) log into NP and appends the changed points to `chg`; replays
+// that are long, or whose log another (discarded) replay overwrote, are redone warp per break (rare).
+// One launch instead of compaction + replay + validation + write-back: after k_chain the chain part of K1 is pure
+// dependent latency, and every launch boundary in it costs as much as the work between two of them.
+#define TAIL_WARPS 4
+#define TAIL_THREADS (32 * TAIL_WARPS)
+#define VALID_CHUNK 1024
+#define TAIL_SHORT 8
+__global__ void __launch_bounds__(TAIL_THREADS)
+k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
+       const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
+       const long long* __restrict__ breaks, long long* __restrict__ scal,
+       long long* __restrict__ stop, long long* __restrict__ first, unsigned char* __restrict__ valid,
+       unsigned long long* __restrict__ wlog, long long* __restrict__ NP,
+       long long* __restrict__ chg, unsigned long long* __restrict__ nchg, unsigned* __restrict__ done_ctr,
+       long long* __restrict__ stats_out) {
+    __shared__ WarpSm ws[TAIL_WARPS];
     __shared__ long long sb[VALID_CHUNK + 1];
     __shared__ long long ss[VALID_CHUNK];
+    __shared__ int s_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     gzb_pdl_wait();
-    gzb_pdl_trigger();
-    const int lane = threadIdx.x & 31;
-    const long long nb = *nbrk_p;
+    const long long nb = scal[0];
+    unsigned long long* steps = (unsigned long long*)(scal + 1);
+    // ---- (1) replays
+    {
+        const long long nwarps = (long long)gridDim.x * TAIL_WARPS;
+        for (long long k = (long long)blockIdx.x * TAIL_WARPS + warp; k < nb; k += nwarps)
+            replay<false>(g, p, ws[warp], lane, nt, yt, xt, G, dG, k, breaks[k], nt - 1, stop, first, wlog, NP, steps, nullptr, nullptr);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(done_ctr, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- (2) validation (warp 0; the block stages the break list in shared memory, VALID_CHUNK entries at a time)
     long long cur_end = -1;
     for (long long c0 = 0; c0 < nb; c0 += VALID_CHUNK) {
         const int cn = (int)((nb - c0 < VALID_CHUNK) ? (nb - c0) : VALID_CHUNK);
         for (int e = threadIdx.x; e <= cn; e += blockDim.x) {
             sb[e] = (c0 + e < nb) ? breaks[c0 + e] : GZB_NOFLAT;
-            if (e < cn) ss[e] = stop[c0 + e];
+            if (e < cn) ss[e] = __ldcg(stop + c0 + e);
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -1348,8 +1379,8 @@ k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop
                 const long long b0 = __shfl_sync(0xffffffffu, b, 0);
                 if (__all_sync(0xffffffffu, simple) && b0 > cur_end) {
                     if (in) valid[c0 + e] = 1;
-                    const int last = ((cn - base < 32) ? (cn - base) : 32) - 1;
-                    cur_end = __shfl_sync(0xffffffffu, s, last);
+                    const int lastl = ((cn - base < 32) ? (cn - base) : 32) - 1;
+                    cur_end = __shfl_sync(0xffffffffu, s, lastl);
                 } else {
                     for (int l = 0; l < 32; ++l) {
                         const long long kb = __shfl_sync(0xffffffffu, b, l);
@@ -1365,10 +1396,52 @@ k_valid(const long long* __restrict__ breaks, const long long* __restrict__ stop
         }
         __syncthreads();
     }
+    // ---- (3) write-back of the valid replays, thread per break (short, intact logs); 2 = left to the warps below
+    for (long long k = threadIdx.x; k < nb; k += blockDim.x) {
+        if (!valid[k]) continue;
+        const long long b = breaks[k], e = __ldcg(stop + k);
+        if (e == b) {
+            NP[2 * b] = __ldcg(first + 2 * k);
+            NP[2 * b + 1] = __ldcg(first + 2 * k + 1);
+            if (chg) chg[atomicAdd(nchg, 1ull)] = b;
+            continue;
+        }
+        bool ok = (e - b) < TAIL_SHORT;
+        unsigned long long v[TAIL_SHORT];
+        if (ok) {
+#pragma unroll
+            for (int q = 0; q < TAIL_SHORT; ++q) {
+                v[q] = 0;
+                if (b + q <= e) {
+                    v[q] = __ldcg(wlog + b + q);
+                    if ((v[q] >> 36) != (WLOG_TAG(k) >> 36)) ok = false;
+                }
+            }
+        }
+        if (!ok) { valid[k] = 2; continue; }
+        const int cnt = (int)(e - b + 1);
+        const unsigned long long base = chg ? atomicAdd(nchg, (unsigned long long)cnt) : 0ull;
+#pragma unroll
+        for (int q = 0; q < TAIL_SHORT; ++q) {
+            if (b + q <= e) {
+                const long long f = (long long)(v[q] & 0xfffffffffULL) - 1;
+                long long j = -1, i = -1;
+                if (f >= 0) gzb_split(g, f, j, i);
+                NP[2 * (b + q)] = j;
+                NP[2 * (b + q) + 1] = i;
+                if (chg) chg[base + q] = b + q;
+            }
+        }
+    }
+    __syncthreads();
+    for (long long k = warp; k < nb; k += TAIL_WARPS) {
+        if (valid[k] != 2) continue;
+        replay<true>(g, p, ws[warp], lane, nt, yt, xt, G, dG, k, breaks[k], __ldcg(stop + k), stop, first, wlog, NP, steps, chg, nchg);
+    }
     if (threadIdx.x == 0) {      // (breaks, replay steps, ...) of this call, for gzb_get_stats
-        stats_out[0] = nbrk_p[0];
-        stats_out[1] = nbrk_p[1];
-        for (int q = 2; q < 7; ++q) stats_out[q] = nbrk_p[q];   // k_near_search: unresolved (total, no seed, not converged, not proven); longest replay
+        stats_out[0] = scal[0];
+        stats_out[1] = (long long)__ldcg(steps);
+        for (int q = 2; q < 7; ++q) stats_out[q] = __ldcg(scal + q);   // k_near_search: unresolved (total, no seed, not converged, not proven); longest replay
     }
 }
 
@@ -1431,11 +1504,10 @@ k_corner(const GzbGrid g, const int r, double* __restrict__ out) {
 // ------------------------------------------------------------------------------------------
 size_t gzb_nearest_ws_bytes(int64_t nt) {
     const size_t n = (size_t)(nt > 0 ? nt : 1);
-    const size_t nblk = (n + FLAGS_BLOCK - 1) / FLAGS_BLOCK;
+    const size_t nblk = (n + CH_PTS - 1) / CH_PTS;
     return gzb_align(n * 8) * 2      // G, dG
-           + gzb_align(n)            // brk
-           + gzb_align((nblk + 1) * 4)   // published block maps + ticket
-           + gzb_align(nblk * 4) + gzb_align(nblk * 8)   // counts, offsets
+           + gzb_align((nblk + 2) * 4)   // published block maps + ticket + the done counter of k_tail
+           + gzb_align(nblk * 8)     // break-count status words of k_chain
            + gzb_align(n * 8) * 2    // breaks, stop
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
@@ -1473,13 +1545,11 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     if (nt <= 0) return GZB_OK;
     if (np_box_r < 0) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_nearest: np_box_r must be >= 0");
     const size_t n = (size_t)nt;
-    const long long nblk = (long long)((n + FLAGS_BLOCK - 1) / FLAGS_BLOCK);
+    const long long nblk = (long long)((n + CH_PTS - 1) / CH_PTS);
     long long* G = (long long*)gzb_arena_take(ctx, n * 8);
     double* dG = (double*)gzb_arena_take(ctx, n * 8);
-    unsigned char* brk = (unsigned char*)gzb_arena_take(ctx, n);
-    unsigned* agg = (unsigned*)gzb_arena_take(ctx, ((size_t)nblk + 1) * 4);      // published block maps + the ticket
-    int* counts = (int*)gzb_arena_take(ctx, (size_t)nblk * 4);
-    (void)gzb_arena_take(ctx, (size_t)nblk * 8);      // (formerly the scanned offsets: kept so that the workspace layout matches gzb_nearest_ws_bytes)
+    unsigned* agg = (unsigned*)gzb_arena_take(ctx, ((size_t)nblk + 2) * 4);      // published block maps + the ticket + k_tail's done counter
+    unsigned long long* cstat = (unsigned long long*)gzb_arena_take(ctx, (size_t)nblk * 8);      // break-count status words
     long long* breaks = (long long*)gzb_arena_take(ctx, n * 8);
     long long* stop = (long long*)gzb_arena_take(ctx, n * 8);
     long long* first = (long long*)gzb_arena_take(ctx, n * 16);
@@ -1514,8 +1584,15 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     p.chord_r0 = 2.0 * sn * (1.0 + 1.0e-6) + 1.0e-12;
     p.r = np_box_r;
     p.edge = ctx->edge_exclusion;
-    p.seed_j = seed_j;
-    p.seed_i = seed_i;
+    if (ctx->segs_next.n > 0) {          // gzb_map_interp_multi: several chains, consumed by this call
+        p.segs = ctx->segs_next;
+        ctx->segs_next.n = 0;
+    } else {
+        p.segs.n = 1;
+        p.segs.start[0] = 0;
+        p.segs.sj[0] = seed_j;
+        p.segs.si[0] = seed_i;
+    }
     p.corner = corner;
     p.rowsafe = nullptr;
     if (ctx->twin_chain && ctx->g.kew > 0 && ctx->g.kew < ctx->g.Ni / 2) {
@@ -1529,7 +1606,8 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     }
 
     GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 64, s));
-    GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 1) * sizeof(unsigned), s));     // k_chain's ticket and block maps
+    GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 2) * sizeof(unsigned), s));     // k_chain's ticket and block maps, k_tail's counter
+    GZB_CUDA(ctx, cudaMemsetAsync(cstat, 0, (size_t)nblk * 8, s));
     if (ctx->corner_r != np_box_r) {
         k_corner<<<1, 256, 0, s>>>(ctx->g, np_box_r, corner);
         GZB_LAUNCH_CHECK(ctx);
@@ -1586,27 +1664,18 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     // before it (gzb_pdl_wait() at its top), so its launch overlaps the tail of its predecessor
     const bool pdl = ctx->pdl != 0 && !ctx->trace;
     launch_dep(pdl && sb_has_kernel, k_chain, (unsigned)nblk, FLAGS_BLOCK, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
-               (const double*)dG, (long long*)np_out, brk, counts, (volatile unsigned*)agg, agg + nblk, chg, nchg);
+               (const double*)dG, (long long*)np_out, breaks, (volatile unsigned long long*)cstat, (volatile unsigned*)agg, agg + nblk,
+               scal, chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
     gzb_trace(ctx, sb, "chain kernel end");
-    launch_dep(pdl, k_compact, (unsigned)nblk, FLAGS_BLOCK, sb, (const unsigned char*)brk, (const int*)counts, (long long)nt, breaks, scal);
-    GZB_LAUNCH_CHECK(ctx);
-    long long wblocks = (long long)((n + WALK_WARPS - 1) / WALK_WARPS);
-    const long long wmax = (long long)nsm * 64 / WALK_WARPS;
+    long long wblocks = (long long)((n + TAIL_WARPS - 1) / TAIL_WARPS);
+    const long long wmax = (long long)nsm * 64 / TAIL_WARPS;
     if (wblocks > wmax) wblocks = wmax;
-    launch_dep(pdl, k_walk<false>, (unsigned)wblocks, 32 * WALK_WARPS, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
-               (const double*)dG, (const long long*)breaks, (const long long*)scal, stop, first, (const unsigned char*)valid, wlog,
-               (long long*)np_out, (unsigned long long*)(scal + 1), (long long*)nullptr, (unsigned long long*)nullptr);
+    launch_dep(pdl, k_tail, (unsigned)wblocks, TAIL_THREADS, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
+               (const double*)dG, (const long long*)breaks, scal, stop, first, valid, wlog, (long long*)np_out, chg, nchg,
+               agg + nblk + 1, (long long*)(ctx->d_flags + 8));
     GZB_LAUNCH_CHECK(ctx);
-    gzb_trace(ctx, sb, "walk0 end");
-    launch_dep(pdl, k_valid, 1u, 256u, sb, (const long long*)breaks, (const long long*)stop, (const long long*)scal, valid,
-               (long long*)(ctx->d_flags + 8));
-    GZB_LAUNCH_CHECK(ctx);
-    launch_dep(pdl, k_walk<true>, (unsigned)wblocks, 32 * WALK_WARPS, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
-               (const double*)dG, (const long long*)breaks, (const long long*)scal, stop, first, (const unsigned char*)valid, wlog,
-               (long long*)np_out, (unsigned long long*)(scal + 1), chg, nchg);
-    GZB_LAUNCH_CHECK(ctx);
-    gzb_trace(ctx, sb, "walk1 end (chain done)");
+    gzb_trace(ctx, sb, "tail end (chain done)");
     if (split) GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[1], sb));
     ctx->nearest_stats_pending = 1;      // k_valid left (breaks, replay steps) in the persistent flags
     return GZB_OK;

@@ -72,6 +72,17 @@ class CudaEngine:
                                             int(k0), int(slab.shape[0]), float(config.rmissval), self._p(NP),
                                             self._p(SM), self._p(WB), self._p(v_np), self._p(v_bl)))
 
+    def map_interp_multi(self, seg_start, seg_seed, y, x, t, rd, r, tmod, slab, k0, NP, SM, WB, v_np, v_bl):
+        """K1-K4 of several independent chains in one call: sub-track s starts at point seg_start[s] (seg_start[0] == 0) and is
+        seeded with seg_seed[s] (host int64 arrays) -- several missions inside one window of records."""
+        dt = L.GZB_F32 if slab.dtype == self.torch.float32 else L.GZB_F64
+        st = np.ascontiguousarray(seg_start, dtype=np.int64)
+        sd = np.ascontiguousarray(seg_seed, dtype=np.int64).reshape(len(st), 2)
+        self.ctx._ck(L.lib().gzb_map_interp_multi(self.ctx._h, len(st), L.ptr(st), L.ptr(sd), y.numel(), self._p(y), self._p(x),
+                                                  self._p(t), float(rd), int(r), tmod.numel(), self._p(tmod), self._p(slab), dt,
+                                                  int(k0), int(slab.shape[0]), float(config.rmissval), self._p(NP), self._p(SM),
+                                                  self._p(WB), self._p(v_np), self._p(v_bl)))
+
     def mesh_weights_interp(self, y, x, t, NP, tmod, slab, k0, SM, WB, v_np, v_bl):
         """K2 + K3 + K4 as one kernel from known nearest points (the bulk kernel of `map_interp`)."""
         dt = L.GZB_F32 if slab.dtype == self.torch.float32 else L.GZB_F64

@@ -183,6 +183,17 @@ int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt,
                    double rmissval, int64_t* np_out, int64_t* sm_out, double* wb_out,
                    double* vnp_out, double* vbl_out);
 
+/* The same for SEVERAL independent chains in one call (BASELINE config 5: the points of several altimeter missions that
+ * fall into one window of model records).  The track arrays are the concatenation of nseg (<= 16) sub-tracks; sub-track s
+ * starts at point seg_start[s] (host array; seg_start[0] == 0, strictly increasing) and its first point is seeded with
+ * seg_seed[2s], seg_seed[2s+1] (host array) -- what one BilinTrack per mission would do (gonzag/bilin_mapping.py:570,
+ * 579-580).  Same results as one gzb_map_interp per sub-track; the latency-bound chain part of K1 is paid once. */
+int gzb_map_interp_multi(gzb_ctx* ctx, int nseg, const int64_t* seg_start, const int64_t* seg_seed, int64_t nt,
+                         const double* yt, const double* xt, const double* tt, double rd_found_km, int np_box_r,
+                         int64_t nrec, const double* tmod, const void* slab, int dtype, int64_t k0, int64_t nk,
+                         double rmissval, int64_t* np_out, int64_t* sm_out, double* wb_out, double* vnp_out,
+                         double* vbl_out);
+
 /* K2+K3+K4 in ONE kernel from known nearest points (BilinTrack.srcm() + wght(),
  * gonzag/bilin_mapping.py:595-617, then the interpolation loop, gonzag/mod2sat.py:74-139): the bulk
  * kernel of gzb_map_interp on its own.  Device-resident track, slab as for gzb_map_interp.  Same

@@ -370,6 +370,20 @@ class EmuLib:
         return rc or self.gzb_interp(h, nt, tt, sm_out, wb_out, nrec, tmod, slab, dtype, k0, nk, rmiss, 1, vnp_out, vbl_out,
                                      L.GZB_DEVICE)
 
+    def gzb_map_interp_multi(self, h, nseg, seg_start, seg_seed, nt, yt, xt, tt, rd, r, nrec, tmod, slab, dtype, k0, nk, rmiss,
+                             np_out, sm_out, wb_out, vnp_out, vbl_out):
+        st = list(_view(seg_start, (nseg,), np.int64)) + [int(nt)]
+        sd = _view(seg_seed, (nseg, 2), np.int64)
+        off = lambda p, k: _addr(p) + int(k)
+        for q in range(nseg):
+            a_, b_ = int(st[q]), int(st[q + 1])
+            rc = self.gzb_map_interp(h, b_ - a_, off(yt, a_ * 8), off(xt, a_ * 8), off(tt, a_ * 8), rd, r, int(sd[q, 0]), int(sd[q, 1]),
+                                     nrec, tmod, slab, dtype, k0, nk, rmiss, off(np_out, a_ * 16), off(sm_out, a_ * 64),
+                                     off(wb_out, a_ * 32), off(vnp_out, a_ * 8), off(vbl_out, a_ * 8))
+            if rc:
+                return rc
+        return L.GZB_OK
+
     # ------------------------------------------------------------------ a14
     def gzb_track_distance(self, h, nt, yt, xt, out, where):
         ctx = self._c(h)

@@ -364,6 +364,64 @@ def test_map_interp_matches_staged(golden_global):
             assert np.array_equal(ctx.download(o2[3], (n,), np.float64), v_bl)
 
 
+@pytest.mark.parametrize("case", ["global", "seam"])
+def test_several_chains_in_one_call(golden_global, golden_seam, case):
+    """gzb_map_interp_multi: the track cut into sub-tracks, each a chain of its own with its own seed (BASELINE config 5:
+    several missions in one window of records), against one gzb_map_interp per sub-track -- bit for bit, on the global -D
+    case and on the seam-hugging tracks (cuts inside chain deviations, single-point and two-point sub-tracks)."""
+    import ctypes as C
+    from gonzag_b200 import _lib as L
+    g = golden_global
+    lat, lon = _grid(g)
+    res = float(g["res"])
+    rd, r = 0.75 * res * 111.11, int(0.5 * 500. / (res * 111.11))
+    if case == "global":
+        y, x, t, tm, fld, ang, msk = g["ysat"], g["xsat"], g["tsat"], g["tmod"], g["f32"], g["angle"], g["mask"]
+    else:                        # the seam-hugging tracks live on the same grid
+        y, x = golden_seam["ysat"], golden_seam["xsat"]
+        rd, r = float(golden_seam["rd"]), int(golden_seam["r"])
+        t = 10.0 + np.arange(len(y), dtype=np.float64)
+        tm = np.array([0.0, t[-1] + 100.0])
+        fld, ang, msk = syn.ssh_records(lat, lon, 2), None, g["mask"]
+    n = len(y)
+    rng = np.random.default_rng(3)
+    cuts = np.unique(np.concatenate([[0, 1, 3, n // 2, n // 2 + 2], rng.integers(1, n - 1, 9)]))[:16]
+    seeds = np.array([[r, r]] + [[int(v), int(w_)] for v, w_ in rng.integers(0, 40, (len(cuts) - 1, 2))], dtype=np.int64)
+    seeds[2] = [0, 0]            # "no previous hit": global search only (gonzag/bilin_mapping.py:157)
+    seeds[3] = [-1, -1]          # a not-found predecessor: the corner box
+    with gzb.GridContext(lat, lon, angle=ang, mask=msk, k_ew_per=int(g["kew"])) as ctx:
+        d = [ctx.upload(a) for a in (L.as_f64(y), L.as_f64(x), L.as_f64(t), L.as_f64(tm), np.ascontiguousarray(fld))]
+        P = lambda b, off=0: C.c_void_p(b.ptr + off)
+        dt = ctx._field_dtype(fld)
+        want = [np.empty((n, 2), np.int64), np.empty((n, 4, 2), np.int64), np.empty((n, 4)), np.empty(n), np.empty(n)]
+        o = [ctx.dev_alloc(n * k) for k in (16, 64, 32, 8, 8)]
+        ends = list(cuts[1:]) + [n]
+        for s_, (a, b) in enumerate(zip(cuts, ends)):
+            m = int(b - a)
+            ctx._ck(L.lib().gzb_map_interp(ctx._h, m, P(d[0], a * 8), P(d[1], a * 8), P(d[2], a * 8), rd, r, int(seeds[s_, 0]),
+                                           int(seeds[s_, 1]), len(tm), P(d[3]), P(d[4]), dt, 0, fld.shape[0], -9999.,
+                                           P(o[0], a * 16), P(o[1], a * 64), P(o[2], a * 32), P(o[3], a * 8), P(o[4], a * 8)))
+        ctx.sync()
+        shapes = [((n, 2), np.int64), ((n, 4, 2), np.int64), ((n, 4), np.float64), ((n,), np.float64), ((n,), np.float64)]
+        want = [ctx.download(b, sh, ty) for b, (sh, ty) in zip(o, shapes)]
+        for overlap in (1, 0):
+            ctx.set_option("overlap", overlap)
+            o2 = [ctx.dev_alloc(n * k) for k in (16, 64, 32, 8, 8)]
+            st = np.ascontiguousarray(cuts, dtype=np.int64)
+            ctx._ck(L.lib().gzb_map_interp_multi(ctx._h, len(st), L.ptr(st), L.ptr(seeds), n, P(d[0]), P(d[1]), P(d[2]), rd, r,
+                                                 len(tm), P(d[3]), P(d[4]), dt, 0, fld.shape[0], -9999., P(o2[0]), P(o2[1]),
+                                                 P(o2[2]), P(o2[3]), P(o2[4])))
+            ctx.sync()
+            for b, w_, (sh, ty) in zip(o2, want, shapes):
+                got = ctx.download(b, sh, ty)
+                assert np.array_equal(got.view(np.int64), w_.view(np.int64))
+        # bad arguments are refused, and the next ordinary call is unaffected
+        bad = np.array([0, 5, 5], dtype=np.int64)
+        rc = L.lib().gzb_map_interp_multi(ctx._h, 3, L.ptr(bad), L.ptr(seeds), n, P(d[0]), P(d[1]), P(d[2]), rd, r, len(tm), P(d[3]),
+                                          P(d[4]), dt, 0, fld.shape[0], -9999., P(o[0]), P(o[1]), P(o[2]), P(o[3]), P(o[4]))
+        assert rc == L.GZB_ERR_ARG
+
+
 def test_launch_and_memory_options_do_not_change_results(golden_global):
     """Options that only change HOW the kernels are launched or fed -- "pdl" (programmatic dependent
     launches of K1's chain kernels), "prefetch" (L2 prefetch of the gather in the fused kernel and in
