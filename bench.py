@@ -1013,9 +1013,12 @@ def run_windowed(args, w):
                     pred_pos[m] = hit[0][1] + hit[0][2] - 1
                     break
 
+    k1s = {}
+
     def one_pass(keep=None, seeds0=None):
         """One pass over this rank's windows.  Returns (timed ms, kernel launches, the seed each mission started from)."""
         seeds = {}
+        k1s.update(unresolved=0, breaks=0, calls=0)
         for m in range(nm):
             if seeds0 is not None and m in seeds0:
                 seeds[m] = seeds0[m]
@@ -1050,6 +1053,8 @@ def run_windowed(args, w):
             e1.record()
             pairs.append((e0, e1))
             tails = NPa[[blk[1] + blk[2] - 1 for blk in row]].cpu().numpy()      # every mission goes on from here (one sync; untimed)
+            st_ = ctx.stats()
+            k1s["unresolved"] += int(st_["last_unresolved"]); k1s["breaks"] += int(st_["last_breaks"]); k1s["calls"] += 1
             for blk, v in zip(row, tails):
                 seeds[blk[0]] = (int(v[0]), int(v[1]))
         launches = ctx.stats()["kernel_launches"] - n0
@@ -1174,6 +1179,8 @@ def run_windowed(args, w):
                             "timed": "sum over the pass of every gzb_map_interp_multi call (K1-K4 of ALL missions' points in one record "
                                      "window, one chain per mission; CUDA events on the launching stream) + the final all-gather; max over ranks",
                             "ms_per_step_by_rank": [round(v, 3) for v in per_rank], "seed_reseeds": reseeds,
+                            "k1_this_gpu_per_pass": {"calls": k1s.get("calls"), "points_left_to_the_warp_search": k1s.get("unresolved"),
+                                                     "chain_breaks": k1s.get("breaks")},
                             "whole_path_algorithmic_gbs_per_gpu": ach, "frac_of_hbm_peak": ach / peak},
                 "verified": verified, "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": {"kernel": "whole path K1-K4 (per GPU), see the C3 line for the per-kernel table", "bound": "hbm",

@@ -983,26 +983,22 @@ __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned*
 // predecessor T(t-1)), composed map of the block, state entering the block by a decoupled look-back
 // over the maps the earlier blocks published (a map that sends both states to the same one -- any
 // block away from the seam -- ends the look-back, so its depth is almost always one), then the
-// speculative chain and the ORDERED list of breaks: the block's offset in that list comes from a second
-// decoupled look-back, over the break counts (status word per block: aggregate, then inclusive prefix).
+// speculative chain and the ORDERED list of breaks (per-block lists, put together by the block that finishes last).
 // A thread owns CH_PPT consecutive points (one composed map per thread goes through the block scan; a
 // 10-day track is ~600 blocks: one wave).  Blocks take their index from a ticket, so a block only ever
 // waits for blocks that already started.
 #define CH_PPT 4
 #define CH_PTS (FLAGS_BLOCK * CH_PPT)
-#define CST_AGG 0x4000000000000000ull
-#define CST_INC 0x8000000000000000ull
 __global__ void __launch_bounds__(FLAGS_BLOCK)
 k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
         const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
-        long long* __restrict__ NP, long long* __restrict__ breaks, volatile unsigned long long* cstat,
-        volatile unsigned* agg, unsigned* __restrict__ ticket, long long* __restrict__ nbrk_out,
-        long long* __restrict__ chg, unsigned long long* __restrict__ nchg) {
+        long long* __restrict__ NP, long long* __restrict__ breaks, long long* __restrict__ blist, int* __restrict__ bcount,
+        volatile unsigned* agg, unsigned* __restrict__ ticket, unsigned* __restrict__ done_ctr,
+        long long* __restrict__ nbrk_out, long long* __restrict__ chg, unsigned long long* __restrict__ nchg) {
     __shared__ unsigned sh[FLAGS_BLOCK / 32];
     __shared__ unsigned last[FLAGS_BLOCK / 32];
     __shared__ int wcnt[FLAGS_BLOCK / 32];
     __shared__ unsigned s_bid, s_entry;
-    __shared__ long long s_base;
     __shared__ int sE[FLAGS_BLOCK][2], sT[FLAGS_BLOCK][3];      // E / T of the LAST point of every thread
     gzb_pdl_wait();
     if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
@@ -1107,7 +1103,10 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
             st = out == 1u ? 1u : 0u;
         }
     }
-    // ---- ordered break list: exclusive offsets inside the block, block offset by look-back over the counts
+    // ---- ordered break list.  Every block writes its own breaks, in order, into its slot of `blist` (CH_PTS entries per
+    // block) and its count into `bcount`; the block that finishes LAST adds up the counts and copies the slots, in block
+    // order, into `breaks` -- no block ever waits for another one's count (a look-back over counts serialises a grid that
+    // runs as a single wave), and the usual few hundred breaks are copied in one step.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mycnt = __popc(bmask);
     int wincl = mycnt;
@@ -1124,32 +1123,50 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
         if (w2 < warp) wbase += wcnt[w2];
         btotal += wcnt[w2];
     }
-    if (threadIdx.x == 0) {
-        long long excl = 0;
-        if (bid > 0) {
-            cstat[bid] = CST_AGG | (unsigned long long)btotal;
-            __threadfence();
-            long long k = (long long)bid - 1;
-            for (;;) {
-                unsigned long long v;
-                while (((v = cstat[k]) & (CST_AGG | CST_INC)) == 0ull) __nanosleep(40);
-                excl += (long long)(v & 0x3fffffffffffffffull);
-                if (v & CST_INC) break;
-                --k;      // block 0 always publishes an inclusive prefix: k never goes below 0
-            }
-        }
-        cstat[bid] = CST_INC | (unsigned long long)(excl + btotal);
-        __threadfence();
-        s_base = excl;
-        if ((long long)(bid + 1) * CH_PTS >= nt) nbrk_out[0] = excl + btotal;      // the block that holds the last point
-    }
-    __syncthreads();
     if (bmask) {
-        long long pos = s_base + wbase + (wincl - mycnt);
+        long long pos = (long long)bid * CH_PTS + wbase + (wincl - mycnt);
 #pragma unroll
         for (int k = 0; k < CH_PPT; ++k)
-            if (bmask & (1u << k)) breaks[pos++] = t0 + k;
+            if (bmask & (1u << k)) blist[pos++] = t0 + k;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bcount[bid] = btotal;
+        __threadfence();
+        s_entry = (atomicAdd(done_ctr, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_entry) return;
+    __threadfence();
+    // the last block: exclusive prefix of the counts (chunks of FLAGS_BLOCK blocks), then the ordered copy
+    const long long nblk = gridDim.x;
+    long long carry = 0;
+    for (long long c0 = 0; c0 < nblk; c0 += FLAGS_BLOCK) {
+        const long long bk = c0 + threadIdx.x;
+        const int cnt = bk < nblk ? __ldcg(bcount + bk) : 0;
+        int incl2 = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl2, o);
+            if (lane >= o) incl2 += u;
+        }
+        __syncthreads();
+        if (lane == 31) wcnt[warp] = incl2;
+        __syncthreads();
+        int wb2 = 0, ctot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < FLAGS_BLOCK / 32; ++w2) {
+            if (w2 < warp) wb2 += wcnt[w2];
+            ctot += wcnt[w2];
+        }
+        if (ctot) {
+            // (block, position) pairs of this chunk: the chunk's breaks, cut over the threads of the block
+            const long long excl = carry + wb2 + (incl2 - cnt);
+            for (int e = 0; e < cnt; ++e) breaks[excl + e] = __ldcg(blist + bk * CH_PTS + e);
+        }
+        carry += ctot;
+    }
+    if (threadIdx.x == 0) nbrk_out[0] = carry;
 }
 
 // per row: 1 = no cell strictly between a leading overlap cell and its East-West twin has that cell's
@@ -1506,8 +1523,9 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
     const size_t n = (size_t)(nt > 0 ? nt : 1);
     const size_t nblk = (n + CH_PTS - 1) / CH_PTS;
     return gzb_align(n * 8) * 2      // G, dG
-           + gzb_align((nblk + 2) * 4)   // published block maps + ticket + the done counter of k_tail
-           + gzb_align(nblk * 8)     // break-count status words of k_chain
+           + gzb_align((nblk + 3) * 4)   // published block maps + ticket + the done counters of k_chain and k_tail
+           + gzb_align(nblk * 4)     // break counts of k_chain's blocks
+           + gzb_align(nblk * CH_PTS * 8)   // ... and their break lists
            + gzb_align(n * 8) * 2    // breaks, stop
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
@@ -1548,8 +1566,9 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     const long long nblk = (long long)((n + CH_PTS - 1) / CH_PTS);
     long long* G = (long long*)gzb_arena_take(ctx, n * 8);
     double* dG = (double*)gzb_arena_take(ctx, n * 8);
-    unsigned* agg = (unsigned*)gzb_arena_take(ctx, ((size_t)nblk + 2) * 4);      // published block maps + the ticket + k_tail's done counter
-    unsigned long long* cstat = (unsigned long long*)gzb_arena_take(ctx, (size_t)nblk * 8);      // break-count status words
+    unsigned* agg = (unsigned*)gzb_arena_take(ctx, ((size_t)nblk + 3) * 4);      // published block maps + the ticket + the done counters of k_chain / k_tail
+    int* bcount = (int*)gzb_arena_take(ctx, (size_t)nblk * 4);
+    long long* blist = (long long*)gzb_arena_take(ctx, (size_t)nblk * CH_PTS * 8);
     long long* breaks = (long long*)gzb_arena_take(ctx, n * 8);
     long long* stop = (long long*)gzb_arena_take(ctx, n * 8);
     long long* first = (long long*)gzb_arena_take(ctx, n * 16);
@@ -1606,8 +1625,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     }
 
     GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 64, s));
-    GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 2) * sizeof(unsigned), s));     // k_chain's ticket and block maps, k_tail's counter
-    GZB_CUDA(ctx, cudaMemsetAsync(cstat, 0, (size_t)nblk * 8, s));
+    GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 3) * sizeof(unsigned), s));     // k_chain's ticket and block maps, the two done counters
     if (ctx->corner_r != np_box_r) {
         k_corner<<<1, 256, 0, s>>>(ctx->g, np_box_r, corner);
         GZB_LAUNCH_CHECK(ctx);
@@ -1664,12 +1682,14 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     // before it (gzb_pdl_wait() at its top), so its launch overlaps the tail of its predecessor
     const bool pdl = ctx->pdl != 0 && !ctx->trace;
     launch_dep(pdl && sb_has_kernel, k_chain, (unsigned)nblk, FLAGS_BLOCK, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
-               (const double*)dG, (long long*)np_out, breaks, (volatile unsigned long long*)cstat, (volatile unsigned*)agg, agg + nblk,
+               (const double*)dG, (long long*)np_out, breaks, blist, bcount, (volatile unsigned*)agg, agg + nblk, agg + nblk + 2,
                scal, chg, nchg);
     GZB_LAUNCH_CHECK(ctx);
     gzb_trace(ctx, sb, "chain kernel end");
+    // enough warps for the usual few hundred breaks (the replay loop strides over the rest): every block of the grid,
+    // empty or not, has to pass the "who is last" counter
     long long wblocks = (long long)((n + TAIL_WARPS - 1) / TAIL_WARPS);
-    const long long wmax = (long long)nsm * 64 / TAIL_WARPS;
+    const long long wmax = (long long)nsm * 4;
     if (wblocks > wmax) wblocks = wmax;
     launch_dep(pdl, k_tail, (unsigned)wblocks, TAIL_THREADS, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
                (const double*)dG, (const long long*)breaks, scal, stop, first, valid, wlog, (long long*)np_out, chg, nchg,

@@ -391,7 +391,7 @@ def test_several_chains_in_one_call(golden_global, golden_seam, case):
     seeds[3] = [-1, -1]          # a not-found predecessor: the corner box
     with gzb.GridContext(lat, lon, angle=ang, mask=msk, k_ew_per=int(g["kew"])) as ctx:
         d = [ctx.upload(a) for a in (L.as_f64(y), L.as_f64(x), L.as_f64(t), L.as_f64(tm), np.ascontiguousarray(fld))]
-        P = lambda b, off=0: C.c_void_p(b.ptr + off)
+        P = lambda b, off=0: C.c_void_p(int(b.ptr) + int(off))
         dt = ctx._field_dtype(fld)
         want = [np.empty((n, 2), np.int64), np.empty((n, 4, 2), np.int64), np.empty((n, 4)), np.empty(n), np.empty(n)]
         o = [ctx.dev_alloc(n * k) for k in (16, 64, 32, 8, 8)]
