@@ -335,8 +335,8 @@ def run_ours(args, w):
 
     # NCCL's own log (communicator size, transports, NVLS) goes to stderr with the rest: stdout was re-pointed by
     # claim_stdout(), the JSON line is written to the saved descriptor
-    os.environ.setdefault("NCCL_DEBUG", os.environ.get("GZB_NCCL_DEBUG", "INFO"))
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ["NCCL_DEBUG"] = os.environ.get("GZB_NCCL_DEBUG", "INFO")      # (the image presets a quieter level)
+    os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("GZB_NCCL_DEBUG_SUBSYS", "INIT")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -891,8 +891,8 @@ def run_windowed(args, w):
     from gonzag_b200.multi import CudaEngine
     from gonzag_b200.sharded import tensor_view
 
-    os.environ.setdefault("NCCL_DEBUG", os.environ.get("GZB_NCCL_DEBUG", "INFO"))
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ["NCCL_DEBUG"] = os.environ.get("GZB_NCCL_DEBUG", "INFO")      # (the image presets a quieter level)
+    os.environ["NCCL_DEBUG_SUBSYS"] = os.environ.get("GZB_NCCL_DEBUG_SUBSYS", "INIT")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

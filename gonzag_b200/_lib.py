@@ -31,7 +31,7 @@ class Stats(C.Structure):
                 ("lut_bins", C.c_int64), ("last_unresolved", C.c_int64),
                 ("last_unres_noseed", C.c_int64), ("last_unres_noconv", C.c_int64),
                 ("last_unres_nocert", C.c_int64), ("last_max_chain", C.c_int64),
-                ("heading_table", C.c_int64)]
+                ("heading_table", C.c_int64), ("weak_cells", C.c_int64)]
 
 
 _P = C.c_void_p

@@ -379,6 +379,7 @@ void* gzb_arena_take(gzb_ctx* ctx, size_t bytes) {
 
 // ======================================================================== pyramid build
 int gzb_build_cert(gzb_ctx* ctx);   // gzb_nearest.cu
+int gzb_build_weak(gzb_ctx* ctx);   // gzb_nearest.cu
 
 // fp32 storage of a sphere computed in fp64: the radius is rounded up and padded by 2.5e-7 so
 // that it still bounds the members after the centre itself was rounded to float
@@ -820,6 +821,7 @@ static int build_pyramid(gzb_ctx* ctx) {
         if ((rc = build_lut(ctx, (const unsigned long long*)((char*)ctx->pinned + 256))) != GZB_OK) return rc;
         k_cellcert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cellv);
         GZB_LAUNCH_CHECK(ctx);
+        if ((rc = gzb_build_weak(ctx)) != GZB_OK) return rc;
     }
     return GZB_OK;
 }
@@ -934,6 +936,8 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     gzb_pool_free(ctx->d_cells);
     gzb_pool_free(ctx->d_cert);
     gzb_pool_free(ctx->d_cellv);
+    gzb_pool_free(ctx->d_weak);
+    gzb_pool_free(ctx->d_weak_list);
     gzb_pool_free(ctx->d_lut[0]);
     gzb_pool_free(ctx->d_lut[1]);
     gzb_pool_free(ctx->d_hdg);

@@ -69,6 +69,7 @@ struct Srch {          // warp-uniform state of the search for one point
     float Pmin;        // smallest chord^2 seen (fp32 proxy)
     float B, B2;       // candidate / pruning bound on the chord and its square
     int bJ, bI;        // leaf tile holding the best proxy
+    long long bflat;   // M_EXCL only: flat index of the cell holding the best proxy
 };
 
 struct Owner {         // the point a lane owns (exact evaluation needs its coordinates)
@@ -111,6 +112,7 @@ __device__ __forceinline__ void srch_init(Srch& s, float px, float py, float pz)
     s.px = px; s.py = py; s.pz = pz;
     s.Pmin = INFINITY; s.B = INFINITY; s.B2 = INFINITY;
     s.bJ = -1; s.bI = -1;
+    s.bflat = -1;
 }
 
 // exact evaluation of the queued candidates, 32 at a time, and per-point lexicographic minimum
@@ -149,7 +151,8 @@ __device__ __forceinline__ void flush_queue(const GzbGrid& g, WarpSm& w, const i
 template <int MODE>
 __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
                                           const int tJ, const int tI, const long long j0, const long long j1,
-                                          const long long i0, const long long i1, int& qn, const Owner& me) {
+                                          const long long i0, const long long i1, int& qn, const Owner& me,
+                                          const long long* xb = nullptr /* M_EXCL: a second excluded box j0,j1,i0,i1 */) {
     const float* __restrict__ cc = g.cells + ((long long)tJ * g.lev[0].nI + tI) * 96;
     const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
     const long long j = (long long)tJ * GZB_TILE_J + (lane >> 3);
@@ -159,6 +162,7 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
     if (MODE != M_GLOBAL) {
         const bool inside = (j >= j0) && (j < j1) && (i >= i0) && (i < i1);
         ok = (j < g.Nj) && (i < g.Ni) && (MODE == M_BOX ? inside : !inside);
+        if (MODE == M_EXCL && xb && ok) ok = !((j >= xb[0]) && (j < xb[1]) && (i >= xb[2]) && (i < xb[3]));
     }
     const float dx = s.px - x, dy = s.py - y, dz = s.pz - z;
     const float P = dx * dx + dy * dy + dz * dz;
@@ -168,6 +172,11 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
         s.bJ = tJ;
         s.bI = tI;
         if (MODE != M_EXCL && lane == 0) w.pb2[pt] = s.B2;
+        if (MODE == M_EXCL) {
+            const unsigned hm = __ballot_sync(0xffffffffu, ok && P == pm);
+            const int hl = hm ? __ffs(hm) - 1 : 0;
+            s.bflat = __shfl_sync(0xffffffffu, j * g.Ni + i, hl);
+        }
     }
     if (MODE != M_EXCL) {
         const bool cand = ok && (P <= s.B2);
@@ -191,7 +200,7 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
 template <int MODE>
 __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
                                                const long long j0, const long long j1, const long long i0,
-                                               const long long i1, int& qn, const Owner& me) {
+                                               const long long i1, int& qn, const Owner& me, const long long* xb = nullptr) {
     int depth = 0;
     if (lane == 0) w.fmask[0] = 0xffffffffu;
     __syncwarp();
@@ -218,7 +227,10 @@ __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, cons
         if (MODE != M_GLOBAL && keep) {
             const long long a0 = (long long)cJ * L.sJ, b0 = (long long)cI * L.sI;
             if (MODE == M_BOX) keep = (a0 < j1) && (a0 + L.sJ > j0) && (b0 < i1) && (b0 + L.sI > i0);
-            else keep = !((a0 >= j0) && (a0 + L.sJ <= j1) && (b0 >= i0) && (b0 + L.sI <= i1));
+            else {
+                keep = !((a0 >= j0) && (a0 + L.sJ <= j1) && (b0 >= i0) && (b0 + L.sI <= i1));
+                if (xb && keep) keep = !((a0 >= xb[0]) && (a0 + L.sJ <= xb[1]) && (b0 >= xb[2]) && (b0 + L.sI <= xb[3]));
+            }
         }
         const float dx = s.px - nd.x, dy = s.py - nd.y, dz = s.pz - nd.z;
         const float dn2 = dx * dx + dy * dy + dz * dz;
@@ -245,7 +257,7 @@ __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, cons
             }
             __syncwarp();
         } else {
-            leaf_eval<MODE>(g, w, lane, s, pt, sJ, sI, j0, j1, i0, i1, qn, me);
+            leaf_eval<MODE>(g, w, lane, s, pt, sJ, sI, j0, j1, i0, i1, qn, me, xb);
             __syncwarp();
         }
     }
@@ -605,6 +617,28 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
     }
 }
 
+// weak-cell table of the per-thread search (built by gzb_build_weak below)
+#define WEAK_NONE 0xffffffffu
+#define WEAK_HMAX 24
+
+__device__ __forceinline__ unsigned weak_hash(const unsigned key) { return key * 2654435761u; }
+
+__device__ __forceinline__ bool weak_lookup(const GzbGrid& g, const unsigned key, uint4& e) {
+    unsigned slot = weak_hash(key) & g.weak_mask;
+    for (int probe = 0; probe < 64; ++probe) {
+        e = __ldg(g.weak + slot);
+        if (e.x == key) return true;
+        if (e.x == WEAK_NONE) return false;
+        slot = (slot + 1) & g.weak_mask;
+    }
+    return false;
+}
+
+__device__ __forceinline__ float cell_chord(const float4 a, const float4 b) {
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
 __global__ void __launch_bounds__(128, 8)
 k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
               long long* __restrict__ G, double* __restrict__ dG, long long* __restrict__ ulist,
@@ -688,12 +722,83 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
                     }
                 }
             }
+            bool settled = false;
+            if (reason == 3 && g.weak) {
+                // a weak cell (anisotropic, or next to duplicated columns): scan its box and its portal's neighbourhood
+                // instead of 5x5; move while something there is strictly nearer; prove with the table's certificate
+                int jj = (int)(myhint / (unsigned)g.Ni), ii = (int)(myhint - (unsigned)jj * (unsigned)g.Ni);
+                float Pcc;
+                {
+                    const float4 v = __ldg(g.cellv + myhint);
+                    const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+                    Pcc = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                }
+                for (int att = 0; att < 6; ++att) {
+                    uint4 e;
+                    if (!weak_lookup(g, (unsigned)jj * (unsigned)g.Ni + (unsigned)ii, e)) break;
+                    const int hj = (int)(e.w & 0xffu), hi = (int)((e.w >> 8) & 0xffu);
+                    int pj = -1000, pi = -1000;
+                    if (e.y != WEAK_NONE) { pj = (int)(e.y / (unsigned)g.Ni); pi = (int)(e.y - (unsigned)pj * (unsigned)g.Ni); }
+                    const int ja = max(jj - hj, 0), jb = min(jj + hj, (int)g.Nj - 1);
+                    const int ia = max(ii - hi, 0), ib = min(ii + hi, (int)g.Ni - 1);
+                    const int qa = max(pj - 2, 0), qb = min(pj + 2, (int)g.Nj - 1);
+                    const int ra = max(pi - 2, 0), rb = min(pi + 2, (int)g.Ni - 1);
+                    float best = Pcc;
+                    int bj = jj, bi = ii;
+                    for (int part = 0; part < (e.y != WEAK_NONE ? 2 : 1); ++part) {
+                        const int j0 = part ? qa : ja, j1 = part ? qb : jb, i0 = part ? ra : ia, i1 = part ? rb : ib;
+                        for (int row = j0; row <= j1; ++row) {
+                            const float4* __restrict__ rp = g.cellv + (long long)row * g.Ni;
+                            for (int col = i0; col <= i1; ++col) {
+                                const float4 v = __ldg(rp + col);
+                                const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+                                const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                                if (P < best) { best = P; bj = row; bi = col; }
+                            }
+                        }
+                    }
+                    if (bj != jj || bi != ii) { jj = bj; ii = bi; Pcc = best; continue; }
+                    const float a = sqrtf(Pcc);
+                    const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
+                    if ((__uint_as_float(e.z) - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
+                        // proven: the reference's fp64 formula on every cell of the region within the fp32 margin;
+                        // lexicographic minimum (distance bits, flat index) == numpy.argmin's first occurrence
+                        const float B2 = B * B;
+                        const double cpl = cos(lat * GZB_D2R);
+                        unsigned long long bd = ~0ull;
+                        long long bf = GZB_NOFLAT;
+                        for (int part = 0; part < (e.y != WEAK_NONE ? 2 : 1); ++part) {
+                            const int j0 = part ? qa : ja, j1 = part ? qb : jb, i0 = part ? ra : ia, i1 = part ? rb : ib;
+                            for (int row = j0; row <= j1; ++row) {
+                                for (int col = i0; col <= i1; ++col) {
+                                    const long long fl = (long long)row * g.Ni + col;
+                                    const float4 v = __ldg(g.cellv + fl);
+                                    const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+                                    const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                                    if (!(P <= B2)) continue;
+                                    const double2 cf = __ldg(g.ll + fl);
+                                    const double d = gzb_haversine_dev(lat, lon, cpl, cf.x, cf.y);
+                                    if (!(d == d)) continue;
+                                    const unsigned long long db = (unsigned long long)__double_as_longlong(d);
+                                    if (db < bd || (db == bd && fl < bf)) { bd = db; bf = fl; }
+                                }
+                            }
+                        }
+                        G[t] = bf;
+                        dG[t] = __longlong_as_double((long long)bd);
+                        settled = true;
+                        reason = 0;
+                    }
+                    break;
+                }
+                myhint = (unsigned)jj * (unsigned)g.Ni + (unsigned)ii;
+            }
             if (reason) {
                 unresolved = true;
                 out = CAND_UNRES;
                 atomicAdd(ucount + reason, 1ull);
             }
-            if (!unresolved) {
+            if (!unresolved && !settled) {
                 // settle the point here: the reference's fp64 formula on the candidate(s)
 #if GZB_EXP_SKIP_DG
                 const float m2 = a_win * 4.0e-6f + 4.0e-6f;           // twice the proven fp32 error of the chord
@@ -819,6 +924,131 @@ int gzb_build_cert(gzb_ctx* ctx) {
     const long long ntile = (long long)ctx->g.lev[0].nJ * ctx->g.lev[0].nI;
     k_cert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(ctx->g, ctx->d_cert);
     GZB_LAUNCH_CHECK(ctx);
+    return GZB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// WEAK cells: cells whose 5x5 certificate is too small for the targets that belong to them -- strongly anisotropic
+// cells (converging meridians near a displaced grid pole: the nearest cells in space are many columns away) and cells
+// next to duplicated / folded columns (the East-West overlap: a copy of the neighbourhood sits at the other end of the
+// row).  Found from the coordinates alone (nothing here trusts k_ew_per).  For each of them the table holds
+//   (hj, hi)   half-widths of an index box around the cell that reaches ~1.8 x its largest spacing in both directions,
+//   portal     the nearest cell OUTSIDE that box when it is closer than that (the copy at the other end), else none,
+//   wcert      a lower bound of the chord from the cell to any cell outside  box U 5x5(portal).
+// k_near_search scans box U 5x5(portal) for such a cell instead of 5x5 and settles the point itself; what is left
+// for the warp-cooperative search are the cells where even that is not enough (pole rows, |ratio| > 1:13).
+// thread per cell: weak iff the 5x5 certificate is below 1.5 x the largest chord to a direct neighbour
+__global__ void __launch_bounds__(256)
+k_weak_mark(const GzbGrid g, unsigned* __restrict__ list, unsigned* __restrict__ count, const unsigned cap) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= g.Nj * g.Ni) return;
+    const long long j = k / g.Ni, i = k - j * g.Ni;
+    const float4 c = __ldg(g.cellv + k);
+    float s = 0.0f;
+    if (i > 0) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k - 1)));
+    if (i + 1 < g.Ni) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k + 1)));
+    if (j > 0) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k - g.Ni)));
+    if (j + 1 < g.Nj) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k + g.Ni)));
+    const float w5 = __uint_as_float(__float_as_uint(c.w) << 16);
+    if (w5 < 1.5f * s) {
+        const unsigned pos = atomicAdd(count, 1u);
+        if (pos < cap) list[pos] = (unsigned)k;
+    }
+}
+
+// warp per weak cell: box, portal, certificate -> hash table
+__global__ void __launch_bounds__(128)
+k_weak_build(const GzbGrid g, const unsigned* __restrict__ list, const unsigned* __restrict__ count, const unsigned cap,
+             uint4* __restrict__ table, const unsigned mask) {
+    __shared__ WarpSm ws[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned n = min(*count, cap);
+    const unsigned e = blockIdx.x * 4 + warp;
+    if (e >= n) return;
+    const unsigned key = list[e];
+    const long long j = key / g.Ni, i = key - j * g.Ni;
+    const float4 c = __ldg(g.cellv + key);
+    float dxa = 0.0f, dxb = INFINITY, dya = 0.0f, dyb = INFINITY;      // largest / smallest spacing along i and along j
+    if (i > 0) { const float d = cell_chord(c, __ldg(g.cellv + key - 1)); dxa = fmaxf(dxa, d); dxb = fminf(dxb, d); }
+    if (i + 1 < g.Ni) { const float d = cell_chord(c, __ldg(g.cellv + key + 1)); dxa = fmaxf(dxa, d); dxb = fminf(dxb, d); }
+    if (j > 0) { const float d = cell_chord(c, __ldg(g.cellv + key - g.Ni)); dya = fmaxf(dya, d); dyb = fminf(dyb, d); }
+    if (j + 1 < g.Nj) { const float d = cell_chord(c, __ldg(g.cellv + key + g.Ni)); dya = fmaxf(dya, d); dyb = fminf(dyb, d); }
+    const float R = 1.8f * fmaxf(dxa, dya);
+    int hi = (dxb > 0.0f && dxb < INFINITY) ? (int)fminf(ceilf(R / dxb), (float)WEAK_HMAX) : WEAK_HMAX;
+    int hj = (dyb > 0.0f && dyb < INFINITY) ? (int)fminf(ceilf(R / dyb), (float)WEAK_HMAX) : WEAK_HMAX;
+    hi = hi < 2 ? 2 : hi;
+    hj = hj < 2 ? 2 : hj;
+    Owner me;
+    me.plat = me.plon = me.cpl = 0.0;
+    int qn = 0;
+    Srch s;
+    srch_init(s, c.x, c.y, c.z);
+    pyramid_search<M_EXCL>(g, ws[warp], lane, s, 0, j - hj, j + hj + 1, i - hi, i + hi + 1, qn, me);
+    float d = s.Pmin < INFINITY ? sqrtf(s.Pmin) : INFINITY;
+    unsigned portal = WEAK_NONE;
+    if (d < 0.9f * R && s.bflat >= 0) {
+        portal = (unsigned)s.bflat;
+        const long long pj = s.bflat / g.Ni, pi = s.bflat - pj * g.Ni;
+        long long xb[4] = {pj - 2, pj + 3, pi - 2, pi + 3};
+        Srch s2;
+        srch_init(s2, c.x, c.y, c.z);
+        __syncwarp();
+        pyramid_search<M_EXCL>(g, ws[warp], lane, s2, 0, j - hj, j + hj + 1, i - hi, i + hi + 1, qn, me, xb);
+        d = s2.Pmin < INFINITY ? sqrtf(s2.Pmin) : INFINITY;
+    }
+    if (lane == 0) {
+        float wc = (d - 5.0e-7f) * (1.0f - 1.0e-6f);
+        if (!(wc > 0.0f)) wc = 0.0f;
+        unsigned slot = weak_hash(key) & mask;
+        for (;;) {
+            const unsigned old = atomicCAS(&table[slot].x, WEAK_NONE, key);
+            if (old == WEAK_NONE) break;
+            slot = (slot + 1) & mask;
+        }
+        table[slot].y = portal;
+        table[slot].z = __float_as_uint(wc);
+        table[slot].w = (unsigned)hj | ((unsigned)hi << 8);
+    }
+}
+
+// after k_cellcert (gzb_grid.cu): list the weak cells, size the table, fill it.  Not fatal when memory is short or the
+// grid is mostly weak (> 1/8 of the cells): the warp-cooperative search takes the points as before.
+int gzb_build_weak(gzb_ctx* ctx) {
+    GzbGrid& g = ctx->g;
+    g.weak = nullptr;
+    g.weak_mask = 0;
+    if (!g.cellv || getenv("GZB_NO_WEAK_TABLE")) return GZB_OK;
+    const long long cells = g.Nj * g.Ni;
+    if (cells >= 0xfffffff0LL) return GZB_OK;
+    const unsigned cap = (unsigned)(cells / 8 + 1024);
+    if (gzb_pool_malloc((void**)&ctx->d_weak_list, ((size_t)cap + 4) * sizeof(unsigned)) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->d_weak_list = nullptr;
+        return GZB_OK;
+    }
+    unsigned* count = ctx->d_weak_list + cap;
+    cudaStream_t s = ctx->stream;
+    GZB_CUDA(ctx, cudaMemsetAsync(count, 0, 4 * sizeof(unsigned), s));
+    k_weak_mark<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(g, ctx->d_weak_list, count, cap);
+    GZB_LAUNCH_CHECK(ctx);
+    unsigned* h_n = (unsigned*)((char*)ctx->pinned + 384);
+    GZB_CUDA(ctx, cudaMemcpyAsync(h_n, count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    GZB_CUDA(ctx, cudaStreamSynchronize(s));
+    const unsigned n = *h_n;
+    ctx->stats.weak_cells = (int64_t)n;
+    if (n == 0 || n > cap) return GZB_OK;
+    unsigned size = 1024;
+    while (size < 2u * n) size <<= 1;
+    if (gzb_pool_malloc((void**)&ctx->d_weak, (size_t)size * sizeof(uint4)) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->d_weak = nullptr;
+        return GZB_OK;
+    }
+    GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_weak, 0xff, (size_t)size * sizeof(uint4), s));
+    k_weak_build<<<(n + 3) / 4, 128, 0, s>>>(g, ctx->d_weak_list, count, cap, ctx->d_weak, size - 1);
+    GZB_LAUNCH_CHECK(ctx);
+    g.weak = ctx->d_weak;
+    g.weak_mask = size - 1;
     return GZB_OK;
 }
 
@@ -987,7 +1217,11 @@ __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned*
 // A thread owns CH_PPT consecutive points (one composed map per thread goes through the block scan; a
 // 10-day track is ~600 blocks: one wave).  Blocks take their index from a ticket, so a block only ever
 // waits for blocks that already started.
+#ifdef GZB_CH_PPT
+#define CH_PPT GZB_CH_PPT
+#else
 #define CH_PPT 4
+#endif
 #define CH_PTS (FLAGS_BLOCK * CH_PPT)
 __global__ void __launch_bounds__(FLAGS_BLOCK)
 k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,

@@ -53,6 +53,7 @@ typedef struct gzb_stats {
     int64_t  last_unres_nocert; /*   ... per-cell certificate not sufficient                  */
     int64_t  last_max_chain;    /* last gzb_nearest: longest sequential replay (steps)         */
     int64_t  heading_table;     /* 1 once the per-cell heading table of K2 has been built       */
+    int64_t  weak_cells;        /* grid cells in the weak-cell table of the per-thread search (0: none / not built) */
 } gzb_stats;
 
 const char* gzb_version(void);
