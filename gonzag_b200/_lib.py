@@ -92,6 +92,7 @@ _SIGNATURES = {
     "gzb_pool_trim": (C.c_int, []),
     "gzb_pool_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gzb_peer_barrier": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, _I64]),
+    "gzb_peer_finish": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P, _P, C.c_int, C.c_int, _I64, _P, _I64, _I64, _P]),
     "gzb_check_edges": (C.c_int, [_P, _P, _I64, _I64, C.c_int, _P]),
     "gzb_pack_mask": (C.c_int, [_P, C.c_int, _I64, _P]),
     "gzb_track_mask": (C.c_int, [_P, _I64, _P, _P, _P, _P]),

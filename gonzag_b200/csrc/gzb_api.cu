@@ -24,6 +24,7 @@ int gzb_interp_dev(gzb_ctx* ctx, int64_t nt, const double* t, const int64_t* sm,
                    const double* tmod, const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss,
                    double* np_out, double* bl_out, const long long* list, const unsigned long long* count);
 int gzb_slab_device_pointer(const void* slab, const void** dev_out, int* is_host);
+int gzb_push_join(gzb_ctx* ctx);
 
 int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
                                 const GzbGlobalNearest* gn_or_null, int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
@@ -184,8 +185,9 @@ extern "C" int gzb_mesh_weights_interp(gzb_ctx* ctx, int64_t nt, const double* y
                         "(gzb_host_alloc / gzb_host_register)", who);
     if (slab_is_host) ctx->stats.h2d_bytes += (uint64_t)nt * 8 * 32;
     ctx->pf_now = ctx->prefetch && !slab_is_host;
-    return gzb_mesh_weights_interp_dev(ctx, nt, yt, xt, np, nullptr, sm_out, wb_out, tt, nrec, tmod, slab_dev, dtype, k0, nk,
-                                       rmissval, vnp_out, vbl_out);
+    const int rc = gzb_mesh_weights_interp_dev(ctx, nt, yt, xt, np, nullptr, sm_out, wb_out, tt, nrec, tmod, slab_dev, dtype, k0, nk,
+                                               rmissval, vnp_out, vbl_out);
+    return rc != GZB_OK ? rc : gzb_push_join(ctx);
 }
 
 // K1 + K2 + K3 + K4 in one call, device-resident track.  The chain replays of K1 (a few long
@@ -239,6 +241,7 @@ extern "C" int gzb_map_interp(gzb_ctx* ctx, int64_t nt, const double* yt, const 
                                    dtype, k0, nk,
                                    rmissval, vnp_out, vbl_out)) != GZB_OK) return rc;
     }
+    if ((rc = gzb_push_join(ctx)) != GZB_OK) return rc;      // (no repair kernel ran: nothing joined the chunk copies yet)
     gzb_trace(ctx, s, "path end (main)");
     return GZB_OK;
 }

@@ -111,6 +111,10 @@ struct gzb_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaStream_t aux_stream = nullptr;     // chain part of K1 while K2+K3 run on `stream` (gzb_mapping)
+    cudaStream_t push_stream = nullptr;    // copies of finished chunks of the two series into the peers' buffers (k_push)
+    cudaEvent_t ev_push[9] = {};           // chunk c of the bulk kernel done (0..7); all pushes done (8)
+    int push_pending = 0;                  // pushes of the last bulk call are in flight on push_stream (ev_push[8] marks their end)
+    int bulk_chunks = 0;                   // option "bulk_chunks": 0 = automatic (1 alone, 4 with peer outputs), else 1..8
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};
     GzbPeerOut peer_out = {0, {}, {}};   // gzb_set_peer_outputs: where K4 also writes its two series
     double* peer_local_np = nullptr;     // ... when its local outputs are these buffers

@@ -857,6 +857,8 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
 #define CK(call) if ((e = (call)) != cudaSuccess) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
         CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->push_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 9; ++k) CK(cudaEventCreateWithFlags(&ctx->ev_push[k], cudaEventDisableTiming));
         {   // the chain part of K1 is latency-bound and small: it must get SM slots ahead of the bulk kernels
             int least = 0, greatest = 0;
             CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -928,6 +930,7 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     if (ctx->stream && ctx->stream != ctx->own_stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->push_stream) cudaStreamSynchronize(ctx->push_stream);
     gzb_pool_free(ctx->d_lat);
     gzb_pool_free(ctx->d_lon);
     gzb_pool_free(ctx->d_ll);
@@ -953,6 +956,8 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->push_stream) cudaStreamDestroy(ctx->push_stream);
+    for (int k = 0; k < 9; ++k) if (ctx->ev_push[k]) cudaEventDestroy(ctx->ev_push[k]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     for (int k = 0; k < 2; ++k)
         if (ctx->ev_k1[k]) cudaEventDestroy(ctx->ev_k1[k]);
@@ -1048,6 +1053,7 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "twin_chain")) { ctx->twin_chain = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "fuse_k4")) { ctx->fuse_k4 = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "overlap")) { ctx->overlap = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "bulk_chunks")) { ctx->bulk_chunks = value < 0 ? 0 : (value > 8 ? 8 : (int)value); return GZB_OK; }
     if (!strcmp(name, "k4_early")) { ctx->k4_early = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "pdl")) { ctx->pdl = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "prefetch")) { ctx->prefetch = value < 0 ? 0 : (value > 3 ? 3 : (int)value); return GZB_OK; }
@@ -1307,6 +1313,62 @@ extern "C" int gzb_peer_barrier(gzb_ctx* ctx, int n, void* const* peer_slots, vo
     for (int k = 0; k < n; ++k) d.p[k] = (long long*)peer_slots[k];
     k_peer_barrier<<<1, 32, 0, ctx->stream>>>(d, n, (volatile long long*)local_bar, world, my_rank, (long long)epoch,
                                              ctx->d_flags + 3);
+    GZB_LAUNCH_CHECK(ctx);
+    ctx->barrier_err_pending = 1;
+    return GZB_OK;
+}
+
+// The end of a sharded step in ONE kernel (instead of edge publication + barrier + boundary check as three launches, one
+// of them a collective): (1) this rank's 4 edge words -- first and last row of its (nrows, 2) nearest-point array: the halo
+// assumption and the segment's last nearest point -- go to its own gathered buffer and to every peer's; (2) barrier over peer
+// memory as k_peer_barrier: after it every rank's series (stored by K4 / the push kernels over NVLink) and edge words are
+// visible in this rank's buffer; (3) *flag |= 1 if some segment's halo assumption differs from the last nearest point of
+// the segment before it.
+__global__ void k_peer_finish(const long long* __restrict__ rows, const long long nrows, const int nedge, const GzbEdgeDst ed,
+                              const GzbBarDst bd, const int nbar, volatile long long* local_bar, const int world,
+                              const int my_rank, const long long epoch, const long long* edges, const long long stride,
+                              const long long offset, int* __restrict__ flag, int* __restrict__ err) {
+    const int t = threadIdx.x;
+    {
+        const int k = t >> 2, w = t & 3;
+        if (k < nedge) ed.p[k][w] = (w < 2) ? rows[w] : rows[2 * (nrows - 1) + (w - 2)];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < nbar) *(volatile long long*)bd.p[t] = epoch;
+    __threadfence_system();
+    if (t < world && t != my_rank) {
+        const long long start = clock64();
+        while (local_bar[t] < epoch) {
+            if (clock64() - start > 8000000000LL) { atomicOr(err, 2); break; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    const int g = t + 1;
+    if (g < world && flag) {
+        const volatile long long* cur = edges + (long long)g * stride + offset;
+        const volatile long long* prv = edges + (long long)(g - 1) * stride + offset;
+        if (cur[0] != prv[2] || cur[1] != prv[3]) atomicOr(flag, 1);
+    }
+}
+
+extern "C" int gzb_peer_finish(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int nedge, void* const* edge_dst, int nbar,
+                               void* const* peer_slots, void* local_bar, int world, int my_rank, int64_t epoch,
+                               const int64_t* gathered, int64_t stride_words, int64_t offset_words, int* flag_dev_or_null) {
+    if (!ctx || !np_rows || nrows < 1 || nedge < 0 || nedge > GZB_MAX_PEERS + 1 || (nedge > 0 && !edge_dst) || nbar < 0 ||
+        nbar > GZB_MAX_PEERS || world < 1 || world > GZB_MAX_PEERS + 1 || !local_bar || (nbar > 0 && !peer_slots) || !gathered)
+        return gzb_fail(ctx, GZB_ERR_ARG, "gzb_peer_finish: bad arguments");
+    if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
+    GzbEdgeDst ed;
+    GzbBarDst bd;
+    for (int k = 0; k < nedge; ++k) ed.p[k] = (long long*)edge_dst[k];
+    for (int k = 0; k < nbar; ++k) bd.p[k] = (long long*)peer_slots[k];
+    k_peer_finish<<<1, 4 * (GZB_MAX_PEERS + 1), 0, ctx->stream>>>((const long long*)np_rows, nrows, nedge, ed, bd, nbar,
+                                                                  (volatile long long*)local_bar, world, my_rank, (long long)epoch,
+                                                                  (const long long*)gathered, stride_words, offset_words,
+                                                                  flag_dev_or_null, ctx->d_flags + 3);
     GZB_LAUNCH_CHECK(ctx);
     ctx->barrier_err_pending = 1;
     return GZB_OK;

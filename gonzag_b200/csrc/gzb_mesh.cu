@@ -399,10 +399,10 @@ __device__ __forceinline__ void prefetch_point(const GzbGrid& g, const long long
 #endif
 template <typename T, int PF>      // PF: 0 plain, 1 L2 prefetch of the gather, 3 gather with 64-byte L2 fetches
 __global__ void GZB_BULK_BOUNDS             // 86 registers; capping it at 64 (more warps, some spills) measured 3 % slower
-k_mesh_weights_interp(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
-                      const long long* __restrict__ NP, const GzbGlobalNearest gn, long long* __restrict__ SM,
-                      double* __restrict__ WB, const int force_heavy, const InterpArgs ia) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+k_mesh_weights_interp(const GzbGrid g, const long long t_first, const long long nt, const double* __restrict__ yt,
+                      const double* __restrict__ xt, const long long* __restrict__ NP, const GzbGlobalNearest gn,
+                      long long* __restrict__ SM, double* __restrict__ WB, const int force_heavy, const InterpArgs ia) {
+    const long long t = t_first + (long long)blockIdx.x * blockDim.x + threadIdx.x;      // this launch: points [t_first, nt)
     if (t >= nt) return;
     const double yT = yt[t], xT = xt[t];
     long long cj[4], ci[4], jP, iP;
@@ -437,6 +437,40 @@ static void fill_interp_args(gzb_ctx* ctx, InterpArgs& ia, const double* tt, int
     if (ctx->peer_out.n > 0 && vnp_out == ctx->peer_local_np && vbl_out == ctx->peer_local_bl) ia.peers = ctx->peer_out;
 }
 
+// The two series of points [a, b), just written by a bulk launch, into every registered peer buffer: the gather of a
+// sharded step, issued chunk by chunk on its own stream so that the NVLink stores of chunk c travel while the bulk kernel
+// works on chunk c+1 (the same stores issued from inside the bulk kernel throttle it: +120 us per step at 8 GPUs).
+__global__ void __launch_bounds__(256)
+k_push(const double* __restrict__ np_loc, const double* __restrict__ bl_loc, const GzbPeerOut peers, const long long a,
+       const long long b) {
+    for (long long t = a + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < b; t += (long long)gridDim.x * blockDim.x) {
+        const double v = np_loc[t], w = bl_loc[t];
+        for (int k = 0; k < peers.n; ++k) {
+            peers.np[k][t] = v;
+            peers.bl[k][t] = w;
+        }
+    }
+}
+
+// ... and the points the repair kernel rewrote afterwards (two device-side lists)
+__global__ void __launch_bounds__(128)
+k_push_list(const double* __restrict__ np_loc, const double* __restrict__ bl_loc, const GzbPeerOut peers,
+            const long long* __restrict__ list, const unsigned long long* __restrict__ count,
+            const long long* __restrict__ list2, const unsigned long long* __restrict__ count2) {
+    const long long n1 = (long long)*count;
+    const long long n = n1 + (list2 ? (long long)*count2 : 0);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long t = e < n1 ? list[e] : list2[e - n1];
+        const double v = np_loc[t], w = bl_loc[t];
+        for (int k = 0; k < peers.n; ++k) {
+            peers.np[k][t] = v;
+            peers.bl[k][t] = w;
+        }
+    }
+}
+
+int gzb_push_join(gzb_ctx* ctx);
+
 int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* np,
                                 const GzbGlobalNearest* gn_or_null, int64_t* sm_out, double* wb_out, const double* tt, int64_t nrec, const double* tmod,
                                 const void* slab_dev, int dtype, int64_t k0, int64_t nk, double rmiss, double* vnp_out,
@@ -445,17 +479,38 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
     InterpArgs ia;
     fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
-    const unsigned nblk = (unsigned)((nt + 127) / 128);
+    const GzbPeerOut peers = ia.peers;
+    // with peer outputs the bulk kernel writes locally only and runs in chunks; k_push copies each finished chunk
+    int nchunk = ctx->bulk_chunks > 0 ? ctx->bulk_chunks : (peers.n > 0 ? 4 : 1);
+    if (nt < 4096 * nchunk) nchunk = 1;
+    const bool push = peers.n > 0;
+    if (push) ia.peers.n = 0;
     GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0, nullptr, nullptr};
     const long long* npp = (const long long*)np;
     if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
-#define GZB_BULK(T, PF) k_mesh_weights_interp<T, PF><<<nblk, 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out, \
-                                                                                   wb_out, ctx->force_heavy, ia)
     const int pfm = !ctx->pf_now ? 0 : (ctx->prefetch == 3 ? 3 : 1);
-    if (dtype == GZB_F32) { if (pfm == 3) GZB_BULK(float, 3); else if (pfm) GZB_BULK(float, 1); else GZB_BULK(float, 0); }
-    else                  { if (pfm == 3) GZB_BULK(double, 3); else if (pfm) GZB_BULK(double, 1); else GZB_BULK(double, 0); }
+    cudaStream_t s = ctx->stream;
+    for (int c = 0; c < nchunk; ++c) {
+        const long long a = ((nt * c / nchunk) + 127) & ~127LL, b = c + 1 == nchunk ? nt : (((nt * (c + 1) / nchunk) + 127) & ~127LL);
+        if (b <= a) continue;
+        const unsigned nblk = (unsigned)((b - a + 127) / 128);
+#define GZB_BULK(T, PF) k_mesh_weights_interp<T, PF><<<nblk, 128, 0, s>>>(ctx->g, a, b, yt, xt, npp, gn, (long long*)sm_out, \
+                                                                         wb_out, ctx->force_heavy, ia)
+        if (dtype == GZB_F32) { if (pfm == 3) GZB_BULK(float, 3); else if (pfm) GZB_BULK(float, 1); else GZB_BULK(float, 0); }
+        else                  { if (pfm == 3) GZB_BULK(double, 3); else if (pfm) GZB_BULK(double, 1); else GZB_BULK(double, 0); }
 #undef GZB_BULK
-    GZB_LAUNCH_CHECK(ctx);
+        GZB_LAUNCH_CHECK(ctx);
+        if (push) {
+            GZB_CUDA(ctx, cudaEventRecord(ctx->ev_push[c], s));
+            GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->push_stream, ctx->ev_push[c], 0));
+            k_push<<<64, 256, 0, ctx->push_stream>>>(vnp_out, vbl_out, peers, a, b);
+            GZB_LAUNCH_CHECK(ctx);
+        }
+    }
+    if (push) {      // the caller joins the copies (gzb_push_join): the repair kernel runs beside the last of them
+        GZB_CUDA(ctx, cudaEventRecord(ctx->ev_push[8], ctx->push_stream));
+        ctx->push_pending = 1;
+    }
     ctx->time_err_pending = 1;
     return GZB_OK;
 }
@@ -468,10 +523,26 @@ int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int
                      double rmiss, double* vnp_out, double* vbl_out) {
     InterpArgs ia;
     fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
+    const GzbPeerOut peers = ia.peers;
+    const bool joined = ctx->push_pending && peers.n > 0;
+    if (joined) ia.peers.n = 0;       // chunk copies in flight: repair locally beside them, then copy the repaired points
     k_path_fix<<<192, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
                                            list2, count2, ctx->force_heavy, ia);
     GZB_LAUNCH_CHECK(ctx);
+    if (joined) {
+        if (gzb_push_join(ctx) != GZB_OK) return GZB_ERR_CUDA;
+        k_push_list<<<32, 128, 0, ctx->stream>>>(vnp_out, vbl_out, peers, list, count, list2, count2);
+        GZB_LAUNCH_CHECK(ctx);
+    }
     if (slab_dev) ctx->time_err_pending = 1;
+    return GZB_OK;
+}
+
+// the main stream waits for the chunk copies of the last bulk call (no-op when there are none)
+int gzb_push_join(gzb_ctx* ctx) {
+    if (!ctx->push_pending) return GZB_OK;
+    ctx->push_pending = 0;
+    GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_push[8], 0));
     return GZB_OK;
 }
 

@@ -575,7 +575,7 @@ __device__ __forceinline__ int fast_ring(const GzbGrid& g, const float px, const
 // returns the first-index argmin and its distance bits
 __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long long c, const double lat, const double lon,
                                                 const float px, const float py, const float pz, long long& bf,
-                                                unsigned long long& bd) {
+                                                unsigned long long& bd, const float Pbest = -1.0f /* >= 0: chord^2 of the best cell */) {
     bf = GZB_NOFLAT;
     bd = ~0ull;
     if (c & CAND_NONE) return;
@@ -591,9 +591,13 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
     const long long j = f0 / g.Ni, i = f0 - j * g.Ni;
     float B2;
     {
-        const float4 v = __ldg(g.cellv + f0);
-        const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
-        const float a = sqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)));
+        float P0 = Pbest;
+        if (P0 < 0.0f) {
+            const float4 v = __ldg(g.cellv + f0);
+            const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+            P0 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+        }
+        const float a = sqrtf(P0);
         const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
         B2 = B * B;
     }
@@ -639,6 +643,78 @@ __device__ __forceinline__ float cell_chord(const float4 a, const float4 b) {
     return sqrtf(dx * dx + dy * dy + dz * dz);
 }
 
+// all 25 cells of the 5x5 neighbourhood of (j, i), bounds-checked, loads issued back to back: chord^2 of the centre,
+// smallest chord^2 among the other 24 and where it sits
+__device__ __forceinline__ void eval25(const GzbGrid& g, const int j, const int i, const float px, const float py,
+                                       const float pz, float& Pc, float& nbest, int& bj, int& bi) {
+    const float4* __restrict__ c0 = g.cellv + ((long long)j * g.Ni + i);
+    float nb = INFINITY;
+    int mj = 0, mi = 0;
+#define W5(DJ, DI) FAST_UPD((fast_cell<true, DJ, DI>(g, c0, j, i, px, py, pz)), DJ, DI)
+    W5(-2, -2) W5(-2, -1) W5(-2, 0) W5(-2, 1) W5(-2, 2) W5(-1, -2) W5(-1, -1) W5(-1, 0) W5(-1, 1) W5(-1, 2)
+    W5(0, -2) W5(0, -1) W5(0, 1) W5(0, 2) W5(1, -2) W5(1, -1) W5(1, 0) W5(1, 1) W5(1, 2)
+    W5(2, -2) W5(2, -1) W5(2, 0) W5(2, 1) W5(2, 2)
+#undef W5
+    Pc = fast_cell<true, 0, 0>(g, c0, j, i, px, py, pz);
+    nbest = nb;
+    bj = j + mj;
+    bi = i + mi;
+}
+
+// A point whose climb ended on a cell with (near-)copies elsewhere in index space (duplicated East-West columns, a
+// folded row): follow the table's portals.  At every stop: walk to the local minimum of the 5x5 neighbourhoods; if the
+// cell's own certificate holds, done; else look at the 5x5 neighbourhood of its portal -- something nearer there: hop
+// over and go on; nothing nearer and the table's certificate (everything outside the two neighbourhoods) holds: done,
+// candidates of both neighbourhoods through the reference's fp64 formula, lexicographic minimum (distance bits, flat
+// index) == numpy.argmin's first occurrence.  false: left to the warp search.
+__device__ __noinline__ bool weak_settle(const GzbGrid& g, const unsigned flat0, const double lat, const double lon,
+                                         const float px, const float py, const float pz, long long& bf,
+                                         unsigned long long& bd, unsigned& last) {
+    int j = (int)(flat0 / (unsigned)g.Ni), i = (int)(flat0 - (unsigned)j * (unsigned)g.Ni);
+    for (int hop = 0; hop < 4; ++hop) {
+        float Pc = 0.0f, nb = 0.0f;
+        int bj = j, bi = i, it = 0;
+        for (; it < 12; ++it) {
+            eval25(g, j, i, px, py, pz, Pc, nb, bj, bi);
+            if (!(nb < Pc)) break;
+            j = bj;
+            i = bi;
+        }
+        const unsigned f = (unsigned)j * (unsigned)g.Ni + (unsigned)i;
+        last = f;
+        if (it >= 12) return false;
+        const float a = sqrtf(Pc);
+        const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
+        const float w5 = __uint_as_float(__float_as_uint(__ldg(g.cellv + f).w) << 16);
+        if ((w5 - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
+            exact_from_cand(g, (long long)f | CAND_MULTI, lat, lon, px, py, pz, bf, bd, Pc);
+            return true;
+        }
+        uint4 e;
+        if (!weak_lookup(g, f, e) || e.y == WEAK_NONE) return false;
+        const int pj = (int)(e.y / (unsigned)g.Ni), pi = (int)(e.y - (unsigned)pj * (unsigned)g.Ni);
+        float Pp = 0.0f, nbp = 0.0f;
+        int qj = pj, qi = pi;
+        eval25(g, pj, pi, px, py, pz, Pp, nbp, qj, qi);
+        if (Pp <= nbp) { nbp = Pp; qj = pj; qi = pi; }
+        if (nbp < Pc) {          // nearer on the other side: go on from there
+            j = qj;
+            i = qi;
+            continue;
+        }
+        if ((__uint_as_float(e.z) - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
+            long long bf2;
+            unsigned long long bd2;
+            exact_from_cand(g, (long long)f | CAND_MULTI, lat, lon, px, py, pz, bf, bd, Pc);
+            exact_from_cand(g, (long long)e.y | CAND_MULTI, lat, lon, px, py, pz, bf2, bd2, Pc);
+            if (bd2 < bd || (bd2 == bd && bf2 < bf)) { bd = bd2; bf = bf2; }
+            return true;
+        }
+        return false;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(128, 8)
 k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
               long long* __restrict__ G, double* __restrict__ dG, long long* __restrict__ ulist,
@@ -669,12 +745,13 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
             }
             const unsigned seed = __ldg(g.lut.bins + gzb_lut_bin(g.lut, lat, lon));
             int reason = 1;      // 1 no seed, 2 not converged, 3 not proven
+            float Pc = 0.0f;     // chord^2 (fp32 proxy) of the cell the climb converged to
             if (seed != 0xffffffffu) {
                 int j = (int)(seed / (unsigned)g.Ni);
                 int i = (int)(seed - (unsigned)j * (unsigned)g.Ni);
                 const unsigned nj4 = g.Nj > 4 ? (unsigned)(g.Nj - 4) : 0u, ni4 = g.Ni > 4 ? (unsigned)(g.Ni - 4) : 0u;
                 const unsigned nj2 = (unsigned)(g.Nj - 2), ni2 = (unsigned)(g.Ni - 2);     // Nj, Ni >= 3
-                float Pc = 0.0f, cw = 0.0f, nb8 = INFINITY, ring = INFINITY;
+                float cw = 0.0f, nb8 = INFINITY, ring = INFINITY;
                 bool conv = false, proven3 = false;
                 int moves = 0;
                 for (;;) {
@@ -724,74 +801,16 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
             }
             bool settled = false;
             if (reason == 3 && g.weak) {
-                // a weak cell (anisotropic, or next to duplicated columns): scan its box and its portal's neighbourhood
-                // instead of 5x5; move while something there is strictly nearer; prove with the table's certificate
-                int jj = (int)(myhint / (unsigned)g.Ni), ii = (int)(myhint - (unsigned)jj * (unsigned)g.Ni);
-                float Pcc;
-                {
-                    const float4 v = __ldg(g.cellv + myhint);
-                    const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
-                    Pcc = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                long long bfw;
+                unsigned long long bdw;
+                unsigned last = myhint;
+                if (weak_settle(g, myhint, lat, lon, px, py, pz, bfw, bdw, last)) {
+                    G[t] = bfw;
+                    dG[t] = __longlong_as_double((long long)bdw);
+                    settled = true;
+                    reason = 0;
                 }
-                for (int att = 0; att < 6; ++att) {
-                    uint4 e;
-                    if (!weak_lookup(g, (unsigned)jj * (unsigned)g.Ni + (unsigned)ii, e)) break;
-                    const int hj = (int)(e.w & 0xffu), hi = (int)((e.w >> 8) & 0xffu);
-                    int pj = -1000, pi = -1000;
-                    if (e.y != WEAK_NONE) { pj = (int)(e.y / (unsigned)g.Ni); pi = (int)(e.y - (unsigned)pj * (unsigned)g.Ni); }
-                    const int ja = max(jj - hj, 0), jb = min(jj + hj, (int)g.Nj - 1);
-                    const int ia = max(ii - hi, 0), ib = min(ii + hi, (int)g.Ni - 1);
-                    const int qa = max(pj - 2, 0), qb = min(pj + 2, (int)g.Nj - 1);
-                    const int ra = max(pi - 2, 0), rb = min(pi + 2, (int)g.Ni - 1);
-                    float best = Pcc;
-                    int bj = jj, bi = ii;
-                    for (int part = 0; part < (e.y != WEAK_NONE ? 2 : 1); ++part) {
-                        const int j0 = part ? qa : ja, j1 = part ? qb : jb, i0 = part ? ra : ia, i1 = part ? rb : ib;
-                        for (int row = j0; row <= j1; ++row) {
-                            const float4* __restrict__ rp = g.cellv + (long long)row * g.Ni;
-                            for (int col = i0; col <= i1; ++col) {
-                                const float4 v = __ldg(rp + col);
-                                const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
-                                const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-                                if (P < best) { best = P; bj = row; bi = col; }
-                            }
-                        }
-                    }
-                    if (bj != jj || bi != ii) { jj = bj; ii = bi; Pcc = best; continue; }
-                    const float a = sqrtf(Pcc);
-                    const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
-                    if ((__uint_as_float(e.z) - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
-                        // proven: the reference's fp64 formula on every cell of the region within the fp32 margin;
-                        // lexicographic minimum (distance bits, flat index) == numpy.argmin's first occurrence
-                        const float B2 = B * B;
-                        const double cpl = cos(lat * GZB_D2R);
-                        unsigned long long bd = ~0ull;
-                        long long bf = GZB_NOFLAT;
-                        for (int part = 0; part < (e.y != WEAK_NONE ? 2 : 1); ++part) {
-                            const int j0 = part ? qa : ja, j1 = part ? qb : jb, i0 = part ? ra : ia, i1 = part ? rb : ib;
-                            for (int row = j0; row <= j1; ++row) {
-                                for (int col = i0; col <= i1; ++col) {
-                                    const long long fl = (long long)row * g.Ni + col;
-                                    const float4 v = __ldg(g.cellv + fl);
-                                    const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
-                                    const float P = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-                                    if (!(P <= B2)) continue;
-                                    const double2 cf = __ldg(g.ll + fl);
-                                    const double d = gzb_haversine_dev(lat, lon, cpl, cf.x, cf.y);
-                                    if (!(d == d)) continue;
-                                    const unsigned long long db = (unsigned long long)__double_as_longlong(d);
-                                    if (db < bd || (db == bd && fl < bf)) { bd = db; bf = fl; }
-                                }
-                            }
-                        }
-                        G[t] = bf;
-                        dG[t] = __longlong_as_double((long long)bd);
-                        settled = true;
-                        reason = 0;
-                    }
-                    break;
-                }
-                myhint = (unsigned)jj * (unsigned)g.Ni + (unsigned)ii;
+                myhint = last;
             }
             if (reason) {
                 unresolved = true;
@@ -928,15 +947,16 @@ int gzb_build_cert(gzb_ctx* ctx) {
 }
 
 // ------------------------------------------------------------------------------------------
-// WEAK cells: cells whose 5x5 certificate is too small for the targets that belong to them -- strongly anisotropic
-// cells (converging meridians near a displaced grid pole: the nearest cells in space are many columns away) and cells
-// next to duplicated / folded columns (the East-West overlap: a copy of the neighbourhood sits at the other end of the
-// row).  Found from the coordinates alone (nothing here trusts k_ew_per).  For each of them the table holds
-//   (hj, hi)   half-widths of an index box around the cell that reaches ~1.8 x its largest spacing in both directions,
-//   portal     the nearest cell OUTSIDE that box when it is closer than that (the copy at the other end), else none,
-//   wcert      a lower bound of the chord from the cell to any cell outside  box U 5x5(portal).
-// k_near_search scans box U 5x5(portal) for such a cell instead of 5x5 and settles the point itself; what is left
-// for the warp-cooperative search are the cells where even that is not enough (pole rows, |ratio| > 1:13).
+// WEAK cells: cells that have a (near-)copy outside their 5x5 index neighbourhood -- the duplicated East-West overlap
+// columns of a global grid (a copy of the whole neighbourhood sits at the other end of the row), a folded row.  Their
+// 5x5 certificate is ~0, so every track point next to the seam used to go to the warp-cooperative search (0.7 % of a
+// Jason-like track: the whole of k_near_slow's 26 us).  Found from the coordinates alone (nothing here trusts k_ew_per).
+// For each of them the table holds
+//   portal     the nearest cell outside the 5x5 neighbourhood (the copy at the other end),
+//   wcert      a lower bound of the chord from the cell to any cell outside  5x5(cell) U 5x5(portal).
+// k_near_search looks at 5x5(portal) as well for such a cell and settles the point itself.  (A table with wider index
+// boxes for strongly anisotropic cells was tried in round 2: its build cost 8 ms per ORCA12 context and the per-thread
+// scans made k_near_search 2x slower on polar tracks -- those points stay with the warp search.)
 // thread per cell: weak iff the 5x5 certificate is below 1.5 x the largest chord to a direct neighbour
 __global__ void __launch_bounds__(256)
 k_weak_mark(const GzbGrid g, unsigned* __restrict__ list, unsigned* __restrict__ count, const unsigned cap) {
@@ -950,7 +970,7 @@ k_weak_mark(const GzbGrid g, unsigned* __restrict__ list, unsigned* __restrict__
     if (j > 0) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k - g.Ni)));
     if (j + 1 < g.Nj) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k + g.Ni)));
     const float w5 = __uint_as_float(__float_as_uint(c.w) << 16);
-    if (w5 < 1.5f * s) {
+    if (s > 0.0f && w5 < 0.05f * s) {      // something outside the 5x5 neighbourhood is (nearly) on top of the cell
         const unsigned pos = atomicAdd(count, 1u);
         if (pos < cap) list[pos] = (unsigned)k;
     }
@@ -968,16 +988,13 @@ k_weak_build(const GzbGrid g, const unsigned* __restrict__ list, const unsigned*
     const unsigned key = list[e];
     const long long j = key / g.Ni, i = key - j * g.Ni;
     const float4 c = __ldg(g.cellv + key);
-    float dxa = 0.0f, dxb = INFINITY, dya = 0.0f, dyb = INFINITY;      // largest / smallest spacing along i and along j
-    if (i > 0) { const float d = cell_chord(c, __ldg(g.cellv + key - 1)); dxa = fmaxf(dxa, d); dxb = fminf(dxb, d); }
-    if (i + 1 < g.Ni) { const float d = cell_chord(c, __ldg(g.cellv + key + 1)); dxa = fmaxf(dxa, d); dxb = fminf(dxb, d); }
-    if (j > 0) { const float d = cell_chord(c, __ldg(g.cellv + key - g.Ni)); dya = fmaxf(dya, d); dyb = fminf(dyb, d); }
-    if (j + 1 < g.Nj) { const float d = cell_chord(c, __ldg(g.cellv + key + g.Ni)); dya = fmaxf(dya, d); dyb = fminf(dyb, d); }
-    const float R = 1.8f * fmaxf(dxa, dya);
-    int hi = (dxb > 0.0f && dxb < INFINITY) ? (int)fminf(ceilf(R / dxb), (float)WEAK_HMAX) : WEAK_HMAX;
-    int hj = (dyb > 0.0f && dyb < INFINITY) ? (int)fminf(ceilf(R / dyb), (float)WEAK_HMAX) : WEAK_HMAX;
-    hi = hi < 2 ? 2 : hi;
-    hj = hj < 2 ? 2 : hj;
+    float smax = 0.0f;      // largest spacing to a direct neighbour
+    if (i > 0) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key - 1)));
+    if (i + 1 < g.Ni) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key + 1)));
+    if (j > 0) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key - g.Ni)));
+    if (j + 1 < g.Nj) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key + g.Ni)));
+    const float R = smax;
+    const int hi = 2, hj = 2;
     Owner me;
     me.plat = me.plon = me.cpl = 0.0;
     int qn = 0;
@@ -986,7 +1003,7 @@ k_weak_build(const GzbGrid g, const unsigned* __restrict__ list, const unsigned*
     pyramid_search<M_EXCL>(g, ws[warp], lane, s, 0, j - hj, j + hj + 1, i - hi, i + hi + 1, qn, me);
     float d = s.Pmin < INFINITY ? sqrtf(s.Pmin) : INFINITY;
     unsigned portal = WEAK_NONE;
-    if (d < 0.9f * R && s.bflat >= 0) {
+    if (d < 0.05f * R && s.bflat >= 0) {
         portal = (unsigned)s.bflat;
         const long long pj = s.bflat / g.Ni, pi = s.bflat - pj * g.Ni;
         long long xb[4] = {pj - 2, pj + 3, pi - 2, pi + 3};
@@ -1223,7 +1240,12 @@ __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned*
 #define CH_PPT 4
 #endif
 #define CH_PTS (FLAGS_BLOCK * CH_PPT)
-__global__ void __launch_bounds__(FLAGS_BLOCK)
+#ifdef GZB_CH_MINB
+#define CH_BOUNDS __launch_bounds__(FLAGS_BLOCK, GZB_CH_MINB)
+#else
+#define CH_BOUNDS __launch_bounds__(FLAGS_BLOCK)
+#endif
+__global__ void CH_BOUNDS
 k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
         const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
         long long* __restrict__ NP, long long* __restrict__ breaks, long long* __restrict__ blist, int* __restrict__ bcount,

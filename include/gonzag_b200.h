@@ -279,6 +279,12 @@ int gzb_publish_edges(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int n
  * peer that does not arrive within ~4 s is reported by the next gzb_sync (GZB_ERR_STATE). */
 int gzb_peer_barrier(gzb_ctx* ctx, int n, void* const* peer_slots, void* local_bar, int world, int my_rank,
                      int64_t epoch);
+/* The end of a sharded step in ONE kernel: gzb_publish_edges (np_rows / nrows / nedge / edge_dst), then gzb_peer_barrier
+ * (nbar / peer_slots / local_bar / world / my_rank / epoch), then gzb_check_edges on this rank's gathered buffer
+ * (gathered / stride_words / offset_words / flag_dev, which may be NULL: no check). */
+int gzb_peer_finish(gzb_ctx* ctx, const int64_t* np_rows, int64_t nrows, int nedge, void* const* edge_dst, int nbar,
+                    void* const* peer_slots, void* local_bar, int world, int my_rank, int64_t epoch,
+                    const int64_t* gathered, int64_t stride_words, int64_t offset_words, int* flag_dev_or_null);
 /* *flag_dev |= 1 if, for some rank g > 0, the halo words of row g differ from the last-point words of
  * row g-1 (rows of stride_words int64, the 4 edge words at offset_words). */
 int gzb_check_edges(gzb_ctx* ctx, const int64_t* gathered, int64_t stride_words, int64_t offset_words,
