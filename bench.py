@@ -743,9 +743,10 @@ def run_ours(args, w):
 
     if rank == 0:
         sharding = ("contiguous time segments, grid replicated; " + (
-            "K4 stores the two series into " + ("rank 0's buffer" if args.gather == "p2p-root" else "every rank's buffer") +
-            " over NVLink (CUDA IPC peer memory), a barrier ("
-            + ("own kernel over peer memory" if args.barrier == "p2p" else "one-word NCCL all-reduce") + ") orders the ranks"
+            "the two series go into " + ("rank 0's buffer" if args.gather == "p2p-root" else "every rank's buffer") +
+            " over NVLink (CUDA IPC peer memory), copied chunk by chunk behind the bulk kernel by a push kernel on its own stream; "
+            "the step ends with " + ("ONE own kernel over peer memory (edge words + barrier + boundary check)" if args.barrier == "p2p"
+                                     else "an edge publication kernel, a one-word NCCL all-reduce and a check kernel")
             if isinstance(mapper, P2PShardedMapper) else "1 all-gather of (ssh_np, ssh_bl, NP)") +
             "; segment-boundary check on the device, verdict read once after the timed steps")
         line = {"metric": "track points/sec (mapping+interp)", "value": value, "unit": "points/s",
@@ -1205,8 +1206,10 @@ def main():
                     help="N > 1: p2p = K4 stores its results into EVERY rank's buffer over NVLink (all-gather; one-word "
                          "all-reduce as the barrier); p2p-root = into rank 0's buffer only (gather); nccl = all-gather of the "
                          "packed products after K4")
-    ap.add_argument("--barrier", default="nccl", choices=["p2p", "nccl"],
-                    help="with --gather p2p: how the ranks are ordered after K4 (own kernel over peer memory, or NCCL all-reduce)")
+    ap.add_argument("--barrier", default="p2p", choices=["p2p", "nccl"],
+                    help="with --gather p2p: how the ranks are ordered at the end of a step: p2p = ONE own kernel over peer memory "
+                         "(edge words + barrier + boundary check, gzb_peer_finish); nccl = one-word NCCL all-reduce between an edge "
+                         "publication kernel and a check kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-exact check of the sharded result against "

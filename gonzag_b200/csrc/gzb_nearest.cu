@@ -667,7 +667,7 @@ __device__ __forceinline__ void eval25(const GzbGrid& g, const int j, const int 
 // over and go on; nothing nearer and the table's certificate (everything outside the two neighbourhoods) holds: done,
 // candidates of both neighbourhoods through the reference's fp64 formula, lexicographic minimum (distance bits, flat
 // index) == numpy.argmin's first occurrence.  false: left to the warp search.
-__device__ __noinline__ bool weak_settle(const GzbGrid& g, const unsigned flat0, const double lat, const double lon,
+__device__ __forceinline__ bool weak_settle(const GzbGrid& g, const unsigned flat0, const double lat, const double lon,
                                          const float px, const float py, const float pz, long long& bf,
                                          unsigned long long& bd, unsigned& last) {
     int j = (int)(flat0 / (unsigned)g.Ni), i = (int)(flat0 - (unsigned)j * (unsigned)g.Ni);
@@ -799,25 +799,12 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
                     }
                 }
             }
-            bool settled = false;
-            if (reason == 3 && g.weak) {
-                long long bfw;
-                unsigned long long bdw;
-                unsigned last = myhint;
-                if (weak_settle(g, myhint, lat, lon, px, py, pz, bfw, bdw, last)) {
-                    G[t] = bfw;
-                    dG[t] = __longlong_as_double((long long)bdw);
-                    settled = true;
-                    reason = 0;
-                }
-                myhint = last;
-            }
             if (reason) {
                 unresolved = true;
                 out = CAND_UNRES;
                 atomicAdd(ucount + reason, 1ull);
             }
-            if (!unresolved && !settled) {
+            if (!unresolved) {
                 // settle the point here: the reference's fp64 formula on the candidate(s)
 #if GZB_EXP_SKIP_DG
                 const float m2 = a_win * 4.0e-6f + 4.0e-6f;           // twice the proven fp32 error of the chord
@@ -850,6 +837,59 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
             ulist[base + __popc(um & ((1u << lane) - 1u))] = t;
             hint[t] = myhint;
             G[t] = GZB_UNRESOLVED;
+        }
+    }
+}
+
+// K1, seam path: a thread per point the search could not prove.  Points whose cell has (near-)copies elsewhere in index
+// space (the duplicated East-West columns: 0.7 % of a Jason-like track, ALL of what the per-thread search leaves on such a
+// track) are settled here through the weak-cell table (weak_settle); the rest goes on to the warp search in `ulist2`.
+// Runs on the main stream right behind k_near_search, so the bulk kernel sees these points as settled.
+__global__ void __launch_bounds__(128)
+k_near_weak(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt, long long* __restrict__ G,
+            double* __restrict__ dG, const long long* __restrict__ ulist, unsigned* __restrict__ hint,
+            const unsigned long long* __restrict__ ucount, long long* __restrict__ ulist2,
+            unsigned long long* __restrict__ ucount2) {
+    const long long nu = (long long)*ucount;
+    for (long long e0 = (long long)blockIdx.x * blockDim.x; e0 < nu; e0 += (long long)gridDim.x * blockDim.x) {
+        const long long e = e0 + threadIdx.x;
+        bool left = false;
+        long long t = 0;
+        if (e < nu) {
+            t = ulist[e];
+            left = true;
+            const unsigned h = hint[t];
+            if (g.weak && h != 0xffffffffu) {
+                const double lat = yt[t], lon = xt[t];
+                float px, py, pz;
+                {
+                    const double la = lat * GZB_D2R, lo = lon * GZB_D2R;
+                    double sa, ca, so, co;
+                    sincos(la, &sa, &ca);
+                    sincos(lo, &so, &co);
+                    px = (float)(ca * co);
+                    py = (float)(ca * so);
+                    pz = (float)sa;
+                }
+                long long bf;
+                unsigned long long bd;
+                unsigned last = h;
+                if (weak_settle(g, h, lat, lon, px, py, pz, bf, bd, last)) {
+                    G[t] = bf;
+                    dG[t] = __longlong_as_double((long long)bd);
+                    left = false;
+                } else {
+                    hint[t] = last;
+                }
+            }
+        }
+        const unsigned um = __ballot_sync(0xffffffffu, left);
+        if (um) {
+            const int lane = threadIdx.x & 31;
+            unsigned long long base = 0;
+            if (lane == (__ffs(um) - 1)) base = atomicAdd(ucount2, (unsigned long long)__popc(um));
+            base = __shfl_sync(0xffffffffu, base, __ffs(um) - 1);
+            if (left) ulist2[base + __popc(um & ((1u << lane) - 1u))] = t;
         }
     }
 }
@@ -970,7 +1010,19 @@ k_weak_mark(const GzbGrid g, unsigned* __restrict__ list, unsigned* __restrict__
     if (j > 0) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k - g.Ni)));
     if (j + 1 < g.Nj) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k + g.Ni)));
     const float w5 = __uint_as_float(__float_as_uint(c.w) << 16);
-    if (s > 0.0f && w5 < 0.05f * s) {      // something outside the 5x5 neighbourhood is (nearly) on top of the cell
+    if (s > 0.0f && w5 < 1.5f * s) {
+        // the 5x5 certificate is too small for a target of this cell.  Anisotropy (the nearest outside cell is right next
+        // to the neighbourhood, at index distance 3) is not what the table is for: only cells whose nearest outside
+        // cell is elsewhere in index space
+        float ring = INFINITY;
+        for (int dj = -3; dj <= 3; ++dj)
+            for (int di = -3; di <= 3; ++di) {
+                if ((dj > -3 && dj < 3) && (di > -3 && di < 3)) continue;
+                const long long jj = j + dj, ii = i + di;
+                if (jj < 0 || jj >= g.Nj || ii < 0 || ii >= g.Ni) continue;
+                ring = fminf(ring, cell_chord(c, __ldg(g.cellv + jj * g.Ni + ii)));
+            }
+        if (ring <= w5 * 1.02f + 1.0e-6f) return;
         const unsigned pos = atomicAdd(count, 1u);
         if (pos < cap) list[pos] = (unsigned)k;
     }
@@ -1003,7 +1055,7 @@ k_weak_build(const GzbGrid g, const unsigned* __restrict__ list, const unsigned*
     pyramid_search<M_EXCL>(g, ws[warp], lane, s, 0, j - hj, j + hj + 1, i - hi, i + hi + 1, qn, me);
     float d = s.Pmin < INFINITY ? sqrtf(s.Pmin) : INFINITY;
     unsigned portal = WEAK_NONE;
-    if (d < 0.05f * R && s.bflat >= 0) {
+    if (d < 1.5f * R && s.bflat >= 0) {
         portal = (unsigned)s.bflat;
         const long long pj = s.bflat / g.Ni, pi = s.bflat - pj * g.Ni;
         long long xb[4] = {pj - 2, pj + 3, pi - 2, pi + 3};
@@ -1714,7 +1766,8 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
     if (threadIdx.x == 0) {      // (breaks, replay steps, ...) of this call, for gzb_get_stats
         stats_out[0] = scal[0];
         stats_out[1] = (long long)__ldcg(steps);
-        for (int q = 2; q < 7; ++q) stats_out[q] = __ldcg(scal + q);   // k_near_search: unresolved (total, no seed, not converged, not proven); longest replay
+        stats_out[2] = __ldcg(scal + 8);      // points that went to the warp search (after the seam pass)
+        for (int q = 3; q < 7; ++q) stats_out[q] = __ldcg(scal + q);   // k_near_search leftovers by reason (no seed, not converged, not proven); longest replay
     }
 }
 
@@ -1786,9 +1839,9 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
            + gzb_align(n * 8)        // replay log
-           + gzb_align(n * 8) + gzb_align(n * 4)   // unresolved list, hints
+           + gzb_align(n * 8) * 2 + gzb_align(n * 4)   // unresolved lists (search, after the seam pass), hints
            + gzb_align(n * 24)       // points whose nearest point differs from E(t): twin states + replay writes
-           + gzb_align(64) * 2;      // scalars, corner
+           + gzb_align(128) + gzb_align(64);      // scalars, corner
 }
 
 // device-level driver: all pointers are device pointers, work is enqueued on ctx->stream
@@ -1831,9 +1884,10 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     unsigned char* valid = (unsigned char*)gzb_arena_take(ctx, n);
     unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
     long long* ulist = (long long*)gzb_arena_take(ctx, n * 8);
+    long long* ulist2 = (long long*)gzb_arena_take(ctx, n * 8);
     unsigned* hint = (unsigned*)gzb_arena_take(ctx, n * 4);
     long long* chg = (long long*)gzb_arena_take(ctx, n * 24);
-    long long* scal = (long long*)gzb_arena_take(ctx, 64);
+    long long* scal = (long long*)gzb_arena_take(ctx, 128);      // [0] breaks [1] replay steps [2..5] search leftovers (total, by reason) [6] longest replay [7] changed points [8] left to the warp search
     if (!scal) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
     unsigned long long* nchg = (unsigned long long*)(scal + 7);
     if (!split) chg = nullptr;
@@ -1841,7 +1895,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     if (nchg_out) *nchg_out = nchg;
     if (gn_out) {
         gn_out->G = G; gn_out->dG = dG; gn_out->thr2 = 0.0; gn_out->edge = ctx->edge_exclusion;
-        gn_out->ulist = ulist; gn_out->ucount = (const unsigned long long*)(scal + 2);
+        gn_out->ulist = ulist2; gn_out->ucount = (const unsigned long long*)(scal + 8);
     }
     double* corner = (double*)(ctx->d_flags + 32);      // persistent: 4 doubles, keyed by np_box_r
     cudaStream_t s = ctx->stream;
@@ -1880,7 +1934,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
         p.rowsafe = ctx->d_rowsafe;
     }
 
-    GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 64, s));
+    GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 128, s));
     GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 3) * sizeof(unsigned), s));     // k_chain's ticket and block maps, the two done counters
     if (ctx->corner_r != np_box_r) {
         k_corner<<<1, 256, 0, s>>>(ctx->g, np_box_r, corner);
@@ -1910,6 +1964,9 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
                                                                  (unsigned long long*)(scal + 2));
 #endif
         GZB_LAUNCH_CHECK(ctx);
+        k_near_weak<<<64, 128, 0, s>>>(ctx->g, yt, xt, G, dG, ulist, hint, (const unsigned long long*)(scal + 2), ulist2,
+                                       (unsigned long long*)(scal + 8));
+        GZB_LAUNCH_CHECK(ctx);
         // from here on everything is latency-bound (the warp search of the few unresolved points, then
         // the chain): with `split` it goes to the auxiliary stream and the caller runs K2-K4 meanwhile on
         // E(t) = the plain global answers, which it derives from G / dG itself, skipping the unresolved points
@@ -1919,8 +1976,8 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
             GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
         }
         gzb_trace(ctx, s, "search end (main)");
-        k_near_slow<<<(unsigned)(nsm * 32 / SLOW_WARPS), 32 * SLOW_WARPS, 0, sb>>>(ctx->g, yt, xt, G, dG, ulist, hint,
-                                                        (const unsigned long long*)(scal + 2));
+        k_near_slow<<<(unsigned)(nsm * 32 / SLOW_WARPS), 32 * SLOW_WARPS, 0, sb>>>(ctx->g, yt, xt, G, dG, ulist2, hint,
+                                                        (const unsigned long long*)(scal + 8));
         GZB_LAUNCH_CHECK(ctx);
         sb_has_kernel = true;
         gzb_trace(ctx, sb, "slow end");

@@ -440,19 +440,37 @@ class P2PShardedMapper(ShardedMapper):
         ctx._ck(L.lib().gzb_publish_edges(ctx._h, C.c_void_p(self.NPh.data_ptr()), self.n + 1, len(self._peers) + 1,
                                           self._edge_dst))
 
+    def _fused_finish(self):
+        """barrier "p2p": edge publication, barrier and boundary check are ONE kernel (gzb_peer_finish)"""
+        return getattr(self, "barrier", "nccl") == "p2p" and self.world > 1 and not getattr(self, "root_only", False)
+
     def path_speculative(self, y_halo, x_halo, t_halo, rd, r, tmod, slab, k0):
-        """K1-K4 on [halo +] own points; K4 writes the series here and into every peer."""
+        """K1-K4 on [halo +] own points; the two series go here and, chunk by chunk behind the bulk kernel, into
+        every peer (k_push on its own stream)."""
         self._select(self.step_no & 1)
         self.step_no += 1
         super().path_speculative(y_halo, x_halo, t_halo, rd, r, tmod, slab, k0)
-        self._publish()
+        if not self._fused_finish():
+            self._publish()
 
     def gather(self):
-        """No data moves here: a barrier orders the ranks (a stream-ordered kernel over peer memory,
-        or NCCL's one-word all-reduce with ``barrier="nccl"``), after it every rank's buffer holds the
-        series of all segments."""
+        """No data moves here: a barrier orders the ranks (``barrier="p2p"``: one stream-ordered kernel over peer
+        memory that also publishes the edge words and checks the boundaries; ``"nccl"``: NCCL's one-word
+        all-reduce), after it every rank's buffer holds the series of all segments."""
         if self.world > 1:
-            if getattr(self, "barrier", "nccl") == "nccl":
+            if self._fused_finish():
+                ctx = self.e.ctx
+                if getattr(self, "flag_acc", None) is None:
+                    self.flag_acc = self.e.empty((1,), self.torch.int32)
+                    self.flag_acc.zero_()
+                self._epoch += 1
+                g = self.gath[self.cur]
+                ctx._ck(L.lib().gzb_peer_finish(ctx._h, C.c_void_p(self.NPh.data_ptr()), self.n + 1, len(self._peers) + 1,
+                                                self._edge_dst, len(self._peers), self._bar_slots, self._bar_local, self.world,
+                                                self.rank, self._epoch, C.c_void_p(g.data_ptr()), self.slot, 2 * self.m1,
+                                                C.c_void_p(self.flag_acc.data_ptr())))
+                self._checked = True
+            elif getattr(self, "barrier", "nccl") == "nccl":
                 self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.MAX)
             else:
                 ctx = self.e.ctx
@@ -471,6 +489,9 @@ class P2PShardedMapper(ShardedMapper):
             self.flag_acc.zero_()
         if self.world == 1 or (getattr(self, "root_only", False) and self.rank != 0):
             return                          # gather to root: only rank 0 holds every segment's edge words
+        if getattr(self, "_checked", False):      # the fused finish kernel of `gather` has already compared the edges
+            self._checked = False
+            return
         ctx = self.e.ctx
         ctx._ck(L.lib().gzb_check_edges(ctx._h, C.c_void_p(gathered.data_ptr()), self.slot, 2 * self.m1, self.world,
                                         C.c_void_p(self.flag_acc.data_ptr())))
@@ -507,6 +528,9 @@ class P2PShardedMapper(ShardedMapper):
             gathered = self.gather()
             if self.boundaries_ok(gathered):
                 break
+        if getattr(self, "flag_acc", None) is not None:      # the rounds above may have flagged boundaries that are settled now
+            self.flag_acc.zero_()
+        self._checked = False
         return changed
 
     def redo_own_points(self, y_own, x_own, t_own, tmod, slab, k0):
