@@ -31,7 +31,7 @@ class Stats(C.Structure):
                 ("lut_bins", C.c_int64), ("last_unresolved", C.c_int64),
                 ("last_unres_noseed", C.c_int64), ("last_unres_noconv", C.c_int64),
                 ("last_unres_nocert", C.c_int64), ("last_max_chain", C.c_int64),
-                ("heading_table", C.c_int64), ("weak_cells", C.c_int64)]
+                ("heading_table", C.c_int64)]
 
 
 _P = C.c_void_p
@@ -41,6 +41,7 @@ _SIGNATURES = {
     "gzb_last_global_error": (C.c_char_p, []),
     "gzb_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "gzb_create": (C.c_int, [C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int, C.POINTER(_P)]),
+    "gzb_create_imask": (C.c_int, [C.c_int, _I64, _I64, _P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
     "gzb_destroy": (C.c_int, [_P]),
     "gzb_last_error": (C.c_char_p, [_P]),
     "gzb_set_stream": (C.c_int, [_P, _P]),

@@ -48,12 +48,18 @@ class GridContext:
         ang = None
         if angle is not None and np.shape(angle) == Ys.shape:
             ang = L.as_f64(angle)
-        msk = None
+        msk, isz = None, 1
         if mask is not None:
-            msk = self._mask8(mask)
+            m = np.asarray(np.ma.getdata(mask))
+            if m.shape != (self.Nj, self.Ni):
+                raise ValueError("mask has shape %s, grid is %s" % (m.shape, (self.Nj, self.Ni)))
+            if m.dtype.kind in "iu" and m.dtype.isnative and m.flags["C_CONTIGUOUS"] and m.dtype.itemsize in (2, 4, 8):
+                msk, isz = m, m.dtype.itemsize          # the reference's int64 {0,1} mask: packed to int8 by the upload itself
+            else:
+                msk = self._mask8(mask)
         h = C.c_void_p()
-        L.check(L.lib().gzb_create(self.device, self.Nj, self.Ni, L.ptr(Ys), L.ptr(Xs), L.ptr(ang),
-                                   L.ptr(msk), int(k_ew_per), C.byref(h)))
+        L.check(L.lib().gzb_create_imask(self.device, self.Nj, self.Ni, L.ptr(Ys), L.ptr(Xs), L.ptr(ang),
+                                         L.ptr(msk), isz, int(k_ew_per), C.byref(h)))
         self._h = h
         self.k_ew_per = int(k_ew_per)
         self.has_mask = msk is not None

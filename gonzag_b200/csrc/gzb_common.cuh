@@ -58,12 +58,6 @@ struct GzbGrid {
                             // from this cell to any cell outside its 5x5 index neighbourhood
     const double* hdg;      // optional per-cell table of K2 (6 doubles per cell): Mercator ordinate and
                             // longitude (radians, [0,2pi)) of the cell, headings to its N, E, S, W neighbours
-    const uint4* weak;      // table of the WEAK cells (5x5 certificate too small for a target of the cell: strongly
-                            // anisotropic cells, duplicated / folded columns): open-addressing hash keyed by flat index,
-                            // entry = (key, portal flat index or 0xffffffff, certificate as float bits, hj | hi << 8);
-                            // the per-thread search scans the box [j-hj, j+hj] x [i-hi, i+hi] (and the 5x5 neighbourhood
-                            // of the portal) instead of 5x5.  null: no table.
-    unsigned weak_mask;     // table size - 1 (a power of two)
     GzbLut lut;
     int nlev;
     GzbLevel lev[GZB_MAXLEV];
@@ -141,8 +135,6 @@ struct gzb_ctx {
     float4* d_nodes[GZB_MAXLEV] = {};
     float* d_cert = nullptr;
     float4* d_cellv = nullptr;
-    uint4* d_weak = nullptr;         // weak-cell table (GzbGrid::weak)
-    unsigned* d_weak_list = nullptr;
     unsigned* d_lut[2] = {nullptr, nullptr};
     unsigned* d_mbits = nullptr;     // land-sea mask as bits in 16x16-cell tiles (K4); d_flags[2] != 0: mask not {0,1}
     int mask_bits_ok = 0;

@@ -118,7 +118,15 @@ bool bigcopy_ready(int dev) {
     return true;
 }
 
-void bigcopy_part(int dev, int t, char* dst, const char* src, size_t bytes, bool h2d, cudaError_t* err) {
+// pack > 0 (uploads only): `src` holds integers of `pack` bytes each and dst[k] = (int8_t)src[k] -- the land-sea mask of the
+// reference is int64 {0,1} (gonzag/ncio.py:164-191), the context keeps int8: the conversion rides on the staging copy
+template <typename T> static void pack_into(int8_t* out, const char* src, size_t first, size_t n) {
+    const T* p = (const T*)src + first;
+    for (size_t k = 0; k < n; ++k) out[k] = (int8_t)p[k];
+}
+
+void bigcopy_part(int dev, int t, char* dst, const char* src, size_t bytes, bool h2d, cudaError_t* err, int pack = 0,
+                  size_t first_elem = 0) {
     cudaSetDevice(dev);
     cudaError_t e = cudaSuccess;
     size_t off = 0;
@@ -133,7 +141,10 @@ void bigcopy_part(int dev, int t, char* dst, const char* src, size_t bytes, bool
         }
         if (e != cudaSuccess) break;
         if (h2d) {
-            memcpy(g_bc.slot[t][k], src + off, len);
+            if (pack == 8) pack_into<int64_t>((int8_t*)g_bc.slot[t][k], src, first_elem + off, len);
+            else if (pack == 4) pack_into<int32_t>((int8_t*)g_bc.slot[t][k], src, first_elem + off, len);
+            else if (pack == 2) pack_into<int16_t>((int8_t*)g_bc.slot[t][k], src, first_elem + off, len);
+            else memcpy(g_bc.slot[t][k], src + off, len);
             e = cudaMemcpyAsync(dst + off, g_bc.slot[t][k], len, cudaMemcpyHostToDevice, g_bc.stream[t]);
         } else {
             e = cudaMemcpyAsync(g_bc.slot[t][k], src + off, len, cudaMemcpyDeviceToHost, g_bc.stream[t]);
@@ -157,10 +168,10 @@ void bigcopy_part(int dev, int t, char* dst, const char* src, size_t bytes, bool
 
 // Copies `bytes` between pageable host memory and the device and RETURNS WHEN DONE.  Falls back to
 // one cudaMemcpyAsync + stream synchronisation for small or already pinned buffers.
-int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true) {
+int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true, int pack = 0) {
     if (bytes == 0) return GZB_OK;
     const void* host = h2d ? src : dst;
-    bool plain = bytes < GZB_BC_MIN;
+    bool plain = bytes < GZB_BC_MIN && pack <= 1;
     if (!plain) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, host) == cudaSuccess) {
@@ -173,6 +184,15 @@ int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d
     if (!plain) {
         lk.lock();
         if (!bigcopy_ready(ctx->device)) { plain = true; lk.unlock(); }
+    }
+    if (plain && pack > 1) {          // no staging slots on this device: convert on this thread, then one plain copy
+        std::vector<int8_t> tmp(bytes);
+        if (pack == 8) pack_into<int64_t>(tmp.data(), (const char*)src, 0, bytes);
+        else if (pack == 4) pack_into<int32_t>(tmp.data(), (const char*)src, 0, bytes);
+        else pack_into<int16_t>(tmp.data(), (const char*)src, 0, bytes);
+        GZB_CUDA(ctx, cudaMemcpyAsync(dst, tmp.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return GZB_OK;
     }
     if (plain) {
         // cudaMemcpyDefault: `src` of an upload may itself be device memory (a grid replicated from another GPU)
@@ -194,7 +214,8 @@ int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d
         if (a >= bytes) break;
         const size_t len = bytes - a < part ? bytes - a : part;
         errs[t] = cudaSuccess;
-        th[t] = std::thread(bigcopy_part, ctx->device, t, (char*)dst + a, (const char*)src + a, len, h2d, &errs[t]);
+        if (pack > 1) th[t] = std::thread(bigcopy_part, ctx->device, t, (char*)dst + a, (const char*)src, len, h2d, &errs[t], pack, a);
+        else th[t] = std::thread(bigcopy_part, ctx->device, t, (char*)dst + a, (const char*)src + a, len, h2d, &errs[t], 0, (size_t)0);
         ++nth;
     }
     for (int t = 0; t < nth; ++t) th[t].join();
@@ -379,7 +400,6 @@ void* gzb_arena_take(gzb_ctx* ctx, size_t bytes) {
 
 // ======================================================================== pyramid build
 int gzb_build_cert(gzb_ctx* ctx);   // gzb_nearest.cu
-int gzb_build_weak(gzb_ctx* ctx);   // gzb_nearest.cu
 
 // fp32 storage of a sphere computed in fp64: the radius is rounded up and padded by 2.5e-7 so
 // that it still bounds the members after the centre itself was rounded to float
@@ -821,15 +841,32 @@ static int build_pyramid(gzb_ctx* ctx) {
         if ((rc = build_lut(ctx, (const unsigned long long*)((char*)ctx->pinned + 256))) != GZB_OK) return rc;
         k_cellcert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(g, ctx->d_cellv);
         GZB_LAUNCH_CHECK(ctx);
-        if ((rc = gzb_build_weak(ctx)) != GZB_OK) return rc;
     }
     return GZB_OK;
 }
 
 // ======================================================================== create / destroy
+static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, const double* lon, const double* angle_or_null,
+                       const void* mask_or_null, int mask_itemsize, int k_ew_per, gzb_ctx** ctx_out);
+
 extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat, const double* lon,
                           const double* angle_or_null, const int8_t* mask_or_null, int k_ew_per,
                           gzb_ctx** ctx_out) {
+    return create_impl(device, nj, ni, lat, lon, angle_or_null, mask_or_null, 1, k_ew_per, ctx_out);
+}
+
+// gzb_create with the land-sea mask in the caller's integer type (HOST memory, 1 / 2 / 4 / 8 bytes per cell): the reference's
+// MG.mask is int64; converting it to int8 rides on the upload's staging copies instead of being a pass of its own
+extern "C" int gzb_create_imask(int device, int64_t nj, int64_t ni, const double* lat, const double* lon,
+                                const double* angle_or_null, const void* mask_or_null, int mask_itemsize, int k_ew_per,
+                                gzb_ctx** ctx_out) {
+    if (mask_or_null && mask_itemsize != 1 && mask_itemsize != 2 && mask_itemsize != 4 && mask_itemsize != 8)
+        return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create_imask: mask_itemsize must be 1, 2, 4 or 8 (got %d)", mask_itemsize);
+    return create_impl(device, nj, ni, lat, lon, angle_or_null, mask_or_null, mask_itemsize, k_ew_per, ctx_out);
+}
+
+static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, const double* lon, const double* angle_or_null,
+                       const void* mask_or_null, int mask_itemsize, int k_ew_per, gzb_ctx** ctx_out) {
     if (!ctx_out) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_create: null ctx_out");
     *ctx_out = nullptr;
     if (nj < 3 || ni < 3 || !lat || !lon)
@@ -905,7 +942,7 @@ extern "C" int gzb_create(int device, int64_t nj, int64_t ni, const double* lat,
             ctx->stats.h2d_bytes += n * sizeof(double);
         }
         if (mask_or_null) {
-            if ((rc = gzb_bigcopy(ctx, ctx->d_mask, mask_or_null, n, true, false)) != GZB_OK) break;
+            if ((rc = gzb_bigcopy(ctx, ctx->d_mask, mask_or_null, n, true, false, mask_itemsize)) != GZB_OK) break;
             ctx->stats.h2d_bytes += n;
         }
         if ((rc = gzb_build_mask_bits(ctx)) != GZB_OK) break;
@@ -939,8 +976,6 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     gzb_pool_free(ctx->d_cells);
     gzb_pool_free(ctx->d_cert);
     gzb_pool_free(ctx->d_cellv);
-    gzb_pool_free(ctx->d_weak);
-    gzb_pool_free(ctx->d_weak_list);
     gzb_pool_free(ctx->d_lut[0]);
     gzb_pool_free(ctx->d_lut[1]);
     gzb_pool_free(ctx->d_hdg);

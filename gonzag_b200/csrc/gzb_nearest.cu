@@ -69,7 +69,6 @@ struct Srch {          // warp-uniform state of the search for one point
     float Pmin;        // smallest chord^2 seen (fp32 proxy)
     float B, B2;       // candidate / pruning bound on the chord and its square
     int bJ, bI;        // leaf tile holding the best proxy
-    long long bflat;   // M_EXCL only: flat index of the cell holding the best proxy
 };
 
 struct Owner {         // the point a lane owns (exact evaluation needs its coordinates)
@@ -112,7 +111,6 @@ __device__ __forceinline__ void srch_init(Srch& s, float px, float py, float pz)
     s.px = px; s.py = py; s.pz = pz;
     s.Pmin = INFINITY; s.B = INFINITY; s.B2 = INFINITY;
     s.bJ = -1; s.bI = -1;
-    s.bflat = -1;
 }
 
 // exact evaluation of the queued candidates, 32 at a time, and per-point lexicographic minimum
@@ -151,8 +149,7 @@ __device__ __forceinline__ void flush_queue(const GzbGrid& g, WarpSm& w, const i
 template <int MODE>
 __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
                                           const int tJ, const int tI, const long long j0, const long long j1,
-                                          const long long i0, const long long i1, int& qn, const Owner& me,
-                                          const long long* xb = nullptr /* M_EXCL: a second excluded box j0,j1,i0,i1 */) {
+                                          const long long i0, const long long i1, int& qn, const Owner& me) {
     const float* __restrict__ cc = g.cells + ((long long)tJ * g.lev[0].nI + tI) * 96;
     const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
     const long long j = (long long)tJ * GZB_TILE_J + (lane >> 3);
@@ -162,7 +159,6 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
     if (MODE != M_GLOBAL) {
         const bool inside = (j >= j0) && (j < j1) && (i >= i0) && (i < i1);
         ok = (j < g.Nj) && (i < g.Ni) && (MODE == M_BOX ? inside : !inside);
-        if (MODE == M_EXCL && xb && ok) ok = !((j >= xb[0]) && (j < xb[1]) && (i >= xb[2]) && (i < xb[3]));
     }
     const float dx = s.px - x, dy = s.py - y, dz = s.pz - z;
     const float P = dx * dx + dy * dy + dz * dz;
@@ -172,11 +168,6 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
         s.bJ = tJ;
         s.bI = tI;
         if (MODE != M_EXCL && lane == 0) w.pb2[pt] = s.B2;
-        if (MODE == M_EXCL) {
-            const unsigned hm = __ballot_sync(0xffffffffu, ok && P == pm);
-            const int hl = hm ? __ffs(hm) - 1 : 0;
-            s.bflat = __shfl_sync(0xffffffffu, j * g.Ni + i, hl);
-        }
     }
     if (MODE != M_EXCL) {
         const bool cand = ok && (P <= s.B2);
@@ -200,7 +191,7 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
 template <int MODE>
 __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
                                                const long long j0, const long long j1, const long long i0,
-                                               const long long i1, int& qn, const Owner& me, const long long* xb = nullptr) {
+                                               const long long i1, int& qn, const Owner& me) {
     int depth = 0;
     if (lane == 0) w.fmask[0] = 0xffffffffu;
     __syncwarp();
@@ -227,10 +218,7 @@ __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, cons
         if (MODE != M_GLOBAL && keep) {
             const long long a0 = (long long)cJ * L.sJ, b0 = (long long)cI * L.sI;
             if (MODE == M_BOX) keep = (a0 < j1) && (a0 + L.sJ > j0) && (b0 < i1) && (b0 + L.sI > i0);
-            else {
-                keep = !((a0 >= j0) && (a0 + L.sJ <= j1) && (b0 >= i0) && (b0 + L.sI <= i1));
-                if (xb && keep) keep = !((a0 >= xb[0]) && (a0 + L.sJ <= xb[1]) && (b0 >= xb[2]) && (b0 + L.sI <= xb[3]));
-            }
+            else keep = !((a0 >= j0) && (a0 + L.sJ <= j1) && (b0 >= i0) && (b0 + L.sI <= i1));
         }
         const float dx = s.px - nd.x, dy = s.py - nd.y, dz = s.pz - nd.z;
         const float dn2 = dx * dx + dy * dy + dz * dz;
@@ -257,7 +245,7 @@ __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, cons
             }
             __syncwarp();
         } else {
-            leaf_eval<MODE>(g, w, lane, s, pt, sJ, sI, j0, j1, i0, i1, qn, me, xb);
+            leaf_eval<MODE>(g, w, lane, s, pt, sJ, sI, j0, j1, i0, i1, qn, me);
             __syncwarp();
         }
     }
@@ -575,7 +563,7 @@ __device__ __forceinline__ int fast_ring(const GzbGrid& g, const float px, const
 // returns the first-index argmin and its distance bits
 __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long long c, const double lat, const double lon,
                                                 const float px, const float py, const float pz, long long& bf,
-                                                unsigned long long& bd, const float Pbest = -1.0f /* >= 0: chord^2 of the best cell */) {
+                                                unsigned long long& bd) {
     bf = GZB_NOFLAT;
     bd = ~0ull;
     if (c & CAND_NONE) return;
@@ -591,13 +579,9 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
     const long long j = f0 / g.Ni, i = f0 - j * g.Ni;
     float B2;
     {
-        float P0 = Pbest;
-        if (P0 < 0.0f) {
-            const float4 v = __ldg(g.cellv + f0);
-            const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
-            P0 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-        }
-        const float a = sqrtf(P0);
+        const float4 v = __ldg(g.cellv + f0);
+        const float dx = px - v.x, dy = py - v.y, dz = pz - v.z;
+        const float a = sqrtf(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)));
         const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
         B2 = B * B;
     }
@@ -619,100 +603,6 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
             if (db < bd) { bd = db; bf = f; }     // row-major scan: the first index keeps a tie
         }
     }
-}
-
-// weak-cell table of the per-thread search (built by gzb_build_weak below)
-#define WEAK_NONE 0xffffffffu
-#define WEAK_HMAX 24
-
-__device__ __forceinline__ unsigned weak_hash(const unsigned key) { return key * 2654435761u; }
-
-__device__ __forceinline__ bool weak_lookup(const GzbGrid& g, const unsigned key, uint4& e) {
-    unsigned slot = weak_hash(key) & g.weak_mask;
-    for (int probe = 0; probe < 64; ++probe) {
-        e = __ldg(g.weak + slot);
-        if (e.x == key) return true;
-        if (e.x == WEAK_NONE) return false;
-        slot = (slot + 1) & g.weak_mask;
-    }
-    return false;
-}
-
-__device__ __forceinline__ float cell_chord(const float4 a, const float4 b) {
-    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-    return sqrtf(dx * dx + dy * dy + dz * dz);
-}
-
-// all 25 cells of the 5x5 neighbourhood of (j, i), bounds-checked, loads issued back to back: chord^2 of the centre,
-// smallest chord^2 among the other 24 and where it sits
-__device__ __forceinline__ void eval25(const GzbGrid& g, const int j, const int i, const float px, const float py,
-                                       const float pz, float& Pc, float& nbest, int& bj, int& bi) {
-    const float4* __restrict__ c0 = g.cellv + ((long long)j * g.Ni + i);
-    float nb = INFINITY;
-    int mj = 0, mi = 0;
-#define W5(DJ, DI) FAST_UPD((fast_cell<true, DJ, DI>(g, c0, j, i, px, py, pz)), DJ, DI)
-    W5(-2, -2) W5(-2, -1) W5(-2, 0) W5(-2, 1) W5(-2, 2) W5(-1, -2) W5(-1, -1) W5(-1, 0) W5(-1, 1) W5(-1, 2)
-    W5(0, -2) W5(0, -1) W5(0, 1) W5(0, 2) W5(1, -2) W5(1, -1) W5(1, 0) W5(1, 1) W5(1, 2)
-    W5(2, -2) W5(2, -1) W5(2, 0) W5(2, 1) W5(2, 2)
-#undef W5
-    Pc = fast_cell<true, 0, 0>(g, c0, j, i, px, py, pz);
-    nbest = nb;
-    bj = j + mj;
-    bi = i + mi;
-}
-
-// A point whose climb ended on a cell with (near-)copies elsewhere in index space (duplicated East-West columns, a
-// folded row): follow the table's portals.  At every stop: walk to the local minimum of the 5x5 neighbourhoods; if the
-// cell's own certificate holds, done; else look at the 5x5 neighbourhood of its portal -- something nearer there: hop
-// over and go on; nothing nearer and the table's certificate (everything outside the two neighbourhoods) holds: done,
-// candidates of both neighbourhoods through the reference's fp64 formula, lexicographic minimum (distance bits, flat
-// index) == numpy.argmin's first occurrence.  false: left to the warp search.
-__device__ __forceinline__ bool weak_settle(const GzbGrid& g, const unsigned flat0, const double lat, const double lon,
-                                         const float px, const float py, const float pz, long long& bf,
-                                         unsigned long long& bd, unsigned& last) {
-    int j = (int)(flat0 / (unsigned)g.Ni), i = (int)(flat0 - (unsigned)j * (unsigned)g.Ni);
-    for (int hop = 0; hop < 4; ++hop) {
-        float Pc = 0.0f, nb = 0.0f;
-        int bj = j, bi = i, it = 0;
-        for (; it < 12; ++it) {
-            eval25(g, j, i, px, py, pz, Pc, nb, bj, bi);
-            if (!(nb < Pc)) break;
-            j = bj;
-            i = bi;
-        }
-        const unsigned f = (unsigned)j * (unsigned)g.Ni + (unsigned)i;
-        last = f;
-        if (it >= 12) return false;
-        const float a = sqrtf(Pc);
-        const float B = a * (1.0f + 2.0e-6f) + 2.0e-6f;
-        const float w5 = __uint_as_float(__float_as_uint(__ldg(g.cellv + f).w) << 16);
-        if ((w5 - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
-            exact_from_cand(g, (long long)f | CAND_MULTI, lat, lon, px, py, pz, bf, bd, Pc);
-            return true;
-        }
-        uint4 e;
-        if (!weak_lookup(g, f, e) || e.y == WEAK_NONE) return false;
-        const int pj = (int)(e.y / (unsigned)g.Ni), pi = (int)(e.y - (unsigned)pj * (unsigned)g.Ni);
-        float Pp = 0.0f, nbp = 0.0f;
-        int qj = pj, qi = pi;
-        eval25(g, pj, pi, px, py, pz, Pp, nbp, qj, qi);
-        if (Pp <= nbp) { nbp = Pp; qj = pj; qi = pi; }
-        if (nbp < Pc) {          // nearer on the other side: go on from there
-            j = qj;
-            i = qi;
-            continue;
-        }
-        if ((__uint_as_float(e.z) - (a * (1.0f + 2.0e-7f) + 5.0e-7f)) > (B + 1.0e-6f)) {
-            long long bf2;
-            unsigned long long bd2;
-            exact_from_cand(g, (long long)f | CAND_MULTI, lat, lon, px, py, pz, bf, bd, Pc);
-            exact_from_cand(g, (long long)e.y | CAND_MULTI, lat, lon, px, py, pz, bf2, bd2, Pc);
-            if (bd2 < bd || (bd2 == bd && bf2 < bf)) { bd = bd2; bf = bf2; }
-            return true;
-        }
-        return false;
-    }
-    return false;
 }
 
 __global__ void __launch_bounds__(128, 8)
@@ -745,13 +635,12 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
             }
             const unsigned seed = __ldg(g.lut.bins + gzb_lut_bin(g.lut, lat, lon));
             int reason = 1;      // 1 no seed, 2 not converged, 3 not proven
-            float Pc = 0.0f;     // chord^2 (fp32 proxy) of the cell the climb converged to
             if (seed != 0xffffffffu) {
                 int j = (int)(seed / (unsigned)g.Ni);
                 int i = (int)(seed - (unsigned)j * (unsigned)g.Ni);
                 const unsigned nj4 = g.Nj > 4 ? (unsigned)(g.Nj - 4) : 0u, ni4 = g.Ni > 4 ? (unsigned)(g.Ni - 4) : 0u;
                 const unsigned nj2 = (unsigned)(g.Nj - 2), ni2 = (unsigned)(g.Ni - 2);     // Nj, Ni >= 3
-                float cw = 0.0f, nb8 = INFINITY, ring = INFINITY;
+                float Pc = 0.0f, cw = 0.0f, nb8 = INFINITY, ring = INFINITY;
                 bool conv = false, proven3 = false;
                 int moves = 0;
                 for (;;) {
@@ -837,59 +726,6 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
             ulist[base + __popc(um & ((1u << lane) - 1u))] = t;
             hint[t] = myhint;
             G[t] = GZB_UNRESOLVED;
-        }
-    }
-}
-
-// K1, seam path: a thread per point the search could not prove.  Points whose cell has (near-)copies elsewhere in index
-// space (the duplicated East-West columns: 0.7 % of a Jason-like track, ALL of what the per-thread search leaves on such a
-// track) are settled here through the weak-cell table (weak_settle); the rest goes on to the warp search in `ulist2`.
-// Runs on the main stream right behind k_near_search, so the bulk kernel sees these points as settled.
-__global__ void __launch_bounds__(128)
-k_near_weak(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt, long long* __restrict__ G,
-            double* __restrict__ dG, const long long* __restrict__ ulist, unsigned* __restrict__ hint,
-            const unsigned long long* __restrict__ ucount, long long* __restrict__ ulist2,
-            unsigned long long* __restrict__ ucount2) {
-    const long long nu = (long long)*ucount;
-    for (long long e0 = (long long)blockIdx.x * blockDim.x; e0 < nu; e0 += (long long)gridDim.x * blockDim.x) {
-        const long long e = e0 + threadIdx.x;
-        bool left = false;
-        long long t = 0;
-        if (e < nu) {
-            t = ulist[e];
-            left = true;
-            const unsigned h = hint[t];
-            if (g.weak && h != 0xffffffffu) {
-                const double lat = yt[t], lon = xt[t];
-                float px, py, pz;
-                {
-                    const double la = lat * GZB_D2R, lo = lon * GZB_D2R;
-                    double sa, ca, so, co;
-                    sincos(la, &sa, &ca);
-                    sincos(lo, &so, &co);
-                    px = (float)(ca * co);
-                    py = (float)(ca * so);
-                    pz = (float)sa;
-                }
-                long long bf;
-                unsigned long long bd;
-                unsigned last = h;
-                if (weak_settle(g, h, lat, lon, px, py, pz, bf, bd, last)) {
-                    G[t] = bf;
-                    dG[t] = __longlong_as_double((long long)bd);
-                    left = false;
-                } else {
-                    hint[t] = last;
-                }
-            }
-        }
-        const unsigned um = __ballot_sync(0xffffffffu, left);
-        if (um) {
-            const int lane = threadIdx.x & 31;
-            unsigned long long base = 0;
-            if (lane == (__ffs(um) - 1)) base = atomicAdd(ucount2, (unsigned long long)__popc(um));
-            base = __shfl_sync(0xffffffffu, base, __ffs(um) - 1);
-            if (left) ulist2[base + __popc(um & ((1u << lane) - 1u))] = t;
         }
     }
 }
@@ -983,141 +819,6 @@ int gzb_build_cert(gzb_ctx* ctx) {
     const long long ntile = (long long)ctx->g.lev[0].nJ * ctx->g.lev[0].nI;
     k_cert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(ctx->g, ctx->d_cert);
     GZB_LAUNCH_CHECK(ctx);
-    return GZB_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// WEAK cells: cells that have a (near-)copy outside their 5x5 index neighbourhood -- the duplicated East-West overlap
-// columns of a global grid (a copy of the whole neighbourhood sits at the other end of the row), a folded row.  Their
-// 5x5 certificate is ~0, so every track point next to the seam used to go to the warp-cooperative search (0.7 % of a
-// Jason-like track: the whole of k_near_slow's 26 us).  Found from the coordinates alone (nothing here trusts k_ew_per).
-// For each of them the table holds
-//   portal     the nearest cell outside the 5x5 neighbourhood (the copy at the other end),
-//   wcert      a lower bound of the chord from the cell to any cell outside  5x5(cell) U 5x5(portal).
-// k_near_search looks at 5x5(portal) as well for such a cell and settles the point itself.  (A table with wider index
-// boxes for strongly anisotropic cells was tried in round 2: its build cost 8 ms per ORCA12 context and the per-thread
-// scans made k_near_search 2x slower on polar tracks -- those points stay with the warp search.)
-// thread per cell: weak iff the 5x5 certificate is below 1.5 x the largest chord to a direct neighbour
-__global__ void __launch_bounds__(256)
-k_weak_mark(const GzbGrid g, unsigned* __restrict__ list, unsigned* __restrict__ count, const unsigned cap) {
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= g.Nj * g.Ni) return;
-    const long long j = k / g.Ni, i = k - j * g.Ni;
-    const float4 c = __ldg(g.cellv + k);
-    float s = 0.0f;
-    if (i > 0) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k - 1)));
-    if (i + 1 < g.Ni) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k + 1)));
-    if (j > 0) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k - g.Ni)));
-    if (j + 1 < g.Nj) s = fmaxf(s, cell_chord(c, __ldg(g.cellv + k + g.Ni)));
-    const float w5 = __uint_as_float(__float_as_uint(c.w) << 16);
-    if (s > 0.0f && w5 < 1.5f * s) {
-        // the 5x5 certificate is too small for a target of this cell.  Anisotropy (the nearest outside cell is right next
-        // to the neighbourhood, at index distance 3) is not what the table is for: only cells whose nearest outside
-        // cell is elsewhere in index space
-        float ring = INFINITY;
-        for (int dj = -3; dj <= 3; ++dj)
-            for (int di = -3; di <= 3; ++di) {
-                if ((dj > -3 && dj < 3) && (di > -3 && di < 3)) continue;
-                const long long jj = j + dj, ii = i + di;
-                if (jj < 0 || jj >= g.Nj || ii < 0 || ii >= g.Ni) continue;
-                ring = fminf(ring, cell_chord(c, __ldg(g.cellv + jj * g.Ni + ii)));
-            }
-        if (ring <= w5 * 1.02f + 1.0e-6f) return;
-        const unsigned pos = atomicAdd(count, 1u);
-        if (pos < cap) list[pos] = (unsigned)k;
-    }
-}
-
-// warp per weak cell: box, portal, certificate -> hash table
-__global__ void __launch_bounds__(128)
-k_weak_build(const GzbGrid g, const unsigned* __restrict__ list, const unsigned* __restrict__ count, const unsigned cap,
-             uint4* __restrict__ table, const unsigned mask) {
-    __shared__ WarpSm ws[4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned n = min(*count, cap);
-    const unsigned e = blockIdx.x * 4 + warp;
-    if (e >= n) return;
-    const unsigned key = list[e];
-    const long long j = key / g.Ni, i = key - j * g.Ni;
-    const float4 c = __ldg(g.cellv + key);
-    float smax = 0.0f;      // largest spacing to a direct neighbour
-    if (i > 0) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key - 1)));
-    if (i + 1 < g.Ni) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key + 1)));
-    if (j > 0) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key - g.Ni)));
-    if (j + 1 < g.Nj) smax = fmaxf(smax, cell_chord(c, __ldg(g.cellv + key + g.Ni)));
-    const float R = smax;
-    const int hi = 2, hj = 2;
-    Owner me;
-    me.plat = me.plon = me.cpl = 0.0;
-    int qn = 0;
-    Srch s;
-    srch_init(s, c.x, c.y, c.z);
-    pyramid_search<M_EXCL>(g, ws[warp], lane, s, 0, j - hj, j + hj + 1, i - hi, i + hi + 1, qn, me);
-    float d = s.Pmin < INFINITY ? sqrtf(s.Pmin) : INFINITY;
-    unsigned portal = WEAK_NONE;
-    if (d < 1.5f * R && s.bflat >= 0) {
-        portal = (unsigned)s.bflat;
-        const long long pj = s.bflat / g.Ni, pi = s.bflat - pj * g.Ni;
-        long long xb[4] = {pj - 2, pj + 3, pi - 2, pi + 3};
-        Srch s2;
-        srch_init(s2, c.x, c.y, c.z);
-        __syncwarp();
-        pyramid_search<M_EXCL>(g, ws[warp], lane, s2, 0, j - hj, j + hj + 1, i - hi, i + hi + 1, qn, me, xb);
-        d = s2.Pmin < INFINITY ? sqrtf(s2.Pmin) : INFINITY;
-    }
-    if (lane == 0) {
-        float wc = (d - 5.0e-7f) * (1.0f - 1.0e-6f);
-        if (!(wc > 0.0f)) wc = 0.0f;
-        unsigned slot = weak_hash(key) & mask;
-        for (;;) {
-            const unsigned old = atomicCAS(&table[slot].x, WEAK_NONE, key);
-            if (old == WEAK_NONE) break;
-            slot = (slot + 1) & mask;
-        }
-        table[slot].y = portal;
-        table[slot].z = __float_as_uint(wc);
-        table[slot].w = (unsigned)hj | ((unsigned)hi << 8);
-    }
-}
-
-// after k_cellcert (gzb_grid.cu): list the weak cells, size the table, fill it.  Not fatal when memory is short or the
-// grid is mostly weak (> 1/8 of the cells): the warp-cooperative search takes the points as before.
-int gzb_build_weak(gzb_ctx* ctx) {
-    GzbGrid& g = ctx->g;
-    g.weak = nullptr;
-    g.weak_mask = 0;
-    if (!g.cellv || getenv("GZB_NO_WEAK_TABLE")) return GZB_OK;
-    const long long cells = g.Nj * g.Ni;
-    if (cells >= 0xfffffff0LL) return GZB_OK;
-    const unsigned cap = (unsigned)(cells / 8 + 1024);
-    if (gzb_pool_malloc((void**)&ctx->d_weak_list, ((size_t)cap + 4) * sizeof(unsigned)) != cudaSuccess) {
-        cudaGetLastError();
-        ctx->d_weak_list = nullptr;
-        return GZB_OK;
-    }
-    unsigned* count = ctx->d_weak_list + cap;
-    cudaStream_t s = ctx->stream;
-    GZB_CUDA(ctx, cudaMemsetAsync(count, 0, 4 * sizeof(unsigned), s));
-    k_weak_mark<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(g, ctx->d_weak_list, count, cap);
-    GZB_LAUNCH_CHECK(ctx);
-    unsigned* h_n = (unsigned*)((char*)ctx->pinned + 384);
-    GZB_CUDA(ctx, cudaMemcpyAsync(h_n, count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
-    GZB_CUDA(ctx, cudaStreamSynchronize(s));
-    const unsigned n = *h_n;
-    ctx->stats.weak_cells = (int64_t)n;
-    if (n == 0 || n > cap) return GZB_OK;
-    unsigned size = 1024;
-    while (size < 2u * n) size <<= 1;
-    if (gzb_pool_malloc((void**)&ctx->d_weak, (size_t)size * sizeof(uint4)) != cudaSuccess) {
-        cudaGetLastError();
-        ctx->d_weak = nullptr;
-        return GZB_OK;
-    }
-    GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_weak, 0xff, (size_t)size * sizeof(uint4), s));
-    k_weak_build<<<(n + 3) / 4, 128, 0, s>>>(g, ctx->d_weak_list, count, cap, ctx->d_weak, size - 1);
-    GZB_LAUNCH_CHECK(ctx);
-    g.weak = ctx->d_weak;
-    g.weak_mask = size - 1;
     return GZB_OK;
 }
 
@@ -1286,18 +987,9 @@ __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned*
 // A thread owns CH_PPT consecutive points (one composed map per thread goes through the block scan; a
 // 10-day track is ~600 blocks: one wave).  Blocks take their index from a ticket, so a block only ever
 // waits for blocks that already started.
-#ifdef GZB_CH_PPT
-#define CH_PPT GZB_CH_PPT
-#else
 #define CH_PPT 4
-#endif
 #define CH_PTS (FLAGS_BLOCK * CH_PPT)
-#ifdef GZB_CH_MINB
-#define CH_BOUNDS __launch_bounds__(FLAGS_BLOCK, GZB_CH_MINB)
-#else
-#define CH_BOUNDS __launch_bounds__(FLAGS_BLOCK)
-#endif
-__global__ void CH_BOUNDS
+__global__ void __launch_bounds__(FLAGS_BLOCK)
 k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
         const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
         long long* __restrict__ NP, long long* __restrict__ breaks, long long* __restrict__ blist, int* __restrict__ bcount,
@@ -1766,8 +1458,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
     if (threadIdx.x == 0) {      // (breaks, replay steps, ...) of this call, for gzb_get_stats
         stats_out[0] = scal[0];
         stats_out[1] = (long long)__ldcg(steps);
-        stats_out[2] = __ldcg(scal + 8);      // points that went to the warp search (after the seam pass)
-        for (int q = 3; q < 7; ++q) stats_out[q] = __ldcg(scal + q);   // k_near_search leftovers by reason (no seed, not converged, not proven); longest replay
+        for (int q = 2; q < 7; ++q) stats_out[q] = __ldcg(scal + q);   // k_near_search: unresolved (total, no seed, not converged, not proven); longest replay
     }
 }
 
@@ -1839,9 +1530,9 @@ size_t gzb_nearest_ws_bytes(int64_t nt) {
            + gzb_align(n * 16)       // first
            + gzb_align(n)            // valid
            + gzb_align(n * 8)        // replay log
-           + gzb_align(n * 8) * 2 + gzb_align(n * 4)   // unresolved lists (search, after the seam pass), hints
+           + gzb_align(n * 8) + gzb_align(n * 4)   // unresolved list, hints
            + gzb_align(n * 24)       // points whose nearest point differs from E(t): twin states + replay writes
-           + gzb_align(128) + gzb_align(64);      // scalars, corner
+           + gzb_align(64) * 2;      // scalars, corner
 }
 
 // device-level driver: all pointers are device pointers, work is enqueued on ctx->stream
@@ -1884,10 +1575,9 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     unsigned char* valid = (unsigned char*)gzb_arena_take(ctx, n);
     unsigned long long* wlog = (unsigned long long*)gzb_arena_take(ctx, n * 8);
     long long* ulist = (long long*)gzb_arena_take(ctx, n * 8);
-    long long* ulist2 = (long long*)gzb_arena_take(ctx, n * 8);
     unsigned* hint = (unsigned*)gzb_arena_take(ctx, n * 4);
     long long* chg = (long long*)gzb_arena_take(ctx, n * 24);
-    long long* scal = (long long*)gzb_arena_take(ctx, 128);      // [0] breaks [1] replay steps [2..5] search leftovers (total, by reason) [6] longest replay [7] changed points [8] left to the warp search
+    long long* scal = (long long*)gzb_arena_take(ctx, 64);
     if (!scal) return gzb_fail(ctx, GZB_ERR_NOMEM, "gzb_nearest: workspace too small");
     unsigned long long* nchg = (unsigned long long*)(scal + 7);
     if (!split) chg = nullptr;
@@ -1895,7 +1585,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     if (nchg_out) *nchg_out = nchg;
     if (gn_out) {
         gn_out->G = G; gn_out->dG = dG; gn_out->thr2 = 0.0; gn_out->edge = ctx->edge_exclusion;
-        gn_out->ulist = ulist2; gn_out->ucount = (const unsigned long long*)(scal + 8);
+        gn_out->ulist = ulist; gn_out->ucount = (const unsigned long long*)(scal + 2);
     }
     double* corner = (double*)(ctx->d_flags + 32);      // persistent: 4 doubles, keyed by np_box_r
     cudaStream_t s = ctx->stream;
@@ -1934,7 +1624,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
         p.rowsafe = ctx->d_rowsafe;
     }
 
-    GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 128, s));
+    GZB_CUDA(ctx, cudaMemsetAsync(scal, 0, 64, s));
     GZB_CUDA(ctx, cudaMemsetAsync(agg, 0, ((size_t)nblk + 3) * sizeof(unsigned), s));     // k_chain's ticket and block maps, the two done counters
     if (ctx->corner_r != np_box_r) {
         k_corner<<<1, 256, 0, s>>>(ctx->g, np_box_r, corner);
@@ -1964,9 +1654,6 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
                                                                  (unsigned long long*)(scal + 2));
 #endif
         GZB_LAUNCH_CHECK(ctx);
-        k_near_weak<<<64, 128, 0, s>>>(ctx->g, yt, xt, G, dG, ulist, hint, (const unsigned long long*)(scal + 2), ulist2,
-                                       (unsigned long long*)(scal + 8));
-        GZB_LAUNCH_CHECK(ctx);
         // from here on everything is latency-bound (the warp search of the few unresolved points, then
         // the chain): with `split` it goes to the auxiliary stream and the caller runs K2-K4 meanwhile on
         // E(t) = the plain global answers, which it derives from G / dG itself, skipping the unresolved points
@@ -1976,8 +1663,8 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
             GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
         }
         gzb_trace(ctx, s, "search end (main)");
-        k_near_slow<<<(unsigned)(nsm * 32 / SLOW_WARPS), 32 * SLOW_WARPS, 0, sb>>>(ctx->g, yt, xt, G, dG, ulist2, hint,
-                                                        (const unsigned long long*)(scal + 8));
+        k_near_slow<<<(unsigned)(nsm * 32 / SLOW_WARPS), 32 * SLOW_WARPS, 0, sb>>>(ctx->g, yt, xt, G, dG, ulist, hint,
+                                                        (const unsigned long long*)(scal + 2));
         GZB_LAUNCH_CHECK(ctx);
         sb_has_kernel = true;
         gzb_trace(ctx, sb, "slow end");

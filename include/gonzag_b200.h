@@ -53,7 +53,6 @@ typedef struct gzb_stats {
     int64_t  last_unres_nocert; /*   ... per-cell certificate not sufficient                  */
     int64_t  last_max_chain;    /* last gzb_nearest: longest sequential replay (steps)         */
     int64_t  heading_table;     /* 1 once the per-cell heading table of K2 has been built       */
-    int64_t  weak_cells;        /* grid cells in the weak-cell table of the per-thread search (0: none / not built) */
 } gzb_stats;
 
 const char* gzb_version(void);
@@ -70,6 +69,11 @@ int gzb_device_count(int* n_out);
 int gzb_create(int device, int64_t nj, int64_t ni, const double* lat, const double* lon,
                const double* angle_or_null, const int8_t* mask_or_null, int k_ew_per,
                gzb_ctx** ctx_out);
+/* gzb_create with the land-sea mask in the caller's integer type (HOST memory; 1, 2, 4 or 8 bytes per cell, values {0,1}):
+ * the reference's MG.mask is int64 (gonzag/ncio.py:164-191); the conversion to int8 rides on the upload's staging copies. */
+int gzb_create_imask(int device, int64_t nj, int64_t ni, const double* lat, const double* lon,
+                     const double* angle_or_null, const void* mask_or_null, int mask_itemsize, int k_ew_per,
+                     gzb_ctx** ctx_out);
 int gzb_destroy(gzb_ctx* ctx);
 const char* gzb_last_error(const gzb_ctx* ctx);
 int gzb_set_stream(gzb_ctx* ctx, void* cuda_stream);      /* a cudaStream_t; NULL = the legacy default stream */

@@ -153,6 +153,13 @@ class EmuLib:
         _target(h_out).value = self._next
         return L.GZB_OK
 
+    def gzb_create_imask(self, device, nj, ni, lat, lon, angle, mask, isz, kew, h_out):
+        if _addr(mask) and isz != 1:
+            m8 = np.ascontiguousarray(_view(mask, (nj, ni), {2: np.int16, 4: np.int32, 8: np.int64}[isz]).astype(np.int8))
+            self._keep_mask = m8
+            return self.gzb_create(device, nj, ni, lat, lon, angle, C.c_void_p(m8.ctypes.data), kew, h_out)
+        return self.gzb_create(device, nj, ni, lat, lon, angle, mask, kew, h_out)
+
     def gzb_destroy(self, h):
         self._ctx.pop(_addr(h), None)
         return L.GZB_OK
