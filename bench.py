@@ -324,6 +324,78 @@ def run_reference(args, w):
     emit(line)
 
 
+# ----------------------------------------------------------------------------- f2: streamed record providers
+def streamed_legs(gzb, L, torch, local, lat, lon, mask, angle_h, res, tmod_all, k_lo, host_field, tt, yy, xx, barrier, nrec=26):
+    import tempfile
+    import types
+    from scipy.io import netcdf_file
+    nrec = min(nrec, host_field.shape[0])
+    tm = np.ascontiguousarray(tmod_all[k_lo:k_lo + nrec])
+    sel = tt < tm[-1]
+    t1, y1, x1 = np.ascontiguousarray(tt[sel]), np.ascontiguousarray(yy[sel]), np.ascontiguousarray(xx[sel])
+    n1 = len(t1)
+    recs = np.array(host_field[:nrec])                       # a pageable copy: what a reader hands back
+    rec_bytes = recs[0].nbytes
+    ST = types.SimpleNamespace(size=n1, lat=y1, lon=x1, time=t1, file="mem", jt1=0, jt2=0, keepit=[], ssh=np.zeros(n1))
+    out = {"track_points": int(n1), "records": int(nrec), "record_bytes": int(rec_bytes)}
+
+    def run(MG, ctx, reps=3):
+        ts = []
+        R = None
+        for it in range(1 + reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            R = gzb.Model2SatTrack(MG, "ssh", ST, "ssh", device=local, ctx=ctx, keep_mapping=False)
+            torch.cuda.synchronize()
+            if it:
+                ts.append(time.perf_counter() - t0)
+            R.release()
+        return float(np.mean(ts)), R
+
+    with gzb.GridContext(lat, lon, angle=angle_h, mask=mask, k_ew_per=2, device=local) as ctx:
+        base = types.SimpleNamespace(shape=lat.shape, HResDeg=res, lat=lat, lon=lon, xangle=angle_h, EWPer=2, time=tm, file="mem",
+                                     mask=mask)
+        # (a) per-record callable over pageable memory
+        MGa = types.SimpleNamespace(**vars(base))
+        MGa.get_record = lambda k: recs[k]
+        ta, Ra = run(MGa, ctx)
+        used = len(np.unique(np.searchsorted(tm, t1, side="right") - 1)) + 1
+        out["per_record_callable"] = {"ms_per_call": ta * 1e3, "points_per_s": n1 / ta, "records_streamed": int(used),
+                                      "record_gb_per_s": used * rec_bytes / ta / 1e9, "fused_path": bool(Ra.fused_path)}
+        # (b) the same records in a NetCDF-3 file read by the built-in reader (memory map -> pinned slab, byte-swapped on the way)
+        tmp = tempfile.mkdtemp(prefix="gzbf2", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        path = os.path.join(tmp, "model.nc")
+        try:
+            with netcdf_file(path, "w", version=2) as f:
+                f.createDimension("time_counter", None)
+                f.createDimension("y", lat.shape[0])
+                f.createDimension("x", lat.shape[1])
+                v = f.createVariable("time_counter", "f8", ("time_counter",))
+                v.units = "seconds since 1970-01-01 00:00:00"
+                v.calendar = "gregorian"
+                v[:] = tm
+                v = f.createVariable("ssh", "f4", ("time_counter", "y", "x"))
+                v[:] = recs
+            src = gzb.NetCDF3Source(path)
+            MGb = types.SimpleNamespace(**vars(base))
+            MGb.source = src
+            MGb.file = path
+            tb, Rb = run(MGb, ctx)
+            out["netcdf3_file"] = {"ms_per_call": tb * 1e3, "points_per_s": n1 / tb, "records_streamed": int(used),
+                                   "record_gb_per_s": used * rec_bytes / tb / 1e9, "fused_path": bool(Rb.fused_path),
+                                   "file_bytes": int(os.path.getsize(path)), "where": os.path.dirname(path)}
+            same = (np.array_equal(np.ma.getdata(Ra.ssh_mod).view(np.int64), np.ma.getdata(Rb.ssh_mod).view(np.int64)))
+            out["providers_agree_bit_for_bit"] = bool(same)
+            src.close()
+        finally:
+            try:
+                os.remove(path)
+                os.rmdir(tmp)
+            except OSError:
+                pass
+    return out
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, w):
     import torch
@@ -718,6 +790,16 @@ def run_ours(args, w):
                                         "note": "same API call with ctx= a grid context kept on the GPU (no grid upload)"}
             except Exception as exc:          # never lose the bench line to the extras
                 e2e["extras_skipped"] = "%s: %s" % (type(exc).__name__, exc)
+        if world == 1 and not args.no_f2:
+            # ---- f2: the record STREAMING providers a real run uses -- one 2-D record at a time
+            # (gonzag/ncio.py:194-210 access shape) from pageable host memory, and from a NetCDF-3 file -- on the first day of
+            # the track (26 hourly records), grid resident.  Records go through the pinned staging slab into K4, copies
+            # overlapped with the gather; reported against the bytes of the records streamed.
+            try:
+                e2e["streamed"] = streamed_legs(gzb, L, torch, local, lat, lon, mask, angle_h, res, tmod_all, k_lo, host_field,
+                                                tt[s0:s1], yy[s0:s1], xx[s0:s1], barrier)
+            except Exception as exc:
+                e2e["streamed"] = {"skipped": "%s: %s" % (type(exc).__name__, exc)}
         del R
         L.pinned_free(host_field)
 
@@ -1212,6 +1294,7 @@ def main():
                          "publication kernel and a check kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-f2", action="store_true", help="skip the streamed-provider legs (e2e.streamed, N = 1)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the bit-exact check of the sharded result against "
                     "one GPU mapping the whole track (run by default, outside the timed region)")
     ap.add_argument("--verify", action="store_true", help=argparse.SUPPRESS)      # the default now; kept so that old command lines parse

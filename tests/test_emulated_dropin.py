@@ -89,3 +89,46 @@ def test_surface_functions(emu, golden_units, golden_surface):
     from tests import test_zz_gpu_surface as S
     S.test_haversine_family(golden_units)
     S.test_iqh(golden_surface)
+
+
+def test_mapping_cache_and_spectral_hand_off(emu, golden_grid, tmp_path):
+    """f4: (1) a mapping saved to disk and loaded for the same grid + track skips K1-K3 and reproduces the products; a file
+    that belongs to another track is ignored.  (2) The hand-off to the reference's spectral post-processing: its
+    `FindUnbrokenSegments(time, distance, ssh_mod)` (gonzag/spectralysis.py:42) cuts the drop-in's output into the very
+    segments it cuts the reference's own output into."""
+    import types
+    from oracle import ref_loader
+    from tests.conftest import grid_case_sources
+    g = golden_grid
+    model, track, lsm, varlsm, dist, Np = grid_case_sources(g, "a")
+    (it1, it2), _ = gz.GetEpochTimeOverlap(track, model)
+    MG = gz.ModGrid(model, it1, it2, lsm, varlsm, distorded_grid=dist)
+    try:
+        ST = gz.SatTrack(track, it1, it2, Np=Np, domain_bounds=MG.domain_bounds, l_0_360=MG.l360)
+        path = tmp_path / "mapping.npz"
+        assert gz.load_mapping(path, MG, ST) is None
+        R = gz.Model2SatTrack(MG, "ssh", ST, "ssh")
+        gz.save_mapping(path, R.BT, MG, ST)
+        cached = gz.load_mapping(path, MG, ST)
+        assert cached is not None and np.array_equal(cached.NP, R.BT.NP) and np.array_equal(cached.WB, R.BT.WB)
+        n0 = MG.ctx.stats()["kernel_launches"]
+        R2 = gz.Model2SatTrack(MG, "ssh", ST, "ssh", mapping=cached)
+        assert MG.ctx.stats()["kernel_launches"] - n0 < 12
+        T._check_results(R2, g, "a")
+        other = types.SimpleNamespace(size=ST.size - 1, lat=ST.lat[1:], lon=ST.lon[1:])
+        assert gz.load_mapping(path, MG, other) is None
+        moved = types.SimpleNamespace(size=ST.size, lat=ST.lat + 1.0e-3, lon=ST.lon)
+        assert gz.load_mapping(path, MG, moved) is None
+        # ---- spectral hand-off
+        root = ref_loader.find_reference()
+        if root is None:
+            pytest.skip("reference neither mounted nor copied (make -C oracle)")
+        ref, _ = ref_loader.load_reference(root)
+        want_mod = np.ma.MaskedArray(g["a_r_ssh_mod_data"], mask=g["a_r_ssh_mod_mask"])
+        a0, a1 = ref.FindUnbrokenSegments(g["a_st_time"], g["a_r_dist"], want_mod, rcut_time=1.2, rcut_dist=7.8)
+        b0, b1 = ref.FindUnbrokenSegments(R.time, R.distance, R.ssh_mod, rcut_time=1.2, rcut_dist=7.8)
+        assert len(a0) > 3
+        np.testing.assert_array_equal(a0, b0)
+        np.testing.assert_array_equal(a1, b1)
+    finally:
+        MG.close()
