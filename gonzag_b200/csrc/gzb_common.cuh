@@ -53,10 +53,7 @@ struct GzbGrid {
     const int8_t* mask;     // may be null
     const float* cells;     // per leaf tile: x[32] y[32] z[32] (unit vectors), tile row-major
     const float* cert;      // per leaf tile (same index as its node): chord distance from the tile
-                            // centre to the nearest cell outside the tile's WINDOW of leaf tiles
-    const unsigned char* wshape;   // per leaf tile: shape code of that window (gzb_window_shape): 5x3 tiles where cells are
-                            // about as tall as wide, wider or taller where they are not (converging meridians near a
-                            // displaced grid pole: a 5x3 window is a sliver there and proves nothing); null = 5x3 everywhere
+                            // centre to the nearest cell outside the tile's 5x3-tile neighbourhood
     const float4* cellv;    // per cell, row-major: unit vector (x,y,z) + w = lower bound of the chord
                             // from this cell to any cell outside its 5x5 index neighbourhood
     const double* hdg;      // optional per-cell table of K2 (6 doubles per cell): Mercator ordinate and
@@ -137,7 +134,6 @@ struct gzb_ctx {
     float* d_cells = nullptr;
     float4* d_nodes[GZB_MAXLEV] = {};
     float* d_cert = nullptr;
-    unsigned char* d_wshape = nullptr;
     float4* d_cellv = nullptr;
     unsigned* d_lut[2] = {nullptr, nullptr};
     unsigned* d_mbits = nullptr;     // land-sea mask as bits in 16x16-cell tiles (K4); d_flags[2] != 0: mask not {0,1}
@@ -369,22 +365,6 @@ __device__ __forceinline__ long long gzb_lut_bin(const GzbLut& L, double lat, do
         bi = fi >= (double)L.nlon ? L.nlon - 1 : (int)fi;
     }
     return (long long)bj * L.nlon + bi;
-}
-
-// window of leaf tiles around a tile, by shape code: half-extents (nbj, nbi) in tiles, (2 nbj + 1)(2 nbi + 1) <= 32
-#define GZB_NSHAPE 9
-__host__ __device__ __forceinline__ void gzb_window_shape(const int code, int& nbj, int& nbi) {
-    switch (code) {
-        case 1: nbj = 1; nbi = 2; break;
-        case 2: nbj = 1; nbi = 3; break;
-        case 3: nbj = 1; nbi = 4; break;
-        case 4: nbj = 0; nbi = 7; break;
-        case 5: nbj = 3; nbi = 1; break;
-        case 6: nbj = 4; nbi = 1; break;
-        case 7: nbj = 7; nbi = 0; break;
-        case 8: nbj = 2; nbi = 2; break;
-        default: nbj = 2; nbi = 1; break;      // 0: the 5x3 window
-    }
 }
 
 // index of leaf tile (tJ, tI) in the level-0 node array (and in GzbGrid::cert)

@@ -655,17 +655,12 @@ k_cellcert(const GzbGrid g, float4* __restrict__ cellv) {
     }
     float m2 = INFINITY;     // smallest chord^2 to a window cell outside the 5x5 neighbourhood
     float m3 = INFINITY;     // ... outside the 3x3 neighbourhood (m3 <= m2)
-    // the tile's window (its shape code: 5x3 tiles unless the cells are anisotropic), nearest tiles first -- rings of growing
-    // Chebyshev distance -- so that the far ones can be skipped
-    int nbj, nbi;
-    gzb_window_shape(g.wshape ? (int)g.wshape[tidx] : 0, nbj, nbi);
-    const int nring = nbj > nbi ? nbj : nbi;
-    for (int ring = 0; ring <= nring; ++ring) {
-        for (int q = 0; q < (2 * ring + 1) * (2 * ring + 1); ++q) {
-            const int dJ = q / (2 * ring + 1) - ring, dI = q % (2 * ring + 1) - ring;
-            if ((dJ > -ring && dJ < ring) && (dI > -ring && dI < ring)) continue;      // inner rings are done
-            if (dJ < -nbj || dJ > nbj || dI < -nbi || dI > nbi) continue;
-            const int wJ = tJ + dJ, wI = tI + dI;
+    // nearest tiles first, so that the far ones can be skipped
+    const int order_j[5] = {0, -1, 1, -2, 2};
+    const int order_i[3] = {0, -1, 1};
+    for (int a = 0; a < 5; ++a) {
+        for (int b = 0; b < 3; ++b) {
+            const int wJ = tJ + order_j[a], wI = tI + order_i[b];
             if (wJ < 0 || wJ >= L0.nJ || wI < 0 || wI >= L0.nI) continue;
             const float4 wn = L0.nodes[gzb_leaf_index(g, wJ, wI)];
             if (wn.w < 0.0f) continue;
@@ -810,9 +805,6 @@ static int build_pyramid(gzb_ctx* ctx) {
             GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_cert, (size_t)n * sizeof(float)));
             GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_cert, 0, (size_t)n * sizeof(float), ctx->stream));
             g.cert = ctx->d_cert;
-            GZB_CUDA(ctx, gzb_pool_malloc((void**)&ctx->d_wshape, (size_t)n));
-            GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_wshape, 0, (size_t)n, ctx->stream));
-            g.wshape = nullptr;
         }
     }
     {   // per-cell vectors + certificates of the per-thread search (optional: skipped when out of memory)
@@ -983,7 +975,6 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     gzb_pool_free(ctx->d_mask);
     gzb_pool_free(ctx->d_cells);
     gzb_pool_free(ctx->d_cert);
-    gzb_pool_free(ctx->d_wshape);
     gzb_pool_free(ctx->d_cellv);
     gzb_pool_free(ctx->d_lut[0]);
     gzb_pool_free(ctx->d_lut[1]);

@@ -253,13 +253,13 @@ __device__ __forceinline__ void pyramid_search(const GzbGrid& g, WarpSm& w, cons
 
 // K1a: the 5x3-tile window around tile (sJ, sI); returns true when the certificate proves that
 // no cell outside the window can tie or beat the best cell found inside it
+#define NBJ 2
+#define NBI 1
 template <int MODE>
 __device__ __forceinline__ bool window_search(const GzbGrid& g, WarpSm& w, const int lane, Srch& s, const int pt,
                                               const int sJ, const int sI, const long long j0, const long long j1,
                                               const long long i0, const long long i1, int& qn, const Owner& me) {
     const GzbLevel& L0 = g.lev[0];
-    int NBJ, NBI;      // the window of tile (sJ, sI): 5x3 tiles, or wider / taller where the cells are anisotropic
-    gzb_window_shape(g.wshape ? (int)g.wshape[gzb_leaf_index(g, sJ, sI)] : 0, NBJ, NBI);
     const int nJ = sJ + lane / (2 * NBI + 1) - NBJ;
     const int nI = sI + lane % (2 * NBI + 1) - NBI;
     const bool nv = (lane < (2 * NBJ + 1) * (2 * NBI + 1)) && nJ >= 0 && nJ < L0.nJ && nI >= 0 && nI < L0.nI;
@@ -790,7 +790,7 @@ k_near_slow(const GzbGrid g, const double* __restrict__ yt, const double* __rest
 
 // certificate of every leaf tile: chord from its centre to the nearest cell outside its window
 __global__ void __launch_bounds__(256)
-k_cert(const GzbGrid g, float* __restrict__ cert, unsigned char* __restrict__ wshape) {
+k_cert(const GzbGrid g, float* __restrict__ cert) {
     __shared__ WarpSm ws[8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GzbLevel L0 = g.lev[0];
@@ -800,39 +800,14 @@ k_cert(const GzbGrid g, float* __restrict__ cert, unsigned char* __restrict__ ws
     const int tJ = (int)(tile / L0.nI), tI = (int)(tile - (long long)tJ * L0.nI);
     const long long idx = gzb_leaf_index(g, tJ, tI);
     const float4 nd = L0.nodes[idx];
-    // shape of the tile's window: the one whose smaller half-extent (in space) is largest.  ey, ex = height and width of
-    // the tile from its corner cells (a full 4x8 tile; edge tiles with padded cells keep the 5x3 window)
-    int code = 0;
-    if (wshape) {
-        const float* __restrict__ cc = g.cells + tile * 96;
-        const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
-        const float x0 = __shfl_sync(0xffffffffu, x, 0), y0 = __shfl_sync(0xffffffffu, y, 0), z0 = __shfl_sync(0xffffffffu, z, 0);
-        const float x7 = __shfl_sync(0xffffffffu, x, 7), y7 = __shfl_sync(0xffffffffu, y, 7), z7 = __shfl_sync(0xffffffffu, z, 7);
-        const float xr = __shfl_sync(0xffffffffu, x, 24), yr = __shfl_sync(0xffffffffu, y, 24), zr = __shfl_sync(0xffffffffu, z, 24);
-        const bool full = fabsf(x7) < 2.0f && fabsf(xr) < 2.0f && fabsf(x0) < 2.0f;
-        if (full) {
-            const float ex = sqrtf((x7 - x0) * (x7 - x0) + (y7 - y0) * (y7 - y0) + (z7 - z0) * (z7 - z0)) * (8.0f / 7.0f);
-            const float ey = sqrtf((xr - x0) * (xr - x0) + (yr - y0) * (yr - y0) + (zr - z0) * (zr - z0)) * (4.0f / 3.0f);
-            float best = 1.5f * fminf(2.5f * ey, 1.5f * ex);      // the 5x3 window stays unless another shape reaches 1.5 x as far
-            for (int c = 1; c < GZB_NSHAPE; ++c) {
-                int a, b;
-                gzb_window_shape(c, a, b);
-                const float m = fminf(((float)a + 0.5f) * ey, ((float)b + 0.5f) * ex);
-                if (m > best) { best = m; code = c; }
-            }
-        }
-        if (lane == 0) wshape[idx] = (unsigned char)code;
-    }
-    int nbj, nbi;
-    gzb_window_shape(code, nbj, nbi);
     Srch s;
     srch_init(s, nd.x, nd.y, nd.z);
     Owner me;
     me.plat = me.plon = me.cpl = 0.0;
     int qn = 0;
-    pyramid_search<M_EXCL>(g, ws[warp], lane, s, 0, (long long)(tJ - nbj) * GZB_TILE_J,
-                           (long long)(tJ + nbj + 1) * GZB_TILE_J, (long long)(tI - nbi) * GZB_TILE_I,
-                           (long long)(tI + nbi + 1) * GZB_TILE_I, qn, me);
+    pyramid_search<M_EXCL>(g, ws[warp], lane, s, 0, (long long)(tJ - NBJ) * GZB_TILE_J,
+                           (long long)(tJ + NBJ + 1) * GZB_TILE_J, (long long)(tI - NBI) * GZB_TILE_I,
+                           (long long)(tI + NBI + 1) * GZB_TILE_I, qn, me);
     if (lane == 0) {
         float gval = INFINITY;
         if (s.Pmin < INFINITY) gval = fmaxf((sqrtf(s.Pmin) - 5.0e-7f) * (1.0f - 1.0e-6f), 0.0f);
@@ -842,12 +817,8 @@ k_cert(const GzbGrid g, float* __restrict__ cert, unsigned char* __restrict__ ws
 
 int gzb_build_cert(gzb_ctx* ctx) {
     const long long ntile = (long long)ctx->g.lev[0].nJ * ctx->g.lev[0].nI;
-    // (the kernel fills ctx->d_wshape; the grid struct only points at it afterwards, so that the search it runs itself
-    // still sees "no shapes")
-    ctx->g.wshape = nullptr;
-    k_cert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(ctx->g, ctx->d_cert, getenv("GZB_NO_WINDOW_SHAPES") ? nullptr : ctx->d_wshape);
+    k_cert<<<(unsigned)((ntile + 7) / 8), 256, 0, ctx->stream>>>(ctx->g, ctx->d_cert);
     GZB_LAUNCH_CHECK(ctx);
-    ctx->g.wshape = getenv("GZB_NO_WINDOW_SHAPES") ? nullptr : ctx->d_wshape;
     return GZB_OK;
 }
 
