@@ -91,7 +91,7 @@ static int launch_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_
 #define GZB_K4(EARLY, PF) k_interp<T, EARLY, PF><<<nblk, 256, 0, ctx->stream>>>(ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, \
         (const T*)slab, k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count, po)
     if (ctx->k4_early) GZB_K4(true, 0);
-    else if (pf && ctx->prefetch == 3) GZB_K4(false, 3);
+    else if (pf && ctx->prefetch >= 3) GZB_K4(false, 3);
     else if (pf && ctx->prefetch == 2) GZB_K4(false, 2);
     else if (pf) GZB_K4(false, 1);
     else GZB_K4(false, 0);

@@ -392,6 +392,41 @@ __device__ __forceinline__ void prefetch_point(const GzbGrid& g, const long long
     }
 }
 
+// Early prefetch (option "prefetch" = 4): everything a point will gather lies in the 3x3 index neighbourhood of its
+// nearest point -- the heading-table row and the angle of the cell, the coordinates of the mesh corners, the mask tile, and
+// in both bracketing records the field values -- but the kernel reaches them one dependent round trip after the other
+// (table -> quadrant -> corners -> Newton -> mask -> field).  Ask L2 for all of it the moment the nearest point is known:
+// the later loads then hit L2.  Costs the third (unused) row of the field and of the coordinates in DRAM traffic.
+template <typename T>
+__device__ __forceinline__ void prefetch_hood(const GzbGrid& g, const long long t, const InterpArgs& ia, const long long jP,
+                                              const long long iP) {
+    if (jP < 0 || iP < 0 || jP >= g.Nj || iP >= g.Ni) return;
+    const long long c = jP * g.Ni + iP;
+    const long long ja = jP > 0 ? jP - 1 : jP, jb = jP + 1 < g.Nj ? jP + 1 : jP;
+    const long long ia0 = iP > 0 ? iP - 1 : iP;
+    if (g.hdg) {
+        const double* h = g.hdg + GZB_EXP_HDG_STRIDE * c;
+        gzb_l2_prefetch(h);
+        gzb_l2_prefetch(h + 5);
+    }
+    if (g.angle) gzb_l2_prefetch(g.angle + c);
+    gzb_l2_prefetch(g.ll + ja * g.Ni + ia0);
+    gzb_l2_prefetch(g.ll + jP * g.Ni + ia0);
+    gzb_l2_prefetch(g.ll + jb * g.Ni + ia0);
+    if (ia.mbits) gzb_l2_prefetch(ia.mbits + ((jP >> 4) * ((g.Ni + 15) >> 4) + (iP >> 4)) * 8);
+    const double now = __ldg(ia.t_sat + t);
+    const double ta = __ldg(ia.tmod), tb = __ldg(ia.tmod + ia.nrec - 1);
+    if (!(now >= ta) || !(now < tb)) return;
+    long long lo = (long long)((now - ta) / (tb - ta) * (double)(ia.nrec - 1));
+    lo = lo < 0 ? 0 : (lo > ia.nrec - 2 ? ia.nrec - 2 : lo);
+    if (lo < ia.k0 || lo + 1 >= ia.k0 + ia.nk) return;
+    const long long cells = g.Nj * g.Ni;
+    const T* X1 = (const T*)ia.slab + (lo - ia.k0) * cells;
+    gzb_l2_prefetch(X1 + ja * g.Ni + iP); gzb_l2_prefetch(X1 + cells + ja * g.Ni + iP);
+    gzb_l2_prefetch(X1 + c);              gzb_l2_prefetch(X1 + cells + c);
+    gzb_l2_prefetch(X1 + jb * g.Ni + iP); gzb_l2_prefetch(X1 + cells + jb * g.Ni + iP);
+}
+
 #ifdef GZB_EXP_BULK_BLOCKS
 #define GZB_BULK_BOUNDS __launch_bounds__(128, GZB_EXP_BULK_BLOCKS)
 #else
@@ -407,6 +442,7 @@ k_mesh_weights_interp(const GzbGrid g, const long long t_first, const long long 
     const double yT = yt[t], xT = xt[t];
     long long cj[4], ci[4], jP, iP;
     if (!nearest_of(g, NP, gn, t, jP, iP)) return;
+    if (PF == 4) prefetch_hood<T>(g, t, ia, jP, iP);
     source_mesh_one(g, yT, xT, jP, iP, force_heavy, cj, ci);
     if (PF == 1) prefetch_point<T>(g, t, ia, cj, ci);
     longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
@@ -422,7 +458,7 @@ k_mesh_weights_interp(const GzbGrid g, const long long t_first, const long long 
     const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
     out[0] = rw[0];
     out[1] = rw[1];
-    interp_point<T, false, true, (PF == 3 ? 3 : 0)>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
+    interp_point<T, false, true, (PF >= 3 ? 3 : 0)>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
                                  ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
 }
 
@@ -488,7 +524,7 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0, nullptr, nullptr};
     const long long* npp = (const long long*)np;
     if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
-    const int pfm = !ctx->pf_now ? 0 : (ctx->prefetch == 3 ? 3 : 1);
+    const int pfm = !ctx->pf_now ? 0 : (ctx->prefetch >= 3 ? ctx->prefetch : 1);
     cudaStream_t s = ctx->stream;
     for (int c = 0; c < nchunk; ++c) {
         const long long a = ((nt * c / nchunk) + 127) & ~127LL, b = c + 1 == nchunk ? nt : (((nt * (c + 1) / nchunk) + 127) & ~127LL);
@@ -496,8 +532,8 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
         const unsigned nblk = (unsigned)((b - a + 127) / 128);
 #define GZB_BULK(T, PF) k_mesh_weights_interp<T, PF><<<nblk, 128, 0, s>>>(ctx->g, a, b, yt, xt, npp, gn, (long long*)sm_out, \
                                                                          wb_out, ctx->force_heavy, ia)
-        if (dtype == GZB_F32) { if (pfm == 3) GZB_BULK(float, 3); else if (pfm) GZB_BULK(float, 1); else GZB_BULK(float, 0); }
-        else                  { if (pfm == 3) GZB_BULK(double, 3); else if (pfm) GZB_BULK(double, 1); else GZB_BULK(double, 0); }
+        if (dtype == GZB_F32) { if (pfm == 4) GZB_BULK(float, 4); else if (pfm == 3) GZB_BULK(float, 3); else if (pfm) GZB_BULK(float, 1); else GZB_BULK(float, 0); }
+        else                  { if (pfm == 4) GZB_BULK(double, 4); else if (pfm == 3) GZB_BULK(double, 3); else if (pfm) GZB_BULK(double, 1); else GZB_BULK(double, 0); }
 #undef GZB_BULK
         GZB_LAUNCH_CHECK(ctx);
         if (push) {
