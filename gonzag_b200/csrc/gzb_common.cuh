@@ -58,6 +58,7 @@ struct GzbGrid {
                             // from this cell to any cell outside its 5x5 index neighbourhood
     const double* hdg;      // optional per-cell table of K2 (6 doubles per cell): Mercator ordinate and
                             // longitude (radians, [0,2pi)) of the cell, headings to its N, E, S, W neighbours
+    int* chk;               // CHECKED build (-DGZB_CHECKED=1): device word that collects violated bounds (see GZB_CHK); else unused
     GzbLut lut;
     int nlev;
     GzbLevel lev[GZB_MAXLEV];
@@ -138,7 +139,7 @@ struct gzb_ctx {
     unsigned* d_lut[2] = {nullptr, nullptr};
     unsigned* d_mbits = nullptr;     // land-sea mask as bits in 16x16-cell tiles (K4); d_flags[2] != 0: mask not {0,1}
     int mask_bits_ok = 0;
-    int prefetch = 0;                // bulk kernel: 1 = L2 prefetch of a point's eight field values + mask word as soon as its mesh is known (before the Newton solve)
+    int prefetch = 3;                // field gather from device-resident records: 3 (default) = 64-byte L2 fetches (K4 alone 38.9 -> 36.5 us, the fused kernel unchanged); 0 plain loads; 1 / 2 = L2 prefetch once the mesh is known (slower); 4 = prefetch of the whole 3x3 neighbourhood as soon as the nearest point is known (slower: 92 -> 98 us)
     int pf_now = 0;                  // ... resolved per call (off for host-resident slabs)
     int k4_early = 0;                // K4 load order: 1 field loads issued before the ocean test, 0 after it (measured faster)
     double* d_hdg = nullptr;         // heading table of K2 (48 B per cell), built on demand
@@ -185,6 +186,19 @@ int gzb_fail(gzb_ctx* ctx, int code, const char* fmt, ...);
 #ifdef __CUDACC__
 __device__ __forceinline__ void gzb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void gzb_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
+// ---- CHECKED build: GZB_NVCC_EXTRA="-DGZB_CHECKED=1" python -m gonzag_b200.build --force -----------------------------
+// compute-sanitizer is not available on the GPU pool, so the library carries its own bounds checks: every index a kernel
+// computes into a list, a log or a workspace slot, and every flat grid index before it is dereferenced, is compared with
+// its bound; a violation sets a bit of a device word (the access itself is skipped where it can be) and the next gzb_sync
+// fails with GZB_ERR_STATE naming the bits.  The product build compiles the checks away.
+//   1 unresolved list   2 break list   4 changed-points list   8 replay log / NP index   16 candidate queue
+//   32 flat grid index  64 mesh corner index  128 push range
+#ifdef GZB_CHECKED
+#define GZB_CHK(g, cond, bit) ((cond) ? true : (atomicOr((g).chk, (bit)), false))
+#else
+#define GZB_CHK(g, cond, bit) (true)
 #endif
 
 // ---- compile-time experiments (GZB_NVCC_EXTRA of gonzag_b200/build.py); all OFF in the product build ----------

@@ -32,7 +32,11 @@ int gzb_fail(gzb_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-extern "C" const char* gzb_version(void) { return "gonzag_b200 0.1 (sm_100a)"; }
+#ifdef GZB_CHECKED
+extern "C" const char* gzb_version(void) { return "gonzag_b200 0.2 (sm_100a, CHECKED build)"; }
+#else
+extern "C" const char* gzb_version(void) { return "gonzag_b200 0.2 (sm_100a)"; }
+#endif
 extern "C" const char* gzb_last_global_error(void) { return g_global_err; }
 extern "C" const char* gzb_last_error(const gzb_ctx* ctx) { return ctx ? ctx->err : g_global_err; }
 
@@ -926,6 +930,7 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
         memset(ctx->pinned, 0, 4096);
         ctx->pinned_cap = 4096;
 #undef CK
+        ctx->g.chk = ctx->d_flags + 4;
         ctx->g.Nj = nj;
         ctx->g.Ni = ni;
         ctx->g.kew = k_ew_per;
@@ -1031,7 +1036,21 @@ extern "C" int gzb_sync(gzb_ctx* ctx) {
     }
     if (ctx->barrier_err_pending)
         GZB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 72, ctx->d_flags + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
+#ifdef GZB_CHECKED
+    GZB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 80, ctx->d_flags + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
+#endif
     GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#ifdef GZB_CHECKED
+    {
+        int* h_c = (int*)((char*)ctx->pinned + 80);
+        if (*h_c) {
+            const int bits = *h_c;
+            *h_c = 0;
+            GZB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags + 4, 0, 4, ctx->stream));
+            return gzb_fail(ctx, GZB_ERR_STATE, "CHECKED build: a kernel computed an index outside its bound (bits 0x%x, see GZB_CHK)", bits);
+        }
+    }
+#endif
     if (ctx->barrier_err_pending) {
         ctx->barrier_err_pending = 0;
         int* h_b = (int*)((char*)ctx->pinned + 72);

@@ -60,6 +60,7 @@ __device__ __forceinline__ void cell_frame(const GzbGrid& g, const long long jP,
                                            const long long jm, const long long jp, const long long im,
                                            const long long ip, double& y0, double& x0, double& hN, double& hE,
                                            double& hS, double& hW) {
+    GZB_CHK(g, jm >= 0 && jp < g.Nj && im >= 0 && ip < g.Ni && jp >= 0 && ip >= 0, 64);
     const double2 cP = GZB_LDS_LDG(g.ll + (jP * g.Ni + iP)), cN = GZB_LDS_LDG(g.ll + (jp * g.Ni + iP));
     const double2 cE = GZB_LDS_LDG(g.ll + (jP * g.Ni + ip)), cS = GZB_LDS_LDG(g.ll + (jm * g.Ni + iP));
     const double2 cW = GZB_LDS_LDG(g.ll + (jP * g.Ni + im));
@@ -125,6 +126,7 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
                 double qy[4], qx[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
+                    GZB_CHK(g, cj[k] >= 0 && cj[k] < g.Nj && ci[k] >= 0 && ci[k] < g.Ni, 64);
                     const double2 c = GZB_LDS_LDG(g.ll + (cj[k] * g.Ni + ci[k]));
                     qy[k] = c.x;
                     qx[k] = c.y;
@@ -335,6 +337,7 @@ k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restr
     const long long n = n1 + (list2 ? (long long)*count2 : 0);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const long long t = e < n1 ? list[e] : list2[e - n1];
+        if (!GZB_CHK(g, t >= 0, 4)) continue;
         const double yT = yt[t], xT = xt[t];
         long long cj[4], ci[4];
         source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
@@ -477,9 +480,10 @@ static void fill_interp_args(gzb_ctx* ctx, InterpArgs& ia, const double* tt, int
 // sharded step, issued chunk by chunk on its own stream so that the NVLink stores of chunk c travel while the bulk kernel
 // works on chunk c+1 (the same stores issued from inside the bulk kernel throttle it: +120 us per step at 8 GPUs).
 __global__ void __launch_bounds__(256)
-k_push(const double* __restrict__ np_loc, const double* __restrict__ bl_loc, const GzbPeerOut peers, const long long a,
-       const long long b) {
+k_push(const GzbGrid g, const long long nt, const double* __restrict__ np_loc, const double* __restrict__ bl_loc,
+       const GzbPeerOut peers, const long long a, const long long b) {
     for (long long t = a + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < b; t += (long long)gridDim.x * blockDim.x) {
+        if (!GZB_CHK(g, t >= 0 && t < nt, 128)) continue;
         const double v = np_loc[t], w = bl_loc[t];
         for (int k = 0; k < peers.n; ++k) {
             peers.np[k][t] = v;
@@ -539,7 +543,7 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
         if (push) {
             GZB_CUDA(ctx, cudaEventRecord(ctx->ev_push[c], s));
             GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->push_stream, ctx->ev_push[c], 0));
-            k_push<<<64, 256, 0, ctx->push_stream>>>(vnp_out, vbl_out, peers, a, b);
+            k_push<<<64, 256, 0, ctx->push_stream>>>(ctx->g, nt, vnp_out, vbl_out, peers, a, b);
             GZB_LAUNCH_CHECK(ctx);
         }
     }

@@ -128,6 +128,7 @@ __device__ __forceinline__ void flush_queue(const GzbGrid& g, WarpSm& w, const i
         long long flat = 0;
         if (act) {
             flat = w.qflat[e];
+            if (!GZB_CHK(g, flat >= 0 && flat < g.Nj * g.Ni, 32)) flat = 0;
             const double2 c = __ldg(g.ll + flat);
             const double d = gzb_haversine_dev(plat, plon, cpl, c.x, c.y);
             if (d == d) dbits = (unsigned long long)__double_as_longlong(d); else act = false;
@@ -177,9 +178,11 @@ __device__ __forceinline__ void leaf_eval(const GzbGrid& g, WarpSm& w, const int
             if (qn + nnew > GZB_QCAP) flush_queue(g, w, lane, qn, me);
             if (cand) {
                 const int pos = qn + __popc(cm & ((1u << lane) - 1u));
-                w.qpt[pos] = pt;
-                w.qP[pos] = P;
-                w.qflat[pos] = j * g.Ni + i;
+                if (GZB_CHK(g, pos >= 0 && pos < GZB_QCAP, 16)) {
+                    w.qpt[pos] = pt;
+                    w.qP[pos] = P;
+                    w.qflat[pos] = j * g.Ni + i;
+                }
             }
             qn += nnew;
         }
@@ -569,6 +572,7 @@ __device__ __forceinline__ void exact_from_cand(const GzbGrid& g, const long lon
     if (c & CAND_NONE) return;
     const double cpl = cos(lat * GZB_D2R);
     const long long f0 = CAND_FLAT(c);
+    if (!GZB_CHK(g, f0 >= 0 && f0 < g.Nj * g.Ni, 32)) return;
     if (!(c & CAND_MULTI)) {
         const double2 c0 = __ldg(g.ll + f0);
         const double d = gzb_haversine_dev(lat, lon, cpl, c0.x, c0.y);
@@ -722,7 +726,7 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
         unsigned long long base = 0;
         if (lane == (__ffs(um) - 1)) base = atomicAdd(ucount, (unsigned long long)__popc(um));
         base = __shfl_sync(0xffffffffu, base, __ffs(um) - 1);
-        if (unresolved) {
+        if (unresolved && GZB_CHK(g, (long long)(base + __popc(um & ((1u << lane) - 1u))) < nt, 1)) {
             ulist[base + __popc(um & ((1u << lane) - 1u))] = t;
             hint[t] = myhint;
             G[t] = GZB_UNRESOLVED;
@@ -1096,7 +1100,10 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
             if (out == 1u) {
                 rj = q[k].tj;
                 ri = q[k].ti;
-                if (chg) chg[atomicAdd(nchg, 1ull)] = t0 + k;      // differs from E(t): K2-K4 of this point are redone (gzb_mapping overlap)
+                if (chg) {      // differs from E(t): K2-K4 of this point are redone (gzb_mapping overlap)
+                    const unsigned long long cp = atomicAdd(nchg, 1ull);
+                    if (GZB_CHK(g, cp < 3ull * (unsigned long long)nt, 4)) chg[cp] = t0 + k;
+                }
             }
             reinterpret_cast<longlong2*>(NP)[t0 + k] = make_longlong2(rj, ri);
             if (out == 2u) bmask |= 1u << k;
@@ -1127,7 +1134,10 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
         long long pos = (long long)bid * CH_PTS + wbase + (wincl - mycnt);
 #pragma unroll
         for (int k = 0; k < CH_PPT; ++k)
-            if (bmask & (1u << k)) blist[pos++] = t0 + k;
+            if (bmask & (1u << k)) {
+                if (GZB_CHK(g, pos >= (long long)bid * CH_PTS && pos < (long long)(bid + 1) * CH_PTS, 2)) blist[pos] = t0 + k;
+                ++pos;
+            }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1162,7 +1172,8 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
         if (ctot) {
             // (block, position) pairs of this chunk: the chunk's breaks, cut over the threads of the block
             const long long excl = carry + wb2 + (incl2 - cnt);
-            for (int e = 0; e < cnt; ++e) breaks[excl + e] = __ldcg(blist + bk * CH_PTS + e);
+            for (int e = 0; e < cnt; ++e)
+                if (GZB_CHK(g, excl + e >= 0 && excl + e < nt && e < CH_PTS, 2)) breaks[excl + e] = __ldcg(blist + bk * CH_PTS + e);
         }
         carry += ctot;
     }
@@ -1303,14 +1314,17 @@ __device__ __forceinline__ void replay(const GzbGrid& g, const NearParams& p, Wa
             }
             ++n;
             if (WRITE) {
-                if (lane == 0) {
+                if (lane == 0 && GZB_CHK(g, t >= 0 && t < nt, 8)) {
                     NP[2 * t] = rj;
                     NP[2 * t + 1] = ri;
-                    if (chg) chg[atomicAdd(nchg, 1ull)] = t;
+                    if (chg) {
+                        const unsigned long long cp = atomicAdd(nchg, 1ull);
+                        if (GZB_CHK(g, cp < 3ull * (unsigned long long)nt, 4)) chg[cp] = t;
+                    }
                 }
                 if (t >= tend) { done = true; break; }
             } else {
-                if (lane == 0) {
+                if (lane == 0 && GZB_CHK(g, t >= 0 && t < nt, 8)) {
                     wlog[t] = WLOG_TAG(k) | (unsigned long long)(rj < 0 ? 0 : rj * g.Ni + ri + 1);
                     if (t == b) {
                         first[2 * k] = rj;
@@ -1417,10 +1431,14 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
     for (long long k = threadIdx.x; k < nb; k += blockDim.x) {
         if (!valid[k]) continue;
         const long long b = breaks[k], e = __ldcg(stop + k);
+        if (!GZB_CHK(g, b >= 0 && b < nt && e >= b && e < nt, 8)) continue;
         if (e == b) {
             NP[2 * b] = __ldcg(first + 2 * k);
             NP[2 * b + 1] = __ldcg(first + 2 * k + 1);
-            if (chg) chg[atomicAdd(nchg, 1ull)] = b;
+            if (chg) {
+                const unsigned long long cp = atomicAdd(nchg, 1ull);
+                if (GZB_CHK(g, cp < 3ull * (unsigned long long)nt, 4)) chg[cp] = b;
+            }
             continue;
         }
         bool ok = (e - b) < TAIL_SHORT;
@@ -1446,7 +1464,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
                 if (f >= 0) gzb_split(g, f, j, i);
                 NP[2 * (b + q)] = j;
                 NP[2 * (b + q) + 1] = i;
-                if (chg) chg[base + q] = b + q;
+                if (chg && GZB_CHK(g, base + q < 3ull * (unsigned long long)nt, 4)) chg[base + q] = b + q;
             }
         }
     }

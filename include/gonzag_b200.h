@@ -100,11 +100,12 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * columns (two-state scan, far fewer replays); 0 plain speculation + replays.  Same results.
  * "fuse_k4": 1 (default) gzb_map_interp runs K2+K3+K4 as one kernel; 0 K2+K3 then K4.
  * "k4_early", "mask_bits": K4 variants (load order; tiled bit mask on/off).  Same results.
- * "prefetch": variants of the field gather for device-resident slabs, same results: 0 (default) plain
- * loads; 1 = L2 prefetch of a point's eight field values as soon as its mesh is known (2: the same with
- * 64 registers in K4) -- measured slower; 3 = the eight values are loaded with a 64-byte L2 fetch
- * (ld.global.nc.L2::64B: a plain sparse load fills a whole 128-byte line from DRAM on B200) --
- * K4 alone 39.0 -> 36.1 us, the fused kernel unchanged.
+ * "prefetch": variants of the field gather for device-resident slabs, same results: 3 (default) = the eight values are
+ * loaded with a 64-byte L2 fetch (ld.global.nc.L2::64B: a plain sparse load fills a whole 128-byte line from DRAM on
+ * B200) -- K4 alone 38.9 -> 36.5 us, the fused kernel unchanged; 0 = plain loads; 1 = L2 prefetch of a point's eight field
+ * values as soon as its mesh is known (2: the same with 64 registers in K4) -- measured slower; 4 = L2 prefetch of the
+ * whole 3x3 neighbourhood (table row, angle, coordinates, mask tile, field rows of both records) as soon as the nearest
+ * point is known -- measured slower (fused kernel 92 -> 98 us: it is not DRAM-latency bound).
  * "pdl": 1 (default) the kernels of K1's chain part (k_chain, k_compact, k_walk, k_valid), which follow each
  * other on one stream, are launched as programmatic dependents (griddepcontrol.wait at their top): the
  * launch of each overlaps the tail of the one before it (gzb_nearest 158 -> 143 us on ORCA12); 0 plain

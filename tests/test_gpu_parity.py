@@ -439,7 +439,8 @@ def test_launch_and_memory_options_do_not_change_results(golden_global):
         o = [ctx.dev_alloc(n * k) for k in (16, 64, 32, 8, 8)]
         P = lambda b: C.c_void_p(b.ptr)
         ref = None
-        for opts in ({"pdl": 1, "prefetch": 0}, {"pdl": 0}, {"pdl": 1, "prefetch": 1}, {"prefetch": 2}, {"prefetch": 3},
+        for opts in ({"pdl": 1, "prefetch": 0}, {"pdl": 0}, {"pdl": 1, "prefetch": 1}, {"prefetch": 2}, {"prefetch": 3}, {"prefetch": 4},
+                     {"bulk_chunks": 3, "prefetch": 3}, {"bulk_chunks": 0},
                      {"prefetch": 0, "l2_fetch": 32}, {"l2_fetch": 128}, {"l2_fetch": 64}):
             for k, v in opts.items():
                 ctx.set_option(k, v)
