@@ -436,6 +436,8 @@ def run_ours(args, w):
 
     ctx = gzb.GridContext(lat, lon, mask=mask, k_ew_per=2, device=local)
     ctx.set_option("heading_table", args.heading_table)
+    if args.bulk_chunks >= 0:
+        ctx.set_option("bulk_chunks", args.bulk_chunks)
     eng = CudaEngine(ctx, torch)
     Mapper = P2PShardedMapper if (world > 1 and args.gather in ("p2p", "p2p-root")) else ShardedMapper
     mapper = Mapper(eng, dist if world > 1 else None, torch)
@@ -1292,6 +1294,8 @@ def main():
                     help="with --gather p2p: how the ranks are ordered at the end of a step: p2p = ONE own kernel over peer memory "
                          "(edge words + barrier + boundary check, gzb_peer_finish); nccl = one-word NCCL all-reduce between an edge "
                          "publication kernel and a check kernel")
+    ap.add_argument("--bulk-chunks", type=int, default=-1, help="N > 1: chunks of the bulk kernel behind which the peer copies are "
+                    "issued (0 = the library's choice, the default)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-f2", action="store_true", help="skip the streamed-provider legs (e2e.streamed, N = 1)")

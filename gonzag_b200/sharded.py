@@ -229,10 +229,17 @@ class ShardedModel2SatTrack(_LazyXNPMixin):
                 raise RuntimeError("segment boundaries did not settle in %d rounds" % world)
 
             # ---- a14 on the segment, then the gather
-            vssh_s = satellite_ssh(ST, name_ssh_sat)
-            if vssh_s.shape != (Nt,):
-                raise ValueError("the satellite series has %s values, the track %d points" % (vssh_s.shape, Nt))
-            job.distance_and_mask(np.ascontiguousarray(vssh_s[s0:s1]))
+            ssh_attr = getattr(ST, "ssh", None)
+            if ssh_attr is not None and not self.complete and np.shape(ssh_attr) == (Nt,):
+                vssh_s = None                                   # this rank only needs its own slice: no whole-track copy
+                my_sat = np.ascontiguousarray(np.ma.filled(np.ma.asarray(ssh_attr[s0:s1], dtype=np.float64), float(config.rmissval))
+                                              if isinstance(ssh_attr, np.ma.MaskedArray) else ssh_attr[s0:s1], dtype=np.float64)
+            else:
+                vssh_s = satellite_ssh(ST, name_ssh_sat)
+                if vssh_s.shape != (Nt,):
+                    raise ValueError("the satellite series has %s values, the track %d points" % (vssh_s.shape, Nt))
+                my_sat = np.ascontiguousarray(vssh_s[s0:s1])
+            job.distance_and_mask(my_sat)
             tim["segment_issue_s"] = time.perf_counter() - tc
             tc = time.perf_counter()
             off = job.off
