@@ -521,7 +521,8 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
     const GzbPeerOut peers = ia.peers;
     // with peer outputs the bulk kernel writes locally only and runs in chunks; k_push copies each finished chunk
-    int nchunk = ctx->bulk_chunks > 0 ? ctx->bulk_chunks : (peers.n > 0 ? 4 : 1);
+    // (measured at 2 GPUs: every extra chunk costs ~3 us of launch gap and tail; worth it once several peers' copies queue up)
+    int nchunk = ctx->bulk_chunks > 0 ? ctx->bulk_chunks : (peers.n >= 3 ? 4 : 1);
     if (nt < 4096 * nchunk) nchunk = 1;
     const bool push = peers.n > 0;
     if (push) ia.peers.n = 0;

@@ -23,9 +23,25 @@ PY
 run C3 --steps 10 --warmup 3
 run C5 --workload C5 --steps 3 --warmup 1
 run C4 --workload C4 --steps 3 --warmup 1
+if [ "$N" = "8" ] || [ "$N" = "4" ]; then
+  run C3chunks1 --steps 10 --warmup 3 --no-e2e --bulk-chunks 1
+  run C3chunks4 --steps 10 --warmup 3 --no-e2e --bulk-chunks 4
+  run C3chunks2 --steps 10 --warmup 3 --no-e2e --bulk-chunks 2
+fi
 if [ "$N" = "8" ]; then
   run C3nccl --steps 10 --warmup 3 --barrier nccl --no-e2e
   run C3gathernccl --steps 10 --warmup 3 --gather nccl --no-e2e
 fi
 grep -h "nranks" $OUT/scale_C3_n${N}_$TAG.err | head -2
+if [ "$N" = "8" ]; then      # the smaller worlds on the same box (what the driver's scaling run does): C3 weak at 1, 2, 4
+  for M in 1 2 4; do
+    TRM="python -m torch.distributed.run --nnodes=1 --nproc-per-node $M --master-addr 127.0.0.1 --master-port 29543"
+    timeout 300 $TRM bench.py --gpus $M --steps 10 --warmup 3 --no-cpu --no-f2 > $OUT/scale_C3_n${M}on8_$TAG.json 2> $OUT/scale_C3_n${M}on8_$TAG.err
+    python - $OUT/scale_C3_n${M}on8_$TAG.json $M <<'PY'
+import json, sys
+b = json.load(open(sys.argv[1])); e = b.get("e2e") or {}
+print("   same box, N=%s: value %.4g pts/s  ms/step %.4f  e2e %s ms  verified %s" % (sys.argv[2], b["value"], b["ms_per_step"], e.get("ms_per_step"), b.get("verified")))
+PY
+  done
+fi
 echo "done ($((SECONDS-t0)) s)"
