@@ -155,6 +155,7 @@ struct gzb_ctx {
     size_t stage_cap = 0;
     int nearest_stats_pending = 0;
     int edge_exclusion = 1;          // 0: plain NearestPoint() semantics (no BilinTrack.nrpt edge rule)
+    int force_ix64 = 0;              // option "ix64": 1 = K2-K4 run their 64-bit index variants whatever the grid size (tests)
     int force_heavy = 0;             // 1: heavy-duty quadrant search even if the light test succeeds; 2: skip the light test
     int time_err_pending = 0;
     int barrier_err_pending = 0;     // d_flags[3] != 0: a peer barrier timed out (checked by gzb_sync)

@@ -1110,6 +1110,7 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "bulk_chunks")) { ctx->bulk_chunks = value < 0 ? 0 : (value > 8 ? 8 : (int)value); return GZB_OK; }
     if (!strcmp(name, "k4_early")) { ctx->k4_early = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "pdl")) { ctx->pdl = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "ix64")) { ctx->force_ix64 = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "prefetch")) { ctx->prefetch = value < 0 ? 0 : (value > 4 ? 4 : (int)value); return GZB_OK; }
     if (!strcmp(name, "l2_fetch")) {      // device-wide hint (cudaLimitMaxL2FetchGranularity): 32, 64 or 128 bytes
         if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;

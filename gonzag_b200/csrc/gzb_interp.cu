@@ -33,10 +33,15 @@ k_mask_bits(const long long Nj, const long long Ni, const int8_t* __restrict__ m
     if (odd) atomicOr(flag, 1);
 }
 
+// resident blocks of 256 threads per SM for the 32-bit index variant of K4 (6 = a cap of 40 registers)
+#ifndef GZB_K4_BLOCKS
+#define GZB_K4_BLOCKS 6
+#endif
+
 // `list` == nullptr: thread per point t < nt.  Otherwise only the *count points listed (the ones
 // whose mesh changed after a speculative pass, gzb_map_interp), grid-stride.
-template <typename T, bool EARLY, int PF>      // PF: 0 no prefetch, 1 prefetch, 2 prefetch with 64 registers (4 blocks per SM)
-__global__ void __launch_bounds__(256, (EARLY || PF == 2) ? 4 : 5)
+template <typename T, bool EARLY, int PF, typename IX>      // PF: 0 no prefetch, 1 prefetch, 2 prefetch with 64 registers (4 blocks per SM); IX: gzb_point.cuh
+__global__ void __launch_bounds__(256, (EARLY || PF == 2) ? 4 : (sizeof(IX) == 4 ? GZB_K4_BLOCKS : 5))
 k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
          const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
          const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
@@ -47,11 +52,11 @@ k_interp(const GzbGrid g, const long long nt, const double* __restrict__ t_sat,
     if (list) {
         const long long n = (long long)*count;
         for (long long e = gt; e < n; e += (long long)gridDim.x * blockDim.x)
-            interp_point<T, EARLY, false, PF>(g, list[e], t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl,
-                                              err, mbits, mflag, peers);
+            interp_point<T, EARLY, false, PF, IX>(g, list[e], t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl,
+                                                  err, mbits, mflag, peers);
     } else if (gt < nt) {
-        interp_point<T, EARLY, false, PF>(g, gt, t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl, err,
-                                          mbits, mflag, peers);
+        interp_point<T, EARLY, false, PF, IX>(g, gt, t_sat, SM, WB, nrec, tmod, slab, k0, nk, rmiss, init, out_np, out_bl, err,
+                                              mbits, mflag, peers);
     }
 }
 
@@ -88,14 +93,17 @@ static int launch_interp(gzb_ctx* ctx, int64_t nt, const double* t, const int64_
         if (cudaPointerGetAttributes(&at, slab) == cudaSuccess) pf = at.type == cudaMemoryTypeDevice;
         else cudaGetLastError();
     }
-#define GZB_K4(EARLY, PF) k_interp<T, EARLY, PF><<<nblk, 256, 0, ctx->stream>>>(ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, \
+    const bool ix32 = ctx->g.Nj * ctx->g.Ni < 0x7fffffffLL && !ctx->force_ix64;
+#define GZB_K4I(EARLY, PF, IX) k_interp<T, EARLY, PF, IX><<<nblk, 256, 0, ctx->stream>>>(ctx->g, nt, t, (const long long*)sm, wb, nrec, tmod, \
         (const T*)slab, k0, nk, rmiss, init, np_out, bl_out, err, mb, ctx->d_flags + 2, list, count, po)
-    if (ctx->k4_early) GZB_K4(true, 0);
-    else if (pf && ctx->prefetch >= 3) GZB_K4(false, 3);
-    else if (pf && ctx->prefetch == 2) GZB_K4(false, 2);
-    else if (pf) GZB_K4(false, 1);
-    else GZB_K4(false, 0);
+#define GZB_K4(EARLY, PF) { if (ix32) GZB_K4I(EARLY, PF, int); else GZB_K4I(EARLY, PF, long long); }
+    if (ctx->k4_early) GZB_K4(true, 0)
+    else if (pf && ctx->prefetch >= 3) GZB_K4(false, 3)
+    else if (pf && ctx->prefetch == 2) GZB_K4(false, 2)
+    else if (pf) GZB_K4(false, 1)
+    else GZB_K4(false, 0)
 #undef GZB_K4
+#undef GZB_K4I
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }

@@ -2,29 +2,31 @@
 //   K2 restates BilinTrack.srcm / IDSourceMesh / Iquadran / Iquadran2SrcMesh / surrounding_j_i
 //      (gonzag/bilin_mapping.py:595-608, 453-486, 329-449, 215-262, 194-212)
 //   K3 restates BilinTrack.wght / WeightBL / AlfaBeta (gonzag/bilin_mapping.py:610-617, 490-527, 50-141)
+// The per-point functions are templates on the index type IX (gzb_point.cuh): `int` for grids of fewer than 2^31 cells.
 #include "gzb_common.cuh"
 #include "gzb_point.cuh"
 
 // gonzag/bilin_mapping.py:194-212; -1 flags a missing neighbour
-__device__ __forceinline__ void neighbours(const GzbGrid& g, long long jP, long long iP, long long& jm,
-                                           long long& jp, long long& im, long long& ip) {
+template <typename IX>
+__device__ __forceinline__ void neighbours(const GzbGrid& g, IX jP, IX iP, IX& jm, IX& jp, IX& im, IX& ip) {
+    const IX Nj = (IX)g.Nj, Ni = (IX)g.Ni;
     jm = jP - 1;
     jp = jP + 1;
     im = iP - 1;
     ip = iP + 1;
-    if (jp == g.Nj) jp = -1;
+    if (jp == Nj) jp = -1;
     if (im == -1) {
-        if (g.kew >= 0) im = g.Ni - g.kew - 1;
+        if (g.kew >= 0) im = Ni - g.kew - 1;
     }
-    if (ip == g.Ni) {
+    if (ip == Ni) {
         ip = -1;
         if (g.kew >= 0) ip = g.kew;
     }
 }
 
 // gonzag/bilin_mapping.py:241-260: the three other corners, counter-clockwise from P
-__device__ __forceinline__ void quad_corners(int iq, long long jP, long long iP, long long jm, long long jp,
-                                             long long im, long long ip, long long* cj, long long* ci) {
+template <typename IX>
+__device__ __forceinline__ void quad_corners(int iq, IX jP, IX iP, IX jm, IX jp, IX im, IX ip, IX* cj, IX* ci) {
     cj[0] = jP; ci[0] = iP;
     if (iq == 1)      { cj[1] = jP; ci[1] = ip; cj[2] = jp; ci[2] = ip; cj[3] = jp; ci[3] = iP; }
     else if (iq == 2) { cj[1] = jm; ci[1] = iP; cj[2] = jm; ci[2] = ip; cj[3] = jP; ci[3] = ip; }
@@ -54,16 +56,22 @@ __device__ __forceinline__ bool strictly_in_quad(double py, double px, const dou
     return wn != 0;
 }
 
+// coordinates of cell (j, i)
+template <typename IX>
+__device__ __forceinline__ double2 cell_ll(const GzbGrid& g, const IX j, const IX i) {
+    return GZB_LDS_LDG(g.ll + (j * (IX)g.Ni + i));
+}
+
 // the grid-only part of Iquadran's light test (gonzag/bilin_mapping.py:377-397): Mercator ordinate
 // and longitude of P, loxodromic headings from P to its four neighbours, hN already brought below hE
-__device__ __forceinline__ void cell_frame(const GzbGrid& g, const long long jP, const long long iP,
-                                           const long long jm, const long long jp, const long long im,
-                                           const long long ip, double& y0, double& x0, double& hN, double& hE,
+template <typename IX>
+__device__ __forceinline__ void cell_frame(const GzbGrid& g, const IX jP, const IX iP, const IX jm, const IX jp, const IX im,
+                                           const IX ip, double& y0, double& x0, double& hN, double& hE,
                                            double& hS, double& hW) {
     GZB_CHK(g, jm >= 0 && jp < g.Nj && im >= 0 && ip < g.Ni && jp >= 0 && ip >= 0, 64);
-    const double2 cP = GZB_LDS_LDG(g.ll + (jP * g.Ni + iP)), cN = GZB_LDS_LDG(g.ll + (jp * g.Ni + iP));
-    const double2 cE = GZB_LDS_LDG(g.ll + (jP * g.Ni + ip)), cS = GZB_LDS_LDG(g.ll + (jm * g.Ni + iP));
-    const double2 cW = GZB_LDS_LDG(g.ll + (jP * g.Ni + im));
+    const double2 cP = cell_ll<IX>(g, jP, iP), cN = cell_ll<IX>(g, jp, iP);
+    const double2 cE = cell_ll<IX>(g, jP, ip), cS = cell_ll<IX>(g, jm, iP);
+    const double2 cW = cell_ll<IX>(g, jP, im);
     const double lat0 = cP.x, lonP = cP.y, latN = cN.x, lonN = cN.y, latE = cE.x, lonE = cE.y;
     const double latS = cS.x, lonS = cS.y, latW = cW.x, lonW = cW.y;
     y0 = gzb_merc_y(lat0);
@@ -76,39 +84,41 @@ __device__ __forceinline__ void cell_frame(const GzbGrid& g, const long long jP,
 }
 
 // can a quadrant be looked for around (jP, iP)?  (all four neighbours exist)
-__device__ __forceinline__ bool mesh_usable(const GzbGrid& g, const long long jP, const long long iP, long long& jm,
-                                            long long& jp, long long& im, long long& ip) {
-    if (!(jP >= 0 && jP < g.Nj && iP >= 0 && iP < g.Ni)) return false;
-    neighbours(g, jP, iP, jm, jp, im, ip);
+template <typename IX>
+__device__ __forceinline__ bool mesh_usable(const GzbGrid& g, const IX jP, const IX iP, IX& jm, IX& jp, IX& im, IX& ip) {
+    const IX Nj = (IX)g.Nj, Ni = (IX)g.Ni;
+    if (!(jP >= 0 && jP < Nj && iP >= 0 && iP < Ni)) return false;
+    neighbours<IX>(g, jP, iP, jm, jp, im, ip);
     if (jm == -1 || jp == -1 || im == -1 || ip == -1) return false;
-    if (im < 0 || jm < 0 || ip > g.Ni - 1) return false;
+    if (im < 0 || jm < 0 || ip > Ni - 1) return false;
     return true;
 }
 
 // source mesh of one point: corners P1(nearest)..P4 counter-clockwise, all -1 when no quadrant
 // is found, all 0 when the nearest point itself was not found
+template <typename IX>
 __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double yT, const double xT,
-                                                const long long jP, const long long iP, const int force_heavy,
-                                                long long* cj, long long* ci) {
+                                                const IX jP, const IX iP, const int force_heavy, IX* cj, IX* ci) {
     if (jP == -1 && iP == -1) {   // nearest point not found: the row stays zero
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cj[k] = 0; ci[k] = 0; }
         return;
     }
     int iq = -1;
-    long long jm = 0, jp = 0, im = 0, ip = 0;
-    const bool usable = mesh_usable(g, jP, iP, jm, jp, im, ip);
+    IX jm = 0, jp = 0, im = 0, ip = 0;
+    const bool usable = mesh_usable<IX>(g, jP, iP, jm, jp, im, ip);
     if (usable) {
         // five headings from P (to the target and to the N, E, S, W neighbours): the Mercator
         // ordinate of P is common to all of them; the four that depend on the grid only come from
         // the per-cell table when it has been built (same code, same bits)
         double y0, x0, hN, hE, hS, hW;
+        const IX cP = jP * (IX)g.Ni + iP;
         if (g.hdg) {
-            const double2* __restrict__ h = reinterpret_cast<const double2*>(g.hdg + GZB_EXP_HDG_STRIDE * (jP * g.Ni + iP));
+            const double2* __restrict__ h = reinterpret_cast<const double2*>(g.hdg + (long long)GZB_EXP_HDG_STRIDE * cP);
             const double2 a = GZB_LDS_REF(h), b = GZB_LDS_REF(h + 1), c = GZB_LDS_REF(h + 2);
             y0 = a.x; x0 = a.y; hN = b.x; hE = b.y; hS = c.x; hW = c.y;
         } else {
-            cell_frame(g, jP, iP, jm, jp, im, ip, y0, x0, hN, hE, hS, hW);
+            cell_frame<IX>(g, jP, iP, jm, jp, im, ip, y0, x0, hN, hE, hS, hW);
         }
         const double ht = gzb_heading_y(y0, x0, gzb_merc_y(yT), gzb_pymod(xT, 360.0) * GZB_D2R);
         const double hz = gzb_pm180(ht);
@@ -118,16 +128,16 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
             if (ht > hS && ht <= hW) iq = 3;
             if (ht > hW && hz <= hN) iq = 4;
         }
-        const double ang = g.angle ? GZB_LDS_REF(g.angle + (jP * g.Ni + iP)) : 0.0;
+        const double ang = g.angle ? GZB_LDS_REF(g.angle + cP) : 0.0;
         if (iq < 1 || fabs(ang) > 45.0 || force_heavy) {
             // heavy-duty: quads 4,3,2,1 in the raw (lat, lon) plane, first strict-interior hit
             for (int cand = 4; cand >= 1; --cand) {
-                quad_corners(cand, jP, iP, jm, jp, im, ip, cj, ci);
+                quad_corners<IX>(cand, jP, iP, jm, jp, im, ip, cj, ci);
                 double qy[4], qx[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     GZB_CHK(g, cj[k] >= 0 && cj[k] < g.Nj && ci[k] >= 0 && ci[k] < g.Ni, 64);
-                    const double2 c = GZB_LDS_LDG(g.ll + (cj[k] * g.Ni + ci[k]));
+                    const double2 c = cell_ll<IX>(g, cj[k], ci[k]);
                     qy[k] = c.x;
                     qx[k] = c.y;
                 }
@@ -139,56 +149,66 @@ __device__ __forceinline__ void source_mesh_one(const GzbGrid& g, const double y
         }
     }
     if (iq >= 1) {
-        quad_corners(iq, jP, iP, jm, jp, im, ip, cj, ci);
+        quad_corners<IX>(iq, jP, iP, jm, jp, im, ip, cj, ci);
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) { cj[k] = -1; ci[k] = -1; }
     }
 }
 
-__device__ __forceinline__ long long pywrap(long long k, long long n) { return k < 0 ? k + n : k; }
+// a nearest-point index read from a caller's int64 array, as an IX: what does not fit 32 bits becomes -2, which is outside
+// every grid like the original value (only the pair (-1, -1) means "not found")
+template <typename IX> __device__ __forceinline__ IX narrow_np(long long v);
+template <> __device__ __forceinline__ long long narrow_np<long long>(long long v) { return v; }
+template <> __device__ __forceinline__ int narrow_np<int>(long long v) { return ((long long)(int)v == v) ? (int)v : -2; }
 
 // nearest point of track point t for the bulk kernels: from the NP array, or (gzb_mapping overlap, while
 // the chain logic still runs) E(t) derived from the plain global answer -- gonzag/bilin_mapping.py:169-190
 // threshold acceptance + :582-585 edge exclusion, as accept_edge() of gzb_nearest.cu
+template <typename IX>
 __device__ __forceinline__ bool nearest_of(const GzbGrid& g, const long long* __restrict__ NP, const GzbGlobalNearest& gn,
-                                           const long long t, long long& jP, long long& iP) {
+                                           const long long t, IX& jP, IX& iP) {
     if (NP) {
-        jP = NP[2 * t];
-        iP = NP[2 * t + 1];
+        const longlong2 v = reinterpret_cast<const longlong2*>(NP)[t];
+        jP = narrow_np<IX>(v.x);
+        iP = narrow_np<IX>(v.y);
         return true;
     }
     const long long flat = gn.G[t];
     if (flat == 0x7ffffffffffffffeLL) return false;      // not settled yet: left to the repair kernel
     const double d = gn.dG[t];
     if (flat != 0x7fffffffffffffffLL && d < gn.thr2) {
-        jP = flat / g.Ni;
-        iP = flat - jP * g.Ni;
+        if (sizeof(IX) == 4) {                           // flat < Nj * Ni < 2^31
+            const unsigned f = (unsigned)flat, n = (unsigned)g.Ni, q = f / n;
+            jP = (IX)q;
+            iP = (IX)(f - q * n);
+        } else {
+            jP = (IX)(flat / g.Ni);
+            iP = (IX)(flat - (long long)jP * g.Ni);
+        }
     } else {
         jP = -1;
         iP = -1;
     }
     if (gn.edge) {
-        if (iP == 0 || (iP == g.Ni - 1 && g.kew == -1)) { jP = -1; iP = -1; }
-        if (jP == 0 || jP == g.Nj - 1) { jP = -1; iP = -1; }
+        if (iP == 0 || (iP == (IX)g.Ni - 1 && g.kew == -1)) { jP = -1; iP = -1; }
+        if (jP == 0 || jP == (IX)g.Nj - 1) { jP = -1; iP = -1; }
     }
     return true;
 }
 
 // bilinear weights of one point inside its source mesh (gonzag/bilin_mapping.py:490-527)
+template <typename IX>
 __device__ __forceinline__ void weights_one(const GzbGrid& g, const double yT, const double xT,
-                                            const long long* cj, const long long* ci, double* w) {
+                                            const IX* cj, const IX* ci, double* w) {
     w[0] = 1.0; w[1] = 0.0; w[2] = 0.0; w[3] = 0.0;
     if (cj[0] >= 0) {
         double vy[5], vx[5];
         vy[0] = yT;
         vx[0] = xT;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            long long j = pywrap(cj[k], g.Nj), i = pywrap(ci[k], g.Ni);
-            j = j < 0 ? 0 : (j >= g.Nj ? g.Nj - 1 : j);
-            i = i < 0 ? 0 : (i >= g.Ni ? g.Ni - 1 : i);
-            const double2 c = GZB_LDS_LDG(g.ll + (j * g.Ni + i));
+        for (int k = 0; k < 4; ++k) {      // Python negative indexing, then clamped (never faults)
+            const double2 c = cell_ll<IX>(g, pywrap_ix<IX>(cj[k], (IX)g.Nj), pywrap_ix<IX>(ci[k], (IX)g.Ni));
             vy[k + 1] = c.x;
             vx[k + 1] = c.y;
         }
@@ -201,39 +221,59 @@ __device__ __forceinline__ void weights_one(const GzbGrid& g, const double yT, c
     }
 }
 
+// does this grid take the 32-bit index variants?
+static inline bool gzb_ix32(const gzb_ctx* ctx) { return ctx->g.Nj * ctx->g.Ni < 0x7fffffffLL && !ctx->force_ix64; }
+
+// the mesh of a point as the reference's int64 rows (SM[t, k] = [j, i])
+template <typename IX>
+__device__ __forceinline__ void store_mesh(long long* __restrict__ SM, const long long t, const IX* cj, const IX* ci) {
+    longlong2* out = reinterpret_cast<longlong2*>(SM + 8 * t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = make_longlong2((long long)cj[k], (long long)ci[k]);
+}
+
+template <typename IX>
 __global__ void __launch_bounds__(128)
 k_source_mesh(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
               const long long* __restrict__ NP, long long* __restrict__ SM, const int force_heavy) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
-    long long cj[4], ci[4];
-    source_mesh_one(g, yt[t], xt[t], NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
-    longlong2* out = reinterpret_cast<longlong2*>(SM + 8 * t);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) out[k] = make_longlong2(cj[k], ci[k]);
+    IX cj[4], ci[4];
+    source_mesh_one<IX>(g, yt[t], xt[t], narrow_np<IX>(NP[2 * t]), narrow_np<IX>(NP[2 * t + 1]), force_heavy, cj, ci);
+    store_mesh<IX>(SM, t, cj, ci);
 }
 
+// K3 alone reads a caller's SM: an entry that does not fit the index type lies far outside the grid; it keeps its sign
+// (a negative first row means "no mesh") and clamps like the 64-bit rule in weights_one
+template <typename IX> __device__ __forceinline__ IX narrow_sm(long long v);
+template <> __device__ __forceinline__ long long narrow_sm<long long>(long long v) { return v; }
+template <> __device__ __forceinline__ int narrow_sm<int>(long long v) {
+    return ((long long)(int)v == v) ? (int)v : (v < 0 ? (int)0x80000000 : 0x7fffffff);
+}
+
+template <typename IX>
 __global__ void __launch_bounds__(128)
 k_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
           const long long* __restrict__ SM, double* __restrict__ WB) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
-    long long cj[4], ci[4];
+    IX cj[4], ci[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const longlong2 p = sm[k];
-        cj[k] = p.x;
-        ci[k] = p.y;
+        cj[k] = narrow_sm<IX>(p.x);
+        ci[k] = narrow_sm<IX>(p.y);
     }
     double w[4];
-    weights_one(g, yt[t], xt[t], cj, ci, w);
+    weights_one<IX>(g, yt[t], xt[t], cj, ci, w);
     double2* out = reinterpret_cast<double2*>(WB + 4 * t);
     out[0] = make_double2(w[0], w[1]);
     out[1] = make_double2(w[2], w[3]);
 }
 
 // K2 + K3 in one pass (what gzb_mapping runs): the mesh never travels through HBM between them
+template <typename IX>
 __global__ void __launch_bounds__(128)
 k_mesh_weights(const GzbGrid g, const long long nt, const double* __restrict__ yt, const double* __restrict__ xt,
                const long long* __restrict__ NP, const GzbGlobalNearest gn, long long* __restrict__ SM,
@@ -241,14 +281,12 @@ k_mesh_weights(const GzbGrid g, const long long nt, const double* __restrict__ y
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nt) return;
     const double yT = yt[t], xT = xt[t];
-    long long cj[4], ci[4], jP, iP;
-    if (!nearest_of(g, NP, gn, t, jP, iP)) return;
-    source_mesh_one(g, yT, xT, jP, iP, force_heavy, cj, ci);
-    longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) sm[k] = make_longlong2(cj[k], ci[k]);
+    IX cj[4], ci[4], jP, iP;
+    if (!nearest_of<IX>(g, NP, gn, t, jP, iP)) return;
+    source_mesh_one<IX>(g, yT, xT, jP, iP, force_heavy, cj, ci);
+    store_mesh<IX>(SM, t, cj, ci);
     double w[4];
-    weights_one(g, yT, xT, cj, ci, w);
+    weights_one<IX>(g, yT, xT, cj, ci, w);
     double2* out = reinterpret_cast<double2*>(WB + 4 * t);
     out[0] = make_double2(w[0], w[1]);
     out[1] = make_double2(w[2], w[3]);
@@ -262,7 +300,7 @@ k_heading_table(const GzbGrid g, double* __restrict__ hdg) {
     const long long jP = k / g.Ni, iP = k - jP * g.Ni;
     long long jm = 0, jp = 0, im = 0, ip = 0;
     double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (mesh_usable(g, jP, iP, jm, jp, im, ip)) cell_frame(g, jP, iP, jm, jp, im, ip, v[0], v[1], v[2], v[3], v[4], v[5]);
+    if (mesh_usable<long long>(g, jP, iP, jm, jp, im, ip)) cell_frame<long long>(g, jP, iP, jm, jp, im, ip, v[0], v[1], v[2], v[3], v[4], v[5]);
     double2* out = reinterpret_cast<double2*>(hdg + GZB_EXP_HDG_STRIDE * k);
     out[0] = make_double2(v[0], v[1]);
     out[1] = make_double2(v[2], v[3]);
@@ -302,8 +340,12 @@ int gzb_mesh_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const doubl
     GzbGlobalNearest gn = {nullptr, nullptr, 0.0, 0, nullptr, nullptr};
     const long long* npp = (const long long*)np;
     if (gn_or_null) { gn = *gn_or_null; npp = nullptr; }
-    k_mesh_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out,
-                                                                         wb_out, ctx->force_heavy);
+    if (gzb_ix32(ctx))
+        k_mesh_weights<int><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out,
+                                                                                  wb_out, ctx->force_heavy);
+    else
+        k_mesh_weights<long long><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, npp, gn, (long long*)sm_out,
+                                                                                        wb_out, ctx->force_heavy);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }
@@ -327,6 +369,7 @@ struct InterpArgs {            // K4 arguments of the fused path; slab == nullpt
     GzbPeerOut peers;
 };
 
+template <typename IX>
 __global__ void __launch_bounds__(64)
 k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
            const long long* __restrict__ NP, long long* __restrict__ SM, double* __restrict__ WB,
@@ -339,28 +382,22 @@ k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restr
         const long long t = e < n1 ? list[e] : list2[e - n1];
         if (!GZB_CHK(g, t >= 0, 4)) continue;
         const double yT = yt[t], xT = xt[t];
-        long long cj[4], ci[4];
-        source_mesh_one(g, yT, xT, NP[2 * t], NP[2 * t + 1], force_heavy, cj, ci);
-        longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
-        longlong2 rp[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            rp[k] = make_longlong2(cj[k], ci[k]);
-            sm[k] = rp[k];
-        }
+        IX cj[4], ci[4];
+        source_mesh_one<IX>(g, yT, xT, narrow_np<IX>(NP[2 * t]), narrow_np<IX>(NP[2 * t + 1]), force_heavy, cj, ci);
+        store_mesh<IX>(SM, t, cj, ci);
         double w[4];
-        weights_one(g, yT, xT, cj, ci, w);
+        weights_one<IX>(g, yT, xT, cj, ci, w);
         double2* out = reinterpret_cast<double2*>(WB + 4 * t);
         const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
         out[0] = rw[0];
         out[1] = rw[1];
         if (ia.slab) {      // K4 straight from the registers: the arrays just written are not read back
             if (ia.dtype == GZB_F32)
-                interp_point<float, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const float*)ia.slab, ia.k0,
-                                                 ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
+                interp_point<float, false, true, 0, IX>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const float*)ia.slab, ia.k0,
+                                                        ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, cj, ci, rw);
             else
-                interp_point<double, false, true>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const double*)ia.slab, ia.k0,
-                                                  ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
+                interp_point<double, false, true, 0, IX>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const double*)ia.slab, ia.k0,
+                                                         ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, cj, ci, rw);
         }
     }
 }
@@ -373,9 +410,9 @@ static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt);
 // (table -> mesh corners -> [Newton solve] -> mask word -> field values).  Its addresses are known as soon as
 // the mesh is: ask L2 for the sectors right then, so that they travel while the Newton iteration runs.
 // The time bracket is only guessed (mean record spacing); a wrong guess fetches a neighbouring record.
-template <typename T>
+template <typename T, typename IX>
 __device__ __forceinline__ void prefetch_point(const GzbGrid& g, const long long t, const InterpArgs& ia,
-                                               const long long* cj, const long long* ci) {
+                                               const IX* cj, const IX* ci) {
     const double now = __ldg(ia.t_sat + t);
     const double ta = __ldg(ia.tmod), tb = __ldg(ia.tmod + ia.nrec - 1);
     if (!(now >= ta) || !(now < tb)) return;
@@ -387,7 +424,7 @@ __device__ __forceinline__ void prefetch_point(const GzbGrid& g, const long long
     const long long ntI = (g.Ni + 15) >> 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const long long j = pywrap_idx(cj[k], g.Nj), i = pywrap_idx(ci[k], g.Ni);
+        const long long j = pywrap_idx((long long)cj[k], g.Nj), i = pywrap_idx((long long)ci[k], g.Ni);
         const long long c = j * g.Ni + i;
         gzb_l2_prefetch(X1 + c);
         gzb_l2_prefetch(X1 + cells + c);
@@ -430,39 +467,33 @@ __device__ __forceinline__ void prefetch_hood(const GzbGrid& g, const long long 
     gzb_l2_prefetch(X1 + jb * g.Ni + iP); gzb_l2_prefetch(X1 + cells + jb * g.Ni + iP);
 }
 
-#ifdef GZB_EXP_BULK_BLOCKS
-#define GZB_BULK_BOUNDS __launch_bounds__(128, GZB_EXP_BULK_BLOCKS)
-#else
-#define GZB_BULK_BOUNDS __launch_bounds__(128)
+// 7 blocks of 128 threads per SM (a cap of 72 registers): measured on the C3 track 93 -> 86 us with the 64-bit indices
+// (round 2, GZB_EXP_BULK_BLOCKS=7); the 32-bit index variant needs fewer registers to begin with
+#ifndef GZB_EXP_BULK_BLOCKS
+#define GZB_EXP_BULK_BLOCKS 7
 #endif
-template <typename T, int PF>      // PF: 0 plain, 1 L2 prefetch of the gather, 3 gather with 64-byte L2 fetches
-__global__ void GZB_BULK_BOUNDS             // 86 registers; capping it at 64 (more warps, some spills) measured 3 % slower
+template <typename T, int PF, typename IX>      // PF: 0 plain, 1 L2 prefetch of the gather, 3 gather with 64-byte L2 fetches, 4 early prefetch
+__global__ void __launch_bounds__(128, GZB_EXP_BULK_BLOCKS)
 k_mesh_weights_interp(const GzbGrid g, const long long t_first, const long long nt, const double* __restrict__ yt,
                       const double* __restrict__ xt, const long long* __restrict__ NP, const GzbGlobalNearest gn,
                       long long* __restrict__ SM, double* __restrict__ WB, const int force_heavy, const InterpArgs ia) {
     const long long t = t_first + (long long)blockIdx.x * blockDim.x + threadIdx.x;      // this launch: points [t_first, nt)
     if (t >= nt) return;
     const double yT = yt[t], xT = xt[t];
-    long long cj[4], ci[4], jP, iP;
-    if (!nearest_of(g, NP, gn, t, jP, iP)) return;
-    if (PF == 4) prefetch_hood<T>(g, t, ia, jP, iP);
-    source_mesh_one(g, yT, xT, jP, iP, force_heavy, cj, ci);
-    if (PF == 1) prefetch_point<T>(g, t, ia, cj, ci);
-    longlong2* sm = reinterpret_cast<longlong2*>(SM + 8 * t);
-    longlong2 rp[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        rp[k] = make_longlong2(cj[k], ci[k]);
-        sm[k] = rp[k];
-    }
+    IX cj[4], ci[4], jP, iP;
+    if (!nearest_of<IX>(g, NP, gn, t, jP, iP)) return;
+    if (PF == 4) prefetch_hood<T>(g, t, ia, (long long)jP, (long long)iP);
+    source_mesh_one<IX>(g, yT, xT, jP, iP, force_heavy, cj, ci);
+    if (PF == 1) prefetch_point<T, IX>(g, t, ia, cj, ci);
+    store_mesh<IX>(SM, t, cj, ci);
     double w[4];
-    weights_one(g, yT, xT, cj, ci, w);
+    weights_one<IX>(g, yT, xT, cj, ci, w);
     double2* out = reinterpret_cast<double2*>(WB + 4 * t);
     const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
     out[0] = rw[0];
     out[1] = rw[1];
-    interp_point<T, false, true, (PF >= 3 ? 3 : 0)>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
-                                 ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, rp, rw);
+    interp_point<T, false, true, (PF >= 3 ? 3 : 0), IX>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
+                                 ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, cj, ci, rw);
 }
 
 static void fill_interp_args(gzb_ctx* ctx, InterpArgs& ia, const double* tt, int64_t nrec, const double* tmod,
@@ -535,10 +566,12 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
         const long long a = ((nt * c / nchunk) + 127) & ~127LL, b = c + 1 == nchunk ? nt : (((nt * (c + 1) / nchunk) + 127) & ~127LL);
         if (b <= a) continue;
         const unsigned nblk = (unsigned)((b - a + 127) / 128);
-#define GZB_BULK(T, PF) k_mesh_weights_interp<T, PF><<<nblk, 128, 0, s>>>(ctx->g, a, b, yt, xt, npp, gn, (long long*)sm_out, \
-                                                                         wb_out, ctx->force_heavy, ia)
-        if (dtype == GZB_F32) { if (pfm == 4) GZB_BULK(float, 4); else if (pfm == 3) GZB_BULK(float, 3); else if (pfm) GZB_BULK(float, 1); else GZB_BULK(float, 0); }
-        else                  { if (pfm == 4) GZB_BULK(double, 4); else if (pfm == 3) GZB_BULK(double, 3); else if (pfm) GZB_BULK(double, 1); else GZB_BULK(double, 0); }
+#define GZB_BULK(T, PF, IX) k_mesh_weights_interp<T, PF, IX><<<nblk, 128, 0, s>>>(ctx->g, a, b, yt, xt, npp, gn, (long long*)sm_out, \
+                                                                                wb_out, ctx->force_heavy, ia)
+#define GZB_BULK_PF(T, IX) { if (pfm == 4) GZB_BULK(T, 4, IX); else if (pfm == 3) GZB_BULK(T, 3, IX); else if (pfm) GZB_BULK(T, 1, IX); else GZB_BULK(T, 0, IX); }
+        if (gzb_ix32(ctx)) { if (dtype == GZB_F32) GZB_BULK_PF(float, int) else GZB_BULK_PF(double, int) }
+        else               { if (dtype == GZB_F32) GZB_BULK_PF(float, long long) else GZB_BULK_PF(double, long long) }
+#undef GZB_BULK_PF
 #undef GZB_BULK
         GZB_LAUNCH_CHECK(ctx);
         if (push) {
@@ -567,8 +600,12 @@ int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int
     const GzbPeerOut peers = ia.peers;
     const bool joined = ctx->push_pending && peers.n > 0;
     if (joined) ia.peers.n = 0;       // chunk copies in flight: repair locally beside them, then copy the repaired points
-    k_path_fix<<<192, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
-                                           list2, count2, ctx->force_heavy, ia);
+    if (gzb_ix32(ctx))
+        k_path_fix<int><<<192, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
+                                                    list2, count2, ctx->force_heavy, ia);
+    else
+        k_path_fix<long long><<<192, 64, 0, ctx->stream>>>(ctx->g, yt, xt, (const long long*)np, (long long*)sm_out, wb_out, list, count,
+                                                          list2, count2, ctx->force_heavy, ia);
     GZB_LAUNCH_CHECK(ctx);
     if (joined) {
         if (gzb_push_join(ctx) != GZB_OK) return GZB_ERR_CUDA;
@@ -591,8 +628,12 @@ int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double
                         int64_t* sm_out) {
     if (nt <= 0) return GZB_OK;
     if (maybe_build_heading_table(ctx, nt) != GZB_OK) return GZB_ERR_CUDA;
-    k_source_mesh<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
-                                                                        (long long*)sm_out, ctx->force_heavy);
+    if (gzb_ix32(ctx))
+        k_source_mesh<int><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
+                                                                                 (long long*)sm_out, ctx->force_heavy);
+    else
+        k_source_mesh<long long><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)np,
+                                                                                       (long long*)sm_out, ctx->force_heavy);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }
@@ -600,7 +641,10 @@ int gzb_source_mesh_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double
 int gzb_weights_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt, const int64_t* sm,
                     double* wb_out) {
     if (nt <= 0) return GZB_OK;
-    k_weights<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)sm, wb_out);
+    if (gzb_ix32(ctx))
+        k_weights<int><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)sm, wb_out);
+    else
+        k_weights<long long><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(ctx->g, nt, yt, xt, (const long long*)sm, wb_out);
     GZB_LAUNCH_CHECK(ctx);
     return GZB_OK;
 }

@@ -49,11 +49,29 @@ __device__ __forceinline__ long long pywrap_idx(long long k, long long n) {
     return k < 0 ? 0 : (k >= n ? n - 1 : k);    // anything else out of range is clamped, never faults
 }
 
-__device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const long long ntI, const long long j,
-                                        const long long i) {
-    const long long tile = (j >> 4) * ntI + (i >> 4);
+// Index type of the per-point kernels.  Every grid of fewer than 2^31 cells (ORCA12: 13 M, an ORCA36-class grid: 117 M)
+// takes the `int` variants: row / column numbers, flat cell indices and mask-tile numbers are then 32-bit values, which
+// halves the integer work of K2-K4 (the reference's int64 arrays are only widened at the stores and narrowed at the
+// loads).  `long long` is the general path.  Both give the same indices wherever the narrow one is used.
+template <typename IX> __device__ __forceinline__ IX pywrap_ix(IX k, IX n) {
+    k = k < 0 ? k + n : k;
+    return k < 0 ? 0 : (k >= n ? n - 1 : k);
+}
+// pywrap_idx() of a 64-bit value read from memory (a mesh corner of a caller's SM array), as an IX: a value that does
+// not fit 32 bits lies far outside the grid and clamps to the first / last index exactly as the 64-bit rule does
+template <typename IX> __device__ __forceinline__ IX pywrap_from64(long long k, IX n);
+template <> __device__ __forceinline__ long long pywrap_from64<long long>(long long k, long long n) { return pywrap_idx(k, n); }
+template <> __device__ __forceinline__ int pywrap_from64<int>(long long k, int n) {
+    const int lo = (int)k;
+    if ((long long)lo == k) return pywrap_ix<int>(lo, n);
+    return k < 0 ? 0 : n - 1;
+}
+
+template <typename IX>
+__device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const IX ntI, const IX j, const IX i) {
+    const IX tile = (j >> 4) * ntI + (i >> 4);
     const int b = (int)(((j & 15) << 4) | (i & 15));
-    return (int)((GZB_LDS_LDG(bits + tile * 8 + (b >> 5)) >> (b & 31)) & 1u);
+    return (int)((GZB_LDS_LDG(bits + ((long long)tile * 8 + (b >> 5))) >> (b & 31)) & 1u);
 }
 
 // One thread per track point.  T is the dtype of the model field: the time interpolation
@@ -67,14 +85,14 @@ __device__ __forceinline__ int mask_bit(const unsigned* __restrict__ bits, const
 // instead of through a collective afterwards.  n == 0: local outputs only.
 // (struct GzbPeerOut: gzb_common.cuh)
 
-// REG: the mesh and weights come in registers (rp[4], rw[2]) instead of SM / WB.
-template <typename T, bool EARLY, bool REG = false, int PF = 0>
+// REG: the mesh and weights come in registers (cj[4], ci[4], rw[2]) instead of SM / WB.
+template <typename T, bool EARLY, bool REG = false, int PF = 0, typename IX = long long>
 __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t, const double* __restrict__ t_sat,
          const long long* __restrict__ SM, const double* __restrict__ WB, const long long nrec,
          const double* __restrict__ tmod, const T* __restrict__ slab, const long long k0, const long long nk,
          const double rmiss, const int init, double* __restrict__ out_np, double* __restrict__ out_bl,
          int* __restrict__ err, const unsigned* __restrict__ mbits, const int* __restrict__ mflag,
-         const GzbPeerOut& peers, const longlong2* rp = nullptr, const double2* rw = nullptr) {
+         const GzbPeerOut& peers, const IX* rcj = nullptr, const IX* rci = nullptr, const double2* rw = nullptr) {
     const double now = __ldg(t_sat + t);
     const longlong2* sm = reinterpret_cast<const longlong2*>(SM + 8 * t);
     const double2* wb = reinterpret_cast<const double2*>(WB + 4 * t);
@@ -82,7 +100,6 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
     longlong2 p1, p2, p3, p4;
     double2 wa, wc;
     if (REG) {
-        p1 = rp[0]; p2 = rp[1]; p3 = rp[2]; p4 = rp[3];
         wa = rw[0]; wc = rw[1];
     } else if (EARLY) {
         p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
@@ -99,7 +116,9 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
         // bracket tmod[lo] <= now < tmod[lo+1] (gonzag/mod2sat.py:94-96).  Model records are almost always
         // evenly spaced: guess the index from the mean spacing, verify it against the actual times, and
         // only search (binary, eight dependent loads for 242 records) when the guess is off
-        long long lo = (long long)((now - tmod[0]) / (tmod[nrec - 1] - tmod[0]) * (double)(nrec - 1));
+        // (the guess is only a guess: single precision and an approximate division are plenty, whatever it says is
+        // checked against the record times themselves)
+        long long lo = (long long)(__fdividef((float)(now - tmod[0]), (float)(tmod[nrec - 1] - tmod[0])) * (float)(nrec - 1));
         lo = lo < 0 ? 0 : (lo > nrec - 2 ? nrec - 2 : lo);
         if (!(tmod[lo] <= now && now < tmod[lo + 1])) {
             lo = 0;
@@ -113,11 +132,20 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
         if (!EARLY && !REG) {
             p1 = sm[0]; p2 = sm[1]; p3 = sm[2]; p4 = sm[3];
         }
-        const long long j1 = pywrap_idx(p1.x, g.Nj), i1 = pywrap_idx(p1.y, g.Ni);
-        const long long j2 = pywrap_idx(p2.x, g.Nj), i2 = pywrap_idx(p2.y, g.Ni);
-        const long long j3 = pywrap_idx(p3.x, g.Nj), i3 = pywrap_idx(p3.y, g.Ni);
-        const long long j4 = pywrap_idx(p4.x, g.Nj), i4 = pywrap_idx(p4.y, g.Ni);
-        const long long c1 = j1 * g.Ni + i1, c2 = j2 * g.Ni + i2, c3 = j3 * g.Ni + i3, c4 = j4 * g.Ni + i4;
+        const IX gNj = (IX)g.Nj, gNi = (IX)g.Ni;
+        IX j1, i1, j2, i2, j3, i3, j4, i4;
+        if (REG) {
+            j1 = pywrap_ix<IX>(rcj[0], gNj); i1 = pywrap_ix<IX>(rci[0], gNi);
+            j2 = pywrap_ix<IX>(rcj[1], gNj); i2 = pywrap_ix<IX>(rci[1], gNi);
+            j3 = pywrap_ix<IX>(rcj[2], gNj); i3 = pywrap_ix<IX>(rci[2], gNi);
+            j4 = pywrap_ix<IX>(rcj[3], gNj); i4 = pywrap_ix<IX>(rci[3], gNi);
+        } else {
+            j1 = pywrap_from64<IX>(p1.x, gNj); i1 = pywrap_from64<IX>(p1.y, gNi);
+            j2 = pywrap_from64<IX>(p2.x, gNj); i2 = pywrap_from64<IX>(p2.y, gNi);
+            j3 = pywrap_from64<IX>(p3.x, gNj); i3 = pywrap_from64<IX>(p3.y, gNi);
+            j4 = pywrap_from64<IX>(p4.x, gNj); i4 = pywrap_from64<IX>(p4.y, gNi);
+        }
+        const IX c1 = j1 * gNi + i1, c2 = j2 * gNi + i2, c3 = j3 * gNi + i3, c4 = j4 * gNi + i4;
         const long long cells = g.Nj * g.Ni;
         const T* __restrict__ X1 = slab + (lo - k0) * cells;
         const T* __restrict__ X2 = X1 + cells;
@@ -132,9 +160,9 @@ __device__ __forceinline__ void interp_point(const GzbGrid& g, const long long t
         }
         int ocean;
         if (mbits && *mflag == 0) {
-            const long long ntI = (g.Ni + 15) >> 4;
-            ocean = mask_bit(mbits, ntI, j1, i1) + mask_bit(mbits, ntI, j2, i2) + mask_bit(mbits, ntI, j3, i3) +
-                    mask_bit(mbits, ntI, j4, i4);
+            const IX ntI = (gNi + 15) >> 4;
+            ocean = mask_bit<IX>(mbits, ntI, j1, i1) + mask_bit<IX>(mbits, ntI, j2, i2) + mask_bit<IX>(mbits, ntI, j3, i3) +
+                    mask_bit<IX>(mbits, ntI, j4, i4);
         } else {
             ocean = (int)g.mask[c1] + (int)g.mask[c2] + (int)g.mask[c3] + (int)g.mask[c4];
         }

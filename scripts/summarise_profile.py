@@ -23,7 +23,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 out = ["# ncu --set full --clock-control none --import-source on, one launch of every kernel of a bench step",
-       "#   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu   (C3: global ORCA12 3059x4322, 633122 track points)",
+       "#   python scripts/ncu_case.py (round 2; round 1: bench.py --steps 1 --warmup 3 --no-e2e --no-cpu)   (C3: global ORCA12 3059x4322, 633122 track points)",
        "# caches are flushed before every profiled launch and launches are serialised: compare SHARES with the live run", ""]
 traffic = {}
 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -77,14 +77,21 @@ with open(os.path.join(ROOT, "profiles", rnd + "_launches_C3.csv"), "w") as f:
     for r in lr[i0 + 1:]:
         if len(r) > d and r[d].isdigit() and int(r[d]) in step:
             w.writerow(r)
-K1 = ["k_near_search", "k_near_slow", "k_chain", "k_compact", "k_walk<0>", "k_valid", "k_walk<1>"]
+K1 = ["k_near_search", "k_near_slow", "k_chain", "k_tail", "k_compact", "k_walk<0>", "k_valid", "k_walk<1>"]
+
+
+def pick(prefix):          # template arguments changed between rounds: match by prefix
+    for k, v in per.items():
+        if k.startswith(prefix):
+            return v
+    return 0.0
 per = {k: sum(v) / len(v) for k, v in traffic.items()}
 for k in step:      # kernels the full capture did not include: take the launch list's counters
     e = rec[k]
     per.setdefault(e["name"], e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0))
 stage = {"K1_nearest": sum(per.get(k, 0.0) for k in K1), "K2K3_mesh_weights": per.get("k_mesh_weights", 0.0),
-         "K4_interp_gather": per.get("k_interp<float, 0>", per.get("k_interp<float, 1>", 0.0))}
-stage["K2K3K4_bulk"] = per.get("k_mesh_weights_interp<float>", 0.0)
+         "K4_interp_gather": pick("k_interp<float")}
+stage["K2K3K4_bulk"] = pick("k_mesh_weights_interp<float")
 stage["K1-K4_path"] = stage["K1_nearest"] + stage["K2K3K4_bulk"] + per.get("k_path_fix", 0.0)
 stage["K1K2K3_mapping"] = stage["K1_nearest"] + stage["K2K3_mesh_weights"]
 json.dump({"source": os.path.basename(raw), "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",

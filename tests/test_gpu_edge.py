@@ -154,6 +154,42 @@ def test_every_overlap_convention(kew):
     _against_oracle(lat, lon, y[::-1].copy(), x[::-1].copy(), kew, rd, r, what="k_ew_per=%d, westward" % kew)
 
 
+def test_arbitrary_int64_indices_in_caller_arrays():
+    """K2, K3 and K4 take NP / SM arrays from the caller: entries outside the grid -- also far outside 32 bits -- must give
+    what the 64-bit rules give (no mesh; Python-wrapped then clamped corner), in the 32-bit index variant the kernels use
+    on every grid of fewer than 2^31 cells exactly as in the 64-bit one (option "ix64")."""
+    lat, lon = syn.orca_like_grid(72, 92)
+    mask = syn.land_mask(lat, lon)
+    res = syn.grid_resolution_deg(lon)
+    rd, r = syn.search_params(res)
+    t, y, x = syn.orbit_track(4000, t0=3.0, **syn.JASON)
+    tm = np.array([0.0, 3000.0, 6000.0])
+    fld = syn.ssh_records(lat, lon, 3).astype(np.float32)
+    rng = np.random.default_rng(77)
+    odd = np.array([-1, -2, 0, 71, 72, 91, 92, 2 ** 31 - 1, 2 ** 31, -2 ** 31, -2 ** 31 - 1, 2 ** 40, -2 ** 40, 2 ** 62, -2 ** 62,
+                    2 ** 32 + 5, -2 ** 32 + 5], dtype=np.int64)
+    out = {}
+    for ix64 in (0, 1):
+        with gzb.GridContext(lat, lon, mask=mask, k_ew_per=2) as ctx:
+            ctx.set_option("ix64", ix64)
+            NP, SM, WB = ctx.mapping(y, x, rd, r)
+            NP2, SM2 = NP.copy(), SM.copy()
+            k = rng.integers(0, len(y), 600)
+            NP2[k[:300], rng.integers(0, 2, 300)] = rng.choice(odd, 300)
+            NP2[k[300:400]] = rng.choice(odd, (100, 2))
+            SM2[k, rng.integers(0, 4, 600), rng.integers(0, 2, 600)] = rng.choice(odd, 600)
+            sm_from_np2 = ctx.source_mesh(y, x, NP2)
+            wb_from_sm2 = ctx.weights(y, x, SM2)
+            v = ctx.interp(t, SM2, WB, tm, fld)
+            out[ix64] = (NP, SM, WB, sm_from_np2, wb_from_sm2, v[0], v[1])
+        rng = np.random.default_rng(77)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a.view(np.int64), b.view(np.int64))
+    # an out-of-grid nearest point gives "no mesh" (-1 everywhere), never a wrapped cell
+    sm = out[0][3]
+    assert ((sm == -1).all(axis=(1, 2)) | (sm == 0).all(axis=(1, 2)) | (sm >= 0).all(axis=(1, 2))).all()
+
+
 def test_heavy_duty_quadrant_everywhere():
     """|angle| > 45 everywhere forces the polygon search for every point (option -D on a grid
     declared fully rotated), including targets due north of their nearest point."""

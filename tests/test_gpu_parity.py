@@ -425,7 +425,8 @@ def test_several_chains_in_one_call(golden_global, golden_seam, case):
 def test_launch_and_memory_options_do_not_change_results(golden_global):
     """Options that only change HOW the kernels are launched or fed -- "pdl" (programmatic dependent
     launches of K1's chain kernels), "prefetch" (L2 prefetch of the gather in the fused kernel and in
-    K4; 3 = 64-byte L2 fetches instead), "l2_fetch" (device-wide fetch-granularity hint) -- must leave every output bit-identical."""
+    K4; 3 = 64-byte L2 fetches instead), "l2_fetch" (device-wide fetch-granularity hint), "ix64" (64-bit instead of 32-bit
+    index arithmetic in K2-K4) -- must leave every output bit-identical."""
     import ctypes as C
     from gonzag_b200 import _lib as L
     g = golden_global
@@ -441,7 +442,8 @@ def test_launch_and_memory_options_do_not_change_results(golden_global):
         ref = None
         for opts in ({"pdl": 1, "prefetch": 0}, {"pdl": 0}, {"pdl": 1, "prefetch": 1}, {"prefetch": 2}, {"prefetch": 3}, {"prefetch": 4},
                      {"bulk_chunks": 3, "prefetch": 3}, {"bulk_chunks": 0},
-                     {"prefetch": 0, "l2_fetch": 32}, {"l2_fetch": 128}, {"l2_fetch": 64}):
+                     {"prefetch": 0, "l2_fetch": 32}, {"l2_fetch": 128}, {"l2_fetch": 64},
+                     {"ix64": 1, "prefetch": 3}, {"ix64": 1, "prefetch": 0}, {"ix64": 0, "prefetch": 3}):
             for k, v in opts.items():
                 ctx.set_option(k, v)
             # fused path on a device-resident slab (k_mesh_weights_interp: the prefetch variant applies)
@@ -455,11 +457,17 @@ def test_launch_and_memory_options_do_not_change_results(golden_global):
             # K1 alone (the whole chain on one stream: where the dependent launches matter) and K4 alone
             got.append(ctx.nearest(y, x, rd, r))
             got += list(ctx.interp(t, got[1], got[2], tm, fld))
+            # the staged kernels (K2, K3, K2+K3): "ix64" switches their index type as well
+            got.append(ctx.source_mesh(y, x, got[0]))
+            got.append(ctx.weights(y, x, got[1]))
+            got += list(ctx.mapping(y, x, rd, r))
             if ref is None:
                 ref = got
                 _report_index_mismatch("NP", got[0], g["NP"])
                 _report_index_mismatch("SM", got[1], g["SM"])
                 assert np.array_equal(got[5], got[0]) and np.array_equal(got[6], got[3]) and np.array_equal(got[7], got[4])
+                assert np.array_equal(got[8], got[1]) and np.array_equal(got[9].view(np.int64), got[2].view(np.int64))
+                assert np.array_equal(got[10], got[0]) and np.array_equal(got[11], got[1])
             for a, b in zip(got, ref):
                 assert np.array_equal(a, b), opts
         assert ctx.stats()["l2_fetch_bytes"] in (0, 32, 64, 128)
