@@ -58,6 +58,7 @@ struct GzbGrid {
                             // from this cell to any cell outside its 5x5 index neighbourhood
     const double* hdg;      // optional per-cell table of K2 (6 doubles per cell): Mercator ordinate and
                             // longitude (radians, [0,2pi)) of the cell, headings to its N, E, S, W neighbours
+    unsigned long long* kt; // KTIME build (-DGZB_KTIME=1): 64 device words of in-kernel time marks (see GZB_KT_MIN); else unused
     int* chk;               // CHECKED build (-DGZB_CHECKED=1): device word that collects violated bounds (see GZB_CHK); else unused
     GzbLut lut;
     int nlev;
@@ -160,6 +161,7 @@ struct gzb_ctx {
     int time_err_pending = 0;
     int barrier_err_pending = 0;     // d_flags[3] != 0: a peer barrier timed out (checked by gzb_sync)
     int* d_flags = nullptr;          // persistent device status words (word 0: K4 time-range error)
+    unsigned long long* d_kt = nullptr;   // KTIME build: the 64 time-mark words
     int zero_copy = 1;               // gather from pinned+mapped host slabs instead of copying them
     // corner-box bounding sphere cache (predecessor == (-1,-1)), keyed by np_box_r
     int corner_r = -1;
@@ -200,6 +202,26 @@ __device__ __forceinline__ void gzb_pdl_trigger() { asm volatile("griddepcontrol
 #define GZB_CHK(g, cond, bit) ((cond) ? true : (atomicOr((g).chk, (bit)), false))
 #else
 #define GZB_CHK(g, cond, bit) (true)
+#endif
+
+// ---- KTIME build: GZB_NVCC_EXTRA="-DGZB_KTIME=1" python -m gonzag_b200.build --force -------------------------------------
+// In-kernel time marks (%globaltimer) of the kernels of a step: thread 0 of every block folds its time into slot s with
+// atomicMin (first block to get there: slots 0..31) or atomicMax (last block to get there: slots 32..63); gzb_sync prints
+// the table relative to the earliest mark and resets it.  Shows launch gaps and the phases INSIDE the chain kernels,
+// which stream events cannot (and recording events switches the dependent launches off).  Compiled away in the product.
+#ifdef __CUDACC__
+#ifdef GZB_KTIME
+__device__ __forceinline__ unsigned long long gzb_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GZB_KT_MIN(g, s) do { if (threadIdx.x == 0 && (g).kt) atomicMin((g).kt + (s), gzb_gtime()); } while (0)
+#define GZB_KT_MAX(g, s) do { if (threadIdx.x == 0 && (g).kt) atomicMax((g).kt + 32 + (s), gzb_gtime()); } while (0)
+#else
+#define GZB_KT_MIN(g, s) do { } while (0)
+#define GZB_KT_MAX(g, s) do { } while (0)
+#endif
 #endif
 
 // ---- compile-time experiments (GZB_NVCC_EXTRA of gonzag_b200/build.py); all OFF in the product build ----------

@@ -931,6 +931,14 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
         ctx->pinned_cap = 4096;
 #undef CK
         ctx->g.chk = ctx->d_flags + 4;
+        ctx->g.kt = nullptr;
+#ifdef GZB_KTIME
+        if (gzb_pool_malloc((void**)&ctx->d_kt, 64 * 8) == cudaSuccess) {
+            cudaMemsetAsync(ctx->d_kt, 0xff, 32 * 8, ctx->stream);
+            cudaMemsetAsync(ctx->d_kt + 32, 0, 32 * 8, ctx->stream);
+            ctx->g.kt = ctx->d_kt;
+        } else cudaGetLastError();
+#endif
         ctx->g.Nj = nj;
         ctx->g.Ni = ni;
         ctx->g.kew = k_ew_per;
@@ -1040,6 +1048,29 @@ extern "C" int gzb_sync(gzb_ctx* ctx) {
     GZB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->pinned + 80, ctx->d_flags + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
 #endif
     GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#ifdef GZB_KTIME
+    if (ctx->d_kt) {
+        static const char* nm[16] = {"k_near_search", "k_near_slow", "k_chain entry", "k_chain (after the dependency wait | summaries of the points read)",
+                                     "k_chain (- | block maps published)", "k_chain (- | look-back done)", "k_chain (- | NP and block break lists written)",
+                                     "k_chain (- | end, ordered break list)", "k_tail entry", "k_tail (after the dependency wait | replays done)",
+                                     "k_tail (- | validation done)", "k_tail (- | write-back done)", "k_tail (- | end)", "bulk kernel", "k_path_fix", "-"};
+        unsigned long long h[64];
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(h, ctx->d_kt, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            unsigned long long t0 = ~0ull;
+            for (int k = 0; k < 32; ++k) if (h[k] < t0) t0 = h[k];
+            if (t0 != ~0ull) {
+                for (int k = 0; k < 15; ++k) {
+                    if (h[k] == ~0ull && h[32 + k] == 0ull) continue;
+                    fprintf(stderr, "[gzb ktime] first %8.2f us   last %8.2f us   %s\n", h[k] == ~0ull ? -1.0 : 1e-3 * (double)(h[k] - t0),
+                            h[32 + k] == 0ull ? -1.0 : 1e-3 * (double)(h[32 + k] - t0), nm[k]);
+                }
+                cudaMemset(ctx->d_kt, 0xff, 32 * 8);
+                cudaMemset(ctx->d_kt + 32, 0, 32 * 8);
+            }
+        } else cudaGetLastError();
+    }
+#endif
 #ifdef GZB_CHECKED
     {
         int* h_c = (int*)((char*)ctx->pinned + 80);

@@ -33,7 +33,8 @@ k_mask_bits(const long long Nj, const long long Ni, const int8_t* __restrict__ m
     if (odd) atomicOr(flag, 1);
 }
 
-// resident blocks of 256 threads per SM for the 32-bit index variant of K4 (6 = a cap of 40 registers)
+// resident blocks of 256 threads per SM for the 32-bit index variant of K4 (6 = a cap of 40 registers, no spills; measured
+// 34.9 us at 5 and at 6 blocks, 41 us at 7 and 8 where the kernel spills -- gpurun_out/ab_exp*_r2n.log)
 #ifndef GZB_K4_BLOCKS
 #define GZB_K4_BLOCKS 6
 #endif

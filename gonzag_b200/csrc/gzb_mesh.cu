@@ -378,6 +378,7 @@ k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restr
            const int force_heavy, const InterpArgs ia) {
     const long long n1 = (long long)*count;
     const long long n = n1 + (list2 ? (long long)*count2 : 0);
+    GZB_KT_MIN(g, 14);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
         const long long t = e < n1 ? list[e] : list2[e - n1];
         if (!GZB_CHK(g, t >= 0, 4)) continue;
@@ -400,6 +401,7 @@ k_path_fix(const GzbGrid g, const double* __restrict__ yt, const double* __restr
                                                          ia.nk, ia.rmiss, 1, ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, cj, ci, rw);
         }
     }
+    GZB_KT_MAX(g, 14);
 }
 
 static int maybe_build_heading_table(gzb_ctx* ctx, int64_t nt);
@@ -467,10 +469,11 @@ __device__ __forceinline__ void prefetch_hood(const GzbGrid& g, const long long 
     gzb_l2_prefetch(X1 + jb * g.Ni + iP); gzb_l2_prefetch(X1 + cells + jb * g.Ni + iP);
 }
 
-// 7 blocks of 128 threads per SM (a cap of 72 registers): measured on the C3 track 93 -> 86 us with the 64-bit indices
-// (round 2, GZB_EXP_BULK_BLOCKS=7); the 32-bit index variant needs fewer registers to begin with
+// Resident blocks of 128 threads per SM (8 = a cap of 64 registers; uncapped the kernel takes 91).  Measured on the C3 track,
+// 32-bit indices (gpurun_out/ab_exp*_r2n.log): 5 blocks 90.1 us, 6 blocks 84.1, 7 blocks 82.0, 8 blocks 80.6 -- the kernel is
+// bound by the latency of its dependent gathers, so warps in flight beat the spills they cost (64-bit indices: 7 blocks 86.8)
 #ifndef GZB_EXP_BULK_BLOCKS
-#define GZB_EXP_BULK_BLOCKS 7
+#define GZB_EXP_BULK_BLOCKS 8
 #endif
 template <typename T, int PF, typename IX>      // PF: 0 plain, 1 L2 prefetch of the gather, 3 gather with 64-byte L2 fetches, 4 early prefetch
 __global__ void __launch_bounds__(128, GZB_EXP_BULK_BLOCKS)
@@ -478,6 +481,7 @@ k_mesh_weights_interp(const GzbGrid g, const long long t_first, const long long 
                       const double* __restrict__ xt, const long long* __restrict__ NP, const GzbGlobalNearest gn,
                       long long* __restrict__ SM, double* __restrict__ WB, const int force_heavy, const InterpArgs ia) {
     const long long t = t_first + (long long)blockIdx.x * blockDim.x + threadIdx.x;      // this launch: points [t_first, nt)
+    GZB_KT_MIN(g, 13);
     if (t >= nt) return;
     const double yT = yt[t], xT = xt[t];
     IX cj[4], ci[4], jP, iP;
@@ -494,6 +498,7 @@ k_mesh_weights_interp(const GzbGrid g, const long long t_first, const long long 
     out[1] = rw[1];
     interp_point<T, false, true, (PF >= 3 ? 3 : 0), IX>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
                                  ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, cj, ci, rw);
+    GZB_KT_MAX(g, 13);
 }
 
 static void fill_interp_args(gzb_ctx* ctx, InterpArgs& ia, const double* tt, int64_t nrec, const double* tmod,

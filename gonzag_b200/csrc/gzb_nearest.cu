@@ -618,6 +618,7 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
 #endif
               ) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    GZB_KT_MIN(g, 0);
     bool unresolved = false;
     unsigned myhint = 0xffffffffu;
 #if GZB_EXP_SKIP_DG
@@ -732,6 +733,7 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
             G[t] = GZB_UNRESOLVED;
         }
     }
+    GZB_KT_MAX(g, 0);
 }
 
 // K1, slow path: the warp-cooperative search (seeded window, then pyramid) for the listed points.
@@ -746,6 +748,7 @@ k_near_slow(const GzbGrid g, const double* __restrict__ yt, const double* __rest
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSm& w = ws[warp];
     const long long nu = (long long)*ucount;
+    GZB_KT_MIN(g, 1);
     if (nu <= 0) return;
     const long long nwarps = (long long)gridDim.x * SLOW_WARPS;
     long long K = (nu + nwarps - 1) / nwarps;
@@ -790,6 +793,7 @@ k_near_slow(const GzbGrid g, const double* __restrict__ yt, const double* __rest
         }
         __syncwarp();
     }
+    GZB_KT_MAX(g, 1);
 }
 
 // certificate of every leaf tile: chord from its centre to the nearest cell outside its window
@@ -1004,7 +1008,9 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     __shared__ int wcnt[FLAGS_BLOCK / 32];
     __shared__ unsigned s_bid, s_entry;
     __shared__ int sE[FLAGS_BLOCK][2], sT[FLAGS_BLOCK][3];      // E / T of the LAST point of every thread
+    GZB_KT_MIN(g, 2);
     gzb_pdl_wait();
+    GZB_KT_MIN(g, 3);
     if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned bid = s_bid;
@@ -1019,6 +1025,7 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     sE[threadIdx.x][0] = q[CH_PPT - 1].ej; sE[threadIdx.x][1] = q[CH_PPT - 1].ei;
     sT[threadIdx.x][0] = q[CH_PPT - 1].tj; sT[threadIdx.x][1] = q[CH_PPT - 1].ti; sT[threadIdx.x][2] = q[CH_PPT - 1].tv;
     __syncthreads();
+    GZB_KT_MAX(g, 3);
     unsigned c[CH_PPT];
     unsigned mine = FN_ID;
     {
@@ -1069,6 +1076,7 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     unsigned total;
     const unsigned incl = block_scan_fn(mine, sh, total);
     if ((threadIdx.x & 31) == 31) last[threadIdx.x >> 5] = incl;
+    GZB_KT_MAX(g, 4);
     if (threadIdx.x == 0) {
         agg[bid] = 0x100u | total;               // publish this block's map
         __threadfence();
@@ -1085,6 +1093,7 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
         s_entry = fmap & 1u;                     // the track starts in state 0
     }
     __syncthreads();
+    GZB_KT_MAX(g, 5);
     const unsigned prev = __shfl_up_sync(0xffffffffu, incl, 1);
     unsigned before;          // map from the block's entry state to the state entering this thread's first point
     if (threadIdx.x == 0) before = FN_ID;
@@ -1140,6 +1149,7 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
             }
     }
     __syncthreads();
+    GZB_KT_MAX(g, 6);
     if (threadIdx.x == 0) {
         bcount[bid] = btotal;
         __threadfence();
@@ -1178,6 +1188,7 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
         carry += ctot;
     }
     if (threadIdx.x == 0) nbrk_out[0] = carry;
+    GZB_KT_MAX(g, 7);
 }
 
 // per row: 1 = no cell strictly between a leading overlap cell and its East-West twin has that cell's
@@ -1373,7 +1384,9 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
     __shared__ long long ss[VALID_CHUNK];
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    GZB_KT_MIN(g, 8);
     gzb_pdl_wait();
+    GZB_KT_MIN(g, 9);
     const long long nb = scal[0];
     unsigned long long* steps = (unsigned long long*)(scal + 1);
     // ---- (1) replays
@@ -1383,6 +1396,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
             replay<false>(g, p, ws[warp], lane, nt, yt, xt, G, dG, k, breaks[k], nt - 1, stop, first, wlog, NP, steps, nullptr, nullptr);
     }
     __syncthreads();
+    GZB_KT_MAX(g, 9);
     if (threadIdx.x == 0) {
         __threadfence();
         s_last = (atomicAdd(done_ctr, 1u) == gridDim.x - 1) ? 1 : 0;
@@ -1427,6 +1441,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
         }
         __syncthreads();
     }
+    GZB_KT_MAX(g, 10);
     // ---- (3) write-back of the valid replays, thread per break (short, intact logs); 2 = left to the warps below
     for (long long k = threadIdx.x; k < nb; k += blockDim.x) {
         if (!valid[k]) continue;
@@ -1469,6 +1484,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
         }
     }
     __syncthreads();
+    GZB_KT_MAX(g, 11);
     for (long long k = warp; k < nb; k += TAIL_WARPS) {
         if (valid[k] != 2) continue;
         replay<true>(g, p, ws[warp], lane, nt, yt, xt, G, dG, k, breaks[k], __ldcg(stop + k), stop, first, wlog, NP, steps, chg, nchg);
@@ -1478,6 +1494,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
         stats_out[1] = (long long)__ldcg(steps);
         for (int q = 2; q < 7; ++q) stats_out[q] = __ldcg(scal + q);   // k_near_search: unresolved (total, no seed, not converged, not proven); longest replay
     }
+    GZB_KT_MAX(g, 12);
 }
 
 // bounding sphere of the grid corner [0,r)^2 (the search box of a not-found predecessor)
