@@ -590,6 +590,47 @@ def run_ours(args, w):
     if not mapper.boundaries_verdict():
         raise SystemExit("a timed step needed a re-seed across a segment boundary: its result was not final")
     launches = ctx.stats()["kernel_launches"] - launches0
+    # GZB_AB="opt=v,opt=v;opt=v;..." (experiments): the same timed loop again under every listed setting of the
+    # library's integer options (gzb_set_option), all ranks alike; max over ranks on stderr; GZB_AB_TRACE=1 adds the
+    # stream timeline of one step of rank 0 under each setting.  Not part of the bench line.
+    if os.environ.get("GZB_AB"):
+        for cfg in os.environ["GZB_AB"].split(";"):
+            for kv in cfg.split(","):
+                k_, v_ = kv.split("=")
+                ctx.set_option(k_, int(v_))
+            for _ in range(3):
+                flush_l2()
+                step(check_now=True)
+            ab_ms = []
+            for _ in range(args.steps):
+                barrier()
+                flush_l2()
+                if world > 1:
+                    dist.all_reduce(sync_word)
+                e0.record()
+                step()
+                e1.record()
+                torch.cuda.synchronize()
+                ab_ms.append(e0.elapsed_time(e1))
+            tm_ab = torch.tensor([float(np.mean(ab_ms)), float(np.min(ab_ms))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tm_ab, op=dist.ReduceOp.MAX)
+            ok_ab = mapper.boundaries_verdict()
+            log("[rank %d] A/B %-44s mean %.4f ms  min %.4f ms (max over ranks: %.4f / %.4f)%s"
+                % (rank, cfg, float(np.mean(ab_ms)), float(np.min(ab_ms)), float(tm_ab[0].item()), float(tm_ab[1].item()),
+                   "" if ok_ab else "  RE-SEED NEEDED"))
+            if os.environ.get("GZB_AB_TRACE"):
+                barrier()
+                if rank == 0:
+                    ctx.set_option("trace", 1)
+                flush_l2()
+                if world > 1:
+                    dist.all_reduce(sync_word)
+                step()
+                ctx.sync()
+                if rank == 0:
+                    ctx.set_option("trace", 0)
+                barrier()
     if hasattr(mapper, "detach"):
         mapper.detach()                    # the per-stage timings below are local: no stores into the peers
     total_ms = float(np.sum(step_ms))
@@ -723,9 +764,9 @@ def run_ours(args, w):
         torch.cuda.empty_cache()
         n_e2e = max(3, min(args.steps, 5))
 
-        def timed_calls(make, reps, after=None, warm=3):
+        def timed_calls(make, reps, after=None, warm=4):
             # `warm` untimed calls first (the library's staging buffers, workspaces and the allocator's pools reach their
-            # steady state after two or three calls: 27 / 23 / 22.6 / 19.5 / 19.6 ms measured for the first five)
+            # steady state after four calls: 27 / 23 / 22.6 / 21.4 / 17.7 / 17.9 ms measured for the first six)
             out, last = [], None
             for it in range(warm + reps):
                 barrier()
@@ -773,7 +814,7 @@ def run_ours(args, w):
             dist.all_reduce(hb, op=dist.ReduceOp.SUM)
         e2e = {"value": nt_total / t_e2e, "unit": "points/s", "h2d_bytes_per_step": int(hb[0].item()),
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": t_e2e * 1e3, "api": api,
-               "gpu_launches_per_step": int(stats["kernel_launches"]), "warmup_calls": 3, "timed_calls": n_e2e,
+               "gpu_launches_per_step": int(stats["kernel_launches"]), "warmup_calls": 4, "timed_calls": n_e2e,
                "breakdown_s": {k: round(v, 5) for k, v in timing.items()}}
         if world > 1:
             e2e["nvlink_bytes_per_step"] = {"grid_broadcast": int(hb[2].item()), "product_gather": int(hb[3].item())}

@@ -109,9 +109,17 @@ struct gzb_ctx {
     cudaStream_t aux_stream = nullptr;     // chain part of K1 while K2+K3 run on `stream` (gzb_mapping)
     cudaStream_t push_stream = nullptr;    // copies of finished chunks of the two series into the peers' buffers (k_push)
     cudaEvent_t ev_push[9] = {};           // chunk c of the bulk kernel done (0..7); all pushes done (8)
+    int push_blocks = 64;                  // option "push_blocks": grid of k_push (blocks of 256 threads)
+    int push_mode = 0;                     // option "push_mode": 0 = k_push (stores over NVLink issued by SMs), 1 = one peer copy per peer and series on the copy engines (peer_stream[])
+    cudaStream_t peer_stream[GZB_MAX_PEERS] = {};   // push_mode 1: one stream per peer, created on first use
+    cudaEvent_t ev_peer[GZB_MAX_PEERS] = {};
+    int peer_streams_used = 0;             // how many of them carry copies of the last bulk call
     int push_pending = 0;                  // pushes of the last bulk call are in flight on push_stream (ev_push[8] marks their end)
     int bulk_chunks = 0;                   // option "bulk_chunks": 0 = automatic (1 alone, 4 with peer outputs), else 1..8
-    cudaEvent_t ev_k1[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k1[3] = {nullptr, nullptr, nullptr};   // 0: search kernel done; 1: chain part done; 2: the auxiliary stream has passed its wait on 0
+    int carveout = -1;                     // option "carveout": preferred shared-memory carve-out (percent of the SM's maximum) of the kernels of a step, -1 = the driver's choice per kernel (see gzb_apply_carveout)
+    int chain_first = 0;                   // option "chain_first": the bulk kernel is released through the auxiliary stream (see gzb_nearest_dev)
+    int bulk_resident = 0;                 // option "bulk_resident": n > 0 = the fused bulk kernel runs as n persistent blocks per SM (grid-stride), leaving the rest of every SM to the chain kernels; 0 = one block per 128 points
     GzbPeerOut peer_out = {0, {}, {}};   // gzb_set_peer_outputs: where K4 also writes its two series
     double* peer_local_np = nullptr;     // ... when its local outputs are these buffers
     double* peer_local_bl = nullptr;
@@ -284,7 +292,15 @@ int gzb_arena_reserve(gzb_ctx* ctx, size_t bytes);            // grow (contents 
 void* gzb_arena_take(gzb_ctx* ctx, size_t bytes);             // 256-byte aligned slice or null
 int gzb_use_device(gzb_ctx* ctx);
 void gzb_trace(gzb_ctx* ctx, cudaStream_t s, const char* what);   // option "trace": timestamped marks on any stream (debugging aid)
-int gzb_build_mask_bits(gzb_ctx* ctx);                        // gzb_interp.cu: after every change of the mask
+int gzb_build_mask_bits(gzb_ctx* ctx);
+// Kernels that ask for different shared-memory / L1 splits cannot share an SM: the SM has to drain before its split changes.
+// The bulk kernels use no shared memory (the driver gives them the whole array as L1), the chain kernels of K1 that run
+// beside them a few KB per block -- so every launch of a chain kernel waits for SMs to drain (in-kernel time marks: the warp
+// search starts ~20 us after the search kernel ends when the bulk kernel got there first; with persistent bulk blocks, only
+// when the bulk kernel ends).  One preferred carve-out for all the kernels of a step lets their blocks co-reside at once.
+void gzb_apply_carveout(gzb_ctx* ctx);
+void gzb_carveout_nearest(int pct);      // gzb_nearest.cu
+void gzb_carveout_mesh(int pct);         // gzb_mesh.cu                        // gzb_interp.cu: after every change of the mask
 
 static inline size_t gzb_align(size_t n) { return (n + 255) & ~size_t(255); }
 

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -60,6 +61,18 @@ void gzb_trace(gzb_ctx* ctx, cudaStream_t s, const char* what) {
     cudaEventRecord(ctx->trace_ev[k], s);
 }
 
+void gzb_apply_carveout(gzb_ctx* ctx) {
+    static int applied[64];
+    static bool init = false;
+    if (!init) { for (int k = 0; k < 64; ++k) applied[k] = -2; init = true; }
+    const int d = ctx->device & 63;
+    if (applied[d] == ctx->carveout) return;
+    applied[d] = ctx->carveout;
+    gzb_carveout_nearest(ctx->carveout);
+    gzb_carveout_mesh(ctx->carveout);
+    cudaGetLastError();
+}
+
 int gzb_use_device(gzb_ctx* ctx) {
     GZB_CUDA(ctx, cudaSetDevice(ctx->device));
     return GZB_OK;
@@ -72,7 +85,7 @@ int gzb_use_device(gzb_ctx* ctx) {
 // Large transfers are therefore cut into GZB_BC_THREADS contiguous parts, each moved by its own
 // thread through two pinned 8 MiB slots on its own stream (host memcpy of one slot overlapping the
 // DMA of the other).  The slots are allocated once per process and kept (gzb_pool_trim frees them).
-#define GZB_BC_THREADS 12
+#define GZB_BC_THREADS 24
 // how many host threads the library's host-side helpers (parallel copies, mask packing, record staging) may start:
 // 0 = automatic (the machine's hardware threads), else the cap set by gzb_set_host_threads() or GZB_HOST_THREADS --
 // with one process per GPU every rank gets its share of the cores instead of all of them (8 x 12 threads on 32 cores)
@@ -94,7 +107,7 @@ extern "C" int gzb_set_host_threads(int n) {
     g_host_threads = n < 0 ? 0 : n;
     return GZB_OK;
 }
-#define GZB_BC_SLOT ((size_t)4 << 20)
+#define GZB_BC_SLOT ((size_t)1 << 20)      /* small slots: a thread fills one before its first DMA can start */
 #define GZB_BC_MIN ((size_t)24 << 20)
 namespace {
 struct BigCopy {
@@ -129,42 +142,62 @@ template <typename T> static void pack_into(int8_t* out, const char* src, size_t
     for (size_t k = 0; k < n; ++k) out[k] = (int8_t)p[k];
 }
 
-void bigcopy_part(int dev, int t, char* dst, const char* src, size_t bytes, bool h2d, cudaError_t* err, int pack = 0,
-                  size_t first_elem = 0) {
+// one transfer of a threaded copy: `bytes` from src to dst; pack > 1: see pack_into (then `bytes` counts int8 elements)
+struct BcJob {
+    char* dst;
+    const char* src;
+    size_t bytes;
+    int pack;
+};
+
+// Thread t of `nth` moves its slice of every job, one after the other, through its two pinned slots: the slots keep
+// alternating across jobs, so that several arrays (lat + lon, angle + mask) go up in ONE pipelined pass -- no second
+// ramp-up (every thread fills a slot before the first DMA can start) and no second round of thread starts and joins.
+void bigcopy_part(int dev, int t, int nth, const BcJob* jobs, int njobs, bool h2d, cudaError_t* err) {
     cudaSetDevice(dev);
     cudaError_t e = cudaSuccess;
-    size_t off = 0;
     int k = 0;
     bool used[2] = {false, false};
-    size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
-    while (off < bytes && e == cudaSuccess) {
-        const size_t len = bytes - off < GZB_BC_SLOT ? bytes - off : GZB_BC_SLOT;
-        if (used[k]) {                           // the slot's previous transfer must be over
-            e = cudaEventSynchronize(g_bc.ev[t][k]);
-            if (!h2d && e == cudaSuccess) memcpy(dst + pend_off[k], g_bc.slot[t][k], pend_len[k]);
+    char* pend_dst[2] = {nullptr, nullptr};
+    size_t pend_len[2] = {0, 0};
+    for (int q = 0; q < njobs && e == cudaSuccess; ++q) {
+        const BcJob& J = jobs[q];
+        const size_t part = (((J.bytes + nth - 1) / nth) + 4095) & ~(size_t)4095;
+        const size_t a = (size_t)t * part;
+        if (a >= J.bytes) continue;
+        const size_t bytes = J.bytes - a < part ? J.bytes - a : part;
+        char* dst = J.dst + a;
+        const char* src = J.pack > 1 ? J.src : J.src + a;      // packed sources are addressed by element (first_elem below)
+        size_t off = 0;
+        while (off < bytes && e == cudaSuccess) {
+            const size_t len = bytes - off < GZB_BC_SLOT ? bytes - off : GZB_BC_SLOT;
+            if (used[k]) {                           // the slot's previous transfer must be over
+                e = cudaEventSynchronize(g_bc.ev[t][k]);
+                if (!h2d && e == cudaSuccess) memcpy(pend_dst[k], g_bc.slot[t][k], pend_len[k]);
+            }
+            if (e != cudaSuccess) break;
+            if (h2d) {
+                if (J.pack == 8) pack_into<int64_t>((int8_t*)g_bc.slot[t][k], src, a + off, len);
+                else if (J.pack == 4) pack_into<int32_t>((int8_t*)g_bc.slot[t][k], src, a + off, len);
+                else if (J.pack == 2) pack_into<int16_t>((int8_t*)g_bc.slot[t][k], src, a + off, len);
+                else memcpy(g_bc.slot[t][k], src + off, len);
+                e = cudaMemcpyAsync(dst + off, g_bc.slot[t][k], len, cudaMemcpyHostToDevice, g_bc.stream[t]);
+            } else {
+                e = cudaMemcpyAsync(g_bc.slot[t][k], src + off, len, cudaMemcpyDeviceToHost, g_bc.stream[t]);
+                pend_dst[k] = dst + off;
+                pend_len[k] = len;
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(g_bc.ev[t][k], g_bc.stream[t]);
+            used[k] = true;
+            off += len;
+            k ^= 1;
         }
-        if (e != cudaSuccess) break;
-        if (h2d) {
-            if (pack == 8) pack_into<int64_t>((int8_t*)g_bc.slot[t][k], src, first_elem + off, len);
-            else if (pack == 4) pack_into<int32_t>((int8_t*)g_bc.slot[t][k], src, first_elem + off, len);
-            else if (pack == 2) pack_into<int16_t>((int8_t*)g_bc.slot[t][k], src, first_elem + off, len);
-            else memcpy(g_bc.slot[t][k], src + off, len);
-            e = cudaMemcpyAsync(dst + off, g_bc.slot[t][k], len, cudaMemcpyHostToDevice, g_bc.stream[t]);
-        } else {
-            e = cudaMemcpyAsync(g_bc.slot[t][k], src + off, len, cudaMemcpyDeviceToHost, g_bc.stream[t]);
-            pend_off[k] = off;
-            pend_len[k] = len;
-        }
-        if (e == cudaSuccess) e = cudaEventRecord(g_bc.ev[t][k], g_bc.stream[t]);
-        used[k] = true;
-        off += len;
-        k ^= 1;
     }
     for (int q = 0; q < 2 && e == cudaSuccess; ++q) {
         const int kk = k ^ q;                    // oldest first
         if (!used[kk]) continue;
         e = cudaEventSynchronize(g_bc.ev[t][kk]);
-        if (!h2d && e == cudaSuccess) memcpy(dst + pend_off[kk], g_bc.slot[t][kk], pend_len[kk]);
+        if (!h2d && e == cudaSuccess) memcpy(pend_dst[kk], g_bc.slot[t][kk], pend_len[kk]);
     }
     *err = e;
 }
@@ -172,24 +205,20 @@ void bigcopy_part(int dev, int t, char* dst, const char* src, size_t bytes, bool
 
 // Copies `bytes` between pageable host memory and the device and RETURNS WHEN DONE.  Falls back to
 // one cudaMemcpyAsync + stream synchronisation for small or already pinned buffers.
-int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true, int pack = 0) {
-    if (bytes == 0) return GZB_OK;
-    const void* host = h2d ? src : dst;
-    bool plain = bytes < GZB_BC_MIN && pack <= 1;
-    if (!plain) {
-        cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, host) == cudaSuccess) {
-            if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) plain = true;
-        } else {
-            cudaGetLastError();
-        }
+// A transfer is "plain" (one cudaMemcpyAsync) when it is small or when the host side is not pageable memory.
+static bool bigcopy_plain(const void* host, size_t bytes, int pack) {
+    if (bytes < GZB_BC_MIN && pack <= 1) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess) {
+        if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return true;
+    } else {
+        cudaGetLastError();
     }
-    std::unique_lock<std::mutex> lk(g_bc_mu, std::defer_lock);
-    if (!plain) {
-        lk.lock();
-        if (!bigcopy_ready(ctx->device)) { plain = true; lk.unlock(); }
-    }
-    if (plain && pack > 1) {          // no staging slots on this device: convert on this thread, then one plain copy
+    return false;
+}
+
+static int bigcopy_one_plain(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, int pack) {
+    if (pack > 1) {          // no staging slots: convert on this thread, then one plain copy
         std::vector<int8_t> tmp(bytes);
         if (pack == 8) pack_into<int64_t>(tmp.data(), (const char*)src, 0, bytes);
         else if (pack == 4) pack_into<int32_t>(tmp.data(), (const char*)src, 0, bytes);
@@ -198,10 +227,35 @@ int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d
         GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return GZB_OK;
     }
-    if (plain) {
-        // cudaMemcpyDefault: `src` of an upload may itself be device memory (a grid replicated from another GPU)
-        GZB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
-        GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // cudaMemcpyDefault: `src` of an upload may itself be device memory (a grid replicated from another GPU)
+    GZB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    GZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GZB_OK;
+}
+
+// Moves every job between pageable host memory and the device in one threaded, pipelined pass and RETURNS WHEN DONE.
+int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d, bool sync_before) {
+    BcJob jobs[4];
+    int njobs = 0;
+    for (int q = 0; q < njobs_in && q < 4; ++q) {
+        const BcJob& J = jobs_in[q];
+        if (J.bytes == 0) continue;
+        const void* host = h2d ? (const void*)J.src : (const void*)J.dst;
+        if (bigcopy_plain(host, J.bytes, J.pack)) {
+            const int rc = bigcopy_one_plain(ctx, J.dst, J.src, J.bytes, J.pack);
+            if (rc != GZB_OK) return rc;
+        } else {
+            jobs[njobs++] = J;
+        }
+    }
+    if (njobs == 0) return GZB_OK;
+    std::unique_lock<std::mutex> lk(g_bc_mu);
+    if (!bigcopy_ready(ctx->device)) {
+        lk.unlock();
+        for (int q = 0; q < njobs; ++q) {
+            const int rc = bigcopy_one_plain(ctx, jobs[q].dst, jobs[q].src, jobs[q].bytes, jobs[q].pack);
+            if (rc != GZB_OK) return rc;
+        }
         return GZB_OK;
     }
     // everything queued so far (producers of `src`, users of `dst`) -- unless the caller knows better
@@ -211,21 +265,22 @@ int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d
     int want = gzb_host_threads(GZB_BC_THREADS);
     if (want > 2 && want == (int)std::thread::hardware_concurrency()) --want;      // leave one core to the caller
     want = want < 2 ? 2 : want;
-    const size_t part = (((bytes + want - 1) / want) + 4095) & ~(size_t)4095;
-    int nth = 0;
     for (int t = 0; t < want; ++t) {
-        const size_t a = (size_t)t * part;
-        if (a >= bytes) break;
-        const size_t len = bytes - a < part ? bytes - a : part;
         errs[t] = cudaSuccess;
-        if (pack > 1) th[t] = std::thread(bigcopy_part, ctx->device, t, (char*)dst + a, (const char*)src, len, h2d, &errs[t], pack, a);
-        else th[t] = std::thread(bigcopy_part, ctx->device, t, (char*)dst + a, (const char*)src + a, len, h2d, &errs[t], 0, (size_t)0);
-        ++nth;
+        th[t] = std::thread(bigcopy_part, ctx->device, t, want, (const BcJob*)jobs, njobs, h2d, &errs[t]);
     }
-    for (int t = 0; t < nth; ++t) th[t].join();
-    for (int t = 0; t < nth; ++t)
+    for (int t = 0; t < want; ++t) th[t].join();
+    for (int t = 0; t < want; ++t)
         if (errs[t] != cudaSuccess) return gzb_fail(ctx, GZB_ERR_CUDA, "parallel copy failed: %s", cudaGetErrorString(errs[t]));
     return GZB_OK;
+}
+
+// Copies `bytes` between pageable host memory and the device and RETURNS WHEN DONE.  Falls back to
+// one cudaMemcpyAsync + stream synchronisation for small or already pinned buffers.
+int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true, int pack = 0) {
+    if (bytes == 0) return GZB_OK;
+    const BcJob J = {(char*)dst, (const char*)src, bytes, pack};
+    return gzb_bigcopy_jobs(ctx, &J, 1, h2d, sync_before);
 }
 
 // ======================================================================== device memory pool
@@ -636,9 +691,24 @@ k_lut_fill(const GzbLut L, const unsigned* __restrict__ in, unsigned* __restrict
 // every cell OUTSIDE its 5x5 index neighbourhood, and outside its 3x3 one.  One warp per leaf tile T, lane = cell of T:
 //   cells inside T's 5x3-tile window  -> evaluated one by one (tiles too far to matter skipped);
 //   cells outside that window         -> cert(T) - |c - centre(T)|   (triangle inequality).
+// The inner loop (every cell of the tile against every cell of a window tile) is what a grid context costs on the GPU
+// (4.1 of 6.2 ms on ORCA12), so it is kept lean: the candidates are broadcast from shared memory (one 128-bit load
+// instead of three shuffles), and which candidates lie inside a lane's 5x5 / 3x3 neighbourhood is one bit test on a mask
+// the lane builds once per window tile.
+__device__ __forceinline__ unsigned cc_inside_mask(const int A, const int B, const int h) {
+    // bit k = (kj, ki) of a 4 x 8 tile set iff |A + kj| <= h and |B + ki| <= h
+    unsigned rows = 0, cols = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rows |= (unsigned)(A + q >= -h && A + q <= h) << (8 * q);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cols |= (unsigned)(B + q >= -h && B + q <= h) << q;
+    return rows * cols;      // rows holds one bit per byte: the product copies `cols` into the bytes of the rows that are in
+}
+
 __global__ void __launch_bounds__(256)
 k_cellcert(const GzbGrid g, float4* __restrict__ cellv) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float4 sq[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const GzbLevel L0 = g.lev[0];
     const int64_t ntile = (int64_t)L0.nJ * L0.nI;
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -646,8 +716,9 @@ k_cellcert(const GzbGrid g, float4* __restrict__ cellv) {
     const int tJ = (int)(tile / L0.nI), tI = (int)(tile - (int64_t)tJ * L0.nI);
     const float* __restrict__ cc = g.cells + tile * 96;
     const float x = cc[lane], y = cc[32 + lane], z = cc[64 + lane];
-    const int64_t j = (int64_t)tJ * GZB_TILE_J + (lane >> 3);
-    const int64_t i = (int64_t)tI * GZB_TILE_I + (lane & 7);
+    const int lj = lane >> 3, li = lane & 7;
+    const int64_t j = (int64_t)tJ * GZB_TILE_J + lj;
+    const int64_t i = (int64_t)tI * GZB_TILE_I + li;
     const bool ok = (j < g.Nj) && (i < g.Ni);
     const int64_t tidx = gzb_leaf_index(g, tJ, tI);
     const float4 nd = L0.nodes[tidx];
@@ -675,21 +746,19 @@ k_cellcert(const GzbGrid g, float4* __restrict__ cellv) {
                 if (__all_sync(0xffffffffu, skip)) continue;
             }
             const float* __restrict__ wc = g.cells + ((int64_t)wJ * L0.nI + wI) * 96;
-            const float qx = wc[lane], qy = wc[32 + lane], qz = wc[64 + lane];
-            const int64_t qj0 = (int64_t)wJ * GZB_TILE_J, qi0 = (int64_t)wI * GZB_TILE_I;
-#pragma unroll 8
+            __syncwarp();
+            sq[warp][lane] = make_float4(wc[lane], wc[32 + lane], wc[64 + lane], 0.0f);
+            __syncwarp();
+            // candidate k = (kj, ki) of W sits at index offset (4 dJ + kj - lj, 8 dI + ki - li) from this lane's cell
+            const int A = GZB_TILE_J * order_j[a] - lj, B = GZB_TILE_I * order_i[b] - li;
+            const unsigned in5 = cc_inside_mask(A, B, 2), in3 = cc_inside_mask(A, B, 1);
+#pragma unroll
             for (int k = 0; k < 32; ++k) {
-                const float ux = __shfl_sync(0xffffffffu, qx, k);
-                const float uy = __shfl_sync(0xffffffffu, qy, k);
-                const float uz = __shfl_sync(0xffffffffu, qz, k);
-                const int64_t qj = qj0 + (k >> 3), qi = qi0 + (k & 7);
-                const int64_t aj = qj - j, ai = qi - i;
-                const bool inside = (aj >= -2) && (aj <= 2) && (ai >= -2) && (ai <= 2);
-                const bool inside3 = (aj >= -1) && (aj <= 1) && (ai >= -1) && (ai <= 1);
-                const float dx = x - ux, dy = y - uy, dz = z - uz;
+                const float4 u = sq[warp][k];
+                const float dx = x - u.x, dy = y - u.y, dz = z - u.z;
                 const float d2 = dx * dx + dy * dy + dz * dz;     // padded cells sit at 1e3: never the minimum
-                if (!inside) m2 = fminf(m2, d2);
-                if (!inside3) m3 = fminf(m3, d2);
+                if (!((in5 >> k) & 1u)) m2 = fminf(m2, d2);
+                if (!((in3 >> k) & 1u)) m3 = fminf(m3, d2);
             }
         }
     }
@@ -908,16 +977,27 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
         }
         CK(cudaEventCreateWithFlags(&ctx->ev_k1[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_k1[1], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_k1[2], cudaEventDisableTiming));
         ctx->stream = ctx->own_stream;
         bool evfail = false;
         for (int k = 0; k < 4; ++k)
             if ((e = cudaEventCreateWithFlags(&ctx->ev[k], cudaEventDisableTiming)) != cudaSuccess) evfail = true;
         if (evfail) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); break; }
         const size_t n = (size_t)nj * (size_t)ni;
+        // GZB_CREATE_TIMING=1: host-side time marks of the phases below on stderr (where a context's milliseconds go)
+        const bool ctime = getenv("GZB_CREATE_TIMING") != nullptr;
+        const auto tc0 = std::chrono::steady_clock::now();
+        auto cmark = [&](const char* what) {
+            if (ctime) fprintf(stderr, "[gzb create] %7.2f ms  %s\n",
+                               1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count(), what);
+        };
         CK(gzb_pool_malloc((void**)&ctx->d_lat, n * sizeof(double)));
         CK(gzb_pool_malloc((void**)&ctx->d_lon, n * sizeof(double)));
-        if ((rc = gzb_bigcopy(ctx, ctx->d_lat, lat, n * sizeof(double), true)) != GZB_OK) break;
-        if ((rc = gzb_bigcopy(ctx, ctx->d_lon, lon, n * sizeof(double), true)) != GZB_OK) break;
+        {
+            const BcJob up[2] = {{(char*)ctx->d_lat, (const char*)lat, n * sizeof(double), 0}, {(char*)ctx->d_lon, (const char*)lon, n * sizeof(double), 0}};
+            if ((rc = gzb_bigcopy_jobs(ctx, up, 2, true, true)) != GZB_OK) break;
+        }
+        cmark("lat, lon uploaded");
         CK(gzb_pool_malloc((void**)&ctx->d_ll, n * sizeof(double2)));
         k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, ctx->d_lat, ctx->d_lon, ctx->d_ll);
         ctx->stats.kernel_launches++;
@@ -948,18 +1028,27 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
         ctx->g.angle = ctx->d_angle;
         ctx->g.mask = ctx->d_mask;
         if ((rc = build_pyramid(ctx)) != GZB_OK) break;
+        cmark("search structures enqueued");
+        if (ctime && getenv("GZB_CREATE_TIMING")[0] == '2') { cudaStreamSynchronize(ctx->stream); cmark("search structures built (synchronised: GZB_CREATE_TIMING=2)"); }
         // the angle and the mask are not needed by the search structures: their upload runs on the host
         // threads while the GPU finishes the certificates and the seed table
-        if (angle_or_null) {
-            if ((rc = gzb_bigcopy(ctx, ctx->d_angle, angle_or_null, n * sizeof(double), true, false)) != GZB_OK) break;
-            ctx->stats.h2d_bytes += n * sizeof(double);
+        {
+            BcJob up[2];
+            int nup = 0;
+            if (angle_or_null) {
+                up[nup++] = {(char*)ctx->d_angle, (const char*)angle_or_null, n * sizeof(double), 0};
+                ctx->stats.h2d_bytes += n * sizeof(double);
+            }
+            if (mask_or_null) {
+                up[nup++] = {(char*)ctx->d_mask, (const char*)mask_or_null, n, mask_itemsize};
+                ctx->stats.h2d_bytes += n;
+            }
+            if (nup && (rc = gzb_bigcopy_jobs(ctx, up, nup, true, false)) != GZB_OK) break;
         }
-        if (mask_or_null) {
-            if ((rc = gzb_bigcopy(ctx, ctx->d_mask, mask_or_null, n, true, false, mask_itemsize)) != GZB_OK) break;
-            ctx->stats.h2d_bytes += n;
-        }
+        cmark("angle, mask uploaded");
         if ((rc = gzb_build_mask_bits(ctx)) != GZB_OK) break;
         e = cudaStreamSynchronize(ctx->stream);
+        cmark("device idle: context ready");
         if (e != cudaSuccess) { rc = gzb_fail(ctx, GZB_ERR_CUDA, "grid upload / pyramid build: %s", cudaGetErrorString(e)); break; }
     } while (0);
     if (rc != GZB_OK) {
@@ -1005,9 +1094,13 @@ extern "C" int gzb_destroy(gzb_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->push_stream) cudaStreamDestroy(ctx->push_stream);
+    for (int k = 0; k < GZB_MAX_PEERS; ++k) {
+        if (ctx->peer_stream[k]) { cudaStreamSynchronize(ctx->peer_stream[k]); cudaStreamDestroy(ctx->peer_stream[k]); }
+        if (ctx->ev_peer[k]) cudaEventDestroy(ctx->ev_peer[k]);
+    }
     for (int k = 0; k < 9; ++k) if (ctx->ev_push[k]) cudaEventDestroy(ctx->ev_push[k]);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 3; ++k)
         if (ctx->ev_k1[k]) cudaEventDestroy(ctx->ev_k1[k]);
     cudaGetLastError();
     delete ctx;
@@ -1141,6 +1234,11 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "bulk_chunks")) { ctx->bulk_chunks = value < 0 ? 0 : (value > 8 ? 8 : (int)value); return GZB_OK; }
     if (!strcmp(name, "k4_early")) { ctx->k4_early = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "pdl")) { ctx->pdl = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "push_blocks")) { ctx->push_blocks = value < 1 ? 1 : (value > 4096 ? 4096 : (int)value); return GZB_OK; }
+    if (!strcmp(name, "push_mode")) { ctx->push_mode = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "carveout")) { ctx->carveout = value < 0 ? -1 : (value > 100 ? 100 : (int)value); return GZB_OK; }
+    if (!strcmp(name, "chain_first")) { ctx->chain_first = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "bulk_resident")) { ctx->bulk_resident = value < 0 ? 0 : (value > 16 ? 16 : (int)value); return GZB_OK; }
     if (!strcmp(name, "ix64")) { ctx->force_ix64 = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "prefetch")) { ctx->prefetch = value < 0 ? 0 : (value > 4 ? 4 : (int)value); return GZB_OK; }
     if (!strcmp(name, "l2_fetch")) {      // device-wide hint (cudaLimitMaxL2FetchGranularity): 32, 64 or 128 bytes
@@ -1456,6 +1554,7 @@ extern "C" int gzb_peer_finish(gzb_ctx* ctx, const int64_t* np_rows, int64_t nro
                                                                   (const long long*)gathered, stride_words, offset_words,
                                                                   flag_dev_or_null, ctx->d_flags + 3);
     GZB_LAUNCH_CHECK(ctx);
+    gzb_trace(ctx, ctx->stream, "end-of-step kernel end: edges, barrier, check (main)");
     ctx->barrier_err_pending = 1;
     return GZB_OK;
 }

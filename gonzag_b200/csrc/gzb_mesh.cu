@@ -480,25 +480,43 @@ __global__ void __launch_bounds__(128, GZB_EXP_BULK_BLOCKS)
 k_mesh_weights_interp(const GzbGrid g, const long long t_first, const long long nt, const double* __restrict__ yt,
                       const double* __restrict__ xt, const long long* __restrict__ NP, const GzbGlobalNearest gn,
                       long long* __restrict__ SM, double* __restrict__ WB, const int force_heavy, const InterpArgs ia) {
-    const long long t = t_first + (long long)blockIdx.x * blockDim.x + threadIdx.x;      // this launch: points [t_first, nt)
     GZB_KT_MIN(g, 13);
-    if (t >= nt) return;
-    const double yT = yt[t], xT = xt[t];
-    IX cj[4], ci[4], jP, iP;
-    if (!nearest_of<IX>(g, NP, gn, t, jP, iP)) return;
-    if (PF == 4) prefetch_hood<T>(g, t, ia, (long long)jP, (long long)iP);
-    source_mesh_one<IX>(g, yT, xT, jP, iP, force_heavy, cj, ci);
-    if (PF == 1) prefetch_point<T, IX>(g, t, ia, cj, ci);
-    store_mesh<IX>(SM, t, cj, ci);
-    double w[4];
-    weights_one<IX>(g, yT, xT, cj, ci, w);
-    double2* out = reinterpret_cast<double2*>(WB + 4 * t);
-    const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
-    out[0] = rw[0];
-    out[1] = rw[1];
-    interp_point<T, false, true, (PF >= 3 ? 3 : 0), IX>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
-                                 ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, cj, ci, rw);
+    // this launch: points [t_first, nt), one block per 128 points -- or (option "bulk_resident") a few persistent blocks per
+    // SM striding over them, so that the chain kernels of K1, which run beside this one, always find room on every SM
+    for (long long t = t_first + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += (long long)gridDim.x * blockDim.x) {
+        const double yT = yt[t], xT = xt[t];
+        IX cj[4], ci[4], jP, iP;
+        if (!nearest_of<IX>(g, NP, gn, t, jP, iP)) continue;
+        if (PF == 4) prefetch_hood<T>(g, t, ia, (long long)jP, (long long)iP);
+        source_mesh_one<IX>(g, yT, xT, jP, iP, force_heavy, cj, ci);
+        if (PF == 1) prefetch_point<T, IX>(g, t, ia, cj, ci);
+        store_mesh<IX>(SM, t, cj, ci);
+        double w[4];
+        weights_one<IX>(g, yT, xT, cj, ci, w);
+        double2* out = reinterpret_cast<double2*>(WB + 4 * t);
+        const double2 rw[2] = {make_double2(w[0], w[1]), make_double2(w[2], w[3])};
+        out[0] = rw[0];
+        out[1] = rw[1];
+        interp_point<T, false, true, (PF >= 3 ? 3 : 0), IX>(g, t, ia.t_sat, SM, WB, ia.nrec, ia.tmod, (const T*)ia.slab, ia.k0, ia.nk, ia.rmiss, 1,
+                                     ia.out_np, ia.out_bl, ia.err, ia.mbits, ia.mflag, ia.peers, cj, ci, rw);
+    }
     GZB_KT_MAX(g, 13);
+}
+
+template <typename IX> static void carveout_ix(int v) {
+#define GZB_CV(K) cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, v)
+    GZB_CV((k_mesh_weights_interp<float, 0, IX>)); GZB_CV((k_mesh_weights_interp<float, 1, IX>));
+    GZB_CV((k_mesh_weights_interp<float, 3, IX>)); GZB_CV((k_mesh_weights_interp<float, 4, IX>));
+    GZB_CV((k_mesh_weights_interp<double, 0, IX>)); GZB_CV((k_mesh_weights_interp<double, 1, IX>));
+    GZB_CV((k_mesh_weights_interp<double, 3, IX>)); GZB_CV((k_mesh_weights_interp<double, 4, IX>));
+    GZB_CV(k_mesh_weights<IX>); GZB_CV(k_path_fix<IX>);
+#undef GZB_CV
+}
+
+void gzb_carveout_mesh(int pct) {
+    const int v = pct < 0 ? (int)cudaSharedmemCarveoutDefault : pct;
+    carveout_ix<int>(v);
+    carveout_ix<long long>(v);
 }
 
 static void fill_interp_args(gzb_ctx* ctx, InterpArgs& ia, const double* tt, int64_t nrec, const double* tmod,
@@ -570,7 +588,13 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     for (int c = 0; c < nchunk; ++c) {
         const long long a = ((nt * c / nchunk) + 127) & ~127LL, b = c + 1 == nchunk ? nt : (((nt * (c + 1) / nchunk) + 127) & ~127LL);
         if (b <= a) continue;
-        const unsigned nblk = (unsigned)((b - a + 127) / 128);
+        unsigned nblk = (unsigned)((b - a + 127) / 128);
+        if (ctx->bulk_resident > 0) {
+            int nsm = 148;
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+            const unsigned cap = (unsigned)(nsm * ctx->bulk_resident);
+            if (nblk > cap) nblk = cap;
+        }
 #define GZB_BULK(T, PF, IX) k_mesh_weights_interp<T, PF, IX><<<nblk, 128, 0, s>>>(ctx->g, a, b, yt, xt, npp, gn, (long long*)sm_out, \
                                                                                 wb_out, ctx->force_heavy, ia)
 #define GZB_BULK_PF(T, IX) { if (pfm == 4) GZB_BULK(T, 4, IX); else if (pfm == 3) GZB_BULK(T, 3, IX); else if (pfm) GZB_BULK(T, 1, IX); else GZB_BULK(T, 0, IX); }
@@ -579,16 +603,33 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
 #undef GZB_BULK_PF
 #undef GZB_BULK
         GZB_LAUNCH_CHECK(ctx);
-        if (push) {
+        if (push && ctx->push_mode == 0) {
             GZB_CUDA(ctx, cudaEventRecord(ctx->ev_push[c], s));
             GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->push_stream, ctx->ev_push[c], 0));
-            k_push<<<64, 256, 0, ctx->push_stream>>>(ctx->g, nt, vnp_out, vbl_out, peers, a, b);
+            k_push<<<(unsigned)ctx->push_blocks, 256, 0, ctx->push_stream>>>(ctx->g, nt, vnp_out, vbl_out, peers, a, b);
             GZB_LAUNCH_CHECK(ctx);
+            gzb_trace(ctx, ctx->push_stream, "push of a chunk end (push stream)");
+        } else if (push) {
+            // copy engines: one stream per peer, two copies (the two series) per chunk on each -- the SMs issue nothing
+            GZB_CUDA(ctx, cudaEventRecord(ctx->ev_push[c], s));
+            for (int k = 0; k < peers.n; ++k) {
+                if (!ctx->peer_stream[k]) {
+                    GZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->peer_stream[k], cudaStreamNonBlocking));
+                    GZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_peer[k], cudaEventDisableTiming));
+                }
+                GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->peer_stream[k], ctx->ev_push[c], 0));
+                GZB_CUDA(ctx, cudaMemcpyAsync(peers.np[k] + a, vnp_out + a, (size_t)(b - a) * 8, cudaMemcpyDeviceToDevice, ctx->peer_stream[k]));
+                GZB_CUDA(ctx, cudaMemcpyAsync(peers.bl[k] + a, vbl_out + a, (size_t)(b - a) * 8, cudaMemcpyDeviceToDevice, ctx->peer_stream[k]));
+            }
         }
     }
-    if (push) {      // the caller joins the copies (gzb_push_join): the repair kernel runs beside the last of them
+    if (push && ctx->push_mode == 0) {      // the caller joins the copies (gzb_push_join): the repair kernel runs beside the last of them
         GZB_CUDA(ctx, cudaEventRecord(ctx->ev_push[8], ctx->push_stream));
         ctx->push_pending = 1;
+    } else if (push) {
+        for (int k = 0; k < peers.n; ++k) GZB_CUDA(ctx, cudaEventRecord(ctx->ev_peer[k], ctx->peer_stream[k]));
+        ctx->peer_streams_used = peers.n;
+        ctx->push_pending = 2;
     }
     ctx->time_err_pending = 1;
     return GZB_OK;
@@ -614,6 +655,7 @@ int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int
     GZB_LAUNCH_CHECK(ctx);
     if (joined) {
         if (gzb_push_join(ctx) != GZB_OK) return GZB_ERR_CUDA;
+        gzb_trace(ctx, ctx->stream, "repair kernel end, pushes joined (main)");
         k_push_list<<<32, 128, 0, ctx->stream>>>(vnp_out, vbl_out, peers, list, count, list2, count2);
         GZB_LAUNCH_CHECK(ctx);
     }
@@ -624,8 +666,13 @@ int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int
 // the main stream waits for the chunk copies of the last bulk call (no-op when there are none)
 int gzb_push_join(gzb_ctx* ctx) {
     if (!ctx->push_pending) return GZB_OK;
+    const int mode = ctx->push_pending;
     ctx->push_pending = 0;
-    GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_push[8], 0));
+    if (mode == 1) {
+        GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_push[8], 0));
+    } else {
+        for (int k = 0; k < ctx->peer_streams_used; ++k) GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_peer[k], 0));
+    }
     return GZB_OK;
 }
 

@@ -997,6 +997,7 @@ __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned*
 // waits for blocks that already started.
 #define CH_PPT 4
 #define CH_PTS (FLAGS_BLOCK * CH_PPT)
+#define CH_LB 4        /* blocks per thread in the last block's ordered copy */
 __global__ void __launch_bounds__(FLAGS_BLOCK)
 k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
         const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
@@ -1158,13 +1159,21 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
     __syncthreads();
     if (!s_entry) return;
     __threadfence();
-    // the last block: exclusive prefix of the counts (chunks of FLAGS_BLOCK blocks), then the ordered copy
+    // the last block: exclusive prefix of the counts, then the ordered copy.  A thread owns CH_LB consecutive blocks and
+    // loads their counts in one go (independent loads: one round trip for the usual ~600 blocks instead of one per
+    // 256 blocks), the block scans the per-thread sums once per super-chunk of FLAGS_BLOCK * CH_LB blocks.
     const long long nblk = gridDim.x;
     long long carry = 0;
-    for (long long c0 = 0; c0 < nblk; c0 += FLAGS_BLOCK) {
-        const long long bk = c0 + threadIdx.x;
-        const int cnt = bk < nblk ? __ldcg(bcount + bk) : 0;
-        int incl2 = cnt;
+    for (long long c0 = 0; c0 < nblk; c0 += (long long)FLAGS_BLOCK * CH_LB) {
+        const long long bk0 = c0 + (long long)threadIdx.x * CH_LB;
+        int cnt[CH_LB];
+        int mysum = 0;
+#pragma unroll
+        for (int q = 0; q < CH_LB; ++q) {
+            cnt[q] = bk0 + q < nblk ? __ldcg(bcount + bk0 + q) : 0;
+            mysum += cnt[q];
+        }
+        int incl2 = mysum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, incl2, o);
@@ -1179,11 +1188,14 @@ k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* _
             if (w2 < warp) wb2 += wcnt[w2];
             ctot += wcnt[w2];
         }
-        if (ctot) {
-            // (block, position) pairs of this chunk: the chunk's breaks, cut over the threads of the block
-            const long long excl = carry + wb2 + (incl2 - cnt);
-            for (int e = 0; e < cnt; ++e)
-                if (GZB_CHK(g, excl + e >= 0 && excl + e < nt && e < CH_PTS, 2)) breaks[excl + e] = __ldcg(blist + bk * CH_PTS + e);
+        if (mysum) {
+            long long excl = carry + wb2 + (incl2 - mysum);
+#pragma unroll
+            for (int q = 0; q < CH_LB; ++q) {
+                for (int e = 0; e < cnt[q]; ++e)
+                    if (GZB_CHK(g, excl + e >= 0 && excl + e < nt && e < CH_PTS, 2)) breaks[excl + e] = __ldcg(blist + (bk0 + q) * CH_PTS + e);
+                excl += cnt[q];
+            }
         }
         carry += ctot;
     }
@@ -1369,7 +1381,7 @@ __device__ __forceinline__ void replay(const GzbGrid& g, const NearParams& p, Wa
 // dependent latency, and every launch boundary in it costs as much as the work between two of them.
 #define TAIL_WARPS 4
 #define TAIL_THREADS (32 * TAIL_WARPS)
-#define VALID_CHUNK 1024
+#define VALID_CHUNK 512
 #define TAIL_SHORT 8
 __global__ void __launch_bounds__(TAIL_THREADS)
 k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
@@ -1382,6 +1394,9 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
     __shared__ WarpSm ws[TAIL_WARPS];
     __shared__ long long sb[VALID_CHUNK + 1];
     __shared__ long long ss[VALID_CHUNK];
+    __shared__ unsigned char sv[VALID_CHUNK];      // verdicts of the chunk: 1 valid
+    __shared__ short s2[VALID_CHUNK];              // entries of the chunk whose replay is redone by a warp
+    __shared__ int s_n2;
     __shared__ int s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GZB_KT_MIN(g, 8);
@@ -1404,7 +1419,11 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // ---- (2) validation (warp 0; the block stages the break list in shared memory, VALID_CHUNK entries at a time)
+    // ---- (2) validation and (3) write-back, VALID_CHUNK breaks at a time.  The block stages the chunk's breaks and stops in
+    // shared memory; warp 0 decides validity (an ordered scan); then a THREAD per break copies its (short, intact) log into
+    // NP -- breaks, stops and verdicts come from shared memory, so a write-back costs two dependent round trips (the log,
+    // the slot in `chg`) -- and the replays that are long, or whose log another (discarded) replay overwrote, are listed in
+    // shared memory and redone warp per break (rare).  Validity of a chunk is final once the chunk has been scanned.
     long long cur_end = -1;
     for (long long c0 = 0; c0 < nb; c0 += VALID_CHUNK) {
         const int cn = (int)((nb - c0 < VALID_CHUNK) ? (nb - c0) : VALID_CHUNK);
@@ -1412,6 +1431,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
             sb[e] = (c0 + e < nb) ? breaks[c0 + e] : GZB_NOFLAT;
             if (e < cn) ss[e] = __ldcg(stop + c0 + e);
         }
+        if (threadIdx.x == 0) s_n2 = 0;
         __syncthreads();
         if (threadIdx.x < 32) {
             for (int base = 0; base < cn; base += 32) {
@@ -1423,7 +1443,7 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
                 const bool simple = !in || (s < nxt);
                 const long long b0 = __shfl_sync(0xffffffffu, b, 0);
                 if (__all_sync(0xffffffffu, simple) && b0 > cur_end) {
-                    if (in) valid[c0 + e] = 1;
+                    if (in) sv[e] = 1;
                     const int lastl = ((cn - base < 32) ? (cn - base) : 32) - 1;
                     cur_end = __shfl_sync(0xffffffffu, s, lastl);
                 } else {
@@ -1433,61 +1453,64 @@ k_tail(const GzbGrid g, const NearParams p, const long long nt, const double* __
                         if (base + l < cn) {
                             const bool v = kb > cur_end;
                             if (v) cur_end = ks;
-                            if (lane == l) valid[c0 + e] = v ? 1 : 0;
+                            if (lane == l) sv[e] = v ? 1 : 0;
                         }
                     }
                 }
             }
         }
         __syncthreads();
-    }
-    GZB_KT_MAX(g, 10);
-    // ---- (3) write-back of the valid replays, thread per break (short, intact logs); 2 = left to the warps below
-    for (long long k = threadIdx.x; k < nb; k += blockDim.x) {
-        if (!valid[k]) continue;
-        const long long b = breaks[k], e = __ldcg(stop + k);
-        if (!GZB_CHK(g, b >= 0 && b < nt && e >= b && e < nt, 8)) continue;
-        if (e == b) {
-            NP[2 * b] = __ldcg(first + 2 * k);
-            NP[2 * b + 1] = __ldcg(first + 2 * k + 1);
-            if (chg) {
-                const unsigned long long cp = atomicAdd(nchg, 1ull);
-                if (GZB_CHK(g, cp < 3ull * (unsigned long long)nt, 4)) chg[cp] = b;
+        if (c0 + VALID_CHUNK >= nb) GZB_KT_MAX(g, 10);
+        for (int e = threadIdx.x; e < cn; e += blockDim.x) {
+            const long long k = c0 + e;
+            valid[k] = sv[e];
+            if (!sv[e]) continue;
+            const long long b = sb[e], en = ss[e];
+            if (!GZB_CHK(g, b >= 0 && b < nt && en >= b && en < nt, 8)) continue;
+            if (en == b) {
+                const longlong2 f = __ldcg(reinterpret_cast<const longlong2*>(first) + k);
+                reinterpret_cast<longlong2*>(NP)[b] = f;
+                if (chg) {
+                    const unsigned long long cp = atomicAdd(nchg, 1ull);
+                    if (GZB_CHK(g, cp < 3ull * (unsigned long long)nt, 4)) chg[cp] = b;
+                }
+                continue;
             }
-            continue;
-        }
-        bool ok = (e - b) < TAIL_SHORT;
-        unsigned long long v[TAIL_SHORT];
-        if (ok) {
+            bool ok = (en - b) < TAIL_SHORT;
+            unsigned long long v[TAIL_SHORT];
+            if (ok) {
+#pragma unroll
+                for (int q = 0; q < TAIL_SHORT; ++q) v[q] = (b + q <= en) ? __ldcg(wlog + b + q) : 0ull;
+#pragma unroll
+                for (int q = 0; q < TAIL_SHORT; ++q)
+                    if (b + q <= en && (v[q] >> 36) != (WLOG_TAG(k) >> 36)) ok = false;
+            }
+            if (!ok) {
+                valid[k] = 2;
+                s2[atomicAdd(&s_n2, 1)] = e;
+                continue;
+            }
+            const int cnt = (int)(en - b + 1);
+            const unsigned long long base = chg ? atomicAdd(nchg, (unsigned long long)cnt) : 0ull;
 #pragma unroll
             for (int q = 0; q < TAIL_SHORT; ++q) {
-                v[q] = 0;
-                if (b + q <= e) {
-                    v[q] = __ldcg(wlog + b + q);
-                    if ((v[q] >> 36) != (WLOG_TAG(k) >> 36)) ok = false;
+                if (b + q <= en) {
+                    const long long f = (long long)(v[q] & 0xfffffffffULL) - 1;
+                    long long j = -1, i = -1;
+                    if (f >= 0) gzb_split(g, f, j, i);
+                    reinterpret_cast<longlong2*>(NP)[b + q] = make_longlong2(j, i);
+                    if (chg && GZB_CHK(g, base + q < 3ull * (unsigned long long)nt, 4)) chg[base + q] = b + q;
                 }
             }
         }
-        if (!ok) { valid[k] = 2; continue; }
-        const int cnt = (int)(e - b + 1);
-        const unsigned long long base = chg ? atomicAdd(nchg, (unsigned long long)cnt) : 0ull;
-#pragma unroll
-        for (int q = 0; q < TAIL_SHORT; ++q) {
-            if (b + q <= e) {
-                const long long f = (long long)(v[q] & 0xfffffffffULL) - 1;
-                long long j = -1, i = -1;
-                if (f >= 0) gzb_split(g, f, j, i);
-                NP[2 * (b + q)] = j;
-                NP[2 * (b + q) + 1] = i;
-                if (chg && GZB_CHK(g, base + q < 3ull * (unsigned long long)nt, 4)) chg[base + q] = b + q;
-            }
+        __syncthreads();
+        if (c0 + VALID_CHUNK >= nb) GZB_KT_MAX(g, 11);
+        const int n2 = s_n2;
+        for (int q = warp; q < n2; q += TAIL_WARPS) {
+            const int e = s2[q];
+            replay<true>(g, p, ws[warp], lane, nt, yt, xt, G, dG, c0 + e, sb[e], ss[e], stop, first, wlog, NP, steps, chg, nchg);
         }
-    }
-    __syncthreads();
-    GZB_KT_MAX(g, 11);
-    for (long long k = warp; k < nb; k += TAIL_WARPS) {
-        if (valid[k] != 2) continue;
-        replay<true>(g, p, ws[warp], lane, nt, yt, xt, G, dG, k, breaks[k], __ldcg(stop + k), stop, first, wlog, NP, steps, chg, nchg);
+        __syncthreads();
     }
     if (threadIdx.x == 0) {      // (breaks, replay steps, ...) of this call, for gzb_get_stats
         stats_out[0] = scal[0];
@@ -1553,6 +1576,14 @@ k_corner(const GzbGrid g, const int r, double* __restrict__ out) {
     }
 }
 
+void gzb_carveout_nearest(int pct) {
+    const int v = pct < 0 ? (int)cudaSharedmemCarveoutDefault : pct;
+    cudaFuncSetAttribute(k_near_search, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(k_near_slow, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(k_chain, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(k_tail, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+}
+
 // ------------------------------------------------------------------------------------------
 size_t gzb_nearest_ws_bytes(int64_t nt) {
     const size_t n = (size_t)(nt > 0 ? nt : 1);
@@ -1597,6 +1628,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
                     const long long** chg_out, const unsigned long long** nchg_out, GzbGlobalNearest* gn_out) {
     if (nt <= 0) return GZB_OK;
     if (np_box_r < 0) return gzb_fail(ctx, GZB_ERR_ARG, "gzb_nearest: np_box_r must be >= 0");
+    gzb_apply_carveout(ctx);
     const size_t n = (size_t)nt;
     const long long nblk = (long long)((n + CH_PTS - 1) / CH_PTS);
     long long* G = (long long*)gzb_arena_take(ctx, n * 8);
@@ -1696,6 +1728,15 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
             sb = ctx->aux_stream;
             GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[0], s));
             GZB_CUDA(ctx, cudaStreamWaitEvent(sb, ctx->ev_k1[0], 0));
+            // The bulk kernel the caller launches next on `s` and the warp search below become eligible at the same moment,
+            // when the search kernel ends; whichever the GPU starts first fills it, and when that is the bulk kernel (same
+            // stream as the search: no cross-stream hop) the chain part starts ~25 us late (in-kernel time marks, KTIME
+            // build).  So `s` is made to wait for an event that the auxiliary stream records once it has passed ITS wait:
+            // the bulk kernel then needs two hops, the warp search one.
+            if (ctx->chain_first) {
+                GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[2], sb));
+                GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[2], 0));
+            }
         }
         gzb_trace(ctx, s, "search end (main)");
         k_near_slow<<<(unsigned)(nsm * 32 / SLOW_WARPS), 32 * SLOW_WARPS, 0, sb>>>(ctx->g, yt, xt, G, dG, ulist, hint,
@@ -1724,7 +1765,7 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
     // enough warps for the usual few hundred breaks (the replay loop strides over the rest): every block of the grid,
     // empty or not, has to pass the "who is last" counter
     long long wblocks = (long long)((n + TAIL_WARPS - 1) / TAIL_WARPS);
-    const long long wmax = (long long)nsm * 4;
+    const long long wmax = (long long)nsm * 2;
     if (wblocks > wmax) wblocks = wmax;
     launch_dep(pdl, k_tail, (unsigned)wblocks, TAIL_THREADS, sb, ctx->g, p, (long long)nt, yt, xt, (const long long*)G,
                (const double*)dG, (const long long*)breaks, scal, stop, first, valid, wlog, (long long*)np_out, chg, nchg,

@@ -217,7 +217,7 @@ class EmuLib:
         ctx = self._c(h)
         name = name.decode() if isinstance(name, bytes) else name
         known = ("zero_copy", "nearest_path", "heading_table", "overlap", "twin_chain", "fuse_k4", "k4_early", "mask_bits",
-                 "prefetch", "pdl", "l2_fetch", "trace", "edge_exclusion", "force_heavy", "bulk_chunks", "ix64")
+                 "prefetch", "pdl", "l2_fetch", "trace", "edge_exclusion", "force_heavy", "bulk_chunks", "ix64", "chain_first", "bulk_resident", "carveout", "push_blocks", "push_mode")
         if name not in known:
             return self._fail(ctx, L.GZB_ERR_ARG, "gzb_set_option: unknown option " + name)
         ctx.opt[name] = int(value)
