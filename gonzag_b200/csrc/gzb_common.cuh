@@ -115,7 +115,7 @@ struct gzb_ctx {
     cudaEvent_t ev_peer[GZB_MAX_PEERS] = {};
     int peer_streams_used = 0;             // how many of them carry copies of the last bulk call
     int push_pending = 0;                  // pushes of the last bulk call are in flight on push_stream (ev_push[8] marks their end)
-    int bulk_chunks = 0;                   // option "bulk_chunks": 0 = automatic (1 alone, 4 with peer outputs), else 1..8
+    int bulk_chunks = 0;                   // option "bulk_chunks": 0 = automatic (one chunk: measured best at 2 and at 8 GPUs), else 1..8
     cudaEvent_t ev_k1[3] = {nullptr, nullptr, nullptr};   // 0: search kernel done; 1: chain part done; 2: the auxiliary stream has passed its wait on 0
     int carveout = -1;                     // option "carveout": preferred shared-memory carve-out (percent of the SM's maximum) of the kernels of a step, -1 = the driver's choice per kernel (see gzb_apply_carveout)
     int chain_first = 0;                   // option "chain_first": the bulk kernel is released through the auxiliary stream (see gzb_nearest_dev)

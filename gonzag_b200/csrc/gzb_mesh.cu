@@ -574,9 +574,12 @@ int gzb_mesh_weights_interp_dev(gzb_ctx* ctx, int64_t nt, const double* yt, cons
     InterpArgs ia;
     fill_interp_args(ctx, ia, tt, nrec, tmod, slab_dev, dtype, k0, nk, rmiss, vnp_out, vbl_out);
     const GzbPeerOut peers = ia.peers;
-    // with peer outputs the bulk kernel writes locally only and runs in chunks; k_push copies each finished chunk
-    // (measured at 2 GPUs: every extra chunk costs ~3 us of launch gap and tail; worth it once several peers' copies queue up)
-    int nchunk = ctx->bulk_chunks > 0 ? ctx->bulk_chunks : (peers.n >= 3 ? 4 : 1);
+    // with peer outputs the bulk kernel writes locally only; k_push copies the finished series into the peers' buffers on
+    // its own stream.  Option "bulk_chunks" > 1 cuts the kernel into chunks so that the copies of chunk c travel while chunk
+    // c+1 is computed -- measured at 8 GPUs (gpurun_out/abm_n8_r2t.err) that overlap is a loss: the peers' stores arriving
+    // in this GPU's memory (71 MB per step, ~480 GB/s of ingress) slow the latency-bound bulk kernel down by a factor 2
+    // (its end moves from 169 to 308 us), so the default is ONE chunk: 0.361 -> 0.338 ms per step.
+    int nchunk = ctx->bulk_chunks > 0 ? ctx->bulk_chunks : 1;
     if (nt < 4096 * nchunk) nchunk = 1;
     const bool push = peers.n > 0;
     if (push) ia.peers.n = 0;
