@@ -18,15 +18,19 @@ of the workload:  K1 nearest points + K2 source mesh + K3 weights + K4 time/spac
             registers), launched alone through gzb_mesh_weights_interp: fused algorithmic bytes
             (260 + 8 s B/point) / CUDA-event time; `gather_kernel` = the same for K4 alone; under
             "kernels", every stage.
-  cpu_baseline  the CPU oracle (NumPy port of the reference) on a bounded prefix of the same
-            workload, 1 core.
+  cpu_baseline  the reference's own code (gonzag.BilinTrack + gonzag.Model2SatTrack, unmodified, from oracle/_ref -- a
+            verbatim copy made by oracle/make_ref.py in the build container; the oracle port when that copy is absent) on a
+            bounded prefix of the same workload, 1 core.
 
-`--impl reference` times the reference's CPU algorithm (the oracle port: the reference is pure
-Python and is not present on the GPU box) on all host cores, bounded sample per step.
-Multi-GPU: launched by torchrun, one rank per GPU; the track is time-sharded (weak scaling:
-each rank maps its own 10-day segment of one long track), grid replicated; the gather of the
-products is fused into K4 (stores into every rank's buffer over NVLink, --gather p2p, default)
-or done by one NCCL all-gather at the end of the step (--gather nccl).
+`--impl reference` times the same reference code on all host cores (one worker per core, each mapping and interpolating
+its own contiguous track segment), bounded sample per step, -D angle on.
+Multi-GPU: launched by torchrun, one rank per GPU; the track is time-sharded (weak scaling: each rank maps its own
+10-day segment of one long track), grid replicated; the gather of the two series goes over NVLink into every rank's
+buffer (CUDA IPC peer memory, a copy kernel on its own stream behind the bulk kernel: --gather p2p, default; p2p-root:
+into rank 0's buffer only) or through one NCCL all-gather at the end of the step (--gather nccl); the sharded result
+is compared bit for bit with one GPU mapping the whole track, outside the timed region (`verified`).
+Workloads C4 (ORCA36-class grid, 30 days) and C5 (6 missions x 1 year) are strong-scaling runs (--workload).
+GZB_AB="opt=v;..." repeats the timed loop under other settings of the library's options (experiments, stderr only).
 """
 from __future__ import annotations
 

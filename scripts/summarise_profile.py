@@ -61,7 +61,7 @@ ids = list(rec)
 starts = [k for k in ids if rec[k]["name"] == "k_near_search"]
 steps = [[k for k in ids if a_ <= k < b_] for a_, b_ in zip(starts[:-1], starts[1:])]
 step = [st for st in steps if any(rec[k]["name"].startswith("k_mesh_weights_interp") for k in st)][-1]     # a whole K1-K4 step
-step = step[:[rec[k]["name"] for k in step].index("k_path_fix") + 1]
+step = step[:[rec[k]["name"].startswith("k_path_fix") for k in step].index(True) + 1]
 tot = sum(rec[k]["gpu__time_duration.sum"] for k in step)
 txt = ["# one step of bench.py (C3) under `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
        "--clock-control none`: serialised, cold caches", "# kernel, duration us, share of the step, dram read MB, dram write MB"]
@@ -89,10 +89,17 @@ per = {k: sum(v) / len(v) for k, v in traffic.items()}
 for k in step:      # kernels the full capture did not include: take the launch list's counters
     e = rec[k]
     per.setdefault(e["name"], e.get("dram__bytes_read.sum", 0.0) + e.get("dram__bytes_write.sum", 0.0))
-stage = {"K1_nearest": sum(per.get(k, 0.0) for k in K1), "K2K3_mesh_weights": per.get("k_mesh_weights", 0.0),
+def pick_exact(base):      # "k_mesh_weights" or "k_mesh_weights<int>", not "k_mesh_weights_interp<...>"
+    for k, v in per.items():
+        if k == base or k.startswith(base + "<"):
+            return v
+    return 0.0
+
+
+stage = {"K1_nearest": sum(per.get(k, 0.0) for k in K1), "K2K3_mesh_weights": pick_exact("k_mesh_weights"),
          "K4_interp_gather": pick("k_interp<float")}
 stage["K2K3K4_bulk"] = pick("k_mesh_weights_interp<float")
-stage["K1-K4_path"] = stage["K1_nearest"] + stage["K2K3K4_bulk"] + per.get("k_path_fix", 0.0)
+stage["K1-K4_path"] = stage["K1_nearest"] + stage["K2K3K4_bulk"] + pick("k_path_fix")
 stage["K1K2K3_mapping"] = stage["K1_nearest"] + stage["K2K3_mesh_weights"]
 json.dump({"source": os.path.basename(raw), "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
            "kernels": per, **stage}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
