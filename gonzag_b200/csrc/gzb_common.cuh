@@ -118,7 +118,7 @@ struct gzb_ctx {
     int bulk_chunks = 0;                   // option "bulk_chunks": 0 = automatic (one chunk: measured best at 2 and at 8 GPUs), else 1..8
     cudaEvent_t ev_k1[3] = {nullptr, nullptr, nullptr};   // 0: search kernel done; 1: chain part done; 2: the auxiliary stream has passed its wait on 0
     int carveout = -1;                     // option "carveout": preferred shared-memory carve-out (percent of the SM's maximum) of the kernels of a step, -1 = the driver's choice per kernel (see gzb_apply_carveout)
-    int chain_first = 0;                   // option "chain_first": the bulk kernel is released through the auxiliary stream (see gzb_nearest_dev)
+    int chain_first = 6;                   // option "chain_first": n >= 2 = the bulk kernel is released n microseconds after the search kernel ends, behind the warp search (step 212 -> 200 us); 1 = released through the auxiliary stream (no effect); 0 = at once
     int bulk_resident = 0;                 // option "bulk_resident": n > 0 = the fused bulk kernel runs as n persistent blocks per SM (grid-stride), leaving the rest of every SM to the chain kernels; 0 = one block per 128 points
     GzbPeerOut peer_out = {0, {}, {}};   // gzb_set_peer_outputs: where K4 also writes its two series
     double* peer_local_np = nullptr;     // ... when its local outputs are these buffers

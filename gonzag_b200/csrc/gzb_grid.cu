@@ -1237,7 +1237,7 @@ extern "C" int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "push_blocks")) { ctx->push_blocks = value < 1 ? 1 : (value > 4096 ? 4096 : (int)value); return GZB_OK; }
     if (!strcmp(name, "push_mode")) { ctx->push_mode = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "carveout")) { ctx->carveout = value < 0 ? -1 : (value > 100 ? 100 : (int)value); return GZB_OK; }
-    if (!strcmp(name, "chain_first")) { ctx->chain_first = value ? 1 : 0; return GZB_OK; }
+    if (!strcmp(name, "chain_first")) { ctx->chain_first = value < 0 ? 0 : (value > 50 ? 50 : (int)value); return GZB_OK; }
     if (!strcmp(name, "bulk_resident")) { ctx->bulk_resident = value < 0 ? 0 : (value > 16 ? 16 : (int)value); return GZB_OK; }
     if (!strcmp(name, "ix64")) { ctx->force_ix64 = value ? 1 : 0; return GZB_OK; }
     if (!strcmp(name, "prefetch")) { ctx->prefetch = value < 0 ? 0 : (value > 4 ? 4 : (int)value); return GZB_OK; }

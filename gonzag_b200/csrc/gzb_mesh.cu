@@ -469,11 +469,13 @@ __device__ __forceinline__ void prefetch_hood(const GzbGrid& g, const long long 
     gzb_l2_prefetch(X1 + jb * g.Ni + iP); gzb_l2_prefetch(X1 + cells + jb * g.Ni + iP);
 }
 
-// Resident blocks of 128 threads per SM (8 = a cap of 64 registers; uncapped the kernel takes 91).  Measured on the C3 track,
-// 32-bit indices (gpurun_out/ab_exp*_r2n.log): 5 blocks 90.1 us, 6 blocks 84.1, 7 blocks 82.0, 8 blocks 80.6 -- the kernel is
-// bound by the latency of its dependent gathers, so warps in flight beat the spills they cost (64-bit indices: 7 blocks 86.8)
+// Resident blocks of 128 threads per SM (7 = a cap of 72 registers; uncapped the kernel takes 91).  Measured on the C3 track,
+// 32-bit indices: 5 blocks 90.1 us, 6 blocks 84.1, 7 blocks 82.0, 8 blocks 80.6 before the grid-stride form of the loop
+// (gpurun_out/ab_exp*_r2n.log), 86.3 / 81.4 / 76.0 / 76.0 with it (ab_exp*_r2w.log) -- the kernel is bound by the latency of
+// its dependent gathers, so warps in flight beat the spills they cost.  7, not 8: alone the two are equal, inside a step
+// 7 is 1-2 % faster (197 vs 199.6 us; 6 blocks: 195 us, but the kernel alone then takes 81 us).
 #ifndef GZB_EXP_BULK_BLOCKS
-#define GZB_EXP_BULK_BLOCKS 8
+#define GZB_EXP_BULK_BLOCKS 7
 #endif
 template <typename T, int PF, typename IX>      // PF: 0 plain, 1 L2 prefetch of the gather, 3 gather with 64-byte L2 fetches, 4 early prefetch
 __global__ void __launch_bounds__(128, GZB_EXP_BULK_BLOCKS)
@@ -659,7 +661,7 @@ int gzb_path_fix_dev(gzb_ctx* ctx, const double* yt, const double* xt, const int
     if (joined) {
         if (gzb_push_join(ctx) != GZB_OK) return GZB_ERR_CUDA;
         gzb_trace(ctx, ctx->stream, "repair kernel end, pushes joined (main)");
-        k_push_list<<<32, 128, 0, ctx->stream>>>(vnp_out, vbl_out, peers, list, count, list2, count2);
+        k_push_list<<<148, 128, 0, ctx->stream>>>(vnp_out, vbl_out, peers, list, count, list2, count2);      // ~10 k points: one pass
         GZB_LAUNCH_CHECK(ctx);
     }
     if (slab_dev) ctx->time_err_pending = 1;

@@ -998,7 +998,10 @@ __device__ __forceinline__ unsigned block_scan_fn(const unsigned mine, unsigned*
 #define CH_PPT 4
 #define CH_PTS (FLAGS_BLOCK * CH_PPT)
 #define CH_LB 4        /* blocks per thread in the last block's ordered copy */
-__global__ void __launch_bounds__(FLAGS_BLOCK)
+#ifndef GZB_CHAIN_MINBLOCKS
+#define GZB_CHAIN_MINBLOCKS 4      /* resident blocks of k_chain per SM the compiler must allow: 4 = a cap of 64 registers (natural: 74, 3 blocks); measured with the bulk kernel at 7 blocks: step 199.6 -> 197.0 us, K1 alone 142 -> 140 (gpurun_out/ab_exp*_r2w.log) */
+#endif
+__global__ void __launch_bounds__(FLAGS_BLOCK, GZB_CHAIN_MINBLOCKS)
 k_chain(const GzbGrid g, const NearParams p, const long long nt, const double* __restrict__ yt,
         const double* __restrict__ xt, const long long* __restrict__ G, const double* __restrict__ dG,
         long long* __restrict__ NP, long long* __restrict__ breaks, long long* __restrict__ blist, int* __restrict__ bcount,
@@ -1576,6 +1579,16 @@ k_corner(const GzbGrid g, const int r, double* __restrict__ out) {
     }
 }
 
+// one thread that lets `ns` nanoseconds pass (see chain_first in gzb_nearest_dev)
+__global__ void k_delay(const unsigned ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < (unsigned long long)ns);
+}
+
 void gzb_carveout_nearest(int pct) {
     const int v = pct < 0 ? (int)cudaSharedmemCarveoutDefault : pct;
     cudaFuncSetAttribute(k_near_search, cudaFuncAttributePreferredSharedMemoryCarveout, v);
@@ -1733,8 +1746,17 @@ int gzb_nearest_dev(gzb_ctx* ctx, int64_t nt, const double* yt, const double* xt
             // stream as the search: no cross-stream hop) the chain part starts ~25 us late (in-kernel time marks, KTIME
             // build).  So `s` is made to wait for an event that the auxiliary stream records once it has passed ITS wait:
             // the bulk kernel then needs two hops, the warp search one.
-            if (ctx->chain_first) {
+            if (ctx->chain_first == 1) {
                 GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[2], sb));
+                GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[2], 0));
+            } else if (ctx->chain_first >= 2 && nt >= 100000) {
+                // ... which still leaves the two launches racing (measured).  chain_first = n >= 2: a one-thread kernel on a
+                // third stream sleeps n microseconds after the search kernel's end before `s` is released: the warp search's
+                // blocks are resident by then and the bulk kernel fills the SMs as they retire.
+                GZB_CUDA(ctx, cudaStreamWaitEvent(ctx->push_stream, ctx->ev_k1[0], 0));
+                k_delay<<<1, 1, 0, ctx->push_stream>>>((unsigned)ctx->chain_first * 1000u);
+                GZB_LAUNCH_CHECK(ctx);
+                GZB_CUDA(ctx, cudaEventRecord(ctx->ev_k1[2], ctx->push_stream));
                 GZB_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_k1[2], 0));
             }
         }

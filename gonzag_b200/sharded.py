@@ -181,14 +181,20 @@ class ShardedModel2SatTrack(_LazyXNPMixin):
         self.reseeds = 0
         try:
             # the predecessor's last point, unseeded: its value on the speculative chain (E(t) of DESIGN.md K1)
+            tim["job_alloc_h2d_s"] = time.perf_counter() - tc
+            tq = time.perf_counter()
             if prev_point is not None:
                 halo = ctx.nearest(yt[s0 - 1:s0], xt[s0 - 1:s0], d_found_km, r, seed=(0, 0))[0]
                 seed = (int(halo[0]), int(halo[1]))
             else:
                 seed = (r, r)                                                      # bilin_mapping.py:570
+            tim["halo_s"] = time.perf_counter() - tq
+            tq = time.perf_counter()
             kw = dict(slab_bytes=slab_bytes, resident_bytes=resident_bytes)
             if n > 0:
                 job.run(MG, name_ssh_mod, d_found_km, r, seed, **kw)
+            tim["run_issue_s"] = time.perf_counter() - tq
+            tq = time.perf_counter()
             edges = torch.zeros((world, 4), dtype=torch.int64, device=tdev)
             mine = torch.zeros(4, dtype=torch.int64, device=tdev)
             last = np.zeros(2, dtype=np.int64)
@@ -227,6 +233,8 @@ class ShardedModel2SatTrack(_LazyXNPMixin):
                         job.run(MG, name_ssh_mod, d_found_km, r, seed, **kw)
             else:
                 raise RuntimeError("segment boundaries did not settle in %d rounds" % world)
+            tim["run_wait_and_edges_s"] = time.perf_counter() - tq
+            tq = time.perf_counter()
 
             # ---- a14 on the segment, then the gather
             ssh_attr = getattr(ST, "ssh", None)
@@ -240,6 +248,7 @@ class ShardedModel2SatTrack(_LazyXNPMixin):
                     raise ValueError("the satellite series has %s values, the track %d points" % (vssh_s.shape, Nt))
                 my_sat = np.ascontiguousarray(vssh_s[s0:s1])
             job.distance_and_mask(my_sat)
+            tim["sat_distmask_s"] = time.perf_counter() - tq
             tim["segment_issue_s"] = time.perf_counter() - tc
             tc = time.perf_counter()
             off = job.off

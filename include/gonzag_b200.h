@@ -120,12 +120,14 @@ int gzb_set_ew_per(gzb_ctx* ctx, int k_ew_per);
  * "ix64": 0 (default) K2-K4 use 32-bit row / column / cell indices on every grid of fewer than 2^31 cells (the int64
  * arrays of the reference are widened at the stores, narrowed at the loads: fused kernel 93 -> 82 us on ORCA12);
  * 1 = the 64-bit variants whatever the grid size.  Same results.
- * Scheduling experiments, all measured on the C3 track and OFF by default (same results in every setting):
+ * Scheduling options, all measured on the C3 track (same results in every setting; off by default unless stated):
  * "bulk_chunks": n > 1 cuts the fused bulk kernel of a sharded step into n chunks so that the peers' copies of chunk c
  *   travel while chunk c+1 is computed (0 / 1 = one chunk: at 8 GPUs the arriving stores slow the bulk kernel by 2x);
  * "bulk_resident": n > 0 runs the fused bulk kernel as n persistent blocks per SM (the block scheduler fills SMs one
  *   after the other, so this does NOT leave room on every SM: slower);
- * "chain_first": 1 releases the bulk kernel through the auxiliary stream (no effect on who starts first);
+ * "chain_first": n >= 2 (default 6, tracks of 100 000 points or more) releases the bulk kernel n microseconds after the search
+ *   kernel ends, so that the warp search of K1's chain part is resident first (step 212 -> 200 us; 4 to 24 us measured
+ *   alike); 1 = through the auxiliary stream only (the two launches still race); 0 = at once;
  * "carveout": preferred shared-memory carve-out (percent) of all kernels of a step, -1 = the driver's choice (no effect);
  * "push_blocks" (64) grid of the peer-copy kernel, "push_mode" 1 = peer copies on the copy engines (2x slower). */
 int gzb_set_option(gzb_ctx* ctx, const char* name, int64_t value);
