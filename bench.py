@@ -875,7 +875,7 @@ def run_ours(args, w):
     if rank == 0:
         sharding = ("contiguous time segments, grid replicated; " + (
             "the two series go into " + ("rank 0's buffer" if args.gather == "p2p-root" else "every rank's buffer") +
-            " over NVLink (CUDA IPC peer memory), copied chunk by chunk behind the bulk kernel by a push kernel on its own stream; "
+            " over NVLink (CUDA IPC peer memory), copied behind the bulk kernel by a push kernel on its own stream (one chunk: overlapping the copies with the bulk kernel was measured slower at 8 GPUs); "
             "the step ends with " + ("ONE own kernel over peer memory (edge words + barrier + boundary check)" if args.barrier == "p2p"
                                      else "an edge publication kernel, a one-word NCCL all-reduce and a check kernel")
             if isinstance(mapper, P2PShardedMapper) else "1 all-gather of (ssh_np, ssh_bl, NP)") +

@@ -740,7 +740,10 @@ k_near_search(const GzbGrid g, const long long nt, const double* __restrict__ yt
 // A warp takes K list entries at a time (K chosen so that every warp of the grid has work).
 // small blocks (SLOW_WARPS warps): they must find room on SMs that the bulk kernels of gzb_mapping fill
 #define SLOW_WARPS 2
-__global__ void __launch_bounds__(32 * SLOW_WARPS)
+#ifndef GZB_SLOW_MINBLOCKS
+#define GZB_SLOW_MINBLOCKS 10     /* resident blocks of 64 threads per SM the compiler must allow (10 = a cap of 102 registers) */
+#endif
+__global__ void __launch_bounds__(32 * SLOW_WARPS, GZB_SLOW_MINBLOCKS)
 k_near_slow(const GzbGrid g, const double* __restrict__ yt, const double* __restrict__ xt,
             long long* __restrict__ G, double* __restrict__ dG, const long long* __restrict__ ulist,
             const unsigned* __restrict__ hint, const unsigned long long* __restrict__ ucount) {
