@@ -160,6 +160,13 @@ def test_c3_chain_links_and_oracle_prefix(c3):
     a = g["ctx"].nearest(g["y"][:cut], g["x"][:cut], g["rd"], g["r"])
     b = g["ctx"].nearest(g["y"][cut:], g["x"][cut:], g["rd"], g["r"], seed=tuple(int(v) for v in a[-1]))
     np.testing.assert_array_equal(np.concatenate([a, b]), NP)
+    # the scheduling of the overlapped path (bulk kernel released at once / behind the warp search, persistent bulk blocks)
+    # changes nothing in the results; the default (chain_first = 6) only applies to tracks this long
+    for opts in ({"chain_first": 0}, {"chain_first": 12, "bulk_resident": 3}, {"chain_first": 6, "bulk_resident": 0}):
+        for k_, v_ in opts.items():
+            g["ctx"].set_option(k_, v_)
+        NP2, SM2, WB2 = g["ctx"].mapping(g["y"], g["x"], g["rd"], g["r"])
+        assert np.array_equal(NP2, NP) and np.array_equal(SM2, SM) and np.array_equal(WB2.view(np.int64), WB.view(np.int64)), opts
     # per-point stages against the oracle on a random subset (includes cells with |angle| > 45)
     rng = np.random.default_rng(0)
     idx = np.sort(rng.choice(len(g["y"]), 3000, replace=False))

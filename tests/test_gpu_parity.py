@@ -426,7 +426,8 @@ def test_launch_and_memory_options_do_not_change_results(golden_global):
     """Options that only change HOW the kernels are launched or fed -- "pdl" (programmatic dependent
     launches of K1's chain kernels), "prefetch" (L2 prefetch of the gather in the fused kernel and in
     K4; 3 = 64-byte L2 fetches instead), "l2_fetch" (device-wide fetch-granularity hint), "ix64" (64-bit instead of 32-bit
-    index arithmetic in K2-K4) -- must leave every output bit-identical."""
+    index arithmetic in K2-K4), the scheduling options ("chain_first", "bulk_resident", "carveout", "push_blocks", "push_mode") -- must
+    leave every output bit-identical."""
     import ctypes as C
     from gonzag_b200 import _lib as L
     g = golden_global
@@ -443,7 +444,9 @@ def test_launch_and_memory_options_do_not_change_results(golden_global):
         for opts in ({"pdl": 1, "prefetch": 0}, {"pdl": 0}, {"pdl": 1, "prefetch": 1}, {"prefetch": 2}, {"prefetch": 3}, {"prefetch": 4},
                      {"bulk_chunks": 3, "prefetch": 3}, {"bulk_chunks": 0},
                      {"prefetch": 0, "l2_fetch": 32}, {"l2_fetch": 128}, {"l2_fetch": 64},
-                     {"ix64": 1, "prefetch": 3}, {"ix64": 1, "prefetch": 0}, {"ix64": 0, "prefetch": 3}):
+                     {"ix64": 1, "prefetch": 3}, {"ix64": 1, "prefetch": 0}, {"ix64": 0, "prefetch": 3},
+                     {"chain_first": 0}, {"chain_first": 1}, {"chain_first": 6, "bulk_resident": 2}, {"bulk_resident": 0, "carveout": 28},
+                     {"carveout": -1, "push_blocks": 296, "push_mode": 1}, {"push_blocks": 64, "push_mode": 0}):
             for k, v in opts.items():
                 ctx.set_option(k, v)
             # fused path on a device-resident slab (k_mesh_weights_interp: the prefetch variant applies)
