@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <new>
@@ -142,6 +143,24 @@ template <typename T> static void pack_into(int8_t* out, const char* src, size_t
     for (size_t k = 0; k < n; ++k) out[k] = (int8_t)p[k];
 }
 
+// Narrowing upload (pack == GZB_BC_NARROW, uploads only): `src` holds float64 values, `bytes` counts SOURCE bytes, and what
+// travels is float32 -- as long as every value survives the round trip double -> float -> double unchanged (model grids are
+// commonly written by NEMO in single precision and widened by the reader: half the bytes over PCIe, bit-identical values
+// after the widening kernel).  The first value that does not (or a NaN) raises g_bc_inexact and the caller repeats the
+// transfer in full precision.
+#define GZB_BC_NARROW 108
+std::atomic<int> g_bc_inexact{0};
+
+static bool narrow_into(float* out, const double* p, size_t n) {
+    bool ok = true;
+    for (size_t k = 0; k < n; ++k) {
+        const float f = (float)p[k];
+        ok &= ((double)f == p[k]);
+        out[k] = f;
+    }
+    return ok;
+}
+
 // one transfer of a threaded copy: `bytes` from src to dst; pack > 1: see pack_into (then `bytes` counts int8 elements)
 struct BcJob {
     char* dst;
@@ -166,17 +185,22 @@ void bigcopy_part(int dev, int t, int nth, const BcJob* jobs, int njobs, bool h2
         const size_t a = (size_t)t * part;
         if (a >= J.bytes) continue;
         const size_t bytes = J.bytes - a < part ? J.bytes - a : part;
-        char* dst = J.dst + a;
-        const char* src = J.pack > 1 ? J.src : J.src + a;      // packed sources are addressed by element (first_elem below)
+        const bool narrow = h2d && J.pack == GZB_BC_NARROW;
+        char* dst = narrow ? J.dst + a / 2 : J.dst + a;
+        const char* src = (J.pack > 1 && !narrow) ? J.src : J.src + a;      // packed sources are addressed by element (first_elem below)
         size_t off = 0;
         while (off < bytes && e == cudaSuccess) {
+            if (narrow && g_bc_inexact.load(std::memory_order_relaxed)) break;      // somebody found an inexact value: the transfer will be redone
             const size_t len = bytes - off < GZB_BC_SLOT ? bytes - off : GZB_BC_SLOT;
             if (used[k]) {                           // the slot's previous transfer must be over
                 e = cudaEventSynchronize(g_bc.ev[t][k]);
                 if (!h2d && e == cudaSuccess) memcpy(pend_dst[k], g_bc.slot[t][k], pend_len[k]);
             }
             if (e != cudaSuccess) break;
-            if (h2d) {
+            if (narrow) {
+                if (!narrow_into((float*)g_bc.slot[t][k], (const double*)(src + off), len / 8)) g_bc_inexact.store(1);
+                e = cudaMemcpyAsync(dst + off / 2, g_bc.slot[t][k], len / 2, cudaMemcpyHostToDevice, g_bc.stream[t]);
+            } else if (h2d) {
                 if (J.pack == 8) pack_into<int64_t>((int8_t*)g_bc.slot[t][k], src, a + off, len);
                 else if (J.pack == 4) pack_into<int32_t>((int8_t*)g_bc.slot[t][k], src, a + off, len);
                 else if (J.pack == 2) pack_into<int16_t>((int8_t*)g_bc.slot[t][k], src, a + off, len);
@@ -241,7 +265,9 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
         const BcJob& J = jobs_in[q];
         if (J.bytes == 0) continue;
         const void* host = h2d ? (const void*)J.src : (const void*)J.dst;
-        if (bigcopy_plain(host, J.bytes, J.pack)) {
+        if (J.pack == GZB_BC_NARROW && (!h2d || bigcopy_plain(host, J.bytes, 0))) {
+            g_bc_inexact.store(1);      // not a threaded pageable upload: the caller takes the full-precision path
+        } else if (bigcopy_plain(host, J.bytes, J.pack)) {
             const int rc = bigcopy_one_plain(ctx, J.dst, J.src, J.bytes, J.pack);
             if (rc != GZB_OK) return rc;
         } else {
@@ -253,6 +279,7 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
     if (!bigcopy_ready(ctx->device)) {
         lk.unlock();
         for (int q = 0; q < njobs; ++q) {
+            if (jobs[q].pack == GZB_BC_NARROW) { g_bc_inexact.store(1); continue; }
             const int rc = bigcopy_one_plain(ctx, jobs[q].dst, jobs[q].src, jobs[q].bytes, jobs[q].pack);
             if (rc != GZB_OK) return rc;
         }
@@ -568,6 +595,16 @@ k_build_level(GzbGrid g, int l, int is_top) {
             idx = ((int64_t)pJ * P.nI + pI) * 32 + (J % P.bj) * P.bi + (I % P.bi);
         }
         L.nodes[idx] = pack_sphere(cx, cy, cz, r);
+    }
+}
+
+// float32 -> float64 of the narrowed uploads (exact by construction: the host checked every value)
+__global__ void __launch_bounds__(256)
+k_widen2(const int64_t n, const float* __restrict__ a32, const float* __restrict__ b32, double* __restrict__ a, double* __restrict__ b) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) {
+        a[k] = (double)a32[k];
+        b[k] = (double)b32[k];
     }
 }
 
@@ -993,15 +1030,34 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
         };
         CK(gzb_pool_malloc((void**)&ctx->d_lat, n * sizeof(double)));
         CK(gzb_pool_malloc((void**)&ctx->d_lon, n * sizeof(double)));
-        {
-            const BcJob up[2] = {{(char*)ctx->d_lat, (const char*)lat, n * sizeof(double), 0}, {(char*)ctx->d_lon, (const char*)lon, n * sizeof(double), 0}};
-            if ((rc = gzb_bigcopy_jobs(ctx, up, 2, true, true)) != GZB_OK) break;
-        }
-        cmark("lat, lon uploaded");
         CK(gzb_pool_malloc((void**)&ctx->d_ll, n * sizeof(double2)));
+        {
+            // first as float32 (half the bytes; exact for grids that were written in single precision), staged in the
+            // memory of `ll` and widened on the device; in full precision when a value does not survive the narrowing
+            bool narrowed = false;
+            if (n * sizeof(double) >= GZB_BC_MIN && !getenv("GZB_NO_NARROW_UPLOAD")) {
+                float* st = (float*)ctx->d_ll;
+                const BcJob up32[2] = {{(char*)st, (const char*)lat, n * sizeof(double), GZB_BC_NARROW},
+                                       {(char*)(st + n), (const char*)lon, n * sizeof(double), GZB_BC_NARROW}};
+                g_bc_inexact.store(0);
+                if ((rc = gzb_bigcopy_jobs(ctx, up32, 2, true, true)) != GZB_OK) break;
+                if (!g_bc_inexact.load()) {
+                    k_widen2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, st, st + n, ctx->d_lat, ctx->d_lon);
+                    ctx->stats.kernel_launches++;
+                    ctx->stats.h2d_bytes += 2 * n * sizeof(float);
+                    narrowed = true;
+                    cmark("lat, lon uploaded as float32 (exact)");
+                }
+            }
+            if (!narrowed) {
+                const BcJob up[2] = {{(char*)ctx->d_lat, (const char*)lat, n * sizeof(double), 0}, {(char*)ctx->d_lon, (const char*)lon, n * sizeof(double), 0}};
+                if ((rc = gzb_bigcopy_jobs(ctx, up, 2, true, true)) != GZB_OK) break;
+                ctx->stats.h2d_bytes += 2 * n * sizeof(double);
+                cmark("lat, lon uploaded");
+            }
+        }
         k_interleave<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, ctx->d_lat, ctx->d_lon, ctx->d_ll);
         ctx->stats.kernel_launches++;
-        ctx->stats.h2d_bytes += 2 * n * sizeof(double);
         if (angle_or_null) CK(gzb_pool_malloc((void**)&ctx->d_angle, n * sizeof(double)));
         if (mask_or_null) CK(gzb_pool_malloc((void**)&ctx->d_mask, n));
         CK(gzb_pool_malloc((void**)&ctx->d_flags, 256));

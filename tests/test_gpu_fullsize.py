@@ -10,6 +10,8 @@ every point would take hours.  Two kinds of evidence:
   - a constant field interpolates to the constant wherever the reference interpolates at all;
   - K0 against a vectorised torch restatement of GridAngle.
 """
+import types
+
 import numpy as np
 import pytest
 import torch
@@ -144,6 +146,43 @@ def test_c3_grid_angle(c3):
     assert 0.02 < (np.abs(c3["ang"]) > 45.0).mean() < 0.3
     band = orc.grid_angle(c3["lat"][:, 1000:1003], c3["lon"][:, 1000:1003])
     np.testing.assert_allclose(c3["ang"][:, 1000:1003], band, rtol=0, atol=1e-9)
+
+
+def test_c3_narrowed_upload_is_exact(c3, monkeypatch):
+    """A big grid whose float64 coordinates are float32 values (written in single precision by the model, widened by the
+    reader) goes up as float32 and is widened on the device; a grid with a value that does not survive the narrowing goes up
+    in full precision.  Both must give the context the very same float64 arrays as the plain upload: compared through K0
+    (every cell's angle depends on its coordinates and its neighbours') and K1 on a day of track."""
+    import os
+    g = c3
+    n = 20000
+    want_ang, want_np = g["ang"], g["ctx"].nearest(g["y"][:n], g["x"][:n], g["rd"], g["r"])
+    monkeypatch.setenv("GZB_NO_NARROW_UPLOAD", "1")
+    with gzb.GridContext(g["lat"], g["lon"], k_ew_per=2) as c_full:
+        assert c_full.stats()["h2d_bytes"] >= 2 * g["lat"].nbytes
+        assert np.array_equal(c_full.grid_angle().view(np.int64), want_ang.view(np.int64))
+        np.testing.assert_array_equal(c_full.nearest(g["y"][:n], g["x"][:n], g["rd"], g["r"]), want_np)
+    monkeypatch.delenv("GZB_NO_NARROW_UPLOAD")
+    with gzb.GridContext(g["lat"], g["lon"], k_ew_per=2) as c_nar:
+        assert c_nar.stats()["h2d_bytes"] < 1.5 * g["lat"].nbytes          # the fixture's grid is float32-exact: half the bytes
+        assert np.array_equal(c_nar.grid_angle().view(np.int64), want_ang.view(np.int64))
+        for q, src in ((0, g["lat"]), (1, g["lon"])):
+            back = c_nar.download(types.SimpleNamespace(ptr=c_nar.grid_arrays()[q]), src.shape, np.float64)
+            assert np.array_equal(back.view(np.int64), src.view(np.int64))
+    # one value that float32 cannot hold, somewhere in the middle: full precision, and the value arrives intact
+    lat2 = g["lat"].copy()
+    j, i = 1500, 2100
+    lat2[j, i] = lat2[j, i] + 1.0e-11
+    assert float(np.float32(lat2[j, i])) != lat2[j, i]
+    with gzb.GridContext(lat2, g["lon"], k_ew_per=2) as c2:
+        assert c2.stats()["h2d_bytes"] >= 2 * g["lat"].nbytes
+        a2 = c2.grid_angle()
+        back = c2.download(types.SimpleNamespace(ptr=c2.grid_arrays()[0]), lat2.shape, np.float64)
+        assert np.array_equal(back.view(np.int64), lat2.view(np.int64))
+    monkeypatch.setenv("GZB_NO_NARROW_UPLOAD", "1")
+    with gzb.GridContext(lat2, g["lon"], k_ew_per=2) as c3_:
+        a3 = c3_.grid_angle()
+    assert np.array_equal(a2.view(np.int64), a3.view(np.int64))
 
 
 def test_c3_chain_links_and_oracle_prefix(c3):
