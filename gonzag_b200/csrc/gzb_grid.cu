@@ -167,6 +167,7 @@ struct BcJob {
     const char* src;
     size_t bytes;
     int pack;
+    size_t min_bytes;      // below this the transfer is one plain copy (0 = GZB_BC_MIN)
 };
 
 // Thread t of `nth` moves its slice of every job, one after the other, through its two pinned slots: the slots keep
@@ -230,8 +231,8 @@ void bigcopy_part(int dev, int t, int nth, const BcJob* jobs, int njobs, bool h2
 // Copies `bytes` between pageable host memory and the device and RETURNS WHEN DONE.  Falls back to
 // one cudaMemcpyAsync + stream synchronisation for small or already pinned buffers.
 // A transfer is "plain" (one cudaMemcpyAsync) when it is small or when the host side is not pageable memory.
-static bool bigcopy_plain(const void* host, size_t bytes, int pack) {
-    if (bytes < GZB_BC_MIN && pack <= 1) return true;
+static bool bigcopy_plain(const void* host, size_t bytes, int pack, size_t min_bytes = 0) {
+    if (bytes < (min_bytes ? min_bytes : GZB_BC_MIN) && pack <= 1) return true;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, host) == cudaSuccess) {
         if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return true;
@@ -267,7 +268,7 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
         const void* host = h2d ? (const void*)J.src : (const void*)J.dst;
         if (J.pack == GZB_BC_NARROW && (!h2d || bigcopy_plain(host, J.bytes, 0))) {
             g_bc_inexact.store(1);      // not a threaded pageable upload: the caller takes the full-precision path
-        } else if (bigcopy_plain(host, J.bytes, J.pack)) {
+        } else if (bigcopy_plain(host, J.bytes, J.pack, J.min_bytes)) {
             const int rc = bigcopy_one_plain(ctx, J.dst, J.src, J.bytes, J.pack);
             if (rc != GZB_OK) return rc;
         } else {
@@ -291,6 +292,12 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
     cudaError_t errs[GZB_BC_THREADS];
     int want = gzb_host_threads(GZB_BC_THREADS);
     if (want > 2 && want == (int)std::thread::hardware_concurrency()) --want;      // leave one core to the caller
+    {   // no more threads than slots' worth of data (a 5 MB track array: 5 threads, not 16)
+        size_t total = 0;
+        for (int q = 0; q < njobs; ++q) total += jobs[q].bytes;
+        const size_t by_data = (total + GZB_BC_SLOT - 1) / GZB_BC_SLOT;
+        if ((size_t)want > by_data) want = (int)by_data;
+    }
     want = want < 2 ? 2 : want;
     for (int t = 0; t < want; ++t) {
         errs[t] = cudaSuccess;
@@ -304,9 +311,10 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
 
 // Copies `bytes` between pageable host memory and the device and RETURNS WHEN DONE.  Falls back to
 // one cudaMemcpyAsync + stream synchronisation for small or already pinned buffers.
-int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true, int pack = 0) {
+int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true, int pack = 0,
+                size_t min_bytes = 0) {
     if (bytes == 0) return GZB_OK;
-    const BcJob J = {(char*)dst, (const char*)src, bytes, pack};
+    const BcJob J = {(char*)dst, (const char*)src, bytes, pack, min_bytes};
     return gzb_bigcopy_jobs(ctx, &J, 1, h2d, sync_before);
 }
 
@@ -1037,8 +1045,8 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
             bool narrowed = false;
             if (n * sizeof(double) >= GZB_BC_MIN && !getenv("GZB_NO_NARROW_UPLOAD")) {
                 float* st = (float*)ctx->d_ll;
-                const BcJob up32[2] = {{(char*)st, (const char*)lat, n * sizeof(double), GZB_BC_NARROW},
-                                       {(char*)(st + n), (const char*)lon, n * sizeof(double), GZB_BC_NARROW}};
+                const BcJob up32[2] = {{(char*)st, (const char*)lat, n * sizeof(double), GZB_BC_NARROW, 0},
+                                       {(char*)(st + n), (const char*)lon, n * sizeof(double), GZB_BC_NARROW, 0}};
                 g_bc_inexact.store(0);
                 if ((rc = gzb_bigcopy_jobs(ctx, up32, 2, true, true)) != GZB_OK) break;
                 if (!g_bc_inexact.load()) {
@@ -1050,7 +1058,7 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
                 }
             }
             if (!narrowed) {
-                const BcJob up[2] = {{(char*)ctx->d_lat, (const char*)lat, n * sizeof(double), 0}, {(char*)ctx->d_lon, (const char*)lon, n * sizeof(double), 0}};
+                const BcJob up[2] = {{(char*)ctx->d_lat, (const char*)lat, n * sizeof(double), 0, 0}, {(char*)ctx->d_lon, (const char*)lon, n * sizeof(double), 0, 0}};
                 if ((rc = gzb_bigcopy_jobs(ctx, up, 2, true, true)) != GZB_OK) break;
                 ctx->stats.h2d_bytes += 2 * n * sizeof(double);
                 cmark("lat, lon uploaded");
@@ -1092,11 +1100,11 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
             BcJob up[2];
             int nup = 0;
             if (angle_or_null) {
-                up[nup++] = {(char*)ctx->d_angle, (const char*)angle_or_null, n * sizeof(double), 0};
+                up[nup++] = {(char*)ctx->d_angle, (const char*)angle_or_null, n * sizeof(double), 0, 0};
                 ctx->stats.h2d_bytes += n * sizeof(double);
             }
             if (mask_or_null) {
-                up[nup++] = {(char*)ctx->d_mask, (const char*)mask_or_null, n, mask_itemsize};
+                up[nup++] = {(char*)ctx->d_mask, (const char*)mask_or_null, n, mask_itemsize, 0};
                 ctx->stats.h2d_bytes += n;
             }
             if (nup && (rc = gzb_bigcopy_jobs(ctx, up, nup, true, false)) != GZB_OK) break;
@@ -1783,8 +1791,16 @@ extern "C" int gzb_dev_free(gzb_ctx* ctx, void* dptr) {
 extern "C" int gzb_h2d(gzb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes) {
     if (!ctx) return gzb_fail(nullptr, GZB_ERR_ARG, "gzb_h2d: null ctx");
     if (gzb_use_device(ctx) != GZB_OK) return GZB_ERR_CUDA;
-    if (bytes >= GZB_BC_MIN) {         // large: parallel staging when the host buffer is pageable (returns when done)
-        const int rc = gzb_bigcopy(ctx, dst_dev, src_host, (size_t)bytes, true);
+    // large: parallel staging when the host buffer is pageable (returns when done).  Medium (a track array of a few MB): the
+    // same when the stream is idle -- a plain copy from pageable memory runs at 11 GB/s, and nothing is queued that the
+    // staged copy would have to wait for
+    bool idle = false;
+    if (bytes >= ((size_t)3 << 20) && bytes < GZB_BC_MIN) {
+        idle = cudaStreamQuery(ctx->stream) == cudaSuccess;
+        if (!idle) cudaGetLastError();
+    }
+    if (bytes >= GZB_BC_MIN || idle) {
+        const int rc = gzb_bigcopy(ctx, dst_dev, src_host, (size_t)bytes, true, true, 0, (size_t)3 << 20);
         if (rc != GZB_OK) return rc;
     } else {
         GZB_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
