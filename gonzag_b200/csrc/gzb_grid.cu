@@ -146,10 +146,9 @@ template <typename T> static void pack_into(int8_t* out, const char* src, size_t
 // Narrowing upload (pack == GZB_BC_NARROW, uploads only): `src` holds float64 values, `bytes` counts SOURCE bytes, and what
 // travels is float32 -- as long as every value survives the round trip double -> float -> double unchanged (model grids are
 // commonly written by NEMO in single precision and widened by the reader: half the bytes over PCIe, bit-identical values
-// after the widening kernel).  The first value that does not (or a NaN) raises g_bc_inexact and the caller repeats the
-// transfer in full precision.
+// after the widening kernel).  The first value that does not (or a NaN) raises the job's `inexact` flag (the caller's:
+// contexts may be created from several host threads) and the caller repeats the transfer in full precision.
 #define GZB_BC_NARROW 108
-std::atomic<int> g_bc_inexact{0};
 
 static bool narrow_into(float* out, const double* p, size_t n) {
     bool ok = true;
@@ -168,6 +167,7 @@ struct BcJob {
     size_t bytes;
     int pack;
     size_t min_bytes;      // below this the transfer is one plain copy (0 = GZB_BC_MIN)
+    std::atomic<int>* inexact;   // GZB_BC_NARROW only: raised when a value does not survive the narrowing, or when the job cannot be narrowed
 };
 
 // Thread t of `nth` moves its slice of every job, one after the other, through its two pinned slots: the slots keep
@@ -191,7 +191,7 @@ void bigcopy_part(int dev, int t, int nth, const BcJob* jobs, int njobs, bool h2
         const char* src = (J.pack > 1 && !narrow) ? J.src : J.src + a;      // packed sources are addressed by element (first_elem below)
         size_t off = 0;
         while (off < bytes && e == cudaSuccess) {
-            if (narrow && g_bc_inexact.load(std::memory_order_relaxed)) break;      // somebody found an inexact value: the transfer will be redone
+            if (narrow && J.inexact->load(std::memory_order_relaxed)) break;      // somebody found an inexact value: the transfer will be redone
             const size_t len = bytes - off < GZB_BC_SLOT ? bytes - off : GZB_BC_SLOT;
             if (used[k]) {                           // the slot's previous transfer must be over
                 e = cudaEventSynchronize(g_bc.ev[t][k]);
@@ -199,7 +199,7 @@ void bigcopy_part(int dev, int t, int nth, const BcJob* jobs, int njobs, bool h2
             }
             if (e != cudaSuccess) break;
             if (narrow) {
-                if (!narrow_into((float*)g_bc.slot[t][k], (const double*)(src + off), len / 8)) g_bc_inexact.store(1);
+                if (!narrow_into((float*)g_bc.slot[t][k], (const double*)(src + off), len / 8)) J.inexact->store(1);
                 e = cudaMemcpyAsync(dst + off / 2, g_bc.slot[t][k], len / 2, cudaMemcpyHostToDevice, g_bc.stream[t]);
             } else if (h2d) {
                 if (J.pack == 8) pack_into<int64_t>((int8_t*)g_bc.slot[t][k], src, a + off, len);
@@ -266,8 +266,8 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
         const BcJob& J = jobs_in[q];
         if (J.bytes == 0) continue;
         const void* host = h2d ? (const void*)J.src : (const void*)J.dst;
-        if (J.pack == GZB_BC_NARROW && (!h2d || bigcopy_plain(host, J.bytes, 0))) {
-            g_bc_inexact.store(1);      // not a threaded pageable upload: the caller takes the full-precision path
+        if (J.pack == GZB_BC_NARROW && (!h2d || !J.inexact || bigcopy_plain(host, J.bytes, 0))) {
+            if (J.inexact) J.inexact->store(1);      // not a threaded pageable upload: the caller takes the full-precision path
         } else if (bigcopy_plain(host, J.bytes, J.pack, J.min_bytes)) {
             const int rc = bigcopy_one_plain(ctx, J.dst, J.src, J.bytes, J.pack);
             if (rc != GZB_OK) return rc;
@@ -280,7 +280,7 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
     if (!bigcopy_ready(ctx->device)) {
         lk.unlock();
         for (int q = 0; q < njobs; ++q) {
-            if (jobs[q].pack == GZB_BC_NARROW) { g_bc_inexact.store(1); continue; }
+            if (jobs[q].pack == GZB_BC_NARROW) { jobs[q].inexact->store(1); continue; }
             const int rc = bigcopy_one_plain(ctx, jobs[q].dst, jobs[q].src, jobs[q].bytes, jobs[q].pack);
             if (rc != GZB_OK) return rc;
         }
@@ -314,7 +314,7 @@ int gzb_bigcopy_jobs(gzb_ctx* ctx, const BcJob* jobs_in, int njobs_in, bool h2d,
 int gzb_bigcopy(gzb_ctx* ctx, void* dst, const void* src, size_t bytes, bool h2d, bool sync_before = true, int pack = 0,
                 size_t min_bytes = 0) {
     if (bytes == 0) return GZB_OK;
-    const BcJob J = {(char*)dst, (const char*)src, bytes, pack, min_bytes};
+    const BcJob J = {(char*)dst, (const char*)src, bytes, pack, min_bytes, nullptr};
     return gzb_bigcopy_jobs(ctx, &J, 1, h2d, sync_before);
 }
 
@@ -1045,11 +1045,11 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
             bool narrowed = false;
             if (n * sizeof(double) >= GZB_BC_MIN && !getenv("GZB_NO_NARROW_UPLOAD")) {
                 float* st = (float*)ctx->d_ll;
-                const BcJob up32[2] = {{(char*)st, (const char*)lat, n * sizeof(double), GZB_BC_NARROW, 0},
-                                       {(char*)(st + n), (const char*)lon, n * sizeof(double), GZB_BC_NARROW, 0}};
-                g_bc_inexact.store(0);
+                std::atomic<int> inexact{0};
+                const BcJob up32[2] = {{(char*)st, (const char*)lat, n * sizeof(double), GZB_BC_NARROW, 0, &inexact},
+                                       {(char*)(st + n), (const char*)lon, n * sizeof(double), GZB_BC_NARROW, 0, &inexact}};
                 if ((rc = gzb_bigcopy_jobs(ctx, up32, 2, true, true)) != GZB_OK) break;
-                if (!g_bc_inexact.load()) {
+                if (!inexact.load()) {
                     k_widen2<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((int64_t)n, st, st + n, ctx->d_lat, ctx->d_lon);
                     ctx->stats.kernel_launches++;
                     ctx->stats.h2d_bytes += 2 * n * sizeof(float);
@@ -1058,7 +1058,8 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
                 }
             }
             if (!narrowed) {
-                const BcJob up[2] = {{(char*)ctx->d_lat, (const char*)lat, n * sizeof(double), 0, 0}, {(char*)ctx->d_lon, (const char*)lon, n * sizeof(double), 0, 0}};
+                const BcJob up[2] = {{(char*)ctx->d_lat, (const char*)lat, n * sizeof(double), 0, 0, nullptr},
+                                     {(char*)ctx->d_lon, (const char*)lon, n * sizeof(double), 0, 0, nullptr}};
                 if ((rc = gzb_bigcopy_jobs(ctx, up, 2, true, true)) != GZB_OK) break;
                 ctx->stats.h2d_bytes += 2 * n * sizeof(double);
                 cmark("lat, lon uploaded");
@@ -1100,11 +1101,11 @@ static int create_impl(int device, int64_t nj, int64_t ni, const double* lat, co
             BcJob up[2];
             int nup = 0;
             if (angle_or_null) {
-                up[nup++] = {(char*)ctx->d_angle, (const char*)angle_or_null, n * sizeof(double), 0, 0};
+                up[nup++] = {(char*)ctx->d_angle, (const char*)angle_or_null, n * sizeof(double), 0, 0, nullptr};
                 ctx->stats.h2d_bytes += n * sizeof(double);
             }
             if (mask_or_null) {
-                up[nup++] = {(char*)ctx->d_mask, (const char*)mask_or_null, n, mask_itemsize, 0};
+                up[nup++] = {(char*)ctx->d_mask, (const char*)mask_or_null, n, mask_itemsize, 0, nullptr};
                 ctx->stats.h2d_bytes += n;
             }
             if (nup && (rc = gzb_bigcopy_jobs(ctx, up, nup, true, false)) != GZB_OK) break;
