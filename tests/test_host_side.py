@@ -206,3 +206,22 @@ def test_integration_doc_matches_the_binding():
     assert len(found) >= 3
     for name, lst in found:
         assert [a for a in eval(lst, env)] == list(L._SIGNATURES[name][1]), name
+
+
+def test_every_option_is_documented_and_known_to_the_emulation():
+    """Every integer option gzb_set_option accepts (csrc/gzb_grid.cu) is described in the header's comment and accepted by
+    the CPU emulation of the C ABI (tests/emulib.py), so that host tests and documentation follow the library."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "gonzag_b200", "csrc", "gzb_grid.cu")).read()
+    body = src[src.index('extern "C" int gzb_set_option'):]
+    body = body[:body.index("\n}\n")]
+    names = sorted(set(re.findall(r'!strcmp\(name, "([a-z0-9_]+)"\)', body)))
+    assert len(names) >= 20, names
+    header = open(os.path.join(root, "include", "gonzag_b200.h")).read()
+    emu = open(os.path.join(root, "tests", "emulib.py")).read()
+    known = emu[emu.index("known = ("):]
+    known = known[:known.index(")")]
+    for n in names:
+        assert '"%s"' % n in header, "option %s is not described in include/gonzag_b200.h" % n
+        assert '"%s"' % n in known, "option %s is not accepted by tests/emulib.py" % n
